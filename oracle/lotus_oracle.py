@@ -1,0 +1,583 @@
+"""CPU oracle: a restatement of the 3D-LOTUS policy hot path.
+
+TEST INFRASTRUCTURE.  Only `tests/`, `__graft_entry__.smoke()` and `bench.py`'s `cpu_baseline` /
+`--impl reference` legs may import this file; the product (`robot-3dlotus_b200/`) never does and fails
+loudly when its CUDA library is missing.
+
+Parity status: PINNED.  The reference ships no golden vectors, so this restatement is pinned
+against outputs of the reference's own, unmodified Python code imported in the build container
+(`oracle/ref_import.py` + `oracle/make_golden.py` -> `tests/golden/*.pt`); `tests/test_oracle_golden.py`
+checks every function below against those fixtures (bit-exact for integer outputs, 1e-5 for fp32).
+
+Integer work is numpy/torch int64; float work is torch fp32 on CPU (autograd supplies the backward).
+Attention follows the reference's *flash* branch semantics in fp32 (SURVEY finding 5 / Appendix D.1).
+All paths in the citations are relative to /root/reference/genrobo3d/.
+"""
+import math
+
+import numpy as np
+import torch
+import torch.nn.functional as F
+
+# --------------------------------------------------------------------------------------------------
+# §8a rows 1-2: batch ids, grid coordinates, space-filling-curve codes, orders
+# --------------------------------------------------------------------------------------------------
+
+
+def offset2bincount(offset):
+    """models/PointTransformerV3/model.py:30-34"""
+    return torch.diff(offset, prepend=offset.new_zeros(1))
+
+
+def offset2batch(offset):
+    """models/PointTransformerV3/model.py:37-42"""
+    cnt = offset2bincount(offset)
+    return torch.repeat_interleave(torch.arange(len(cnt), dtype=torch.long), cnt)
+
+
+def grid_coords(coord, grid_size=0.01):
+    """model.py:96-98 — min over the WHOLE packed batch, fp32 divide, truncate."""
+    return torch.div(coord - coord.min(0)[0], grid_size, rounding_mode="trunc").int()
+
+
+def serialized_depth(grid):
+    """model.py:102"""
+    return int(grid.max()).bit_length()
+
+
+def z_order_code(x, y, z, depth):
+    """serialization/z_order.py:40-50,66-101 — bit i of x -> 3i+2, y -> 3i+1, z -> 3i.
+    (The reference uses 8-bit LUTs; the result is the plain bit interleave.)"""
+    x, y, z = (np.asarray(v).astype(np.int64) for v in (x, y, z))
+    key = np.zeros_like(x)
+    for i in range(depth):
+        key |= ((x >> i) & 1) << (3 * i + 2)
+        key |= ((y >> i) & 1) << (3 * i + 1)
+        key |= ((z >> i) & 1) << (3 * i)
+    return key
+
+
+def hilbert_code(x, y, z, depth):
+    """serialization/hilbert.py:91-198 — Skilling's transform, MSB-first plane loop, then the bits of
+    (X0,X1,X2) interleaved MSB-first and Gray->binary over the whole 3*depth-bit string."""
+    X = [np.asarray(v).astype(np.int64).copy() for v in (x, y, z)]
+    for bit in range(depth):                      # bit 0 == most significant plane
+        q = np.int64(1) << (depth - 1 - bit)
+        low = q - 1                               # planes below this one
+        for d in range(3):
+            on = (X[d] & q) != 0
+            # plane set: invert the low planes of axis 0; plane clear: swap low planes of axis 0 and d
+            t = np.where(on, 0, (X[0] ^ X[d]) & low)
+            X[0] = np.where(on, X[0] ^ low, X[0] ^ t)
+            X[d] = X[d] ^ t if d != 0 else X[0]
+    g = np.zeros_like(X[0])
+    for i in range(depth):                        # interleave: plane i of X0,X1,X2 -> bits 3i+2,3i+1,3i
+        g |= ((X[0] >> i) & 1) << (3 * i + 2)
+        g |= ((X[1] >> i) & 1) << (3 * i + 1)
+        g |= ((X[2] >> i) & 1) << (3 * i)
+    h = g.copy()                                  # Gray -> binary (prefix xor from the MSB)
+    s = 1
+    while s < 3 * depth:
+        h ^= h >> s
+        s <<= 1
+    return h
+
+
+def encode(grid, batch, depth, order):
+    """serialization/default.py:10-27"""
+    g = grid.numpy().astype(np.int64)
+    if order in ("z-trans", "hilbert-trans"):
+        g = g[:, [1, 0, 2]]
+    fn = z_order_code if order.startswith("z") else hilbert_code
+    code = fn(g[:, 0], g[:, 1], g[:, 2], depth)
+    code = (batch.numpy().astype(np.int64) << (3 * depth)) | code
+    return torch.from_numpy(code)
+
+
+def order_and_inverse(code):
+    """model.py:121-128"""
+    order = torch.argsort(code, dim=1, stable=True)
+    inverse = torch.zeros_like(order)
+    ar = torch.arange(code.shape[1]).repeat(code.shape[0], 1)
+    inverse.scatter_(1, order, ar)
+    return order, inverse
+
+
+def serialize(grid, batch, orders=("z", "z-trans", "hilbert", "hilbert-trans"), perm=None):
+    """model.py:83-138; `perm` is the recorded `torch.randperm(len(orders))` of shuffle_orders."""
+    depth = serialized_depth(grid)
+    assert depth * 3 + int(batch.max() + 1).bit_length() <= 63 and depth <= 16
+    code = torch.stack([encode(grid, batch, depth, o) for o in orders])
+    order, inverse = order_and_inverse(code)
+    if perm is not None:
+        code, order, inverse = code[perm], order[perm], inverse[perm]
+    return dict(code=code, order=order, inverse=inverse, depth=depth)
+
+
+# --------------------------------------------------------------------------------------------------
+# §8a row 6: patch plan
+# --------------------------------------------------------------------------------------------------
+
+
+def patch_plan(offset, K=128):
+    """model.py:410-466.  pad: padded slot -> sorted position; unpad: sorted position ->
+    padded slot; cu_seqlens: int32 sequence starts + total."""
+    counts = offset2bincount(offset).tolist()
+    pad, unpad, cu = [], [], []
+    start, start_pad = 0, 0
+    for c in counts:
+        if c > K:
+            c_pad = (c + K - 1) // K * K
+        else:
+            c_pad = c
+        p = np.arange(c_pad, dtype=np.int64)
+        if c_pad != c:
+            r = c % K
+            # the tail of the last patch re-uses the same slots of the previous patch
+            p[c_pad - K + r:] = p[c_pad - 2 * K + r: c_pad - K]
+        pad.append(p + start)
+        unpad.append(np.arange(c, dtype=np.int64) + start_pad)
+        cu.append(np.arange(start_pad, start_pad + c_pad, K, dtype=np.int32) if c_pad > 0 else np.zeros(0, np.int32))
+        start += c
+        start_pad += c_pad
+    cu.append(np.array([start_pad], dtype=np.int32))
+    return (torch.from_numpy(np.concatenate(pad)), torch.from_numpy(np.concatenate(unpad)),
+            torch.from_numpy(np.concatenate(cu)))
+
+
+# --------------------------------------------------------------------------------------------------
+# §8a rows 3-4: sparsify + submanifold conv (third-party spconv 2.3.6 semantics, restated)
+# --------------------------------------------------------------------------------------------------
+
+
+def neighbor_table(batch, grid, k):
+    """nbr[p, d] = index of the occupied voxel at grid[p] + (d0,d1,d2) - k//2 of the same cloud, else -1;
+    d = (d0*k + d1)*k + d2 with d0 along x (column order of the spconv indices, model.py:169-171)."""
+    r = k // 2
+    b = batch.long()
+    c = grid.long() + r
+    dims = c.max(0).values + r + 1
+
+    def lin(cc):
+        return ((b * dims[0] + cc[:, 0]) * dims[1] + cc[:, 1]) * dims[2] + cc[:, 2]
+
+    skey, sidx = torch.sort(lin(c))
+    n = c.shape[0]
+    nbr = torch.full((n, k ** 3), -1, dtype=torch.long)
+    d = 0
+    for d0 in range(k):
+        for d1 in range(k):
+            for d2 in range(k):
+                qk = lin(c + torch.tensor([d0 - r, d1 - r, d2 - r]))
+                pos = torch.searchsorted(skey, qk).clamp(max=n - 1)
+                nbr[:, d] = torch.where(skey[pos] == qk, sidx[pos], torch.full_like(pos, -1))
+                d += 1
+    return nbr
+
+
+def subm_conv(feat, nbr, weight, bias=None):
+    """out[p] = sum_d W[:, d, :] @ feat[nbr[p, d]]  (+ bias); weight [Cout, k, k, k, Cin] (model.py:616-622, 845-852)."""
+    cout, cin = weight.shape[0], weight.shape[-1]
+    w = weight.reshape(cout, -1, cin)
+    out = feat.new_zeros(feat.shape[0], cout)
+    for d in range(w.shape[1]):
+        q = nbr[:, d]
+        m = (q >= 0).nonzero()[:, 0]
+        if m.numel():
+            out = out.index_add(0, m, feat[q[m]] @ w[:, d].t())
+    return out if bias is None else out + bias
+
+
+# --------------------------------------------------------------------------------------------------
+# norms / activations
+# --------------------------------------------------------------------------------------------------
+
+
+def batch_norm(x, w, b, rm, rv, train, eps=1e-3, momentum=0.01):
+    """nn.BatchNorm1d(eps=1e-3, momentum=0.01) (model.py:932).  Returns y and the updated (rm, rv)."""
+    if train:
+        mean = x.mean(0)
+        var = x.var(0, unbiased=False)
+        n = x.shape[0]
+        new_rm = (1 - momentum) * rm + momentum * mean.detach()
+        new_rv = (1 - momentum) * rv + momentum * var.detach() * n / max(n - 1, 1)
+    else:
+        mean, var, new_rm, new_rv = rm, rv, rm, rv
+    return (x - mean) / torch.sqrt(var + eps) * w + b, new_rm, new_rv
+
+
+def layer_norm(x, w, b, eps=1e-5):
+    return F.layer_norm(x, (x.shape[-1],), w, b, eps)
+
+
+# --------------------------------------------------------------------------------------------------
+# §8a rows 7-9: patch self-attention, RPE, cross-attention
+# --------------------------------------------------------------------------------------------------
+
+
+def _varlen_attention(q, k, v, cu_q, cu_k, scale, bias=None):
+    """softmax(q k^T * scale [+ bias]) v per (cu_q[i]:cu_q[i+1]) x (cu_k[i]:cu_k[i+1]) segment; q (Nq,H,D)."""
+    out = torch.empty_like(q)
+    lens = {}
+    for i in range(len(cu_q) - 1):
+        lens.setdefault((cu_q[i + 1] - cu_q[i], cu_k[i + 1] - cu_k[i]), []).append(i)
+    pieces, index = [], []
+    for (lq, lk), ids in lens.items():
+        if lq == 0:
+            continue
+        iq = torch.tensor([cu_q[i] for i in ids])[:, None] + torch.arange(lq)[None]
+        ik = torch.tensor([cu_k[i] for i in ids])[:, None] + torch.arange(lk)[None]
+        s = torch.einsum("bqhd,bkhd->bhqk", q[iq], k[ik]) * scale
+        if bias is not None:
+            s = s + bias[torch.tensor(ids)]
+        p = torch.softmax(s, dim=-1)
+        pieces.append(torch.einsum("bhqk,bkhd->bqhd", p, v[ik]).reshape(-1, q.shape[1], q.shape[2]))
+        index.append(iq.reshape(-1))
+    index = torch.cat(index)
+    inv = torch.empty_like(index)
+    inv[index] = torch.arange(index.numel())
+    return torch.cat(pieces)[inv]
+
+
+def rpe_bias(table, rel, pos_bnd):
+    """model.py:307-326: bias[n,h,i,j] = sum_axis table[clamp(rel)+bnd+axis*(2bnd+1), h]."""
+    num = 2 * pos_bnd + 1
+    idx = rel.clamp(-pos_bnd, pos_bnd) + pos_bnd + torch.arange(3) * num
+    return table[idx.reshape(-1)].view(idx.shape + (-1,)).sum(3).permute(0, 3, 1, 2)
+
+
+def patch_attention(x, P, pre, H, order, inverse, plan, K=128, qk_norm=True, rpe_table=None, grid=None):
+    """SerializedAttention.forward, flash branch semantics in fp32 (model.py:468-557).
+    x is the *normed* input; returns proj(attn) (dropout 0)."""
+    pad, unpad, cu = plan
+    C = x.shape[1]
+    D = C // H
+    o = order[pad]
+    inv = unpad[inverse]
+    qkv = F.linear(x, P[pre + "qkv.weight"], P.get(pre + "qkv.bias"))[o].reshape(-1, 3, H, D)
+    q, k, v = qkv.unbind(1)
+    if qk_norm:
+        q = layer_norm(q, P[pre + "q_norm.weight"], P[pre + "q_norm.bias"], 1e-6)
+        k = layer_norm(k, P[pre + "k_norm.weight"], P[pre + "k_norm.bias"], 1e-6)
+    cul = cu.tolist()
+    bias = None
+    if rpe_table is not None:
+        # only defined when every sequence is a full K patch (model.py:400-408 reshape(-1, K, 3))
+        g = grid[o].reshape(-1, K, 3).long()
+        pos_bnd = int((4 * K) ** (1 / 3) * 2)
+        bias = rpe_bias(rpe_table, g.unsqueeze(2) - g.unsqueeze(1), pos_bnd)
+    a = _varlen_attention(q, k, v, cul, cul, D ** -0.5, bias)
+    a = a.reshape(-1, C)[inv]
+    return F.linear(a, P[pre + "proj.weight"], P[pre + "proj.bias"])
+
+
+def cross_attention(x, ctx, P, pre, H, offset, ctx_offset, qk_norm=True):
+    """CrossAttention.forward (model_ca.py:46-101), flash branch semantics in fp32."""
+    C = x.shape[1]
+    D = C // H
+    q = F.linear(x, P[pre + "q.weight"], P[pre + "q.bias"]).view(-1, H, D)
+    kv = F.linear(ctx, P[pre + "kv.weight"], P[pre + "kv.bias"]).view(-1, 2, H, D)
+    k, v = kv[:, 0], kv[:, 1]
+    if qk_norm:
+        q = layer_norm(q, P[pre + "q_norm.weight"], P[pre + "q_norm.bias"], 1e-6)
+        k = layer_norm(k, P[pre + "k_norm.weight"], P[pre + "k_norm.bias"], 1e-6)
+    cq = [0] + offset.tolist()
+    ck = [0] + ctx_offset.tolist()
+    a = _varlen_attention(q, k, v, cq, ck, D ** -0.5).reshape(-1, C)
+    return F.linear(a, P[pre + "proj.weight"], P[pre + "proj.bias"])
+
+
+def mlp(x, P, pre):
+    """model.py:560-583 (dropout 0)"""
+    h = F.gelu(F.linear(x, P[pre + "fc1.weight"], P[pre + "fc1.bias"]))
+    return F.linear(h, P[pre + "fc2.weight"], P[pre + "fc2.bias"])
+
+
+def block(pt, P, pre, H, order_index, K=128, qk_norm=True):
+    """Block.forward (model.py:659-680), pre-norm, drop_path 0.
+
+    The CPE conv reads `point.sparse_conv_feat.features` (model.py:235-238), which after a
+    SerializedUnpooling is the *skip branch only*: `parent.feat = parent.feat + point.feat[inverse]`
+    (model.py:824) updates `feat` but not `sparse_conv_feat`.  `pt["conv_feat"]` carries that tensor."""
+    x = pt["feat"]
+    c = subm_conv(pt.pop("conv_feat", x), pt["nbr3"], P[pre + "cpe.0.weight"], P[pre + "cpe.0.bias"])
+    c = F.linear(c, P[pre + "cpe.1.weight"], P[pre + "cpe.1.bias"])
+    x = x + layer_norm(c, P[pre + "cpe.2.weight"], P[pre + "cpe.2.bias"])
+    h = layer_norm(x, P[pre + "norm1.0.weight"], P[pre + "norm1.0.bias"])
+    x = x + patch_attention(h, P, pre + "attn.", H, pt["order"][order_index], pt["inverse"][order_index],
+                            pt["plan"], K, qk_norm)
+    h = layer_norm(x, P[pre + "norm2.0.weight"], P[pre + "norm2.0.bias"])
+    x = x + mlp(h, P, pre + "mlp.0.")
+    pt["feat"] = x
+    return pt
+
+
+def ca_block(pt, P, pre, H, qk_norm=True):
+    """CABlock.forward (model_ca.py:135-152)."""
+    x = pt["feat"]
+    h = layer_norm(x, P[pre + "norm1.0.weight"], P[pre + "norm1.0.bias"])
+    x = x + cross_attention(h, pt["context"], P, pre + "attn.", H, pt["offset"], pt["context_offset"], qk_norm)
+    h = layer_norm(x, P[pre + "norm2.0.weight"], P[pre + "norm2.0.bias"])
+    x = x + mlp(h, P, pre + "mlp.0.")
+    pt["feat"] = x
+    return pt
+
+
+# --------------------------------------------------------------------------------------------------
+# §8a rows 10-11: grid pooling / unpooling
+# --------------------------------------------------------------------------------------------------
+
+
+def pool_structure(pt, perm=None, stride=2):
+    """The integer half of SerializedPooling.forward (model.py:713-755, 766-771)."""
+    pooling_depth = (math.ceil(stride) - 1).bit_length()
+    if pooling_depth > pt["depth"]:
+        pooling_depth = 0
+    code = pt["code"] >> (pooling_depth * 3)
+    _, cluster, counts = torch.unique(code[0], sorted=True, return_inverse=True, return_counts=True)
+    indices = torch.sort(cluster, stable=True)[1]
+    idx_ptr = torch.cat([counts.new_zeros(1), torch.cumsum(counts, 0)])
+    head = indices[idx_ptr[:-1]]
+    code = code[:, head]
+    order, inverse = order_and_inverse(code)
+    if perm is not None:
+        code, order, inverse = code[perm], order[perm], inverse[perm]
+    batch = pt["batch"][head]
+    return dict(cluster=cluster, indices=indices, idx_ptr=idx_ptr, head=head, code=code, order=order,
+                inverse=inverse, depth=pt["depth"] - pooling_depth, grid=pt["grid"][head] >> pooling_depth,
+                batch=batch, offset=torch.cumsum(torch.bincount(batch), 0))
+
+
+def segment_max(x, idx_ptr):
+    return torch.segment_reduce(x, "max", offsets=idx_ptr, axis=0)
+
+
+def segment_mean(x, idx_ptr):
+    return torch.segment_reduce(x, "mean", offsets=idx_ptr, axis=0)
+
+
+# --------------------------------------------------------------------------------------------------
+# §8a rows 14-18: backbone, context, head, loss, decode
+# --------------------------------------------------------------------------------------------------
+
+
+def _stage_aux(pt, K):
+    pt["nbr3"] = neighbor_table(pt["batch"], pt["grid"], 3)
+    pt["plan"] = patch_plan(pt["offset"], K)
+    return pt
+
+
+def ptv3ca_forward(P, cfg, feat, coord, offset, context, context_offset, perms, train, bn_out=None, inter=None):
+    """PointTransformerV3CA.forward(return_dec_layers=True) (model_ca.py:383-412).
+    P: state dict with the `ptv3_model.` prefix stripped.  perms: list of 5 recorded randperm(4) (or None)."""
+    pre = ""
+    S = len(cfg["enc_channels"])
+    qk_norm = cfg["qk_norm"]
+    assert not cfg.get("pdnorm_bn") and not cfg.get("pdnorm_ln"), "oracle covers the plain BN/LN (CA) model"
+    batch = offset2batch(offset)
+    grid = grid_coords(coord, 0.01)
+    ser = serialize(grid, batch, cfg["order"], perms[0] if perms is not None else None)
+    pt = dict(feat=feat, coord=coord, grid=grid, batch=batch, offset=offset, context=context,
+              context_offset=context_offset, **ser)
+    K = cfg["enc_patch_size"][0]
+    _stage_aux(pt, K)
+
+    def bn(x, name):
+        y, rm, rv = batch_norm(x, P[name + ".weight"], P[name + ".bias"], P[name + ".running_mean"],
+                               P[name + ".running_var"], train)
+        if bn_out is not None and train:
+            bn_out[name + ".running_mean"], bn_out[name + ".running_var"] = rm, rv
+        return y
+
+    def rec(name, p):
+        if inter is not None:
+            inter[name] = p["feat"]
+
+    # stem (model.py:831-861)
+    nbr5 = neighbor_table(batch, grid, 5)
+    x = subm_conv(feat, nbr5, P["embedding.stem.conv.weight"], None)
+    pt["feat"] = F.gelu(bn(x, "embedding.stem.norm"))
+    rec("embedding", pt)
+    stack = []
+    for s in range(S):
+        if s > 0:
+            parent = pt
+            st = pool_structure(parent, perms[s] if perms is not None else None, cfg["stride"][s - 1])
+            pn = f"enc.enc{s}.down."
+            proj = F.linear(parent["feat"], P[pn + "proj.weight"], P[pn + "proj.bias"])
+            f = segment_max(proj[st["indices"]], st["idx_ptr"])
+            c = segment_mean(parent["coord"][st["indices"]], st["idx_ptr"])
+            f = F.gelu(bn(f, pn + "norm.0"))
+            stack.append((parent, st["cluster"]))
+            pt = dict(feat=f, coord=c, grid=st["grid"], batch=st["batch"], offset=st["offset"],
+                      context=context, context_offset=context_offset, code=st["code"], order=st["order"],
+                      inverse=st["inverse"], depth=st["depth"])
+            _stage_aux(pt, cfg["enc_patch_size"][s])
+            rec(f"enc{s}.down", pt)
+        for i in range(cfg["enc_depths"][s]):
+            pt = block(pt, P, f"enc.enc{s}.block{i}.", cfg["enc_num_head"][s], i % len(cfg["order"]),
+                       cfg["enc_patch_size"][s], qk_norm)
+            rec(f"enc{s}.block{i}", pt)
+            pt = ca_block(pt, P, f"enc.enc{s}.ca_block{i}.", cfg["enc_num_head"][s], qk_norm)
+            rec(f"enc{s}.ca_block{i}", pt)
+    outs = [pt]
+    for s in reversed(range(S - 1)):
+        parent, cluster = stack.pop()
+        un = f"dec.dec{s}.up."
+        a = F.gelu(bn(F.linear(pt["feat"], P[un + "proj.0.weight"], P[un + "proj.0.bias"]), un + "proj.1"))
+        b = F.gelu(bn(F.linear(parent["feat"], P[un + "proj_skip.0.weight"], P[un + "proj_skip.0.bias"]),
+                      un + "proj_skip.1"))
+        parent = dict(parent)
+        parent["feat"] = b + a[cluster]
+        parent["conv_feat"] = b            # sparse_conv_feat is NOT refreshed by the add (model.py:824)
+        pt = parent
+        rec(f"dec{s}.up", pt)
+        for i in range(cfg["dec_depths"][s]):
+            pt = block(pt, P, f"dec.dec{s}.block{i}.", cfg["dec_num_head"][s], i % len(cfg["order"]),
+                       cfg["dec_patch_size"][s], qk_norm)
+            rec(f"dec{s}.block{i}", pt)
+            pt = ca_block(pt, P, f"dec.dec{s}.ca_block{i}.", cfg["dec_num_head"][s], qk_norm)
+            rec(f"dec{s}.ca_block{i}", pt)
+            outs.append(pt)
+    return outs
+
+
+def action_head(x, P, npoints, pos_bins=15, euler_bins=72):
+    """ActionHead.forward, heatmap_disc + max + euler_disc (simple_policy_ptv3.py:70-157), dropout 0."""
+    pre = "act_proj_head."
+    h = F.leaky_relu(F.linear(x, P[pre + "heatmap_mlp.0.weight"], P[pre + "heatmap_mlp.0.bias"]), 0.02)
+    xt = F.linear(h, P[pre + "heatmap_mlp.3.weight"], P[pre + "heatmap_mlp.3.bias"])
+    xt = xt.view(x.shape[0], 3, 2 * pos_bins).permute(1, 0, 2)               # 'n (c b) -> c n b'
+    pc = torch.stack([t.max(0)[0] for t in torch.split(x, npoints)], 0)
+    h = F.leaky_relu(F.linear(pc, P[pre + "action_mlp.0.weight"], P[pre + "action_mlp.0.bias"]), 0.02)
+    a = F.linear(h, P[pre + "action_mlp.3.weight"], P[pre + "action_mlp.3.bias"])
+    xr = a[..., : euler_bins * 3].reshape(-1, euler_bins, 3)
+    xo = a[..., -1]
+    return xt, xr, xo
+
+
+def policy_loss(xt, xr, xo, gt_actions, disc_pos_probs, npoints, pos_weight=1.0, rot_weight=1.0):
+    """compute_loss (simple_policy_ptv3.py:308-373), heatmap_disc + euler_disc."""
+    pos = 0
+    for i, t in enumerate(torch.split(xt, npoints, dim=1)):
+        pos = pos + F.cross_entropy(t.reshape(3, -1), disc_pos_probs[i], reduction="mean")
+    pos = pos / len(npoints)
+    rot = F.cross_entropy(xr, gt_actions[..., 3:-1].long(), reduction="mean")
+    opn = F.binary_cross_entropy_with_logits(xo, gt_actions[..., -1], reduction="mean")
+    return {"pos": pos, "rot": rot, "open": opn, "total": pos_weight * pos + rot_weight * rot + opn}
+
+
+def euler_bins_to_quat(bins, resolution=5):
+    """utils/rotation_transform.py:192-193: extrinsic 'xyz' euler (deg) -> quaternion xyzw, closed form
+    (scipy: q = qz * qy * qx), canonicalised like scipy >= 1.? does NOT canonicalise sign; we match scipy."""
+    e = np.deg2rad(np.asarray(bins, dtype=np.float64) * resolution - 180.0)
+    cx, sx = np.cos(e[..., 0] / 2), np.sin(e[..., 0] / 2)
+    cy, sy = np.cos(e[..., 1] / 2), np.sin(e[..., 1] / 2)
+    cz, sz = np.cos(e[..., 2] / 2), np.sin(e[..., 2] / 2)
+    x = sx * cy * cz - cx * sy * sz
+    y = cx * sy * cz + sx * cy * sz
+    z = cx * cy * sz - sx * sy * cz
+    w = cx * cy * cz + sx * sy * sz
+    return np.stack([x, y, z, w], -1)
+
+
+def best_pos_from_logits(xt, coord, npoints, pos_bins=15, pos_bin_size=0.01):
+    """final-action position decode (simple_policy_ptv3.py:250-275; utils/action_position_utils.py:48-60,
+    best='max'): argmax over (n_i * 2*pos_bins) per axis of the per-cloud softmax -> xyz[n,c] + (b-pos_bins)*size."""
+    outs = []
+    shift = np.arange(-pos_bins, pos_bins) * pos_bin_size
+    for t, c in zip(torch.split(xt, npoints, dim=1), torch.split(coord, npoints)):
+        prob = torch.softmax(t.reshape(3, -1), dim=-1).numpy()
+        idx = prob.argmax(-1)
+        xyz = c.numpy()
+        cands = xyz[:, :, None] + shift[None, None, :]                         # float64 via numpy promotion
+        cands = np.transpose(cands, (1, 0, 2)).reshape(3, -1)
+        outs.append(cands[np.arange(3), idx])
+    return torch.from_numpy(np.array(outs)).float()
+
+
+def policy_forward(sd, cfg, batch, perms=None, train=True, compute_loss=True, compute_final_action=False,
+                   bn_out=None, inter=None):
+    """SimplePolicyPTV3CA.forward (simple_policy_ptv3.py:225-306, 403-431).
+    sd: state dict (reference names); cfg: MODEL config mapping; perms: (5,4) recorded shuffles or None."""
+    pc, ac = cfg["ptv3_config"], cfg["action_config"]
+    assert not ac["use_ee_pose"] and not ac["use_step_id"], "oracle covers the production CA context (text only)"
+    fts = batch["pc_fts"]
+    npoints = list(batch["npoints_in_batch"])
+    ctx = F.linear(batch["txt_embeds"], sd["txt_fc.weight"], sd["txt_fc.bias"])
+    ctx_off = torch.cumsum(torch.tensor(batch["txt_lens"], dtype=torch.long), 0)
+    P = {k[len("ptv3_model."):]: v for k, v in sd.items() if k.startswith("ptv3_model.")}
+    bn_local = {} if bn_out is not None else None
+    outs = ptv3ca_forward(P, pc, fts, fts[:, :3], batch["offset"], ctx, ctx_off, perms, train, bn_local, inter)
+    if bn_out is not None:
+        bn_out.update({"ptv3_model." + k: v for k, v in bn_local.items()})
+    last = outs[-1]
+    xt, xr, xo = action_head(last["feat"], sd, npoints, ac["pos_bins"], 72)
+    if compute_final_action:
+        pos = best_pos_from_logits(xt.detach(), last["coord"], npoints, ac["pos_bins"], ac["pos_bin_size"])
+    else:
+        pos = batch["gt_actions"][..., :3]
+    rot = torch.from_numpy(euler_bins_to_quat(torch.argmax(xr, 1).numpy(), 5))
+    final = torch.cat([pos, rot, xo.detach().unsqueeze(-1)], -1)
+    res = {"final": final, "xt": xt, "xr": xr, "xo": xo, "dec_feat": last["feat"]}
+    if compute_loss:
+        lc = cfg["loss_config"]
+        res["losses"] = policy_loss(xt, xr, xo, batch["gt_actions"], batch["disc_pos_probs"], npoints,
+                                    lc["pos_weight"], lc["rot_weight"])
+    return res
+
+
+# --------------------------------------------------------------------------------------------------
+# §8a rows 12-13: FPS (reference helper) and kNN / ball query (no reference function; brute force)
+# --------------------------------------------------------------------------------------------------
+
+
+def farthest_point_sample_indices(xyz, npoint, start):
+    """train/datasets/common.py:108-129 with the random start made explicit.  xyz (N,3) float32; the
+    reference computes in the array's dtype: dist = sum((xyz - c)**2, -1) in x,y,z order; argmax -> lowest index."""
+    xyz = np.asarray(xyz)[:, :3]
+    n = xyz.shape[0]
+    idx = np.zeros(npoint, dtype=np.int64)
+    distance = np.full(n, 1e10, dtype=np.float64)
+    far = int(start)
+    for i in range(npoint):
+        idx[i] = far
+        d = np.sum((xyz - xyz[far]) ** 2, -1)
+        m = d < distance
+        distance[m] = d[m]
+        far = int(np.argmax(distance))
+    return idx
+
+
+def knn_indices(query, ref, k, q_offset=None, r_offset=None):
+    """brute-force kNN (squared L2 in fp32, x,y,z summation order), ties -> lowest index; per cloud."""
+    def one(q, r):
+        d = ((q[:, None, 0] - r[None, :, 0]) ** 2 + (q[:, None, 1] - r[None, :, 1]) ** 2) + (q[:, None, 2] - r[None, :, 2]) ** 2
+        order = np.argsort(d, axis=1, kind="stable")[:, :k]
+        return order, np.take_along_axis(d, order, 1)
+    q, r = np.asarray(query, np.float32), np.asarray(ref, np.float32)
+    if q_offset is None:
+        return one(q, r)
+    idx, dist = [], []
+    qs = rs = 0
+    for qe, re in zip(q_offset, r_offset):
+        i, d = one(q[qs:qe], r[rs:re])
+        idx.append(i + rs)
+        dist.append(d)
+        qs, rs = qe, re
+    return np.concatenate(idx), np.concatenate(dist)
+
+
+def ball_query_indices(query, ref, radius, nsample):
+    """first `nsample` reference indices (ascending index) within `radius`; missing slots repeat the first hit
+    (pointnet2 convention), -1 if none."""
+    q, r = np.asarray(query, np.float32), np.asarray(ref, np.float32)
+    d = ((q[:, None, 0] - r[None, :, 0]) ** 2 + (q[:, None, 1] - r[None, :, 1]) ** 2) + (q[:, None, 2] - r[None, :, 2]) ** 2
+    out = np.full((q.shape[0], nsample), -1, dtype=np.int64)
+    r2 = np.float32(radius) * np.float32(radius)
+    for i in range(q.shape[0]):
+        hit = np.nonzero(d[i] < r2)[0][:nsample]
+        if hit.size:
+            out[i, :] = hit[0]
+            out[i, : hit.size] = hit
+    return out
