@@ -1,0 +1,106 @@
+// Shared helpers for the lotus sm_100a kernels.
+#pragma once
+#include <cuda_runtime.h>
+#include <cuda_bf16.h>
+#include <stdint.h>
+#include <stdio.h>
+#include <string.h>
+
+#define LOTUS_API extern "C" __attribute__((visibility("default")))
+
+// ---- error channel (thread-local message, retrievable via lotus_last_error()) ----
+void lotus_set_error(const char* fmt, ...);
+
+#define LOTUS_CHECK_ARG(cond, ...)            \
+  do {                                        \
+    if (!(cond)) {                            \
+      lotus_set_error(__VA_ARGS__);           \
+      return 2;                               \
+    }                                         \
+  } while (0)
+
+#define LOTUS_CUDA_OK()                                                          \
+  do {                                                                           \
+    cudaError_t _e = cudaGetLastError();                                         \
+    if (_e != cudaSuccess) {                                                     \
+      lotus_set_error("%s:%d CUDA error: %s", __FILE__, __LINE__, cudaGetErrorString(_e)); \
+      return 1;                                                                  \
+    }                                                                            \
+  } while (0)
+
+#define LOTUS_CUDA_CALL(x)                                                       \
+  do {                                                                           \
+    cudaError_t _e = (x);                                                        \
+    if (_e != cudaSuccess) {                                                     \
+      lotus_set_error("%s:%d CUDA error: %s", __FILE__, __LINE__, cudaGetErrorString(_e)); \
+      return 1;                                                                  \
+    }                                                                            \
+  } while (0)
+
+static inline int ceil_div(int64_t a, int64_t b) { return (int)((a + b - 1) / b); }
+static const int kNumSM = 148;  // B200
+
+// ---- device helpers ----
+__device__ __forceinline__ float warp_sum(float v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  return v;
+}
+__device__ __forceinline__ float warp_max(float v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v = fmaxf(v, __shfl_xor_sync(0xffffffffu, v, o));
+  return v;
+}
+__device__ __forceinline__ int warp_sum_i(int v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  return v;
+}
+
+// block-wide sum; `red` must hold >= 32 floats. All threads get the result.
+__device__ __forceinline__ float block_sum(float v, float* red) {
+  int lane = threadIdx.x & 31, w = threadIdx.x >> 5, nw = (blockDim.x + 31) >> 5;
+  v = warp_sum(v);
+  __syncthreads();
+  if (lane == 0) red[w] = v;
+  __syncthreads();
+  float r = (threadIdx.x < nw) ? red[threadIdx.x] : 0.f;
+  if (w == 0) {
+    r = warp_sum(r);
+    if (lane == 0) red[0] = r;
+  }
+  __syncthreads();
+  return red[0];
+}
+__device__ __forceinline__ float block_max(float v, float* red) {
+  int lane = threadIdx.x & 31, w = threadIdx.x >> 5, nw = (blockDim.x + 31) >> 5;
+  v = warp_max(v);
+  __syncthreads();
+  if (lane == 0) red[w] = v;
+  __syncthreads();
+  float r = (threadIdx.x < nw) ? red[threadIdx.x] : -INFINITY;
+  if (w == 0) {
+    r = warp_max(r);
+    if (lane == 0) red[0] = r;
+  }
+  __syncthreads();
+  return red[0];
+}
+
+__device__ __forceinline__ float gelu_f(float x) { return 0.5f * x * (1.f + erff(x * 0.70710678118654752440f)); }
+__device__ __forceinline__ float gelu_grad_f(float x) {
+  float cdf = 0.5f * (1.f + erff(x * 0.70710678118654752440f));
+  float pdf = 0.39894228040143267794f * expf(-0.5f * x * x);
+  return cdf + x * pdf;
+}
+
+// counter-based RNG for dropout masks: one 32-bit hash per element (seed, stream id, index) -> uniform [0,1)
+__device__ __forceinline__ uint32_t lotus_hash3(uint32_t a, uint32_t b, uint32_t c) {
+  uint32_t h = a * 0x9E3779B1u ^ (b + 0x7F4A7C15u) * 0x85EBCA77u ^ (c + 0x165667B1u) * 0xC2B2AE3Du;
+  h ^= h >> 16; h *= 0x7FEB352Du; h ^= h >> 15; h *= 0x846CA68Bu; h ^= h >> 16;
+  return h;
+}
+__device__ __forceinline__ bool dropout_keep(uint64_t seed, uint32_t idx_hi, uint32_t idx_lo, float p) {
+  uint32_t h = lotus_hash3((uint32_t)seed ^ idx_hi * 0x27D4EB2Fu, (uint32_t)(seed >> 32), idx_lo);
+  return (h >> 8) * (1.0f / 16777216.0f) >= p;
+}

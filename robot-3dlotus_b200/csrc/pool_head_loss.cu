@@ -1,0 +1,258 @@
+// Grid pooling / unpooling reductions, the action head's per-cloud reductions, the losses and the
+// final-action decode, fp32.
+//   segment max / mean over CSR clusters ........ torch_scatter.segment_csr, model.py:760-765
+//   unpool gather-add ........................... model.py:824
+//   per-cloud max over points ................... simple_policy_ptv3.py:117-119
+//   soft-label CE + rot CE + open BCE ........... simple_policy_ptv3.py:308-373
+//   argmax decode + euler bins -> quaternion .... simple_policy_ptv3.py:250-295, action_position_utils.py:48-60,
+//                                                 rotation_transform.py:192-193
+#include "common.cuh"
+
+// out[m, c] = max_{j in [ptr[m], ptr[m+1])} x[member ? member[j] : j, c]; arg[m, c] = winning source row
+__global__ void k_segment_max(const float* __restrict__ x, int C, const int32_t* __restrict__ ptr,
+                              const int32_t* __restrict__ member, int M, float* __restrict__ out,
+                              int32_t* __restrict__ arg) {
+  int64_t total = (int64_t)M * C;
+  for (int64_t t = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; t < total; t += (int64_t)gridDim.x * blockDim.x) {
+    int m = (int)(t / C), c = (int)(t % C);
+    int s = ptr[m], e = ptr[m + 1];
+    float best = -INFINITY; int bi = -1;
+    for (int j = s; j < e; ++j) {
+      int r = member ? member[j] : j;
+      float v = x[(int64_t)r * C + c];
+      if (v > best || bi < 0) { best = v; bi = r; }
+    }
+    out[t] = best;
+    if (arg) arg[t] = bi;
+  }
+}
+LOTUS_API int lotus_segment_max_fwd_f32(const float* x, int C, const int32_t* seg_ptr, const int32_t* member, int M,
+                                        float* out, int32_t* argmax, void* stream_) {
+  if (M <= 0) return 0;
+  int64_t total = (int64_t)M * C;
+  k_segment_max<<<min(ceil_div(total, 256), kNumSM * 16), 256, 0, (cudaStream_t)stream_>>>(x, C, seg_ptr, member, M, out, argmax);
+  LOTUS_CUDA_OK();
+  return 0;
+}
+// dx[arg[m,c], c] = dy[m,c]   (dx zero-initialised by the caller; segments are disjoint -> no atomics)
+__global__ void k_segment_max_bwd(const float* __restrict__ dy, const int32_t* __restrict__ arg, int64_t total, int C,
+                                  float* __restrict__ dx) {
+  for (int64_t t = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; t < total; t += (int64_t)gridDim.x * blockDim.x) {
+    int r = arg[t];
+    if (r >= 0) dx[(int64_t)r * C + (t % C)] = dy[t];
+  }
+}
+LOTUS_API int lotus_segment_max_bwd_f32(const float* dy, const int32_t* argmax, int M, int C, float* dx_zeroed,
+                                        void* stream_) {
+  if (M <= 0) return 0;
+  int64_t total = (int64_t)M * C;
+  k_segment_max_bwd<<<min(ceil_div(total, 256), kNumSM * 16), 256, 0, (cudaStream_t)stream_>>>(dy, argmax, total, C, dx_zeroed);
+  LOTUS_CUDA_OK();
+  return 0;
+}
+
+// op 0: mean, 1: sum  (sum is the backward of the unpool gather: d_child[m] = sum_{p in cluster m} dy[p])
+__global__ void k_segment_sum(const float* __restrict__ x, int C, const int32_t* __restrict__ ptr,
+                              const int32_t* __restrict__ member, int M, int mean, float* __restrict__ out) {
+  int64_t total = (int64_t)M * C;
+  for (int64_t t = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; t < total; t += (int64_t)gridDim.x * blockDim.x) {
+    int m = (int)(t / C), c = (int)(t % C);
+    int s = ptr[m], e = ptr[m + 1];
+    float acc = 0.f;
+    for (int j = s; j < e; ++j) acc += x[(int64_t)(member ? member[j] : j) * C + c];
+    out[t] = mean ? acc / (float)(e - s) : acc;
+  }
+}
+LOTUS_API int lotus_segment_sum_f32(const float* x, int C, const int32_t* seg_ptr, const int32_t* member, int M,
+                                    int mean, float* out, void* stream_) {
+  if (M <= 0) return 0;
+  int64_t total = (int64_t)M * C;
+  k_segment_sum<<<min(ceil_div(total, 256), kNumSM * 16), 256, 0, (cudaStream_t)stream_>>>(x, C, seg_ptr, member, M, mean, out);
+  LOTUS_CUDA_OK();
+  return 0;
+}
+
+// out[p] = skip[p] + child[cluster[p]]
+__global__ void k_unpool_add(const float* __restrict__ skip, const float* __restrict__ child,
+                             const int32_t* __restrict__ cluster, int64_t total, int C, float* __restrict__ out) {
+  for (int64_t t = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; t < total; t += (int64_t)gridDim.x * blockDim.x) {
+    int p = (int)(t / C), c = (int)(t % C);
+    out[t] = skip[t] + child[(int64_t)cluster[p] * C + c];
+  }
+}
+LOTUS_API int lotus_unpool_add_f32(const float* skip, const float* child, const int32_t* cluster, int n, int C,
+                                   float* out, void* stream_) {
+  if (n <= 0) return 0;
+  int64_t total = (int64_t)n * C;
+  k_unpool_add<<<min(ceil_div(total, 256), kNumSM * 16), 256, 0, (cudaStream_t)stream_>>>(skip, child, cluster, total, C, out);
+  LOTUS_CUDA_OK();
+  return 0;
+}
+
+// ---------------------------------------------------------------- losses
+// position: per cloud b and axis c, CE between logits x[n, c*NB + k] (n in cloud, k < NB) and soft targets
+// prob[90*off[b] + c*(n_b*NB) + n*NB + k]; loss_pos = mean_b mean_c ( lse*sum(p) - sum(p*x) ).
+// Writes dlogits = s_pos * (softmax*sum(p) - p) / (3*B) when dlogits != null, with
+// s_pos = gout[0] + gout[3]*pos_w (gout = upstream gradient of {pos, rot, open, total}; null -> {0,0,0,1}).
+__global__ void k_pos_ce(const float* __restrict__ logits, const float* __restrict__ prob,
+                         const int32_t* __restrict__ off, int B, int NB, float* __restrict__ loss_accum,
+                         float* __restrict__ dlogits, const float* __restrict__ gout, float pos_w) {
+  float gscale = gout ? gout[0] + gout[3] * pos_w : pos_w;
+  __shared__ float red[32];
+  int b = blockIdx.x, c = blockIdx.y;
+  int s = off[b], n = off[b + 1] - s;
+  int ld = 3 * NB;
+  int tot = n * NB;
+  const float* pb = prob + (int64_t)ld * s + (int64_t)c * tot;
+  float mx = -INFINITY;
+  for (int t = threadIdx.x; t < tot; t += blockDim.x) mx = fmaxf(mx, logits[(int64_t)(s + t / NB) * ld + c * NB + t % NB]);
+  mx = block_max(mx, red);
+  float se = 0.f, sp = 0.f, spx = 0.f;
+  for (int t = threadIdx.x; t < tot; t += blockDim.x) {
+    float x = logits[(int64_t)(s + t / NB) * ld + c * NB + t % NB];
+    float p = pb[t];
+    se += expf(x - mx); sp += p; spx += p * x;
+  }
+  se = block_sum(se, red); sp = block_sum(sp, red); spx = block_sum(spx, red);
+  float lse = mx + logf(se);
+  if (threadIdx.x == 0) atomicAdd(loss_accum, (lse * sp - spx) / (3.f * B));
+  if (dlogits) {
+    float k = gscale / (3.f * B);
+    for (int t = threadIdx.x; t < tot; t += blockDim.x) {
+      int64_t o = (int64_t)(s + t / NB) * ld + c * NB + t % NB;
+      dlogits[o] = k * (expf(logits[o] - lse) * sp - pb[t]);
+    }
+  }
+}
+
+// rotation CE over 72 bins x 3 axes (logit index bin*3 + axis) + open BCE-with-logits on the last column.
+// act: [B, ld] ; gt: [B, 7] = pos(3), rot bins(3), open(1).  losses[1]=rot, [2]=open.
+__global__ void k_rot_open_loss(const float* __restrict__ act, int ld, const float* __restrict__ gt, int gt_ld, int B,
+                                int nbins, float* __restrict__ losses, float* __restrict__ dact, float rot_w,
+                                const float* __restrict__ gout) {
+  __shared__ float red[32];
+  float s_rot = gout ? gout[1] + gout[3] * rot_w : rot_w;
+  float s_open = gout ? gout[2] + gout[3] : 1.f;
+  float lrot = 0.f, lopen = 0.f;
+  for (int t = threadIdx.x; t < B * 3; t += blockDim.x) {
+    int b = t / 3, a = t % 3;
+    const float* row = act + (int64_t)b * ld;
+    float mx = -INFINITY;
+    for (int k = 0; k < nbins; ++k) mx = fmaxf(mx, row[k * 3 + a]);
+    float se = 0.f;
+    for (int k = 0; k < nbins; ++k) se += expf(row[k * 3 + a] - mx);
+    float lse = mx + logf(se);
+    int tgt = (int)gt[(int64_t)b * gt_ld + 3 + a];
+    lrot += lse - row[tgt * 3 + a];
+    if (dact) {
+      float kf = s_rot / (3.f * B);
+      for (int k = 0; k < nbins; ++k)
+        dact[(int64_t)b * ld + k * 3 + a] = kf * (expf(row[k * 3 + a] - lse) - (k == tgt ? 1.f : 0.f));
+    }
+  }
+  for (int b = threadIdx.x; b < B; b += blockDim.x) {
+    float x = act[(int64_t)b * ld + nbins * 3], y = gt[(int64_t)b * gt_ld + gt_ld - 1];
+    lopen += fmaxf(x, 0.f) - x * y + log1pf(expf(-fabsf(x)));
+    if (dact) dact[(int64_t)b * ld + nbins * 3] = s_open * (1.f / (1.f + expf(-x)) - y) / B;
+  }
+  lrot = block_sum(lrot, red);
+  lopen = block_sum(lopen, red);
+  if (threadIdx.x == 0) { losses[1] = lrot / (3.f * B); losses[2] = lopen / B; }
+}
+__global__ void k_total_loss(float* losses, float pos_w, float rot_w) {
+  losses[3] = pos_w * losses[0] + rot_w * losses[1] + losses[2];
+}
+
+// losses[4] = {pos, rot, open, total}.  When non-null, d_heatmap [N, 3*NB] and d_action [B, act_ld] receive
+// sum_i gout[i] * d(losses[i])/d(logits)  (gout: 4 device floats, null -> gradient of `total`).
+LOTUS_API int lotus_policy_loss_f32(const float* heatmap_logits, const float* pos_prob, const int32_t* cloud_off, int B,
+                                    int NB, const float* action_logits, int act_ld, int rot_bins, const float* gt_actions,
+                                    int gt_ld, float pos_w, float rot_w, float* losses, float* d_heatmap,
+                                    float* d_action, const float* gout, void* stream_) {
+  cudaStream_t st = (cudaStream_t)stream_;
+  LOTUS_CHECK_ARG(act_ld == rot_bins * 3 + 1, "lotus_policy_loss_f32: action width %d != %d*3+1", act_ld, rot_bins);
+  LOTUS_CUDA_CALL(cudaMemsetAsync(losses, 0, 16, st));
+  k_pos_ce<<<dim3(B, 3), 256, 0, st>>>(heatmap_logits, pos_prob, cloud_off, B, NB, losses, d_heatmap, gout, pos_w);
+  k_rot_open_loss<<<1, 256, 0, st>>>(action_logits, act_ld, gt_actions, gt_ld, B, rot_bins, losses, d_action, rot_w, gout);
+  k_total_loss<<<1, 1, 0, st>>>(losses, pos_w, rot_w);
+  LOTUS_CUDA_OK();
+  return 0;
+}
+
+// ---------------------------------------------------------------- final-action decode
+// position: per cloud and axis argmax over (n_b * NB) logits (== argmax of the softmax), first max wins;
+// best = (double)xyz[n, c] + (k - NB/2) * bin_size   (numpy promotes to float64, then the reference casts to f32)
+// rotation: per cloud argmax over bins per axis -> euler 'xyz' (extrinsic) -> quaternion xyzw, float64.
+// out: [B, 8] float64 = pos(3), quat(4), open logit.
+__global__ void k_decode(const float* __restrict__ logits, const float* __restrict__ xyz, int xyz_ld,
+                         const int32_t* __restrict__ off, int NB, double bin_size, const float* __restrict__ act, int act_ld,
+                         int rot_bins, float resolution, const float* __restrict__ gt_pos, int gt_ld,
+                         double* __restrict__ out) {
+  __shared__ float rv[32];
+  __shared__ int ri[32];
+  int b = blockIdx.x;
+  int s = off[b], n = off[b + 1] - s, ld = 3 * NB, tot = n * NB;
+  int lane = threadIdx.x & 31, w = threadIdx.x >> 5, nw = blockDim.x >> 5;
+  for (int c = 0; c < 3; ++c) {
+    if (gt_pos) {  // compute_final_action=False: pred_pos := gt (simple_policy_ptv3.py:276-277)
+      if (threadIdx.x == 0) out[b * 8 + c] = (double)gt_pos[(int64_t)b * gt_ld + c];
+      continue;
+    }
+    float best = -INFINITY; int bi = 0x7fffffff;
+    for (int t = threadIdx.x; t < tot; t += blockDim.x) {
+      float v = logits[(int64_t)(s + t / NB) * ld + c * NB + t % NB];
+      if (v > best) { best = v; bi = t; }
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+      float ov = __shfl_xor_sync(0xffffffffu, best, o);
+      int oi = __shfl_xor_sync(0xffffffffu, bi, o);
+      if (ov > best || (ov == best && oi < bi)) { best = ov; bi = oi; }
+    }
+    __syncthreads();
+    if (lane == 0) { rv[w] = best; ri[w] = bi; }
+    __syncthreads();
+    if (w == 0) {
+      best = lane < nw ? rv[lane] : -INFINITY;
+      bi = lane < nw ? ri[lane] : 0x7fffffff;
+#pragma unroll
+      for (int o = 16; o > 0; o >>= 1) {
+        float ov = __shfl_xor_sync(0xffffffffu, best, o);
+        int oi = __shfl_xor_sync(0xffffffffu, bi, o);
+        if (ov > best || (ov == best && oi < bi)) { best = ov; bi = oi; }
+      }
+      if (lane == 0) {
+        int pn = bi / NB, k = bi % NB;
+        double cand = (double)xyz[(int64_t)(s + pn) * xyz_ld + c] + (double)(k - NB / 2) * bin_size;
+        out[b * 8 + c] = (double)(float)cand;  // torch.from_numpy(np.array(...)).float()
+      }
+    }
+    __syncthreads();
+  }
+  if (threadIdx.x == 0) {
+    const float* row = act + (int64_t)b * act_ld;
+    double e[3];
+    for (int a = 0; a < 3; ++a) {
+      float best = -INFINITY; int bk = 0;
+      for (int k = 0; k < rot_bins; ++k)
+        if (row[k * 3 + a] > best) { best = row[k * 3 + a]; bk = k; }
+      e[a] = ((double)bk * (double)resolution - 180.0) * 0.017453292519943295;
+    }
+    double cx = cos(e[0] / 2), sx = sin(e[0] / 2), cy = cos(e[1] / 2), sy = sin(e[1] / 2), cz = cos(e[2] / 2), sz = sin(e[2] / 2);
+    out[b * 8 + 3] = sx * cy * cz - cx * sy * sz;
+    out[b * 8 + 4] = cx * sy * cz + sx * cy * sz;
+    out[b * 8 + 5] = cx * cy * sz - sx * sy * cz;
+    out[b * 8 + 6] = cx * cy * cz + sx * sy * sz;
+    out[b * 8 + 7] = (double)row[rot_bins * 3];
+  }
+}
+LOTUS_API int lotus_decode_actions(const float* heatmap_logits, const float* xyz, int xyz_ld, const int32_t* cloud_off,
+                                   int B, int NB, double bin_size, const float* action_logits, int act_ld, int rot_bins,
+                                   float euler_resolution, const float* gt_pos_or_null, int gt_ld, double* out,
+                                   void* stream_) {
+  if (B <= 0) return 0;
+  k_decode<<<B, 256, 0, (cudaStream_t)stream_>>>(heatmap_logits, xyz, xyz_ld, cloud_off, NB, bin_size, action_logits, act_ld,
+                                                 rot_bins, euler_resolution, gt_pos_or_null, gt_ld, out);
+  LOTUS_CUDA_OK();
+  return 0;
+}

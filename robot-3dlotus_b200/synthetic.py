@@ -107,18 +107,19 @@ def make_batch(seed=2024, batch_size=32, max_points=4096, min_raw=1500, max_raw=
         xyz = (vox[sel] + rng.uniform(0.2, 0.8, size=(sel.size, 3))) * VOXEL
         xyz = (xyz - xyz.mean(0, keepdims=True)).astype(np.float32)        # xyz_shift 'center'
         clouds.append((xyz, n))
-    # de-duplicate under the model's quantisation (global min over the packed batch)
-    for _ in range(8):
+    # de-duplicate under the model's quantisation (global min over the packed batch); the points that define
+    # the global min corner are always kept so the quantisation does not move between iterations
+    for _ in range(50):
         coord = np.concatenate([c for c, _ in clouds], 0)
         bid = np.concatenate([np.full(c.shape[0], i, dtype=np.int64) for i, (c, _) in enumerate(clouds)])
         key = _model_grid(coord, bid)
-        _, first = np.unique(key, axis=0, return_index=True)
+        gmin = np.unique(np.argmin(coord, 0))
+        prio = np.concatenate([gmin, np.setdiff1d(np.arange(key.shape[0]), gmin)])
+        _, first = np.unique(key[prio], axis=0, return_index=True)
         if first.size == key.shape[0]:
             break
         keep = np.zeros(key.shape[0], dtype=bool)
-        keep[first] = True
-        # never drop the points that define the global min corner
-        keep[np.argmin(coord, 0)] = True
+        keep[prio[first]] = True
         off = 0
         new = []
         for c, n in clouds:

@@ -1,0 +1,175 @@
+"""Integer tokeniser driver: one stream-ordered pass that builds EVERY stage's structure (grid coords,
+curve codes, orders, patch plans, pooling clusters, sparse-conv neighbourhoods) from the input coordinates
+with no host synchronisation, followed by ONE device->host copy of the data-dependent sizes.
+
+Reference behaviour replaced (relative to /root/reference/genrobo3d/models/PointTransformerV3/):
+Point.serialization model.py:83-138, Point.sparsify :140-176 (+ spconv indice generation),
+SerializedAttention.get_padding_and_inverse :410-466, SerializedPooling.forward (integer half) :713-771.
+The reference syncs the host at :102, :164-166, :173, :440 (per cloud) — SURVEY D.3.
+"""
+import ctypes
+from dataclasses import dataclass, field
+from typing import Dict, List, Optional
+
+import torch
+
+from .lib import load
+from .ops import _p, _st
+
+CURVE_ID = {"z": 0, "z-trans": 1, "hilbert": 2, "hilbert-trans": 3}
+META_STRIDE = 8
+
+
+@dataclass
+class PatchPlan:
+    gather_idx: torch.Tensor      # (n_pad,) int32: order[pad]
+    slot_of_point: torch.Tensor   # (n,) int32: unpad[inverse]
+    cu_seqlens: torch.Tensor      # (n_patches+1,) int32
+    pad: torch.Tensor
+    unpad: torch.Tensor
+    n_pad: int = 0
+    n_patches: int = 0
+    max_len: int = 128
+
+
+@dataclass
+class CrossGeo:
+    pt_off: torch.Tensor
+    tok_off: torch.Tensor
+    B: int
+    max_points: int
+    max_tokens: int
+
+
+@dataclass
+class Stage:
+    n: int = 0
+    depth: int = 0
+    stride_alloc: int = 0                      # row stride of code/order/inverse/nbr allocations
+    grid: torch.Tensor = None                  # (n,3) int32
+    batch: torch.Tensor = None                 # (n,) int32
+    cloud_off: torch.Tensor = None             # (B+1,) int32 device
+    cloud_off_host: List[int] = None
+    code: torch.Tensor = None                  # (4, stride) int64
+    order: torch.Tensor = None                 # (4, stride) int32
+    inverse: torch.Tensor = None
+    curves: List[int] = None
+    nbr3: torch.Tensor = None                  # (27, stride) int32
+    nbr5: Optional[torch.Tensor] = None        # (125, stride) int32, stage 0 only
+    plans: Dict[int, PatchPlan] = field(default_factory=dict)
+    # pooling from the parent stage
+    cluster: Optional[torch.Tensor] = None     # (n_parent,) int32 : parent point -> this stage's point
+    seg_ptr: Optional[torch.Tensor] = None     # (n+1,) int32 : CSR over the parent's code-sorted order (row 0)
+    member: Optional[torch.Tensor] = None      # parent's order row 0
+    head: Optional[torch.Tensor] = None
+
+    @property
+    def max_cloud(self):
+        c = self.cloud_off_host
+        return max(b - a for a, b in zip(c[:-1], c[1:]))
+
+
+def _next_pow2(x):
+    p = 1
+    while p < x:
+        p <<= 1
+    return p
+
+
+def tokenize(coord, npoints: List[int], orders, strides, patch_sizes, rows_needed, perms=None, grid_size=0.01,
+             div_mode=0, need_stem=True):
+    """coord (N,3) fp32 cuda (may be a strided view of pc_fts); npoints: host list of per-cloud counts.
+    perms: list of S row permutations (host lists) or None.  Returns [Stage_0 .. Stage_{S-1}]."""
+    L = load()
+    dev = coord.device
+    st = _st()
+    S = len(strides) + 1
+    B = len(npoints)
+    N0 = int(sum(npoints))
+    i32 = dict(device=dev, dtype=torch.int32)
+    coordc = coord if coord.is_contiguous() else coord.contiguous()
+
+    off0 = [0]
+    for c in npoints:
+        off0.append(off0[-1] + int(c))
+    cloud_off_all = torch.empty((S, B + 1), **i32)
+    cloud_off_all[0].copy_(torch.tensor(off0, dtype=torch.int32), non_blocking=True)
+    meta = torch.zeros((S, META_STRIDE), **i32)
+    scratch = torch.empty(4 * (B + 2) + 8, **i32)
+    err = torch.zeros(1, **i32)
+    max_cloud = max(npoints)
+    hash_cap = _next_pow2(2 * N0)
+    hkeys = torch.empty(hash_cap, device=dev, dtype=torch.int64)
+    hvals = torch.empty(hash_cap, **i32)
+
+    stages: List[Stage] = []
+    grid = torch.empty((N0, 3), **i32)
+    batch = torch.empty(N0, **i32)
+    L.lotus_grid_coord(_p(coordc), N0, grid_size, div_mode, _p(grid), _p(meta[0]), _p(scratch), st)
+    L.lotus_batch_ids(_p(cloud_off_all[0]), B, _p(batch), st)
+    curves = [CURVE_ID[o] for o in orders]
+    R = len(curves)
+    for s in range(S):
+        if perms is not None:
+            curves = [curves[int(i)] for i in perms[s]]
+        stg = Stage(stride_alloc=N0, grid=grid, batch=batch, cloud_off=cloud_off_all[s], curves=list(curves))
+        stg.code = torch.empty((R, N0), device=dev, dtype=torch.int64)
+        stg.order = torch.empty((R, N0), **i32)
+        stg.inverse = torch.empty((R, N0), **i32)
+        cv = (ctypes.c_int32 * 4)(*(curves + [0] * (4 - R)))
+        L.lotus_serialize(_p(grid), _p(batch), _p(stg.cloud_off), B, N0, max_cloud, _p(meta[s]), cv, R, N0, _p(stg.code),
+                          _p(stg.order), _p(stg.inverse), _p(err), st)
+        # sparse-conv neighbourhoods (hash built once per stage, probed for k=3 and, at stage 0, k=5)
+        stg.nbr3 = torch.empty((27, N0), **i32)
+        L.lotus_neighbor_table(_p(grid), _p(batch), _p(meta[s]), N0, 3, _p(hkeys), _p(hvals), hash_cap, 1, _p(stg.nbr3), N0, st)
+        if s == 0 and need_stem:
+            stg.nbr5 = torch.empty((125, N0), **i32)
+            L.lotus_neighbor_table(_p(grid), _p(batch), _p(meta[s]), N0, 5, _p(hkeys), _p(hvals), hash_cap, 0, _p(stg.nbr5), N0, st)
+        K = patch_sizes[s]
+        npad_upper = N0 + B * K
+        cu_len = N0 // K + B + 2
+        for r in rows_needed[s]:
+            pl = PatchPlan(gather_idx=torch.empty(npad_upper, **i32), slot_of_point=torch.empty(N0, **i32),
+                           cu_seqlens=torch.empty(cu_len, **i32), pad=torch.empty(npad_upper, **i32),
+                           unpad=torch.empty(N0, **i32), max_len=K)
+            L.lotus_patch_plan(_p(stg.cloud_off), B, K, _p(stg.order[r]), _p(stg.inverse[r]), _p(pl.pad), _p(pl.unpad),
+                               _p(pl.gather_idx), _p(pl.slot_of_point), _p(pl.cu_seqlens), cu_len, _p(meta[s]),
+                               _p(scratch[8:]), st)
+            stg.plans[r] = pl
+        stages.append(stg)
+        if s < S - 1:
+            nxt_grid = torch.empty((N0, 3), **i32)
+            nxt_batch = torch.empty(N0, **i32)
+            cluster = torch.empty(N0, **i32)
+            head = torch.empty(N0, **i32)
+            seg_ptr = torch.empty(N0 + 1, **i32)
+            L.lotus_pool_structure(_p(stg.code[0]), _p(stg.order[0]), _p(grid), _p(stg.cloud_off), B, int(strides[s]),
+                                   _p(meta[s]), _p(cluster), _p(head), _p(seg_ptr), _p(nxt_grid), _p(nxt_batch),
+                                   _p(cloud_off_all[s + 1]), _p(meta[s + 1]), _p(scratch), st)
+            stg._next = (cluster, head, seg_ptr)
+            grid, batch = nxt_grid, nxt_batch
+
+    # ---- the single host sync of the forward: data-dependent sizes
+    host = torch.cat([meta.reshape(-1), cloud_off_all.reshape(-1), err]).cpu()
+    meta_h = host[: S * META_STRIDE].view(S, META_STRIDE).tolist()
+    off_h = host[S * META_STRIDE: S * META_STRIDE + S * (B + 1)].view(S, B + 1).tolist()
+    if int(host[-1]) != 0:
+        raise RuntimeError("lotus tokeniser: a cloud exceeds the shared-memory sort capacity (16384 points) or depth > 16")
+    for s, stg in enumerate(stages):
+        stg.n, stg.depth = meta_h[s][0], meta_h[s][1]
+        stg.cloud_off_host = off_h[s]
+        n = stg.n
+        stg.grid, stg.batch = stg.grid[:n], stg.batch[:n]
+        for pl in stg.plans.values():
+            pl.n_pad, pl.n_patches = meta_h[s][2], meta_h[s][3]
+            pl.gather_idx, pl.pad = pl.gather_idx[: pl.n_pad], pl.pad[: pl.n_pad]
+            pl.slot_of_point, pl.unpad = pl.slot_of_point[:n], pl.unpad[:n]
+            pl.cu_seqlens = pl.cu_seqlens[: pl.n_patches + 1]
+        if s > 0:
+            cluster, head, seg_ptr = stages[s - 1]._next
+            stg.cluster = cluster[: stages[s - 1].n]
+            stg.head = head[:n]
+            stg.seg_ptr = seg_ptr[: n + 1]
+            stg.member = stages[s - 1].order[0]
+    assert stages[0].depth <= 16 and stages[0].depth * 3 + B.bit_length() <= 63, "serialization code overflow (model.py:105,110)"
+    return stages

@@ -1,0 +1,112 @@
+#!/usr/bin/env python
+"""Regenerate include/lotus.h from the `LOTUS_API` definitions in robot-3dlotus_b200/csrc/*.cu.
+
+The .cu definitions are the single source of the C ABI; this script copies each prototype verbatim and
+attaches the reference interface it replaces (file:line, relative to /root/reference/genrobo3d/).
+"""
+import glob
+import os
+import re
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+SRC = os.path.join(ROOT, "robot-3dlotus_b200", "csrc")
+
+DOC = {
+    "lotus_last_error": "Message of the last failing call on this thread (reference signals errors with Python exceptions/asserts).",
+    "lotus_version": "ABI version (major*10000 + minor*100 + patch).",
+    "lotus_device_arch": "Compute capability of the current device (100 on B200).",
+    "lotus_grid_coord": "Replaces Point.serialization grid step: models/PointTransformerV3/model.py:96-103 "
+                        "(grid = trunc((coord-min_over_batch)/grid_size), depth = bit_length(max)). mode 0 = true "
+                        "division (torch CPU kernel), 1 = multiply by reciprocal (torch CUDA kernel). meta[0]=n, meta[1]=depth.",
+    "lotus_batch_ids": "Replaces offset2batch: model.py:37-42.",
+    "lotus_serialize": "Replaces serialization.encode x4 + argsort + inverse scatter (+ shuffle_orders row permutation): "
+                       "serialization/default.py:10-27, z_order.py:66-101, hilbert.py:91-198, model.py:117-138. "
+                       "curve_of_row: 0 z, 1 z-trans, 2 hilbert, 3 hilbert-trans (row r of the outputs uses that curve).",
+    "lotus_pool_structure": "Replaces the integer half of SerializedPooling.forward: model.py:713-755,766-771 "
+                            "(code>>3, unique -> cluster, CSR over the code-sorted order, head attributes, pooled depth/offsets).",
+    "lotus_patch_plan": "Replaces SerializedAttention.get_padding_and_inverse and the order[pad] / unpad[inverse] "
+                        "compositions: model.py:410-466,480-481. gather_idx = order[pad]; slot_of_point = unpad[inverse].",
+    "lotus_neighbor_table": "Replaces spconv 2.3.6 SubMConv3d indice-pair generation (call sites model.py:616-622,845-852): "
+                            "nbr[d*stride + p] = voxel at grid[p]+off(d) in the same cloud or -1; d=(d0*k+d1)*k+d2, d0 along x.",
+    "lotus_fps": "Replaces farthest_point_sample (explicit start index): train/datasets/common.py:108-129. Bit-exact indices.",
+    "lotus_knn": "North-star kNN grouping (no reference function; SURVEY §8a row 13): brute force inside each cloud, ties -> lowest index.",
+    "lotus_ball_query": "North-star radius grouping (no reference function; SURVEY §8a row 13): first nsample indices within radius.",
+    "lotus_rpe_bias": "Replaces RPE.forward + get_rel_pos: model.py:307-326,400-408 (materialised bias; the attention kernels fuse it).",
+    "lotus_linear_fwd_f32": "Replaces nn.Linear forward (qkv/proj/fc1/fc2/q/kv/pool/unpool/txt_fc/head): model.py:386-387,572-574,707,804-805; "
+                            "model_ca.py:27-31; simple_policy_ptv3.py:40-68,387. Optional row gather, bias, GELU/LeakyReLU, residual epilogue.",
+    "lotus_linear_dgrad_f32": "Backward of nn.Linear w.r.t. its input (autograd of the call sites above).",
+    "lotus_linear_wgrad_f32": "Backward of nn.Linear w.r.t. its weight (accumulates into dw).",
+    "lotus_subm_conv_fwd_f32": "Replaces spconv.SubMConv3d forward (stem k=5, CPE k=3): model.py:616-622,845-852.",
+    "lotus_subm_conv_dgrad_f32": "Backward of SubMConv3d w.r.t. its input features.",
+    "lotus_subm_conv_wgrad_f32": "Backward of SubMConv3d w.r.t. its weight (accumulates into dw).",
+    "lotus_layernorm_fwd_f32": "Replaces nn.LayerNorm (block norms, CPE norm, per-head q/k norm eps 1e-6): model.py:393-394,624,627,645; model_ca.py:43-44,114,124. "
+                               "Rows are addressed as (r/inner)*outer_stride + (r%inner)*inner_stride so per-head norms read the packed qkv in place.",
+    "lotus_layernorm_bwd_f32": "Backward of nn.LayerNorm (dx, and accumulated dgamma/dbeta).",
+    "lotus_colsum_f32": "Bias gradients (column sums of dy), accumulated.",
+    "lotus_batchnorm_fwd_f32": "Replaces nn.BatchNorm1d(eps=1e-3, momentum=0.01) [+ GELU] (stem, pool, unpool): model.py:932,785-788,807-813,854-857.",
+    "lotus_batchnorm_bwd_f32": "Backward of BatchNorm1d [+ GELU].",
+    "lotus_pointwise_f32": "GELU / LeakyReLU(0.02) and their derivatives, add, scale: model.py:573; simple_policy_ptv3.py:42,65.",
+    "lotus_dropout_f32": "Replaces nn.Dropout (counter-based mask; the same call on dy is the backward): model.py:388,575; simple_policy_ptv3.py:43,66.",
+    "lotus_patch_attn_fwd_f32": "Replaces flash_attn_varlen_qkvpacked_func over the serialized patches incl. the qkv[order] gather and feat[inverse] scatter "
+                                "(and the RPE bias of the non-flash branch): model.py:497,520-521,543-551.",
+    "lotus_patch_attn_bwd_f32": "Backward of the patch attention (dq, dk, dv accumulated in point order; optional RPE table gradient).",
+    "lotus_cross_attn_fwd_f32": "Replaces flash_attn_varlen_kvpacked_func (points of a cloud attend to that cloud's tokens): model_ca.py:56-67.",
+    "lotus_cross_attn_bwd_f32": "Backward of the cross attention.",
+    "lotus_segment_max_fwd_f32": "Replaces torch_scatter.segment_csr(reduce='max') and the per-cloud max of the action head: model.py:760-762; simple_policy_ptv3.py:117-119.",
+    "lotus_segment_max_bwd_f32": "Backward of the segment max (routes dy to the arg-max rows).",
+    "lotus_segment_sum_f32": "Replaces torch_scatter.segment_csr(reduce='mean') for coords (model.py:763-765); sum mode is the backward of the unpool gather.",
+    "lotus_unpool_add_f32": "Replaces parent.feat + point.feat[inverse]: model.py:824.",
+    "lotus_policy_loss_f32": "Replaces compute_loss (heatmap_disc soft-label CE, euler_disc CE, open BCE) and its backward: simple_policy_ptv3.py:308-373.",
+    "lotus_decode_actions": "Replaces the final-action decode: simple_policy_ptv3.py:250-296; utils/action_position_utils.py:48-60; utils/rotation_transform.py:192-193.",
+    "lotus_grad_sumsq_f32": "Global gradient norm of clip_grad_norm_: train/train_simple_policy.py:237-241.",
+    "lotus_adamw_step_f32": "Replaces the reference AdamW.step over one flat buffer (+ fused clip coefficient): train/optim/adamw.py:53-112.",
+}
+
+
+def prototypes():
+    out = []
+    for f in sorted(glob.glob(os.path.join(SRC, "*.cu"))):
+        src = open(f).read()
+        for m in re.finditer(r"LOTUS_API\s+([^\{;]+?)\s*\{", src, re.S):
+            proto = " ".join(m.group(1).split())
+            name = re.search(r"(lotus_\w+)\s*\(", proto).group(1)
+            out.append((name, proto, os.path.basename(f)))
+    return out
+
+
+def main():
+    lines = [
+        "/* lotus.h — C ABI of the B200-native 3D-LOTUS hot path (generated by tools/gen_header.py; do not edit).",
+        " *",
+        " * Conventions: every function returns 0 on success, non-zero on failure (message: lotus_last_error());",
+        " * pointers are DEVICE pointers unless the parameter name says host; the library never allocates —",
+        " * callers pass outputs and scratch; `stream` is a cudaStream_t; calls are stream-ordered and re-entrant",
+        " * per stream.  Index arrays are int32, curve codes int64.  Citations are relative to",
+        " * /root/reference/genrobo3d/ (models/PointTransformerV3/ for bare model.py / model_ca.py / serialization/).",
+        " */",
+        "#ifndef LOTUS_H_",
+        "#define LOTUS_H_",
+        "#include <stdint.h>",
+        "#ifdef __cplusplus",
+        'extern "C" {',
+        "#endif",
+        "",
+    ]
+    missing = []
+    for name, proto, f in prototypes():
+        doc = DOC.get(name)
+        if doc is None:
+            missing.append(name)
+            doc = "(undocumented)"
+        lines.append("/* [%s] %s */" % (f, doc))
+        lines.append(proto + ";")
+        lines.append("")
+    lines += ["#ifdef __cplusplus", "}", "#endif", "#endif  /* LOTUS_H_ */", ""]
+    open(os.path.join(ROOT, "include", "lotus.h"), "w").write("\n".join(lines))
+    if missing:
+        print("WARNING: undocumented:", missing)
+    print("wrote include/lotus.h with", len(prototypes()), "entry points")
+
+
+if __name__ == "__main__":
+    main()
