@@ -28,6 +28,24 @@ def make_model(g):
     return cfg, model
 
 
+def lattice_clouds(sizes, side, seed):
+    """unique voxels on a side^3 lattice per cloud; coordinates sit mid-voxel and an anchor point at the origin
+    (first point of cloud 0) pins the batch minimum, so the model's quantisation returns the lattice exactly."""
+    rng = np.random.default_rng(seed)
+    grids = []
+    for i, n in enumerate(sizes):
+        v = rng.permutation(side ** 3 - 1)[: n - (1 if i == 0 else 0)] + 1          # voxel 0 is reserved for the anchor
+        g = np.stack([v // (side * side), (v // side) % side, v % side], 1)
+        if i == 0:
+            g = np.concatenate([np.zeros((1, 3), dtype=g.dtype), g])
+        grids.append(g)
+    grid = torch.from_numpy(np.concatenate(grids)).int()
+    coord = grid.float() * 0.01 + 0.005
+    coord[0] = 0.0
+    assert torch.equal(O.grid_coords(coord), grid)
+    return coord, grid
+
+
 # ------------------------------------------------------------------------------------------------ tokeniser
 def _tokenize_gold(g, perms):
     tk = pkg("tokenizer")
@@ -132,11 +150,8 @@ def test_codes_golden_all_depths(units, depth):
 def test_empty_and_tiny_clouds():
     """ragged input: clouds of 1 and 2 points next to a padded one (reference patch-plan edge cases)."""
     tk = pkg("tokenizer")
-    rng = np.random.default_rng(0)
     sizes = [1, 300, 2, 129]
-    vox = [rng.permutation(40 ** 3)[:n] for n in sizes]
-    coord = np.concatenate([np.stack([v // 1600, (v // 40) % 40, v % 40], 1) for v in vox]).astype(np.float32) * 0.01 + 0.005
-    coord = torch.from_numpy(coord)
+    coord, _ = lattice_clouds(sizes, 40, 0)
     stages = tk.tokenize(coord.to(DEV), sizes, ["z", "z-trans", "hilbert", "hilbert-trans"], [2, 2, 2, 2], [128] * 5,
                          [[0]] * 5, None)
     off = torch.tensor(np.cumsum(sizes))
@@ -168,8 +183,9 @@ def test_fps_bit_exact(units):
     starts = [5, 999, 0]
     out = torch.empty((3, 32), dtype=torch.int32, device=DEV)
     x = torch.from_numpy(xyz).to(DEV)
-    L.lotus_fps(P(x), 3, P(torch.tensor(offs, dtype=torch.int32, device=DEV)), 3, max(sizes), 32,
-                P(torch.tensor(starts, dtype=torch.int32, device=DEV)), P(out), None)
+    t_off = torch.tensor(offs, dtype=torch.int32, device=DEV)          # keep the device buffers alive across the call
+    t_start = torch.tensor(starts, dtype=torch.int32, device=DEV)
+    L.lotus_fps(P(x), 3, P(t_off), 3, max(sizes), 32, P(t_start), P(out), None)
     for b in range(3):
         ref = O.farthest_point_sample_indices(xyz[offs[b]:offs[b + 1]], 32, starts[b]) + offs[b]
         assert np.array_equal(out[b].cpu().numpy(), ref), b
@@ -212,7 +228,8 @@ def test_rpe_bias_golden(units):
     want = O.rpe_bias(r["table"], rel_, r["pos_bnd"])
     out = torch.empty((2, H, K, K), device=DEV)
     gi = torch.arange(2 * K, dtype=torch.int32, device=DEV)
-    L.lotus_rpe_bias(P(r["table"].to(DEV)), P(g.to(DEV)), P(gi), 2, K, H, r["pos_bnd"], P(out), None)
+    t_table, t_g = r["table"].to(DEV), g.to(DEV)
+    L.lotus_rpe_bias(P(t_table), P(t_g), P(gi), 2, K, H, r["pos_bnd"], P(out), None)
     assert torch.allclose(out.cpu(), want, atol=1e-7)
     assert torch.allclose(O.rpe_bias(r["table"], r["rel"], r["pos_bnd"]), r["bias"], atol=1e-7)   # oracle == reference
 
@@ -227,10 +244,16 @@ def _check_grads(fn_cuda, fn_ref, inputs, tol=TOL):
     go = torch.randn(yr.shape, generator=torch.Generator().manual_seed(5))
     yc.backward(go.to(DEV))
     yr.backward(go)
+    # some gradients are mathematically zero (k_norm.bias under softmax): compare those against the scale of
+    # the largest gradient of the same call instead of against their own rounding noise
+    scale = max(rf[k].grad.abs().max().item() for k in inputs if rf[k].grad is not None)
     for k in inputs:
         if rf[k].grad is not None:
             gc = cu[k].grad if cu[k].grad is not None else torch.zeros_like(cu[k])     # unused input -> zero grad
-            assert rel(gc, rf[k].grad) < tol, (k, rel(gc, rf[k].grad))
+            if rf[k].grad.abs().max().item() < 1e-4 * scale:
+                assert gc.abs().max().item() < 1e-4 * scale, (k, "expected ~0", gc.abs().max().item(), scale)
+            else:
+                assert rel(gc, rf[k].grad) < tol, (k, rel(gc, rf[k].grad))
 
 
 def test_linear_layernorm_act_kernels():
@@ -279,11 +302,8 @@ def test_batchnorm_gelu_kernel():
 
 def test_subm_conv_kernel():
     ops, tk = pkg("ops"), pkg("tokenizer")
-    rng = np.random.default_rng(4)
     sizes = [500, 260]
-    vox = [rng.permutation(20 ** 3)[:n] for n in sizes]
-    grid = torch.from_numpy(np.concatenate([np.stack([v // 400, (v // 20) % 20, v % 20], 1) for v in vox])).int()
-    coord = grid.float() * 0.01 + 0.004
+    coord, grid = lattice_clouds(sizes, 20, 4)
     stages = tk.tokenize(coord.to(DEV), sizes, ["z"], [2], [128, 128], [[0], [0]], None)
     batch_ids = O.offset2batch(torch.tensor(np.cumsum(sizes)))
     g = torch.Generator().manual_seed(2)
@@ -298,11 +318,8 @@ def test_subm_conv_kernel():
 @pytest.mark.parametrize("H,D,qk_norm,rpe", [(2, 16, True, False), (4, 24, True, False), (2, 32, False, False), (1, 32, True, True)])
 def test_patch_attention_kernel(H, D, qk_norm, rpe):
     ops, tk, mods = pkg("ops"), pkg("tokenizer"), pkg("modules")
-    rng = np.random.default_rng(6)
     sizes = [256, 128] if rpe else [300, 90, 129, 1]          # RPE (non-flash branch) needs full patches
-    vox = [rng.permutation(24 ** 3)[:n] for n in sizes]
-    grid = torch.from_numpy(np.concatenate([np.stack([v // 576, (v // 24) % 24, v % 24], 1) for v in vox])).int()
-    coord = grid.float() * 0.01 + 0.004
+    coord, grid = lattice_clouds(sizes, 24, 6)
     stg = tk.tokenize(coord.to(DEV), sizes, ["hilbert"], [2], [128, 128], [[0], [0]], None)[0]
     off = torch.tensor(np.cumsum(sizes))
     ser = O.serialize(O.grid_coords(coord), O.offset2batch(off), ["hilbert"])
@@ -310,18 +327,20 @@ def test_patch_attention_kernel(H, D, qk_norm, rpe):
     C = H * D
     g = torch.Generator().manual_seed(3)
     attn = mods.SerializedAttention(C, H, 128, qk_norm=qk_norm, enable_rpe=rpe, enable_flash=not rpe)
-    inputs = dict(qkv=torch.randn(sum(sizes), 3 * C, generator=g), qg=torch.randn(D, generator=g), qb=torch.randn(D, generator=g),
+    inputs = dict(x=torch.randn(sum(sizes), C, generator=g), wqkv=torch.randn(3 * C, C, generator=g) * C ** -0.5,
+                  qg=torch.randn(D, generator=g), qb=torch.randn(D, generator=g),
                   kg=torch.randn(D, generator=g), kb=torch.randn(D, generator=g), table=torch.randn(93, H, generator=g) * 0.5)
 
-    def cuda_fn(qkv, qg, qb, kg, kb, table):
+    def cuda_fn(x, wqkv, qg, qb, kg, kb, table):
+        qkv = ops.linear(x, wqkv)
         return ops.PatchAttnFn.apply(qkv, qg if qk_norm else None, qb if qk_norm else None, kg if qk_norm else None,
                                      kb if qk_norm else None, table if rpe else None, stg.plans[0], H, qk_norm, ops.NO_DROP,
                                      stg.grid, 15)
 
-    def ref_fn(qkv, qg, qb, kg, kb, table):
-        P = {"qkv.weight": torch.eye(3 * C), "q_norm.weight": qg, "q_norm.bias": qb, "k_norm.weight": kg, "k_norm.bias": kb,
+    def ref_fn(x, wqkv, qg, qb, kg, kb, table):
+        P = {"qkv.weight": wqkv, "q_norm.weight": qg, "q_norm.bias": qb, "k_norm.weight": kg, "k_norm.bias": kb,
              "proj.weight": torch.eye(C), "proj.bias": torch.zeros(C)}
-        y = O.patch_attention(qkv, P, "", H, ser["order"][0], ser["inverse"][0], plan, 128, qk_norm,
+        y = O.patch_attention(x, P, "", H, ser["order"][0], ser["inverse"][0], plan, 128, qk_norm,
                               table if rpe else None, O.grid_coords(coord))
         return y + 0 * (qg.sum() + qb.sum() + kg.sum() + kb.sum() + table.sum())
     _check_grads(cuda_fn, ref_fn, inputs)
