@@ -83,6 +83,7 @@ class PolicyEngine:
             assert pt.dec_patch_size[s] == psz[s], "enc/dec patch sizes of a stage must match (shared patch plan)"
         stages = tokenize(coord, npoints, pt.order, pt.stride, psz, rows, self._perms(S, R, pt.shuffle_orders),
                           self.m.config.action_config.voxel_size, self.div_mode)
+        self.last_stages = stages
         dev = feat.device
         B = len(npoints)
         tok_off = torch.tensor(tok_off_host, dtype=torch.int32).to(dev, non_blocking=True)

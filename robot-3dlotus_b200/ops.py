@@ -41,6 +41,26 @@ class DropCtx:
 
 NO_DROP = (0.0, 0, 0)
 
+# Gradient sinks: parameter storage address -> fp32 view inside the trainer's flat gradient buffer.  When a
+# parameter has a sink, the backward kernels ACCUMULATE its gradient there directly ("flat grad
+# buffer written directly by the backward kernels") and autograd receives None for it.
+GRAD_SINK = {}
+
+
+def _sink(param):
+    return GRAD_SINK.get(param.data_ptr()) if param is not None else None
+
+
+def _grad_buf(param, needs):
+    """-> (buffer to accumulate into or None, value to hand back to autograd)"""
+    if param is None or not needs:
+        return None, None
+    s = _sink(param)
+    if s is not None:
+        return s, None
+    z = torch.zeros_like(param)
+    return z, z
+
 # ------------------------------------------------------------------------------------------ Linear
 
 
@@ -58,6 +78,7 @@ class LinearFn(torch.autograd.Function):
             residual = _f32c(residual)
         L.lotus_linear_fwd_f32(_p(x), _p(w), _p(b), _p(residual), _p(y), M, N, K, 0, None, drop[0], drop[1], drop[2], _st())
         ctx.save_for_backward(x, w)
+        ctx.bias = b
         ctx.has_b, ctx.has_res, ctx.drop = b is not None, residual is not None, drop
         return y
 
@@ -77,12 +98,12 @@ class LinearFn(torch.autograd.Function):
         if ctx.needs_input_grad[0]:
             dx = torch.empty_like(x)
             L.lotus_linear_dgrad_f32(_p(dy), _p(w), None, _p(dx), M, N, K, _st())
-        if ctx.needs_input_grad[1]:
-            dw = torch.zeros_like(w)
-            L.lotus_linear_wgrad_f32(_p(dy), _p(x), _p(dw), M, N, K, None, _st())
-        if ctx.has_b and ctx.needs_input_grad[2]:
-            db = torch.zeros(N, device=x.device, dtype=torch.float32)
-            L.lotus_colsum_f32(_p(dy), M, N, _p(db), _st())
+        wbuf, dw = _grad_buf(w, ctx.needs_input_grad[1])
+        if wbuf is not None:
+            L.lotus_linear_wgrad_f32(_p(dy), _p(x), _p(wbuf), M, N, K, None, _st())
+        bbuf, db = _grad_buf(ctx.bias, ctx.has_b and ctx.needs_input_grad[2])
+        if bbuf is not None:
+            L.lotus_colsum_f32(_p(dy), M, N, _p(bbuf), _st())
         return dx, dw, db, dres, None
 
 
@@ -140,6 +161,7 @@ class LayerNormFn(torch.autograd.Function):
         L.lotus_layernorm_fwd_f32(_p(x), 1, C, 0, _p(y), 1, C, 0, _p(residual), _p(g), _p(b), _p(mean), _p(rstd), rows, C,
                                   eps, _st())
         ctx.save_for_backward(x, g, mean, rstd)
+        ctx.beta = b
         ctx.has_res = residual is not None
         return y
 
@@ -150,9 +172,9 @@ class LayerNormFn(torch.autograd.Function):
         dy = _f32c(dy)
         rows, C = x.shape
         dx = torch.empty_like(x)
-        dg = torch.zeros(C, device=x.device, dtype=torch.float32)
-        db = torch.zeros_like(dg)
-        L.lotus_layernorm_bwd_f32(_p(dy), 1, C, 0, _p(x), 1, C, 0, _p(dx), 1, C, 0, _p(g), _p(mean), _p(rstd), _p(dg), _p(db),
+        gbuf, dg = _grad_buf(g, True)
+        bbuf, db = _grad_buf(ctx.beta, True)
+        L.lotus_layernorm_bwd_f32(_p(dy), 1, C, 0, _p(x), 1, C, 0, _p(dx), 1, C, 0, _p(g), _p(mean), _p(rstd), _p(gbuf), _p(bbuf),
                                   rows, C, 0, _st())
         return dx, dg, db, None, (dy if ctx.has_res else None)
 
@@ -190,6 +212,12 @@ class BatchNormActFn(torch.autograd.Function):
         db = torch.zeros_like(dg)
         L.lotus_batchnorm_bwd_f32(_p(dy), _p(x), rows, C, _p(g), _p(b), _p(mean), _p(rstd), _p(dx), _p(dg), _p(db),
                                   int(ctx.train), int(ctx.gelu), _st())
+        for param, d in ((g, dg), (b, db)):
+            s = _sink(param)
+            if s is not None:
+                L.lotus_pointwise_f32(_p(d), _p(s), _p(s), C, 4, 0.0, 0.0, 0, 0, _st())     # sink += batch sums
+        if _sink(g) is not None:
+            dg = db = None
         return dx, dg, db, None, None, None, None, None, None
 
 
@@ -213,6 +241,7 @@ class SubmConvFn(torch.autograd.Function):
         y = torch.empty((n, cout), device=x.device, dtype=torch.float32)
         L.lotus_subm_conv_fwd_f32(_p(x), _p(w), _p(b), _p(y), _p(nbr), nbr_stride, n, cin, cout, k3, _st())
         ctx.save_for_backward(x, w, nbr)
+        ctx.bias = b
         ctx.meta = (n, cin, cout, k3, nbr_stride, b is not None)
         return y
 
@@ -226,12 +255,12 @@ class SubmConvFn(torch.autograd.Function):
         if ctx.needs_input_grad[0]:
             dx = torch.empty_like(x)
             L.lotus_subm_conv_dgrad_f32(_p(dy), _p(w), _p(dx), _p(nbr), nbr_stride, n, cin, cout, k3, _st())
-        if ctx.needs_input_grad[1]:
-            dw = torch.zeros_like(w)
-            L.lotus_subm_conv_wgrad_f32(_p(dy), _p(x), _p(dw), _p(nbr), nbr_stride, n, cin, cout, k3, _st())
-        if has_b and ctx.needs_input_grad[2]:
-            db = torch.zeros(cout, device=x.device, dtype=torch.float32)
-            L.lotus_colsum_f32(_p(dy), n, cout, _p(db), _st())
+        wbuf, dw = _grad_buf(w, ctx.needs_input_grad[1])
+        if wbuf is not None:
+            L.lotus_subm_conv_wgrad_f32(_p(dy), _p(x), _p(wbuf), _p(nbr), nbr_stride, n, cin, cout, k3, _st())
+        bbuf, db = _grad_buf(ctx.bias, has_b and ctx.needs_input_grad[2])
+        if bbuf is not None:
+            L.lotus_colsum_f32(_p(dy), n, cout, _p(bbuf), _st())
         return dx, dw, db, None, None
 
 
@@ -275,6 +304,7 @@ class PatchAttnFn(torch.autograd.Function):
                                    attn_drop[0], attn_drop[1], attn_drop[2], st)
         ctx.save_for_backward(qkv, qg, kg, qh, kh, stats, out, lse, rpe_table, grid if rpe_table is not None else None)
         ctx.plan, ctx.H, ctx.qk_norm, ctx.attn_drop, ctx.pos_bnd = plan, H, qk_norm, attn_drop, pos_bnd
+        ctx.nb = (qb, kb)
         return out
 
     @staticmethod
@@ -304,12 +334,12 @@ class PatchAttnFn(torch.autograd.Function):
                                    _po(dqkv, 2 * C * 4), lddq, lddq, C3, ctx.attn_drop[0], ctx.attn_drop[1], ctx.attn_drop[2], st)
         dqg = dqb = dkg = dkb = None
         if ctx.qk_norm:
-            dqg = torch.zeros(D, device=dev, dtype=torch.float32)
-            dqb, dkg, dkb = torch.zeros_like(dqg), torch.zeros_like(dqg), torch.zeros_like(dqg)
+            (qgb, dqg), (qbb, dqb) = _grad_buf(qg, True), _grad_buf(ctx.nb[0], True)
+            (kgb, dkg), (kbb, dkb) = _grad_buf(kg, True), _grad_buf(ctx.nb[1], True)
             L.lotus_layernorm_bwd_f32(_p(dqh), 1, D, 0, _p(qkv), H, C3, D, _p(dqkv), H, C3, D, _p(qg), _p(stats[0]), _p(stats[1]),
-                                      _p(dqg), _p(dqb), N * H, D, 0, st)
+                                      _p(qgb), _p(qbb), N * H, D, 0, st)
             L.lotus_layernorm_bwd_f32(_p(dkh), 1, D, 0, _po(qkv, C * 4), H, C3, D, _po(dqkv, C * 4), H, C3, D, _p(kg),
-                                      _p(stats[2]), _p(stats[3]), _p(dkg), _p(dkb), N * H, D, 0, st)
+                                      _p(stats[2]), _p(stats[3]), _p(kgb), _p(kbb), N * H, D, 0, st)
         return dqkv, dqg, dqb, dkg, dkb, drpe, None, None, None, None, None, None
 
 
@@ -354,6 +384,7 @@ class CrossAttnFn(torch.autograd.Function):
                                    attn_drop[0], attn_drop[1], attn_drop[2], st)
         ctx.save_for_backward(q, kv, qg, kg, qh, kh, qs, ks, out, lse)
         ctx.geo, ctx.H, ctx.qk_norm, ctx.attn_drop = geo, H, qk_norm, attn_drop
+        ctx.nb = (qb, kb)
         return out
 
     @staticmethod
@@ -383,12 +414,12 @@ class CrossAttnFn(torch.autograd.Function):
                                    ctx.attn_drop[2], st)
         dqg = dqb = dkg = dkb = None
         if ctx.qk_norm:
-            dqg = torch.zeros(D, device=dev, dtype=torch.float32)
-            dqb, dkg, dkb = torch.zeros_like(dqg), torch.zeros_like(dqg), torch.zeros_like(dqg)
-            L.lotus_layernorm_bwd_f32(_p(dqh), 1, D, 0, _p(q), 1, D, 0, _p(dq), 1, D, 0, _p(qg), _p(qs[0]), _p(qs[1]), _p(dqg),
-                                      _p(dqb), N * H, D, 0, st)
+            (qgb, dqg), (qbb, dqb) = _grad_buf(qg, True), _grad_buf(ctx.nb[0], True)
+            (kgb, dkg), (kbb, dkb) = _grad_buf(kg, True), _grad_buf(ctx.nb[1], True)
+            L.lotus_layernorm_bwd_f32(_p(dqh), 1, D, 0, _p(q), 1, D, 0, _p(dq), 1, D, 0, _p(qg), _p(qs[0]), _p(qs[1]), _p(qgb),
+                                      _p(qbb), N * H, D, 0, st)
             L.lotus_layernorm_bwd_f32(_p(dkh), 1, D, 0, _p(kv), H, 2 * C, D, _p(dkv), H, 2 * C, D, _p(kg), _p(ks[0]), _p(ks[1]),
-                                      _p(dkg), _p(dkb), Lt * H, D, 0, st)
+                                      _p(kgb), _p(kbb), Lt * H, D, 0, st)
         return dq, dkv, dqg, dqb, dkg, dkb, None, None, None, None
 
 

@@ -1,0 +1,150 @@
+"""B200-native training step for the drop-in policy.
+
+What the reference does per step (train/train_simple_policy.py:202-243): forward, `backward()` with DDP
+bucketed all-reduces, `clip_grad_norm_`, a per-tensor Python AdamW loop over 421 tensors, `zero_grad`.
+Here: every parameter lives in ONE flat fp32 buffer and every gradient in another; backward kernels accumulate
+straight into the flat gradient buffer (ops.GRAD_SINK); data parallelism is ONE NCCL all-reduce over that buffer
+(the only collective — keysteps shard by batch); clip coefficient and the reference's AdamW
+arithmetic (train/optim/adamw.py:53-112) are fused into one kernel over the flat buffers.
+
+BatchNorm statistics stay per-rank: identical to the reference at world_size 1, and it keeps the
+gradient all-reduce the only collective.
+"""
+import math
+
+import torch
+import torch.distributed as dist
+
+from . import ops
+from .lib import load
+from .ops import _p, _st
+
+
+def warmup_cosine(step, warmup_step, tot_step, num_cycles=0.5):
+    """train/optim/sched.py:44-55"""
+    if step < warmup_step:
+        return step / warmup_step
+    progress = float(step - warmup_step) / float(max(1, tot_step - warmup_step))
+    return 0.5 * (1.0 + math.cos(math.pi * float(num_cycles) * 2.0 * progress))
+
+
+def get_lr_sched_decay_rate(global_step, warmup_steps, num_train_steps):
+    """train/optim/sched.py:95-113 (cosine)"""
+    return max(warmup_cosine(global_step, warmup_steps, num_train_steps), 1e-5)
+
+
+class FlatAdamW:
+    """The reference optimizer (optim/misc.py:13-55 grouping: names containing 'bias' are not decayed; optim/adamw.py)
+    over flat buffers.  `state_dict()` / `load_state_dict()` use the reference's per-parameter layout
+    (`{'state': {i: {'step','exp_avg','exp_avg_sq'}}, 'param_groups': [...]}`) so `train_state_latest.pt` round-trips."""
+
+    def __init__(self, model, lr=1e-4, betas=(0.9, 0.98), eps=1e-6, weight_decay=0.05, max_grad_norm=10.0):
+        named = [(n, p) for n, p in model.named_parameters() if p.requires_grad]
+        assert named and all(p.is_cuda and p.dtype == torch.float32 for _, p in named), "move the model to CUDA first"
+        dev = named[0][1].device
+        # group order of the reference: decayed tensors first, then the 'bias' tensors
+        decay = [(n, p) for n, p in named if "bias" not in n]
+        no_decay = [(n, p) for n, p in named if "bias" in n]
+        self.names = [n for n, _ in decay + no_decay]
+        self.params = [p for _, p in decay + no_decay]
+        self.group_sizes = (len(decay), len(no_decay))
+        sizes = [p.numel() for p in self.params]
+        total = sum(sizes)
+        self.flat_param = torch.empty(total, device=dev, dtype=torch.float32)
+        self.flat_grad = torch.zeros(total, device=dev, dtype=torch.float32)
+        self.exp_avg = torch.zeros(total, device=dev, dtype=torch.float32)
+        self.exp_avg_sq = torch.zeros(total, device=dev, dtype=torch.float32)
+        ends, off = [], 0
+        ops.GRAD_SINK.clear()
+        for p, n in zip(self.params, sizes):
+            view = self.flat_param[off: off + n].view_as(p)
+            view.copy_(p.data)
+            p.data = view                                   # parameters now alias the flat buffer
+            g = self.flat_grad[off: off + n].view_as(p)
+            p.grad = g                                      # reference-style access (`p.grad`) keeps working
+            ops.GRAD_SINK[p.data_ptr()] = g
+            off += n
+            ends.append(off)
+        self.seg_end = torch.tensor(ends, dtype=torch.int64, device=dev)
+        wd = [weight_decay] * len(decay) + [0.0] * len(no_decay)
+        self.seg_wd = torch.tensor(wd, dtype=torch.float32, device=dev)
+        self.lr, self.betas, self.eps, self.weight_decay, self.max_grad_norm = lr, betas, eps, weight_decay, max_grad_norm
+        self.step_count = 0
+        self.sumsq = torch.zeros(1, device=dev, dtype=torch.float32)
+        self.world = dist.get_world_size() if dist.is_available() and dist.is_initialized() else 1
+
+    def zero_grad(self):
+        self.flat_grad.zero_()
+
+    def all_reduce(self):
+        """the one collective of the path: sum of the flat gradient over ranks (mean applied inside the AdamW kernel)"""
+        if self.world > 1:
+            dist.all_reduce(self.flat_grad, op=dist.ReduceOp.SUM)
+
+    def step(self, lr=None):
+        L = load()
+        lr = self.lr if lr is None else lr
+        self.step_count += 1
+        st = _st()
+        n = self.flat_param.numel()
+        scale = 1.0 / self.world
+        if self.max_grad_norm and self.max_grad_norm > 0:
+            L.lotus_grad_sumsq_f32(_p(self.flat_grad), n, _p(self.sumsq), st)
+            sumsq = _p(self.sumsq)
+        else:
+            sumsq = None
+        L.lotus_adamw_step_f32(_p(self.flat_param), _p(self.flat_grad), _p(self.exp_avg), _p(self.exp_avg_sq), n,
+                               _p(self.seg_end), _p(self.seg_wd), len(self.params), lr, self.betas[0], self.betas[1],
+                               self.eps, self.step_count, 1, sumsq, float(self.max_grad_norm or 0.0), scale, st)
+
+    def grad_norm(self):
+        """global gradient norm of the last step (after the all-reduce mean) — one D2H read"""
+        return math.sqrt(float(self.sumsq.item())) / self.world
+
+    # ---- reference checkpoint layout (train/utils/save.py:38-45)
+    def state_dict(self):
+        state, off = {}, 0
+        for i, p in enumerate(self.params):
+            n = p.numel()
+            state[i] = {"step": self.step_count, "exp_avg": self.exp_avg[off: off + n].view_as(p).clone(),
+                        "exp_avg_sq": self.exp_avg_sq[off: off + n].view_as(p).clone()}
+            off += n
+        nd = self.group_sizes[0]
+        groups = [
+            {"lr": self.lr, "betas": self.betas, "eps": self.eps, "weight_decay": self.weight_decay, "correct_bias": True,
+             "params": list(range(nd))},
+            {"lr": self.lr, "betas": self.betas, "eps": self.eps, "weight_decay": 0.0, "correct_bias": True,
+             "params": list(range(nd, len(self.params)))},
+        ]
+        return {"state": state, "param_groups": groups}
+
+    def load_state_dict(self, sd):
+        off = 0
+        for i, p in enumerate(self.params):
+            n = p.numel()
+            if i in sd["state"]:
+                self.exp_avg[off: off + n].copy_(sd["state"][i]["exp_avg"].reshape(-1))
+                self.exp_avg_sq[off: off + n].copy_(sd["state"][i]["exp_avg_sq"].reshape(-1))
+                self.step_count = int(sd["state"][i]["step"])
+            off += n
+
+
+class TrainStep:
+    """one optimizer step of `train_simple_policy.py:202-243` on the calling rank"""
+
+    def __init__(self, model, learning_rate=1e-4, betas=(0.9, 0.98), weight_decay=0.05, grad_norm=10.0, warmup_steps=5000,
+                 num_train_steps=150000):
+        self.model = model
+        self.opt = FlatAdamW(model, learning_rate, betas, 1e-6, weight_decay, grad_norm)
+        self.learning_rate, self.warmup_steps, self.num_train_steps = learning_rate, warmup_steps, num_train_steps
+        self.global_step = 0
+
+    def __call__(self, batch):
+        self.opt.zero_grad()
+        _, losses = self.model(batch, compute_loss=True, compute_final_action=False)
+        losses["total"].backward()
+        self.opt.all_reduce()
+        self.global_step += 1
+        lr = self.learning_rate * get_lr_sched_decay_rate(self.global_step, self.warmup_steps, self.num_train_steps)
+        self.opt.step(lr)
+        return losses
