@@ -4,4 +4,4 @@ set -e
 cd "$(dirname "$0")/csrc"
 nvcc -gencode arch=compute_100a,code=sm_100a -lineinfo -O3 -std=c++17 \
      -Xcompiler -fPIC,-fvisibility=hidden -shared "$@" \
-     -o ../liblotus.so *.cu -lcuda
+     -o ../liblotus.so *.cu

@@ -1,0 +1,544 @@
+// bf16 tensor-core GEMM family for sm_100a: tcgen05.mma with TMEM accumulators, TMA-fed operands
+// (cp.async.bulk.tensor, SWIZZLE_128B), gathered operands staged by cp.async for the sparse conv.
+//
+//   D[M,N] (+)= sum_k A[m,k] * B[n,k]
+//
+// One 128 x BN output tile per CTA, BK = 64, 4-stage mbarrier pipeline, warp roles:
+//   warp 0 ........ TMA producer (one elected lane)
+//   warp 1 ........ TMEM allocator + tcgen05.mma issuer (one elected lane)
+//   warps 2-5 ..... (gather modes) cp.async producers of the gathered operand; then the epilogue:
+//                   tcgen05.ld of the accumulator -> bias / GELU / LeakyReLU / dropout / residual -> global
+//
+// Operand modes (reference contractions they serve are listed in include/lotus.h):
+//   OP_K_TMA ....... operand stored [rows][K] (K contiguous)         -> K-major smem tile via TMA
+//   OP_K_GATHER .... rows gathered through an index table (-1 -> 0)  -> K-major smem tile via cp.async
+//   OP_MN_TMA ...... operand stored [K][rows] (rows contiguous)      -> MN-major smem tile via TMA
+//   OP_MN_GATHER ... K-rows gathered through an index table          -> MN-major smem tile via cp.async
+#include "common.cuh"
+#include <cuda.h>
+
+namespace tc {
+
+constexpr int BM = 128;
+constexpr int BK = 64;            // 64 bf16 = 128 B = one SWIZZLE_128B span
+constexpr int STAGES = 4;
+constexpr int NUM_THREADS = 192;  // 6 warps
+constexpr int EPI_THREADS = 128;
+
+enum { OP_K_TMA = 0, OP_K_GATHER = 1, OP_MN_TMA = 2, OP_MN_GATHER = 3 };
+enum { ACT_NONE = 0, ACT_GELU = 1, ACT_LEAKY = 2 };
+
+struct GatherSpec {
+  const __nv_bfloat16* base;   // rows of `row_elems` bf16
+  const int32_t* idx;          // K-major gather: idx[(kb / kb_per_tap) * idx_stride + m]; MN gather: idx[k]
+  int64_t idx_stride;
+  int row_elems;               // elements per source row (Cin)
+  int kb_per_tap;              // k-blocks per kernel tap (Cin / 64)
+  int mirror_taps;             // K-major gather: use tap (ntaps-1-d) (conv dgrad)
+  int ntaps;
+};
+
+struct Params {
+  int M, N, K;                 // logical GEMM extents (K = reduction)
+  int a_mode, b_mode;
+  int kb_begin_stride;         // k-blocks per split (split-K over blockIdx.z)
+  GatherSpec ga, gb;
+  // epilogue
+  void* out;                   // [M, ldo] bf16 or fp32
+  void* out2;                  // optional second output (pre-activation), same dtype/ld as out
+  int64_t ldo;
+  int out_fp32;
+  int atomic;                  // fp32 atomicAdd accumulate (split-K)
+  const float* bias;           // [N] or null
+  const void* residual;        // [M, ldo] same dtype as out, or null
+  int act;
+  float drop_p;
+  uint64_t seed;
+  uint32_t drop_stream;
+};
+
+// ------------------------------------------------------------------------------------------------ PTX wrappers
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
+}
+__device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive_expect_tx(uint64_t* bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
+  asm volatile(
+      "{\n"
+      ".reg .pred p;\n"
+      "LAB_WAIT:\n"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
+      "@p bra DONE;\n"
+      "bra LAB_WAIT;\n"
+      "DONE:\n"
+      "}\n" ::"r"(smem_u32(bar)),
+      "r"(parity)
+      : "memory");
+}
+__device__ __forceinline__ void tma_load_2d(void* dst, const CUtensorMap* map, uint64_t* bar, int c0, int c1) {
+  asm volatile(
+      "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];" ::"r"(smem_u32(dst)),
+      "l"(map), "r"(smem_u32(bar)), "r"(c0), "r"(c1)
+      : "memory");
+}
+__device__ __forceinline__ void cp_async_16(void* dst, const void* src, bool valid) {
+  int sz = valid ? 16 : 0;  // src-size 0 -> zero fill
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(smem_u32(dst)), "l"(src), "r"(sz) : "memory");
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+template <int N>
+__device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory"); }
+__device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+
+__device__ __forceinline__ void tmem_alloc(uint32_t* dst_smem, uint32_t cols) {
+  asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(dst_smem)), "r"(cols) : "memory");
+  asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+}
+__device__ __forceinline__ void tmem_dealloc(uint32_t taddr, uint32_t cols) {
+  asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(taddr), "r"(cols) : "memory");
+}
+__device__ __forceinline__ void umma_bf16(uint32_t tmem_d, uint64_t desc_a, uint64_t desc_b, uint32_t idesc, uint32_t accumulate) {
+  asm volatile(
+      "{\n"
+      ".reg .pred p;\n"
+      "setp.ne.b32 p, %4, 0;\n"
+      "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n"
+      "}\n" ::"r"(tmem_d),
+      "l"(desc_a), "l"(desc_b), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+__device__ __forceinline__ void umma_commit(uint64_t* bar) {
+  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void tmem_ld_32x32b_x32(uint32_t taddr, uint32_t* r) {
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+      "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+      "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]), "=r"(r[9]),
+        "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]), "=r"(r[16]), "=r"(r[17]), "=r"(r[18]),
+        "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]), "=r"(r[24]), "=r"(r[25]), "=r"(r[26]), "=r"(r[27]),
+        "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
+      : "r"(taddr)
+      : "memory");
+}
+__device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
+
+// smem matrix descriptor (cute::UMMA::SmemDescriptor): SWIZZLE_128B, version 1
+__device__ __forceinline__ uint64_t make_desc(uint32_t saddr, uint32_t lbo_bytes, uint32_t sbo_bytes) {
+  uint64_t d = 0;
+  d |= (uint64_t)((saddr >> 4) & 0x3FFF);
+  d |= (uint64_t)((lbo_bytes >> 4) & 0x3FFF) << 16;
+  d |= (uint64_t)((sbo_bytes >> 4) & 0x3FFF) << 32;
+  d |= (uint64_t)1 << 46;   // version
+  d |= (uint64_t)2 << 61;   // SWIZZLE_128B
+  return d;
+}
+
+// ------------------------------------------------------------------------------------------------ kernel
+// smem per stage: A tile 128 x 64 bf16 = 16 KB, B tile BN x 64 bf16.
+// K-major tile:  row r (m or n) at r*128 B, 16-B chunk c at (c ^ (r & 7)) * 16          (SBO = 1024)
+// MN-major tile: block j = rows/64, k-row r at j*8192 + r*128 B, chunk c swizzled the same way
+//                (LBO = 8192 between 64-wide MN blocks, SBO = 1024 between 8-k-row groups)
+template <int BN>
+__global__ void __launch_bounds__(NUM_THREADS, 1)
+k_gemm_tc(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_b, const Params p) {
+  extern __shared__ __align__(1024) uint8_t smem_raw[];
+  constexpr uint32_t A_BYTES = BM * BK * 2, B_BYTES = BN * BK * 2;
+  uint8_t* smem = (uint8_t*)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
+  uint8_t* sA = smem;
+  uint8_t* sB = smem + STAGES * A_BYTES;
+  uint64_t* full = (uint64_t*)(sB + STAGES * B_BYTES);
+  uint64_t* empty = full + STAGES;
+  uint64_t* tmem_full = empty + STAGES;
+  uint32_t* tmem_slot = (uint32_t*)(tmem_full + 1);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int m0 = blockIdx.x * BM, n0 = blockIdx.y * BN;
+  const int num_kb_total = (p.K + BK - 1) / BK;
+  const int kb0 = blockIdx.z * p.kb_begin_stride;
+  const int kb1 = min(num_kb_total, kb0 + p.kb_begin_stride);
+  const int num_kb = kb1 - kb0;
+  const bool a_gather = (p.a_mode == OP_K_GATHER), b_gather = (p.b_mode == OP_MN_GATHER);
+  const bool a_mn = (p.a_mode >= OP_MN_TMA), b_mn = (p.b_mode >= OP_MN_TMA);
+
+  if (threadIdx.x == 0) {
+    uint32_t full_count = 1 + ((a_gather || b_gather) ? EPI_THREADS : 0);
+    for (int s = 0; s < STAGES; ++s) { mbar_init(&full[s], full_count); mbar_init(&empty[s], 1); }
+    mbar_init(tmem_full, 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  if (warp == 1) tmem_alloc(tmem_slot, BN);   // BN in {64,128,256}: power of two >= 32
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  if (num_kb > 0) {
+    if (warp == 0) {
+      // ===================== TMA producer =====================
+      if (lane == 0) {
+        uint32_t tx = (a_gather ? 0 : A_BYTES) + (b_gather ? 0 : B_BYTES);
+        for (int i = 0; i < num_kb; ++i) {
+          int s = i % STAGES, ph = (i / STAGES) & 1;
+          mbar_wait(&empty[s], ph ^ 1);
+          mbar_arrive_expect_tx(&full[s], tx);
+          int k0 = (kb0 + i) * BK;
+          if (!a_gather) {
+            if (!a_mn) tma_load_2d(sA + s * A_BYTES, &map_a, &full[s], k0, m0);
+            else { tma_load_2d(sA + s * A_BYTES, &map_a, &full[s], m0, k0); tma_load_2d(sA + s * A_BYTES + 8192, &map_a, &full[s], m0 + 64, k0); }
+          }
+          if (!b_gather) {
+            if (!b_mn) tma_load_2d(sB + s * B_BYTES, &map_b, &full[s], k0, n0);
+            else {
+#pragma unroll
+              for (int j = 0; j < BN / 64; ++j) tma_load_2d(sB + s * B_BYTES + j * 8192, &map_b, &full[s], n0 + j * 64, k0);
+            }
+          }
+        }
+      }
+    } else if (warp == 1) {
+      // ===================== MMA issuer =====================
+      if (lane == 0) {
+        uint32_t idesc = (1u << 4) | (1u << 7) | (1u << 10) | ((a_mn ? 1u : 0u) << 15) | ((b_mn ? 1u : 0u) << 16) |
+                         ((uint32_t)(BN >> 3) << 17) | ((uint32_t)(BM >> 4) << 24);
+        for (int i = 0; i < num_kb; ++i) {
+          int s = i % STAGES, ph = (i / STAGES) & 1;
+          mbar_wait(&full[s], ph);
+          tc_fence_after();
+          uint32_t a_addr = smem_u32(sA + s * A_BYTES), b_addr = smem_u32(sB + s * B_BYTES);
+#pragma unroll
+          for (int k = 0; k < BK / 16; ++k) {
+            // K-major: +32 B per 16-element K step inside the 128-B swizzle span; MN-major: +2 k-groups of 1024 B
+            uint64_t da = a_mn ? make_desc(a_addr + k * 2048, 8192, 1024) : make_desc(a_addr + k * 32, 16, 1024);
+            uint64_t db = b_mn ? make_desc(b_addr + k * 2048, 8192, 1024) : make_desc(b_addr + k * 32, 16, 1024);
+            umma_bf16(tmem_base, da, db, idesc, (i > 0 || k > 0) ? 1u : 0u);
+          }
+          umma_commit(&empty[s]);                       // frees the smem stage when these MMAs retire
+          if (i == num_kb - 1) umma_commit(tmem_full);  // accumulator complete
+        }
+      }
+    } else if (a_gather || b_gather) {
+      // ===================== cp.async gather producers (warps 2-5) =====================
+      const int t = threadIdx.x - 64;                   // 0..127
+      constexpr int LAG = 2;                            // stages in flight per thread before signalling
+      for (int i = 0; i < num_kb + LAG; ++i) {
+        if (i < num_kb) {
+          int s = i % STAGES, ph = (i / STAGES) & 1;
+          mbar_wait(&empty[s], ph ^ 1);
+          int kb = kb0 + i;
+          if (a_gather) {
+            // thread t stages row (m0 + t): 8 chunks of 16 B
+            int tap = kb / p.ga.kb_per_tap, c0 = (kb - tap * p.ga.kb_per_tap) * BK;
+            if (p.ga.mirror_taps) tap = p.ga.ntaps - 1 - tap;
+            int m = m0 + t;
+            int src_row = (m < p.M) ? p.ga.idx[(int64_t)tap * p.ga.idx_stride + m] : -1;
+            const __nv_bfloat16* src = p.ga.base + (int64_t)max(src_row, 0) * p.ga.row_elems + c0;
+            uint8_t* dst = sA + s * A_BYTES + t * 128;
+#pragma unroll
+            for (int c = 0; c < 8; ++c) cp_async_16(dst + ((c ^ (t & 7)) << 4), src + c * 8, src_row >= 0);
+          } else {
+            // MN-major gathered B (conv wgrad): k-row r = point (kb*64 + r); thread t stages chunks of rows r = t/2 .. (2 threads per row)
+            // BN/64 blocks of 64 ci: row bytes = BN*2; thread handles half of the row's chunks
+            int r = t >> 1, half = t & 1;
+            int kpt = kb * BK + r;
+            int src_row = (kpt < p.K) ? p.gb.idx[kpt] : -1;
+            const __nv_bfloat16* src = p.gb.base + (int64_t)max(src_row, 0) * p.gb.row_elems + n0;
+            constexpr int CH = BN / 8;                  // 16-B chunks per row
+#pragma unroll
+            for (int cc = 0; cc < CH / 2; ++cc) {
+              int c = half * (CH / 2) + cc;             // chunk within the BN-wide row
+              int blk = c >> 3, cw = c & 7;
+              bool ok = src_row >= 0 && (n0 + c * 8) < p.N;
+              cp_async_16(sB + s * B_BYTES + blk * 8192 + r * 128 + ((cw ^ (r & 7)) << 4), src + c * 8, ok);
+            }
+          }
+        }
+        cp_async_commit();
+        if (i >= LAG) {
+          cp_async_wait<LAG>();
+          fence_proxy_async();
+          mbar_arrive(&full[(i - LAG) % STAGES]);
+        }
+      }
+    }
+  }
+
+  // ===================== epilogue (warps 2-5) =====================
+  if (warp >= 2) {
+    const int lane_grp = warp & 3;                     // TMEM lanes [32*lane_grp, +32) are visible to this warp
+    const int row = m0 + lane_grp * 32 + lane;
+    if (num_kb > 0) {
+      mbar_wait(tmem_full, 0);
+      tc_fence_after();
+    }
+    const bool row_ok = row < p.M;
+    const float keep_scale = p.drop_p > 0.f ? 1.f / (1.f - p.drop_p) : 1.f;
+#pragma unroll 1
+    for (int c0 = 0; c0 < BN; c0 += 32) {
+      uint32_t v[32];
+      if (num_kb > 0) {
+        tmem_ld_32x32b_x32(tmem_base + ((uint32_t)(lane_grp * 32) << 16) + (uint32_t)c0, v);
+        tmem_ld_wait();
+      } else {
+#pragma unroll
+        for (int j = 0; j < 32; ++j) v[j] = 0u;
+      }
+      if (!row_ok) continue;
+      const int nbase = n0 + c0;
+      if (nbase >= p.N) continue;
+      const int64_t obase = (int64_t)row * p.ldo + nbase;
+      if (p.atomic) {
+        float* o = (float*)p.out + obase;
+#pragma unroll
+        for (int j = 0; j < 32; ++j)
+          if (nbase + j < p.N) atomicAdd(o + j, __uint_as_float(v[j]));
+        continue;
+      }
+      float f[32];
+#pragma unroll
+      for (int j = 0; j < 32; ++j) {
+        float x = __uint_as_float(v[j]);
+        if (p.bias && nbase + j < p.N) x += p.bias[nbase + j];
+        f[j] = x;
+      }
+      const bool full32 = (nbase + 32 <= p.N) && ((p.ldo & 7) == 0);
+      if (p.out2) {  // pre-activation copy
+        if (p.out_fp32) {
+          float* o = (float*)p.out2 + obase;
+#pragma unroll
+          for (int j = 0; j < 32; ++j) if (nbase + j < p.N) o[j] = f[j];
+        } else {
+          __nv_bfloat16* o = (__nv_bfloat16*)p.out2 + obase;
+          if (full32) {
+#pragma unroll
+            for (int j = 0; j < 32; j += 8) {
+              uint4 w;
+              __nv_bfloat162 h0 = __floats2bfloat162_rn(f[j], f[j + 1]), h1 = __floats2bfloat162_rn(f[j + 2], f[j + 3]);
+              __nv_bfloat162 h2 = __floats2bfloat162_rn(f[j + 4], f[j + 5]), h3 = __floats2bfloat162_rn(f[j + 6], f[j + 7]);
+              w.x = *(uint32_t*)&h0; w.y = *(uint32_t*)&h1; w.z = *(uint32_t*)&h2; w.w = *(uint32_t*)&h3;
+              *(uint4*)(o + j) = w;
+            }
+          } else {
+#pragma unroll
+            for (int j = 0; j < 32; ++j) if (nbase + j < p.N) o[j] = __float2bfloat16(f[j]);
+          }
+        }
+      }
+#pragma unroll
+      for (int j = 0; j < 32; ++j) {
+        float x = f[j];
+        if (p.act == ACT_GELU) x = gelu_f(x);
+        else if (p.act == ACT_LEAKY) x = x > 0.f ? x : 0.02f * x;
+        if (p.drop_p > 0.f) {
+          uint64_t o = (uint64_t)(obase + j);
+          x = dropout_keep(p.seed, p.drop_stream ^ (uint32_t)(o >> 32), (uint32_t)o, p.drop_p) ? x * keep_scale : 0.f;
+        }
+        f[j] = x;
+      }
+      if (p.out_fp32) {
+        float* o = (float*)p.out + obase;
+        const float* r = p.residual ? (const float*)p.residual + obase : nullptr;
+#pragma unroll
+        for (int j = 0; j < 32; ++j) if (nbase + j < p.N) o[j] = f[j] + (r ? r[j] : 0.f);
+      } else {
+        __nv_bfloat16* o = (__nv_bfloat16*)p.out + obase;
+        const __nv_bfloat16* r = p.residual ? (const __nv_bfloat16*)p.residual + obase : nullptr;
+        if (full32) {
+#pragma unroll
+          for (int j = 0; j < 32; j += 8) {
+            if (r) {
+              uint4 rv = *(const uint4*)(r + j);
+              const __nv_bfloat162* rh = (const __nv_bfloat162*)&rv;
+#pragma unroll
+              for (int q = 0; q < 4; ++q) { float2 t2 = __bfloat1622float2(rh[q]); f[j + 2 * q] += t2.x; f[j + 2 * q + 1] += t2.y; }
+            }
+            uint4 w;
+            __nv_bfloat162 h0 = __floats2bfloat162_rn(f[j], f[j + 1]), h1 = __floats2bfloat162_rn(f[j + 2], f[j + 3]);
+            __nv_bfloat162 h2 = __floats2bfloat162_rn(f[j + 4], f[j + 5]), h3 = __floats2bfloat162_rn(f[j + 6], f[j + 7]);
+            w.x = *(uint32_t*)&h0; w.y = *(uint32_t*)&h1; w.z = *(uint32_t*)&h2; w.w = *(uint32_t*)&h3;
+            *(uint4*)(o + j) = w;
+          }
+        } else {
+#pragma unroll
+          for (int j = 0; j < 32; ++j)
+            if (nbase + j < p.N) o[j] = __float2bfloat16(f[j] + (r ? __bfloat162float(r[j]) : 0.f));
+        }
+      }
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) tmem_dealloc(tmem_base, BN);
+}
+
+// ------------------------------------------------------------------------------------------------ host side
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
+                                  const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                  CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+static EncodeTiledFn get_encode() {
+  static EncodeTiledFn fn = nullptr;
+  if (!fn) {
+    void* ptr = nullptr;
+    cudaDriverEntryPointQueryResult qres;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &ptr, cudaEnableDefault, &qres) == cudaSuccess &&
+        qres == cudaDriverEntryPointSuccess)
+      fn = (EncodeTiledFn)ptr;
+  }
+  return fn;
+}
+
+// 2-D bf16 tensor [rows][cols] (cols contiguous, row stride ld elements); box = {box_cols (<=64), box_rows}
+static int make_map(CUtensorMap* m, const void* base, int64_t rows, int64_t cols, int64_t ld, int box_cols, int box_rows) {
+  EncodeTiledFn enc = get_encode();
+  if (!enc) { lotus_set_error("cuTensorMapEncodeTiled unavailable"); return 1; }
+  cuuint64_t dims[2] = {(cuuint64_t)cols, (cuuint64_t)rows};
+  cuuint64_t strides[1] = {(cuuint64_t)ld * 2};
+  cuuint32_t box[2] = {(cuuint32_t)box_cols, (cuuint32_t)box_rows};
+  cuuint32_t estr[2] = {1, 1};
+  CUresult r = enc(m, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, (void*)base, dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                   CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) {
+    lotus_set_error("cuTensorMapEncodeTiled failed (%d): base=%p rows=%lld cols=%lld ld=%lld box=%dx%d", (int)r, base, (long long)rows,
+                    (long long)cols, (long long)ld, box_cols, box_rows);
+    return 1;
+  }
+  return 0;
+}
+
+struct Operand {
+  int mode;
+  const __nv_bfloat16* ptr;   // TMA modes: matrix base
+  int64_t ld;                 // TMA modes: row stride in elements
+  GatherSpec g;               // gather modes
+};
+
+static int launch(const Operand& A, const Operand& B, Params p, int BN, int splits, cudaStream_t st) {
+  if (p.M <= 0 || p.N <= 0) return 0;
+  CUtensorMap ma, mb;
+  memset(&ma, 0, sizeof(ma));
+  memset(&mb, 0, sizeof(mb));
+  p.a_mode = A.mode; p.b_mode = B.mode; p.ga = A.g; p.gb = B.g;
+  int rc = 0;
+  if (A.mode == OP_K_TMA) rc = make_map(&ma, A.ptr, p.M, p.K, A.ld, BK, BM);
+  else if (A.mode == OP_MN_TMA) rc = make_map(&ma, A.ptr, p.K, p.M, A.ld, 64, BK);
+  if (rc) return rc;
+  if (B.mode == OP_K_TMA) rc = make_map(&mb, B.ptr, p.N, p.K, B.ld, BK, BN);
+  else if (B.mode == OP_MN_TMA) rc = make_map(&mb, B.ptr, p.K, p.N, B.ld, 64, BK);
+  if (rc) return rc;
+  int num_kb = (p.K + BK - 1) / BK;
+  splits = max(1, min(splits, num_kb));
+  int per = (num_kb + splits - 1) / splits;
+  splits = (num_kb + per - 1) / per;
+  p.kb_begin_stride = per;
+  dim3 grid((p.M + BM - 1) / BM, (p.N + BN - 1) / BN, splits);
+  size_t smem = (size_t)STAGES * (BM * BK * 2 + BN * BK * 2) + 256 + 1024;
+  cudaError_t e;
+  if (BN == 128) {
+    static bool set128 = false;
+    if (!set128) { cudaFuncSetAttribute(k_gemm_tc<128>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024); set128 = true; }
+    k_gemm_tc<128><<<grid, NUM_THREADS, smem, st>>>(ma, mb, p);
+  } else {
+    static bool set64 = false;
+    if (!set64) { cudaFuncSetAttribute(k_gemm_tc<64>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024); set64 = true; }
+    k_gemm_tc<64><<<grid, NUM_THREADS, smem, st>>>(ma, mb, p);
+  }
+  e = cudaGetLastError();
+  if (e != cudaSuccess) { lotus_set_error("gemm_tc launch: %s", cudaGetErrorString(e)); return 1; }
+  return 0;
+}
+
+static int pick_bn(int N) { return N <= 64 ? 64 : 128; }
+
+}  // namespace tc
+
+using tc::Operand;
+using tc::Params;
+
+static Params base_params(int M, int N, int K, void* out, int64_t ldo, int out_fp32) {
+  Params p;
+  memset(&p, 0, sizeof(p));
+  p.M = M; p.N = N; p.K = K; p.out = out; p.ldo = ldo; p.out_fp32 = out_fp32;
+  return p;
+}
+
+// y[M,N] = [residual +] drop(act(x[M,K] @ w[N,K]^T + bias)) ; x, w bf16 ; y (and residual, y_preact) bf16 or fp32
+LOTUS_API int lotus_linear_fwd_bf16(const void* x, const void* w, const float* bias, const void* residual, void* y,
+                                    void* y_preact, int M, int N, int K, int act, int out_fp32, float drop_p, uint64_t seed,
+                                    uint32_t drop_stream, void* stream_) {
+  LOTUS_CHECK_ARG(K % 8 == 0, "lotus_linear_fwd_bf16: K=%d must be a multiple of 8 (16-byte TMA rows)", K);
+  Params p = base_params(M, N, K, y, N, out_fp32);
+  p.out2 = y_preact; p.bias = bias; p.residual = residual; p.act = act; p.drop_p = drop_p; p.seed = seed; p.drop_stream = drop_stream;
+  Operand A{tc::OP_K_TMA, (const __nv_bfloat16*)x, K, {}}, B{tc::OP_K_TMA, (const __nv_bfloat16*)w, K, {}};
+  return tc::launch(A, B, p, tc::pick_bn(N), 1, (cudaStream_t)stream_);
+}
+
+// dx[M,K] = [residual +] dy[M,N] @ w[N,K]   using the pre-transposed weight wt[K,N] (bf16)
+LOTUS_API int lotus_linear_dgrad_bf16(const void* dy, const void* wt, const void* residual, void* dx, int M, int N, int K,
+                                      int out_fp32, void* stream_) {
+  LOTUS_CHECK_ARG(N % 8 == 0, "lotus_linear_dgrad_bf16: N=%d must be a multiple of 8", N);
+  Params p = base_params(M, K, N, dx, K, out_fp32);
+  p.residual = residual;
+  Operand A{tc::OP_K_TMA, (const __nv_bfloat16*)dy, N, {}}, B{tc::OP_K_TMA, (const __nv_bfloat16*)wt, N, {}};
+  return tc::launch(A, B, p, tc::pick_bn(K), 1, (cudaStream_t)stream_);
+}
+
+// dw[N,K] (fp32) += dy[M,N]^T @ x[M,K]   (both operands consumed MN-major straight from their row-major storage)
+LOTUS_API int lotus_linear_wgrad_bf16(const void* dy, const void* x, float* dw, int M, int N, int K, void* stream_) {
+  LOTUS_CHECK_ARG(N % 8 == 0 && K % 8 == 0, "lotus_linear_wgrad_bf16: N=%d, K=%d must be multiples of 8", N, K);
+  Params p = base_params(N, K, M, dw, K, 1);
+  p.atomic = 1;
+  Operand A{tc::OP_MN_TMA, (const __nv_bfloat16*)dy, N, {}}, B{tc::OP_MN_TMA, (const __nv_bfloat16*)x, K, {}};
+  int bn = tc::pick_bn(K);
+  int tiles = ((N + 127) / 128) * ((K + bn - 1) / bn);
+  int splits = max(1, (kNumSM * 2) / tiles);
+  return tc::launch(A, B, p, bn, splits, (cudaStream_t)stream_);
+}
+
+// submanifold conv forward: y[n,Cout] = sum_{d,ci} x[nbr[d][n], ci] * w[co, d, ci] (+bias); Cin % 64 == 0
+LOTUS_API int lotus_subm_conv_fwd_bf16(const void* x, const void* w, const float* bias, void* y, const int32_t* nbr,
+                                       int64_t nbr_stride, int n, int Cin, int Cout, int K3, int out_fp32, void* stream_) {
+  LOTUS_CHECK_ARG(Cin % 64 == 0, "lotus_subm_conv_fwd_bf16: Cin=%d must be a multiple of 64", Cin);
+  Params p = base_params(n, Cout, K3 * Cin, y, Cout, out_fp32);
+  p.bias = bias;
+  Operand A{tc::OP_K_GATHER, nullptr, 0, {(const __nv_bfloat16*)x, nbr, nbr_stride, Cin, Cin / 64, 0, K3}};
+  Operand B{tc::OP_K_TMA, (const __nv_bfloat16*)w, (int64_t)K3 * Cin, {}};
+  return tc::launch(A, B, p, tc::pick_bn(Cout), 1, (cudaStream_t)stream_);
+}
+
+// dgrad: dx[q,ci] = sum_{d,co} dy[nbr[K3-1-d][q], co] * w[co,d,ci], with wt = w re-laid out as [ci][d][co] (bf16)
+LOTUS_API int lotus_subm_conv_dgrad_bf16(const void* dy, const void* wt, void* dx, const int32_t* nbr, int64_t nbr_stride,
+                                         int n, int Cin, int Cout, int K3, int out_fp32, void* stream_) {
+  LOTUS_CHECK_ARG(Cout % 64 == 0, "lotus_subm_conv_dgrad_bf16: Cout=%d must be a multiple of 64", Cout);
+  Params p = base_params(n, Cin, K3 * Cout, dx, Cin, out_fp32);
+  Operand A{tc::OP_K_GATHER, nullptr, 0, {(const __nv_bfloat16*)dy, nbr, nbr_stride, Cout, Cout / 64, 1, K3}};
+  Operand B{tc::OP_K_TMA, (const __nv_bfloat16*)wt, (int64_t)K3 * Cout, {}};
+  return tc::launch(A, B, p, tc::pick_bn(Cin), 1, (cudaStream_t)stream_);
+}
+
+// wgrad: dw[co, d, ci] (fp32) += sum_p dy[p,co] * x[nbr[d][p], ci]
+LOTUS_API int lotus_subm_conv_wgrad_bf16(const void* dy, const void* x, float* dw, const int32_t* nbr, int64_t nbr_stride,
+                                         int n, int Cin, int Cout, int K3, void* stream_) {
+  LOTUS_CHECK_ARG(Cin % 64 == 0 && Cout % 8 == 0, "lotus_subm_conv_wgrad_bf16: Cin=%d (x64), Cout=%d (x8)", Cin, Cout);
+  int bn = tc::pick_bn(Cin);
+  int tiles = ((Cout + 127) / 128) * ((Cin + bn - 1) / bn);
+  int splits = max(1, (kNumSM * 2) / (tiles * K3) + 1);
+  for (int d = 0; d < K3; ++d) {
+    Params p = base_params(Cout, Cin, n, dw + (int64_t)d * Cin, (int64_t)K3 * Cin, 1);
+    p.atomic = 1;
+    Operand A{tc::OP_MN_TMA, (const __nv_bfloat16*)dy, Cout, {}};
+    Operand B{tc::OP_MN_GATHER, nullptr, 0, {(const __nv_bfloat16*)x, nbr + (int64_t)d * nbr_stride, 0, Cin, 0, 0, K3}};
+    int rc = tc::launch(A, B, p, bn, splits, (cudaStream_t)stream_);
+    if (rc) return rc;
+  }
+  return 0;
+}

@@ -1,0 +1,105 @@
+"""bf16 tensor-core (tcgen05) GEMM family vs an fp32 reference computed from the same bf16-rounded operands.
+Tolerance: bf16 inputs are exact in the reference, accumulation is fp32 on both sides -> 2e-3 relative covers
+the accumulation-order difference; 1e-2 where the stored output is itself rounded to bf16."""
+import ctypes
+
+import numpy as np
+import pytest
+import torch
+
+from conftest import pkg
+from oracle import lotus_oracle as O
+
+pytestmark = pytest.mark.gpu
+DEV = "cuda"
+
+
+def P(t):
+    return None if t is None else ctypes.c_void_p(t.data_ptr())
+
+
+def bf(t):
+    return t.to(torch.bfloat16)
+
+
+def rel(a, b):
+    a, b = a.double().cpu(), b.double().cpu()
+    return ((a - b).abs().max() / b.abs().max().clamp_min(1e-12)).item()
+
+
+@pytest.mark.parametrize("M,N,K", [(128, 128, 64), (256, 64, 128), (300, 90, 128), (4096, 256, 64), (1000, 217, 128),
+                                   (5000, 192, 64), (77, 768, 3072), (1344, 3072, 768), (33, 8, 72)])
+@pytest.mark.parametrize("variant", ["plain", "bias_gelu_res_bf16", "fp32_out_preact"])
+def test_linear_fwd_bf16(M, N, K, variant):
+    L = pkg("lib").load()
+    g = torch.Generator().manual_seed(M + N + K)
+    x = bf(torch.randn(M, K, generator=g)).to(DEV)
+    w = bf(torch.randn(N, K, generator=g) * K ** -0.5).to(DEV)
+    ref = x.float() @ w.float().t()
+    bias = res = pre = ref_pre = None
+    act, out_fp32 = 0, 0
+    if variant == "bias_gelu_res_bf16":
+        bias = torch.randn(N, generator=g).to(DEV)
+        res = bf(torch.randn(M, N, generator=g)).to(DEV)
+        act = 1
+        ref = torch.nn.functional.gelu(ref + bias) + res.float()
+    elif variant == "fp32_out_preact":
+        bias = torch.randn(N, generator=g).to(DEV)
+        out_fp32, act = 1, 2
+        pre = torch.empty(M, N, device=DEV, dtype=torch.float32)
+        ref_pre = ref + bias
+        ref = torch.nn.functional.leaky_relu(ref_pre, 0.02)
+    y = torch.full((M, N), float("nan"), device=DEV, dtype=torch.float32 if out_fp32 else torch.bfloat16)
+    L.lotus_linear_fwd_bf16(P(x), P(w), P(bias), P(res), P(y), P(pre), M, N, K, act, out_fp32, 0.0, 0, 0, None)
+    torch.cuda.synchronize()
+    assert rel(y.float(), ref) < (2e-3 if out_fp32 else 1e-2), rel(y.float(), ref)
+    if pre is not None:
+        assert rel(pre, ref_pre) < 2e-3
+
+
+@pytest.mark.parametrize("M,N,K", [(5000, 192, 64), (130, 64, 64), (4096, 256, 128), (131, 768, 3072), (70000, 64, 256)])
+def test_linear_dgrad_wgrad_bf16(M, N, K):
+    L = pkg("lib").load()
+    g = torch.Generator().manual_seed(M + N + K)
+    x = bf(torch.randn(M, K, generator=g)).to(DEV)
+    w = bf(torch.randn(N, K, generator=g) * K ** -0.5).to(DEV)
+    dy = bf(torch.randn(M, N, generator=g)).to(DEV)
+    wt = w.t().contiguous()
+    dx = torch.empty(M, K, device=DEV, dtype=torch.bfloat16)
+    L.lotus_linear_dgrad_bf16(P(dy), P(wt), None, P(dx), M, N, K, 0, None)
+    assert rel(dx.float(), dy.float() @ w.float()) < 1e-2
+    dw = torch.zeros(N, K, device=DEV, dtype=torch.float32)
+    L.lotus_linear_wgrad_bf16(P(dy), P(x), P(dw), M, N, K, None)
+    torch.cuda.synchronize()
+    assert rel(dw, dy.float().t() @ x.float()) < 2e-3, rel(dw, dy.float().t() @ x.float())
+
+
+@pytest.mark.parametrize("cin,cout", [(64, 64), (128, 128), (64, 192)])
+def test_subm_conv_bf16(cin, cout):
+    import test_gpu_parity as tp
+    L, tk = pkg("lib").load(), pkg("tokenizer")
+    sizes = [900, 333]
+    coord, grid = tp.lattice_clouds(sizes, 16, 9)
+    stg = tk.tokenize(coord.to(DEV), sizes, ["z"], [2], [128, 128], [[0], [0]], None)[0]
+    nbr = O.neighbor_table(O.offset2batch(torch.tensor(np.cumsum(sizes))), grid, 3)
+    n = sum(sizes)
+    g = torch.Generator().manual_seed(cin + cout)
+    x = bf(torch.randn(n, cin, generator=g))
+    w = bf(torch.randn(cout, 3, 3, 3, cin, generator=g) * (27 * cin) ** -0.5)
+    b = torch.randn(cout, generator=g)
+    dy = bf(torch.randn(n, cout, generator=g))
+    xr, wr = x.float().requires_grad_(True), w.float().requires_grad_(True)
+    yr = O.subm_conv(xr, nbr, wr, b)
+    yr.backward(dy.float())
+    xd, wd, dyd, bd = x.to(DEV), w.to(DEV), dy.to(DEV), b.to(DEV)
+    y = torch.empty(n, cout, device=DEV, dtype=torch.bfloat16)
+    L.lotus_subm_conv_fwd_bf16(P(xd), P(wd), P(bd), P(y), P(stg.nbr3), stg.stride_alloc, n, cin, cout, 27, 0, None)
+    assert rel(y.float(), yr) < 1e-2
+    wt = wd.reshape(cout, 27, cin).permute(2, 1, 0).contiguous()            # [ci][d][co]
+    dx = torch.empty(n, cin, device=DEV, dtype=torch.bfloat16)
+    L.lotus_subm_conv_dgrad_bf16(P(dyd), P(wt), P(dx), P(stg.nbr3), stg.stride_alloc, n, cin, cout, 27, 0, None)
+    assert rel(dx.float(), xr.grad) < 1e-2
+    dw = torch.zeros(cout, 27, cin, device=DEV, dtype=torch.float32)
+    L.lotus_subm_conv_wgrad_bf16(P(dyd), P(xd), P(dw), P(stg.nbr3), stg.stride_alloc, n, cin, cout, 27, None)
+    torch.cuda.synchronize()
+    assert rel(dw, wr.grad.reshape(cout, 27, cin)) < 2e-3

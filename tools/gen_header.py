@@ -39,6 +39,13 @@ DOC = {
     "lotus_subm_conv_fwd_f32": "Replaces spconv.SubMConv3d forward (stem k=5, CPE k=3): model.py:616-622,845-852.",
     "lotus_subm_conv_dgrad_f32": "Backward of SubMConv3d w.r.t. its input features.",
     "lotus_subm_conv_wgrad_f32": "Backward of SubMConv3d w.r.t. its weight (accumulates into dw).",
+    "lotus_linear_fwd_bf16": "bf16 tensor-core (tcgen05/TMEM/TMA) form of nn.Linear forward, same call sites as lotus_linear_fwd_f32; "
+                             "fused bias/GELU/LeakyReLU/dropout/residual epilogue, optional pre-activation copy.",
+    "lotus_linear_dgrad_bf16": "bf16 tensor-core backward of nn.Linear w.r.t. its input (uses the pre-transposed bf16 weight).",
+    "lotus_linear_wgrad_bf16": "bf16 tensor-core backward of nn.Linear w.r.t. its weight: split-K, MN-major operands read in place, fp32 accumulate.",
+    "lotus_subm_conv_fwd_bf16": "bf16 tensor-core implicit-GEMM form of spconv.SubMConv3d forward (CPE k=3): model.py:616-622; gathered operand staged by cp.async.",
+    "lotus_subm_conv_dgrad_bf16": "bf16 tensor-core backward of SubMConv3d w.r.t. its input features (mirrored taps).",
+    "lotus_subm_conv_wgrad_bf16": "bf16 tensor-core backward of SubMConv3d w.r.t. its weight (per-tap split-K, fp32 accumulate).",
     "lotus_layernorm_fwd_f32": "Replaces nn.LayerNorm (block norms, CPE norm, per-head q/k norm eps 1e-6): model.py:393-394,624,627,645; model_ca.py:43-44,114,124. "
                                "Rows are addressed as (r/inner)*outer_stride + (r%inner)*inner_stride so per-head norms read the packed qkv in place.",
     "lotus_layernorm_bwd_f32": "Backward of nn.LayerNorm (dx, and accumulated dgamma/dbeta).",
