@@ -75,23 +75,39 @@ KERNELS_PER_CALL = {  # kernels (not memsets) launched by one C-ABI call
 def kernels_of(name, args):
     if name == "lotus_subm_conv_wgrad_f32":
         return int(args[-2])           # one split-K GEMM per kernel offset (K3)
+    if name == "lotus_subm_conv_wgrad_bf16":
+        return int(args[8])
     if name == "lotus_neighbor_table":
         return 2 if int(args[8]) else 1
+    if name.startswith("lotus_batchnorm_fwd"):
+        return 5
+    if name.startswith("lotus_batchnorm_bwd"):
+        return 2
     return KERNELS_PER_CALL.get(name, 1)
 
 
-def algorithmic_work(name, a):
-    """-> (flops, bytes) of one call, from its arguments (fp32 path: 4-byte elements)."""
-    iv = lambda i: int(a[i].value if hasattr(a[i], "value") and not isinstance(a[i], int) else a[i])
-    if name == "lotus_linear_fwd_f32":
-        M, N, K = iv(5), iv(6), iv(7)
-        return 2.0 * M * N * K, 4.0 * (M * K + N * K + M * N)
-    if name in ("lotus_linear_dgrad_f32",):
-        M, N, K = iv(4), iv(5), iv(6)
-        return 2.0 * M * N * K, 4.0 * (M * K + N * K + M * N)
-    if name == "lotus_linear_wgrad_f32":
-        M, N, K = iv(3), iv(4), iv(5)
-        return 2.0 * M * N * K, 4.0 * (M * K + N * K + M * N)
+GEMM_ARGS = {  # name -> (index of M, N, K in the argument list, bytes per element)
+    "lotus_linear_fwd_f32": (5, 6, 7, 4), "lotus_linear_dgrad_f32": (4, 5, 6, 4), "lotus_linear_wgrad_f32": (3, 4, 5, 4),
+    "lotus_linear_fwd_bf16": (6, 7, 8, 2), "lotus_linear_dgrad_bf16": (4, 5, 6, 2), "lotus_linear_wgrad_bf16": (3, 4, 5, 2),
+}
+CONV_ARGS = {  # name -> index of n (then Cin, Cout, K3 follow)
+    "lotus_subm_conv_fwd_f32": 6, "lotus_subm_conv_dgrad_f32": 5, "lotus_subm_conv_wgrad_f32": 5,
+    "lotus_subm_conv_fwd_bf16": 6, "lotus_subm_conv_dgrad_bf16": 5, "lotus_subm_conv_wgrad_bf16": 5,
+}
+
+
+def algorithmic_work(name, a, conv_pairs):
+    """-> (flops, bytes) of one call, from its arguments"""
+    if name in GEMM_ARGS:
+        i, j, k, es = GEMM_ARGS[name]
+        M, N, K = int(a[i]), int(a[j]), int(a[k])
+        return 2.0 * M * N * K, float(es) * (M * K + N * K + M * N)
+    if name in CONV_ARGS:
+        i = CONV_ARGS[name]
+        n, cin, cout, k3 = int(a[i]), int(a[i + 1]), int(a[i + 2]), int(a[i + 3])
+        pairs = conv_pairs.get((n, k3), n * k3)            # actual (voxel, neighbour) pairs, not n * k^3
+        es = 2 if name.endswith("bf16") else 4
+        return 2.0 * pairs * cin * cout, float(es) * (pairs * cin + n * cout + k3 * cin * cout)
     return 0.0, 0.0
 
 
@@ -121,11 +137,7 @@ class CallProfiler:
         fam = {}
         for name, args, e0, e1 in self.records:
             ms = e0.elapsed_time(e1)
-            fl, by = algorithmic_work(name, args)
-            if name.startswith("lotus_subm_conv"):
-                n, cin, cout, k3 = [int(x) for x in args[-5:-1]] if name != "lotus_subm_conv_fwd_f32" else [int(x) for x in args[6:10]]
-                pairs = conv_pairs.get((n, k3), n * k3)
-                fl = 2.0 * pairs * cin * cout
+            fl, by = algorithmic_work(name, args, conv_pairs)
             d = fam.setdefault(name, {"ms": 0.0, "calls": 0, "flops": 0.0, "bytes": 0.0})
             d["ms"] += ms
             d["calls"] += 1
@@ -201,6 +213,8 @@ def main():
     ap.add_argument("--batch", type=int, default=32, help="keysteps per GPU per step (BASELINE configs[1]: 32)")
     ap.add_argument("--cpu-sample-batch", type=int, default=2)
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--precision", default="bf16", choices=["bf16", "fp32"],
+                    help="bf16: tensor-core mode (tcgen05 GEMMs, bf16 activations); fp32: validation-mode kernels")
     args = ap.parse_args()
     rank = int(os.environ.get("RANK", 0))
     world = int(os.environ.get("WORLD_SIZE", 1))
@@ -230,6 +244,7 @@ def main():
     cfg = cfgm.production_model_config()
     torch.manual_seed(2024 + rank)
     model = policy.build_parameter_shell(cfg).to(dev).train()
+    model.engine().precision = args.precision
     step_fn = trainer.TrainStep(model)
     nb = 4
     host = [pack_batch(syn.make_batch(seed=2024 + 100 * rank + i, batch_size=args.batch), pin=True) for i in range(nb)]
@@ -308,7 +323,8 @@ def main():
         ach = dom["flops"] / dom["calls"] / (per_launch_ms * 1e-3) / 1e12
         roof = {"bound": "tensor", "kernel": dom_name, "achieved": ach, "peak": tf_peak, "unit": "TFLOP/s", "frac": ach / tf_peak,
                 "traffic": None, "share_of_step": dom["ms"] / tot_ms, "launches_per_step": dom["calls"], "peak_source": peak_src,
-                "note": "fp32 SIMT validation-mode GEMM measured against the bf16 tensor peak"}
+                "note": ("tcgen05 bf16 kernel" if args.precision == "bf16" else "fp32 SIMT validation-mode GEMM") +
+                        " measured against the sustained bf16 tensor peak; achieved = algorithmic FLOPs / CUDA-event time"}
     else:
         roof = {"bound": "hbm", "kernel": dom_name, "achieved": None, "peak": hbm_peak, "unit": "GB/s", "frac": None, "traffic": None,
                 "share_of_step": dom["ms"] / tot_ms, "launches_per_step": dom["calls"], "peak_source": peak_src}
@@ -323,10 +339,11 @@ def main():
     line = {
         "metric": METRIC, "value": args.batch * world * args.steps / (ms * 1e-3), "unit": UNIT, "n_gpus": world, "steps": args.steps,
         "warmup": args.warmup, "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
-        "dtype": "fp32", "data": "synthetic",
+        "dtype": "bf16" if args.precision == "bf16" else "fp32", "data": "synthetic",
         "config": {"workload": workload, "global_batch": args.batch * world, "parallelism": f"dp{world}",
                    "l2": "4 rotating input batches; per-step working set (1.1 GB params+grads+Adam state, multi-GB activations) exceeds the 126 MB L2",
-                   "precision_note": "fp32 validation-mode kernels (parity-checked path)"},
+                   "precision_note": ("bf16 activations + tcgen05 tensor-core GEMM/conv, fp32 master weights/statistics/gradients"
+                                      if args.precision == "bf16" else "fp32 validation-mode kernels (1e-4 parity path)")},
         "clocks": clocks,
         "e2e": {"value": args.batch * world * args.steps / (ms_e2e * 1e-3), "unit": UNIT, "h2d_bytes_per_step": h2d_bytes(host[0]),
                 "d2h_bytes_per_step": 4 + 5 * 8 * 4 + 5 * (args.batch + 1) * 4 + 4, "ms_per_step": ms_e2e / args.steps},

@@ -1,10 +1,10 @@
-// fp32 validation-mode attention kernels (flash-branch semantics of the reference):
+// Attention kernels, fp32 math with fp32 or bf16 activations (flash-branch semantics of the reference):
 //   patch self-attention over the serialized patches  (SerializedAttention.forward, model.py:468-557)
 //   cross-attention of each cloud's points to its text tokens (CrossAttention.forward, model_ca.py:46-101)
 // The gather by `order[pad]` and the scatter by `unpad[inverse]` are fused into the loads / stores, the
 // optional relative-position bias (RPE, model.py:307-326) is added to the logits in-kernel, softmax is
 // online, attention dropout uses the counter-based mask (recomputed in the backward).
-// q and k arrive already per-head LayerNorm'ed (norm_act.cu).  The tensor-core path lives in attn_tc.cu.
+// q and k arrive already per-head LayerNorm'ed (norm_act.cu).
 #include "common.cuh"
 
 struct RpeArgs {
@@ -27,11 +27,11 @@ __device__ __forceinline__ float rpe_bias_ij(const RpeArgs& r, int H, int h, int
 }
 
 // ---------------------------------------------------------------------------------------------- patch fwd
-template <int DH>
+template <int DH, typename T>
 __global__ void __launch_bounds__(128) k_patch_attn_fwd(
-    const float* __restrict__ q, const float* __restrict__ k, const float* __restrict__ v, int64_t ldq, int64_t ldk,
+    const T* __restrict__ q, const T* __restrict__ k, const T* __restrict__ v, int64_t ldq, int64_t ldk,
     int64_t ldv, const int32_t* __restrict__ gather_idx, const int32_t* __restrict__ slot_of_point,
-    const int32_t* __restrict__ cu, int H, float scale, RpeArgs rpe, float* __restrict__ out, int64_t ldo,
+    const int32_t* __restrict__ cu, int H, float scale, RpeArgs rpe, T* __restrict__ out, int64_t ldo,
     float* __restrict__ lse, float drop_p, uint64_t seed, uint32_t layer_id) {
   extern __shared__ float sm[];
   int p = blockIdx.x, h = blockIdx.y;
@@ -43,8 +43,8 @@ __global__ void __launch_bounds__(128) k_patch_attn_fwd(
   for (int t = threadIdx.x; t < len * DH; t += blockDim.x) {
     int j = t / DH, d = t - j * DH;
     int pt = gather_idx[s0 + j];
-    Ks[t] = k[(int64_t)pt * ldk + h * DH + d];
-    Vs[t] = v[(int64_t)pt * ldv + h * DH + d];
+    Ks[t] = ldf(k, (int64_t)pt * ldk + h * DH + d);
+    Vs[t] = ldf(v, (int64_t)pt * ldv + h * DH + d);
   }
   for (int j = threadIdx.x; j < len; j += blockDim.x) Gs[j] = gather_idx[s0 + j];
   __syncthreads();
@@ -53,7 +53,7 @@ __global__ void __launch_bounds__(128) k_patch_attn_fwd(
     int pt = Gs[i];
     float qr[DH], o[DH];
 #pragma unroll
-    for (int d = 0; d < DH; ++d) { qr[d] = q[(int64_t)pt * ldq + h * DH + d] * scale; o[d] = 0.f; }
+    for (int d = 0; d < DH; ++d) { qr[d] = ldf(q, (int64_t)pt * ldq + h * DH + d) * scale; o[d] = 0.f; }
     float m = -INFINITY, l = 0.f;
     for (int j = 0; j < len; ++j) {
       float s = 0.f;
@@ -74,18 +74,18 @@ __global__ void __launch_bounds__(128) k_patch_attn_fwd(
     lse[(int64_t)(s0 + i) * H + h] = m + __logf(l);
     if (slot_of_point[pt] == s0 + i) {  // alias slots of a padded tail are queries whose output is discarded
 #pragma unroll
-      for (int d = 0; d < DH; ++d) out[(int64_t)pt * ldo + h * DH + d] = o[d] * inv;
+      for (int d = 0; d < DH; ++d) stf(out, (int64_t)pt * ldo + h * DH + d, o[d] * inv);
     }
   }
 }
 
 // ---------------------------------------------------------------------------------------------- patch bwd
-template <int DH>
+template <int DH, typename T>
 __global__ void __launch_bounds__(128) k_patch_attn_bwd(
-    const float* __restrict__ q, const float* __restrict__ k, const float* __restrict__ v, int64_t ldq, int64_t ldk,
+    const T* __restrict__ q, const T* __restrict__ k, const T* __restrict__ v, int64_t ldq, int64_t ldk,
     int64_t ldv, const int32_t* __restrict__ gather_idx, const int32_t* __restrict__ slot_of_point,
-    const int32_t* __restrict__ cu, int H, float scale, RpeArgs rpe, const float* __restrict__ out,
-    const float* __restrict__ dout, int64_t ldo, const float* __restrict__ lse, float* __restrict__ dq,
+    const int32_t* __restrict__ cu, int H, float scale, RpeArgs rpe, const T* __restrict__ out,
+    const T* __restrict__ dout, int64_t ldo, const float* __restrict__ lse, float* __restrict__ dq,
     float* __restrict__ dk, float* __restrict__ dv, int64_t lddq, int64_t lddk, int64_t lddv, float drop_p,
     uint64_t seed, uint32_t layer_id) {
   extern __shared__ float sm[];
@@ -105,10 +105,10 @@ __global__ void __launch_bounds__(128) k_patch_attn_bwd(
     int j = t / DH, d = t - j * DH;
     int pt = Gs[j];
     bool real = slot_of_point[pt] == s0 + j;
-    Qs[t] = q[(int64_t)pt * ldq + h * DH + d] * scale;
-    Ks[t] = k[(int64_t)pt * ldk + h * DH + d];
-    Vs[t] = v[(int64_t)pt * ldv + h * DH + d];
-    dOs[t] = real ? dout[(int64_t)pt * ldo + h * DH + d] : 0.f;
+    Qs[t] = ldf(q, (int64_t)pt * ldq + h * DH + d) * scale;
+    Ks[t] = ldf(k, (int64_t)pt * ldk + h * DH + d);
+    Vs[t] = ldf(v, (int64_t)pt * ldv + h * DH + d);
+    dOs[t] = real ? ldf(dout, (int64_t)pt * ldo + h * DH + d) : 0.f;
   }
   __syncthreads();
   for (int i = threadIdx.x; i < len; i += blockDim.x) {
@@ -116,7 +116,7 @@ __global__ void __launch_bounds__(128) k_patch_attn_bwd(
     float dsum = 0.f;
     if (slot_of_point[pt] == s0 + i) {
 #pragma unroll
-      for (int d = 0; d < DH; ++d) dsum = fmaf(dOs[i * DH + d], out[(int64_t)pt * ldo + h * DH + d], dsum);
+      for (int d = 0; d < DH; ++d) dsum = fmaf(dOs[i * DH + d], ldf(out, (int64_t)pt * ldo + h * DH + d), dsum);
     }
     Ds[i] = dsum;
     Ls[i] = lse[(int64_t)(s0 + i) * H + h];
@@ -197,27 +197,67 @@ __global__ void __launch_bounds__(128) k_patch_attn_bwd(
       return 2;                                                 \
   }
 
+template <typename T>
+static int patch_fwd_impl(const void* q, const void* k, const void* v, int64_t ldq, int64_t ldk, int64_t ldv,
+                          const int32_t* gather_idx, const int32_t* slot_of_point, const int32_t* cu_seqlens, int n_patches,
+                          int max_len, int H, int Dh, float scale, const float* rpe_table, const int32_t* grid, int pos_bnd,
+                          void* out, int64_t ldo, float* lse, float drop_p, uint64_t seed, uint32_t layer_id, void* stream_) {
+  cudaStream_t st = (cudaStream_t)stream_;
+  if (n_patches <= 0) return 0;
+  size_t smem = (size_t)max_len * Dh * 8 + (size_t)max_len * 4;
+  LOTUS_CHECK_ARG(smem <= 200 * 1024, "lotus_patch_attn_fwd: patch %d x head_dim %d exceeds shared memory", max_len, Dh);
+  RpeArgs rpe{rpe_table, grid, pos_bnd, nullptr};
+  DISPATCH_DH(Dh, {
+    LOTUS_CUDA_CALL(cudaFuncSetAttribute(k_patch_attn_fwd<DH, T>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+    k_patch_attn_fwd<DH, T><<<dim3(n_patches, H), 128, smem, st>>>((const T*)q, (const T*)k, (const T*)v, ldq, ldk, ldv, gather_idx,
+                                                                   slot_of_point, cu_seqlens, H, scale, rpe, (T*)out, ldo, lse,
+                                                                   drop_p, seed, layer_id);
+  });
+  LOTUS_CUDA_OK();
+  return 0;
+}
 LOTUS_API int lotus_patch_attn_fwd_f32(const float* q, const float* k, const float* v, int64_t ldq, int64_t ldk,
                                        int64_t ldv, const int32_t* gather_idx, const int32_t* slot_of_point,
                                        const int32_t* cu_seqlens, int n_patches, int max_len, int H, int Dh, float scale,
                                        const float* rpe_table, const int32_t* grid, int pos_bnd, float* out,
                                        int64_t ldo, float* lse, float drop_p, uint64_t seed, uint32_t layer_id,
                                        void* stream_) {
+  return patch_fwd_impl<float>(q, k, v, ldq, ldk, ldv, gather_idx, slot_of_point, cu_seqlens, n_patches, max_len, H, Dh, scale,
+                               rpe_table, grid, pos_bnd, out, ldo, lse, drop_p, seed, layer_id, stream_);
+}
+// q, k, v, out bf16 (fp32 softmax / accumulation inside)
+LOTUS_API int lotus_patch_attn_fwd_bf16(const void* q, const void* k, const void* v, int64_t ldq, int64_t ldk, int64_t ldv,
+                                        const int32_t* gather_idx, const int32_t* slot_of_point, const int32_t* cu_seqlens,
+                                        int n_patches, int max_len, int H, int Dh, float scale, const float* rpe_table,
+                                        const int32_t* grid, int pos_bnd, void* out, int64_t ldo, float* lse, float drop_p,
+                                        uint64_t seed, uint32_t layer_id, void* stream_) {
+  return patch_fwd_impl<bf16_t>(q, k, v, ldq, ldk, ldv, gather_idx, slot_of_point, cu_seqlens, n_patches, max_len, H, Dh, scale,
+                                rpe_table, grid, pos_bnd, out, ldo, lse, drop_p, seed, layer_id, stream_);
+}
+
+// dq/dk/dv (fp32) are ACCUMULATED with atomics (alias slots add a second contribution): zero them first.
+template <typename T>
+static int patch_bwd_impl(const void* q, const void* k, const void* v, int64_t ldq, int64_t ldk, int64_t ldv,
+                          const int32_t* gather_idx, const int32_t* slot_of_point, const int32_t* cu_seqlens, int n_patches,
+                          int max_len, int H, int Dh, float scale, const float* rpe_table, const int32_t* grid, int pos_bnd,
+                          float* drpe_table, const void* out, const void* dout, int64_t ldo, const float* lse, float* dq,
+                          float* dk, float* dv, int64_t lddq, int64_t lddk, int64_t lddv, float drop_p, uint64_t seed,
+                          uint32_t layer_id, void* stream_) {
   cudaStream_t st = (cudaStream_t)stream_;
   if (n_patches <= 0) return 0;
-  size_t smem = (size_t)max_len * Dh * 8 + (size_t)max_len * 4;
-  LOTUS_CHECK_ARG(smem <= 200 * 1024, "lotus_patch_attn_fwd_f32: patch %d x head_dim %d exceeds shared memory", max_len, Dh);
-  RpeArgs rpe{rpe_table, grid, pos_bnd, nullptr};
+  size_t smem = (size_t)max_len * Dh * 16 + (size_t)max_len * 12;
+  LOTUS_CHECK_ARG(smem <= 200 * 1024, "lotus_patch_attn_bwd: patch %d x head_dim %d exceeds shared memory", max_len, Dh);
+  RpeArgs rpe{rpe_table, grid, pos_bnd, drpe_table};
   DISPATCH_DH(Dh, {
-    LOTUS_CUDA_CALL(cudaFuncSetAttribute(k_patch_attn_fwd<DH>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
-    k_patch_attn_fwd<DH><<<dim3(n_patches, H), 128, smem, st>>>(q, k, v, ldq, ldk, ldv, gather_idx, slot_of_point,
-                                                                cu_seqlens, H, scale, rpe, out, ldo, lse, drop_p, seed, layer_id);
+    LOTUS_CUDA_CALL(cudaFuncSetAttribute(k_patch_attn_bwd<DH, T>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+    k_patch_attn_bwd<DH, T><<<dim3(n_patches, H), 128, smem, st>>>((const T*)q, (const T*)k, (const T*)v, ldq, ldk, ldv, gather_idx,
+                                                                   slot_of_point, cu_seqlens, H, scale, rpe, (const T*)out,
+                                                                   (const T*)dout, ldo, lse, dq, dk, dv, lddq, lddk, lddv, drop_p,
+                                                                   seed, layer_id);
   });
   LOTUS_CUDA_OK();
   return 0;
 }
-
-// dq/dk/dv are ACCUMULATED with atomics (alias slots add a second contribution): zero them first.
 LOTUS_API int lotus_patch_attn_bwd_f32(const float* q, const float* k, const float* v, int64_t ldq, int64_t ldk,
                                        int64_t ldv, const int32_t* gather_idx, const int32_t* slot_of_point,
                                        const int32_t* cu_seqlens, int n_patches, int max_len, int H, int Dh, float scale,
@@ -225,27 +265,29 @@ LOTUS_API int lotus_patch_attn_bwd_f32(const float* q, const float* k, const flo
                                        const float* out, const float* dout, int64_t ldo, const float* lse, float* dq,
                                        float* dk, float* dv, int64_t lddq, int64_t lddk, int64_t lddv, float drop_p,
                                        uint64_t seed, uint32_t layer_id, void* stream_) {
-  cudaStream_t st = (cudaStream_t)stream_;
-  if (n_patches <= 0) return 0;
-  size_t smem = (size_t)max_len * Dh * 16 + (size_t)max_len * 12;
-  LOTUS_CHECK_ARG(smem <= 200 * 1024, "lotus_patch_attn_bwd_f32: patch %d x head_dim %d exceeds shared memory", max_len, Dh);
-  RpeArgs rpe{rpe_table, grid, pos_bnd, drpe_table};
-  DISPATCH_DH(Dh, {
-    LOTUS_CUDA_CALL(cudaFuncSetAttribute(k_patch_attn_bwd<DH>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
-    k_patch_attn_bwd<DH><<<dim3(n_patches, H), 128, smem, st>>>(q, k, v, ldq, ldk, ldv, gather_idx, slot_of_point, cu_seqlens,
-                                                                H, scale, rpe, out, dout, ldo, lse, dq, dk, dv, lddq, lddk,
-                                                                lddv, drop_p, seed, layer_id);
-  });
-  LOTUS_CUDA_OK();
-  return 0;
+  return patch_bwd_impl<float>(q, k, v, ldq, ldk, ldv, gather_idx, slot_of_point, cu_seqlens, n_patches, max_len, H, Dh, scale,
+                               rpe_table, grid, pos_bnd, drpe_table, out, dout, ldo, lse, dq, dk, dv, lddq, lddk, lddv, drop_p, seed,
+                               layer_id, stream_);
+}
+// q, k, v, out, dout bf16; dq, dk, dv fp32 (accumulated)
+LOTUS_API int lotus_patch_attn_bwd_bf16(const void* q, const void* k, const void* v, int64_t ldq, int64_t ldk, int64_t ldv,
+                                        const int32_t* gather_idx, const int32_t* slot_of_point, const int32_t* cu_seqlens,
+                                        int n_patches, int max_len, int H, int Dh, float scale, const float* rpe_table,
+                                        const int32_t* grid, int pos_bnd, float* drpe_table, const void* out, const void* dout,
+                                        int64_t ldo, const float* lse, float* dq, float* dk, float* dv, int64_t lddq,
+                                        int64_t lddk, int64_t lddv, float drop_p, uint64_t seed, uint32_t layer_id,
+                                        void* stream_) {
+  return patch_bwd_impl<bf16_t>(q, k, v, ldq, ldk, ldv, gather_idx, slot_of_point, cu_seqlens, n_patches, max_len, H, Dh, scale,
+                                rpe_table, grid, pos_bnd, drpe_table, out, dout, ldo, lse, dq, dk, dv, lddq, lddk, lddv, drop_p,
+                                seed, layer_id, stream_);
 }
 
 // ---------------------------------------------------------------------------------------------- cross attention
-template <int DH>
+template <int DH, typename T>
 __global__ void __launch_bounds__(128) k_cross_attn_fwd(
-    const float* __restrict__ q, int64_t ldq, const float* __restrict__ k, const float* __restrict__ v, int64_t ldk,
+    const T* __restrict__ q, int64_t ldq, const T* __restrict__ k, const T* __restrict__ v, int64_t ldk,
     int64_t ldv, const int32_t* __restrict__ pt_off, const int32_t* __restrict__ tok_off, int H, float scale,
-    float* __restrict__ out, int64_t ldo, float* __restrict__ lse, float drop_p, uint64_t seed, uint32_t layer_id) {
+    T* __restrict__ out, int64_t ldo, float* __restrict__ lse, float drop_p, uint64_t seed, uint32_t layer_id) {
   extern __shared__ float sm[];
   int b = blockIdx.y, h = blockIdx.z;
   int ps = pt_off[b], pn = pt_off[b + 1] - ps;
@@ -255,8 +297,8 @@ __global__ void __launch_bounds__(128) k_cross_attn_fwd(
   float* Vs = Ks + (size_t)L * DH;
   for (int t = threadIdx.x; t < L * DH; t += blockDim.x) {
     int j = t / DH, d = t - j * DH;
-    Ks[t] = k[(int64_t)(ts + j) * ldk + h * DH + d];
-    Vs[t] = v[(int64_t)(ts + j) * ldv + h * DH + d];
+    Ks[t] = ldf(k, (int64_t)(ts + j) * ldk + h * DH + d);
+    Vs[t] = ldf(v, (int64_t)(ts + j) * ldv + h * DH + d);
   }
   __syncthreads();
   int i = blockIdx.x * blockDim.x + threadIdx.x;
@@ -264,7 +306,7 @@ __global__ void __launch_bounds__(128) k_cross_attn_fwd(
   int pt = ps + i;
   float qr[DH], o[DH];
 #pragma unroll
-  for (int d = 0; d < DH; ++d) { qr[d] = q[(int64_t)pt * ldq + h * DH + d] * scale; o[d] = 0.f; }
+  for (int d = 0; d < DH; ++d) { qr[d] = ldf(q, (int64_t)pt * ldq + h * DH + d) * scale; o[d] = 0.f; }
   float m = -INFINITY, l = 0.f;
   float keep_scale = drop_p > 0.f ? 1.f / (1.f - drop_p) : 1.f;
   for (int j = 0; j < L; ++j) {
@@ -283,14 +325,14 @@ __global__ void __launch_bounds__(128) k_cross_attn_fwd(
   float inv = L > 0 ? 1.f / l : 0.f;
   lse[(int64_t)pt * H + h] = m + __logf(l);
 #pragma unroll
-  for (int d = 0; d < DH; ++d) out[(int64_t)pt * ldo + h * DH + d] = o[d] * inv;
+  for (int d = 0; d < DH; ++d) stf(out, (int64_t)pt * ldo + h * DH + d, o[d] * inv);
 }
 
-template <int DH>
+template <int DH, typename T>
 __global__ void __launch_bounds__(128) k_cross_attn_bwd(
-    const float* __restrict__ q, int64_t ldq, const float* __restrict__ k, const float* __restrict__ v, int64_t ldk,
+    const T* __restrict__ q, int64_t ldq, const T* __restrict__ k, const T* __restrict__ v, int64_t ldk,
     int64_t ldv, const int32_t* __restrict__ pt_off, const int32_t* __restrict__ tok_off, int H, float scale,
-    const float* __restrict__ out, const float* __restrict__ dout, int64_t ldo, const float* __restrict__ lse,
+    const T* __restrict__ out, const T* __restrict__ dout, int64_t ldo, const float* __restrict__ lse,
     float* __restrict__ dq, int64_t lddq, float* __restrict__ dk, float* __restrict__ dv, int64_t lddk, int64_t lddv,
     float drop_p, uint64_t seed, uint32_t layer_id) {
   extern __shared__ float sm[];
@@ -308,14 +350,14 @@ __global__ void __launch_bounds__(128) k_cross_attn_bwd(
   float* Ds = Ls + 128;                     // [128]
   for (int t = threadIdx.x; t < L * DH; t += blockDim.x) {
     int j = t / DH, d = t - j * DH;
-    Ks[t] = k[(int64_t)(ts + j) * ldk + h * DH + d];
-    Vs[t] = v[(int64_t)(ts + j) * ldv + h * DH + d];
+    Ks[t] = ldf(k, (int64_t)(ts + j) * ldk + h * DH + d);
+    Vs[t] = ldf(v, (int64_t)(ts + j) * ldv + h * DH + d);
   }
   for (int t = threadIdx.x; t < cn * DH; t += blockDim.x) {
     int i = t / DH, d = t - i * DH;
     int pt = ps + i0 + i;
-    Qs[t] = q[(int64_t)pt * ldq + h * DH + d] * scale;
-    dOs[t] = dout[(int64_t)pt * ldo + h * DH + d];
+    Qs[t] = ldf(q, (int64_t)pt * ldq + h * DH + d) * scale;
+    dOs[t] = ldf(dout, (int64_t)pt * ldo + h * DH + d);
   }
   __syncthreads();
   float keep_scale = drop_p > 0.f ? 1.f / (1.f - drop_p) : 1.f;
@@ -325,7 +367,7 @@ __global__ void __launch_bounds__(128) k_cross_attn_bwd(
     int pt = ps + i0 + i;
     float di = 0.f;
 #pragma unroll
-    for (int d = 0; d < DH; ++d) di = fmaf(dOs[i * DH + d], out[(int64_t)pt * ldo + h * DH + d], di);
+    for (int d = 0; d < DH; ++d) di = fmaf(dOs[i * DH + d], ldf(out, (int64_t)pt * ldo + h * DH + d), di);
     Ds[i] = di;
     Ls[i] = lse[(int64_t)pt * H + h];
     // dQ_i
@@ -374,40 +416,75 @@ __global__ void __launch_bounds__(128) k_cross_attn_bwd(
   }
 }
 
-LOTUS_API int lotus_cross_attn_fwd_f32(const float* q, int64_t ldq, const float* k, const float* v, int64_t ldk,
-                                       int64_t ldv, const int32_t* pt_off, const int32_t* tok_off, int B, int max_points,
-                                       int max_tokens, int H, int Dh, float scale, float* out, int64_t ldo, float* lse,
-                                       float drop_p, uint64_t seed, uint32_t layer_id, void* stream_) {
+template <typename T>
+static int cross_fwd_impl(const void* q, int64_t ldq, const void* k, const void* v, int64_t ldk, int64_t ldv,
+                          const int32_t* pt_off, const int32_t* tok_off, int B, int max_points, int max_tokens, int H, int Dh,
+                          float scale, void* out, int64_t ldo, float* lse, float drop_p, uint64_t seed, uint32_t layer_id,
+                          void* stream_) {
   cudaStream_t st = (cudaStream_t)stream_;
   if (B <= 0 || max_points <= 0) return 0;
   size_t smem = (size_t)max_tokens * Dh * 8;
-  LOTUS_CHECK_ARG(smem <= 200 * 1024, "lotus_cross_attn_fwd_f32: %d tokens x head_dim %d exceeds shared memory", max_tokens, Dh);
+  LOTUS_CHECK_ARG(smem <= 200 * 1024, "lotus_cross_attn_fwd: %d tokens x head_dim %d exceeds shared memory", max_tokens, Dh);
+  LOTUS_CHECK_ARG(max_tokens <= 128, "lotus_cross_attn_fwd: at most 128 context tokens per cloud (got %d)", max_tokens);
   dim3 grid(ceil_div(max_points, 128), B, H);
   DISPATCH_DH(Dh, {
-    LOTUS_CUDA_CALL(cudaFuncSetAttribute(k_cross_attn_fwd<DH>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
-    k_cross_attn_fwd<DH><<<grid, 128, smem, st>>>(q, ldq, k, v, ldk, ldv, pt_off, tok_off, H, scale, out, ldo, lse, drop_p, seed, layer_id);
+    LOTUS_CUDA_CALL(cudaFuncSetAttribute(k_cross_attn_fwd<DH, T>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+    k_cross_attn_fwd<DH, T><<<grid, 128, smem, st>>>((const T*)q, ldq, (const T*)k, (const T*)v, ldk, ldv, pt_off, tok_off, H, scale,
+                                                     (T*)out, ldo, lse, drop_p, seed, layer_id);
   });
   LOTUS_CUDA_OK();
   return 0;
 }
+LOTUS_API int lotus_cross_attn_fwd_f32(const float* q, int64_t ldq, const float* k, const float* v, int64_t ldk,
+                                       int64_t ldv, const int32_t* pt_off, const int32_t* tok_off, int B, int max_points,
+                                       int max_tokens, int H, int Dh, float scale, float* out, int64_t ldo, float* lse,
+                                       float drop_p, uint64_t seed, uint32_t layer_id, void* stream_) {
+  return cross_fwd_impl<float>(q, ldq, k, v, ldk, ldv, pt_off, tok_off, B, max_points, max_tokens, H, Dh, scale, out, ldo, lse,
+                               drop_p, seed, layer_id, stream_);
+}
+LOTUS_API int lotus_cross_attn_fwd_bf16(const void* q, int64_t ldq, const void* k, const void* v, int64_t ldk, int64_t ldv,
+                                        const int32_t* pt_off, const int32_t* tok_off, int B, int max_points, int max_tokens,
+                                        int H, int Dh, float scale, void* out, int64_t ldo, float* lse, float drop_p,
+                                        uint64_t seed, uint32_t layer_id, void* stream_) {
+  return cross_fwd_impl<bf16_t>(q, ldq, k, v, ldk, ldv, pt_off, tok_off, B, max_points, max_tokens, H, Dh, scale, out, ldo, lse,
+                                drop_p, seed, layer_id, stream_);
+}
 
-// dq is written; dk/dv are ACCUMULATED with atomics: zero them first.
+// dq (fp32) is written; dk/dv (fp32) are ACCUMULATED with atomics: zero them first.
+template <typename T>
+static int cross_bwd_impl(const void* q, int64_t ldq, const void* k, const void* v, int64_t ldk, int64_t ldv,
+                          const int32_t* pt_off, const int32_t* tok_off, int B, int max_points, int max_tokens, int H, int Dh,
+                          float scale, const void* out, const void* dout, int64_t ldo, const float* lse, float* dq,
+                          int64_t lddq, float* dk, float* dv, int64_t lddk, int64_t lddv, float drop_p, uint64_t seed,
+                          uint32_t layer_id, void* stream_) {
+  cudaStream_t st = (cudaStream_t)stream_;
+  if (B <= 0 || max_points <= 0) return 0;
+  size_t smem = (size_t)max_tokens * Dh * 8 + (size_t)128 * Dh * 8 + 1024;
+  LOTUS_CHECK_ARG(smem <= 200 * 1024, "lotus_cross_attn_bwd: %d tokens x head_dim %d exceeds shared memory", max_tokens, Dh);
+  dim3 grid(ceil_div(max_points, 128), B, H);
+  DISPATCH_DH(Dh, {
+    LOTUS_CUDA_CALL(cudaFuncSetAttribute(k_cross_attn_bwd<DH, T>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+    k_cross_attn_bwd<DH, T><<<grid, 128, smem, st>>>((const T*)q, ldq, (const T*)k, (const T*)v, ldk, ldv, pt_off, tok_off, H, scale,
+                                                     (const T*)out, (const T*)dout, ldo, lse, dq, lddq, dk, dv, lddk, lddv, drop_p,
+                                                     seed, layer_id);
+  });
+  LOTUS_CUDA_OK();
+  return 0;
+}
 LOTUS_API int lotus_cross_attn_bwd_f32(const float* q, int64_t ldq, const float* k, const float* v, int64_t ldk,
                                        int64_t ldv, const int32_t* pt_off, const int32_t* tok_off, int B, int max_points,
                                        int max_tokens, int H, int Dh, float scale, const float* out, const float* dout,
                                        int64_t ldo, const float* lse, float* dq, int64_t lddq, float* dk, float* dv,
                                        int64_t lddk, int64_t lddv, float drop_p, uint64_t seed, uint32_t layer_id,
                                        void* stream_) {
-  cudaStream_t st = (cudaStream_t)stream_;
-  if (B <= 0 || max_points <= 0) return 0;
-  size_t smem = (size_t)max_tokens * Dh * 8 + (size_t)128 * Dh * 8 + 1024;
-  LOTUS_CHECK_ARG(smem <= 200 * 1024, "lotus_cross_attn_bwd_f32: %d tokens x head_dim %d exceeds shared memory", max_tokens, Dh);
-  dim3 grid(ceil_div(max_points, 128), B, H);
-  DISPATCH_DH(Dh, {
-    LOTUS_CUDA_CALL(cudaFuncSetAttribute(k_cross_attn_bwd<DH>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
-    k_cross_attn_bwd<DH><<<grid, 128, smem, st>>>(q, ldq, k, v, ldk, ldv, pt_off, tok_off, H, scale, out, dout, ldo, lse, dq, lddq,
-                                                  dk, dv, lddk, lddv, drop_p, seed, layer_id);
-  });
-  LOTUS_CUDA_OK();
-  return 0;
+  return cross_bwd_impl<float>(q, ldq, k, v, ldk, ldv, pt_off, tok_off, B, max_points, max_tokens, H, Dh, scale, out, dout, ldo, lse,
+                               dq, lddq, dk, dv, lddk, lddv, drop_p, seed, layer_id, stream_);
+}
+LOTUS_API int lotus_cross_attn_bwd_bf16(const void* q, int64_t ldq, const void* k, const void* v, int64_t ldk, int64_t ldv,
+                                        const int32_t* pt_off, const int32_t* tok_off, int B, int max_points, int max_tokens,
+                                        int H, int Dh, float scale, const void* out, const void* dout, int64_t ldo,
+                                        const float* lse, float* dq, int64_t lddq, float* dk, float* dv, int64_t lddk,
+                                        int64_t lddv, float drop_p, uint64_t seed, uint32_t layer_id, void* stream_) {
+  return cross_bwd_impl<bf16_t>(q, ldq, k, v, ldk, ldv, pt_off, tok_off, B, max_points, max_tokens, H, Dh, scale, out, dout, ldo,
+                                lse, dq, lddq, dk, dv, lddk, lddv, drop_p, seed, layer_id, stream_);
 }

@@ -94,6 +94,13 @@ __device__ __forceinline__ float gelu_grad_f(float x) {
   return cdf + x * pdf;
 }
 
+// activation element access: kernels are templated on the storage type (float | __nv_bfloat16), math is fp32
+typedef __nv_bfloat16 bf16_t;
+__device__ __forceinline__ float ldf(const float* p, int64_t i) { return p[i]; }
+__device__ __forceinline__ float ldf(const bf16_t* p, int64_t i) { return __bfloat162float(p[i]); }
+__device__ __forceinline__ void stf(float* p, int64_t i, float v) { p[i] = v; }
+__device__ __forceinline__ void stf(bf16_t* p, int64_t i, float v) { p[i] = __float2bfloat16(v); }
+
 // counter-based RNG for dropout masks: one 32-bit hash per element (seed, stream id, index) -> uniform [0,1)
 __device__ __forceinline__ uint32_t lotus_hash3(uint32_t a, uint32_t b, uint32_t c) {
   uint32_t h = a * 0x9E3779B1u ^ (b + 0x7F4A7C15u) * 0x85EBCA77u ^ (c + 0x165667B1u) * 0xC2B2AE3Du;

@@ -15,34 +15,35 @@ struct RowMap {  // row r -> element offset (r / inner) * outer_stride + (r % in
 
 // ---------------------------------------------------------------- LayerNorm
 // y = [residual +] (x - mean) * rstd * gamma + beta ; one warp per row
-__global__ void k_ln_fwd(const float* __restrict__ x, RowMap xm, float* __restrict__ y, RowMap ym,
-                         const float* __restrict__ residual, const float* __restrict__ gamma,
+template <typename T>
+__global__ void k_ln_fwd(const T* __restrict__ x, RowMap xm, T* __restrict__ y, RowMap ym,
+                         const T* __restrict__ residual, const float* __restrict__ gamma,
                          const float* __restrict__ beta, float* __restrict__ mean, float* __restrict__ rstd,
                          int64_t rows, int C, float eps) {
   int lane = threadIdx.x & 31;
   int64_t r = (int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
   if (r >= rows) return;
-  const float* xr = x + xm(r);
+  const T* xr = x + xm(r);
   float s = 0.f;
-  for (int c = lane; c < C; c += 32) s += xr[c];
+  for (int c = lane; c < C; c += 32) s += ldf(xr, c);
   float mu = warp_sum(s) / C;
   float v = 0.f;
-  for (int c = lane; c < C; c += 32) { float d = xr[c] - mu; v += d * d; }
+  for (int c = lane; c < C; c += 32) { float d = ldf(xr, c) - mu; v += d * d; }
   float rs = rsqrtf(warp_sum(v) / C + eps);
   if (lane == 0) { if (mean) mean[r] = mu; if (rstd) rstd[r] = rs; }
-  float* yr = y + ym(r);
-  const float* rr = residual ? residual + ym(r) : nullptr;
+  T* yr = y + ym(r);
+  const T* rr = residual ? residual + ym(r) : nullptr;
   for (int c = lane; c < C; c += 32) {
-    float o = (xr[c] - mu) * rs * gamma[c] + beta[c];
-    yr[c] = rr ? rr[c] + o : o;
+    float o = (ldf(xr, c) - mu) * rs * gamma[c] + beta[c];
+    stf(yr, c, rr ? ldf(rr, c) + o : o);
   }
 }
 
 // dx = rstd * (g - mean(g) - xhat * mean(g * xhat)), g = dy * gamma ; dgamma += dy*xhat ; dbeta += dy
 // `accumulate_dx`: dx += (used when the normalised tensor also feeds a residual branch)
-template <int CPL>  // channels per lane upper bound (C <= 32*CPL)
-__global__ void k_ln_bwd(const float* __restrict__ dy, RowMap dym, const float* __restrict__ x, RowMap xm,
-                         float* __restrict__ dx, RowMap dxm, const float* __restrict__ gamma,
+template <int CPL, typename TDY, typename T>  // channels per lane upper bound (C <= 32*CPL); dy type, x/dx type
+__global__ void k_ln_bwd(const TDY* __restrict__ dy, RowMap dym, const T* __restrict__ x, RowMap xm,
+                         T* __restrict__ dx, RowMap dxm, const float* __restrict__ gamma,
                          const float* __restrict__ mean, const float* __restrict__ rstd, float* __restrict__ dgamma,
                          float* __restrict__ dbeta, int64_t rows, int C, int rows_per_block, int accumulate_dx) {
   extern __shared__ float sacc[];  // [2][C]
@@ -55,28 +56,28 @@ __global__ void k_ln_bwd(const float* __restrict__ dy, RowMap dym, const float* 
   int64_t r0 = (int64_t)blockIdx.x * rows_per_block;
   int64_t r1 = min(rows, r0 + rows_per_block);
   for (int64_t r = r0 + w; r < r1; r += nw) {
-    const float* dyr = dy + dym(r);
-    const float* xr = x + xm(r);
+    const TDY* dyr = dy + dym(r);
+    const T* xr = x + xm(r);
     float mu = mean[r], rs = rstd[r];
     float s1 = 0.f, s2 = 0.f;
 #pragma unroll
     for (int i = 0; i < CPL; ++i) {
       int c = lane + 32 * i;
       if (c < C) {
-        float xh = (xr[c] - mu) * rs, d = dyr[c], g = d * gamma[c];
+        float xh = (ldf(xr, c) - mu) * rs, d = ldf(dyr, c), g = d * gamma[c];
         s1 += g; s2 += g * xh;
         ag[i] += d * xh; ab[i] += d;
       }
     }
     s1 = warp_sum(s1) / C; s2 = warp_sum(s2) / C;
-    float* dxr = dx + dxm(r);
+    T* dxr = dx + dxm(r);
 #pragma unroll
     for (int i = 0; i < CPL; ++i) {
       int c = lane + 32 * i;
       if (c < C) {
-        float xh = (xr[c] - mu) * rs;
-        float o = rs * (dyr[c] * gamma[c] - s1 - xh * s2);
-        dxr[c] = accumulate_dx ? dxr[c] + o : o;
+        float xh = (ldf(xr, c) - mu) * rs;
+        float o = rs * (ldf(dyr, c) * gamma[c] - s1 - xh * s2);
+        stf(dxr, c, accumulate_dx ? ldf(dxr, c) + o : o);
       }
     }
   }
@@ -92,22 +93,38 @@ __global__ void k_ln_bwd(const float* __restrict__ dy, RowMap dym, const float* 
   }
 }
 
+template <typename T>
+static int ln_fwd_impl(const void* x, int x_inner, int64_t x_outer_stride, int64_t x_inner_stride, void* y, int y_inner,
+                       int64_t y_outer_stride, int64_t y_inner_stride, const void* residual, const float* gamma,
+                       const float* beta, float* mean, float* rstd, int64_t rows, int C, float eps, void* stream_) {
+  if (rows <= 0) return 0;
+  RowMap xm{x_inner, x_outer_stride, x_inner_stride}, ym{y_inner, y_outer_stride, y_inner_stride};
+  k_ln_fwd<T><<<ceil_div(rows, 8), 256, 0, (cudaStream_t)stream_>>>((const T*)x, xm, (T*)y, ym, (const T*)residual, gamma, beta,
+                                                                   mean, rstd, rows, C, eps);
+  LOTUS_CUDA_OK();
+  return 0;
+}
 LOTUS_API int lotus_layernorm_fwd_f32(const float* x, int x_inner, int64_t x_outer_stride, int64_t x_inner_stride,
                                       float* y, int y_inner, int64_t y_outer_stride, int64_t y_inner_stride,
                                       const float* residual, const float* gamma, const float* beta, float* mean,
                                       float* rstd, int64_t rows, int C, float eps, void* stream_) {
-  if (rows <= 0) return 0;
-  RowMap xm{x_inner, x_outer_stride, x_inner_stride}, ym{y_inner, y_outer_stride, y_inner_stride};
-  k_ln_fwd<<<ceil_div(rows, 8), 256, 0, (cudaStream_t)stream_>>>(x, xm, y, ym, residual, gamma, beta, mean, rstd, rows, C, eps);
-  LOTUS_CUDA_OK();
-  return 0;
+  return ln_fwd_impl<float>(x, x_inner, x_outer_stride, x_inner_stride, y, y_inner, y_outer_stride, y_inner_stride, residual,
+                            gamma, beta, mean, rstd, rows, C, eps, stream_);
+}
+// bf16 activations (x, y, residual), fp32 parameters and statistics
+LOTUS_API int lotus_layernorm_fwd_bf16(const void* x, int x_inner, int64_t x_outer_stride, int64_t x_inner_stride, void* y,
+                                       int y_inner, int64_t y_outer_stride, int64_t y_inner_stride, const void* residual,
+                                       const float* gamma, const float* beta, float* mean, float* rstd, int64_t rows, int C,
+                                       float eps, void* stream_) {
+  return ln_fwd_impl<bf16_t>(x, x_inner, x_outer_stride, x_inner_stride, y, y_inner, y_outer_stride, y_inner_stride, residual,
+                             gamma, beta, mean, rstd, rows, C, eps, stream_);
 }
 
-LOTUS_API int lotus_layernorm_bwd_f32(const float* dy, int dy_inner, int64_t dy_outer_stride, int64_t dy_inner_stride,
-                                      const float* x, int x_inner, int64_t x_outer_stride, int64_t x_inner_stride,
-                                      float* dx, int dx_inner, int64_t dx_outer_stride, int64_t dx_inner_stride,
-                                      const float* gamma, const float* mean, const float* rstd, float* dgamma,
-                                      float* dbeta, int64_t rows, int C, int accumulate_dx, void* stream_) {
+template <typename TDY, typename T>
+static int ln_bwd_impl(const void* dy, int dy_inner, int64_t dy_outer_stride, int64_t dy_inner_stride, const void* x,
+                       int x_inner, int64_t x_outer_stride, int64_t x_inner_stride, void* dx, int dx_inner,
+                       int64_t dx_outer_stride, int64_t dx_inner_stride, const float* gamma, const float* mean,
+                       const float* rstd, float* dgamma, float* dbeta, int64_t rows, int C, int accumulate_dx, void* stream_) {
   if (rows <= 0) return 0;
   cudaStream_t st = (cudaStream_t)stream_;
   RowMap dym{dy_inner, dy_outer_stride, dy_inner_stride}, xm{x_inner, x_outer_stride, x_inner_stride},
@@ -116,10 +133,10 @@ LOTUS_API int lotus_layernorm_bwd_f32(const float* dy, int dy_inner, int64_t dy_
   int rpb = ceil_div(rows, blocks);
   blocks = ceil_div(rows, rpb);
   size_t smem = (size_t)2 * C * 4;
-  LOTUS_CHECK_ARG(C <= 32 * 32, "lotus_layernorm_bwd_f32: C=%d > 1024", C);
-#define LN_BWD(CPL)                                                                                          \
-  k_ln_bwd<CPL><<<blocks, 256, smem, st>>>(dy, dym, x, xm, dx, dxm, gamma, mean, rstd, dgamma, dbeta, rows, C, rpb, \
-                                           accumulate_dx)
+  LOTUS_CHECK_ARG(C <= 32 * 32, "lotus_layernorm_bwd: C=%d > 1024", C);
+#define LN_BWD(CPL)                                                                                                   \
+  k_ln_bwd<CPL, TDY, T><<<blocks, 256, smem, st>>>((const TDY*)dy, dym, (const T*)x, xm, (T*)dx, dxm, gamma, mean, rstd, \
+                                                   dgamma, dbeta, rows, C, rpb, accumulate_dx)
   if (C <= 32) LN_BWD(1);
   else if (C <= 64) LN_BWD(2);
   else if (C <= 128) LN_BWD(4);
@@ -130,10 +147,34 @@ LOTUS_API int lotus_layernorm_bwd_f32(const float* dy, int dy_inner, int64_t dy_
   LOTUS_CUDA_OK();
   return 0;
 }
+LOTUS_API int lotus_layernorm_bwd_f32(const float* dy, int dy_inner, int64_t dy_outer_stride, int64_t dy_inner_stride,
+                                      const float* x, int x_inner, int64_t x_outer_stride, int64_t x_inner_stride,
+                                      float* dx, int dx_inner, int64_t dx_outer_stride, int64_t dx_inner_stride,
+                                      const float* gamma, const float* mean, const float* rstd, float* dgamma,
+                                      float* dbeta, int64_t rows, int C, int accumulate_dx, void* stream_) {
+  return ln_bwd_impl<float, float>(dy, dy_inner, dy_outer_stride, dy_inner_stride, x, x_inner, x_outer_stride, x_inner_stride, dx,
+                                   dx_inner, dx_outer_stride, dx_inner_stride, gamma, mean, rstd, dgamma, dbeta, rows, C,
+                                   accumulate_dx, stream_);
+}
+// x, dx bf16; dy bf16 (dy_fp32 = 0) or fp32 (dy_fp32 = 1: gradients coming out of the attention kernels)
+LOTUS_API int lotus_layernorm_bwd_bf16(const void* dy, int dy_fp32, int dy_inner, int64_t dy_outer_stride,
+                                       int64_t dy_inner_stride, const void* x, int x_inner, int64_t x_outer_stride,
+                                       int64_t x_inner_stride, void* dx, int dx_inner, int64_t dx_outer_stride,
+                                       int64_t dx_inner_stride, const float* gamma, const float* mean, const float* rstd,
+                                       float* dgamma, float* dbeta, int64_t rows, int C, int accumulate_dx, void* stream_) {
+  if (dy_fp32)
+    return ln_bwd_impl<float, bf16_t>(dy, dy_inner, dy_outer_stride, dy_inner_stride, x, x_inner, x_outer_stride, x_inner_stride,
+                                      dx, dx_inner, dx_outer_stride, dx_inner_stride, gamma, mean, rstd, dgamma, dbeta, rows, C,
+                                      accumulate_dx, stream_);
+  return ln_bwd_impl<bf16_t, bf16_t>(dy, dy_inner, dy_outer_stride, dy_inner_stride, x, x_inner, x_outer_stride, x_inner_stride,
+                                     dx, dx_inner, dx_outer_stride, dx_inner_stride, gamma, mean, rstd, dgamma, dbeta, rows, C,
+                                     accumulate_dx, stream_);
+}
 
 // ---------------------------------------------------------------- BatchNorm (+GELU)
 // column statistics: grid (ceil(C/32), row_blocks); each block reduces a [rows_chunk x 32] panel
-__global__ void k_col_sum(const float* __restrict__ x, int64_t rows, int C, const float* __restrict__ shift /*C or null*/,
+template <typename T>
+__global__ void k_col_sum(const T* __restrict__ x, int64_t rows, int C, const float* __restrict__ shift /*C or null*/,
                           int square, float* __restrict__ out /*C, pre-zeroed*/, int rows_per_block) {
   __shared__ float red[8][33];
   int cx = threadIdx.x & 31, ry = threadIdx.x >> 5;  // 32 x 8
@@ -143,7 +184,7 @@ __global__ void k_col_sum(const float* __restrict__ x, int64_t rows, int C, cons
   if (c < C) {
     float sh = shift ? shift[c] : 0.f;
     for (int64_t r = r0 + ry; r < r1; r += 8) {
-      float v = x[r * C + c] - sh;
+      float v = ldf(x, r * C + c) - sh;
       s += square ? v * v : v;
     }
   }
@@ -165,13 +206,20 @@ static void col_launch_cfg(int64_t rows, int C, dim3* grid, int* rpb) {
   *grid = dim3(cb, rb);
 }
 
-LOTUS_API int lotus_colsum_f32(const float* x, int64_t rows, int C, float* out_accum, void* stream_) {
+template <typename T>
+static int colsum_impl(const void* x, int64_t rows, int C, float* out_accum, void* stream_) {
   if (rows <= 0) return 0;
   dim3 grid; int rpb;
   col_launch_cfg(rows, C, &grid, &rpb);
-  k_col_sum<<<grid, 256, 0, (cudaStream_t)stream_>>>(x, rows, C, nullptr, 0, out_accum, rpb);
+  k_col_sum<T><<<grid, 256, 0, (cudaStream_t)stream_>>>((const T*)x, rows, C, nullptr, 0, out_accum, rpb);
   LOTUS_CUDA_OK();
   return 0;
+}
+LOTUS_API int lotus_colsum_f32(const float* x, int64_t rows, int C, float* out_accum, void* stream_) {
+  return colsum_impl<float>(x, rows, C, out_accum, stream_);
+}
+LOTUS_API int lotus_colsum_bf16(const void* x, int64_t rows, int C, float* out_accum, void* stream_) {
+  return colsum_impl<bf16_t>(x, rows, C, out_accum, stream_);
 }
 
 __global__ void k_bn_finalize(float* __restrict__ sum /*C: in sum, out mean*/, float* __restrict__ sq, int64_t rows,
@@ -192,22 +240,23 @@ __global__ void k_bn_finalize(float* __restrict__ sum /*C: in sum, out mean*/, f
   }
 }
 
-__global__ void k_bn_apply(const float* __restrict__ x, float* __restrict__ y, const float* __restrict__ mean,
+template <typename TX, typename TY>
+__global__ void k_bn_apply(const TX* __restrict__ x, TY* __restrict__ y, const float* __restrict__ mean,
                            const float* __restrict__ rstd, const float* __restrict__ gamma,
                            const float* __restrict__ beta, int64_t total, int C, int act) {
   for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
     int c = (int)(i % C);
-    float z = (x[i] - mean[c]) * rstd[c] * gamma[c] + beta[c];
-    y[i] = act ? gelu_f(z) : z;
+    float z = (ldf(x, i) - mean[c]) * rstd[c] * gamma[c] + beta[c];
+    stf(y, i, act ? gelu_f(z) : z);
   }
 }
 
 // training: batch statistics (two-pass: mean, then centred second moment), running stats updated in place.
 // eval (train=0): mean/rstd derived from the running stats.  save_mean/save_rstd (C each) feed the backward.
-LOTUS_API int lotus_batchnorm_fwd_f32(const float* x, float* y, int64_t rows, int C, const float* gamma,
-                                      const float* beta, float* run_mean, float* run_var, float* save_mean,
-                                      float* save_rstd, float* scratch_C, int train, float eps, float momentum,
-                                      int act_gelu, void* stream_) {
+template <typename TX, typename TY>
+static int bn_fwd_impl(const void* x, void* y, int64_t rows, int C, const float* gamma, const float* beta, float* run_mean,
+                       float* run_var, float* save_mean, float* save_rstd, float* scratch_C, int train, float eps,
+                       float momentum, int act_gelu, void* stream_) {
   cudaStream_t st = (cudaStream_t)stream_;
   if (rows <= 0) return 0;
   if (train) {
@@ -215,9 +264,9 @@ LOTUS_API int lotus_batchnorm_fwd_f32(const float* x, float* y, int64_t rows, in
     col_launch_cfg(rows, C, &grid, &rpb);
     LOTUS_CUDA_CALL(cudaMemsetAsync(save_mean, 0, (size_t)C * 4, st));
     LOTUS_CUDA_CALL(cudaMemsetAsync(scratch_C, 0, (size_t)C * 4, st));
-    k_col_sum<<<grid, 256, 0, st>>>(x, rows, C, nullptr, 0, save_mean, rpb);
+    k_col_sum<TX><<<grid, 256, 0, st>>>((const TX*)x, rows, C, nullptr, 0, save_mean, rpb);
     k_bn_finalize<<<ceil_div(C, 128), 128, 0, st>>>(save_mean, scratch_C, rows, C, eps, momentum, save_rstd, nullptr, nullptr, 0);
-    k_col_sum<<<grid, 256, 0, st>>>(x, rows, C, save_mean, 1, scratch_C, rpb);
+    k_col_sum<TX><<<grid, 256, 0, st>>>((const TX*)x, rows, C, save_mean, 1, scratch_C, rpb);
     k_bn_finalize<<<ceil_div(C, 128), 128, 0, st>>>(save_mean, scratch_C, rows, C, eps, momentum, save_rstd, run_mean, run_var, 1);
   } else {
     // mean := running_mean ; rstd := rsqrt(running_var + eps)
@@ -226,13 +275,33 @@ LOTUS_API int lotus_batchnorm_fwd_f32(const float* x, float* y, int64_t rows, in
     k_bn_finalize<<<ceil_div(C, 128), 128, 0, st>>>(save_mean, scratch_C, 1, C, eps, 0.f, save_rstd, nullptr, nullptr, 1);
   }
   int64_t total = rows * C;
-  k_bn_apply<<<min(ceil_div(total, 256), kNumSM * 16), 256, 0, st>>>(x, y, save_mean, save_rstd, gamma, beta, total, C, act_gelu);
+  k_bn_apply<TX, TY><<<min(ceil_div(total, 256), kNumSM * 16), 256, 0, st>>>((const TX*)x, (TY*)y, save_mean, save_rstd, gamma, beta,
+                                                                             total, C, act_gelu);
   LOTUS_CUDA_OK();
   return 0;
 }
+LOTUS_API int lotus_batchnorm_fwd_f32(const float* x, float* y, int64_t rows, int C, const float* gamma,
+                                      const float* beta, float* run_mean, float* run_var, float* save_mean,
+                                      float* save_rstd, float* scratch_C, int train, float eps, float momentum,
+                                      int act_gelu, void* stream_) {
+  return bn_fwd_impl<float, float>(x, y, rows, C, gamma, beta, run_mean, run_var, save_mean, save_rstd, scratch_C, train, eps,
+                                   momentum, act_gelu, stream_);
+}
+// y bf16; x bf16 (x_fp32 = 0) or fp32 (x_fp32 = 1: the stem, whose conv runs in fp32)
+LOTUS_API int lotus_batchnorm_fwd_bf16(const void* x, int x_fp32, void* y, int64_t rows, int C, const float* gamma,
+                                       const float* beta, float* run_mean, float* run_var, float* save_mean,
+                                       float* save_rstd, float* scratch_C, int train, float eps, float momentum,
+                                       int act_gelu, void* stream_) {
+  if (x_fp32)
+    return bn_fwd_impl<float, bf16_t>(x, y, rows, C, gamma, beta, run_mean, run_var, save_mean, save_rstd, scratch_C, train, eps,
+                                      momentum, act_gelu, stream_);
+  return bn_fwd_impl<bf16_t, bf16_t>(x, y, rows, C, gamma, beta, run_mean, run_var, save_mean, save_rstd, scratch_C, train, eps,
+                                     momentum, act_gelu, stream_);
+}
 
 // backward of y = act(bn(x)).  pass 1: dbeta = sum dz, dgamma = sum dz*xhat (dz = dy * act'(z)); pass 2: dx.
-__global__ void k_bn_bwd_reduce(const float* __restrict__ dy, const float* __restrict__ x, const float* __restrict__ mean,
+template <typename TX, typename TY>
+__global__ void k_bn_bwd_reduce(const TY* __restrict__ dy, const TX* __restrict__ x, const float* __restrict__ mean,
                                 const float* __restrict__ rstd, const float* __restrict__ gamma,
                                 const float* __restrict__ beta, int64_t rows, int C, int act,
                                 float* __restrict__ dgamma, float* __restrict__ dbeta, int rows_per_block) {
@@ -244,8 +313,8 @@ __global__ void k_bn_bwd_reduce(const float* __restrict__ dy, const float* __res
   if (c < C) {
     float mu = mean[c], rs = rstd[c], g = gamma[c], b = beta[c];
     for (int64_t r = r0 + ry; r < r1; r += 8) {
-      float xh = (x[r * C + c] - mu) * rs;
-      float dz = dy[r * C + c];
+      float xh = (ldf(x, r * C + c) - mu) * rs;
+      float dz = ldf(dy, r * C + c);
       if (act) dz *= gelu_grad_f(xh * g + b);
       sg += dz * xh; sb += dz;
     }
@@ -259,83 +328,180 @@ __global__ void k_bn_bwd_reduce(const float* __restrict__ dy, const float* __res
     atomicAdd(&dgamma[c], a); atomicAdd(&dbeta[c], b2);
   }
 }
-__global__ void k_bn_bwd_apply(const float* __restrict__ dy, const float* __restrict__ x, const float* __restrict__ mean,
+template <typename TX, typename TY>
+__global__ void k_bn_bwd_apply(const TY* __restrict__ dy, const TX* __restrict__ x, const float* __restrict__ mean,
                                const float* __restrict__ rstd, const float* __restrict__ gamma,
                                const float* __restrict__ beta, const float* __restrict__ dgamma_batch,
                                const float* __restrict__ dbeta_batch, int64_t rows, int C, int act, int train,
-                               float* __restrict__ dx) {
+                               TX* __restrict__ dx) {
   int64_t total = rows * C;
   float invn = 1.f / (float)rows;
   for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
     int c = (int)(i % C);
     float rs = rstd[c], g = gamma[c];
-    float xh = (x[i] - mean[c]) * rs;
-    float dz = dy[i];
+    float xh = (ldf(x, i) - mean[c]) * rs;
+    float dz = ldf(dy, i);
     if (act) dz *= gelu_grad_f(xh * g + beta[c]);
-    dx[i] = train ? g * rs * (dz - dbeta_batch[c] * invn - xh * dgamma_batch[c] * invn) : g * rs * dz;
+    stf(dx, i, train ? g * rs * (dz - dbeta_batch[c] * invn - xh * dgamma_batch[c] * invn) : g * rs * dz);
   }
 }
 
 // dgamma_batch/dbeta_batch: zero-initialised C-float scratch receiving THIS batch's sums (the caller adds
 // them to the parameter gradients).
-LOTUS_API int lotus_batchnorm_bwd_f32(const float* dy, const float* x, int64_t rows, int C, const float* gamma,
-                                      const float* beta, const float* save_mean, const float* save_rstd, float* dx,
-                                      float* dgamma_batch, float* dbeta_batch, int train, int act_gelu, void* stream_) {
+template <typename TX, typename TY>
+static int bn_bwd_impl(const void* dy, const void* x, int64_t rows, int C, const float* gamma, const float* beta,
+                       const float* save_mean, const float* save_rstd, void* dx, float* dgamma_batch, float* dbeta_batch,
+                       int train, int act_gelu, void* stream_) {
   cudaStream_t st = (cudaStream_t)stream_;
   if (rows <= 0) return 0;
   dim3 grid; int rpb;
   col_launch_cfg(rows, C, &grid, &rpb);
-  k_bn_bwd_reduce<<<grid, 256, 0, st>>>(dy, x, save_mean, save_rstd, gamma, beta, rows, C, act_gelu, dgamma_batch, dbeta_batch, rpb);
+  k_bn_bwd_reduce<TX, TY><<<grid, 256, 0, st>>>((const TY*)dy, (const TX*)x, save_mean, save_rstd, gamma, beta, rows, C, act_gelu,
+                                                dgamma_batch, dbeta_batch, rpb);
   int64_t total = rows * C;
-  k_bn_bwd_apply<<<min(ceil_div(total, 256), kNumSM * 16), 256, 0, st>>>(dy, x, save_mean, save_rstd, gamma, beta, dgamma_batch,
-                                                                       dbeta_batch, rows, C, act_gelu, train, dx);
+  k_bn_bwd_apply<TX, TY><<<min(ceil_div(total, 256), kNumSM * 16), 256, 0, st>>>(
+      (const TY*)dy, (const TX*)x, save_mean, save_rstd, gamma, beta, dgamma_batch, dbeta_batch, rows, C, act_gelu, train, (TX*)dx);
   LOTUS_CUDA_OK();
   return 0;
+}
+LOTUS_API int lotus_batchnorm_bwd_f32(const float* dy, const float* x, int64_t rows, int C, const float* gamma,
+                                      const float* beta, const float* save_mean, const float* save_rstd, float* dx,
+                                      float* dgamma_batch, float* dbeta_batch, int train, int act_gelu, void* stream_) {
+  return bn_bwd_impl<float, float>(dy, x, rows, C, gamma, beta, save_mean, save_rstd, dx, dgamma_batch, dbeta_batch, train,
+                                   act_gelu, stream_);
+}
+// dy bf16; x and dx bf16 (x_fp32 = 0) or fp32 (x_fp32 = 1)
+LOTUS_API int lotus_batchnorm_bwd_bf16(const void* dy, const void* x, int x_fp32, int64_t rows, int C, const float* gamma,
+                                       const float* beta, const float* save_mean, const float* save_rstd, void* dx,
+                                       float* dgamma_batch, float* dbeta_batch, int train, int act_gelu, void* stream_) {
+  if (x_fp32)
+    return bn_bwd_impl<float, bf16_t>(dy, x, rows, C, gamma, beta, save_mean, save_rstd, dx, dgamma_batch, dbeta_batch, train,
+                                      act_gelu, stream_);
+  return bn_bwd_impl<bf16_t, bf16_t>(dy, x, rows, C, gamma, beta, save_mean, save_rstd, dx, dgamma_batch, dbeta_batch, train,
+                                     act_gelu, stream_);
 }
 
 // ---------------------------------------------------------------- pointwise
 // op 0: y = drop(gelu(x))            1: y = drop(a) * gelu'(x)     (x = pre-activation, a = dy)
 // op 2: y = drop(leaky(x, alpha))    3: y = drop(a) * leaky'(x)
-// op 4: y = a + x                    5: y = x * alpha
+// op 4: y = a + x                    5: y = x * alpha              6: y = x (type conversion)
 // drop(.) is the identity when drop_p == 0; mask index = flat element index (same in fwd and bwd)
-__global__ void k_pointwise(const float* __restrict__ x, const float* __restrict__ a, float* __restrict__ y, int64_t n,
+template <typename TX, typename TY>
+__global__ void k_pointwise(const TX* __restrict__ x, const TX* __restrict__ a, TY* __restrict__ y, int64_t n,
                             int op, float alpha, float drop_p, uint64_t seed, uint32_t sid) {
   float ks = drop_p > 0.f ? 1.f / (1.f - drop_p) : 1.f;
   for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
-    float v = x[i], o;
+    float v = ldf(x, i), o;
     float m = 1.f;
     if (drop_p > 0.f && op < 4) m = dropout_keep(seed, sid ^ (uint32_t)(i >> 32), (uint32_t)i, drop_p) ? ks : 0.f;
     switch (op) {
       case 0: o = gelu_f(v) * m; break;
-      case 1: o = a[i] * m * gelu_grad_f(v); break;
+      case 1: o = ldf(a, i) * m * gelu_grad_f(v); break;
       case 2: o = (v > 0.f ? v : v * alpha) * m; break;
-      case 3: o = a[i] * m * (v > 0.f ? 1.f : alpha); break;
-      case 4: o = a[i] + v; break;
-      default: o = v * alpha; break;
+      case 3: o = ldf(a, i) * m * (v > 0.f ? 1.f : alpha); break;
+      case 4: o = ldf(a, i) + v; break;
+      case 5: o = v * alpha; break;
+      default: o = v; break;
     }
-    y[i] = o;
+    stf(y, i, o);
   }
 }
 LOTUS_API int lotus_pointwise_f32(const float* x, const float* a, float* y, int64_t n, int op, float alpha, float drop_p,
                                   uint64_t seed, uint32_t drop_stream, void* stream_) {
   if (n <= 0) return 0;
-  k_pointwise<<<min(ceil_div(n, 256), kNumSM * 16), 256, 0, (cudaStream_t)stream_>>>(x, a, y, n, op, alpha, drop_p, seed, drop_stream);
+  k_pointwise<float, float><<<min(ceil_div(n, 256), kNumSM * 16), 256, 0, (cudaStream_t)stream_>>>(x, a, y, n, op, alpha, drop_p,
+                                                                                                 seed, drop_stream);
+  LOTUS_CUDA_OK();
+  return 0;
+}
+LOTUS_API int lotus_pointwise_bf16(const void* x, const void* a, void* y, int64_t n, int op, float alpha, float drop_p,
+                                   uint64_t seed, uint32_t drop_stream, void* stream_) {
+  if (n <= 0) return 0;
+  k_pointwise<bf16_t, bf16_t><<<min(ceil_div(n, 256), kNumSM * 16), 256, 0, (cudaStream_t)stream_>>>(
+      (const bf16_t*)x, (const bf16_t*)a, (bf16_t*)y, n, op, alpha, drop_p, seed, drop_stream);
+  LOTUS_CUDA_OK();
+  return 0;
+}
+// dtype conversion: dir 0: fp32 -> bf16, 1: bf16 -> fp32
+LOTUS_API int lotus_convert(const void* x, void* y, int64_t n, int dir, void* stream_) {
+  if (n <= 0) return 0;
+  int blocks = min(ceil_div(n, 256), kNumSM * 16);
+  if (dir == 0)
+    k_pointwise<float, bf16_t><<<blocks, 256, 0, (cudaStream_t)stream_>>>((const float*)x, nullptr, (bf16_t*)y, n, 6, 0.f, 0.f, 0, 0);
+  else
+    k_pointwise<bf16_t, float><<<blocks, 256, 0, (cudaStream_t)stream_>>>((const bf16_t*)x, nullptr, (float*)y, n, 6, 0.f, 0.f, 0, 0);
+  LOTUS_CUDA_OK();
+  return 0;
+}
+
+// strided fp32 -> bf16 row copy: y[r, :C] (row stride ldy) = x[r, :C] (row stride ldx)
+__global__ void k_convert_rows(const float* __restrict__ x, int64_t ldx, bf16_t* __restrict__ y, int64_t ldy, int64_t rows, int C) {
+  int64_t total = rows * C;
+  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+    int64_t r = i / C;
+    int c = (int)(i - r * C);
+    y[r * ldy + c] = __float2bfloat16(x[r * ldx + c]);
+  }
+}
+LOTUS_API int lotus_convert_rows_f32_to_bf16(const float* x, int64_t ldx, void* y, int64_t ldy, int64_t rows, int C, void* stream_) {
+  if (rows <= 0) return 0;
+  k_convert_rows<<<min(ceil_div(rows * C, 256), kNumSM * 16), 256, 0, (cudaStream_t)stream_>>>(x, ldx, (bf16_t*)y, ldy, rows, C);
+  LOTUS_CUDA_OK();
+  return 0;
+}
+
+// weight staging for the tensor-core path: w fp32 [A][D][B] -> w_bf16 (same layout) and wt_bf16 [B][D][A]
+// (Linear: D = 1 -> plain transpose; SubMConv3d: [Cout][K3][Cin] -> [Cin][K3][Cout])
+__global__ void k_cast_transpose(const float* __restrict__ w, bf16_t* __restrict__ wb, bf16_t* __restrict__ wt, int A, int D, int B) {
+  __shared__ float tile[32][33];
+  int d = blockIdx.z;
+  int a0 = blockIdx.y * 32, b0 = blockIdx.x * 32;
+  int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;  // 32 x 8
+  for (int i = ty; i < 32; i += 8) {
+    int a = a0 + i, b = b0 + tx;
+    float v = 0.f;
+    if (a < A && b < B) {
+      v = w[((int64_t)a * D + d) * B + b];
+      if (wb) wb[((int64_t)a * D + d) * B + b] = __float2bfloat16(v);
+    }
+    tile[i][tx] = v;
+  }
+  __syncthreads();
+  if (wt) {
+    for (int i = ty; i < 32; i += 8) {
+      int b = b0 + i, a = a0 + tx;
+      if (a < A && b < B) wt[((int64_t)b * D + d) * A + a] = __float2bfloat16(tile[tx][i]);
+    }
+  }
+}
+LOTUS_API int lotus_cast_transpose_bf16(const float* w, void* w_bf16, void* wt_bf16, int A, int D, int B, void* stream_) {
+  if (A <= 0 || B <= 0 || D <= 0) return 0;
+  dim3 grid(ceil_div(B, 32), ceil_div(A, 32), D);
+  k_cast_transpose<<<grid, 256, 0, (cudaStream_t)stream_>>>(w, (bf16_t*)w_bf16, (bf16_t*)wt_bf16, A, D, B);
   LOTUS_CUDA_OK();
   return 0;
 }
 
 // dropout: y = keep(seed, stream_id, i) ? x / (1-p) : 0 — the same call with dy gives the backward
-__global__ void k_dropout(const float* __restrict__ x, float* __restrict__ y, int64_t n, float p, uint64_t seed,
-                          uint32_t stream_id) {
+template <typename T>
+__global__ void k_dropout(const T* __restrict__ x, T* __restrict__ y, int64_t n, float p, uint64_t seed, uint32_t stream_id) {
   float sc = 1.f / (1.f - p);
   for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x)
-    y[i] = dropout_keep(seed, stream_id ^ (uint32_t)(i >> 32), (uint32_t)i, p) ? x[i] * sc : 0.f;
+    stf(y, i, dropout_keep(seed, stream_id ^ (uint32_t)(i >> 32), (uint32_t)i, p) ? ldf(x, i) * sc : 0.f);
 }
 LOTUS_API int lotus_dropout_f32(const float* x, float* y, int64_t n, float p, uint64_t seed, uint32_t stream_id,
                                 void* stream_) {
   if (n <= 0) return 0;
   LOTUS_CHECK_ARG(p >= 0.f && p < 1.f, "lotus_dropout_f32: p=%f", p);
-  k_dropout<<<min(ceil_div(n, 256), kNumSM * 16), 256, 0, (cudaStream_t)stream_>>>(x, y, n, p, seed, stream_id);
+  k_dropout<float><<<min(ceil_div(n, 256), kNumSM * 16), 256, 0, (cudaStream_t)stream_>>>(x, y, n, p, seed, stream_id);
+  LOTUS_CUDA_OK();
+  return 0;
+}
+LOTUS_API int lotus_dropout_bf16(const void* x, void* y, int64_t n, float p, uint64_t seed, uint32_t stream_id, void* stream_) {
+  if (n <= 0) return 0;
+  LOTUS_CHECK_ARG(p >= 0.f && p < 1.f, "lotus_dropout_bf16: p=%f", p);
+  k_dropout<bf16_t><<<min(ceil_div(n, 256), kNumSM * 16), 256, 0, (cudaStream_t)stream_>>>((const bf16_t*)x, (bf16_t*)y, n, p, seed,
+                                                                                          stream_id);
   LOTUS_CUDA_OK();
   return 0;
 }

@@ -9,8 +9,9 @@
 #include "common.cuh"
 
 // out[m, c] = max_{j in [ptr[m], ptr[m+1])} x[member ? member[j] : j, c]; arg[m, c] = winning source row
-__global__ void k_segment_max(const float* __restrict__ x, int C, const int32_t* __restrict__ ptr,
-                              const int32_t* __restrict__ member, int M, float* __restrict__ out,
+template <typename T>
+__global__ void k_segment_max(const T* __restrict__ x, int C, const int32_t* __restrict__ ptr,
+                              const int32_t* __restrict__ member, int M, T* __restrict__ out,
                               int32_t* __restrict__ arg) {
   int64_t total = (int64_t)M * C;
   for (int64_t t = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; t < total; t += (int64_t)gridDim.x * blockDim.x) {
@@ -19,24 +20,35 @@ __global__ void k_segment_max(const float* __restrict__ x, int C, const int32_t*
     float best = -INFINITY; int bi = -1;
     for (int j = s; j < e; ++j) {
       int r = member ? member[j] : j;
-      float v = x[(int64_t)r * C + c];
+      float v = ldf(x, (int64_t)r * C + c);
       if (v > best || bi < 0) { best = v; bi = r; }
     }
-    out[t] = best;
+    stf(out, t, best);
     if (arg) arg[t] = bi;
   }
 }
-LOTUS_API int lotus_segment_max_fwd_f32(const float* x, int C, const int32_t* seg_ptr, const int32_t* member, int M,
-                                        float* out, int32_t* argmax, void* stream_) {
+template <typename T>
+static int segmax_fwd_impl(const void* x, int C, const int32_t* seg_ptr, const int32_t* member, int M, void* out, int32_t* argmax,
+                           void* stream_) {
   if (M <= 0) return 0;
   int64_t total = (int64_t)M * C;
-  k_segment_max<<<min(ceil_div(total, 256), kNumSM * 16), 256, 0, (cudaStream_t)stream_>>>(x, C, seg_ptr, member, M, out, argmax);
+  k_segment_max<T><<<min(ceil_div(total, 256), kNumSM * 16), 256, 0, (cudaStream_t)stream_>>>((const T*)x, C, seg_ptr, member, M,
+                                                                                             (T*)out, argmax);
   LOTUS_CUDA_OK();
   return 0;
 }
+LOTUS_API int lotus_segment_max_fwd_f32(const float* x, int C, const int32_t* seg_ptr, const int32_t* member, int M,
+                                        float* out, int32_t* argmax, void* stream_) {
+  return segmax_fwd_impl<float>(x, C, seg_ptr, member, M, out, argmax, stream_);
+}
+LOTUS_API int lotus_segment_max_fwd_bf16(const void* x, int C, const int32_t* seg_ptr, const int32_t* member, int M, void* out,
+                                         int32_t* argmax, void* stream_) {
+  return segmax_fwd_impl<bf16_t>(x, C, seg_ptr, member, M, out, argmax, stream_);
+}
 // dx[arg[m,c], c] = dy[m,c]   (dx zero-initialised by the caller; segments are disjoint -> no atomics)
-__global__ void k_segment_max_bwd(const float* __restrict__ dy, const int32_t* __restrict__ arg, int64_t total, int C,
-                                  float* __restrict__ dx) {
+template <typename T>
+__global__ void k_segment_max_bwd(const T* __restrict__ dy, const int32_t* __restrict__ arg, int64_t total, int C,
+                                  T* __restrict__ dx) {
   for (int64_t t = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; t < total; t += (int64_t)gridDim.x * blockDim.x) {
     int r = arg[t];
     if (r >= 0) dx[(int64_t)r * C + (t % C)] = dy[t];
@@ -46,45 +58,73 @@ LOTUS_API int lotus_segment_max_bwd_f32(const float* dy, const int32_t* argmax, 
                                         void* stream_) {
   if (M <= 0) return 0;
   int64_t total = (int64_t)M * C;
-  k_segment_max_bwd<<<min(ceil_div(total, 256), kNumSM * 16), 256, 0, (cudaStream_t)stream_>>>(dy, argmax, total, C, dx_zeroed);
+  k_segment_max_bwd<float><<<min(ceil_div(total, 256), kNumSM * 16), 256, 0, (cudaStream_t)stream_>>>(dy, argmax, total, C, dx_zeroed);
+  LOTUS_CUDA_OK();
+  return 0;
+}
+LOTUS_API int lotus_segment_max_bwd_bf16(const void* dy, const int32_t* argmax, int M, int C, void* dx_zeroed, void* stream_) {
+  if (M <= 0) return 0;
+  int64_t total = (int64_t)M * C;
+  k_segment_max_bwd<bf16_t><<<min(ceil_div(total, 256), kNumSM * 16), 256, 0, (cudaStream_t)stream_>>>((const bf16_t*)dy, argmax, total,
+                                                                                                     C, (bf16_t*)dx_zeroed);
   LOTUS_CUDA_OK();
   return 0;
 }
 
 // op 0: mean, 1: sum  (sum is the backward of the unpool gather: d_child[m] = sum_{p in cluster m} dy[p])
-__global__ void k_segment_sum(const float* __restrict__ x, int C, const int32_t* __restrict__ ptr,
-                              const int32_t* __restrict__ member, int M, int mean, float* __restrict__ out) {
+template <typename T>
+__global__ void k_segment_sum(const T* __restrict__ x, int C, const int32_t* __restrict__ ptr,
+                              const int32_t* __restrict__ member, int M, int mean, T* __restrict__ out) {
   int64_t total = (int64_t)M * C;
   for (int64_t t = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; t < total; t += (int64_t)gridDim.x * blockDim.x) {
     int m = (int)(t / C), c = (int)(t % C);
     int s = ptr[m], e = ptr[m + 1];
     float acc = 0.f;
-    for (int j = s; j < e; ++j) acc += x[(int64_t)(member ? member[j] : j) * C + c];
-    out[t] = mean ? acc / (float)(e - s) : acc;
+    for (int j = s; j < e; ++j) acc += ldf(x, (int64_t)(member ? member[j] : j) * C + c);
+    stf(out, t, mean ? acc / (float)(e - s) : acc);
   }
 }
 LOTUS_API int lotus_segment_sum_f32(const float* x, int C, const int32_t* seg_ptr, const int32_t* member, int M,
                                     int mean, float* out, void* stream_) {
   if (M <= 0) return 0;
   int64_t total = (int64_t)M * C;
-  k_segment_sum<<<min(ceil_div(total, 256), kNumSM * 16), 256, 0, (cudaStream_t)stream_>>>(x, C, seg_ptr, member, M, mean, out);
+  k_segment_sum<float><<<min(ceil_div(total, 256), kNumSM * 16), 256, 0, (cudaStream_t)stream_>>>(x, C, seg_ptr, member, M, mean, out);
+  LOTUS_CUDA_OK();
+  return 0;
+}
+LOTUS_API int lotus_segment_sum_bf16(const void* x, int C, const int32_t* seg_ptr, const int32_t* member, int M, int mean,
+                                     void* out, void* stream_) {
+  if (M <= 0) return 0;
+  int64_t total = (int64_t)M * C;
+  k_segment_sum<bf16_t><<<min(ceil_div(total, 256), kNumSM * 16), 256, 0, (cudaStream_t)stream_>>>((const bf16_t*)x, C, seg_ptr, member,
+                                                                                                  M, mean, (bf16_t*)out);
   LOTUS_CUDA_OK();
   return 0;
 }
 
 // out[p] = skip[p] + child[cluster[p]]
-__global__ void k_unpool_add(const float* __restrict__ skip, const float* __restrict__ child,
-                             const int32_t* __restrict__ cluster, int64_t total, int C, float* __restrict__ out) {
+template <typename T>
+__global__ void k_unpool_add(const T* __restrict__ skip, const T* __restrict__ child,
+                             const int32_t* __restrict__ cluster, int64_t total, int C, T* __restrict__ out) {
   for (int64_t t = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; t < total; t += (int64_t)gridDim.x * blockDim.x) {
     int p = (int)(t / C), c = (int)(t % C);
-    out[t] = skip[t] + child[(int64_t)cluster[p] * C + c];
+    stf(out, t, ldf(skip, t) + ldf(child, (int64_t)cluster[p] * C + c));
   }
 }
 LOTUS_API int lotus_unpool_add_f32(const float* skip, const float* child, const int32_t* cluster, int n, int C,
                                    float* out, void* stream_) {
   if (n <= 0) return 0;
   int64_t total = (int64_t)n * C;
-  k_unpool_add<<<min(ceil_div(total, 256), kNumSM * 16), 256, 0, (cudaStream_t)stream_>>>(skip, child, cluster, total, C, out);
+  k_unpool_add<float><<<min(ceil_div(total, 256), kNumSM * 16), 256, 0, (cudaStream_t)stream_>>>(skip, child, cluster, total, C, out);
+  LOTUS_CUDA_OK();
+  return 0;
+}
+LOTUS_API int lotus_unpool_add_bf16(const void* skip, const void* child, const int32_t* cluster, int n, int C, void* out,
+                                    void* stream_) {
+  if (n <= 0) return 0;
+  int64_t total = (int64_t)n * C;
+  k_unpool_add<bf16_t><<<min(ceil_div(total, 256), kNumSM * 16), 256, 0, (cudaStream_t)stream_>>>((const bf16_t*)skip, (const bf16_t*)child,
+                                                                                                 cluster, total, C, (bf16_t*)out);
   LOTUS_CUDA_OK();
   return 0;
 }

@@ -20,7 +20,30 @@ class PolicyEngine:
         self.seed_counter = 0
         self.last = {}                 # intermediates of the last forward when `self.record` is on
         self.record = False
+        # "fp32": validation mode (SIMT kernels, 1e-4 parity with the reference); "bf16": tensor-core mode
+        # (tcgen05 GEMMs / implicit-GEMM conv, bf16 activations, fp32 master weights, statistics and gradients)
+        self.precision = "fp32"
+        self._tc_weights = None
         load()                         # fail loudly if the CUDA library is absent
+
+    def _stage_weights(self):
+        """bf16 (+ transposed) copies of every weight the tensor-core kernels read, refreshed each forward"""
+        import torch.nn as nn
+        from .modules import SubMConv3d
+        if self._tc_weights is None:
+            ws = []
+            head = self.m.act_proj_head
+            skip = {id(head.heatmap_mlp[3]), id(head.action_mlp[3]), id(self.m.ptv3_model.embedding.stem.conv)}
+            for mod in self.m.modules():
+                if id(mod) in skip:
+                    continue
+                if isinstance(mod, (nn.Linear, SubMConv3d)):
+                    ws.append(mod.weight)
+            self._tc_weights = ws
+        L = load()
+        st = ops._st()
+        for w in self._tc_weights:
+            ops.stage_weight(L, w, st)
 
     # ------------------------------------------------------------------ helpers
     def _rec(self, name, t):
@@ -91,8 +114,8 @@ class PolicyEngine:
         geos = [CrossGeo(stg.cloud_off, tok_off, B, stg.max_cloud, max_tok) for stg in stages]
 
         stem = pt.embedding.stem
-        x = ops.subm_conv(feat, stem.conv.weight, None, stages[0].nbr5, stages[0].stride_alloc)
-        x = ops.batch_norm_act(x, stem.norm, train, gelu=True)
+        x = ops.subm_conv(feat, stem.conv.weight, None, stages[0].nbr5, stages[0].stride_alloc)     # Cin=7: fp32 SIMT in both modes
+        x = ops.batch_norm_act(x, stem.norm, train, gelu=True, out_bf16=(self.precision == "bf16"))
         self._rec("embedding", x)
         skips = []
         for s in range(S):
@@ -152,8 +175,16 @@ class PolicyEngine:
         if self.record:
             self.last = {}
 
+        bf = self.precision == "bf16"
+        if bf:
+            widths = list(m.ptv3_model.enc_channels) + list(m.ptv3_model.dec_channels)
+            if any(c % 64 for c in widths):
+                raise ValueError(f"tensor-core (bf16) mode needs channel widths that are multiples of 64, got {widths}; "
+                                 "use precision='fp32' for this configuration")
+            self._stage_weights()
         # context tokens (simple_policy_ptv3.py:413-429)
-        ctx = ops.linear(batch["txt_embeds"].float(), m.txt_fc.weight, m.txt_fc.bias)
+        txt = batch["txt_embeds"].float()
+        ctx = ops.linear(ops.to_bf16(txt) if bf else txt, m.txt_fc.weight, m.txt_fc.bias)
         tok_off = [0]
         for l in batch["txt_lens"]:
             tok_off.append(tok_off[-1] + int(l))
@@ -165,10 +196,11 @@ class PolicyEngine:
         # action head (simple_policy_ptv3.py:113-120,149-152)
         head = m.act_proj_head
         hm, am = head.heatmap_mlp, head.action_mlp
-        h = ops.act(ops.linear(x, hm[0].weight, hm[0].bias), "leaky", drop.site(head.dropout))
+        # (bf16 mode: the first layers run on tensor cores and emit fp32; the 90/217-wide logits stay fp32 SIMT)
+        h = ops.act(ops.linear(x, hm[0].weight, hm[0].bias, out_fp32=True), "leaky", drop.site(head.dropout))
         heat = ops.linear(h, hm[3].weight, hm[3].bias)                      # (N, 3*2*pos_bins): [n, c*NB + b]
         pc = ops.segment_max(x, s0.cloud_off, None, B)                     # per-cloud max over points
-        h2 = ops.act(ops.linear(pc, am[0].weight, am[0].bias), "leaky", drop.site(head.dropout))
+        h2 = ops.act(ops.linear(pc, am[0].weight, am[0].bias, out_fp32=True), "leaky", drop.site(head.dropout))
         action = ops.linear(h2, am[3].weight, am[3].bias)                  # (B, 72*3 + 1)
         self._rec("heat", heat)
         self._rec("action", action)

@@ -26,6 +26,54 @@ def _f32c(t):
     return t if t.is_contiguous() else t.contiguous()
 
 
+def _actc(t):
+    """activation tensor: fp32 (validation mode) or bf16 (tensor-core mode), contiguous, on the GPU"""
+    assert t.dtype in (torch.float32, torch.bfloat16) and t.is_cuda, (t.dtype, t.device)
+    return t if t.is_contiguous() else t.contiguous()
+
+
+def _sfx(t):
+    return "bf16" if t.dtype == torch.bfloat16 else "f32"
+
+
+def _es(t):
+    return t.element_size()
+
+
+# bf16 weight staging for the tensor-core path: parameter address -> (w_bf16, wt_bf16)
+STAGED = {}
+
+
+def stage_weight(L, w, st):
+    """fp32 master weight -> bf16 copy + transposed bf16 copy ([B][D][A]) used by the dgrad kernels"""
+    if w.ndim == 2:
+        A, D, B = w.shape[0], 1, w.shape[1]
+    else:
+        A, D, B = w.shape[0], w.shape[1] * w.shape[2] * w.shape[3], w.shape[4]
+    ent = STAGED.get(w.data_ptr())
+    if ent is None or ent[0].numel() != w.numel():
+        ent = (torch.empty(w.shape, device=w.device, dtype=torch.bfloat16),
+               torch.empty((B, D, A), device=w.device, dtype=torch.bfloat16))
+        STAGED[w.data_ptr()] = ent
+    L.lotus_cast_transpose_bf16(_p(w), _p(ent[0]), _p(ent[1]), A, D, B, st)
+    return ent
+
+
+def to_bf16(x):
+    L = load()
+    x = _f32c(x)
+    y = torch.empty(x.shape, device=x.device, dtype=torch.bfloat16)
+    L.lotus_convert(_p(x), _p(y), x.numel(), 0, _st())
+    return y
+
+
+def to_f32(x):
+    L = load()
+    y = torch.empty(x.shape, device=x.device, dtype=torch.float32)
+    L.lotus_convert(_p(x.contiguous()), _p(y), x.numel(), 1, _st())
+    return y
+
+
 class DropCtx:
     """dropout bookkeeping of one forward: a seed plus a running stream id per dropout site."""
 
@@ -65,50 +113,67 @@ def _grad_buf(param, needs):
 
 
 class LinearFn(torch.autograd.Function):
-    """y = [residual +] drop(x @ w.T + b)"""
+    """y = [residual +] drop(x @ w.T + b).  fp32 x -> SIMT validation kernel; bf16 x -> tcgen05 kernel (bf16 or fp32 out)"""
 
     @staticmethod
-    def forward(ctx, x, w, b, residual, drop):
+    def forward(ctx, x, w, b, residual, drop, out_fp32):
         L = load()
-        x, w = _f32c(x), _f32c(w)
+        x = _actc(x)
         M, K = x.shape
         N = w.shape[0]
-        y = torch.empty((M, N), device=x.device, dtype=torch.float32)
+        tc = x.dtype == torch.bfloat16
         if residual is not None:
-            residual = _f32c(residual)
-        L.lotus_linear_fwd_f32(_p(x), _p(w), _p(b), _p(residual), _p(y), M, N, K, 0, None, drop[0], drop[1], drop[2], _st())
+            residual = _actc(residual)
+        if tc:
+            wb, _ = STAGED[w.data_ptr()]
+            y = torch.empty((M, N), device=x.device, dtype=torch.float32 if out_fp32 else torch.bfloat16)
+            L.lotus_linear_fwd_bf16(_p(x), _p(wb), _p(b), _p(residual), _p(y), None, M, N, K, 0, int(out_fp32), drop[0], drop[1],
+                                    drop[2], _st())
+        else:
+            y = torch.empty((M, N), device=x.device, dtype=torch.float32)
+            L.lotus_linear_fwd_f32(_p(x), _p(w), _p(b), _p(residual), _p(y), M, N, K, 0, None, drop[0], drop[1], drop[2], _st())
         ctx.save_for_backward(x, w)
         ctx.bias = b
-        ctx.has_b, ctx.has_res, ctx.drop = b is not None, residual is not None, drop
+        ctx.has_b, ctx.has_res, ctx.drop, ctx.tc = b is not None, residual is not None, drop, tc
         return y
 
     @staticmethod
     def backward(ctx, dy):
         L = load()
         x, w = ctx.saved_tensors
-        dy = _f32c(dy)
         M, K = x.shape
         N = w.shape[0]
+        st = _st()
         dres = dy if ctx.has_res else None
+        if ctx.tc and dy.dtype == torch.float32:
+            dy = to_bf16(dy)
+        dy = _actc(dy)
+        sfx = _sfx(dy)
         if ctx.drop[0] > 0:
             dyd = torch.empty_like(dy)
-            L.lotus_dropout_f32(_p(dy), _p(dyd), dy.numel(), ctx.drop[0], ctx.drop[1], ctx.drop[2], _st())
+            getattr(L, "lotus_dropout_" + sfx)(_p(dy), _p(dyd), dy.numel(), ctx.drop[0], ctx.drop[1], ctx.drop[2], st)
             dy = dyd
         dx = dw = db = None
         if ctx.needs_input_grad[0]:
             dx = torch.empty_like(x)
-            L.lotus_linear_dgrad_f32(_p(dy), _p(w), None, _p(dx), M, N, K, _st())
+            if ctx.tc:
+                L.lotus_linear_dgrad_bf16(_p(dy), _p(STAGED[w.data_ptr()][1]), None, _p(dx), M, N, K, 0, st)
+            else:
+                L.lotus_linear_dgrad_f32(_p(dy), _p(w), None, _p(dx), M, N, K, st)
         wbuf, dw = _grad_buf(w, ctx.needs_input_grad[1])
         if wbuf is not None:
-            L.lotus_linear_wgrad_f32(_p(dy), _p(x), _p(wbuf), M, N, K, None, _st())
+            if ctx.tc:
+                L.lotus_linear_wgrad_bf16(_p(dy), _p(x), _p(wbuf), M, N, K, st)
+            else:
+                L.lotus_linear_wgrad_f32(_p(dy), _p(x), _p(wbuf), M, N, K, None, st)
         bbuf, db = _grad_buf(ctx.bias, ctx.has_b and ctx.needs_input_grad[2])
         if bbuf is not None:
-            L.lotus_colsum_f32(_p(dy), M, N, _p(bbuf), _st())
-        return dx, dw, db, dres, None
+            getattr(L, "lotus_colsum_" + sfx)(_p(dy), M, N, _p(bbuf), st)
+        return dx, dw, db, dres, None, None
 
 
-def linear(x, w, b=None, residual=None, drop=NO_DROP):
-    return LinearFn.apply(x, w, b, residual, drop)
+def linear(x, w, b=None, residual=None, drop=NO_DROP, out_fp32=False):
+    return LinearFn.apply(x, w, b, residual, drop, out_fp32)
 
 
 # ------------------------------------------------------------------------------------------ pointwise
@@ -120,10 +185,10 @@ class ActFn(torch.autograd.Function):
     @staticmethod
     def forward(ctx, x, kind, drop):
         L = load()
-        x = _f32c(x)
+        x = _actc(x)
         y = torch.empty_like(x)
         op = 0 if kind == "gelu" else 2
-        L.lotus_pointwise_f32(_p(x), None, _p(y), x.numel(), op, 0.02, drop[0], drop[1], drop[2], _st())
+        getattr(L, "lotus_pointwise_" + _sfx(x))(_p(x), None, _p(y), x.numel(), op, 0.02, drop[0], drop[1], drop[2], _st())
         ctx.save_for_backward(x)
         ctx.op, ctx.drop = op, drop
         return y
@@ -132,9 +197,10 @@ class ActFn(torch.autograd.Function):
     def backward(ctx, dy):
         L = load()
         (x,) = ctx.saved_tensors
-        dy = _f32c(dy)
+        dy = _actc(dy)
         dx = torch.empty_like(x)
-        L.lotus_pointwise_f32(_p(x), _p(dy), _p(dx), x.numel(), ctx.op + 1, 0.02, ctx.drop[0], ctx.drop[1], ctx.drop[2], _st())
+        getattr(L, "lotus_pointwise_" + _sfx(x))(_p(x), _p(dy), _p(dx), x.numel(), ctx.op + 1, 0.02, ctx.drop[0], ctx.drop[1],
+                                                 ctx.drop[2], _st())
         return dx, None, None
 
 
@@ -151,15 +217,15 @@ class LayerNormFn(torch.autograd.Function):
     @staticmethod
     def forward(ctx, x, g, b, eps, residual):
         L = load()
-        x = _f32c(x)
+        x = _actc(x)
         rows, C = x.shape
         y = torch.empty_like(x)
         mean = torch.empty(rows, device=x.device, dtype=torch.float32)
         rstd = torch.empty_like(mean)
         if residual is not None:
-            residual = _f32c(residual)
-        L.lotus_layernorm_fwd_f32(_p(x), 1, C, 0, _p(y), 1, C, 0, _p(residual), _p(g), _p(b), _p(mean), _p(rstd), rows, C,
-                                  eps, _st())
+            residual = _actc(residual)
+        getattr(L, "lotus_layernorm_fwd_" + _sfx(x))(_p(x), 1, C, 0, _p(y), 1, C, 0, _p(residual), _p(g), _p(b), _p(mean), _p(rstd),
+                                                     rows, C, eps, _st())
         ctx.save_for_backward(x, g, mean, rstd)
         ctx.beta = b
         ctx.has_res = residual is not None
@@ -169,13 +235,17 @@ class LayerNormFn(torch.autograd.Function):
     def backward(ctx, dy):
         L = load()
         x, g, mean, rstd = ctx.saved_tensors
-        dy = _f32c(dy)
+        dy = _actc(dy)
         rows, C = x.shape
         dx = torch.empty_like(x)
         gbuf, dg = _grad_buf(g, True)
         bbuf, db = _grad_buf(ctx.beta, True)
-        L.lotus_layernorm_bwd_f32(_p(dy), 1, C, 0, _p(x), 1, C, 0, _p(dx), 1, C, 0, _p(g), _p(mean), _p(rstd), _p(gbuf), _p(bbuf),
-                                  rows, C, 0, _st())
+        if x.dtype == torch.bfloat16:
+            L.lotus_layernorm_bwd_bf16(_p(dy), int(dy.dtype == torch.float32), 1, C, 0, _p(x), 1, C, 0, _p(dx), 1, C, 0, _p(g),
+                                       _p(mean), _p(rstd), _p(gbuf), _p(bbuf), rows, C, 0, _st())
+        else:
+            L.lotus_layernorm_bwd_f32(_p(dy), 1, C, 0, _p(x), 1, C, 0, _p(dx), 1, C, 0, _p(g), _p(mean), _p(rstd), _p(gbuf),
+                                      _p(bbuf), rows, C, 0, _st())
         return dx, dg, db, None, (dy if ctx.has_res else None)
 
 
@@ -184,47 +254,59 @@ def layer_norm(x, g, b, eps=1e-5, residual=None):
 
 
 class BatchNormActFn(torch.autograd.Function):
-    """y = [gelu](BatchNorm1d(x)); updates running stats in place when training"""
+    """y = [gelu](BatchNorm1d(x)); updates running stats in place when training.  out_bf16: y (and dy) bf16 while x may
+    be fp32 (the stem conv runs in fp32)"""
 
     @staticmethod
-    def forward(ctx, x, g, b, run_mean, run_var, train, eps, momentum, gelu):
+    def forward(ctx, x, g, b, run_mean, run_var, train, eps, momentum, gelu, out_bf16):
         L = load()
-        x = _f32c(x)
+        x = _actc(x)
         rows, C = x.shape
-        y = torch.empty_like(x)
+        bf = out_bf16 or x.dtype == torch.bfloat16
+        y = torch.empty((rows, C), device=x.device, dtype=torch.bfloat16 if bf else torch.float32)
         mean = torch.empty(C, device=x.device, dtype=torch.float32)
         rstd = torch.empty_like(mean)
         scratch = torch.empty_like(mean)
-        L.lotus_batchnorm_fwd_f32(_p(x), _p(y), rows, C, _p(g), _p(b), _p(run_mean), _p(run_var), _p(mean), _p(rstd),
-                                  _p(scratch), int(train), eps, momentum, int(gelu), _st())
+        if bf:
+            L.lotus_batchnorm_fwd_bf16(_p(x), int(x.dtype == torch.float32), _p(y), rows, C, _p(g), _p(b), _p(run_mean), _p(run_var),
+                                       _p(mean), _p(rstd), _p(scratch), int(train), eps, momentum, int(gelu), _st())
+        else:
+            L.lotus_batchnorm_fwd_f32(_p(x), _p(y), rows, C, _p(g), _p(b), _p(run_mean), _p(run_var), _p(mean), _p(rstd),
+                                      _p(scratch), int(train), eps, momentum, int(gelu), _st())
         ctx.save_for_backward(x, g, b, mean, rstd)
-        ctx.train, ctx.gelu = train, gelu
+        ctx.train, ctx.gelu, ctx.bf = train, gelu, bf
         return y
 
     @staticmethod
     def backward(ctx, dy):
         L = load()
         x, g, b, mean, rstd = ctx.saved_tensors
-        dy = _f32c(dy)
+        dy = _actc(dy)
         rows, C = x.shape
         dx = torch.empty_like(x)
         dg = torch.zeros(C, device=x.device, dtype=torch.float32)
         db = torch.zeros_like(dg)
-        L.lotus_batchnorm_bwd_f32(_p(dy), _p(x), rows, C, _p(g), _p(b), _p(mean), _p(rstd), _p(dx), _p(dg), _p(db),
-                                  int(ctx.train), int(ctx.gelu), _st())
+        if ctx.bf:
+            if dy.dtype == torch.float32:
+                dy = to_bf16(dy)
+            L.lotus_batchnorm_bwd_bf16(_p(dy), _p(x), int(x.dtype == torch.float32), rows, C, _p(g), _p(b), _p(mean), _p(rstd),
+                                       _p(dx), _p(dg), _p(db), int(ctx.train), int(ctx.gelu), _st())
+        else:
+            L.lotus_batchnorm_bwd_f32(_p(dy), _p(x), rows, C, _p(g), _p(b), _p(mean), _p(rstd), _p(dx), _p(dg), _p(db),
+                                      int(ctx.train), int(ctx.gelu), _st())
         for param, d in ((g, dg), (b, db)):
             s = _sink(param)
             if s is not None:
                 L.lotus_pointwise_f32(_p(d), _p(s), _p(s), C, 4, 0.0, 0.0, 0, 0, _st())     # sink += batch sums
         if _sink(g) is not None:
             dg = db = None
-        return dx, dg, db, None, None, None, None, None, None
+        return dx, dg, db, None, None, None, None, None, None, None
 
 
-def batch_norm_act(x, bn, train, gelu=True):
+def batch_norm_act(x, bn, train, gelu=True, out_bf16=False):
     if train:
         bn.num_batches_tracked.add_(1)
-    return BatchNormActFn.apply(x, bn.weight, bn.bias, bn.running_mean, bn.running_var, train, bn.eps, bn.momentum, gelu)
+    return BatchNormActFn.apply(x, bn.weight, bn.bias, bn.running_mean, bn.running_var, train, bn.eps, bn.momentum, gelu, out_bf16)
 
 
 # ------------------------------------------------------------------------------------------ sparse conv
@@ -234,33 +316,44 @@ class SubmConvFn(torch.autograd.Function):
     @staticmethod
     def forward(ctx, x, w, b, nbr, nbr_stride):
         L = load()
-        x, w = _f32c(x), _f32c(w)
+        x = _actc(x)
         n, cin = x.shape
         cout = w.shape[0]
         k3 = w.shape[1] * w.shape[2] * w.shape[3]
-        y = torch.empty((n, cout), device=x.device, dtype=torch.float32)
-        L.lotus_subm_conv_fwd_f32(_p(x), _p(w), _p(b), _p(y), _p(nbr), nbr_stride, n, cin, cout, k3, _st())
+        tc = x.dtype == torch.bfloat16
+        y = torch.empty((n, cout), device=x.device, dtype=x.dtype)
+        if tc:
+            L.lotus_subm_conv_fwd_bf16(_p(x), _p(STAGED[w.data_ptr()][0]), _p(b), _p(y), _p(nbr), nbr_stride, n, cin, cout, k3, 0, _st())
+        else:
+            L.lotus_subm_conv_fwd_f32(_p(x), _p(w), _p(b), _p(y), _p(nbr), nbr_stride, n, cin, cout, k3, _st())
         ctx.save_for_backward(x, w, nbr)
         ctx.bias = b
-        ctx.meta = (n, cin, cout, k3, nbr_stride, b is not None)
+        ctx.meta = (n, cin, cout, k3, nbr_stride, b is not None, tc)
         return y
 
     @staticmethod
     def backward(ctx, dy):
         L = load()
         x, w, nbr = ctx.saved_tensors
-        n, cin, cout, k3, nbr_stride, has_b = ctx.meta
-        dy = _f32c(dy)
+        n, cin, cout, k3, nbr_stride, has_b, tc = ctx.meta
+        dy = _actc(dy)
+        st = _st()
         dx = dw = db = None
         if ctx.needs_input_grad[0]:
             dx = torch.empty_like(x)
-            L.lotus_subm_conv_dgrad_f32(_p(dy), _p(w), _p(dx), _p(nbr), nbr_stride, n, cin, cout, k3, _st())
+            if tc:
+                L.lotus_subm_conv_dgrad_bf16(_p(dy), _p(STAGED[w.data_ptr()][1]), _p(dx), _p(nbr), nbr_stride, n, cin, cout, k3, 0, st)
+            else:
+                L.lotus_subm_conv_dgrad_f32(_p(dy), _p(w), _p(dx), _p(nbr), nbr_stride, n, cin, cout, k3, st)
         wbuf, dw = _grad_buf(w, ctx.needs_input_grad[1])
         if wbuf is not None:
-            L.lotus_subm_conv_wgrad_f32(_p(dy), _p(x), _p(wbuf), _p(nbr), nbr_stride, n, cin, cout, k3, _st())
+            if tc:
+                L.lotus_subm_conv_wgrad_bf16(_p(dy), _p(x), _p(wbuf), _p(nbr), nbr_stride, n, cin, cout, k3, st)
+            else:
+                L.lotus_subm_conv_wgrad_f32(_p(dy), _p(x), _p(wbuf), _p(nbr), nbr_stride, n, cin, cout, k3, st)
         bbuf, db = _grad_buf(ctx.bias, has_b and ctx.needs_input_grad[2])
         if bbuf is not None:
-            L.lotus_colsum_f32(_p(dy), n, cout, _p(bbuf), _st())
+            getattr(L, "lotus_colsum_" + _sfx(dy))(_p(dy), n, cout, _p(bbuf), st)
         return dx, dw, db, None, None
 
 
@@ -273,35 +366,35 @@ def subm_conv(x, w, b, nbr, nbr_stride):
 
 class PatchAttnFn(torch.autograd.Function):
     """qkv (N,3C) raw projections -> per-head LN on q,k -> attention inside each serialized patch -> (N,C) in
-    point order (gather by order[pad] and scatter by unpad[inverse] fused)."""
+    point order (gather by order[pad] and scatter by unpad[inverse] fused).  fp32 or bf16 activations."""
 
     @staticmethod
     def forward(ctx, qkv, qg, qb, kg, kb, rpe_table, plan, H, qk_norm, attn_drop, grid, pos_bnd):
         L = load()
-        qkv = _f32c(qkv)
+        qkv = _actc(qkv)
+        sfx, es = _sfx(qkv), _es(qkv)
         N, C3 = qkv.shape
         C = C3 // 3
         D = C // H
         dev = qkv.device
         st = _st()
+        ln_fwd = getattr(L, "lotus_layernorm_fwd_" + sfx)
         if qk_norm:
-            qh = torch.empty((N, C), device=dev, dtype=torch.float32)
+            qh = torch.empty((N, C), device=dev, dtype=qkv.dtype)
             kh = torch.empty_like(qh)
             stats = torch.empty((4, N * H), device=dev, dtype=torch.float32)
-            L.lotus_layernorm_fwd_f32(_p(qkv), H, C3, D, _p(qh), 1, D, 0, None, _p(qg), _p(qb), _p(stats[0]), _p(stats[1]),
-                                      N * H, D, 1e-6, st)
-            L.lotus_layernorm_fwd_f32(_po(qkv, C * 4), H, C3, D, _p(kh), 1, D, 0, None, _p(kg), _p(kb), _p(stats[2]),
-                                      _p(stats[3]), N * H, D, 1e-6, st)
+            ln_fwd(_p(qkv), H, C3, D, _p(qh), 1, D, 0, None, _p(qg), _p(qb), _p(stats[0]), _p(stats[1]), N * H, D, 1e-6, st)
+            ln_fwd(_po(qkv, C * es), H, C3, D, _p(kh), 1, D, 0, None, _p(kg), _p(kb), _p(stats[2]), _p(stats[3]), N * H, D, 1e-6, st)
             q_ptr, k_ptr, ldq = _p(qh), _p(kh), C
         else:
             qh = kh = stats = None
-            q_ptr, k_ptr, ldq = _p(qkv), _po(qkv, C * 4), C3
-        out = torch.empty((N, C), device=dev, dtype=torch.float32)
+            q_ptr, k_ptr, ldq = _p(qkv), _po(qkv, C * es), C3
+        out = torch.empty((N, C), device=dev, dtype=qkv.dtype)
         lse = torch.empty((plan.n_pad * H,), device=dev, dtype=torch.float32)
-        L.lotus_patch_attn_fwd_f32(q_ptr, k_ptr, _po(qkv, 2 * C * 4), ldq, ldq, C3, _p(plan.gather_idx), _p(plan.slot_of_point),
-                                   _p(plan.cu_seqlens), plan.n_patches, plan.max_len, H, D, float(D) ** -0.5,
-                                   _p(rpe_table), _p(grid) if rpe_table is not None else None, pos_bnd, _p(out), C, _p(lse),
-                                   attn_drop[0], attn_drop[1], attn_drop[2], st)
+        getattr(L, "lotus_patch_attn_fwd_" + sfx)(
+            q_ptr, k_ptr, _po(qkv, 2 * C * es), ldq, ldq, C3, _p(plan.gather_idx), _p(plan.slot_of_point), _p(plan.cu_seqlens),
+            plan.n_patches, plan.max_len, H, D, float(D) ** -0.5, _p(rpe_table), _p(grid) if rpe_table is not None else None,
+            pos_bnd, _p(out), C, _p(lse), attn_drop[0], attn_drop[1], attn_drop[2], st)
         ctx.save_for_backward(qkv, qg, kg, qh, kh, stats, out, lse, rpe_table, grid if rpe_table is not None else None)
         ctx.plan, ctx.H, ctx.qk_norm, ctx.attn_drop, ctx.pos_bnd = plan, H, qk_norm, attn_drop, pos_bnd
         ctx.nb = (qb, kb)
@@ -312,34 +405,58 @@ class PatchAttnFn(torch.autograd.Function):
         L = load()
         qkv, qg, kg, qh, kh, stats, out, lse, rpe_table, grid = ctx.saved_tensors
         plan, H = ctx.plan, ctx.H
-        dout = _f32c(dout)
+        dout = _actc(dout)
+        bf = qkv.dtype == torch.bfloat16
+        sfx, es = _sfx(qkv), _es(qkv)
         N, C3 = qkv.shape
         C = C3 // 3
         D = C // H
         dev = qkv.device
         st = _st()
-        dqkv = torch.zeros_like(qkv)
+        f32 = dict(device=dev, dtype=torch.float32)
         drpe = torch.zeros_like(rpe_table) if rpe_table is not None else None
+        # fp32 gradient accumulators of the attention core (alias slots add a second contribution -> atomics)
+        if bf or ctx.qk_norm:
+            dqh, dkh = torch.zeros((N, C), **f32), torch.zeros((N, C), **f32)
+        if bf:
+            dvh = torch.zeros((N, C), **f32)
+            dqkv = torch.empty_like(qkv)
+            dv_ptr, lddv = _p(dvh), C
+        else:
+            dqkv = torch.zeros_like(qkv)
+            dv_ptr, lddv = _po(dqkv, 2 * C * 4), C3
         if ctx.qk_norm:
-            dqh = torch.zeros((N, C), device=dev, dtype=torch.float32)
-            dkh = torch.zeros_like(dqh)
             q_ptr, k_ptr, ldq = _p(qh), _p(kh), C
+            dq_ptr, dk_ptr, lddq = _p(dqh), _p(dkh), C
+        elif bf:
+            q_ptr, k_ptr, ldq = _p(qkv), _po(qkv, C * es), C3
             dq_ptr, dk_ptr, lddq = _p(dqh), _p(dkh), C
         else:
             q_ptr, k_ptr, ldq = _p(qkv), _po(qkv, C * 4), C3
             dq_ptr, dk_ptr, lddq = _p(dqkv), _po(dqkv, C * 4), C3
-        L.lotus_patch_attn_bwd_f32(q_ptr, k_ptr, _po(qkv, 2 * C * 4), ldq, ldq, C3, _p(plan.gather_idx), _p(plan.slot_of_point),
-                                   _p(plan.cu_seqlens), plan.n_patches, plan.max_len, H, D, float(D) ** -0.5, _p(rpe_table),
-                                   _p(grid), ctx.pos_bnd, _p(drpe), _p(out), _p(dout), C, _p(lse), dq_ptr, dk_ptr,
-                                   _po(dqkv, 2 * C * 4), lddq, lddq, C3, ctx.attn_drop[0], ctx.attn_drop[1], ctx.attn_drop[2], st)
+        getattr(L, "lotus_patch_attn_bwd_" + sfx)(
+            q_ptr, k_ptr, _po(qkv, 2 * C * es), ldq, ldq, C3, _p(plan.gather_idx), _p(plan.slot_of_point), _p(plan.cu_seqlens),
+            plan.n_patches, plan.max_len, H, D, float(D) ** -0.5, _p(rpe_table), _p(grid), ctx.pos_bnd, _p(drpe), _p(out), _p(dout),
+            C, _p(lse), dq_ptr, dk_ptr, dv_ptr, lddq, lddq, lddv, ctx.attn_drop[0], ctx.attn_drop[1], ctx.attn_drop[2], st)
         dqg = dqb = dkg = dkb = None
         if ctx.qk_norm:
             (qgb, dqg), (qbb, dqb) = _grad_buf(qg, True), _grad_buf(ctx.nb[0], True)
             (kgb, dkg), (kbb, dkb) = _grad_buf(kg, True), _grad_buf(ctx.nb[1], True)
-            L.lotus_layernorm_bwd_f32(_p(dqh), 1, D, 0, _p(qkv), H, C3, D, _p(dqkv), H, C3, D, _p(qg), _p(stats[0]), _p(stats[1]),
-                                      _p(qgb), _p(qbb), N * H, D, 0, st)
-            L.lotus_layernorm_bwd_f32(_p(dkh), 1, D, 0, _po(qkv, C * 4), H, C3, D, _po(dqkv, C * 4), H, C3, D, _p(kg),
-                                      _p(stats[2]), _p(stats[3]), _p(kgb), _p(kbb), N * H, D, 0, st)
+            if bf:
+                L.lotus_layernorm_bwd_bf16(_p(dqh), 1, 1, D, 0, _p(qkv), H, C3, D, _p(dqkv), H, C3, D, _p(qg), _p(stats[0]),
+                                           _p(stats[1]), _p(qgb), _p(qbb), N * H, D, 0, st)
+                L.lotus_layernorm_bwd_bf16(_p(dkh), 1, 1, D, 0, _po(qkv, C * es), H, C3, D, _po(dqkv, C * es), H, C3, D, _p(kg),
+                                           _p(stats[2]), _p(stats[3]), _p(kgb), _p(kbb), N * H, D, 0, st)
+            else:
+                L.lotus_layernorm_bwd_f32(_p(dqh), 1, D, 0, _p(qkv), H, C3, D, _p(dqkv), H, C3, D, _p(qg), _p(stats[0]), _p(stats[1]),
+                                          _p(qgb), _p(qbb), N * H, D, 0, st)
+                L.lotus_layernorm_bwd_f32(_p(dkh), 1, D, 0, _po(qkv, C * 4), H, C3, D, _po(dqkv, C * 4), H, C3, D, _p(kg),
+                                          _p(stats[2]), _p(stats[3]), _p(kgb), _p(kbb), N * H, D, 0, st)
+        elif bf:
+            L.lotus_convert_rows_f32_to_bf16(_p(dqh), C, _p(dqkv), C3, N, C, st)
+            L.lotus_convert_rows_f32_to_bf16(_p(dkh), C, _po(dqkv, C * es), C3, N, C, st)
+        if bf:
+            L.lotus_convert_rows_f32_to_bf16(_p(dvh), C, _po(dqkv, 2 * C * es), C3, N, C, st)
         return dqkv, dqg, dqb, dkg, dkb, drpe, None, None, None, None, None, None
 
 
@@ -359,29 +476,30 @@ class CrossAttnFn(torch.autograd.Function):
     @staticmethod
     def forward(ctx, q, kv, qg, qb, kg, kb, geo, H, qk_norm, attn_drop):
         L = load()
-        q, kv = _f32c(q), _f32c(kv)
+        q, kv = _actc(q), _actc(kv)
+        sfx, es = _sfx(q), _es(q)
         N, C = q.shape
         Lt = kv.shape[0]
         D = C // H
         dev = q.device
         st = _st()
+        ln_fwd = getattr(L, "lotus_layernorm_fwd_" + sfx)
         if qk_norm:
             qh = torch.empty_like(q)
-            kh = torch.empty((Lt, C), device=dev, dtype=torch.float32)
+            kh = torch.empty((Lt, C), device=dev, dtype=q.dtype)
             qs = torch.empty((2, N * H), device=dev, dtype=torch.float32)
             ks = torch.empty((2, Lt * H), device=dev, dtype=torch.float32)
-            L.lotus_layernorm_fwd_f32(_p(q), 1, D, 0, _p(qh), 1, D, 0, None, _p(qg), _p(qb), _p(qs[0]), _p(qs[1]), N * H, D, 1e-6, st)
-            L.lotus_layernorm_fwd_f32(_p(kv), H, 2 * C, D, _p(kh), 1, D, 0, None, _p(kg), _p(kb), _p(ks[0]), _p(ks[1]), Lt * H, D,
-                                      1e-6, st)
+            ln_fwd(_p(q), 1, D, 0, _p(qh), 1, D, 0, None, _p(qg), _p(qb), _p(qs[0]), _p(qs[1]), N * H, D, 1e-6, st)
+            ln_fwd(_p(kv), H, 2 * C, D, _p(kh), 1, D, 0, None, _p(kg), _p(kb), _p(ks[0]), _p(ks[1]), Lt * H, D, 1e-6, st)
             q_ptr, k_ptr, ldk = _p(qh), _p(kh), C
         else:
             qh = kh = qs = ks = None
             q_ptr, k_ptr, ldk = _p(q), _p(kv), 2 * C
         out = torch.empty_like(q)
         lse = torch.empty((N * H,), device=dev, dtype=torch.float32)
-        L.lotus_cross_attn_fwd_f32(q_ptr, C, k_ptr, _po(kv, C * 4), ldk, 2 * C, _p(geo.pt_off), _p(geo.tok_off), geo.B,
-                                   geo.max_points, geo.max_tokens, H, D, float(D) ** -0.5, _p(out), C, _p(lse),
-                                   attn_drop[0], attn_drop[1], attn_drop[2], st)
+        getattr(L, "lotus_cross_attn_fwd_" + sfx)(q_ptr, C, k_ptr, _po(kv, C * es), ldk, 2 * C, _p(geo.pt_off), _p(geo.tok_off), geo.B,
+                                                  geo.max_points, geo.max_tokens, H, D, float(D) ** -0.5, _p(out), C, _p(lse),
+                                                  attn_drop[0], attn_drop[1], attn_drop[2], st)
         ctx.save_for_backward(q, kv, qg, kg, qh, kh, qs, ks, out, lse)
         ctx.geo, ctx.H, ctx.qk_norm, ctx.attn_drop = geo, H, qk_norm, attn_drop
         ctx.nb = (qb, kb)
@@ -392,34 +510,57 @@ class CrossAttnFn(torch.autograd.Function):
         L = load()
         q, kv, qg, kg, qh, kh, qs, ks, out, lse = ctx.saved_tensors
         geo, H = ctx.geo, ctx.H
-        dout = _f32c(dout)
+        dout = _actc(dout)
+        bf = q.dtype == torch.bfloat16
+        sfx, es = _sfx(q), _es(q)
         N, C = q.shape
         Lt = kv.shape[0]
         D = C // H
         dev = q.device
         st = _st()
+        f32 = dict(device=dev, dtype=torch.float32)
         dq = torch.empty_like(q)
-        dkv = torch.zeros_like(kv)
+        if bf or ctx.qk_norm:
+            dqh, dkh = torch.empty((N, C), **f32), torch.zeros((Lt, C), **f32)
+        if bf:
+            dvh = torch.zeros((Lt, C), **f32)
+            dkv = torch.empty_like(kv)
+            dv_ptr, lddv = _p(dvh), C
+        else:
+            dkv = torch.zeros_like(kv)
+            dv_ptr, lddv = _po(dkv, C * 4), 2 * C
         if ctx.qk_norm:
-            dqh = torch.empty_like(q)
-            dkh = torch.zeros((Lt, C), device=dev, dtype=torch.float32)
             q_ptr, k_ptr, ldk = _p(qh), _p(kh), C
+            dq_ptr, dk_ptr, lddk = _p(dqh), _p(dkh), C
+        elif bf:
+            q_ptr, k_ptr, ldk = _p(q), _p(kv), 2 * C
             dq_ptr, dk_ptr, lddk = _p(dqh), _p(dkh), C
         else:
             q_ptr, k_ptr, ldk = _p(q), _p(kv), 2 * C
             dq_ptr, dk_ptr, lddk = _p(dq), _p(dkv), 2 * C
-        L.lotus_cross_attn_bwd_f32(q_ptr, C, k_ptr, _po(kv, C * 4), ldk, 2 * C, _p(geo.pt_off), _p(geo.tok_off), geo.B,
-                                   geo.max_points, geo.max_tokens, H, D, float(D) ** -0.5, _p(out), _p(dout), C, _p(lse),
-                                   dq_ptr, C, dk_ptr, _po(dkv, C * 4), lddk, 2 * C, ctx.attn_drop[0], ctx.attn_drop[1],
-                                   ctx.attn_drop[2], st)
+        getattr(L, "lotus_cross_attn_bwd_" + sfx)(q_ptr, C, k_ptr, _po(kv, C * es), ldk, 2 * C, _p(geo.pt_off), _p(geo.tok_off), geo.B,
+                                                  geo.max_points, geo.max_tokens, H, D, float(D) ** -0.5, _p(out), _p(dout), C,
+                                                  _p(lse), dq_ptr, C, dk_ptr, dv_ptr, lddk, lddv, ctx.attn_drop[0],
+                                                  ctx.attn_drop[1], ctx.attn_drop[2], st)
         dqg = dqb = dkg = dkb = None
         if ctx.qk_norm:
             (qgb, dqg), (qbb, dqb) = _grad_buf(qg, True), _grad_buf(ctx.nb[0], True)
             (kgb, dkg), (kbb, dkb) = _grad_buf(kg, True), _grad_buf(ctx.nb[1], True)
-            L.lotus_layernorm_bwd_f32(_p(dqh), 1, D, 0, _p(q), 1, D, 0, _p(dq), 1, D, 0, _p(qg), _p(qs[0]), _p(qs[1]), _p(qgb),
-                                      _p(qbb), N * H, D, 0, st)
-            L.lotus_layernorm_bwd_f32(_p(dkh), 1, D, 0, _p(kv), H, 2 * C, D, _p(dkv), H, 2 * C, D, _p(kg), _p(ks[0]), _p(ks[1]),
-                                      _p(kgb), _p(kbb), Lt * H, D, 0, st)
+            if bf:
+                L.lotus_layernorm_bwd_bf16(_p(dqh), 1, 1, D, 0, _p(q), 1, D, 0, _p(dq), 1, D, 0, _p(qg), _p(qs[0]), _p(qs[1]), _p(qgb),
+                                           _p(qbb), N * H, D, 0, st)
+                L.lotus_layernorm_bwd_bf16(_p(dkh), 1, 1, D, 0, _p(kv), H, 2 * C, D, _p(dkv), H, 2 * C, D, _p(kg), _p(ks[0]),
+                                           _p(ks[1]), _p(kgb), _p(kbb), Lt * H, D, 0, st)
+            else:
+                L.lotus_layernorm_bwd_f32(_p(dqh), 1, D, 0, _p(q), 1, D, 0, _p(dq), 1, D, 0, _p(qg), _p(qs[0]), _p(qs[1]), _p(qgb),
+                                          _p(qbb), N * H, D, 0, st)
+                L.lotus_layernorm_bwd_f32(_p(dkh), 1, D, 0, _p(kv), H, 2 * C, D, _p(dkv), H, 2 * C, D, _p(kg), _p(ks[0]), _p(ks[1]),
+                                          _p(kgb), _p(kbb), Lt * H, D, 0, st)
+        elif bf:
+            L.lotus_convert_rows_f32_to_bf16(_p(dqh), C, _p(dq), C, N, C, st)
+            L.lotus_convert_rows_f32_to_bf16(_p(dkh), C, _p(dkv), 2 * C, Lt, C, st)
+        if bf:
+            L.lotus_convert_rows_f32_to_bf16(_p(dvh), C, _po(dkv, C * es), 2 * C, Lt, C, st)
         return dq, dkv, dqg, dqb, dkg, dkb, None, None, None, None
 
 
@@ -438,22 +579,24 @@ class SegmentMaxFn(torch.autograd.Function):
     @staticmethod
     def forward(ctx, x, seg_ptr, member, M):
         L = load()
-        x = _f32c(x)
+        x = _actc(x)
         C = x.shape[1]
-        out = torch.empty((M, C), device=x.device, dtype=torch.float32)
+        out = torch.empty((M, C), device=x.device, dtype=x.dtype)
         arg = torch.empty((M, C), device=x.device, dtype=torch.int32)
-        L.lotus_segment_max_fwd_f32(_p(x), C, _p(seg_ptr), _p(member), M, _p(out), _p(arg), _st())
+        getattr(L, "lotus_segment_max_fwd_" + _sfx(x))(_p(x), C, _p(seg_ptr), _p(member), M, _p(out), _p(arg), _st())
         ctx.save_for_backward(arg)
-        ctx.shape = x.shape
+        ctx.shape, ctx.dtype = x.shape, x.dtype
         return out
 
     @staticmethod
     def backward(ctx, dy):
         L = load()
         (arg,) = ctx.saved_tensors
-        dy = _f32c(dy)
-        dx = torch.zeros(ctx.shape, device=dy.device, dtype=torch.float32)
-        L.lotus_segment_max_bwd_f32(_p(dy), _p(arg), arg.shape[0], arg.shape[1], _p(dx), _st())
+        dy = _actc(dy)
+        if dy.dtype != ctx.dtype:
+            dy = to_bf16(dy) if ctx.dtype == torch.bfloat16 else to_f32(dy)
+        dx = torch.zeros(ctx.shape, device=dy.device, dtype=ctx.dtype)
+        getattr(L, "lotus_segment_max_bwd_" + _sfx(dy))(_p(dy), _p(arg), arg.shape[0], arg.shape[1], _p(dx), _st())
         return dx, None, None, None
 
 
@@ -462,7 +605,7 @@ def segment_max(x, seg_ptr, member, M):
 
 
 def segment_mean(x, seg_ptr, member, M):
-    """no-grad segment mean (pooled coordinates)"""
+    """no-grad segment mean (pooled coordinates, fp32)"""
     L = load()
     x = _f32c(x)
     out = torch.empty((M, x.shape[1]), device=x.device, dtype=torch.float32)
@@ -476,10 +619,10 @@ class UnpoolAddFn(torch.autograd.Function):
     @staticmethod
     def forward(ctx, skip, child, cluster, seg_ptr, member):
         L = load()
-        skip, child = _f32c(skip), _f32c(child)
+        skip, child = _actc(skip), _actc(child)
         n, C = skip.shape
         out = torch.empty_like(skip)
-        L.lotus_unpool_add_f32(_p(skip), _p(child), _p(cluster), n, C, _p(out), _st())
+        getattr(L, "lotus_unpool_add_" + _sfx(skip))(_p(skip), _p(child), _p(cluster), n, C, _p(out), _st())
         ctx.save_for_backward(seg_ptr, member)
         ctx.M = child.shape[0]
         return out
@@ -488,9 +631,9 @@ class UnpoolAddFn(torch.autograd.Function):
     def backward(ctx, dy):
         L = load()
         seg_ptr, member = ctx.saved_tensors
-        dy = _f32c(dy)
-        dchild = torch.empty((ctx.M, dy.shape[1]), device=dy.device, dtype=torch.float32)
-        L.lotus_segment_sum_f32(_p(dy), dy.shape[1], _p(seg_ptr), _p(member), ctx.M, 0, _p(dchild), _st())
+        dy = _actc(dy)
+        dchild = torch.empty((ctx.M, dy.shape[1]), device=dy.device, dtype=dy.dtype)
+        getattr(L, "lotus_segment_sum_" + _sfx(dy))(_p(dy), dy.shape[1], _p(seg_ptr), _p(member), ctx.M, 0, _p(dchild), _st())
         return dy, dchild, None, None, None
 
 

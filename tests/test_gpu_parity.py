@@ -538,3 +538,31 @@ def test_checkpoint_roundtrip_strict(gold_small):
     m2 = pkg("policy").build_parameter_shell(pkg("config").ConfigNode(gold_small["config"]))
     missing = m2.load_state_dict(sd, strict=True)
     assert not missing.missing_keys and not missing.unexpected_keys
+
+
+# ------------------------------------------------------------------------------------------------ bf16 tensor-core mode
+def test_policy_bf16_mode_tracks_fp32_reference(gold_prod):
+    """tensor-core mode (bf16 activations, tcgen05 GEMMs) at production width (channel widths must be multiples of 64):
+    losses within 2% of the fp32 reference golden values and gradients pointing the same way."""
+    for g in (gold_prod,):
+        cfg, model = make_model(g)
+        model = model.to(DEV).train()
+        eng = model.engine()
+        eng.forced_perms = g["perms"]
+        eng.precision = "bf16"
+        batch = {k: (v.clone() if isinstance(v, torch.Tensor) else v) for k, v in g["batch"].items()}
+        final, losses = model(batch, compute_loss=True, compute_final_action=False)
+        for k in ("pos", "rot", "open", "total"):
+            assert abs(losses[k].item() - g["losses"][k].item()) <= 2e-2 * abs(g["losses"][k].item()), (k, losses[k].item())
+        losses["total"].backward()
+        grads = {k: p.grad for k, p in model.named_parameters() if p.grad is not None}
+        assert set(grads) == set(g["grad_norms"])
+        big = sorted(g["grad_norms"].items(), key=lambda kv: -kv[1])[:40]
+        for k, n in big:
+            gn = grads[k].norm().item()
+            assert abs(gn - n) <= 0.1 * n, (k, gn, n)
+        for k, ref in g["grads"].items():
+            if ref.norm().item() > 1e-3 * big[0][1]:
+                a, b = grads[k].flatten().double().cpu(), ref.flatten().double()
+                cos = (a @ b / (a.norm() * b.norm())).item()
+                assert cos > 0.95, (k, cos)          # bf16 rounding through ~60 layers; fp32 mode is the 1e-4 path

@@ -46,6 +46,24 @@ DOC = {
     "lotus_subm_conv_fwd_bf16": "bf16 tensor-core implicit-GEMM form of spconv.SubMConv3d forward (CPE k=3): model.py:616-622; gathered operand staged by cp.async.",
     "lotus_subm_conv_dgrad_bf16": "bf16 tensor-core backward of SubMConv3d w.r.t. its input features (mirrored taps).",
     "lotus_subm_conv_wgrad_bf16": "bf16 tensor-core backward of SubMConv3d w.r.t. its weight (per-tap split-K, fp32 accumulate).",
+    "lotus_layernorm_fwd_bf16": "bf16-activation form of lotus_layernorm_fwd_f32 (same reference call sites).",
+    "lotus_layernorm_bwd_bf16": "bf16-activation form of lotus_layernorm_bwd_f32 (dy may be fp32: gradients leaving the attention kernels).",
+    "lotus_colsum_bf16": "bf16-activation form of lotus_colsum_f32 (bias gradients).",
+    "lotus_batchnorm_fwd_bf16": "bf16-activation form of lotus_batchnorm_fwd_f32 (the stem feeds it fp32): model.py:932,785-788,854-857.",
+    "lotus_batchnorm_bwd_bf16": "bf16-activation form of lotus_batchnorm_bwd_f32.",
+    "lotus_pointwise_bf16": "bf16-activation form of lotus_pointwise_f32 (GELU / LeakyReLU and derivatives with fused dropout).",
+    "lotus_convert": "fp32 <-> bf16 conversion between the fp32 head/loss tensors and the bf16 trunk.",
+    "lotus_convert_rows_f32_to_bf16": "strided fp32 -> bf16 row copy (attention dV into the packed dqkv gradient): model.py:541 (torch.stack of q,k,v) in reverse.",
+    "lotus_cast_transpose_bf16": "stages fp32 master weights for the tensor-core path: bf16 copy and [B][D][A] transpose (nn.Linear / SubMConv3d weights).",
+    "lotus_dropout_bf16": "bf16-activation form of lotus_dropout_f32.",
+    "lotus_patch_attn_fwd_bf16": "bf16-activation form of lotus_patch_attn_fwd_f32: model.py:543-551.",
+    "lotus_patch_attn_bwd_bf16": "bf16-activation form of lotus_patch_attn_bwd_f32 (fp32 gradient accumulators).",
+    "lotus_cross_attn_fwd_bf16": "bf16-activation form of lotus_cross_attn_fwd_f32: model_ca.py:56-67.",
+    "lotus_cross_attn_bwd_bf16": "bf16-activation form of lotus_cross_attn_bwd_f32 (fp32 gradient outputs).",
+    "lotus_segment_max_fwd_bf16": "bf16-activation form of lotus_segment_max_fwd_f32: model.py:760-762.",
+    "lotus_segment_max_bwd_bf16": "bf16-activation form of lotus_segment_max_bwd_f32.",
+    "lotus_segment_sum_bf16": "bf16-activation form of lotus_segment_sum_f32.",
+    "lotus_unpool_add_bf16": "bf16-activation form of lotus_unpool_add_f32: model.py:824.",
     "lotus_layernorm_fwd_f32": "Replaces nn.LayerNorm (block norms, CPE norm, per-head q/k norm eps 1e-6): model.py:393-394,624,627,645; model_ca.py:43-44,114,124. "
                                "Rows are addressed as (r/inner)*outer_stride + (r%inner)*inner_stride so per-head norms read the packed qkv in place.",
     "lotus_layernorm_bwd_f32": "Backward of nn.LayerNorm (dx, and accumulated dgamma/dbeta).",
