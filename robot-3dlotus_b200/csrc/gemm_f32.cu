@@ -217,10 +217,43 @@ LOTUS_API int lotus_subm_conv_dgrad_f32(const float* dy, const float* w, float* 
   return launch_gemm(n, Cin, K3 * Cout, AConv{dy, nbr, nbr_stride, Cout, K3, 1}, BConvDgrad{w, Cin, Cout, K3}, ep, 1,
                      (cudaStream_t)stream_);
 }
+// narrow-input weight gradient (the stem: Cin = 7 / 4 / 68-ish is handled by the generic path, Cin*Cout <= 1024 here):
+// one CTA per (point chunk, tap): compact the chunk's existing pairs in shared memory, then thread (co, ci)
+// accumulates sum_j dy[p_j, co] * x[q_j, ci] and issues one atomicAdd.
+#define STEM_CHUNK 2048
+__global__ void k_conv_wgrad_narrow(const float* __restrict__ dy, const float* __restrict__ x, float* __restrict__ dw,
+                                    const int32_t* __restrict__ nbr, int64_t nbr_stride, int n, int Cin, int Cout, int K3) {
+  __shared__ int lp[STEM_CHUNK], lq[STEM_CHUNK];
+  __shared__ int cnt;
+  int d = blockIdx.y, p0 = blockIdx.x * STEM_CHUNK;
+  if (threadIdx.x == 0) cnt = 0;
+  __syncthreads();
+  for (int i = threadIdx.x; i < STEM_CHUNK; i += blockDim.x) {
+    int p = p0 + i;
+    if (p < n) {
+      int q = nbr[(int64_t)d * nbr_stride + p];
+      if (q >= 0) { int pos = atomicAdd(&cnt, 1); lp[pos] = p; lq[pos] = q; }
+    }
+  }
+  __syncthreads();
+  int t = threadIdx.x;
+  if (t >= Cin * Cout) return;
+  int co = t % Cout, ci = t / Cout, m = cnt;
+  float acc = 0.f;
+  for (int j = 0; j < m; ++j) acc = fmaf(dy[(int64_t)lp[j] * Cout + co], x[(int64_t)lq[j] * Cin + ci], acc);
+  if (m > 0) atomicAdd(&dw[((int64_t)co * K3 + d) * Cin + ci], acc);
+}
+
 // dw[co, d, ci] += sum_p dy[p, co] * x[nbr[d][p], ci]
 LOTUS_API int lotus_subm_conv_wgrad_f32(const float* dy, const float* x, float* dw, const int32_t* nbr,
                                         int64_t nbr_stride, int n, int Cin, int Cout, int K3, void* stream_) {
   cudaStream_t st = (cudaStream_t)stream_;
+  if (Cin * Cout <= 1024 && n > 0) {
+    int threads = ((Cin * Cout + 31) / 32) * 32;
+    k_conv_wgrad_narrow<<<dim3(ceil_div(n, STEM_CHUNK), K3), threads, 0, st>>>(dy, x, dw, nbr, nbr_stride, n, Cin, Cout, K3);
+    LOTUS_CUDA_OK();
+    return 0;
+  }
   int splits = pick_splits(Cout, Cin, n);
   splits = max(1, splits / 4);
   for (int d = 0; d < K3; ++d) {

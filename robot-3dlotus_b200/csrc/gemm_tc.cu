@@ -21,7 +21,7 @@ namespace tc {
 
 constexpr int BM = 128;
 constexpr int BK = 64;            // 64 bf16 = 128 B = one SWIZZLE_128B span
-constexpr int STAGES = 4;
+constexpr int MAX_STAGES = 4;
 constexpr int NUM_THREADS = 192;  // 6 warps
 constexpr int EPI_THREADS = 128;
 
@@ -42,6 +42,12 @@ struct Params {
   int M, N, K;                 // logical GEMM extents (K = reduction)
   int a_mode, b_mode;
   int kb_begin_stride;         // k-blocks per split (split-K over blockIdx.z)
+  int stages;                  // smem pipeline depth (2..4): shallow pipelines leave room for several CTAs per SM
+  // pair-list mode (sparse-conv weight gradient): blockIdx.z = tap * splits + split, K read from the device
+  const int32_t* k_dev;        // [taps] reduction extent per tap, or null
+  int splits;
+  int64_t tap_idx_stride;      // gather index arrays advance by this per tap
+  int64_t tap_out_stride;      // output pointer advances by this (elements) per tap
   GatherSpec ga, gb;
   // epilogue
   void* out;                   // [M, ldo] bf16 or fp32
@@ -149,26 +155,58 @@ __device__ __forceinline__ uint64_t make_desc(uint32_t saddr, uint32_t lbo_bytes
 // K-major tile:  row r (m or n) at r*128 B, 16-B chunk c at (c ^ (r & 7)) * 16          (SBO = 1024)
 // MN-major tile: block j = rows/64, k-row r at j*8192 + r*128 B, chunk c swizzled the same way
 //                (LBO = 8192 between 64-wide MN blocks, SBO = 1024 between 8-k-row groups)
+// stage one BK x WIDTH MN-major tile whose k-rows are gathered through idx[] (rows >= kext are zero)
+template <int WIDTH>
+__device__ __forceinline__ void stage_mn_gather(uint8_t* tile, const GatherSpec& g, const int32_t* idx, int kb, int kext, int mn0,
+                                                int mn_extent, int t) {
+  int r = t >> 1, half = t & 1;
+  int kpt = kb * BK + r;
+  int src_row = (kpt < kext) ? idx[kpt] : -1;
+  const __nv_bfloat16* src = g.base + (int64_t)max(src_row, 0) * g.row_elems + mn0;
+  constexpr int CH = WIDTH / 8;                 // 16-B chunks per row
+#pragma unroll
+  for (int cc = 0; cc < CH / 2; ++cc) {
+    int c = half * (CH / 2) + cc;
+    int blk = c >> 3, cw = c & 7;
+    bool ok = src_row >= 0 && (mn0 + c * 8) < mn_extent;
+    cp_async_16(tile + blk * 8192 + r * 128 + ((cw ^ (r & 7)) << 4), src + c * 8, ok);
+  }
+}
+
 template <int BN>
-__global__ void __launch_bounds__(NUM_THREADS, 1)
+__global__ void __launch_bounds__(NUM_THREADS)
 k_gemm_tc(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_b, const Params p) {
   extern __shared__ __align__(1024) uint8_t smem_raw[];
   constexpr uint32_t A_BYTES = BM * BK * 2, B_BYTES = BN * BK * 2;
+  const int STAGES = p.stages;
   uint8_t* smem = (uint8_t*)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
   uint8_t* sA = smem;
   uint8_t* sB = smem + STAGES * A_BYTES;
   uint64_t* full = (uint64_t*)(sB + STAGES * B_BYTES);
-  uint64_t* empty = full + STAGES;
-  uint64_t* tmem_full = empty + STAGES;
+  uint64_t* empty = full + MAX_STAGES;
+  uint64_t* tmem_full = empty + MAX_STAGES;
   uint32_t* tmem_slot = (uint32_t*)(tmem_full + 1);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int m0 = blockIdx.x * BM, n0 = blockIdx.y * BN;
-  const int num_kb_total = (p.K + BK - 1) / BK;
-  const int kb0 = blockIdx.z * p.kb_begin_stride;
-  const int kb1 = min(num_kb_total, kb0 + p.kb_begin_stride);
-  const int num_kb = kb1 - kb0;
-  const bool a_gather = (p.a_mode == OP_K_GATHER), b_gather = (p.b_mode == OP_MN_GATHER);
+  // reduction range of this CTA
+  int tap = 0, Kext = p.K, kb0, kb1;
+  if (p.k_dev) {
+    tap = blockIdx.z / p.splits;
+    int split = blockIdx.z - tap * p.splits;
+    Kext = p.k_dev[tap];
+    int nkb = (Kext + BK - 1) / BK;
+    int per = (nkb + p.splits - 1) / p.splits;
+    kb0 = split * per;
+    kb1 = min(nkb, kb0 + per);
+  } else {
+    int nkb = (p.K + BK - 1) / BK;
+    kb0 = blockIdx.z * p.kb_begin_stride;
+    kb1 = min(nkb, kb0 + p.kb_begin_stride);
+  }
+  const int num_kb = max(0, kb1 - kb0);
+  const bool a_gather = (p.a_mode == OP_K_GATHER || p.a_mode == OP_MN_GATHER);
+  const bool b_gather = (p.b_mode == OP_MN_GATHER);
   const bool a_mn = (p.a_mode >= OP_MN_TMA), b_mn = (p.b_mode >= OP_MN_TMA);
 
   if (threadIdx.x == 0) {
@@ -177,7 +215,7 @@ k_gemm_tc(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUt
     mbar_init(tmem_full, 1);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
-  if (warp == 1) tmem_alloc(tmem_slot, BN);   // BN in {64,128,256}: power of two >= 32
+  if (warp == 1) tmem_alloc(tmem_slot, BN);   // BN in {64,128}: power of two >= 32
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
@@ -230,42 +268,32 @@ k_gemm_tc(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUt
     } else if (a_gather || b_gather) {
       // ===================== cp.async gather producers (warps 2-5) =====================
       const int t = threadIdx.x - 64;                   // 0..127
-      constexpr int LAG = 2;                            // stages in flight per thread before signalling
+      const int LAG = STAGES >= 3 ? 2 : 1;              // stages in flight per thread before signalling
+      const int32_t* a_idx = p.ga.idx + (int64_t)tap * p.tap_idx_stride;
+      const int32_t* b_idx = p.gb.idx + (int64_t)tap * p.tap_idx_stride;
       for (int i = 0; i < num_kb + LAG; ++i) {
         if (i < num_kb) {
           int s = i % STAGES, ph = (i / STAGES) & 1;
           mbar_wait(&empty[s], ph ^ 1);
           int kb = kb0 + i;
-          if (a_gather) {
+          if (p.a_mode == OP_K_GATHER) {
             // thread t stages row (m0 + t): 8 chunks of 16 B
-            int tap = kb / p.ga.kb_per_tap, c0 = (kb - tap * p.ga.kb_per_tap) * BK;
-            if (p.ga.mirror_taps) tap = p.ga.ntaps - 1 - tap;
+            int tp = kb / p.ga.kb_per_tap, c0 = (kb - tp * p.ga.kb_per_tap) * BK;
+            if (p.ga.mirror_taps) tp = p.ga.ntaps - 1 - tp;
             int m = m0 + t;
-            int src_row = (m < p.M) ? p.ga.idx[(int64_t)tap * p.ga.idx_stride + m] : -1;
+            int src_row = (m < p.M) ? p.ga.idx[(int64_t)tp * p.ga.idx_stride + m] : -1;
             const __nv_bfloat16* src = p.ga.base + (int64_t)max(src_row, 0) * p.ga.row_elems + c0;
             uint8_t* dst = sA + s * A_BYTES + t * 128;
 #pragma unroll
             for (int c = 0; c < 8; ++c) cp_async_16(dst + ((c ^ (t & 7)) << 4), src + c * 8, src_row >= 0);
-          } else {
-            // MN-major gathered B (conv wgrad): k-row r = point (kb*64 + r); thread t stages chunks of rows r = t/2 .. (2 threads per row)
-            // BN/64 blocks of 64 ci: row bytes = BN*2; thread handles half of the row's chunks
-            int r = t >> 1, half = t & 1;
-            int kpt = kb * BK + r;
-            int src_row = (kpt < p.K) ? p.gb.idx[kpt] : -1;
-            const __nv_bfloat16* src = p.gb.base + (int64_t)max(src_row, 0) * p.gb.row_elems + n0;
-            constexpr int CH = BN / 8;                  // 16-B chunks per row
-#pragma unroll
-            for (int cc = 0; cc < CH / 2; ++cc) {
-              int c = half * (CH / 2) + cc;             // chunk within the BN-wide row
-              int blk = c >> 3, cw = c & 7;
-              bool ok = src_row >= 0 && (n0 + c * 8) < p.N;
-              cp_async_16(sB + s * B_BYTES + blk * 8192 + r * 128 + ((cw ^ (r & 7)) << 4), src + c * 8, ok);
-            }
+          } else if (p.a_mode == OP_MN_GATHER) {
+            stage_mn_gather<BM>(sA + s * A_BYTES, p.ga, a_idx, kb, Kext, m0, p.M, t);
           }
+          if (b_gather) stage_mn_gather<BN>(sB + s * B_BYTES, p.gb, b_idx, kb, Kext, n0, p.N, t);
         }
         cp_async_commit();
         if (i >= LAG) {
-          cp_async_wait<LAG>();
+          if (LAG == 2) cp_async_wait<2>(); else cp_async_wait<1>();
           fence_proxy_async();
           mbar_arrive(&full[(i - LAG) % STAGES]);
         }
@@ -296,7 +324,7 @@ k_gemm_tc(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUt
       if (!row_ok) continue;
       const int nbase = n0 + c0;
       if (nbase >= p.N) continue;
-      const int64_t obase = (int64_t)row * p.ldo + nbase;
+      const int64_t obase = (int64_t)row * p.ldo + nbase + (int64_t)tap * p.tap_out_stride;
       if (p.atomic) {
         float* o = (float*)p.out + obase;
 #pragma unroll
@@ -422,7 +450,8 @@ struct Operand {
   GatherSpec g;               // gather modes
 };
 
-static int launch(const Operand& A, const Operand& B, Params p, int BN, int splits, cudaStream_t st) {
+static int launch(const Operand& A, const Operand& B, Params p, int BN, int splits, cudaStream_t st, int taps = 1,
+                  int max_kb_hint = -1) {
   if (p.M <= 0 || p.N <= 0) return 0;
   CUtensorMap ma, mb;
   memset(&ma, 0, sizeof(ma));
@@ -438,10 +467,13 @@ static int launch(const Operand& A, const Operand& B, Params p, int BN, int spli
   int num_kb = (p.K + BK - 1) / BK;
   splits = max(1, min(splits, num_kb));
   int per = (num_kb + splits - 1) / splits;
-  splits = (num_kb + per - 1) / per;
+  if (!p.k_dev) splits = (num_kb + per - 1) / per;
   p.kb_begin_stride = per;
-  dim3 grid((p.M + BM - 1) / BM, (p.N + BN - 1) / BN, splits);
-  size_t smem = (size_t)STAGES * (BM * BK * 2 + BN * BK * 2) + 256 + 1024;
+  p.splits = splits;
+  int kb_per_cta = max_kb_hint > 0 ? max_kb_hint : per;
+  p.stages = kb_per_cta >= 4 ? 4 : (kb_per_cta >= 3 ? 3 : 2);
+  dim3 grid((p.M + BM - 1) / BM, (p.N + BN - 1) / BN, splits * taps);
+  size_t smem = (size_t)p.stages * (BM * BK * 2 + BN * BK * 2) + 256 + 1024;
   cudaError_t e;
   if (BN == 128) {
     static bool set128 = false;
@@ -541,4 +573,24 @@ LOTUS_API int lotus_subm_conv_wgrad_bf16(const void* dy, const void* x, float* d
     if (rc) return rc;
   }
   return 0;
+}
+
+// wgrad over the compact pair lists (lotus_pair_lists): dw[co, d, ci] (fp32) += sum_j dy[pairs_out[d][j], co] * x[pairs_in[d][j], ci]
+// One launch for all taps: grid.z = K3 * splits; the per-tap reduction extent is read on the device (pair_cnt).
+LOTUS_API int lotus_subm_conv_wgrad_pairs_bf16(const void* dy, const void* x, float* dw, const int32_t* pairs_out,
+                                               const int32_t* pairs_in, const int32_t* pair_cnt, int64_t pair_stride,
+                                               int n_upper, int Cin, int Cout, int K3, void* stream_) {
+  LOTUS_CHECK_ARG(Cin % 8 == 0 && Cout % 8 == 0, "lotus_subm_conv_wgrad_pairs_bf16: Cin=%d, Cout=%d must be multiples of 8", Cin, Cout);
+  int bn = tc::pick_bn(Cin);
+  int tiles = ((Cout + 127) / 128) * ((Cin + bn - 1) / bn);
+  int max_kb = (n_upper + tc::BK - 1) / tc::BK;
+  int splits = max(1, min(max_kb, (kNumSM * 3) / max(1, tiles * K3) + 1));
+  Params p = base_params(Cout, Cin, n_upper, dw, (int64_t)K3 * Cin, 1);
+  p.atomic = 1;
+  p.k_dev = pair_cnt;
+  p.tap_idx_stride = pair_stride;
+  p.tap_out_stride = Cin;
+  Operand A{tc::OP_MN_GATHER, nullptr, 0, {(const __nv_bfloat16*)dy, pairs_out, 0, Cout, 0, 0, K3}};
+  Operand B{tc::OP_MN_GATHER, nullptr, 0, {(const __nv_bfloat16*)x, pairs_in, 0, Cin, 0, 0, K3}};
+  return tc::launch(A, B, p, bn, splits, (cudaStream_t)stream_, K3, 4);
 }

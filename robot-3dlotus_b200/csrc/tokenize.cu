@@ -691,3 +691,94 @@ LOTUS_API int lotus_rpe_bias(const float* table, const int32_t* grid, const int3
   LOTUS_CUDA_OK();
   return 0;
 }
+
+// ------------------------------------------------------------------------------------------------
+// compact (output voxel, input voxel) pair lists per kernel tap — the rulebook in spconv's sense.
+// pairs_out[d*stride + j] = p, pairs_in[d*stride + j] = nbr[d][p] for the j-th voxel (ascending p) that has
+// a neighbour at tap d; pair_cnt[d] = number of such voxels.  Used by the weight-gradient kernels so they
+// only contract over existing pairs.
+// ------------------------------------------------------------------------------------------------
+#define PAIR_CHUNK 1024
+__global__ void k_pair_count(const int32_t* __restrict__ nbr, int64_t nbr_stride, const int32_t* __restrict__ meta,
+                             int nchunks, int32_t* __restrict__ chunk_cnt /*[K3][nchunks]*/) {
+  __shared__ int red[32];
+  int d = blockIdx.y, ch = blockIdx.x, n = meta[META_N];
+  int p0 = ch * PAIR_CHUNK;
+  int c = 0;
+  for (int i = threadIdx.x; i < PAIR_CHUNK; i += blockDim.x) {
+    int p = p0 + i;
+    if (p < n && nbr[(int64_t)d * nbr_stride + p] >= 0) ++c;
+  }
+  c = warp_sum_i(c);
+  if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = c;
+  __syncthreads();
+  if (threadIdx.x < 32) {
+    int v = threadIdx.x < (blockDim.x >> 5) ? red[threadIdx.x] : 0;
+    v = warp_sum_i(v);
+    if (threadIdx.x == 0) chunk_cnt[d * nchunks + ch] = v;
+  }
+}
+__global__ void k_pair_scan(int32_t* __restrict__ chunk_cnt, int nchunks, int32_t* __restrict__ pair_cnt) {
+  int d = blockIdx.x;
+  if (threadIdx.x == 0) {
+    int acc = 0;
+    for (int c = 0; c < nchunks; ++c) {
+      int v = chunk_cnt[d * nchunks + c];
+      chunk_cnt[d * nchunks + c] = acc;
+      acc += v;
+    }
+    pair_cnt[d] = acc;
+  }
+}
+__global__ void k_pair_fill(const int32_t* __restrict__ nbr, int64_t nbr_stride, const int32_t* __restrict__ meta,
+                            int nchunks, const int32_t* __restrict__ chunk_off, int32_t* __restrict__ pairs_out,
+                            int32_t* __restrict__ pairs_in) {
+  __shared__ int wsum[32];
+  __shared__ int carry;
+  int d = blockIdx.y, ch = blockIdx.x, n = meta[META_N];
+  int p0 = ch * PAIR_CHUNK;
+  int lane = threadIdx.x & 31, w = threadIdx.x >> 5, nw = blockDim.x >> 5;
+  if (threadIdx.x == 0) carry = chunk_off[d * nchunks + ch];
+  __syncthreads();
+  for (int i0 = 0; i0 < PAIR_CHUNK; i0 += blockDim.x) {
+    int p = p0 + i0 + threadIdx.x;
+    int q = (p < n) ? nbr[(int64_t)d * nbr_stride + p] : -1;
+    int f = q >= 0 ? 1 : 0, v = f;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+      int t = __shfl_up_sync(0xffffffffu, v, o);
+      if (lane >= o) v += t;
+    }
+    if (lane == 31) wsum[w] = v;
+    __syncthreads();
+    if (w == 0) {
+      int t = lane < nw ? wsum[lane] : 0;
+#pragma unroll
+      for (int o = 1; o < 32; o <<= 1) {
+        int u = __shfl_up_sync(0xffffffffu, t, o);
+        if (lane >= o) t += u;
+      }
+      wsum[lane] = t;
+    }
+    __syncthreads();
+    int incl = v + (w > 0 ? wsum[w - 1] : 0) + carry;
+    if (f) {
+      pairs_out[(int64_t)d * nbr_stride + incl - 1] = p;
+      pairs_in[(int64_t)d * nbr_stride + incl - 1] = q;
+    }
+    __syncthreads();
+    if (threadIdx.x == blockDim.x - 1) carry = incl;
+    __syncthreads();
+  }
+}
+// scratch: K3 * ceil(n_upper / 1024) ints
+LOTUS_API int lotus_pair_lists(const int32_t* nbr, int64_t nbr_stride, const int32_t* meta, int n_upper, int K3,
+                               int32_t* pairs_out, int32_t* pairs_in, int32_t* pair_cnt, int32_t* scratch, void* stream_) {
+  cudaStream_t st = (cudaStream_t)stream_;
+  int nchunks = ceil_div(n_upper, PAIR_CHUNK);
+  k_pair_count<<<dim3(nchunks, K3), 256, 0, st>>>(nbr, nbr_stride, meta, nchunks, scratch);
+  k_pair_scan<<<K3, 32, 0, st>>>(scratch, nchunks, pair_cnt);
+  k_pair_fill<<<dim3(nchunks, K3), 256, 0, st>>>(nbr, nbr_stride, meta, nchunks, scratch, pairs_out, pairs_in);
+  LOTUS_CUDA_OK();
+  return 0;
+}

@@ -60,7 +60,7 @@ class PolicyEngine:
     # ------------------------------------------------------------------ blocks
     def _block(self, blk, x, stg, drop, conv_in=None):
         a = blk.attn
-        c = ops.subm_conv(x if conv_in is None else conv_in, blk.cpe[0].weight, blk.cpe[0].bias, stg.nbr3, stg.stride_alloc)
+        c = ops.subm_conv(x if conv_in is None else conv_in, blk.cpe[0].weight, blk.cpe[0].bias, stg.nbr3, stg.stride_alloc, rule=stg)
         c = ops.linear(c, blk.cpe[1].weight, blk.cpe[1].bias)
         x = ops.layer_norm(c, blk.cpe[2].weight, blk.cpe[2].bias, blk.cpe[2].eps, residual=x)
         h = ops.layer_norm(x, blk.norm1[0].weight, blk.norm1[0].bias, blk.norm1[0].eps)

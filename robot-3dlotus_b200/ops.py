@@ -314,7 +314,7 @@ def batch_norm_act(x, bn, train, gelu=True, out_bf16=False):
 
 class SubmConvFn(torch.autograd.Function):
     @staticmethod
-    def forward(ctx, x, w, b, nbr, nbr_stride):
+    def forward(ctx, x, w, b, nbr, nbr_stride, rule=None):
         L = load()
         x = _actc(x)
         n, cin = x.shape
@@ -329,6 +329,7 @@ class SubmConvFn(torch.autograd.Function):
         ctx.save_for_backward(x, w, nbr)
         ctx.bias = b
         ctx.meta = (n, cin, cout, k3, nbr_stride, b is not None, tc)
+        ctx.rule = rule
         return y
 
     @staticmethod
@@ -347,18 +348,22 @@ class SubmConvFn(torch.autograd.Function):
                 L.lotus_subm_conv_dgrad_f32(_p(dy), _p(w), _p(dx), _p(nbr), nbr_stride, n, cin, cout, k3, st)
         wbuf, dw = _grad_buf(w, ctx.needs_input_grad[1])
         if wbuf is not None:
-            if tc:
+            if tc and ctx.rule is not None:
+                r = ctx.rule      # compact per-tap pair lists: contract only over existing (voxel, neighbour) pairs
+                L.lotus_subm_conv_wgrad_pairs_bf16(_p(dy), _p(x), _p(wbuf), _p(r.pairs_out), _p(r.pairs_in), _p(r.pair_cnt),
+                                                   r.stride_alloc, n, cin, cout, k3, st)
+            elif tc:
                 L.lotus_subm_conv_wgrad_bf16(_p(dy), _p(x), _p(wbuf), _p(nbr), nbr_stride, n, cin, cout, k3, st)
             else:
                 L.lotus_subm_conv_wgrad_f32(_p(dy), _p(x), _p(wbuf), _p(nbr), nbr_stride, n, cin, cout, k3, st)
         bbuf, db = _grad_buf(ctx.bias, has_b and ctx.needs_input_grad[2])
         if bbuf is not None:
             getattr(L, "lotus_colsum_" + _sfx(dy))(_p(dy), n, cout, _p(bbuf), st)
-        return dx, dw, db, None, None
+        return dx, dw, db, None, None, None
 
 
-def subm_conv(x, w, b, nbr, nbr_stride):
-    return SubmConvFn.apply(x, w, b, nbr, nbr_stride)
+def subm_conv(x, w, b, nbr, nbr_stride, rule=None):
+    return SubmConvFn.apply(x, w, b, nbr, nbr_stride, rule)
 
 
 # ------------------------------------------------------------------------------------------ attention

@@ -55,6 +55,9 @@ class Stage:
     inverse: torch.Tensor = None
     curves: List[int] = None
     nbr3: torch.Tensor = None                  # (27, stride) int32
+    pairs_out: torch.Tensor = None             # (27, stride) int32 compact rulebook: output voxel of the j-th pair of tap d
+    pairs_in: torch.Tensor = None              # (27, stride) int32 ... and its input voxel
+    pair_cnt: torch.Tensor = None              # (27,) int32 pairs per tap (device)
     nbr5: Optional[torch.Tensor] = None        # (125, stride) int32, stage 0 only
     plans: Dict[int, PatchPlan] = field(default_factory=dict)
     # pooling from the parent stage
@@ -99,6 +102,7 @@ def tokenize(coord, npoints: List[int], orders, strides, patch_sizes, rows_neede
     err = torch.zeros(1, **i32)
     max_cloud = max(npoints)
     hash_cap = _next_pow2(2 * N0)
+    pair_scratch = torch.empty(27 * ((N0 + 1023) // 1024 + 1), **i32)
     hkeys = torch.empty(hash_cap, device=dev, dtype=torch.int64)
     hvals = torch.empty(hash_cap, **i32)
 
@@ -122,6 +126,11 @@ def tokenize(coord, npoints: List[int], orders, strides, patch_sizes, rows_neede
         # sparse-conv neighbourhoods (hash built once per stage, probed for k=3 and, at stage 0, k=5)
         stg.nbr3 = torch.empty((27, N0), **i32)
         L.lotus_neighbor_table(_p(grid), _p(batch), _p(meta[s]), N0, 3, _p(hkeys), _p(hvals), hash_cap, 1, _p(stg.nbr3), N0, st)
+        stg.pairs_out = torch.empty((27, N0), **i32)
+        stg.pairs_in = torch.empty((27, N0), **i32)
+        stg.pair_cnt = torch.empty(27, **i32)
+        L.lotus_pair_lists(_p(stg.nbr3), N0, _p(meta[s]), N0, 27, _p(stg.pairs_out), _p(stg.pairs_in), _p(stg.pair_cnt),
+                           _p(pair_scratch), st)
         if s == 0 and need_stem:
             stg.nbr5 = torch.empty((125, N0), **i32)
             L.lotus_neighbor_table(_p(grid), _p(batch), _p(meta[s]), N0, 5, _p(hkeys), _p(hvals), hash_cap, 0, _p(stg.nbr5), N0, st)

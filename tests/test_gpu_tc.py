@@ -103,3 +103,16 @@ def test_subm_conv_bf16(cin, cout):
     L.lotus_subm_conv_wgrad_bf16(P(dyd), P(xd), P(dw), P(stg.nbr3), stg.stride_alloc, n, cin, cout, 27, None)
     torch.cuda.synchronize()
     assert rel(dw, wr.grad.reshape(cout, 27, cin)) < 2e-3
+    # compact pair-list form (one launch for all taps) + the rulebook itself
+    cnt = stg.pair_cnt.cpu()
+    assert torch.equal(cnt.long(), (nbr >= 0).sum(0))
+    for d in (0, 13, 26):
+        m = int(cnt[d])
+        po, pi = stg.pairs_out[d, :m].cpu().long(), stg.pairs_in[d, :m].cpu().long()
+        ref_p = (nbr[:, d] >= 0).nonzero()[:, 0]
+        assert torch.equal(po, ref_p) and torch.equal(pi, nbr[ref_p, d])
+    dw2 = torch.zeros(cout, 27, cin, device=DEV, dtype=torch.float32)
+    L.lotus_subm_conv_wgrad_pairs_bf16(P(dyd), P(xd), P(dw2), P(stg.pairs_out), P(stg.pairs_in), P(stg.pair_cnt), stg.stride_alloc,
+                                       n, cin, cout, 27, None)
+    torch.cuda.synchronize()
+    assert rel(dw2, wr.grad.reshape(cout, 27, cin)) < 2e-3

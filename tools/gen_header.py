@@ -28,6 +28,8 @@ DOC = {
                         "compositions: model.py:410-466,480-481. gather_idx = order[pad]; slot_of_point = unpad[inverse].",
     "lotus_neighbor_table": "Replaces spconv 2.3.6 SubMConv3d indice-pair generation (call sites model.py:616-622,845-852): "
                             "nbr[d*stride + p] = voxel at grid[p]+off(d) in the same cloud or -1; d=(d0*k+d1)*k+d2, d0 along x.",
+    "lotus_pair_lists": "Compact per-tap (output, input) voxel pair lists — the rulebook of spconv 2.3.6 SubMConv3d (call sites model.py:616-622,845-852); "
+                        "consumed by the weight-gradient kernels.",
     "lotus_fps": "Replaces farthest_point_sample (explicit start index): train/datasets/common.py:108-129. Bit-exact indices.",
     "lotus_knn": "North-star kNN grouping (no reference function; SURVEY §8a row 13): brute force inside each cloud, ties -> lowest index.",
     "lotus_ball_query": "North-star radius grouping (no reference function; SURVEY §8a row 13): first nsample indices within radius.",
@@ -46,6 +48,8 @@ DOC = {
     "lotus_subm_conv_fwd_bf16": "bf16 tensor-core implicit-GEMM form of spconv.SubMConv3d forward (CPE k=3): model.py:616-622; gathered operand staged by cp.async.",
     "lotus_subm_conv_dgrad_bf16": "bf16 tensor-core backward of SubMConv3d w.r.t. its input features (mirrored taps).",
     "lotus_subm_conv_wgrad_bf16": "bf16 tensor-core backward of SubMConv3d w.r.t. its weight (per-tap split-K, fp32 accumulate).",
+    "lotus_subm_conv_wgrad_pairs_bf16": "bf16 tensor-core backward of SubMConv3d w.r.t. its weight over the compact rulebook (lotus_pair_lists): "
+                                        "one launch for all 27 taps, both operands gathered by cp.async, fp32 accumulate.",
     "lotus_layernorm_fwd_bf16": "bf16-activation form of lotus_layernorm_fwd_f32 (same reference call sites).",
     "lotus_layernorm_bwd_bf16": "bf16-activation form of lotus_layernorm_bwd_f32 (dy may be fp32: gradients leaving the attention kernels).",
     "lotus_colsum_bf16": "bf16-activation form of lotus_colsum_f32 (bias gradients).",
