@@ -213,6 +213,8 @@ def main():
     ap.add_argument("--batch", type=int, default=32, help="keysteps per GPU per step (BASELINE configs[1]: 32)")
     ap.add_argument("--cpu-sample-batch", type=int, default=2)
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--engine", default="native", choices=["native", "python"],
+                    help="native: one C++ call per step (lotus_policy_step); python: per-op autograd Functions over the same kernels")
     ap.add_argument("--precision", default="bf16", choices=["bf16", "fp32"],
                     help="bf16: tensor-core mode (tcgen05 GEMMs, bf16 activations); fp32: validation-mode kernels")
     args = ap.parse_args()
@@ -245,6 +247,7 @@ def main():
     torch.manual_seed(2024 + rank)
     model = policy.build_parameter_shell(cfg).to(dev).train()
     model.engine().precision = args.precision
+    model.engine().use_native = args.engine == "native"
     step_fn = trainer.TrainStep(model)
     nb = 4
     host = [pack_batch(syn.make_batch(seed=2024 + 100 * rank + i, batch_size=args.batch), pin=True) for i in range(nb)]
@@ -266,8 +269,10 @@ def main():
     calls0 = L.launches
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     e0.record()
+    t_host0 = time.perf_counter()
     for i in range(args.steps):
         losses = step_fn(dict(resident[i % nb]))
+    t_host = time.perf_counter() - t_host0          # host time to ENQUEUE the K steps (includes the tokeniser's size sync)
     e1.record()
     barrier()
     ms = e0.elapsed_time(e1)
@@ -296,9 +301,13 @@ def main():
 
     # ---- one profiled step: per-C-call CUDA events -> shares, dominant kernel, roofline
     kernel_count = [0]
+    native_calls = int(L.cdll.lotus_policy_step_calls()) if args.engine == "native" else 0
+    model.engine().use_native = False          # the per-kernel table comes from the per-op path (same kernels, same order)
+    step_fn(dict(resident[0]))
     prof = CallProfiler(L)
     with prof:
         step_fn(dict(resident[0]))
+    model.engine().use_native = args.engine == "native"
     conv_pairs = {}
     for stg in model.engine().last_stages:                     # actual (voxel, neighbour) pairs -> algorithmic conv FLOPs
         conv_pairs[(stg.n, 27)] = int((stg.nbr3[:, : stg.n] >= 0).sum())
@@ -329,7 +338,7 @@ def main():
         roof = {"bound": "hbm", "kernel": dom_name, "achieved": None, "peak": hbm_peak, "unit": "GB/s", "frac": None, "traffic": None,
                 "share_of_step": dom["ms"] / tot_ms, "launches_per_step": dom["calls"], "peak_source": peak_src}
     kernels = [{"call": k, "share": round(d["ms"] / tot_ms, 4), "ms_per_step": round(d["ms"], 3), "calls": d["calls"],
-                "tflops": round(d["flops"] / (d["ms"] * 1e-3) / 1e12, 2) if d["flops"] else None} for k, d in top[:12]]
+                "tflops": round(d["flops"] / (d["ms"] * 1e-3) / 1e12, 2) if d["flops"] else None} for k, d in top[:40]]
 
     cpu = None
     if not args.no_cpu_baseline and world == 1:
@@ -348,6 +357,8 @@ def main():
         "e2e": {"value": args.batch * world * args.steps / (ms_e2e * 1e-3), "unit": UNIT, "h2d_bytes_per_step": h2d_bytes(host[0]),
                 "d2h_bytes_per_step": 4 + 5 * 8 * 4 + 5 * (args.batch + 1) * 4 + 4, "ms_per_step": ms_e2e / args.steps},
         "gpu_launches": int(round(kernel_count[0] * args.steps)), "c_abi_calls_per_step": calls_per_step,
+        "native_launcher_calls_per_step": native_calls, "engine": args.engine,
+        "host_enqueue_ms_per_step": 1e3 * t_host / args.steps, "kernel_ms_per_step_profiled": tot_ms,
         "roofline": roof, "kernels": kernels, "cpu_baseline": cpu, "loss": loss_host,
     }
     print(json.dumps(line))

@@ -210,10 +210,10 @@ LOTUS_API int lotus_subm_conv_fwd_f32(const float* x, const float* w, const floa
   return launch_gemm(n, Cout, K3 * Cin, AConv{x, nbr, nbr_stride, Cin, K3, 0}, BRowMajorT{w, (int64_t)K3 * Cin}, ep, 1,
                      (cudaStream_t)stream_);
 }
-// dx[q, ci] = sum_{d,co} dy[nbr[K3-1-d][q], co] * w[co, d, ci]
-LOTUS_API int lotus_subm_conv_dgrad_f32(const float* dy, const float* w, float* dx, const int32_t* nbr,
+// dx[q, ci] = [residual[q, ci] +] sum_{d,co} dy[nbr[K3-1-d][q], co] * w[co, d, ci]
+LOTUS_API int lotus_subm_conv_dgrad_f32(const float* dy, const float* w, const float* residual, float* dx, const int32_t* nbr,
                                         int64_t nbr_stride, int n, int Cin, int Cout, int K3, void* stream_) {
-  Epi ep{dx, Cin, nullptr, nullptr, ACT_NONE, 0, 0.f, 0.f, 0, 0};
+  Epi ep{dx, Cin, nullptr, residual, ACT_NONE, 0, 0.f, 0.f, 0, 0};
   return launch_gemm(n, Cin, K3 * Cout, AConv{dy, nbr, nbr_stride, Cout, K3, 1}, BConvDgrad{w, Cin, Cout, K3}, ep, 1,
                      (cudaStream_t)stream_);
 }

@@ -547,11 +547,12 @@ LOTUS_API int lotus_subm_conv_fwd_bf16(const void* x, const void* w, const float
   return tc::launch(A, B, p, tc::pick_bn(Cout), 1, (cudaStream_t)stream_);
 }
 
-// dgrad: dx[q,ci] = sum_{d,co} dy[nbr[K3-1-d][q], co] * w[co,d,ci], with wt = w re-laid out as [ci][d][co] (bf16)
-LOTUS_API int lotus_subm_conv_dgrad_bf16(const void* dy, const void* wt, void* dx, const int32_t* nbr, int64_t nbr_stride,
-                                         int n, int Cin, int Cout, int K3, int out_fp32, void* stream_) {
+// dgrad: dx[q,ci] = [residual[q,ci] +] sum_{d,co} dy[nbr[K3-1-d][q], co] * w[co,d,ci], with wt = w re-laid out as [ci][d][co] (bf16)
+LOTUS_API int lotus_subm_conv_dgrad_bf16(const void* dy, const void* wt, const void* residual, void* dx, const int32_t* nbr,
+                                         int64_t nbr_stride, int n, int Cin, int Cout, int K3, int out_fp32, void* stream_) {
   LOTUS_CHECK_ARG(Cout % 64 == 0, "lotus_subm_conv_dgrad_bf16: Cout=%d must be a multiple of 64", Cout);
   Params p = base_params(n, Cin, K3 * Cout, dx, Cin, out_fp32);
+  p.residual = residual;
   Operand A{tc::OP_K_GATHER, nullptr, 0, {(const __nv_bfloat16*)dy, nbr, nbr_stride, Cout, Cout / 64, 1, K3}};
   Operand B{tc::OP_K_TMA, (const __nv_bfloat16*)wt, (int64_t)K3 * Cout, {}};
   return tc::launch(A, B, p, tc::pick_bn(Cin), 1, (cudaStream_t)stream_);

@@ -45,28 +45,32 @@ LOTUS_API int lotus_segment_max_fwd_bf16(const void* x, int C, const int32_t* se
                                          int32_t* argmax, void* stream_) {
   return segmax_fwd_impl<bf16_t>(x, C, seg_ptr, member, M, out, argmax, stream_);
 }
-// dx[arg[m,c], c] = dy[m,c]   (dx zero-initialised by the caller; segments are disjoint -> no atomics)
+// dx[arg[m,c], c] (+)= dy[m,c]   (segments are disjoint -> no atomics; accumulate=0 expects a zeroed dx)
 template <typename T>
 __global__ void k_segment_max_bwd(const T* __restrict__ dy, const int32_t* __restrict__ arg, int64_t total, int C,
-                                  T* __restrict__ dx) {
+                                  T* __restrict__ dx, int accumulate) {
   for (int64_t t = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; t < total; t += (int64_t)gridDim.x * blockDim.x) {
     int r = arg[t];
-    if (r >= 0) dx[(int64_t)r * C + (t % C)] = dy[t];
+    if (r >= 0) {
+      int64_t o = (int64_t)r * C + (t % C);
+      stf(dx, o, accumulate ? ldf(dx, o) + ldf(dy, t) : ldf(dy, t));
+    }
   }
 }
-LOTUS_API int lotus_segment_max_bwd_f32(const float* dy, const int32_t* argmax, int M, int C, float* dx_zeroed,
+LOTUS_API int lotus_segment_max_bwd_f32(const float* dy, const int32_t* argmax, int M, int C, float* dx, int accumulate,
                                         void* stream_) {
   if (M <= 0) return 0;
   int64_t total = (int64_t)M * C;
-  k_segment_max_bwd<float><<<min(ceil_div(total, 256), kNumSM * 16), 256, 0, (cudaStream_t)stream_>>>(dy, argmax, total, C, dx_zeroed);
+  k_segment_max_bwd<float><<<min(ceil_div(total, 256), kNumSM * 16), 256, 0, (cudaStream_t)stream_>>>(dy, argmax, total, C, dx, accumulate);
   LOTUS_CUDA_OK();
   return 0;
 }
-LOTUS_API int lotus_segment_max_bwd_bf16(const void* dy, const int32_t* argmax, int M, int C, void* dx_zeroed, void* stream_) {
+LOTUS_API int lotus_segment_max_bwd_bf16(const void* dy, const int32_t* argmax, int M, int C, void* dx, int accumulate,
+                                         void* stream_) {
   if (M <= 0) return 0;
   int64_t total = (int64_t)M * C;
   k_segment_max_bwd<bf16_t><<<min(ceil_div(total, 256), kNumSM * 16), 256, 0, (cudaStream_t)stream_>>>((const bf16_t*)dy, argmax, total,
-                                                                                                     C, (bf16_t*)dx_zeroed);
+                                                                                                     C, (bf16_t*)dx, accumulate);
   LOTUS_CUDA_OK();
   return 0;
 }

@@ -23,6 +23,8 @@ class PolicyEngine:
         # "fp32": validation mode (SIMT kernels, 1e-4 parity with the reference); "bf16": tensor-core mode
         # (tcgen05 GEMMs / implicit-GEMM conv, bf16 activations, fp32 master weights, statistics and gradients)
         self.precision = "fp32"
+        self.use_native = False        # one-call C++ executor (csrc/engine_native.cu) for the production topology
+        self._native = None
         self._tc_weights = None
         load()                         # fail loudly if the CUDA library is absent
 
@@ -151,6 +153,34 @@ class PolicyEngine:
                 self._rec(f"dec{s}.ca_block{i}", x)
         return x, stages
 
+    # ------------------------------------------------------------------ native one-call step
+    def native_step(self, batch, compute_loss=True, with_grad=True, compute_final_action=False, dropout_seed=None):
+        """forward (+ loss + backward into the gradient sinks) through `lotus_policy_step`.  Returns (final, losses(4,))."""
+        from . import native
+        m = self.m
+        if self._native is None:
+            if not native.supported(m):
+                raise NotImplementedError("native executor covers the production topology only")
+            self._native = native.NativeStep(m)
+        pt = m.ptv3_model
+        fts = batch["pc_fts"]
+        if not fts.is_cuda:
+            raise RuntimeError("lotus engine needs the model on a CUDA device (there is no CPU fallback)")
+        npoints = [int(v) for v in batch["npoints_in_batch"]]
+        S, R = pt.num_stages, len(pt.order)
+        rows = [[0]] * S
+        stages = tokenize(fts[:, :3], npoints, pt.order, pt.stride, list(pt.enc_patch_size), rows, self._perms(S, R, pt.shuffle_orders),
+                          m.config.action_config.voxel_size, self.div_mode)
+        self.last_stages = stages
+        tok_off = [0]
+        for l in batch["txt_lens"]:
+            tok_off.append(tok_off[-1] + int(l))
+        tok_dev = torch.tensor(tok_off, dtype=torch.int32).to(fts.device, non_blocking=True)
+        self.seed_counter += 1
+        seed = dropout_seed if dropout_seed is not None else int(torch.initial_seed()) * 1000003 + self.seed_counter
+        return self._native.run(batch, stages, tok_dev, tok_off, m.training, self.precision == "bf16", compute_loss,
+                                not compute_final_action, with_grad and compute_loss, seed)
+
     # ------------------------------------------------------------------ policy
     def forward(self, batch, compute_loss=False, **kwargs):
         m = self.m
@@ -165,6 +195,13 @@ class PolicyEngine:
         fts = batch["pc_fts"]
         if not fts.is_cuda:
             raise RuntimeError("lotus engine needs the model on a CUDA device (there is no CPU fallback)")
+        if self.use_native and not torch.is_grad_enabled():
+            final, lv = self.native_step(batch, compute_loss=compute_loss, with_grad=False,
+                                         compute_final_action=kwargs.get("compute_final_action", True))
+            if not compute_loss:
+                return final
+            lv = lv.clone()
+            return final, {"pos": lv[0], "rot": lv[1], "open": lv[2], "total": lv[3]}
         fts = fts.float().contiguous()
         npoints = [int(v) for v in batch["npoints_in_batch"]]
         B = len(npoints)

@@ -55,7 +55,7 @@ class _Lib:
         self.protos = parse_header()
         for name, (ret, args) in self.protos.items():
             fn = getattr(self.cdll, name)          # AttributeError here == header/library mismatch
-            fn.restype = ctypes.c_char_p if "char" in ret else ctypes.c_int
+            fn.restype = ctypes.c_char_p if "char" in ret else (ctypes.c_int64 if "int64_t" in ret else ctypes.c_int)
             fn.argtypes = [_ctype_of(t) for t, _ in args]
         self.cdll.lotus_last_error.restype = ctypes.c_char_p
         self.launches = 0                            # kernels-launching C calls issued (bench `gpu_launches`)

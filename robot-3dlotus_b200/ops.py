@@ -343,9 +343,9 @@ class SubmConvFn(torch.autograd.Function):
         if ctx.needs_input_grad[0]:
             dx = torch.empty_like(x)
             if tc:
-                L.lotus_subm_conv_dgrad_bf16(_p(dy), _p(STAGED[w.data_ptr()][1]), _p(dx), _p(nbr), nbr_stride, n, cin, cout, k3, 0, st)
+                L.lotus_subm_conv_dgrad_bf16(_p(dy), _p(STAGED[w.data_ptr()][1]), None, _p(dx), _p(nbr), nbr_stride, n, cin, cout, k3, 0, st)
             else:
-                L.lotus_subm_conv_dgrad_f32(_p(dy), _p(w), _p(dx), _p(nbr), nbr_stride, n, cin, cout, k3, st)
+                L.lotus_subm_conv_dgrad_f32(_p(dy), _p(w), None, _p(dx), _p(nbr), nbr_stride, n, cin, cout, k3, st)
         wbuf, dw = _grad_buf(w, ctx.needs_input_grad[1])
         if wbuf is not None:
             if tc and ctx.rule is not None:
@@ -601,7 +601,7 @@ class SegmentMaxFn(torch.autograd.Function):
         if dy.dtype != ctx.dtype:
             dy = to_bf16(dy) if ctx.dtype == torch.bfloat16 else to_f32(dy)
         dx = torch.zeros(ctx.shape, device=dy.device, dtype=ctx.dtype)
-        getattr(L, "lotus_segment_max_bwd_" + _sfx(dy))(_p(dy), _p(arg), arg.shape[0], arg.shape[1], _p(dx), _st())
+        getattr(L, "lotus_segment_max_bwd_" + _sfx(dy))(_p(dy), _p(arg), arg.shape[0], arg.shape[1], _p(dx), 0, _st())
         return dx, None, None, None
 
 

@@ -141,8 +141,14 @@ class TrainStep:
 
     def __call__(self, batch):
         self.opt.zero_grad()
-        _, losses = self.model(batch, compute_loss=True, compute_final_action=False)
-        losses["total"].backward()
+        eng = self.model.engine()
+        if eng.use_native:
+            batch = self.model.prepare_batch(batch)
+            _, lv = eng.native_step(batch, compute_loss=True, with_grad=True, compute_final_action=False)
+            losses = {"pos": lv[0], "rot": lv[1], "open": lv[2], "total": lv[3]}
+        else:
+            _, losses = self.model(batch, compute_loss=True, compute_final_action=False)
+            losses["total"].backward()
         self.opt.all_reduce()
         self.global_step += 1
         lr = self.learning_rate * get_lr_sched_decay_rate(self.global_step, self.warmup_steps, self.num_train_steps)

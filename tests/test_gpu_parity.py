@@ -566,3 +566,73 @@ def test_policy_bf16_mode_tracks_fp32_reference(gold_prod):
                 a, b = grads[k].flatten().double().cpu(), ref.flatten().double()
                 cos = (a @ b / (a.norm() * b.norm())).item()
                 assert cos > 0.95, (k, cos)          # bf16 rounding through ~60 layers; fp32 mode is the 1e-4 path
+
+
+# ------------------------------------------------------------------------------------------------ native one-call executor
+@pytest.mark.parametrize("which", ["small", "prod"])
+def test_native_step_matches_reference_fp32(which, gold_small, gold_prod):
+    """lotus_policy_step (C++ executor: forward + loss + backward in one call) in fp32 validation mode against the
+    reference golden vectors: losses 1e-4, every parameter gradient as tight as the per-op path."""
+    g = gold_small if which == "small" else gold_prod
+    cfg, model = make_model(g)
+    model = model.to(DEV).train()
+    eng = model.engine()
+    eng.forced_perms = g["perms"]
+    batch = {k: (v.to(DEV) if isinstance(v, torch.Tensor) else v) for k, v in g["batch"].items()}
+    final, lv = eng.native_step(batch, compute_loss=True, with_grad=True, compute_final_action=False)
+    names = ["pos", "rot", "open", "total"]
+    for i, k in enumerate(names):
+        assert abs(lv[i].item() - g["losses"][k].item()) <= TOL * abs(g["losses"][k].item()), (k, lv[i].item())
+    ref_act = g["train_actions"].double()
+    assert torch.equal(final[:, :3].cpu(), ref_act[:, :3]) and torch.allclose(final[:, 3:7].cpu(), ref_act[:, 3:7], atol=1e-9)
+    grads = {k: p.grad for k, p in model.named_parameters()}
+    floor = 1e-6 * max(g["grad_norms"].values())
+    errs = []
+    for k, n in g["grad_norms"].items():
+        gn = grads[k].norm().item()
+        if n < floor:
+            assert gn < 10 * floor, (k, gn, n)
+        else:
+            errs.append((abs(gn - n) / n, k))
+    errs.sort()
+    assert errs[len(errs) // 2][0] < 2e-5 and errs[-1][0] < (TOL if which == "small" else 2e-2), errs[-5:]
+    for k, ref in g["grads"].items():
+        if ref.norm().item() > floor:
+            assert rel(grads[k], ref) < (TOL if which == "small" else 2e-2), k
+    sd = model.state_dict()
+    for k, ref in g["bn_after"].items():
+        if "num_batches" in k:
+            assert int(sd[k]) == int(ref)
+        else:
+            assert rel(sd[k], ref) < 1e-5, k
+
+
+def test_native_step_bf16_and_eval(gold_prod, gold_small):
+    g = gold_prod
+    cfg, model = make_model(g)
+    model = model.to(DEV).train()
+    eng = model.engine()
+    eng.forced_perms = g["perms"]
+    eng.precision = "bf16"
+    batch = {k: (v.to(DEV) if isinstance(v, torch.Tensor) else v) for k, v in g["batch"].items()}
+    final, lv = eng.native_step(batch, compute_loss=True, with_grad=True, compute_final_action=False)
+    for i, k in enumerate(["pos", "rot", "open", "total"]):
+        assert abs(lv[i].item() - g["losses"][k].item()) <= 2e-2 * abs(g["losses"][k].item()), (k, lv[i].item())
+    grads = {k: p.grad for k, p in model.named_parameters()}
+    big = sorted(g["grad_norms"].items(), key=lambda kv: -kv[1])[:40]
+    for k, n in big:
+        assert abs(grads[k].norm().item() - n) <= 0.1 * n, (k, grads[k].norm().item(), n)
+    # eval / inference through the nn.Module API with the native executor (fp32): final actions == reference
+    g = gold_small
+    cfg, model = make_model(g)
+    sd = model.state_dict()
+    sd.update(g["bn_after"])
+    model.load_state_dict(sd, strict=True)
+    model = model.to(DEV).eval()
+    model.engine().forced_perms = g["perms_eval"]
+    model.engine().use_native = True
+    with torch.no_grad():
+        final = model({k: (v.clone() if isinstance(v, torch.Tensor) else v) for k, v in g["batch"].items()})
+    ref = g["final_actions_eval"]
+    assert torch.allclose(final[:, :3].cpu(), ref[:, :3], atol=1e-6) and torch.allclose(final[:, 3:7].cpu(), ref[:, 3:7], atol=1e-9)
+    assert rel(final[:, 7], ref[:, 7]) < TOL

@@ -97,7 +97,7 @@ def test_subm_conv_bf16(cin, cout):
     assert rel(y.float(), yr) < 1e-2
     wt = wd.reshape(cout, 27, cin).permute(2, 1, 0).contiguous()            # [ci][d][co]
     dx = torch.empty(n, cin, device=DEV, dtype=torch.bfloat16)
-    L.lotus_subm_conv_dgrad_bf16(P(dyd), P(wt), P(dx), P(stg.nbr3), stg.stride_alloc, n, cin, cout, 27, 0, None)
+    L.lotus_subm_conv_dgrad_bf16(P(dyd), P(wt), None, P(dx), P(stg.nbr3), stg.stride_alloc, n, cin, cout, 27, 0, None)
     assert rel(dx.float(), xr.grad) < 1e-2
     dw = torch.zeros(cout, 27, cin, device=DEV, dtype=torch.float32)
     L.lotus_subm_conv_wgrad_bf16(P(dyd), P(xd), P(dw), P(stg.nbr3), stg.stride_alloc, n, cin, cout, 27, None)

@@ -30,6 +30,10 @@ DOC = {
                             "nbr[d*stride + p] = voxel at grid[p]+off(d) in the same cloud or -1; d=(d0*k+d1)*k+d2, d0 along x.",
     "lotus_pair_lists": "Compact per-tap (output, input) voxel pair lists — the rulebook of spconv 2.3.6 SubMConv3d (call sites model.py:616-622,845-852); "
                         "consumed by the weight-gradient kernels.",
+    "lotus_policy_step": "One whole policy step in a single call: replaces SimplePolicyPTV3CA.forward + compute_loss + loss.backward() "
+                         "(models/simple_policy_ptv3.py:225-373; models/PointTransformerV3/model_ca.py:383-412) for the production topology; "
+                         "parameter gradients accumulate into the caller's sinks (train/train_simple_policy.py:211-216).",
+    "lotus_policy_step_calls": "Kernel-launching calls issued by the last lotus_policy_step (bench accounting).",
     "lotus_fps": "Replaces farthest_point_sample (explicit start index): train/datasets/common.py:108-129. Bit-exact indices.",
     "lotus_knn": "North-star kNN grouping (no reference function; SURVEY §8a row 13): brute force inside each cloud, ties -> lowest index.",
     "lotus_ball_query": "North-star radius grouping (no reference function; SURVEY §8a row 13): first nsample indices within radius.",
