@@ -107,6 +107,17 @@ __device__ __forceinline__ uint32_t lotus_hash3(uint32_t a, uint32_t b, uint32_t
   h ^= h >> 16; h *= 0x7FEB352Du; h ^= h >> 15; h *= 0x846CA68Bu; h ^= h >> 16;
   return h;
 }
+// elementwise dropout (GEMM epilogues, pointwise, dropout kernels): one hash decides FOUR consecutive elements (a byte
+// each), so the mask costs a quarter hash per element.  thr = round(p*256); keep-probability = 1 - thr/256.
+__device__ __forceinline__ uint32_t drop_thr(float p) { return (uint32_t)fminf(255.f, floorf(p * 256.f + 0.5f)); }
+__device__ __forceinline__ float drop_scale(uint32_t thr) { return 256.f / (256.f - (float)thr); }
+__device__ __forceinline__ uint32_t drop_hash4(uint64_t seed, uint32_t sid, uint64_t idx) {   // covers elements idx&~3 .. +3
+  return lotus_hash3((uint32_t)seed ^ (sid ^ (uint32_t)(idx >> 34)) * 0x27D4EB2Fu, (uint32_t)(seed >> 32), (uint32_t)(idx >> 2));
+}
+__device__ __forceinline__ bool drop_keep_e(uint64_t seed, uint32_t sid, uint64_t idx, uint32_t thr) {
+  return ((drop_hash4(seed, sid, idx) >> (8 * (uint32_t)(idx & 3))) & 0xFFu) >= thr;
+}
+// attention-probability dropout keeps the per-element hash
 __device__ __forceinline__ bool dropout_keep(uint64_t seed, uint32_t idx_hi, uint32_t idx_lo, float p) {
   uint32_t h = lotus_hash3((uint32_t)seed ^ idx_hi * 0x27D4EB2Fu, (uint32_t)(seed >> 32), idx_lo);
   return (h >> 8) * (1.0f / 16777216.0f) >= p;

@@ -143,8 +143,10 @@ __global__ void __launch_bounds__(256) k_gemm(int M, int N, int K, LA la, LB lb,
         if (ep.bias) v += ep.bias[gn];
         if (ep.act == ACT_GELU) v = gelu_f(v);
         else if (ep.act == ACT_LEAKY) v = v > 0.f ? v : v * ep.leaky;
-        if (ep.drop_p > 0.f)
-          v = dropout_keep(ep.seed, ep.drop_stream ^ (uint32_t)((uint64_t)o >> 32), (uint32_t)o, ep.drop_p) ? v / (1.f - ep.drop_p) : 0.f;
+        if (ep.drop_p > 0.f) {
+          uint32_t thr = drop_thr(ep.drop_p);
+          v = drop_keep_e(ep.seed, ep.drop_stream, (uint64_t)o, thr) ? v * drop_scale(thr) : 0.f;
+        }
         if (ep.residual) v += ep.residual[o];
         ep.out[o] = v;
       }

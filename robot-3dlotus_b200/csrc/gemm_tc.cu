@@ -16,14 +16,15 @@
 //   OP_MN_GATHER ... K-rows gathered through an index table          -> MN-major smem tile via cp.async
 #include "common.cuh"
 #include <cuda.h>
+#include <stdlib.h>
 
 namespace tc {
 
 constexpr int BM = 128;
 constexpr int BK = 64;            // 64 bf16 = 128 B = one SWIZZLE_128B span
 constexpr int MAX_STAGES = 4;
-constexpr int NUM_THREADS = 192;  // 6 warps
-constexpr int EPI_THREADS = 128;
+constexpr int NUM_THREADS = 320;  // 10 warps: TMA, MMA, 8 epilogue (warps 2-5 double as cp.async gather producers)
+constexpr int EPI_THREADS = 128;  // gather-producer threads (warps 2-5)
 
 enum { OP_K_TMA = 0, OP_K_GATHER = 1, OP_MN_TMA = 2, OP_MN_GATHER = 3 };
 enum { ACT_NONE = 0, ACT_GELU = 1, ACT_LEAKY = 2 };
@@ -42,6 +43,8 @@ struct Params {
   int M, N, K;                 // logical GEMM extents (K = reduction)
   int a_mode, b_mode;
   int kb_begin_stride;         // k-blocks per split (split-K over blockIdx.z)
+  unsigned long long* dbg_ts;  // dev knob: per-CTA timestamps (8 slots), set via lotus_tc_debug_buffer
+  int debug;                   // dev knob (LOTUS_TC_DEBUG): 1 skip epilogue math+store, 2 skip mainloop, 4 no store wait
   int stages;                  // smem pipeline depth (2..4): shallow pipelines leave room for several CTAs per SM
   // pair-list mode (sparse-conv weight gradient): blockIdx.z = tap * splits + split, K read from the device
   const int32_t* k_dev;        // [taps] reduction extent per tap, or null
@@ -65,6 +68,8 @@ struct Params {
 
 // ------------------------------------------------------------------------------------------------ PTX wrappers
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ unsigned long long gtimer() { unsigned long long t; asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t)); return t; }
+#define TS(slot) do { if (p.dbg_ts) p.dbg_ts[(blockIdx.x + gridDim.x * (blockIdx.y + gridDim.y * blockIdx.z)) * 8 + (slot)] = gtimer(); } while (0)
 
 __device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
   asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
@@ -93,6 +98,20 @@ __device__ __forceinline__ void tma_load_2d(void* dst, const CUtensorMap* map, u
       "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];" ::"r"(smem_u32(dst)),
       "l"(map), "r"(smem_u32(bar)), "r"(c0), "r"(c1)
       : "memory");
+}
+__device__ __forceinline__ void tma_store_2d(const CUtensorMap* map, const void* src, int c0, int c1) {
+  asm volatile("cp.async.bulk.tensor.2d.global.shared::cta.bulk_group [%0, {%2, %3}], [%1];" ::"l"(map), "r"(smem_u32(src)),
+               "r"(c0), "r"(c1)
+               : "memory");
+}
+__device__ __forceinline__ void tma_reduce_add_2d(const CUtensorMap* map, const void* src, int c0, int c1) {
+  asm volatile("cp.reduce.async.bulk.tensor.2d.global.shared::cta.add.tile.bulk_group [%0, {%2, %3}], [%1];" ::"l"(map),
+               "r"(smem_u32(src)), "r"(c0), "r"(c1)
+               : "memory");
+}
+__device__ __forceinline__ void tma_store_commit_wait() {
+  asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+  asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");   // smem may be released once the TMA has read it
 }
 __device__ __forceinline__ void cp_async_16(void* dst, const void* src, bool valid) {
   int sz = valid ? 16 : 0;  // src-size 0 -> zero fill
@@ -175,7 +194,8 @@ __device__ __forceinline__ void stage_mn_gather(uint8_t* tile, const GatherSpec&
 
 template <int BN>
 __global__ void __launch_bounds__(NUM_THREADS)
-k_gemm_tc(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_b, const Params p) {
+k_gemm_tc(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_b,
+          const __grid_constant__ CUtensorMap map_out, const __grid_constant__ CUtensorMap map_res, const Params p) {
   extern __shared__ __align__(1024) uint8_t smem_raw[];
   constexpr uint32_t A_BYTES = BM * BK * 2, B_BYTES = BN * BK * 2;
   const int STAGES = p.stages;
@@ -185,10 +205,14 @@ k_gemm_tc(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUt
   uint64_t* full = (uint64_t*)(sB + STAGES * B_BYTES);
   uint64_t* empty = full + MAX_STAGES;
   uint64_t* tmem_full = empty + MAX_STAGES;
-  uint32_t* tmem_slot = (uint32_t*)(tmem_full + 1);
+  uint64_t* res_full = tmem_full + 1;
+  uint32_t* tmem_slot = (uint32_t*)(res_full + 1);
+  float* sBias = (float*)(tmem_slot + 4);                                                 // [BN] bias slice of this tile
+  uint8_t* sRes = (uint8_t*)(((uintptr_t)(sBias + BN) + 1023) & ~(uintptr_t)1023);        // residual tile (only when p.residual)
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int m0 = blockIdx.x * BM, n0 = blockIdx.y * BN;
+  if (threadIdx.x == 0) TS(0);
   // reduction range of this CTA
   int tap = 0, Kext = p.K, kb0, kb1;
   if (p.k_dev) {
@@ -213,18 +237,29 @@ k_gemm_tc(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUt
     uint32_t full_count = 1 + ((a_gather || b_gather) ? EPI_THREADS : 0);
     for (int s = 0; s < STAGES; ++s) { mbar_init(&full[s], full_count); mbar_init(&empty[s], 1); }
     mbar_init(tmem_full, 1);
+    mbar_init(res_full, 1);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   if (warp == 1) tmem_alloc(tmem_slot, BN);   // BN in {64,128}: power of two >= 32
+  if (threadIdx.x >= 64 && threadIdx.x - 64 < BN) {   // stage the bias slice once (one coalesced load instead of per-element loads)
+    int n = n0 + threadIdx.x - 64;
+    sBias[threadIdx.x - 64] = (p.bias && n < p.N) ? p.bias[n] : 0.f;
+  }
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
+  if (threadIdx.x == 0) TS(1);
 
-  if (num_kb > 0) {
+  if (num_kb > 0 && !(p.debug & 2)) {
     if (warp == 0) {
       // ===================== TMA producer =====================
       if (lane == 0) {
+        if (p.residual) {   // residual tile [128 x BN] (same dtype as the output), boxes of 128-byte rows
+          const int box_cols = p.out_fp32 ? 32 : 64;
+          mbar_arrive_expect_tx(res_full, (uint32_t)(BM * BN * (p.out_fp32 ? 4 : 2)));
+          for (int j = 0; j < BN / box_cols; ++j) tma_load_2d(sRes + j * 16384, &map_res, res_full, n0 + j * box_cols, m0);
+        }
         uint32_t tx = (a_gather ? 0 : A_BYTES) + (b_gather ? 0 : B_BYTES);
         for (int i = 0; i < num_kb; ++i) {
           int s = i % STAGES, ph = (i / STAGES) & 1;
@@ -253,6 +288,7 @@ k_gemm_tc(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUt
           int s = i % STAGES, ph = (i / STAGES) & 1;
           mbar_wait(&full[s], ph);
           tc_fence_after();
+          if (i == 0) TS(2);
           uint32_t a_addr = smem_u32(sA + s * A_BYTES), b_addr = smem_u32(sB + s * B_BYTES);
 #pragma unroll
           for (int k = 0; k < BK / 16; ++k) {
@@ -262,10 +298,10 @@ k_gemm_tc(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUt
             umma_bf16(tmem_base, da, db, idesc, (i > 0 || k > 0) ? 1u : 0u);
           }
           umma_commit(&empty[s]);                       // frees the smem stage when these MMAs retire
-          if (i == num_kb - 1) umma_commit(tmem_full);  // accumulator complete
+          if (i == num_kb - 1) { umma_commit(tmem_full); TS(3); }  // accumulator complete
         }
       }
-    } else if (a_gather || b_gather) {
+    } else if ((a_gather || b_gather) && warp < 6) {
       // ===================== cp.async gather producers (warps 2-5) =====================
       const int t = threadIdx.x - 64;                   // 0..127
       const int LAG = STAGES >= 3 ? 2 : 1;              // stages in flight per thread before signalling
@@ -302,111 +338,114 @@ k_gemm_tc(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUt
   }
 
   // ===================== epilogue (warps 2-5) =====================
-  if (warp >= 2) {
+  // TMEM -> registers -> (bias, activation, dropout, residual) -> swizzled shared-memory tile -> TMA store
+  // (or TMA reduce-add for the split-K weight gradients).  The tile reuses the pipeline buffers, which are idle once
+  // the last MMA has retired; TMA clips rows >= M and columns >= N.
+  if (warp >= 2 && num_kb > 0 && !(p.debug & 1)) {
     const int lane_grp = warp & 3;                     // TMEM lanes [32*lane_grp, +32) are visible to this warp
-    const int row = m0 + lane_grp * 32 + lane;
-    if (num_kb > 0) {
-      mbar_wait(tmem_full, 0);
-      tc_fence_after();
-    }
-    const bool row_ok = row < p.M;
-    const float keep_scale = p.drop_p > 0.f ? 1.f / (1.f - p.drop_p) : 1.f;
+    const int half = (warp - 2) >> 2;                  // warps w and w+4 share a lane group and split the columns
+    const int r = lane_grp * 32 + lane;                // row inside the tile
+    const int row = m0 + r;
+    if (!(p.debug & 2)) { mbar_wait(tmem_full, 0); tc_fence_after(); }
+    if (threadIdx.x == 64) TS(4);
+    if (p.residual && !(p.debug & 2)) mbar_wait(res_full, 0);
+    const bool plain = (p.act == ACT_NONE) && !(p.drop_p > 0.f);
+    const uint32_t thr = drop_thr(p.drop_p);
+    const float keep_scale = p.drop_p > 0.f ? drop_scale(thr) : 1.f;
+    uint8_t* sOut = smem;                              // [BN/box_cols][128 rows][128 B], SWIZZLE_128B
+    const uint32_t sw = (uint32_t)(r & 7);
 #pragma unroll 1
-    for (int c0 = 0; c0 < BN; c0 += 32) {
+    for (int c0 = half * (BN / 2); c0 < (half + 1) * (BN / 2); c0 += 32) {
       uint32_t v[32];
-      if (num_kb > 0) {
+      if (!(p.debug & 8)) {
         tmem_ld_32x32b_x32(tmem_base + ((uint32_t)(lane_grp * 32) << 16) + (uint32_t)c0, v);
         tmem_ld_wait();
       } else {
 #pragma unroll
-        for (int j = 0; j < 32; ++j) v[j] = 0u;
+        for (int j = 0; j < 32; ++j) v[j] = (uint32_t)(c0 + j + r);
       }
-      if (!row_ok) continue;
       const int nbase = n0 + c0;
-      if (nbase >= p.N) continue;
-      const int64_t obase = (int64_t)row * p.ldo + nbase + (int64_t)tap * p.tap_out_stride;
-      if (p.atomic) {
-        float* o = (float*)p.out + obase;
-#pragma unroll
-        for (int j = 0; j < 32; ++j)
-          if (nbase + j < p.N) atomicAdd(o + j, __uint_as_float(v[j]));
-        continue;
-      }
       float f[32];
+      const float4* b4 = (const float4*)(sBias + c0);
 #pragma unroll
-      for (int j = 0; j < 32; ++j) {
-        float x = __uint_as_float(v[j]);
-        if (p.bias && nbase + j < p.N) x += p.bias[nbase + j];
-        f[j] = x;
+      for (int j = 0; j < 8; ++j) {
+        float4 bb = b4[j];
+        f[4 * j] = __uint_as_float(v[4 * j]) + bb.x; f[4 * j + 1] = __uint_as_float(v[4 * j + 1]) + bb.y;
+        f[4 * j + 2] = __uint_as_float(v[4 * j + 2]) + bb.z; f[4 * j + 3] = __uint_as_float(v[4 * j + 3]) + bb.w;
       }
-      const bool full32 = (nbase + 32 <= p.N) && ((p.ldo & 7) == 0);
-      if (p.out2) {  // pre-activation copy
-        if (p.out_fp32) {
-          float* o = (float*)p.out2 + obase;
+      if (!plain) {
+        if (p.act == ACT_GELU) {
 #pragma unroll
-          for (int j = 0; j < 32; ++j) if (nbase + j < p.N) o[j] = f[j];
-        } else {
-          __nv_bfloat16* o = (__nv_bfloat16*)p.out2 + obase;
-          if (full32) {
+          for (int j = 0; j < 32; ++j) f[j] = gelu_f(f[j]);
+        } else if (p.act == ACT_LEAKY) {
 #pragma unroll
-            for (int j = 0; j < 32; j += 8) {
-              uint4 w;
-              __nv_bfloat162 h0 = __floats2bfloat162_rn(f[j], f[j + 1]), h1 = __floats2bfloat162_rn(f[j + 2], f[j + 3]);
-              __nv_bfloat162 h2 = __floats2bfloat162_rn(f[j + 4], f[j + 5]), h3 = __floats2bfloat162_rn(f[j + 6], f[j + 7]);
-              w.x = *(uint32_t*)&h0; w.y = *(uint32_t*)&h1; w.z = *(uint32_t*)&h2; w.w = *(uint32_t*)&h3;
-              *(uint4*)(o + j) = w;
-            }
-          } else {
-#pragma unroll
-            for (int j = 0; j < 32; ++j) if (nbase + j < p.N) o[j] = __float2bfloat16(f[j]);
-          }
+          for (int j = 0; j < 32; ++j) f[j] = f[j] > 0.f ? f[j] : 0.02f * f[j];
         }
-      }
-#pragma unroll
-      for (int j = 0; j < 32; ++j) {
-        float x = f[j];
-        if (p.act == ACT_GELU) x = gelu_f(x);
-        else if (p.act == ACT_LEAKY) x = x > 0.f ? x : 0.02f * x;
         if (p.drop_p > 0.f) {
-          uint64_t o = (uint64_t)(obase + j);
-          x = dropout_keep(p.seed, p.drop_stream ^ (uint32_t)(o >> 32), (uint32_t)o, p.drop_p) ? x * keep_scale : 0.f;
-        }
-        f[j] = x;
-      }
-      if (p.out_fp32) {
-        float* o = (float*)p.out + obase;
-        const float* r = p.residual ? (const float*)p.residual + obase : nullptr;
+          const uint64_t o0 = (uint64_t)((int64_t)row * p.ldo + nbase);   // multiple of 4: four columns share one hash
 #pragma unroll
-        for (int j = 0; j < 32; ++j) if (nbase + j < p.N) o[j] = f[j] + (r ? r[j] : 0.f);
-      } else {
-        __nv_bfloat16* o = (__nv_bfloat16*)p.out + obase;
-        const __nv_bfloat16* r = p.residual ? (const __nv_bfloat16*)p.residual + obase : nullptr;
-        if (full32) {
+          for (int j = 0; j < 8; ++j) {
+            uint32_t h = drop_hash4(p.seed, p.drop_stream, o0 + 4 * j);
 #pragma unroll
-          for (int j = 0; j < 32; j += 8) {
-            if (r) {
-              uint4 rv = *(const uint4*)(r + j);
-              const __nv_bfloat162* rh = (const __nv_bfloat162*)&rv;
-#pragma unroll
-              for (int q = 0; q < 4; ++q) { float2 t2 = __bfloat1622float2(rh[q]); f[j + 2 * q] += t2.x; f[j + 2 * q + 1] += t2.y; }
-            }
-            uint4 w;
-            __nv_bfloat162 h0 = __floats2bfloat162_rn(f[j], f[j + 1]), h1 = __floats2bfloat162_rn(f[j + 2], f[j + 3]);
-            __nv_bfloat162 h2 = __floats2bfloat162_rn(f[j + 4], f[j + 5]), h3 = __floats2bfloat162_rn(f[j + 6], f[j + 7]);
-            w.x = *(uint32_t*)&h0; w.y = *(uint32_t*)&h1; w.z = *(uint32_t*)&h2; w.w = *(uint32_t*)&h3;
-            *(uint4*)(o + j) = w;
+            for (int q = 0; q < 4; ++q) f[4 * j + q] = (((h >> (8 * q)) & 0xFFu) >= thr) ? f[4 * j + q] * keep_scale : 0.f;
           }
-        } else {
-#pragma unroll
-          for (int j = 0; j < 32; ++j)
-            if (nbase + j < p.N) o[j] = __float2bfloat16(f[j] + (r ? __bfloat162float(r[j]) : 0.f));
         }
       }
+      if (p.debug & 16) { if (f[3] == 12345.678f) sBias[0] = f[5]; continue; }
+      if (p.out_fp32) {
+        // 32 fp32 columns = one 128-byte box row: box index c0/32, 8 chunks of 16 B
+        uint8_t* box = sOut + (c0 >> 5) * 16384 + r * 128;
+        const uint8_t* rbox = sRes + (c0 >> 5) * 16384 + r * 128;
+#pragma unroll
+        for (int ch = 0; ch < 8; ++ch) {
+          float4 w = make_float4(f[4 * ch], f[4 * ch + 1], f[4 * ch + 2], f[4 * ch + 3]);
+          if (p.residual) {
+            float4 q = *(const float4*)(rbox + ((ch ^ sw) << 4));
+            w.x += q.x; w.y += q.y; w.z += q.z; w.w += q.w;
+          }
+          *(float4*)(box + ((ch ^ sw) << 4)) = w;
+        }
+      } else {
+        // 32 bf16 columns = half of a 128-byte box row: box index c0/64, chunks (c0%64)/8 .. +3
+        uint8_t* box = sOut + (c0 >> 6) * 16384 + r * 128;
+        const uint8_t* rbox = sRes + (c0 >> 6) * 16384 + r * 128;
+        const int cb = (c0 & 63) >> 3;
+#pragma unroll
+        for (int ch = 0; ch < 4; ++ch) {
+          float* g = f + 8 * ch;
+          if (p.residual) {
+            uint4 q = *(const uint4*)(rbox + (((cb + ch) ^ sw) << 4));
+            const __nv_bfloat162* qh = (const __nv_bfloat162*)&q;
+#pragma unroll
+            for (int t2 = 0; t2 < 4; ++t2) { float2 e = __bfloat1622float2(qh[t2]); g[2 * t2] += e.x; g[2 * t2 + 1] += e.y; }
+          }
+          uint4 w;
+          __nv_bfloat162 h0 = __floats2bfloat162_rn(g[0], g[1]), h1 = __floats2bfloat162_rn(g[2], g[3]);
+          __nv_bfloat162 h2 = __floats2bfloat162_rn(g[4], g[5]), h3 = __floats2bfloat162_rn(g[6], g[7]);
+          w.x = *(uint32_t*)&h0; w.y = *(uint32_t*)&h1; w.z = *(uint32_t*)&h2; w.w = *(uint32_t*)&h3;
+          *(uint4*)(box + (((cb + ch) ^ sw) << 4)) = w;
+        }
+      }
+    }
+    fence_proxy_async();                               // generic-proxy smem writes -> visible to the TMA (async proxy)
+    asm volatile("bar.sync 1, 256;" ::: "memory");     // the eight epilogue warps
+    if (threadIdx.x == 64) TS(5);
+    if (threadIdx.x == 64 && !(p.debug & 32)) {
+      const int box_cols = p.out_fp32 ? 32 : 64;
+      const int ncol0 = n0 + (int)((int64_t)tap * p.tap_out_stride);      // per-tap column offset (conv weight gradient)
+      for (int j = 0; j < BN / box_cols; ++j) {
+        if (n0 + j * box_cols >= p.N) break;
+        if (p.atomic) tma_reduce_add_2d(&map_out, sOut + j * 16384, ncol0 + j * box_cols, m0);
+        else tma_store_2d(&map_out, sOut + j * 16384, ncol0 + j * box_cols, m0);
+      }
+      if (p.debug & 4) asm volatile("cp.async.bulk.commit_group;" ::: "memory"); else tma_store_commit_wait();
+      TS(6);
     }
   }
   tc_fence_before();
   __syncthreads();
   if (warp == 1) tmem_dealloc(tmem_base, BN);
+  if (threadIdx.x == 0) TS(7);
 }
 
 // ------------------------------------------------------------------------------------------------ host side
@@ -425,23 +464,29 @@ static EncodeTiledFn get_encode() {
   return fn;
 }
 
-// 2-D bf16 tensor [rows][cols] (cols contiguous, row stride ld elements); box = {box_cols (<=64), box_rows}
-static int make_map(CUtensorMap* m, const void* base, int64_t rows, int64_t cols, int64_t ld, int box_cols, int box_rows) {
+// 2-D tensor [rows][cols] (cols contiguous, row stride ld elements); box = {box_cols, box_rows}; 128-byte swizzle
+static int make_map(CUtensorMap* m, const void* base, int64_t rows, int64_t cols, int64_t ld, int box_cols, int box_rows,
+                    bool fp32 = false) {
   EncodeTiledFn enc = get_encode();
   if (!enc) { lotus_set_error("cuTensorMapEncodeTiled unavailable"); return 1; }
+  int es = fp32 ? 4 : 2;
   cuuint64_t dims[2] = {(cuuint64_t)cols, (cuuint64_t)rows};
-  cuuint64_t strides[1] = {(cuuint64_t)ld * 2};
+  cuuint64_t strides[1] = {(cuuint64_t)ld * es};
   cuuint32_t box[2] = {(cuuint32_t)box_cols, (cuuint32_t)box_rows};
   cuuint32_t estr[2] = {1, 1};
-  CUresult r = enc(m, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, (void*)base, dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
-                   CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  CUresult r = enc(m, fp32 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT32 : CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, (void*)base, dims, strides, box,
+                   estr, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                   CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   if (r != CUDA_SUCCESS) {
-    lotus_set_error("cuTensorMapEncodeTiled failed (%d): base=%p rows=%lld cols=%lld ld=%lld box=%dx%d", (int)r, base, (long long)rows,
-                    (long long)cols, (long long)ld, box_cols, box_rows);
+    lotus_set_error("cuTensorMapEncodeTiled failed (%d): base=%p rows=%lld cols=%lld ld=%lld box=%dx%d fp32=%d (base must be 16-byte "
+                    "aligned, row stride a multiple of 16 bytes)", (int)r, base, (long long)rows, (long long)cols, (long long)ld,
+                    box_cols, box_rows, (int)fp32);
     return 1;
   }
   return 0;
 }
+
+static unsigned long long* g_dbg_ts = nullptr;
 
 struct Operand {
   int mode;
@@ -453,9 +498,11 @@ struct Operand {
 static int launch(const Operand& A, const Operand& B, Params p, int BN, int splits, cudaStream_t st, int taps = 1,
                   int max_kb_hint = -1) {
   if (p.M <= 0 || p.N <= 0) return 0;
-  CUtensorMap ma, mb;
+  CUtensorMap ma, mb, mo, mr;
   memset(&ma, 0, sizeof(ma));
   memset(&mb, 0, sizeof(mb));
+  memset(&mo, 0, sizeof(mo));
+  memset(&mr, 0, sizeof(mr));
   p.a_mode = A.mode; p.b_mode = B.mode; p.ga = A.g; p.gb = B.g;
   int rc = 0;
   if (A.mode == OP_K_TMA) rc = make_map(&ma, A.ptr, p.M, p.K, A.ld, BK, BM);
@@ -464,6 +511,15 @@ static int launch(const Operand& A, const Operand& B, Params p, int BN, int spli
   if (B.mode == OP_K_TMA) rc = make_map(&mb, B.ptr, p.N, p.K, B.ld, BK, BN);
   else if (B.mode == OP_MN_TMA) rc = make_map(&mb, B.ptr, p.K, p.N, B.ld, 64, BK);
   if (rc) return rc;
+  {
+    // output (and residual) tile maps: logical [M rows][ld cols]; conv weight gradients address tap d at column offset d*tap_out_stride
+    int box_cols = p.out_fp32 ? 32 : 64;
+    int64_t out_cols = p.tap_out_stride ? p.ldo : p.N;
+    rc = make_map(&mo, p.out, p.M, out_cols, p.ldo, box_cols, BM, p.out_fp32 != 0);
+    if (rc) return rc;
+    if (p.residual) rc = make_map(&mr, p.residual, p.M, p.N, p.ldo, box_cols, BM, p.out_fp32 != 0);
+    if (rc) return rc;
+  }
   int num_kb = (p.K + BK - 1) / BK;
   splits = max(1, min(splits, num_kb));
   int per = (num_kb + splits - 1) / splits;
@@ -472,17 +528,29 @@ static int launch(const Operand& A, const Operand& B, Params p, int BN, int spli
   p.splits = splits;
   int kb_per_cta = max_kb_hint > 0 ? max_kb_hint : per;
   p.stages = kb_per_cta >= 4 ? 4 : (kb_per_cta >= 3 ? 3 : 2);
+  {
+    static int force_stages = -1;                       // dev knob: LOTUS_TC_STAGES=2..4
+    if (force_stages < 0) { const char* e = getenv("LOTUS_TC_STAGES"); force_stages = e ? atoi(e) : 0; }
+    if (force_stages >= 2 && force_stages <= 4) p.stages = min(force_stages, max(2, kb_per_cta));
+    static int dbg = -1;
+    if (dbg < 0) { const char* e = getenv("LOTUS_TC_DEBUG"); dbg = e ? atoi(e) : 0; }
+    p.debug = dbg;
+    p.dbg_ts = g_dbg_ts;
+  }
   dim3 grid((p.M + BM - 1) / BM, (p.N + BN - 1) / BN, splits * taps);
-  size_t smem = (size_t)p.stages * (BM * BK * 2 + BN * BK * 2) + 256 + 1024;
+  size_t tile_bytes = (size_t)BM * BN * (p.out_fp32 ? 4 : 2);
+  size_t pipe = (size_t)p.stages * (BM * BK * 2 + BN * BK * 2);
+  while (pipe < tile_bytes) { ++p.stages; pipe = (size_t)p.stages * (BM * BK * 2 + BN * BK * 2); }   // the output tile reuses the pipeline
+  size_t smem = pipe + 256 + 2048 + (size_t)BN * 4 + (p.residual ? tile_bytes : 0);
   cudaError_t e;
   if (BN == 128) {
     static bool set128 = false;
     if (!set128) { cudaFuncSetAttribute(k_gemm_tc<128>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024); set128 = true; }
-    k_gemm_tc<128><<<grid, NUM_THREADS, smem, st>>>(ma, mb, p);
+    k_gemm_tc<128><<<grid, NUM_THREADS, smem, st>>>(ma, mb, mo, mr, p);
   } else {
     static bool set64 = false;
     if (!set64) { cudaFuncSetAttribute(k_gemm_tc<64>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024); set64 = true; }
-    k_gemm_tc<64><<<grid, NUM_THREADS, smem, st>>>(ma, mb, p);
+    k_gemm_tc<64><<<grid, NUM_THREADS, smem, st>>>(ma, mb, mo, mr, p);
   }
   e = cudaGetLastError();
   if (e != cudaSuccess) { lotus_set_error("gemm_tc launch: %s", cudaGetErrorString(e)); return 1; }
@@ -503,11 +571,13 @@ static Params base_params(int M, int N, int K, void* out, int64_t ldo, int out_f
   return p;
 }
 
-// y[M,N] = [residual +] drop(act(x[M,K] @ w[N,K]^T + bias)) ; x, w bf16 ; y (and residual, y_preact) bf16 or fp32
+// y[M,N] = [residual +] drop(act(x[M,K] @ w[N,K]^T + bias)) ; x, w bf16 ; y (and residual) bf16 or fp32 ; y_preact: reserved (null)
 LOTUS_API int lotus_linear_fwd_bf16(const void* x, const void* w, const float* bias, const void* residual, void* y,
                                     void* y_preact, int M, int N, int K, int act, int out_fp32, float drop_p, uint64_t seed,
                                     uint32_t drop_stream, void* stream_) {
   LOTUS_CHECK_ARG(K % 8 == 0, "lotus_linear_fwd_bf16: K=%d must be a multiple of 8 (16-byte TMA rows)", K);
+  LOTUS_CHECK_ARG(y_preact == nullptr, "lotus_linear_fwd_bf16: y_preact is reserved and must be null");
+  LOTUS_CHECK_ARG(N % (out_fp32 ? 4 : 8) == 0, "lotus_linear_fwd_bf16: N=%d must keep output rows 16-byte aligned", N);
   Params p = base_params(M, N, K, y, N, out_fp32);
   p.out2 = y_preact; p.bias = bias; p.residual = residual; p.act = act; p.drop_p = drop_p; p.seed = seed; p.drop_stream = drop_stream;
   Operand A{tc::OP_K_TMA, (const __nv_bfloat16*)x, K, {}}, B{tc::OP_K_TMA, (const __nv_bfloat16*)w, K, {}};
@@ -595,3 +665,6 @@ LOTUS_API int lotus_subm_conv_wgrad_pairs_bf16(const void* dy, const void* x, fl
   Operand B{tc::OP_MN_GATHER, nullptr, 0, {(const __nv_bfloat16*)x, pairs_in, 0, Cin, 0, 0, K3}};
   return tc::launch(A, B, p, bn, splits, (cudaStream_t)stream_, K3, 4);
 }
+
+// dev tool: device buffer (8 x uint64 per CTA) receiving %globaltimer stamps of the next GEMM launches; null disables
+LOTUS_API int lotus_tc_debug_buffer(void* buf) { tc::g_dbg_ts = (unsigned long long*)buf; return 0; }

@@ -389,11 +389,12 @@ LOTUS_API int lotus_batchnorm_bwd_bf16(const void* dy, const void* x, int x_fp32
 template <typename TX, typename TY>
 __global__ void k_pointwise(const TX* __restrict__ x, const TX* __restrict__ a, TY* __restrict__ y, int64_t n,
                             int op, float alpha, float drop_p, uint64_t seed, uint32_t sid) {
-  float ks = drop_p > 0.f ? 1.f / (1.f - drop_p) : 1.f;
+  const uint32_t thr = drop_thr(drop_p);
+  float ks = drop_p > 0.f ? drop_scale(thr) : 1.f;
   for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
     float v = ldf(x, i), o;
     float m = 1.f;
-    if (drop_p > 0.f && op < 4) m = dropout_keep(seed, sid ^ (uint32_t)(i >> 32), (uint32_t)i, drop_p) ? ks : 0.f;
+    if (drop_p > 0.f && op < 4) m = drop_keep_e(seed, sid, (uint64_t)i, thr) ? ks : 0.f;
     switch (op) {
       case 0: o = gelu_f(v) * m; break;
       case 1: o = ldf(a, i) * m * gelu_grad_f(v); break;
@@ -485,9 +486,10 @@ LOTUS_API int lotus_cast_transpose_bf16(const float* w, void* w_bf16, void* wt_b
 // dropout: y = keep(seed, stream_id, i) ? x / (1-p) : 0 — the same call with dy gives the backward
 template <typename T>
 __global__ void k_dropout(const T* __restrict__ x, T* __restrict__ y, int64_t n, float p, uint64_t seed, uint32_t stream_id) {
-  float sc = 1.f / (1.f - p);
+  const uint32_t thr = drop_thr(p);
+  float sc = drop_scale(thr);
   for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x)
-    stf(y, i, dropout_keep(seed, stream_id ^ (uint32_t)(i >> 32), (uint32_t)i, p) ? ldf(x, i) * sc : 0.f);
+    stf(y, i, drop_keep_e(seed, stream_id, (uint64_t)i, thr) ? ldf(x, i) * sc : 0.f);
 }
 LOTUS_API int lotus_dropout_f32(const float* x, float* y, int64_t n, float p, uint64_t seed, uint32_t stream_id,
                                 void* stream_) {

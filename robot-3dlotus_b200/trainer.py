@@ -49,21 +49,22 @@ class FlatAdamW:
         self.params = [p for _, p in decay + no_decay]
         self.group_sizes = (len(decay), len(no_decay))
         sizes = [p.numel() for p in self.params]
-        total = sum(sizes)
-        self.flat_param = torch.empty(total, device=dev, dtype=torch.float32)
+        slots = [(n + 31) // 32 * 32 for n in sizes]        # 128-byte aligned slots (TMA reduce-add targets need 16-byte bases)
+        total = sum(slots)
+        self.flat_param = torch.zeros(total, device=dev, dtype=torch.float32)
         self.flat_grad = torch.zeros(total, device=dev, dtype=torch.float32)
         self.exp_avg = torch.zeros(total, device=dev, dtype=torch.float32)
         self.exp_avg_sq = torch.zeros(total, device=dev, dtype=torch.float32)
         ends, off = [], 0
         ops.GRAD_SINK.clear()
-        for p, n in zip(self.params, sizes):
+        for p, n, slot in zip(self.params, sizes, slots):
             view = self.flat_param[off: off + n].view_as(p)
             view.copy_(p.data)
             p.data = view                                   # parameters now alias the flat buffer
             g = self.flat_grad[off: off + n].view_as(p)
             p.grad = g                                      # reference-style access (`p.grad`) keeps working
             ops.GRAD_SINK[p.data_ptr()] = g
-            off += n
+            off += slot
             ends.append(off)
         self.seg_end = torch.tensor(ends, dtype=torch.int64, device=dev)
         wd = [weight_decay] * len(decay) + [0.0] * len(no_decay)
@@ -108,7 +109,7 @@ class FlatAdamW:
             n = p.numel()
             state[i] = {"step": self.step_count, "exp_avg": self.exp_avg[off: off + n].view_as(p).clone(),
                         "exp_avg_sq": self.exp_avg_sq[off: off + n].view_as(p).clone()}
-            off += n
+            off += (n + 31) // 32 * 32
         nd = self.group_sizes[0]
         groups = [
             {"lr": self.lr, "betas": self.betas, "eps": self.eps, "weight_decay": self.weight_decay, "correct_bias": True,
@@ -126,7 +127,7 @@ class FlatAdamW:
                 self.exp_avg[off: off + n].copy_(sd["state"][i]["exp_avg"].reshape(-1))
                 self.exp_avg_sq[off: off + n].copy_(sd["state"][i]["exp_avg_sq"].reshape(-1))
                 self.step_count = int(sd["state"][i]["step"])
-            off += n
+            off += (n + 31) // 32 * 32
 
 
 class TrainStep:

@@ -27,9 +27,9 @@ def rel(a, b):
     return ((a - b).abs().max() / b.abs().max().clamp_min(1e-12)).item()
 
 
-@pytest.mark.parametrize("M,N,K", [(128, 128, 64), (256, 64, 128), (300, 90, 128), (4096, 256, 64), (1000, 217, 128),
-                                   (5000, 192, 64), (77, 768, 3072), (1344, 3072, 768), (33, 8, 72)])
-@pytest.mark.parametrize("variant", ["plain", "bias_gelu_res_bf16", "fp32_out_preact"])
+@pytest.mark.parametrize("M,N,K", [(128, 128, 64), (256, 64, 128), (300, 88, 128), (4096, 256, 64), (1000, 216, 128),
+                                   (5000, 192, 64), (77, 768, 3072), (1344, 3072, 768), (33, 8, 72), (130, 40, 64)])
+@pytest.mark.parametrize("variant", ["plain", "bias_gelu_res_bf16", "fp32_out", "fp32_res_inplace"])
 def test_linear_fwd_bf16(M, N, K, variant):
     L = pkg("lib").load()
     g = torch.Generator().manual_seed(M + N + K)
@@ -43,18 +43,19 @@ def test_linear_fwd_bf16(M, N, K, variant):
         res = bf(torch.randn(M, N, generator=g)).to(DEV)
         act = 1
         ref = torch.nn.functional.gelu(ref + bias) + res.float()
-    elif variant == "fp32_out_preact":
+    elif variant == "fp32_out":
         bias = torch.randn(N, generator=g).to(DEV)
         out_fp32, act = 1, 2
-        pre = torch.empty(M, N, device=DEV, dtype=torch.float32)
-        ref_pre = ref + bias
-        ref = torch.nn.functional.leaky_relu(ref_pre, 0.02)
+        ref = torch.nn.functional.leaky_relu(ref + bias, 0.02)
     y = torch.full((M, N), float("nan"), device=DEV, dtype=torch.float32 if out_fp32 else torch.bfloat16)
-    L.lotus_linear_fwd_bf16(P(x), P(w), P(bias), P(res), P(y), P(pre), M, N, K, act, out_fp32, 0.0, 0, 0, None)
+    if variant == "fp32_res_inplace":         # y = y + x @ w^T, residual aliased with the output (dgrad accumulation pattern)
+        out_fp32 = 1
+        y = torch.randn(M, N, generator=g).to(DEV)
+        ref = ref + y
+        res = y
+    L.lotus_linear_fwd_bf16(P(x), P(w), P(bias), P(res), P(y), None, M, N, K, act, out_fp32, 0.0, 0, 0, None)
     torch.cuda.synchronize()
     assert rel(y.float(), ref) < (2e-3 if out_fp32 else 1e-2), rel(y.float(), ref)
-    if pre is not None:
-        assert rel(pre, ref_pre) < 2e-3
 
 
 @pytest.mark.parametrize("M,N,K", [(5000, 192, 64), (130, 64, 64), (4096, 256, 128), (131, 768, 3072), (70000, 64, 256)])

@@ -34,6 +34,7 @@ DOC = {
                          "(models/simple_policy_ptv3.py:225-373; models/PointTransformerV3/model_ca.py:383-412) for the production topology; "
                          "parameter gradients accumulate into the caller's sinks (train/train_simple_policy.py:211-216).",
     "lotus_policy_step_calls": "Kernel-launching calls issued by the last lotus_policy_step (bench accounting).",
+    "lotus_tc_debug_buffer": "Development aid: per-CTA %globaltimer stamps of the tensor-core GEMM phases.",
     "lotus_fps": "Replaces farthest_point_sample (explicit start index): train/datasets/common.py:108-129. Bit-exact indices.",
     "lotus_knn": "North-star kNN grouping (no reference function; SURVEY §8a row 13): brute force inside each cloud, ties -> lowest index.",
     "lotus_ball_query": "North-star radius grouping (no reference function; SURVEY §8a row 13): first nsample indices within radius.",
