@@ -93,12 +93,197 @@ __global__ void k_ln_bwd(const TDY* __restrict__ dy, RowMap dym, const T* __rest
   }
 }
 
+
+// ---------------------------------------------------------------- vectorised bf16 LayerNorm (16-byte accesses, one pass)
+// A row of C channels is covered by LPR lanes (power of two, <= 32), each holding VPL vectors of 8 bf16 in registers;
+// 32/LPR rows per warp; mean / variance by shuffle inside the lane group.  Rows may be strided (RowMap), row bases and
+// strides are multiples of 8 elements so every access is a 16-byte vector.
+__device__ __forceinline__ void unpack8(const uint4& u, float* f) {
+  const __nv_bfloat162* h = (const __nv_bfloat162*)&u;
+#pragma unroll
+  for (int i = 0; i < 4; ++i) { float2 t = __bfloat1622float2(h[i]); f[2 * i] = t.x; f[2 * i + 1] = t.y; }
+}
+__device__ __forceinline__ uint4 pack8(const float* f) {
+  uint4 u;
+  __nv_bfloat162* h = (__nv_bfloat162*)&u;
+#pragma unroll
+  for (int i = 0; i < 4; ++i) h[i] = __floats2bfloat162_rn(f[2 * i], f[2 * i + 1]);
+  return u;
+}
+__device__ __forceinline__ void load8(const bf16_t* p, float* f) { unpack8(*(const uint4*)p, f); }
+__device__ __forceinline__ void load8(const float* p, float* f) {
+  float4 a = *(const float4*)p, b = *(const float4*)(p + 4);
+  f[0] = a.x; f[1] = a.y; f[2] = a.z; f[3] = a.w; f[4] = b.x; f[5] = b.y; f[6] = b.z; f[7] = b.w;
+}
+__device__ __forceinline__ float group_sum(float v, int lpr) {
+  for (int o = lpr >> 1; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  return v;
+}
+
+template <int VPL>
+__global__ void __launch_bounds__(256) k_ln_fwd_vec(const bf16_t* __restrict__ x, RowMap xm, bf16_t* __restrict__ y, RowMap ym,
+                                                    const bf16_t* __restrict__ residual, const float* __restrict__ gamma,
+                                                    const float* __restrict__ beta, float* __restrict__ mean,
+                                                    float* __restrict__ rstd, int64_t rows, int C, int lpr, float eps) {
+  const int lane = threadIdx.x & 31, lig = lane & (lpr - 1), rpw = 32 / lpr;
+  const int nvec = C >> 3;
+  const int64_t warps = (int64_t)gridDim.x * (blockDim.x >> 5);
+  const float invC = 1.f / (float)C;
+  for (int64_t r0 = ((int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5)) * rpw; r0 < rows; r0 += warps * rpw) {
+    int64_t r = r0 + lane / lpr;
+    bool rok = r < rows;
+    float v[VPL][8];
+    float s = 0.f;
+    const bf16_t* xr = x + (rok ? xm(r) : 0);
+#pragma unroll
+    for (int j = 0; j < VPL; ++j) {
+      int vi = lig + j * lpr;
+      if (rok && vi < nvec) { load8(xr + vi * 8, v[j]); } else {
+#pragma unroll
+        for (int e = 0; e < 8; ++e) v[j][e] = 0.f;
+      }
+#pragma unroll
+      for (int e = 0; e < 8; ++e) s += v[j][e];
+    }
+    float mu = group_sum(s, lpr) * invC;
+    float q = 0.f;
+#pragma unroll
+    for (int j = 0; j < VPL; ++j) {
+      int vi = lig + j * lpr;
+      if (vi < nvec) {
+#pragma unroll
+        for (int e = 0; e < 8; ++e) { float d = v[j][e] - mu; q += d * d; }
+      }
+    }
+    float rs = rsqrtf(group_sum(q, lpr) * invC + eps);
+    if (!rok) continue;
+    if (lig == 0) { if (mean) mean[r] = mu; if (rstd) rstd[r] = rs; }
+    int64_t yo = ym(r);
+#pragma unroll
+    for (int j = 0; j < VPL; ++j) {
+      int vi = lig + j * lpr;
+      if (vi < nvec) {
+        float g[8], b[8], o[8];
+        load8(gamma + vi * 8, g); load8(beta + vi * 8, b);
+#pragma unroll
+        for (int e = 0; e < 8; ++e) o[e] = (v[j][e] - mu) * rs * g[e] + b[e];
+        if (residual) {
+          float rr[8];
+          load8(residual + yo + vi * 8, rr);
+#pragma unroll
+          for (int e = 0; e < 8; ++e) o[e] += rr[e];
+        }
+        *(uint4*)(y + yo + vi * 8) = pack8(o);
+      }
+    }
+  }
+}
+
+template <int VPL, typename TDY>
+__global__ void __launch_bounds__(256) k_ln_bwd_vec(const TDY* __restrict__ dy, RowMap dym, const bf16_t* __restrict__ x, RowMap xm,
+                                                    bf16_t* __restrict__ dx, RowMap dxm, const float* __restrict__ gamma,
+                                                    const float* __restrict__ mean, const float* __restrict__ rstd,
+                                                    float* __restrict__ dgamma, float* __restrict__ dbeta, int64_t rows, int C,
+                                                    int lpr, int accumulate_dx) {
+  extern __shared__ float sacc[];  // [2][C]
+  const int lane = threadIdx.x & 31, lig = lane & (lpr - 1), rpw = 32 / lpr;
+  const int nvec = C >> 3;
+  for (int c = threadIdx.x; c < 2 * C; c += blockDim.x) sacc[c] = 0.f;
+  __syncthreads();
+  float ag[VPL][8], ab[VPL][8], g[VPL][8];
+#pragma unroll
+  for (int j = 0; j < VPL; ++j) {
+    int vi = lig + j * lpr;
+#pragma unroll
+    for (int e = 0; e < 8; ++e) { ag[j][e] = 0.f; ab[j][e] = 0.f; g[j][e] = 0.f; }
+    if (vi < nvec) load8(gamma + vi * 8, g[j]);
+  }
+  const int64_t warps = (int64_t)gridDim.x * (blockDim.x >> 5);
+  const float invC = 1.f / (float)C;
+  for (int64_t r0 = ((int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5)) * rpw; r0 < rows; r0 += warps * rpw) {
+    int64_t r = r0 + lane / lpr;
+    bool rok = r < rows;
+    float xh[VPL][8], d[VPL][8];
+    float mu = rok ? mean[r] : 0.f, rs = rok ? rstd[r] : 0.f;
+    float s1 = 0.f, s2 = 0.f;
+    const bf16_t* xr = x + (rok ? xm(r) : 0);
+    const TDY* dyr = dy + (rok ? dym(r) : 0);
+#pragma unroll
+    for (int j = 0; j < VPL; ++j) {
+      int vi = lig + j * lpr;
+      if (rok && vi < nvec) {
+        load8(xr + vi * 8, xh[j]); load8(dyr + vi * 8, d[j]);
+#pragma unroll
+        for (int e = 0; e < 8; ++e) {
+          xh[j][e] = (xh[j][e] - mu) * rs;
+          float gg = d[j][e] * g[j][e];
+          s1 += gg; s2 += gg * xh[j][e];
+          ag[j][e] += d[j][e] * xh[j][e]; ab[j][e] += d[j][e];
+        }
+      } else {
+#pragma unroll
+        for (int e = 0; e < 8; ++e) { xh[j][e] = 0.f; d[j][e] = 0.f; }
+      }
+    }
+    s1 = group_sum(s1, lpr) * invC; s2 = group_sum(s2, lpr) * invC;
+    if (!rok) continue;
+    int64_t xo = dxm(r);
+#pragma unroll
+    for (int j = 0; j < VPL; ++j) {
+      int vi = lig + j * lpr;
+      if (vi < nvec) {
+        float o[8];
+#pragma unroll
+        for (int e = 0; e < 8; ++e) o[e] = rs * (d[j][e] * g[j][e] - s1 - xh[j][e] * s2);
+        if (accumulate_dx) {
+          float old[8];
+          load8(dx + xo + vi * 8, old);
+#pragma unroll
+          for (int e = 0; e < 8; ++e) o[e] += old[e];
+        }
+        *(uint4*)(dx + xo + vi * 8) = pack8(o);
+      }
+    }
+  }
+  // reduce the per-lane parameter-gradient partials: lanes with the same `lig` hold the same channels
+#pragma unroll
+  for (int j = 0; j < VPL; ++j) {
+    int vi = lig + j * lpr;
+#pragma unroll
+    for (int e = 0; e < 8; ++e) {
+      float a = ag[j][e], b = ab[j][e];
+      for (int o = 16; o >= lpr; o >>= 1) { a += __shfl_xor_sync(0xffffffffu, a, o); b += __shfl_xor_sync(0xffffffffu, b, o); }
+      if (lane < lpr && vi < nvec) { atomicAdd(&sacc[vi * 8 + e], a); atomicAdd(&sacc[C + vi * 8 + e], b); }
+    }
+  }
+  __syncthreads();
+  for (int c = threadIdx.x; c < C; c += blockDim.x) {
+    if (dgamma) atomicAdd(&dgamma[c], sacc[c]);
+    if (dbeta) atomicAdd(&dbeta[c], sacc[C + c]);
+  }
+}
+
+static inline bool vec_ok(const RowMap& m) { return (m.outer_stride % 8 == 0) && (m.inner_stride % 8 == 0); }
+static inline int pick_lpr(int C) { int nv = C >> 3, l = 1; while (l < nv && l < 32) l <<= 1; return l; }
+static inline bool aligned16(const void* p) { return ((uintptr_t)p & 15) == 0; }
+
 template <typename T>
 static int ln_fwd_impl(const void* x, int x_inner, int64_t x_outer_stride, int64_t x_inner_stride, void* y, int y_inner,
                        int64_t y_outer_stride, int64_t y_inner_stride, const void* residual, const float* gamma,
                        const float* beta, float* mean, float* rstd, int64_t rows, int C, float eps, void* stream_) {
   if (rows <= 0) return 0;
   RowMap xm{x_inner, x_outer_stride, x_inner_stride}, ym{y_inner, y_outer_stride, y_inner_stride};
+  if (sizeof(T) == 2 && C % 8 == 0 && C <= 1024 && vec_ok(xm) && vec_ok(ym) && aligned16(x) && aligned16(y) &&
+      (!residual || aligned16(residual)) && aligned16(gamma) && aligned16(beta)) {
+    int lpr = pick_lpr(C), vpl = ceil_div(C >> 3, lpr), rpw = 32 / lpr;
+    int blocks = min(ceil_div(ceil_div(rows, rpw), 8), kNumSM * 8);
+    cudaStream_t st = (cudaStream_t)stream_;
+#define LNF(V) k_ln_fwd_vec<V><<<blocks, 256, 0, st>>>((const bf16_t*)x, xm, (bf16_t*)y, ym, (const bf16_t*)residual, gamma, beta, mean, rstd, rows, C, lpr, eps)
+    if (vpl == 1) LNF(1); else if (vpl == 2) LNF(2); else if (vpl == 3) LNF(3); else LNF(4);
+#undef LNF
+    LOTUS_CUDA_OK();
+    return 0;
+  }
   k_ln_fwd<T><<<ceil_div(rows, 8), 256, 0, (cudaStream_t)stream_>>>((const T*)x, xm, (T*)y, ym, (const T*)residual, gamma, beta,
                                                                    mean, rstd, rows, C, eps);
   LOTUS_CUDA_OK();
@@ -134,6 +319,16 @@ static int ln_bwd_impl(const void* dy, int dy_inner, int64_t dy_outer_stride, in
   blocks = ceil_div(rows, rpb);
   size_t smem = (size_t)2 * C * 4;
   LOTUS_CHECK_ARG(C <= 32 * 32, "lotus_layernorm_bwd: C=%d > 1024", C);
+  if (sizeof(T) == 2 && C % 8 == 0 && vec_ok(dym) && vec_ok(xm) && vec_ok(dxm) && aligned16(dy) && aligned16(x) && aligned16(dx) &&
+      aligned16(gamma)) {
+    int lpr = pick_lpr(C), vpl = ceil_div(C >> 3, lpr), rpw = 32 / lpr;
+    int vblocks = min(ceil_div(ceil_div(rows, rpw), 8), kNumSM * 4);
+#define LNB(V) k_ln_bwd_vec<V, TDY><<<vblocks, 256, smem, st>>>((const TDY*)dy, dym, (const bf16_t*)x, xm, (bf16_t*)dx, dxm, gamma, mean, rstd, dgamma, dbeta, rows, C, lpr, accumulate_dx)
+    if (vpl == 1) LNB(1); else if (vpl == 2) LNB(2); else if (vpl == 3) LNB(3); else LNB(4);
+#undef LNB
+    LOTUS_CUDA_OK();
+    return 0;
+  }
 #define LN_BWD(CPL)                                                                                                   \
   k_ln_bwd<CPL, TDY, T><<<blocks, 256, smem, st>>>((const TDY*)dy, dym, (const T*)x, xm, (T*)dx, dxm, gamma, mean, rstd, \
                                                    dgamma, dbeta, rows, C, rpb, accumulate_dx)
@@ -206,9 +401,98 @@ static void col_launch_cfg(int64_t rows, int C, dim3* grid, int* rpb) {
   *grid = dim3(cb, rb);
 }
 
+
+// 8 bf16 per thread (16-byte accesses); same op codes and dropout mask as k_pointwise
+__global__ void __launch_bounds__(256) k_pointwise_vec(const bf16_t* __restrict__ x, const bf16_t* __restrict__ a, bf16_t* __restrict__ y,
+                                                       int64_t nvec, int op, float alpha, float drop_p, uint64_t seed, uint32_t sid) {
+  const uint32_t thr = drop_thr(drop_p);
+  const float ks = drop_p > 0.f ? drop_scale(thr) : 1.f;
+  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < nvec; i += (int64_t)gridDim.x * blockDim.x) {
+    float v[8], av[8], o[8], m[8];
+    load8(x + i * 8, v);
+    if (op == 1 || op == 3 || op == 4) load8(a + i * 8, av);
+#pragma unroll
+    for (int e = 0; e < 8; ++e) m[e] = 1.f;
+    if (drop_p > 0.f && op < 4) {
+      uint32_t h0 = drop_hash4(seed, sid, (uint64_t)i * 8), h1 = drop_hash4(seed, sid, (uint64_t)i * 8 + 4);
+#pragma unroll
+      for (int e = 0; e < 4; ++e) {
+        m[e] = (((h0 >> (8 * e)) & 0xFFu) >= thr) ? ks : 0.f;
+        m[4 + e] = (((h1 >> (8 * e)) & 0xFFu) >= thr) ? ks : 0.f;
+      }
+    }
+#pragma unroll
+    for (int e = 0; e < 8; ++e) {
+      switch (op) {
+        case 0: o[e] = gelu_f(v[e]) * m[e]; break;
+        case 1: o[e] = av[e] * m[e] * gelu_grad_f(v[e]); break;
+        case 2: o[e] = (v[e] > 0.f ? v[e] : v[e] * alpha) * m[e]; break;
+        case 3: o[e] = av[e] * m[e] * (v[e] > 0.f ? 1.f : alpha); break;
+        case 4: o[e] = av[e] + v[e]; break;
+        case 5: o[e] = v[e] * alpha; break;
+        default: o[e] = v[e]; break;
+      }
+    }
+    *(uint4*)(y + i * 8) = pack8(o);
+  }
+}
+__global__ void __launch_bounds__(256) k_dropout_vec(const bf16_t* __restrict__ x, bf16_t* __restrict__ y, int64_t nvec, float p,
+                                                     uint64_t seed, uint32_t sid) {
+  const uint32_t thr = drop_thr(p);
+  const float ks = drop_scale(thr);
+  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < nvec; i += (int64_t)gridDim.x * blockDim.x) {
+    float v[8];
+    load8(x + i * 8, v);
+    uint32_t h0 = drop_hash4(seed, sid, (uint64_t)i * 8), h1 = drop_hash4(seed, sid, (uint64_t)i * 8 + 4);
+#pragma unroll
+    for (int e = 0; e < 4; ++e) {
+      v[e] = (((h0 >> (8 * e)) & 0xFFu) >= thr) ? v[e] * ks : 0.f;
+      v[4 + e] = (((h1 >> (8 * e)) & 0xFFu) >= thr) ? v[4 + e] * ks : 0.f;
+    }
+    *(uint4*)(y + i * 8) = pack8(v);
+  }
+}
+// column sums of a bf16 [rows, C] matrix, C % 8 == 0: thread = (row group, 8-channel vector); block partials via shared memory
+__global__ void __launch_bounds__(256) k_col_sum_vec(const bf16_t* __restrict__ x, int64_t rows, int C, float* __restrict__ out,
+                                                     int rows_per_block) {
+  extern __shared__ float sred[];          // [C]
+  const int nvec = C >> 3;                 // vectors per row
+  const int tpr = min(nvec, 256);          // threads per row
+  const int rg = 256 / tpr;                // row groups per block
+  const int tv = threadIdx.x % tpr, tr = threadIdx.x / tpr;
+  for (int c = threadIdx.x; c < C; c += blockDim.x) sred[c] = 0.f;
+  __syncthreads();
+  int64_t r0 = (int64_t)blockIdx.x * rows_per_block, r1 = min(rows, r0 + rows_per_block);
+  if (tr < rg) {
+    for (int v0 = tv; v0 < nvec; v0 += tpr) {
+      float acc[8];
+#pragma unroll
+      for (int e = 0; e < 8; ++e) acc[e] = 0.f;
+      for (int64_t r = r0 + tr; r < r1; r += rg) {
+        float v[8];
+        load8(x + r * C + v0 * 8, v);
+#pragma unroll
+        for (int e = 0; e < 8; ++e) acc[e] += v[e];
+      }
+#pragma unroll
+      for (int e = 0; e < 8; ++e) atomicAdd(&sred[v0 * 8 + e], acc[e]);
+    }
+  }
+  __syncthreads();
+  for (int c = threadIdx.x; c < C; c += blockDim.x) atomicAdd(&out[c], sred[c]);
+}
+
 template <typename T>
 static int colsum_impl(const void* x, int64_t rows, int C, float* out_accum, void* stream_) {
   if (rows <= 0) return 0;
+  if (sizeof(T) == 2 && C % 8 == 0 && C <= 8192 && aligned16(x)) {
+    int blocks = max(1, min(ceil_div(rows, 64), kNumSM * 4));
+    int rpbv = ceil_div(rows, blocks);
+    blocks = ceil_div(rows, rpbv);
+    k_col_sum_vec<<<blocks, 256, (size_t)C * 4, (cudaStream_t)stream_>>>((const bf16_t*)x, rows, C, out_accum, rpbv);
+    LOTUS_CUDA_OK();
+    return 0;
+  }
   dim3 grid; int rpb;
   col_launch_cfg(rows, C, &grid, &rpb);
   k_col_sum<T><<<grid, 256, 0, (cudaStream_t)stream_>>>((const T*)x, rows, C, nullptr, 0, out_accum, rpb);
@@ -418,6 +702,12 @@ LOTUS_API int lotus_pointwise_f32(const float* x, const float* a, float* y, int6
 LOTUS_API int lotus_pointwise_bf16(const void* x, const void* a, void* y, int64_t n, int op, float alpha, float drop_p,
                                    uint64_t seed, uint32_t drop_stream, void* stream_) {
   if (n <= 0) return 0;
+  if (n % 8 == 0 && aligned16(x) && aligned16(y) && (!a || aligned16(a))) {
+    k_pointwise_vec<<<min(ceil_div(n / 8, 256), kNumSM * 16), 256, 0, (cudaStream_t)stream_>>>(
+        (const bf16_t*)x, (const bf16_t*)a, (bf16_t*)y, n / 8, op, alpha, drop_p, seed, drop_stream);
+    LOTUS_CUDA_OK();
+    return 0;
+  }
   k_pointwise<bf16_t, bf16_t><<<min(ceil_div(n, 256), kNumSM * 16), 256, 0, (cudaStream_t)stream_>>>(
       (const bf16_t*)x, (const bf16_t*)a, (bf16_t*)y, n, op, alpha, drop_p, seed, drop_stream);
   LOTUS_CUDA_OK();
@@ -502,6 +792,12 @@ LOTUS_API int lotus_dropout_f32(const float* x, float* y, int64_t n, float p, ui
 LOTUS_API int lotus_dropout_bf16(const void* x, void* y, int64_t n, float p, uint64_t seed, uint32_t stream_id, void* stream_) {
   if (n <= 0) return 0;
   LOTUS_CHECK_ARG(p >= 0.f && p < 1.f, "lotus_dropout_bf16: p=%f", p);
+  if (n % 8 == 0 && aligned16(x) && aligned16(y)) {
+    k_dropout_vec<<<min(ceil_div(n / 8, 256), kNumSM * 16), 256, 0, (cudaStream_t)stream_>>>((const bf16_t*)x, (bf16_t*)y, n / 8, p, seed,
+                                                                                          stream_id);
+    LOTUS_CUDA_OK();
+    return 0;
+  }
   k_dropout<bf16_t><<<min(ceil_div(n, 256), kNumSM * 16), 256, 0, (cudaStream_t)stream_>>>((const bf16_t*)x, (bf16_t*)y, n, p, seed,
                                                                                           stream_id);
   LOTUS_CUDA_OK();
