@@ -581,3 +581,29 @@ def ball_query_indices(query, ref, radius, nsample):
             out[i, :] = hit[0]
             out[i, : hit.size] = hit
     return out
+
+
+# ---------------------------------------------------------------------------------------------------------------------
+# optimizer step (train/train_simple_policy.py:237-243 -> torch clip_grad_norm_; train/optim/adamw.py:53-112;
+# parameter grouping train/optim/misc.py:13-55: names containing 'bias' get weight_decay 0)
+def clip_coefficient(grads, max_norm):
+    """torch.nn.utils.clip_grad_norm_: total L2 norm over all tensors, coefficient clamped to 1"""
+    total = torch.sqrt(sum((g.double() ** 2).sum() for g in grads)).float()
+    return float(torch.clamp(max_norm / (total + 1e-6), max=1.0)), float(total)
+
+
+def adamw_step(params, grads, exp_avg, exp_avg_sq, step, lr, weight_decays, betas=(0.9, 0.98), eps=1e-6, max_grad_norm=10.0):
+    """in-place reference AdamW over lists of tensors (`step` is the 1-based step being taken); returns the grad norm"""
+    norm = None
+    if max_grad_norm and max_grad_norm > 0:
+        coef, norm = clip_coefficient(grads, max_grad_norm)
+        grads = [g * coef for g in grads]
+    b1, b2 = betas
+    step_size = lr * math.sqrt(1.0 - b2 ** step) / (1.0 - b1 ** step)
+    for p, g, m, v, wd in zip(params, grads, exp_avg, exp_avg_sq, weight_decays):
+        m.mul_(b1).add_(g, alpha=1.0 - b1)
+        v.mul_(b2).addcmul_(g, g, value=1.0 - b2)
+        p.addcdiv_(m, v.sqrt().add_(eps), value=-step_size)
+        if wd > 0.0:
+            p.add_(p, alpha=-lr * wd)
+    return norm

@@ -40,7 +40,9 @@ class FlatAdamW:
 
     def __init__(self, model, lr=1e-4, betas=(0.9, 0.98), eps=1e-6, weight_decay=0.05, max_grad_norm=10.0):
         named = [(n, p) for n, p in model.named_parameters() if p.requires_grad]
-        assert named and all(p.is_cuda and p.dtype == torch.float32 for _, p in named), "move the model to CUDA first"
+        assert named and all(p.dtype == torch.float32 for _, p in named), "fp32 master parameters expected"
+        # the flat layout and the all-reduce are device-agnostic (gloo tests drive them on CPU tensors);
+        # `step()` launches the fused CUDA kernels and refuses to run anywhere else
         dev = named[0][1].device
         # group order of the reference: decayed tensors first, then the 'bias' tensors
         decay = [(n, p) for n, p in named if "bias" not in n]
@@ -83,6 +85,9 @@ class FlatAdamW:
             dist.all_reduce(self.flat_grad, op=dist.ReduceOp.SUM)
 
     def step(self, lr=None):
+        if not self.flat_param.is_cuda:
+            raise RuntimeError("FlatAdamW.step runs the fused CUDA optimizer kernels: move the model to CUDA first "
+                               "(there is no CPU optimizer path)")
         L = load()
         lr = self.lr if lr is None else lr
         self.step_count += 1

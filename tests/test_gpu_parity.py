@@ -638,3 +638,36 @@ def test_native_step_bf16_and_eval(gold_prod, gold_small):
     ref = g["final_actions_eval"]
     assert torch.allclose(final[:, :3].cpu(), ref[:, :3], atol=1e-6) and torch.allclose(final[:, 3:7].cpu(), ref[:, 3:7], atol=1e-9)
     assert rel(final[:, 7], ref[:, 7]) < TOL
+
+
+def test_flat_adamw_matches_reference_optimizer():
+    """three steps of the fused flat-buffer clip+AdamW against the oracle's restatement of train/optim/adamw.py:53-112
+    with torch's clip_grad_norm_ (train_simple_policy.py:237-243), decayed / bias groups as optim/misc.py:13-55"""
+    cfg = pkg("config").small_model_config()
+    model = pkg("policy").build_parameter_shell(cfg)
+    pkg("testing").deterministic_reinit(model, 5)
+    model = model.to(DEV)
+    opt = pkg("trainer").FlatAdamW(model, lr=2e-3, weight_decay=0.05, max_grad_norm=0.5)
+    nd = opt.group_sizes[0]
+    ref_p = [p.detach().cpu().clone() for p in opt.params]
+    ref_m = [torch.zeros_like(p) for p in ref_p]
+    ref_v = [torch.zeros_like(p) for p in ref_p]
+    wds = [0.05] * nd + [0.0] * (len(ref_p) - nd)
+    gen = torch.Generator().manual_seed(3)
+    for step in range(1, 4):
+        opt.zero_grad()
+        amp = [0.02, 5.0, 0.3][step - 1]                     # below, far above and near the clip threshold
+        grads = [torch.randn(p.shape, generator=gen) * amp / np.sqrt(p.numel()) for p in ref_p]
+        for p, g in zip(opt.params, grads):
+            p.grad.copy_(g)
+        lr = 2e-3 * step / 3
+        opt.step(lr)
+        norm = O.adamw_step(ref_p, grads, ref_m, ref_v, step, lr, wds, betas=(0.9, 0.98), eps=1e-6, max_grad_norm=0.5)
+        assert abs(opt.grad_norm() - norm) <= 1e-5 * norm
+        for name, p, r in zip(opt.names, opt.params, ref_p):
+            assert torch.allclose(p.detach().cpu(), r, rtol=2e-5, atol=1e-7), name
+    sd = opt.state_dict()
+    assert sd["state"][0]["step"] == 3 and len(sd["param_groups"]) == 2
+    for i in (0, nd, len(ref_p) - 1):
+        assert torch.allclose(sd["state"][i]["exp_avg"].cpu(), ref_m[i], rtol=2e-5, atol=1e-9)
+        assert torch.allclose(sd["state"][i]["exp_avg_sq"].cpu(), ref_v[i], rtol=2e-5, atol=1e-12)
