@@ -293,6 +293,23 @@ def mlp(x, P, pre):
     return F.linear(h, P[pre + "fc2.weight"], P[pre + "fc2.bias"])
 
 
+def _modulate(pt, P, name, y):
+    """adaptive half of PDNorm.forward (model.py:293-303): per-cloud [shift|scale] = Linear(SiLU(context))"""
+    if name + ".modulation.1.weight" not in P:
+        return y
+    ss = F.linear(F.silu(pt["context"]), P[name + ".modulation.1.weight"], P[name + ".modulation.1.bias"])
+    ss = torch.repeat_interleave(ss, offset2bincount(pt["offset"]), dim=0)
+    shift, scale = ss.chunk(2, dim=1)
+    return y * (1.0 + scale) + shift
+
+
+def _ln(pt, P, name, x):
+    """plain LayerNorm or PDNorm(LayerNorm) (decouple=False), chosen by the parameter names present"""
+    if name + ".norm.weight" in P:
+        return _modulate(pt, P, name, layer_norm(x, P[name + ".norm.weight"], P[name + ".norm.bias"]))
+    return layer_norm(x, P[name + ".weight"], P[name + ".bias"])
+
+
 def block(pt, P, pre, H, order_index, K=128, qk_norm=True):
     """Block.forward (model.py:659-680), pre-norm, drop_path 0.
 
@@ -302,11 +319,11 @@ def block(pt, P, pre, H, order_index, K=128, qk_norm=True):
     x = pt["feat"]
     c = subm_conv(pt.pop("conv_feat", x), pt["nbr3"], P[pre + "cpe.0.weight"], P[pre + "cpe.0.bias"])
     c = F.linear(c, P[pre + "cpe.1.weight"], P[pre + "cpe.1.bias"])
-    x = x + layer_norm(c, P[pre + "cpe.2.weight"], P[pre + "cpe.2.bias"])
-    h = layer_norm(x, P[pre + "norm1.0.weight"], P[pre + "norm1.0.bias"])
+    x = x + _ln(pt, P, pre + "cpe.2", c)
+    h = _ln(pt, P, pre + "norm1.0", x)
     x = x + patch_attention(h, P, pre + "attn.", H, pt["order"][order_index], pt["inverse"][order_index],
                             pt["plan"], K, qk_norm)
-    h = layer_norm(x, P[pre + "norm2.0.weight"], P[pre + "norm2.0.bias"])
+    h = _ln(pt, P, pre + "norm2.0", x)
     x = x + mlp(h, P, pre + "mlp.0.")
     pt["feat"] = x
     return pt
@@ -373,7 +390,8 @@ def ptv3ca_forward(P, cfg, feat, coord, offset, context, context_offset, perms, 
     pre = ""
     S = len(cfg["enc_channels"])
     qk_norm = cfg["qk_norm"]
-    assert not cfg.get("pdnorm_bn") and not cfg.get("pdnorm_ln"), "oracle covers the plain BN/LN (CA) model"
+    assert not (cfg.get("pdnorm_bn") or cfg.get("pdnorm_ln")) or not cfg.get("pdnorm_decouple", True), \
+        "decoupled PDNorm is unused by the policies"
     batch = offset2batch(offset)
     grid = grid_coords(coord, 0.01)
     ser = serialize(grid, batch, cfg["order"], perms[0] if perms is not None else None)
@@ -382,12 +400,15 @@ def ptv3ca_forward(P, cfg, feat, coord, offset, context, context_offset, perms, 
     K = cfg["enc_patch_size"][0]
     _stage_aux(pt, K)
 
-    def bn(x, name):
+    def bn(x, name, p=None):
+        mod = name
+        if name + ".norm.weight" in P:                      # PDNorm(BatchNorm1d) of the AdaNorm / Concat variants
+            name = name + ".norm"
         y, rm, rv = batch_norm(x, P[name + ".weight"], P[name + ".bias"], P[name + ".running_mean"],
                                P[name + ".running_var"], train)
         if bn_out is not None and train:
             bn_out[name + ".running_mean"], bn_out[name + ".running_var"] = rm, rv
-        return y
+        return _modulate(p if p is not None else pt, P, mod, y)
 
     def rec(name, p):
         if inter is not None:
@@ -407,26 +428,27 @@ def ptv3ca_forward(P, cfg, feat, coord, offset, context, context_offset, perms, 
             proj = F.linear(parent["feat"], P[pn + "proj.weight"], P[pn + "proj.bias"])
             f = segment_max(proj[st["indices"]], st["idx_ptr"])
             c = segment_mean(parent["coord"][st["indices"]], st["idx_ptr"])
-            f = F.gelu(bn(f, pn + "norm.0"))
             stack.append((parent, st["cluster"]))
             pt = dict(feat=f, coord=c, grid=st["grid"], batch=st["batch"], offset=st["offset"],
                       context=context, context_offset=context_offset, code=st["code"], order=st["order"],
                       inverse=st["inverse"], depth=st["depth"])
+            pt["feat"] = F.gelu(bn(f, pn + "norm.0", pt))
             _stage_aux(pt, cfg["enc_patch_size"][s])
             rec(f"enc{s}.down", pt)
         for i in range(cfg["enc_depths"][s]):
             pt = block(pt, P, f"enc.enc{s}.block{i}.", cfg["enc_num_head"][s], i % len(cfg["order"]),
                        cfg["enc_patch_size"][s], qk_norm)
             rec(f"enc{s}.block{i}", pt)
-            pt = ca_block(pt, P, f"enc.enc{s}.ca_block{i}.", cfg["enc_num_head"][s], qk_norm)
-            rec(f"enc{s}.ca_block{i}", pt)
+            if f"enc.enc{s}.ca_block{i}.norm1.0.weight" in P:
+                pt = ca_block(pt, P, f"enc.enc{s}.ca_block{i}.", cfg["enc_num_head"][s], qk_norm)
+                rec(f"enc{s}.ca_block{i}", pt)
     outs = [pt]
     for s in reversed(range(S - 1)):
         parent, cluster = stack.pop()
         un = f"dec.dec{s}.up."
-        a = F.gelu(bn(F.linear(pt["feat"], P[un + "proj.0.weight"], P[un + "proj.0.bias"]), un + "proj.1"))
+        a = F.gelu(bn(F.linear(pt["feat"], P[un + "proj.0.weight"], P[un + "proj.0.bias"]), un + "proj.1", pt))
         b = F.gelu(bn(F.linear(parent["feat"], P[un + "proj_skip.0.weight"], P[un + "proj_skip.0.bias"]),
-                      un + "proj_skip.1"))
+                      un + "proj_skip.1", parent))
         parent = dict(parent)
         parent["feat"] = b + a[cluster]
         parent["conv_feat"] = b            # sparse_conv_feat is NOT refreshed by the add (model.py:824)
@@ -436,8 +458,9 @@ def ptv3ca_forward(P, cfg, feat, coord, offset, context, context_offset, perms, 
             pt = block(pt, P, f"dec.dec{s}.block{i}.", cfg["dec_num_head"][s], i % len(cfg["order"]),
                        cfg["dec_patch_size"][s], qk_norm)
             rec(f"dec{s}.block{i}", pt)
-            pt = ca_block(pt, P, f"dec.dec{s}.ca_block{i}.", cfg["dec_num_head"][s], qk_norm)
-            rec(f"dec{s}.ca_block{i}", pt)
+            if f"dec.dec{s}.ca_block{i}.norm1.0.weight" in P:
+                pt = ca_block(pt, P, f"dec.dec{s}.ca_block{i}.", cfg["dec_num_head"][s], qk_norm)
+                rec(f"dec{s}.ca_block{i}", pt)
             outs.append(pt)
     return outs
 
@@ -496,19 +519,59 @@ def best_pos_from_logits(xt, coord, npoints, pos_bins=15, pos_bin_size=0.01):
     return torch.from_numpy(np.array(outs)).float()
 
 
+def robot_pose_embedding(sd, pre, poses):
+    """RobotPoseEmbedding.forward (models/base.py:61-78): Linear(pos) + Embedding(open) + Linear(sin/cos euler 'xyz'),
+    LayerNorm eps 1e-12; the euler angles come from scipy on the host exactly as in the reference."""
+    from scipy.spatial.transform import Rotation as R
+    e = torch.from_numpy(R.from_quat(poses[..., 3:7].detach().cpu().numpy()).as_euler("xyz")).float()
+    rot_in = torch.cat([torch.sin(e), torch.cos(e)], -1)
+    x = F.linear(poses[..., :3], sd[pre + "pos_embedding.weight"], sd[pre + "pos_embedding.bias"]) \
+        + F.linear(rot_in, sd[pre + "rot_embedding.weight"], sd[pre + "rot_embedding.bias"]) \
+        + sd[pre + "open_embedding.weight"][poses[..., -1].long()]
+    return F.layer_norm(x, (x.shape[-1],), sd[pre + "layer_norm.weight"], sd[pre + "layer_norm.bias"], 1e-12)
+
+
+def policy_context(sd, cfg, batch, variant):
+    """prepare_ptv3_batch context: CA (simple_policy_ptv3.py:403-431; motion_planner_ptv3.py:437-463) -> packed tokens +
+    offsets; AdaNorm / Concat (:194-223, :438-463; planner :201-228) -> one vector per cloud."""
+    ac = cfg["action_config"]
+    lens = [int(v) for v in batch["txt_lens"]]
+    ctx = F.linear(batch["txt_embeds"], sd["txt_fc.weight"], sd["txt_fc.bias"])
+    pose = robot_pose_embedding(sd, "pose_embedding.", batch["ee_poses"]) if ac.get("use_ee_pose") else None
+    step = sd["stepid_embedding.weight"][batch["step_ids"]] if (ac.get("use_step_id") and "stepid_embedding.weight" in sd) else None
+    if variant == "ca":
+        toks = list(torch.split(ctx, lens))
+        n = torch.tensor(lens, dtype=torch.long)
+        for extra in (pose, step):
+            if extra is not None:
+                toks = [torch.cat([c, e.unsqueeze(0)], 0) for c, e in zip(toks, extra)]
+                n = n + 1
+        return torch.cat(toks, 0), torch.cumsum(n, 0)
+    if ac.get("txt_reduce") == "attn" and variant != "concat":
+        w = torch.split(F.linear(batch["txt_embeds"], sd["txt_attn_fc.weight"], sd["txt_attn_fc.bias"]), lens)
+        ctx = torch.stack([(torch.softmax(wi, 0) * ci).sum(0) for wi, ci in zip(w, torch.split(ctx, lens))], 0)
+    if pose is not None:
+        ctx = ctx + pose
+    if step is not None:
+        ctx = ctx + step
+    return ctx, None
+
+
 def policy_forward(sd, cfg, batch, perms=None, train=True, compute_loss=True, compute_final_action=False,
-                   bn_out=None, inter=None):
-    """SimplePolicyPTV3CA.forward (simple_policy_ptv3.py:225-306, 403-431).
+                   bn_out=None, inter=None, variant="ca"):
+    """SimplePolicyPTV3{CA,AdaNorm,Concat}.forward (simple_policy_ptv3.py:225-306, 194-223, 403-463).
     sd: state dict (reference names); cfg: MODEL config mapping; perms: (5,4) recorded shuffles or None."""
     pc, ac = cfg["ptv3_config"], cfg["action_config"]
-    assert not ac["use_ee_pose"] and not ac["use_step_id"], "oracle covers the production CA context (text only)"
     fts = batch["pc_fts"]
     npoints = list(batch["npoints_in_batch"])
-    ctx = F.linear(batch["txt_embeds"], sd["txt_fc.weight"], sd["txt_fc.bias"])
-    ctx_off = torch.cumsum(torch.tensor(batch["txt_lens"], dtype=torch.long), 0)
+    ctx, ctx_off = policy_context(sd, cfg, batch, variant)
+    feat = fts
+    if variant == "concat":
+        feat = torch.cat([fts, torch.repeat_interleave(ctx, torch.tensor(npoints), 0)], -1)
+        ctx = None
     P = {k[len("ptv3_model."):]: v for k, v in sd.items() if k.startswith("ptv3_model.")}
     bn_local = {} if bn_out is not None else None
-    outs = ptv3ca_forward(P, pc, fts, fts[:, :3], batch["offset"], ctx, ctx_off, perms, train, bn_local, inter)
+    outs = ptv3ca_forward(P, pc, feat, fts[:, :3], batch["offset"], ctx, ctx_off, perms, train, bn_local, inter)
     if bn_out is not None:
         bn_out.update({"ptv3_model." + k: v for k, v in bn_local.items()})
     last = outs[-1]
@@ -524,6 +587,78 @@ def policy_forward(sd, cfg, batch, perms=None, train=True, compute_loss=True, co
         lc = cfg["loss_config"]
         res["losses"] = policy_loss(xt, xr, xo, batch["gt_actions"], batch["disc_pos_probs"], npoints,
                                     lc["pos_weight"], lc["rot_weight"])
+    return res
+
+
+# --------------------------------------------------------------------------------------------------
+# §8a row 19: motion planner (models/motion_planner_ptv3.py)
+# --------------------------------------------------------------------------------------------------
+
+
+def traj_action_head(x, P, npoints, T, pos_bins=15, euler_bins=72):
+    """trajectory ActionHead.forward, heatmap_disc + max + euler_disc (motion_planner_ptv3.py:77-148), dropout 0"""
+    pre = "act_proj_head."
+    pe = x.unsqueeze(1).expand(-1, T, -1)
+    te = P[pre + "traj_embedding.weight"][:T]
+    pe = torch.cat([pe, te.expand(pe.size(0), -1, -1)], -1)                         # (N, T, C + E)
+    h = F.leaky_relu(F.linear(pe, P[pre + "heatmap_mlp.0.weight"], P[pre + "heatmap_mlp.0.bias"]), 0.02)
+    xt = F.linear(h, P[pre + "heatmap_mlp.3.weight"], P[pre + "heatmap_mlp.3.bias"])   # (N, T, 3*2*pos_bins)
+    xt = xt.view(x.shape[0], T, 3, 2 * pos_bins).permute(1, 2, 0, 3)                  # 'n t (c b) -> t c n b'
+    pc = torch.stack([t.max(0)[0] for t in torch.split(pe, npoints)], 0)              # (B, T, C + E)
+    h = F.leaky_relu(F.linear(pc, P[pre + "action_mlp.0.weight"], P[pre + "action_mlp.0.bias"]), 0.02)
+    a = F.linear(h, P[pre + "action_mlp.3.weight"], P[pre + "action_mlp.3.bias"])     # (B, T, 72*3 + 2)
+    xr = a[..., : euler_bins * 3].reshape(a.shape[0], T, euler_bins, 3)
+    return xt, xr, a[..., -2], a[..., -1]
+
+
+def traj_loss(xt, xr, xo, xstop, gt_trajs, gt_stop, masks, disc_pos_probs, npoints, pos_weight=1.0, rot_weight=1.0):
+    """MotionPlannerPTV3*.compute_loss (motion_planner_ptv3.py:307-397), heatmap_disc + euler_disc"""
+    B, T = gt_trajs.shape[:2]
+    m = masks.float()
+    pos = 0
+    for i, t in enumerate(torch.split(xt, npoints, dim=2)):
+        mk = m[i].unsqueeze(1).expand(-1, 3).reshape(-1)
+        ce = F.cross_entropy(t.reshape(T * 3, -1), disc_pos_probs[i].reshape(T * 3, -1), reduction="none")
+        pos = pos + torch.sum(ce * mk) / mk.sum()
+    pos = pos / len(npoints)
+    tgt = gt_trajs[..., 3:-1].long()
+    ce = F.cross_entropy(xr.permute(0, 1, 3, 2).reshape(B * T * 3, -1), tgt.reshape(-1), reduction="none").reshape(B, T, 3)
+    rot = torch.sum(ce * m.unsqueeze(-1)) / m.sum() / 3
+    opn = (F.binary_cross_entropy_with_logits(xo, gt_trajs[..., -1], reduction="none") * m).sum() / m.sum()
+    stop = (F.binary_cross_entropy_with_logits(xstop, gt_stop.float(), reduction="none") * m).sum() / m.sum()
+    return {"pos": pos, "rot": rot, "open": opn, "stop": stop,
+            "total": pos_weight * pos + rot_weight * rot + opn + stop}
+
+
+def planner_forward(sd, cfg, batch, perms=None, train=True, compute_loss=True, compute_final_action=False,
+                    bn_out=None, inter=None, variant="ca"):
+    """MotionPlannerPTV3{CA,AdaNorm}.forward (motion_planner_ptv3.py:201-305, 437-463)"""
+    pc, ac = cfg["ptv3_config"], cfg["action_config"]
+    T = ac["max_traj_len"]
+    fts = batch["pc_fts"]
+    npoints = list(batch["npoints_in_batch"])
+    feat = torch.cat([fts, sd["pc_label_embedding.weight"][batch["pc_labels"]]], -1)
+    ctx, ctx_off = policy_context(sd, cfg, batch, variant)
+    P = {k[len("ptv3_model."):]: v for k, v in sd.items() if k.startswith("ptv3_model.")}
+    bn_local = {} if bn_out is not None else None
+    outs = ptv3ca_forward(P, pc, feat, fts[:, :3], batch["offset"], ctx, ctx_off, perms, train, bn_local, inter)
+    if bn_out is not None:
+        bn_out.update({"ptv3_model." + k: v for k, v in bn_local.items()})
+    last = outs[-1]
+    xt, xr, xo, xs = traj_action_head(last["feat"], sd, npoints, T, ac["pos_bins"], 72)
+    B = len(npoints)
+    if compute_final_action:
+        pos = torch.stack([best_pos_from_logits(xt[t].detach(), last["coord"], npoints, ac["pos_bins"], ac["pos_bin_size"])
+                           for t in range(T)], 1)
+    else:
+        pos = batch["gt_trajs"][..., :3]
+    rot = torch.from_numpy(euler_bins_to_quat(torch.argmax(xr.reshape(B * T, 72, 3), 1).numpy(), 5)).reshape(B, T, 4)
+    final = torch.cat([pos, rot, xo.detach().unsqueeze(-1), xs.detach().unsqueeze(-1)], -1)
+    res = {"final": final, "xt": xt, "xr": xr, "xo": xo, "xstop": xs, "dec_feat": last["feat"]}
+    if compute_loss:
+        lc = cfg["loss_config"]
+        res["losses"] = traj_loss(xt, xr, xo, xs, batch["gt_trajs"], batch["gt_trajs_stop"], batch["traj_masks"],
+                                  batch["gt_trajs_disc_pos_probs"], npoints, lc["pos_weight"], lc["rot_weight"])
     return res
 
 

@@ -107,3 +107,36 @@ def small_model_config(**ptv3_overrides):
     return production_model_config(
         **{**dict(enc_channels=[32, 32, 48, 64, 96], enc_num_head=[2, 1, 2, 4, 4],
                   dec_channels=[32, 32, 48, 64], dec_num_head=[2, 1, 2, 4]), **ptv3_overrides})
+
+
+def small_variant_config(kind):
+    """Reduced-width configurations of the non-production variants (golden fixtures / parity tests):
+    'adanorm'  SimplePolicyPTV3AdaNorm — PDNorm(BN)+PDNorm(LN) adaptive, txt_reduce 'attn', pose + step-id added, depth-2 stages (the reference indexes decoder outputs assuming dec_depths all 1 or all 2: simple_policy_ptv3.py:243)
+    'concat'   SimplePolicyPTV3Concat  — per-cloud context concatenated to every point feature (plain norms)
+    'ca_tokens' SimplePolicyPTV3CA     — production topology with the pose and step-id context tokens enabled
+    'planner_ca' / 'planner_adanorm'   — MotionPlannerPTV3{CA,AdaNorm} (motion_planner_ptv3.yaml + train_3dlotusplus_motion_planner.sh)"""
+    cfg = small_model_config(attn_drop=0.0, proj_drop=0.0)
+    cfg.action_config.dropout = 0.0
+    p, a = cfg.ptv3_config, cfg.action_config
+    if kind in ("adanorm", "planner_adanorm"):
+        p.update(pdnorm_bn=True, pdnorm_ln=True, pdnorm_decouple=False, pdnorm_adaptive=True, pdnorm_affine=True,
+                 qk_norm=False, enc_depths=[2, 1, 1, 2, 1], dec_depths=[2, 2, 2, 2])
+        a.update(txt_reduce="attn", context_channels=64)
+        p.update(pdnorm_context_channels=64)
+    if kind == "adanorm":
+        cfg.model_class = "SimplePolicyPTV3AdaNorm"
+        a.update(use_ee_pose=True, use_step_id=True)
+    elif kind == "concat":
+        cfg.model_class = "SimplePolicyPTV3Concat"
+        a.update(context_channels=9, use_ee_pose=True, use_step_id=True, txt_reduce="mean")
+        p.update(in_channels=7 + 9)
+    elif kind == "ca_tokens":
+        a.update(use_ee_pose=True, use_step_id=True)
+    elif kind in ("planner_ca", "planner_adanorm"):
+        cfg.model_class = "MotionPlannerPTV3CA" if kind == "planner_ca" else "MotionPlannerPTV3AdaNorm"
+        p.update(in_channels=4)
+        a.update(max_traj_len=5, pc_label_channels=12, traj_embed_size=16, txt_reduce="attn",
+                 use_ee_pose=(kind == "planner_adanorm"))
+    else:
+        raise KeyError(kind)
+    return cfg

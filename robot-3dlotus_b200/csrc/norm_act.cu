@@ -410,7 +410,7 @@ __global__ void __launch_bounds__(256) k_pointwise_vec(const bf16_t* __restrict_
   for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < nvec; i += (int64_t)gridDim.x * blockDim.x) {
     float v[8], av[8], o[8], m[8];
     load8(x + i * 8, v);
-    if (op == 1 || op == 3 || op == 4) load8(a + i * 8, av);
+    if (op == 1 || op == 3 || op == 4 || op == 8) load8(a + i * 8, av);
 #pragma unroll
     for (int e = 0; e < 8; ++e) m[e] = 1.f;
     if (drop_p > 0.f && op < 4) {
@@ -430,6 +430,8 @@ __global__ void __launch_bounds__(256) k_pointwise_vec(const bf16_t* __restrict_
         case 3: o[e] = av[e] * m[e] * (v[e] > 0.f ? 1.f : alpha); break;
         case 4: o[e] = av[e] + v[e]; break;
         case 5: o[e] = v[e] * alpha; break;
+        case 7: o[e] = v[e] / (1.f + __expf(-v[e])); break;
+        case 8: { float sg = 1.f / (1.f + __expf(-v[e])); o[e] = av[e] * sg * (1.f + v[e] * (1.f - sg)); break; }
         default: o[e] = v[e]; break;
       }
     }
@@ -669,6 +671,7 @@ LOTUS_API int lotus_batchnorm_bwd_bf16(const void* dy, const void* x, int x_fp32
 // op 0: y = drop(gelu(x))            1: y = drop(a) * gelu'(x)     (x = pre-activation, a = dy)
 // op 2: y = drop(leaky(x, alpha))    3: y = drop(a) * leaky'(x)
 // op 4: y = a + x                    5: y = x * alpha              6: y = x (type conversion)
+// op 7: y = silu(x)                  8: y = a * silu'(x)
 // drop(.) is the identity when drop_p == 0; mask index = flat element index (same in fwd and bwd)
 template <typename TX, typename TY>
 __global__ void k_pointwise(const TX* __restrict__ x, const TX* __restrict__ a, TY* __restrict__ y, int64_t n,
@@ -686,6 +689,8 @@ __global__ void k_pointwise(const TX* __restrict__ x, const TX* __restrict__ a, 
       case 3: o = ldf(a, i) * m * (v > 0.f ? 1.f : alpha); break;
       case 4: o = ldf(a, i) + v; break;
       case 5: o = v * alpha; break;
+      case 7: o = v / (1.f + expf(-v)); break;
+      case 8: { float sg = 1.f / (1.f + expf(-v)); o = ldf(a, i) * sg * (1.f + v * (1.f - sg)); break; }
       default: o = v; break;
     }
     stf(y, i, o);
@@ -800,6 +805,71 @@ LOTUS_API int lotus_dropout_bf16(const void* x, void* y, int64_t n, float p, uin
   }
   k_dropout<bf16_t><<<min(ceil_div(n, 256), kNumSM * 16), 256, 0, (cudaStream_t)stream_>>>((const bf16_t*)x, (bf16_t*)y, n, p, seed,
                                                                                           stream_id);
+  LOTUS_CUDA_OK();
+  return 0;
+}
+
+
+// ---------------------------------------------------------------- PDNorm modulation (model.py:293-303)
+// y[i, c] = x[i, c] * (1 + ss[b(i), C + c]) + ss[b(i), c]  with ss = Linear(SiLU(context)) per cloud: [B, 2C] = [shift | scale];
+// b(i) from the cloud offsets (points of a cloud are contiguous at every stage).
+__device__ __forceinline__ int cloud_of_row(const int32_t* __restrict__ off, int B, int64_t r) {
+  int lo = 0, hi = B - 1;
+  while (lo < hi) {
+    int mid = (lo + hi) >> 1;
+    if (off[mid + 1] > r) hi = mid; else lo = mid + 1;
+  }
+  return lo;
+}
+__global__ void k_modulate_fwd(const float* __restrict__ x, const float* __restrict__ ss, const int32_t* __restrict__ off, int B,
+                               int64_t rows, int C, float* __restrict__ y) {
+  int64_t total = rows * C;
+  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+    int64_t r = i / C;
+    int c = (int)(i - r * C);
+    const float* s = ss + (int64_t)cloud_of_row(off, B, r) * 2 * C;
+    y[i] = x[i] * (1.f + s[C + c]) + s[c];
+  }
+}
+// dx = dy * (1 + scale);  dss[b, c] = sum_i dy;  dss[b, C + c] = sum_i dy * x     (one block column per cloud)
+__global__ void k_modulate_bwd(const float* __restrict__ dy, const float* __restrict__ x, const float* __restrict__ ss,
+                               const int32_t* __restrict__ off, int C, float* __restrict__ dx, float* __restrict__ dss) {
+  __shared__ float s_a[8][33], s_b[8][33];
+  int b = blockIdx.x;
+  int c = blockIdx.y * 32 + threadIdx.x;
+  int r0 = off[b], r1 = off[b + 1];
+  float a0 = 0.f, a1 = 0.f;
+  if (c < C) {
+    float sc = 1.f + ss[(int64_t)b * 2 * C + C + c];
+    for (int r = r0 + threadIdx.y; r < r1; r += 8) {
+      float g = dy[(int64_t)r * C + c];
+      a0 += g;
+      a1 = fmaf(g, x[(int64_t)r * C + c], a1);
+      dx[(int64_t)r * C + c] = g * sc;
+    }
+  }
+  s_a[threadIdx.y][threadIdx.x] = a0;
+  s_b[threadIdx.y][threadIdx.x] = a1;
+  __syncthreads();
+  if (threadIdx.y == 0 && c < C) {
+#pragma unroll
+    for (int k = 1; k < 8; ++k) { a0 += s_a[k][threadIdx.x]; a1 += s_b[k][threadIdx.x]; }
+    dss[(int64_t)b * 2 * C + c] = a0;
+    dss[(int64_t)b * 2 * C + C + c] = a1;
+  }
+}
+LOTUS_API int lotus_pdnorm_modulate_fwd_f32(const float* x, const float* shift_scale, const int32_t* cloud_off, int B, int64_t rows,
+                                            int C, float* y, void* stream_) {
+  if (rows <= 0) return 0;
+  k_modulate_fwd<<<min(ceil_div(rows * C, 256), kNumSM * 16), 256, 0, (cudaStream_t)stream_>>>(x, shift_scale, cloud_off, B, rows, C, y);
+  LOTUS_CUDA_OK();
+  return 0;
+}
+LOTUS_API int lotus_pdnorm_modulate_bwd_f32(const float* dy, const float* x, const float* shift_scale, const int32_t* cloud_off,
+                                            int B, int C, float* dx, float* d_shift_scale, void* stream_) {
+  if (B <= 0) return 0;
+  k_modulate_bwd<<<dim3(B, ceil_div(C, 32)), dim3(32, 8), 0, (cudaStream_t)stream_>>>(dy, x, shift_scale, cloud_off, C, dx,
+                                                                                       d_shift_scale);
   LOTUS_CUDA_OK();
   return 0;
 }

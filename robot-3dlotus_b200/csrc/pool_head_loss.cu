@@ -138,15 +138,24 @@ LOTUS_API int lotus_unpool_add_bf16(const void* skip, const void* child, const i
 // prob[90*off[b] + c*(n_b*NB) + n*NB + k]; loss_pos = mean_b mean_c ( lse*sum(p) - sum(p*x) ).
 // Writes dlogits = s_pos * (softmax*sum(p) - p) / (3*B) when dlogits != null, with
 // s_pos = gout[0] + gout[3]*pos_w (gout = upstream gradient of {pos, rot, open, total}; null -> {0,0,0,1}).
+// Trajectory form (motion planner, motion_planner_ptv3.py:326-337): T steps -> 3*T axes per cloud (axis a = t*3 + c,
+// logits row width 3*T*NB), row weight mask[b,t] / (3 * sum_t mask[b,t] * B); `total_idx` = index of the total in gout.
 __global__ void k_pos_ce(const float* __restrict__ logits, const float* __restrict__ prob,
                          const int32_t* __restrict__ off, int B, int NB, float* __restrict__ loss_accum,
-                         float* __restrict__ dlogits, const float* __restrict__ gout, float pos_w) {
-  float gscale = gout ? gout[0] + gout[3] * pos_w : pos_w;
+                         float* __restrict__ dlogits, const float* __restrict__ gout, float pos_w, int T,
+                         const float* __restrict__ mask, int total_idx) {
+  float gscale = gout ? gout[0] + gout[total_idx] * pos_w : pos_w;
   __shared__ float red[32];
   int b = blockIdx.x, c = blockIdx.y;
   int s = off[b], n = off[b + 1] - s;
-  int ld = 3 * NB;
+  int ld = 3 * T * NB;
   int tot = n * NB;
+  float wrow = 1.f / (3.f * B);
+  if (mask) {
+    float len = 0.f;
+    for (int t = 0; t < T; ++t) len += mask[b * T + t];
+    wrow = mask[b * T + c / 3] / (3.f * len) / B;
+  }
   const float* pb = prob + (int64_t)ld * s + (int64_t)c * tot;
   float mx = -INFINITY;
   for (int t = threadIdx.x; t < tot; t += blockDim.x) mx = fmaxf(mx, logits[(int64_t)(s + t / NB) * ld + c * NB + t % NB]);
@@ -159,9 +168,9 @@ __global__ void k_pos_ce(const float* __restrict__ logits, const float* __restri
   }
   se = block_sum(se, red); sp = block_sum(sp, red); spx = block_sum(spx, red);
   float lse = mx + logf(se);
-  if (threadIdx.x == 0) atomicAdd(loss_accum, (lse * sp - spx) / (3.f * B));
+  if (threadIdx.x == 0) atomicAdd(loss_accum, mask ? (lse * sp - spx) * wrow : (lse * sp - spx) / (3.f * B));
   if (dlogits) {
-    float k = gscale / (3.f * B);
+    float k = mask ? gscale * wrow : gscale / (3.f * B);
     for (int t = threadIdx.x; t < tot; t += blockDim.x) {
       int64_t o = (int64_t)(s + t / NB) * ld + c * NB + t % NB;
       dlogits[o] = k * (expf(logits[o] - lse) * sp - pb[t]);
@@ -216,9 +225,84 @@ LOTUS_API int lotus_policy_loss_f32(const float* heatmap_logits, const float* po
   cudaStream_t st = (cudaStream_t)stream_;
   LOTUS_CHECK_ARG(act_ld == rot_bins * 3 + 1, "lotus_policy_loss_f32: action width %d != %d*3+1", act_ld, rot_bins);
   LOTUS_CUDA_CALL(cudaMemsetAsync(losses, 0, 16, st));
-  k_pos_ce<<<dim3(B, 3), 256, 0, st>>>(heatmap_logits, pos_prob, cloud_off, B, NB, losses, d_heatmap, gout, pos_w);
+  k_pos_ce<<<dim3(B, 3), 256, 0, st>>>(heatmap_logits, pos_prob, cloud_off, B, NB, losses, d_heatmap, gout, pos_w, 1, nullptr, 3);
   k_rot_open_loss<<<1, 256, 0, st>>>(action_logits, act_ld, gt_actions, gt_ld, B, rot_bins, losses, d_action, rot_w, gout);
   k_total_loss<<<1, 1, 0, st>>>(losses, pos_w, rot_w);
+  LOTUS_CUDA_OK();
+  return 0;
+}
+
+// ---------------------------------------------------------------- trajectory (motion planner) losses
+// act: [B*T, ld = nbins*3 + 2] = rot logits (bin*3 + axis), open logit, stop logit; gt: [B*T, 7]; stop_t, mask: [B*T].
+// rot = sum(mask*CE)/sum(mask)/3, open/stop = sum(mask*BCE)/sum(mask)   (motion_planner_ptv3.py:363-389)
+// losses[5] = {pos, rot, open, stop, total}
+__global__ void k_traj_head_loss(const float* __restrict__ act, int ld, const float* __restrict__ gt, int gt_ld,
+                                 const float* __restrict__ stop_t, const float* __restrict__ mask, int BT, int nbins,
+                                 float* __restrict__ losses, float* __restrict__ dact, float pos_w, float rot_w,
+                                 const float* __restrict__ gout) {
+  __shared__ float red[32];
+  float s_rot = gout ? gout[1] + gout[4] * rot_w : rot_w;
+  float s_open = gout ? gout[2] + gout[4] : 1.f;
+  float s_stop = gout ? gout[3] + gout[4] : 1.f;
+  float msum = 0.f;
+  for (int i = threadIdx.x; i < BT; i += blockDim.x) msum += mask[i];
+  msum = block_sum(msum, red);
+  __shared__ float s_msum;
+  if (threadIdx.x == 0) s_msum = msum;
+  __syncthreads();
+  msum = s_msum;
+  float lrot = 0.f, lopen = 0.f, lstop = 0.f;
+  for (int t = threadIdx.x; t < BT * 3; t += blockDim.x) {
+    int r = t / 3, a = t % 3;
+    const float* row = act + (int64_t)r * ld;
+    float mx = -INFINITY;
+    for (int k = 0; k < nbins; ++k) mx = fmaxf(mx, row[k * 3 + a]);
+    float se = 0.f;
+    for (int k = 0; k < nbins; ++k) se += expf(row[k * 3 + a] - mx);
+    float lse = mx + logf(se);
+    int tgt = (int)gt[(int64_t)r * gt_ld + 3 + a];
+    float m = mask[r];
+    lrot += m * (lse - row[tgt * 3 + a]);
+    if (dact) {
+      float kf = s_rot * m / msum / 3.f;
+      for (int k = 0; k < nbins; ++k)
+        dact[(int64_t)r * ld + k * 3 + a] = kf * (expf(row[k * 3 + a] - lse) - (k == tgt ? 1.f : 0.f));
+    }
+  }
+  for (int r = threadIdx.x; r < BT; r += blockDim.x) {
+    float m = mask[r];
+    float x = act[(int64_t)r * ld + nbins * 3], y = gt[(int64_t)r * gt_ld + gt_ld - 1];
+    lopen += m * (fmaxf(x, 0.f) - x * y + log1pf(expf(-fabsf(x))));
+    float xs = act[(int64_t)r * ld + nbins * 3 + 1], ys = stop_t[r];
+    lstop += m * (fmaxf(xs, 0.f) - xs * ys + log1pf(expf(-fabsf(xs))));
+    if (dact) {
+      dact[(int64_t)r * ld + nbins * 3] = s_open * m * (1.f / (1.f + expf(-x)) - y) / msum;
+      dact[(int64_t)r * ld + nbins * 3 + 1] = s_stop * m * (1.f / (1.f + expf(-xs)) - ys) / msum;
+    }
+  }
+  lrot = block_sum(lrot, red);
+  lopen = block_sum(lopen, red);
+  lstop = block_sum(lstop, red);
+  if (threadIdx.x == 0) {
+    losses[1] = lrot / msum / 3.f; losses[2] = lopen / msum; losses[3] = lstop / msum;
+    losses[4] = pos_w * losses[0] + rot_w * losses[1] + losses[2] + losses[3];
+  }
+}
+// heatmap_logits [N, T*3*NB] (column (t*3+c)*NB + k), pos_prob packed per cloud as (T, 3, n_b*NB);
+// action_logits [B*T, rot_bins*3+2]; gt_trajs [B*T, 7]; stop_targets / traj_mask [B*T] floats (0/1).
+// losses[5] = {pos, rot, open, stop, total}; gradients as in lotus_policy_loss_f32 (gout: 5 floats or null).
+LOTUS_API int lotus_traj_loss_f32(const float* heatmap_logits, const float* pos_prob, const int32_t* cloud_off, int B, int T,
+                                  int NB, const float* action_logits, int act_ld, int rot_bins, const float* gt_trajs,
+                                  int gt_ld, const float* stop_targets, const float* traj_mask, float pos_w, float rot_w,
+                                  float* losses, float* d_heatmap, float* d_action, const float* gout, void* stream_) {
+  cudaStream_t st = (cudaStream_t)stream_;
+  LOTUS_CHECK_ARG(act_ld == rot_bins * 3 + 2, "lotus_traj_loss_f32: action width %d != %d*3+2", act_ld, rot_bins);
+  LOTUS_CHECK_ARG(B > 0 && T > 0, "lotus_traj_loss_f32: empty batch (B=%d, T=%d)", B, T);
+  LOTUS_CUDA_CALL(cudaMemsetAsync(losses, 0, 20, st));
+  k_pos_ce<<<dim3(B, 3 * T), 256, 0, st>>>(heatmap_logits, pos_prob, cloud_off, B, NB, losses, d_heatmap, gout, pos_w, T,
+                                           traj_mask, 4);
+  k_traj_head_loss<<<1, 256, 0, st>>>(action_logits, act_ld, gt_trajs, gt_ld, stop_targets, traj_mask, B * T, rot_bins, losses,
+                                      d_action, pos_w, rot_w, gout);
   LOTUS_CUDA_OK();
   return 0;
 }
@@ -231,15 +315,19 @@ LOTUS_API int lotus_policy_loss_f32(const float* heatmap_logits, const float* po
 __global__ void k_decode(const float* __restrict__ logits, const float* __restrict__ xyz, int xyz_ld,
                          const int32_t* __restrict__ off, int NB, double bin_size, const float* __restrict__ act, int act_ld,
                          int rot_bins, float resolution, const float* __restrict__ gt_pos, int gt_ld,
-                         double* __restrict__ out) {
+                         double* __restrict__ out_, int T, int out_ld) {
   __shared__ float rv[32];
   __shared__ int ri[32];
-  int b = blockIdx.x;
-  int s = off[b], n = off[b + 1] - s, ld = 3 * NB, tot = n * NB;
+  int b = blockIdx.x, tstep = blockIdx.y;
+  int s = off[b], n = off[b + 1] - s, ld = 3 * T * NB, tot = n * NB;
+  logits += tstep * 3 * NB;                       // this step's 3*NB columns
+  act += (int64_t)(b * T + tstep) * act_ld;       // row (b, t) of the action logits
+  if (gt_pos) gt_pos += (int64_t)(b * T + tstep) * gt_ld;
+  double* out = out_ + (int64_t)(b * T + tstep) * out_ld;
   int lane = threadIdx.x & 31, w = threadIdx.x >> 5, nw = blockDim.x >> 5;
   for (int c = 0; c < 3; ++c) {
     if (gt_pos) {  // compute_final_action=False: pred_pos := gt (simple_policy_ptv3.py:276-277)
-      if (threadIdx.x == 0) out[b * 8 + c] = (double)gt_pos[(int64_t)b * gt_ld + c];
+      if (threadIdx.x == 0) out[c] = (double)gt_pos[c];
       continue;
     }
     float best = -INFINITY; int bi = 0x7fffffff;
@@ -268,13 +356,13 @@ __global__ void k_decode(const float* __restrict__ logits, const float* __restri
       if (lane == 0) {
         int pn = bi / NB, k = bi % NB;
         double cand = (double)xyz[(int64_t)(s + pn) * xyz_ld + c] + (double)(k - NB / 2) * bin_size;
-        out[b * 8 + c] = (double)(float)cand;  // torch.from_numpy(np.array(...)).float()
+        out[c] = (double)(float)cand;  // torch.from_numpy(np.array(...)).float()
       }
     }
     __syncthreads();
   }
   if (threadIdx.x == 0) {
-    const float* row = act + (int64_t)b * act_ld;
+    const float* row = act;
     double e[3];
     for (int a = 0; a < 3; ++a) {
       float best = -INFINITY; int bk = 0;
@@ -283,11 +371,12 @@ __global__ void k_decode(const float* __restrict__ logits, const float* __restri
       e[a] = ((double)bk * (double)resolution - 180.0) * 0.017453292519943295;
     }
     double cx = cos(e[0] / 2), sx = sin(e[0] / 2), cy = cos(e[1] / 2), sy = sin(e[1] / 2), cz = cos(e[2] / 2), sz = sin(e[2] / 2);
-    out[b * 8 + 3] = sx * cy * cz - cx * sy * sz;
-    out[b * 8 + 4] = cx * sy * cz + sx * cy * sz;
-    out[b * 8 + 5] = cx * cy * sz - sx * sy * cz;
-    out[b * 8 + 6] = cx * cy * cz + sx * sy * sz;
-    out[b * 8 + 7] = (double)row[rot_bins * 3];
+    out[3] = sx * cy * cz - cx * sy * sz;
+    out[4] = cx * sy * cz + sx * cy * sz;
+    out[5] = cx * cy * sz - sx * sy * cz;
+    out[6] = cx * cy * cz + sx * sy * sz;
+    out[7] = (double)row[rot_bins * 3];
+    if (out_ld > 8) out[8] = (double)row[rot_bins * 3 + 1];   // planner: stop logit
   }
 }
 LOTUS_API int lotus_decode_actions(const float* heatmap_logits, const float* xyz, int xyz_ld, const int32_t* cloud_off,
@@ -296,7 +385,17 @@ LOTUS_API int lotus_decode_actions(const float* heatmap_logits, const float* xyz
                                    void* stream_) {
   if (B <= 0) return 0;
   k_decode<<<B, 256, 0, (cudaStream_t)stream_>>>(heatmap_logits, xyz, xyz_ld, cloud_off, NB, bin_size, action_logits, act_ld,
-                                                 rot_bins, euler_resolution, gt_pos_or_null, gt_ld, out);
+                                                 rot_bins, euler_resolution, gt_pos_or_null, gt_ld, out, 1, 8);
+  LOTUS_CUDA_OK();
+  return 0;
+}
+// Trajectory decode (motion_planner_ptv3.py:250-296): out [B, T, 9] float64 = pos(3), quat(4), open logit, stop logit.
+LOTUS_API int lotus_decode_trajs(const float* heatmap_logits, const float* xyz, int xyz_ld, const int32_t* cloud_off, int B,
+                                 int T, int NB, double bin_size, const float* action_logits, int act_ld, int rot_bins,
+                                 float euler_resolution, const float* gt_pos_or_null, int gt_ld, double* out, void* stream_) {
+  if (B <= 0 || T <= 0) return 0;
+  k_decode<<<dim3(B, T), 256, 0, (cudaStream_t)stream_>>>(heatmap_logits, xyz, xyz_ld, cloud_off, NB, bin_size, action_logits,
+                                                          act_ld, rot_bins, euler_resolution, gt_pos_or_null, gt_ld, out, T, 9);
   LOTUS_CUDA_OK();
   return 0;
 }

@@ -89,6 +89,7 @@ class SimplePolicyPTV3AdaNorm(BaseModel):
 
     backbone_cls = PointTransformerV3
     variant = "adanorm"
+    planner = False
 
     def __init__(self, config):
         super().__init__()
@@ -138,10 +139,88 @@ class SimplePolicyPTV3Concat(SimplePolicyPTV3AdaNorm):
     variant = "concat"
 
 
+class TrajActionHead(nn.Module):
+    """models/motion_planner_ptv3.py:20-76 (parameter holder; heads read [point feature | trajectory-step embedding])."""
+
+    def __init__(self, reduce, pos_pred_type, rot_pred_type, hidden_size, dim_actions, max_traj_len, dropout=0,
+                 voxel_size=0.01, euler_resolution=5, ptv3_config=None, pos_bins=50, traj_embed_size=64):
+        super().__init__()
+        assert reduce in ["max", "mean", "attn"]
+        assert pos_pred_type in ["heatmap_mlp", "heatmap_disc"]
+        assert rot_pred_type in ["quat", "rot6d", "euler", "euler_disc"]
+        self.reduce, self.pos_pred_type, self.rot_pred_type = reduce, pos_pred_type, rot_pred_type
+        self.hidden_size, self.dim_actions, self.voxel_size = hidden_size, dim_actions, voxel_size
+        self.euler_resolution, self.euler_bins, self.pos_bins = euler_resolution, 360 // euler_resolution, pos_bins
+        self.max_traj_len, self.dropout = max_traj_len, dropout
+        if traj_embed_size > 0:
+            self.traj_embedding = nn.Embedding(max_traj_len, traj_embed_size)
+        else:
+            assert max_traj_len == 1
+            self.traj_embedding = None
+        out_hm = 3 * pos_bins * 2 if pos_pred_type == "heatmap_disc" else 1 + 3
+        self.heatmap_mlp = nn.Sequential(nn.Linear(hidden_size + traj_embed_size, hidden_size), nn.LeakyReLU(0.02),
+                                         nn.Dropout(dropout), nn.Linear(hidden_size, out_hm))
+        out_act = self.euler_bins * 3 + 1 if rot_pred_type == "euler_disc" else dim_actions - 3
+        if reduce == "attn":
+            out_act += 1
+        self.action_mlp = nn.Sequential(nn.Linear(hidden_size + traj_embed_size, hidden_size), nn.LeakyReLU(0.02),
+                                        nn.Dropout(dropout), nn.Linear(hidden_size, out_act + 1))   # + stop logit
+
+
+class MotionPlannerPTV3AdaNorm(BaseModel):
+    """models/motion_planner_ptv3.py:151-199 (3D-LOTUS++ motion planner, adaptive-norm conditioning)."""
+
+    backbone_cls = PointTransformerV3
+    variant = "adanorm"
+    planner = True
+
+    def __init__(self, config):
+        super().__init__()
+        config.defrost()
+        config.ptv3_config.pdnorm_only_decoder = config.ptv3_config.get("pdnorm_only_decoder", False)
+        config.ptv3_config.in_channels += config.action_config.pc_label_channels
+        config.freeze()
+        self.config = config
+        self.ptv3_model = self.backbone_cls(**config.ptv3_config)
+        act_cfg = config.action_config
+        self.pc_label_embedding = nn.Embedding(4, act_cfg.pc_label_channels)    # obstacle, robot, object, target
+        self.txt_fc = nn.Linear(act_cfg.txt_ft_size, act_cfg.context_channels)
+        if act_cfg.txt_reduce == "attn":
+            self.txt_attn_fc = nn.Linear(act_cfg.txt_ft_size, 1)       # dead in the CA variant (SURVEY §8e.2), kept for checkpoints
+        if act_cfg.use_ee_pose:
+            self.pose_embedding = RobotPoseEmbedding(act_cfg.context_channels)
+        self.act_proj_head = TrajActionHead(
+            act_cfg.reduce, act_cfg.pos_pred_type, act_cfg.rot_pred_type, config.ptv3_config.dec_channels[0],
+            act_cfg.dim_actions, act_cfg.max_traj_len, dropout=act_cfg.dropout, voxel_size=act_cfg.voxel_size,
+            ptv3_config=config.ptv3_config, pos_bins=act_cfg.pos_bins, traj_embed_size=act_cfg.traj_embed_size)
+        self.apply(self._init_weights)
+        self._engine = None
+
+    def engine(self):
+        if self._engine is None:
+            from .engine import PolicyEngine
+            self._engine = PolicyEngine(self)
+        return self._engine
+
+    def forward(self, batch, compute_loss=False, **kwargs):
+        """-> final_pred_actions (B, T, 9) float64 [, {'pos','rot','open','stop','total'}] (motion_planner_ptv3.py:230-305)"""
+        batch = self.prepare_batch(batch)
+        return self.engine().forward(batch, compute_loss=compute_loss, **kwargs)
+
+
+class MotionPlannerPTV3CA(MotionPlannerPTV3AdaNorm):
+    """models/motion_planner_ptv3.py:400-463 (cross-attention conditioning; the shipped 3D-LOTUS++ planner)."""
+    backbone_cls = PointTransformerV3CA
+    variant = "ca"
+
+
 MODEL_FACTORY = {
     "SimplePolicyPTV3AdaNorm": SimplePolicyPTV3AdaNorm,
     "SimplePolicyPTV3CA": SimplePolicyPTV3CA,
     "SimplePolicyPTV3Concat": SimplePolicyPTV3Concat,
+    # train_motion_planner.py:46-49
+    "MotionPlannerPTV3AdaNorm": MotionPlannerPTV3AdaNorm,
+    "MotionPlannerPTV3CA": MotionPlannerPTV3CA,
 }
 
 

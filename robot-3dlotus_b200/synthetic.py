@@ -179,6 +179,50 @@ def make_batch(seed=2024, batch_size=32, max_points=4096, min_raw=1500, max_raw=
     return batch
 
 
+def randomize_poses(batch, seed=0):
+    """random unit quaternions (xyzw) for `ee_poses` (make_batch keeps the identity rotation)"""
+    rng = np.random.default_rng(seed)
+    q = rng.standard_normal((batch["ee_poses"].shape[0], 4)).astype(np.float32)
+    q /= np.linalg.norm(q, axis=1, keepdims=True)
+    batch["ee_poses"][:, 3:7] = torch.from_numpy(q)
+    return batch
+
+
+def make_planner_batch(seed=2024, batch_size=32, max_traj_len=5, sizes=None, pos_bins=15, pos_bin_size=0.01,
+                       txt_len_range=(3, 8), **kw):
+    """Config-3 style batch: pc_fts (N,4) = xyz + height, pc_labels, trajectories of up to
+    `max_traj_len` steps with stop flags / masks and one soft position label per step."""
+    b = make_batch(seed=seed, batch_size=batch_size, sizes=sizes, txt_len_range=txt_len_range, pos_bins=pos_bins,
+                   pos_bin_size=pos_bin_size, with_targets=False, **kw)
+    rng = np.random.default_rng(seed + 7919)
+    f = b["pc_fts"]
+    b["pc_fts"] = torch.cat([f[:, :3], f[:, 6:7]], 1).contiguous()
+    N, B, T = f.shape[0], len(b["npoints_in_batch"]), max_traj_len
+    b["pc_labels"] = torch.from_numpy(rng.choice(4, size=N, p=[0.7, 0.15, 0.1, 0.05])).long()
+    randomize_poses(b, seed + 1)
+    lens = rng.integers(1, T + 1, size=B)
+    gt = np.zeros((B, T, 7), dtype=np.float32)
+    stop = np.zeros((B, T), dtype=bool)
+    mask = np.zeros((B, T), dtype=bool)
+    probs = []
+    off = 0
+    for i, n in enumerate(b["npoints_in_batch"]):
+        c = f[off: off + n, :3].numpy()
+        off += n
+        pr = np.zeros((T, 3, n * 2 * pos_bins), dtype=np.float32)
+        for t in range(T):
+            gt[i, t, :3] = c[rng.integers(0, n)] + rng.normal(0, 0.004, size=3)
+            gt[i, t, 3:6] = rng.integers(0, 72, size=3)
+            gt[i, t, 6] = rng.integers(0, 2)
+            pr[t] = disc_gt_pos_prob(c, gt[i, t, :3], pos_bin_size=pos_bin_size, pos_bins=pos_bins)
+        mask[i, : lens[i]] = True
+        stop[i, lens[i] - 1] = True
+        probs.append(torch.from_numpy(pr))
+    b.update(gt_trajs=torch.from_numpy(gt), gt_trajs_stop=torch.from_numpy(stop), traj_masks=torch.from_numpy(mask),
+             traj_lens=[int(v) for v in lens], gt_trajs_disc_pos_probs=probs)
+    return b
+
+
 def batch_nbytes(batch):
     n = 0
     for v in batch.values():

@@ -45,3 +45,8 @@ def gold_small():
 @pytest.fixture(scope="session")
 def gold_prod():
     return load_golden("policy_production.pt")
+
+
+@pytest.fixture(scope="session")
+def gold_variants():
+    return load_golden("variants.pt")

@@ -166,3 +166,59 @@ def test_final_action_eval_matches_reference(gold_small):
     sign = torch.sign((q * qr).sum(-1, keepdim=True))
     assert torch.allclose(q * sign, qr, atol=1e-9)
     assert rel_err(res["final"][:, 7], ref[:, 7]) < 2e-5
+
+
+VARIANTS = ["adanorm", "concat", "ca_tokens", "planner_ca", "planner_adanorm"]
+
+
+def _variant_of(kind):
+    return {"adanorm": "adanorm", "concat": "concat", "ca_tokens": "ca", "planner_ca": "ca", "planner_adanorm": "adanorm"}[kind]
+
+
+@pytest.mark.parametrize("kind", VARIANTS)
+def test_variant_models_match_reference(kind, gold_variants):
+    """§8a rows 15 (pose / step tokens), 19 (motion planner), 20 (PDNorm): oracle vs the reference-minted fixtures"""
+    g = gold_variants[kind]
+    cfg = pkg("config").ConfigNode(g["config"])
+    model = pkg("policy").build_parameter_shell(cfg.clone())
+    assert type(model).__name__ == g["model_class"]
+    pkg("testing").deterministic_reinit(model, g["reinit_seed"])
+    sd = {k: v.clone() for k, v in model.state_dict().items()}
+    params = {k: v.requires_grad_(True) for k, v in sd.items() if v.dtype.is_floating_point and "running_" not in k}
+    sd.update(params)
+    bn_out = {}
+    fwd = O.planner_forward if kind.startswith("planner") else O.policy_forward
+    cfg_run = pkg("policy").build_parameter_shell(cfg.clone()).config      # planner ctor widens in_channels; harmless here
+    res = fwd(sd, cfg_run, g["batch"], perms=g["perms"], train=True, bn_out=bn_out, variant=_variant_of(kind))
+    for k, ref in g["losses"].items():
+        assert abs(res["losses"][k].item() - ref.item()) <= 2e-5 * abs(ref.item()), k
+    f = res["dec_feat"]
+    assert tuple(f.shape) == g["dec_feat_shape"]
+    assert rel_err(f[:16], g["dec_feat_head"]) < 2e-5
+    assert abs(f.double().abs().sum().item() - g["dec_feat_abs_sum"]) < 2e-5 * g["dec_feat_abs_sum"]
+    assert rel_err(res["final"], g["train_actions"]) < 1e-6
+    res["losses"]["total"].backward()
+    floor = 1e-6 * max(g["grad_norms"].values())
+    errs = []
+    for k, n in g["grad_norms"].items():
+        gn = params[k].grad.norm().item()
+        if n < floor:
+            assert gn < floor, (k, gn, n)
+        else:
+            errs.append((abs(gn - n) / n, k))
+    errs.sort()
+    assert errs[len(errs) // 2][0] < 1e-5 and errs[-1][0] < 1e-4, errs[-5:]
+    for k, ref in g["grads"].items():
+        if ref.norm().item() > floor:
+            assert rel_err(params[k].grad, ref) < 1e-4, k
+    for k, ref in g["bn_after"].items():
+        assert rel_err(bn_out[k], ref) < 1e-5, k
+    assert {k for k, p in params.items() if p.grad is None} == set(g["params_without_grad"])
+    # eval pass: running statistics + final-action decode
+    sd_eval = {k: v.detach() for k, v in sd.items()}
+    sd_eval.update(g["bn_after"])                          # the reference's eval pass ran after its training step
+    with torch.no_grad():
+        ev = fwd(sd_eval, cfg_run, g["batch"], perms=g["perms_eval"], train=False,
+                 compute_loss=False, compute_final_action=True, variant=_variant_of(kind))
+    assert ev["final"].dtype == g["final_actions_eval"].dtype == torch.float64
+    assert torch.allclose(ev["final"], g["final_actions_eval"], rtol=1e-5, atol=1e-6)

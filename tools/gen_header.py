@@ -79,7 +79,7 @@ DOC = {
     "lotus_colsum_f32": "Bias gradients (column sums of dy), accumulated.",
     "lotus_batchnorm_fwd_f32": "Replaces nn.BatchNorm1d(eps=1e-3, momentum=0.01) [+ GELU] (stem, pool, unpool): model.py:932,785-788,807-813,854-857.",
     "lotus_batchnorm_bwd_f32": "Backward of BatchNorm1d [+ GELU].",
-    "lotus_pointwise_f32": "GELU / LeakyReLU(0.02) and their derivatives, add, scale: model.py:573; simple_policy_ptv3.py:42,65.",
+    "lotus_pointwise_f32": "GELU / LeakyReLU(0.02) / SiLU and their derivatives, add, scale: model.py:573,279; simple_policy_ptv3.py:42,65.",
     "lotus_dropout_f32": "Replaces nn.Dropout (counter-based mask; the same call on dy is the backward): model.py:388,575; simple_policy_ptv3.py:43,66.",
     "lotus_patch_attn_fwd_f32": "Replaces flash_attn_varlen_qkvpacked_func over the serialized patches incl. the qkv[order] gather and feat[inverse] scatter "
                                 "(and the RPE bias of the non-flash branch): model.py:497,520-521,543-551.",
@@ -91,6 +91,10 @@ DOC = {
     "lotus_segment_sum_f32": "Replaces torch_scatter.segment_csr(reduce='mean') for coords (model.py:763-765); sum mode is the backward of the unpool gather.",
     "lotus_unpool_add_f32": "Replaces parent.feat + point.feat[inverse]: model.py:824.",
     "lotus_policy_loss_f32": "Replaces compute_loss (heatmap_disc soft-label CE, euler_disc CE, open BCE) and its backward: simple_policy_ptv3.py:308-373.",
+    "lotus_traj_loss_f32": "Replaces MotionPlannerPTV3*.compute_loss (masked trajectory soft-label CE, rot CE, open/stop BCE) and its backward: motion_planner_ptv3.py:307-397.",
+    "lotus_decode_trajs": "Replaces the trajectory decode (T steps per keystep, stop logit appended): motion_planner_ptv3.py:250-296.",
+    "lotus_pdnorm_modulate_fwd_f32": "Replaces the adaptive modulation of PDNorm, feat*(1+scale)+shift with per-cloud [shift|scale]: model.py:293-303.",
+    "lotus_pdnorm_modulate_bwd_f32": "Backward of the PDNorm modulation (dx and the per-cloud d[shift|scale]).",
     "lotus_decode_actions": "Replaces the final-action decode: simple_policy_ptv3.py:250-296; utils/action_position_utils.py:48-60; utils/rotation_transform.py:192-193.",
     "lotus_grad_sumsq_f32": "Global gradient norm of clip_grad_norm_: train/train_simple_policy.py:237-241.",
     "lotus_adamw_step_f32": "Replaces the reference AdamW.step over one flat buffer (+ fused clip coefficient): train/optim/adamw.py:53-112.",
