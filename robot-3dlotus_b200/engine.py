@@ -9,6 +9,7 @@ import torch
 
 from . import ops
 from .lib import load
+from .modules import PDNorm
 from .tokenizer import tokenize, CrossGeo
 
 
@@ -39,6 +40,8 @@ class PolicyEngine:
             for mod in self.m.modules():
                 if id(mod) in skip:
                     continue
+                if isinstance(mod, nn.Linear) and (mod.in_features % 8 or mod.out_features % 8):
+                    continue                 # pose / txt-attention projections stay fp32 SIMT
                 if isinstance(mod, (nn.Linear, SubMConv3d)):
                     ws.append(mod.weight)
             self._tc_weights = ws
@@ -59,19 +62,43 @@ class PolicyEngine:
             return None
         return [torch.randperm(R).tolist() for _ in range(S)]      # CPU RNG, like model.py:131,751
 
+    # ------------------------------------------------------------------ norms (plain or PDNorm, model.py:257-304)
+    def _modulated(self, mod, y, pd, stg):
+        if not mod.adaptive:
+            return y
+        ss = ops.linear(pd["sctx"], mod.modulation[1].weight, mod.modulation[1].bias)       # (B, 2C) = [shift | scale]
+        return ops.pdnorm_modulate(y, ss, stg.cloud_off, pd["B"])
+
+    def _ln(self, mod, x, pd, stg, residual=None):
+        if isinstance(mod, PDNorm):
+            assert mod.norm.weight is not None, "pdnorm_affine False is not used by any shipped config"
+            y = self._modulated(mod, ops.layer_norm(x, mod.norm.weight, mod.norm.bias, mod.norm.eps), pd, stg)
+            return y if residual is None else ops.add(residual, y)
+        return ops.layer_norm(x, mod.weight, mod.bias, mod.eps, residual=residual)
+
+    def _bn_gelu(self, mod, x, train, pd, stg, out_bf16=False):
+        if isinstance(mod, PDNorm):
+            assert mod.norm.weight is not None, "pdnorm_affine False is not used by any shipped config"
+            y = self._modulated(mod, ops.batch_norm_act(x, mod.norm, train, gelu=False), pd, stg)
+            return ops.act(y, "gelu")
+        return ops.batch_norm_act(x, mod, train, gelu=True, out_bf16=out_bf16)
+
     # ------------------------------------------------------------------ blocks
-    def _block(self, blk, x, stg, drop, conv_in=None):
+    def _block(self, blk, x, stg, drop, conv_in=None, pd=None):
+        if blk.drop_path_p > 0 and drop.enabled:
+            raise NotImplementedError("engine: stochastic depth (drop_path > 0) in training mode is not wired "
+                                      "(0 in the production configuration); use eval mode or drop_path 0")
         a = blk.attn
         c = ops.subm_conv(x if conv_in is None else conv_in, blk.cpe[0].weight, blk.cpe[0].bias, stg.nbr3, stg.stride_alloc, rule=stg)
         c = ops.linear(c, blk.cpe[1].weight, blk.cpe[1].bias)
-        x = ops.layer_norm(c, blk.cpe[2].weight, blk.cpe[2].bias, blk.cpe[2].eps, residual=x)
-        h = ops.layer_norm(x, blk.norm1[0].weight, blk.norm1[0].bias, blk.norm1[0].eps)
+        x = self._ln(blk.cpe[2], c, pd, stg, residual=x)
+        h = self._ln(blk.norm1[0], x, pd, stg)
         qkv = ops.linear(h, a.qkv.weight, a.qkv.bias)
         plan = stg.plans[a.order_index]
         o = ops.patch_attention(qkv, a.q_norm, a.k_norm, a.rpe, plan, a.num_heads, a.qk_norm, drop.site(a.attn_drop),
                                 grid=stg.grid)
         x = ops.linear(o, a.proj.weight, a.proj.bias, residual=x, drop=drop.site(a.proj_drop_p))
-        h = ops.layer_norm(x, blk.norm2[0].weight, blk.norm2[0].bias, blk.norm2[0].eps)
+        h = self._ln(blk.norm2[0], x, pd, stg)
         mlp = blk.mlp[0]
         u = ops.linear(h, mlp.fc1.weight, mlp.fc1.bias)
         g = ops.act(u, "gelu", drop.site(blk.proj_drop))
@@ -93,12 +120,13 @@ class PolicyEngine:
         return x
 
     # ------------------------------------------------------------------ backbone
-    def backbone(self, feat, coord, npoints, ctx, tok_off_host, train, drop):
-        """PointTransformerV3CA.forward(return_dec_layers=True): returns (last decoder feat, stages)."""
+    def backbone(self, feat, coord, npoints, ctx, tok_off_host, train, drop, pd=None):
+        """PointTransformerV3[CA].forward(return_dec_layers=True) (model.py:1072-1101, model_ca.py:383-412):
+        returns (last decoder feat, stages).  `pd` carries the per-cloud context of the PDNorm (AdaNorm) variants."""
         pt = self.m.ptv3_model
-        if not pt.with_ca or pt.pdnorm_bn or pt.pdnorm_ln:
-            raise NotImplementedError("engine: only the CA backbone with plain BN/LN (the production model) is wired; "
-                                      "AdaNorm/Concat variants construct and checkpoint but do not run yet")
+        ca = pt.with_ca
+        if (pt.pdnorm_bn or pt.pdnorm_ln) and pt.pdnorm_adaptive and pd is None:
+            raise ValueError("adaptive PDNorm needs a per-cloud context")
         S = pt.num_stages
         R = len(pt.order)
         rows = [sorted({i % R for i in range(pt.enc_depths[s])} |
@@ -111,13 +139,15 @@ class PolicyEngine:
         self.last_stages = stages
         dev = feat.device
         B = len(npoints)
-        tok_off = torch.tensor(tok_off_host, dtype=torch.int32).to(dev, non_blocking=True)
-        max_tok = max(b - a for a, b in zip(tok_off_host[:-1], tok_off_host[1:]))
-        geos = [CrossGeo(stg.cloud_off, tok_off, B, stg.max_cloud, max_tok) for stg in stages]
+        geos = None
+        if ca:
+            tok_off = torch.tensor(tok_off_host, dtype=torch.int32).to(dev, non_blocking=True)
+            max_tok = max(b - a for a, b in zip(tok_off_host[:-1], tok_off_host[1:]))
+            geos = [CrossGeo(stg.cloud_off, tok_off, B, stg.max_cloud, max_tok) for stg in stages]
 
         stem = pt.embedding.stem
-        x = ops.subm_conv(feat, stem.conv.weight, None, stages[0].nbr5, stages[0].stride_alloc)     # Cin=7: fp32 SIMT in both modes
-        x = ops.batch_norm_act(x, stem.norm, train, gelu=True, out_bf16=(self.precision == "bf16"))
+        x = ops.subm_conv(feat, stem.conv.weight, None, stages[0].nbr5, stages[0].stride_alloc)     # narrow Cin: fp32 SIMT in both modes
+        x = self._bn_gelu(stem.norm, x, train, pd, stages[0], out_bf16=(self.precision == "bf16"))
         self._rec("embedding", x)
         skips = []
         for s in range(S):
@@ -128,29 +158,30 @@ class PolicyEngine:
                 skips.append(x)
                 proj = ops.linear(x, down.proj.weight, down.proj.bias)
                 pooled = ops.segment_max(proj, stg.seg_ptr, stg.member, stg.n)
-                x = ops.batch_norm_act(pooled, down.norm[0], train, gelu=True)
+                x = self._bn_gelu(down.norm[0], pooled, train, pd, stg)
                 self._rec(f"enc{s}.down", x)
             for i in range(pt.enc_depths[s]):
-                x = self._block(getattr(enc, f"block{i}"), x, stg, drop)
+                x = self._block(getattr(enc, f"block{i}"), x, stg, drop, pd=pd)
                 self._rec(f"enc{s}.block{i}", x)
-                x = self._ca_block(getattr(enc, f"ca_block{i}"), x, ctx, geos[s], drop)
-                self._rec(f"enc{s}.ca_block{i}", x)
+                if ca and hasattr(enc, f"ca_block{i}"):
+                    x = self._ca_block(getattr(enc, f"ca_block{i}"), x, ctx, geos[s], drop)
+                    self._rec(f"enc{s}.ca_block{i}", x)
         for s in reversed(range(S - 1)):
             dec = getattr(pt.dec, f"dec{s}")
             stg, child = stages[s], stages[s + 1]
             up = dec.up
-            a = ops.batch_norm_act(ops.linear(x, up.proj[0].weight, up.proj[0].bias), up.proj[1], train, gelu=True)
-            b = ops.batch_norm_act(ops.linear(skips[s], up.proj_skip[0].weight, up.proj_skip[0].bias), up.proj_skip[1],
-                                   train, gelu=True)
+            a = self._bn_gelu(up.proj[1], ops.linear(x, up.proj[0].weight, up.proj[0].bias), train, pd, child)
+            b = self._bn_gelu(up.proj_skip[1], ops.linear(skips[s], up.proj_skip[0].weight, up.proj_skip[0].bias), train, pd, stg)
             x = ops.unpool_add(b, a, child.cluster, child.seg_ptr, child.member)
             self._rec(f"dec{s}.up", x)
             conv_in = b          # sparse_conv_feat is NOT refreshed by the add (model.py:824 vs :235-238)
             for i in range(pt.dec_depths[s]):
-                x = self._block(getattr(dec, f"block{i}"), x, stg, drop, conv_in=conv_in)
+                x = self._block(getattr(dec, f"block{i}"), x, stg, drop, conv_in=conv_in, pd=pd)
                 conv_in = None
                 self._rec(f"dec{s}.block{i}", x)
-                x = self._ca_block(getattr(dec, f"ca_block{i}"), x, ctx, geos[s], drop)
-                self._rec(f"dec{s}.ca_block{i}", x)
+                if ca:
+                    x = self._ca_block(getattr(dec, f"ca_block{i}"), x, ctx, geos[s], drop)
+                    self._rec(f"dec{s}.ca_block{i}", x)
         return x, stages
 
     # ------------------------------------------------------------------ native one-call step
@@ -181,17 +212,62 @@ class PolicyEngine:
         return self._native.run(batch, stages, tok_dev, tok_off, m.training, self.precision == "bf16", compute_loss,
                                 not compute_final_action, with_grad and compute_loss, seed)
 
+    # ------------------------------------------------------------------ context (prepare_ptv3_batch)
+    def _pose_embedding(self, poses):
+        """RobotPoseEmbedding.forward (models/base.py:61-78); the quaternion -> euler step runs in scipy on the host
+        exactly as in the reference"""
+        from scipy.spatial.transform import Rotation as R
+        pe = self.m.pose_embedding
+        poses = poses.float()
+        e = torch.from_numpy(R.from_quat(poses[:, 3:7].detach().cpu().numpy()).as_euler("xyz")).float().to(poses.device)
+        rot_in = torch.cat([torch.sin(e), torch.cos(e)], -1).contiguous()
+        x = ops.linear(poses[:, :3].contiguous(), pe.pos_embedding.weight, pe.pos_embedding.bias)
+        x = ops.add(x, ops.linear(rot_in, pe.rot_embedding.weight, pe.rot_embedding.bias))
+        x = ops.add(x, pe.open_embedding.weight[poses[:, -1].long()])
+        return ops.layer_norm(x, pe.layer_norm.weight, pe.layer_norm.bias, pe.layer_norm.eps)
+
+    def _context(self, batch, bf):
+        """-> (ctx, token offsets) for the CA variants (packed tokens; pose / step-id appended per cloud:
+        simple_policy_ptv3.py:413-429) or (per-cloud vector, None) for AdaNorm / Concat (:194-223, :449-456)"""
+        m = self.m
+        ac = m.config.action_config
+        txt = batch["txt_embeds"].float()
+        lens = [int(l) for l in batch["txt_lens"]]
+        ctx = ops.linear(ops.to_bf16(txt) if bf else txt, m.txt_fc.weight, m.txt_fc.bias)
+        pose = self._pose_embedding(batch["ee_poses"]) if ac.use_ee_pose else None
+        step = m.stepid_embedding.weight[batch["step_ids"]] if (ac.use_step_id and hasattr(m, "stepid_embedding")) else None
+        if m.variant == "ca":
+            if pose is not None or step is not None:
+                toks = list(torch.split(ctx, lens))
+                for extra in (pose, step):
+                    if extra is not None:
+                        e = ops.cast(extra, torch.bfloat16) if bf else extra
+                        toks = [torch.cat([c, e[i:i + 1]], 0) for i, c in enumerate(toks)]
+                        lens = [l + 1 for l in lens]
+                ctx = torch.cat(toks, 0)
+            tok_off = [0]
+            for l in lens:
+                tok_off.append(tok_off[-1] + l)
+            return ctx, tok_off
+        if ac.txt_reduce == "attn" and m.variant != "concat":
+            w = ops.linear(txt, m.txt_attn_fc.weight, m.txt_attn_fc.bias)
+            ctx = torch.stack([(torch.softmax(wi, 0) * ci).sum(0) for wi, ci in zip(torch.split(w, lens), torch.split(ctx, lens))], 0)
+        elif any(l != 1 for l in lens):
+            raise ValueError("AdaNorm / Concat conditioning takes one (pre-reduced) text vector per keystep unless txt_reduce='attn'")
+        if pose is not None:
+            ctx = ops.add(ctx, pose)
+        if step is not None:
+            ctx = ops.add(ctx, step)
+        return ctx, None
+
     # ------------------------------------------------------------------ policy
     def forward(self, batch, compute_loss=False, **kwargs):
         m = self.m
         cfg = m.config
         ac = cfg.action_config
-        if m.variant != "ca":
-            raise NotImplementedError("engine: SimplePolicyPTV3CA is the wired variant")
-        if ac.use_ee_pose or ac.use_step_id:
-            raise NotImplementedError("engine: pose / step-id context tokens are disabled in production and not wired yet")
+        planner = getattr(m, "planner", False)
         if ac.pos_pred_type != "heatmap_disc" or ac.rot_pred_type != "euler_disc" or ac.reduce != "max":
-            raise NotImplementedError("engine: the production head (heatmap_disc / euler_disc / max) is the wired one")
+            raise NotImplementedError("engine: the shipped head (heatmap_disc / euler_disc / max) is the wired one")
         fts = batch["pc_fts"]
         if not fts.is_cuda:
             raise RuntimeError("lotus engine needs the model on a CUDA device (there is no CPU fallback)")
@@ -218,20 +294,30 @@ class PolicyEngine:
             if any(c % 64 for c in widths):
                 raise ValueError(f"tensor-core (bf16) mode needs channel widths that are multiples of 64, got {widths}; "
                                  "use precision='fp32' for this configuration")
+            if m.variant != "ca":
+                raise ValueError("tensor-core (bf16) mode covers the cross-attention variants; AdaNorm / Concat run in precision='fp32'")
             self._stage_weights()
-        # context tokens (simple_policy_ptv3.py:413-429)
-        txt = batch["txt_embeds"].float()
-        ctx = ops.linear(ops.to_bf16(txt) if bf else txt, m.txt_fc.weight, m.txt_fc.bias)
-        tok_off = [0]
-        for l in batch["txt_lens"]:
-            tok_off.append(tok_off[-1] + int(l))
+        ctx, tok_off = self._context(batch, bf)
+        feat, pd = fts, None
+        if planner:                                   # motion_planner_ptv3.py:445-446
+            feat = torch.cat([fts, m.pc_label_embedding.weight[batch["pc_labels"]]], -1).contiguous()
+        if m.variant == "concat":                     # simple_policy_ptv3.py:458-462
+            rep = torch.repeat_interleave(ctx, torch.tensor(npoints, device=fts.device), 0)
+            feat, ctx = torch.cat([feat, rep], -1).contiguous(), None
+        elif m.variant == "adanorm":
+            pd = {"sctx": ops.act(ctx.contiguous(), "silu"), "B": B}
 
-        x, stages = self.backbone(fts, fts[:, :3], npoints, ctx, tok_off, train, drop)
+        x, stages = self.backbone(feat, fts[:, :3], npoints, ctx, tok_off, train, drop, pd)
         self._rec("dec_feat", x)
         s0 = stages[0]
+        head = m.act_proj_head
+        NB = 2 * head.pos_bins
+        final_action = kwargs.get("compute_final_action", True)
+        lc = cfg.loss_config
+        if planner:
+            return self._planner_tail(batch, x, fts, s0, B, NB, drop, compute_loss, final_action, lc)
 
         # action head (simple_policy_ptv3.py:113-120,149-152)
-        head = m.act_proj_head
         hm, am = head.heatmap_mlp, head.action_mlp
         # (bf16 mode: the first layers run on tensor cores and emit fp32; the 90/217-wide logits stay fp32 SIMT)
         h = ops.act(ops.linear(x, hm[0].weight, hm[0].bias, out_fp32=True), "leaky", drop.site(head.dropout))
@@ -242,9 +328,7 @@ class PolicyEngine:
         self._rec("heat", heat)
         self._rec("action", action)
 
-        NB = 2 * head.pos_bins
         gt = batch.get("gt_actions")
-        final_action = kwargs.get("compute_final_action", True)
         with torch.no_grad():
             final = ops.decode_actions(heat, fts, s0.cloud_off, B, NB, ac.pos_bin_size, action, head.euler_bins,
                                        head.euler_resolution, None if final_action else gt.float())
@@ -255,7 +339,44 @@ class PolicyEngine:
         else:
             prob = torch.cat([p.reshape(-1) for p in batch["disc_pos_probs"]])
         prob = prob.to(fts.device, non_blocking=True).float()
-        lc = cfg.loss_config
         lv = ops.policy_loss(heat, action, prob, s0.cloud_off, gt.float().contiguous(), B, NB, head.euler_bins,
                              lc.pos_weight, lc.rot_weight)
         return final, {"pos": lv[0], "rot": lv[1], "open": lv[2], "total": lv[3]}
+
+    def _planner_tail(self, batch, x, fts, s0, B, NB, drop, compute_loss, final_action, lc):
+        """trajectory head, losses and decode of MotionPlannerPTV3* (motion_planner_ptv3.py:77-148, 250-397).
+        The heads read [point feature | step embedding]; the first layers are split accordingly so the per-point GEMM
+        runs once instead of once per trajectory step:  W [x | e_t] + b = W_x x + (W_e e_t + b)."""
+        m = self.m
+        ac = m.config.action_config
+        head = m.act_proj_head
+        T, C = head.max_traj_len, head.hidden_size
+        assert head.traj_embedding is not None, "traj_embed_size 0 is unused by the shipped planner"
+        hm, am = head.heatmap_mlp, head.action_mlp
+        x = ops.cast(x, torch.float32)
+        N = x.shape[0]
+        te = head.traj_embedding.weight[:T]
+        W0 = hm[0].weight
+        h0 = ops.linear(x, W0[:, :C].contiguous(), None)                                   # (N, hidden)
+        tb = ops.linear(te.contiguous(), W0[:, C:].contiguous(), hm[0].bias)               # (T, hidden)
+        h = (h0.unsqueeze(1) + tb.unsqueeze(0)).reshape(N * T, -1)
+        h = ops.act(h, "leaky", drop.site(head.dropout))
+        heat = ops.linear(h, hm[3].weight, hm[3].bias).view(N, T * 3 * NB)                 # [n, (t*3 + c)*NB + b]
+        pc = ops.segment_max(x, s0.cloud_off, None, B)                                     # max over points of [x | e_t] = [max x | e_t]
+        pct = torch.cat([pc.unsqueeze(1).expand(B, T, C), te.unsqueeze(0).expand(B, T, -1)], -1).reshape(B * T, -1).contiguous()
+        h2 = ops.act(ops.linear(pct, am[0].weight, am[0].bias), "leaky", drop.site(head.dropout))
+        action = ops.linear(h2, am[3].weight, am[3].bias)                                  # (B*T, 72*3 + 2)
+        self._rec("heat", heat)
+        self._rec("action", action)
+        gt = batch.get("gt_trajs")
+        gt2 = gt.float().reshape(B * T, -1).contiguous() if gt is not None else None
+        with torch.no_grad():
+            final = ops.decode_trajs(heat, fts, s0.cloud_off, B, T, NB, ac.pos_bin_size, action, head.euler_bins,
+                                     head.euler_resolution, None if final_action else gt2)
+        if not compute_loss:
+            return final
+        prob = torch.cat([p.reshape(-1) for p in batch["gt_trajs_disc_pos_probs"]]).to(fts.device, non_blocking=True).float()
+        stop = batch["gt_trajs_stop"].to(fts.device).float().reshape(-1).contiguous()
+        mask = batch["traj_masks"].to(fts.device).float().reshape(-1).contiguous()
+        lv = ops.traj_loss(heat, action, prob, s0.cloud_off, gt2, stop, mask, B, T, NB, head.euler_bins, lc.pos_weight, lc.rot_weight)
+        return final, {"pos": lv[0], "rot": lv[1], "open": lv[2], "stop": lv[3], "total": lv[4]}

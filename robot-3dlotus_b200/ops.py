@@ -180,14 +180,14 @@ def linear(x, w, b=None, residual=None, drop=NO_DROP, out_fp32=False):
 
 
 class ActFn(torch.autograd.Function):
-    """y = drop(act(x)); act: 'gelu' | 'leaky' (slope 0.02)"""
+    """y = drop(act(x)); act: 'gelu' | 'leaky' (slope 0.02) | 'silu' (no dropout)"""
 
     @staticmethod
     def forward(ctx, x, kind, drop):
         L = load()
         x = _actc(x)
         y = torch.empty_like(x)
-        op = 0 if kind == "gelu" else 2
+        op = {"gelu": 0, "leaky": 2, "silu": 7}[kind]
         getattr(L, "lotus_pointwise_" + _sfx(x))(_p(x), None, _p(y), x.numel(), op, 0.02, drop[0], drop[1], drop[2], _st())
         ctx.save_for_backward(x)
         ctx.op, ctx.drop = op, drop
@@ -687,4 +687,117 @@ def decode_actions(heat, xyz, cloud_off, B, NB, bin_size, action, rot_bins, reso
     xyz_ld = xyz.stride(0)
     L.lotus_decode_actions(_p(heat), _p(xyz), xyz_ld, _p(cloud_off), B, NB, float(bin_size), _p(action), action.shape[1],
                            rot_bins, float(resolution), _p(gt_pos), gt_pos.stride(0) if gt_pos is not None else 0, _p(out), _st())
+    return out
+
+
+
+# ------------------------------------------------------------------------------------------ variants (AdaNorm / planner)
+
+
+class CastFn(torch.autograd.Function):
+    """differentiable fp32 <-> bf16 conversion (the gradient is converted back)"""
+
+    @staticmethod
+    def forward(ctx, x, to_bf):
+        ctx.to_bf = to_bf
+        return to_bf16(x) if to_bf else to_f32(x)
+
+    @staticmethod
+    def backward(ctx, dy):
+        return (to_f32(dy) if ctx.to_bf else to_bf16(dy.float() if dy.dtype != torch.float32 else dy)), None
+
+
+def cast(x, dtype):
+    if x.dtype == dtype:
+        return x
+    return CastFn.apply(x, dtype == torch.bfloat16)
+
+
+class AddFn(torch.autograd.Function):
+    """y = a + b (same shape / dtype), through the pointwise kernel"""
+
+    @staticmethod
+    def forward(ctx, a, b):
+        L = load()
+        a, b = _actc(a), _actc(b)
+        y = torch.empty_like(a)
+        getattr(L, "lotus_pointwise_" + _sfx(a))(_p(b), _p(a), _p(y), a.numel(), 4, 0.0, 0.0, 0, 0, _st())
+        return y
+
+    @staticmethod
+    def backward(ctx, dy):
+        return dy, dy
+
+
+def add(a, b):
+    return AddFn.apply(a, b)
+
+
+class ModulateFn(torch.autograd.Function):
+    """PDNorm modulation y = x * (1 + scale[b]) + shift[b] with per-cloud shift_scale (B, 2C) (model.py:293-303)"""
+
+    @staticmethod
+    def forward(ctx, x, ss, cloud_off, B):
+        L = load()
+        x, ss = _f32c(x), _f32c(ss)
+        rows, C = x.shape
+        assert ss.shape == (B, 2 * C)
+        y = torch.empty_like(x)
+        L.lotus_pdnorm_modulate_fwd_f32(_p(x), _p(ss), _p(cloud_off), B, rows, C, _p(y), _st())
+        ctx.save_for_backward(x, ss, cloud_off)
+        ctx.B = B
+        return y
+
+    @staticmethod
+    def backward(ctx, dy):
+        L = load()
+        x, ss, cloud_off = ctx.saved_tensors
+        dy = _f32c(dy)
+        dx = torch.empty_like(x)
+        dss = torch.empty_like(ss)
+        L.lotus_pdnorm_modulate_bwd_f32(_p(dy), _p(x), _p(ss), _p(cloud_off), ctx.B, x.shape[1], _p(dx), _p(dss), _st())
+        return dx, dss, None, None
+
+
+def pdnorm_modulate(x, ss, cloud_off, B):
+    return ModulateFn.apply(x, ss, cloud_off, B)
+
+
+class TrajLossFn(torch.autograd.Function):
+    """-> losses (5,) = [pos, rot, open, stop, total]  (motion_planner_ptv3.py:307-397)"""
+
+    @staticmethod
+    def forward(ctx, heat, action, prob, cloud_off, gt, stop, mask, B, T, NB, rot_bins, pos_w, rot_w):
+        L = load()
+        heat, action = _f32c(heat), _f32c(action)
+        losses = torch.empty(5, device=heat.device, dtype=torch.float32)
+        L.lotus_traj_loss_f32(_p(heat), _p(prob), _p(cloud_off), B, T, NB, _p(action), action.shape[1], rot_bins, _p(gt),
+                              gt.shape[1], _p(stop), _p(mask), pos_w, rot_w, _p(losses), None, None, None, _st())
+        ctx.save_for_backward(heat, action, prob, cloud_off, gt, stop, mask)
+        ctx.cfg = (B, T, NB, rot_bins, pos_w, rot_w)
+        return losses
+
+    @staticmethod
+    def backward(ctx, g):
+        L = load()
+        heat, action, prob, cloud_off, gt, stop, mask = ctx.saved_tensors
+        B, T, NB, rot_bins, pos_w, rot_w = ctx.cfg
+        g = _f32c(g)
+        dheat = torch.empty_like(heat)
+        dact = torch.empty_like(action)
+        scratch = torch.empty(5, device=heat.device, dtype=torch.float32)
+        L.lotus_traj_loss_f32(_p(heat), _p(prob), _p(cloud_off), B, T, NB, _p(action), action.shape[1], rot_bins, _p(gt),
+                              gt.shape[1], _p(stop), _p(mask), pos_w, rot_w, _p(scratch), _p(dheat), _p(dact), _p(g), _st())
+        return (dheat, dact) + (None,) * 11
+
+
+def traj_loss(heat, action, prob, cloud_off, gt, stop, mask, B, T, NB, rot_bins, pos_w, rot_w):
+    return TrajLossFn.apply(heat, action, prob, cloud_off, gt, stop, mask, B, T, NB, rot_bins, float(pos_w), float(rot_w))
+
+
+def decode_trajs(heat, xyz, cloud_off, B, T, NB, bin_size, action, rot_bins, resolution, gt_pos):
+    L = load()
+    out = torch.empty((B, T, 9), device=heat.device, dtype=torch.float64)
+    L.lotus_decode_trajs(_p(heat), _p(xyz), xyz.stride(0), _p(cloud_off), B, T, NB, float(bin_size), _p(action), action.shape[1],
+                         rot_bins, float(resolution), _p(gt_pos), gt_pos.stride(0) if gt_pos is not None else 0, _p(out), _st())
     return out

@@ -671,3 +671,99 @@ def test_flat_adamw_matches_reference_optimizer():
     for i in (0, nd, len(ref_p) - 1):
         assert torch.allclose(sd["state"][i]["exp_avg"].cpu(), ref_m[i], rtol=2e-5, atol=1e-9)
         assert torch.allclose(sd["state"][i]["exp_avg_sq"].cpu(), ref_v[i], rtol=2e-5, atol=1e-12)
+
+
+def _clone_batch(b):
+    out = {}
+    for k, v in b.items():
+        if isinstance(v, torch.Tensor):
+            out[k] = v.clone()
+        elif isinstance(v, list) and v and isinstance(v[0], torch.Tensor):
+            out[k] = [t.clone() for t in v]
+        else:
+            out[k] = list(v) if isinstance(v, list) else v
+    return out
+
+
+@pytest.mark.parametrize("kind", ["adanorm", "concat", "ca_tokens", "planner_ca", "planner_adanorm"])
+def test_variant_models_match_reference(kind, gold_variants):
+    """§8a rows 15 / 19 / 20: AdaNorm (PDNorm), Concat, pose + step-id context tokens and the two motion planners through
+    the CUDA path against the reference-minted fixtures (training step, then the eval / final-action pass)"""
+    g = gold_variants[kind]
+    cfg = pkg("config").ConfigNode(g["config"])
+    model = pkg("policy").build_parameter_shell(cfg)
+    assert type(model).__name__ == g["model_class"]
+    pkg("testing").deterministic_reinit(model, g["reinit_seed"])
+    model = model.to(DEV).train()
+    eng = model.engine()
+    eng.forced_perms, eng.record = g["perms"], True
+    final, losses = model(_clone_batch(g["batch"]), compute_loss=True, compute_final_action=False)
+    assert set(losses) == set(g["losses"])
+    for k, ref in g["losses"].items():
+        assert abs(losses[k].item() - ref.item()) <= TOL * abs(ref.item()), k
+    f = eng.last["dec_feat"]
+    assert tuple(f.shape) == g["dec_feat_shape"]
+    assert rel(f[:16], g["dec_feat_head"]) < TOL
+    assert abs(f.double().abs().sum().item() - g["dec_feat_abs_sum"]) < TOL * g["dec_feat_abs_sum"]
+    ref_act = g["train_actions"].double()
+    assert final.dtype == torch.float64 and final.shape == ref_act.shape
+    assert torch.equal(final[..., :3].cpu(), ref_act[..., :3])                          # pred_pos := gt
+    assert torch.allclose(final[..., 3:7].cpu(), ref_act[..., 3:7], atol=1e-9)
+    assert rel(final[..., 7:], ref_act[..., 7:]) < TOL
+    losses["total"].backward()
+    grads = {k: p.grad for k, p in model.named_parameters() if p.grad is not None}
+    assert {k for k, p in model.named_parameters() if p.grad is None} == set(g["params_without_grad"])
+    floor = 1e-6 * max(g["grad_norms"].values())
+    errs = []
+    for k, n in g["grad_norms"].items():
+        gn = grads[k].norm().item()
+        if n < floor:
+            assert gn < 10 * floor, (k, gn, n)
+        else:
+            errs.append((abs(gn - n) / n, k))
+    errs.sort()
+    assert errs[len(errs) // 2][0] < 2e-5 and errs[-1][0] < TOL, errs[-5:]
+    for k, ref in g["grads"].items():
+        if ref.norm().item() > floor:
+            assert rel(grads[k], ref) < TOL, k
+    sd = model.state_dict()
+    for k, ref in g["bn_after"].items():
+        assert rel(sd[k], ref) < 1e-5, k
+    # eval pass (BatchNorm running statistics as left by the training step, like the fixture) + final-action decode
+    model.eval()
+    eng.forced_perms = g["perms_eval"]
+    with torch.no_grad():
+        ev = model(_clone_batch(g["batch"]))
+    ref = g["final_actions_eval"]
+    assert ev.dtype == torch.float64 and ev.shape == ref.shape
+    assert torch.allclose(ev[..., :3].cpu(), ref[..., :3], atol=1e-6)
+    assert torch.allclose(ev[..., 3:7].cpu(), ref[..., 3:7], atol=1e-9)
+    assert rel(ev[..., 7:], ref[..., 7:]) < TOL
+
+
+def test_planner_bf16_mode_runs_and_tracks_fp32():
+    """MotionPlannerPTV3CA at production width in tensor-core mode: losses within bf16 tolerance of the fp32 path"""
+    cfgm, syn, testing = pkg("config"), pkg("synthetic"), pkg("testing")
+    cfg = cfgm.production_model_config(attn_drop=0.0, proj_drop=0.0, in_channels=4)
+    cfg.model_class = "MotionPlannerPTV3CA"
+    cfg.action_config.update(dropout=0.0, max_traj_len=5, pc_label_channels=64, traj_embed_size=64, txt_reduce="attn")
+    model = pkg("policy").build_parameter_shell(cfg)
+    testing.deterministic_reinit(model, 31)
+    model = model.to(DEV).train()
+    batch = syn.make_planner_batch(seed=8, sizes=[600, 300])
+    perms = torch.stack([torch.randperm(4, generator=torch.Generator().manual_seed(s)) for s in range(5)])
+    eng = model.engine()
+    eng.forced_perms = perms
+    out = {}
+    for prec in ("fp32", "bf16"):
+        eng.precision = prec
+        for p in model.parameters():
+            p.grad = None
+        final, losses = model(_clone_batch(batch), compute_loss=True, compute_final_action=False)
+        losses["total"].backward()
+        out[prec] = ({k: v.item() for k, v in losses.items()}, model.act_proj_head.traj_embedding.weight.grad.clone())
+        assert final.shape == (2, 5, 9)
+    for k in out["fp32"][0]:
+        assert abs(out["bf16"][0][k] - out["fp32"][0][k]) < 3e-2 * abs(out["fp32"][0][k]) + 1e-3, (k, out)
+    a, b = out["fp32"][1].flatten().double(), out["bf16"][1].flatten().double()
+    assert torch.dot(a, b) / (a.norm() * b.norm()) > 0.9
