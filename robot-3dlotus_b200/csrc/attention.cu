@@ -7,6 +7,22 @@
 // q and k arrive already per-head LayerNorm'ed (norm_act.cu).
 #include "common.cuh"
 
+// tensor-core variants (attention_tc.cu)
+bool lotus_patch_attn_tc_ok(const void* q, const void* k, const void* v, int64_t ldq, int64_t ldk, int64_t ldv, const void* out,
+                            int64_t ldo, int max_len, int Dh, const float* rpe_table);
+int lotus_patch_attn_fwd_tc(const void* q, const void* k, const void* v, int64_t ldq, int64_t ldk, int64_t ldv,
+                            const int32_t* gather_idx, const int32_t* slot_of_point, const int32_t* cu_seqlens, int n_patches, int H,
+                            int Dh, float scale, void* out, int64_t ldo, float* lse, float drop_p, uint64_t seed, uint32_t layer_id,
+                            void* stream_);
+
+bool lotus_patch_attn_bwd_tc_ok(const float* dq, const float* dk, const float* dv, int64_t lddq, int64_t lddk, int64_t lddv, int Dh,
+                                const float* drpe_table);
+int lotus_patch_attn_bwd_tc(const void* q, const void* k, const void* v, int64_t ldq, int64_t ldk, int64_t ldv,
+                            const int32_t* gather_idx, const int32_t* slot_of_point, const int32_t* cu_seqlens, int n_patches, int H,
+                            int Dh, float scale, const void* out, const void* dout, int64_t ldo, const float* lse, float* dq, float* dk,
+                            float* dv, int64_t lddq, int64_t lddk, int64_t lddv, float drop_p, uint64_t seed, uint32_t layer_id,
+                            void* stream_);
+
 struct RpeArgs {
   const float* table;   // [3*(2*bnd+1), H] or null
   const int32_t* grid;  // [N,3]
@@ -231,6 +247,9 @@ LOTUS_API int lotus_patch_attn_fwd_bf16(const void* q, const void* k, const void
                                         int n_patches, int max_len, int H, int Dh, float scale, const float* rpe_table,
                                         const int32_t* grid, int pos_bnd, void* out, int64_t ldo, float* lse, float drop_p,
                                         uint64_t seed, uint32_t layer_id, void* stream_) {
+  if (lotus_patch_attn_tc_ok(q, k, v, ldq, ldk, ldv, out, ldo, max_len, Dh, rpe_table))      // tcgen05 path (attention_tc.cu)
+    return lotus_patch_attn_fwd_tc(q, k, v, ldq, ldk, ldv, gather_idx, slot_of_point, cu_seqlens, n_patches, H, Dh, scale, out, ldo,
+                                   lse, drop_p, seed, layer_id, stream_);
   return patch_fwd_impl<bf16_t>(q, k, v, ldq, ldk, ldv, gather_idx, slot_of_point, cu_seqlens, n_patches, max_len, H, Dh, scale,
                                 rpe_table, grid, pos_bnd, out, ldo, lse, drop_p, seed, layer_id, stream_);
 }
@@ -277,6 +296,10 @@ LOTUS_API int lotus_patch_attn_bwd_bf16(const void* q, const void* k, const void
                                         int64_t ldo, const float* lse, float* dq, float* dk, float* dv, int64_t lddq,
                                         int64_t lddk, int64_t lddv, float drop_p, uint64_t seed, uint32_t layer_id,
                                         void* stream_) {
+  if (lotus_patch_attn_tc_ok(q, k, v, ldq, ldk, ldv, out, ldo, max_len, Dh, rpe_table) &&
+      lotus_patch_attn_bwd_tc_ok(dq, dk, dv, lddq, lddk, lddv, Dh, drpe_table) && ((uintptr_t)dout & 15) == 0)
+    return lotus_patch_attn_bwd_tc(q, k, v, ldq, ldk, ldv, gather_idx, slot_of_point, cu_seqlens, n_patches, H, Dh, scale, out, dout,
+                                   ldo, lse, dq, dk, dv, lddq, lddk, lddv, drop_p, seed, layer_id, stream_);
   return patch_bwd_impl<bf16_t>(q, k, v, ldq, ldk, ldv, gather_idx, slot_of_point, cu_seqlens, n_patches, max_len, H, Dh, scale,
                                 rpe_table, grid, pos_bnd, drpe_table, out, dout, ldo, lse, dq, dk, dv, lddq, lddk, lddv, drop_p,
                                 seed, layer_id, stream_);

@@ -165,3 +165,41 @@ def test_pointwise_dropout_colsum_bf16_vectorised():
     L.lotus_colsum_bf16(P(x), 3000, 256, P(out), None)
     torch.cuda.synchronize()
     assert rel(out, x.float().sum(0)) < 1e-4
+
+
+@pytest.mark.parametrize("H,D,drop_p", [(2, 32, 0.0), (4, 32, 0.1), (32, 24, 0.1), (2, 16, 0.0), (2, 64, 0.1), (3, 8, 0.0)])
+def test_patch_attention_tensor_core_vs_simt(H, D, drop_p):
+    """tcgen05 patch attention (attention_tc.cu) against the SIMT kernel on the same bf16 inputs, same dropout mask:
+    ragged clouds (short patches, a one-point cloud, padded tail with alias slots), forward and backward"""
+    import os
+    ops, tk = pkg("ops"), pkg("tokenizer")
+    from test_gpu_parity import lattice_clouds
+    sizes = [300, 90, 129, 1, 128, 400]
+    coord, grid = lattice_clouds(sizes, 24, 6)
+    stg = tk.tokenize(coord.to(DEV), sizes, ["hilbert"], [2], [128, 128], [[0], [0]], None)[0]
+    C = H * D
+    g = torch.Generator().manual_seed(H * 100 + D)
+    qkv = bf(torch.randn(sum(sizes), 3 * C, generator=g) * 1.5).to(DEV)
+    qg, qb = (1 + 0.1 * torch.randn(D, generator=g)).to(DEV), (0.1 * torch.randn(D, generator=g)).to(DEV)
+    kg, kb = (1 + 0.1 * torch.randn(D, generator=g)).to(DEV), (0.1 * torch.randn(D, generator=g)).to(DEV)
+    go = bf(torch.randn(sum(sizes), C, generator=g)).to(DEV)
+    res = {}
+    for mode in ("simt", "tc"):
+        if mode == "simt":
+            os.environ["LOTUS_ATTN_SIMT"] = "1"
+        else:
+            os.environ.pop("LOTUS_ATTN_SIMT", None)
+        x = qkv.clone().requires_grad_(True)
+        params = [t.clone().requires_grad_(True) for t in (qg, qb, kg, kb)]
+        y = ops.PatchAttnFn.apply(x, *params, None, stg.plans[0], H, True, (drop_p, 1234, 7), stg.grid, 15)
+        y.backward(go)
+        torch.cuda.synchronize()
+        res[mode] = (y.detach().float(), x.grad.float(), [p.grad.float() for p in params])
+    os.environ.pop("LOTUS_ATTN_SIMT", None)
+    ys, yt = res["simt"][0], res["tc"][0]
+    assert torch.isfinite(yt).all()
+    assert rel(yt, ys) < 2e-2, rel(yt, ys)
+    assert rel(res["tc"][1], res["simt"][1]) < 3e-2
+    # (k_norm.bias has a mathematically zero gradient -- softmax shift invariance -- so it is rounding noise on both sides)
+    for a, b in list(zip(res["tc"][2], res["simt"][2]))[:3]:
+        assert rel(a, b) < 3e-2
