@@ -371,6 +371,9 @@ __global__ void __launch_bounds__(128) k_cross_attn_bwd(
   float* dOs = Qs + (size_t)128 * DH;       // [128][DH]
   float* Ls = dOs + (size_t)128 * DH;       // [128]
   float* Ds = Ls + 128;                     // [128]
+  const int LP = L + 1;                     // padded row stride of the P / dS tiles
+  float* Ps = Ds + 128;                     // [128][LP] dropped probabilities (for dV)
+  float* dSs = Ps + (size_t)128 * LP;       // [128][LP] score gradients (for dK)
   for (int t = threadIdx.x; t < L * DH; t += blockDim.x) {
     int j = t / DH, d = t - j * DH;
     Ks[t] = ldf(k, (int64_t)(ts + j) * ldk + h * DH + d);
@@ -402,9 +405,15 @@ __global__ void __launch_bounds__(128) k_cross_attn_bwd(
       float s = 0.f, dp = 0.f;
 #pragma unroll
       for (int d = 0; d < DH; ++d) { s = fmaf(qr[d], Ks[j * DH + d], s); dp = fmaf(dor[d], Vs[j * DH + d], dp); }
-      float pij = __expf(s - li);
-      if (drop_p > 0.f) dp = dropout_keep(seed, sid, (uint32_t)(pt * 128 + j), drop_p) ? dp * keep_scale : 0.f;
+      float pij = __expf(s - li), pd = pij;
+      if (drop_p > 0.f) {
+        bool keep = dropout_keep(seed, sid, (uint32_t)(pt * 128 + j), drop_p);
+        pd = keep ? pij * keep_scale : 0.f;
+        dp = keep ? dp * keep_scale : 0.f;
+      }
       float ds = pij * (dp - di);
+      Ps[i * LP + j] = pd;
+      dSs[i * LP + j] = ds;
 #pragma unroll
       for (int d = 0; d < DH; ++d) aq[d] = fmaf(ds, Ks[j * DH + d], aq[d]);
     }
@@ -412,30 +421,16 @@ __global__ void __launch_bounds__(128) k_cross_attn_bwd(
     for (int d = 0; d < DH; ++d) dq[(int64_t)pt * lddq + h * DH + d] = aq[d] * scale;
   }
   __syncthreads();
-  // dK_j, dV_j : thread = token j, loops over the chunk's points
-  for (int j = threadIdx.x; j < L; j += blockDim.x) {
-    float kr[DH], vr[DH], ak[DH], av[DH];
-#pragma unroll
-    for (int d = 0; d < DH; ++d) { kr[d] = Ks[j * DH + d]; vr[d] = Vs[j * DH + d]; ak[d] = 0.f; av[d] = 0.f; }
+  // dK, dV: thread = (token j, channel d) pairs over the chunk's points, from the P / dS tiles of phase 1
+  for (int o = threadIdx.x; o < L * DH; o += blockDim.x) {
+    int j = o / DH, d = o - j * DH;
+    float ak = 0.f, av = 0.f;
     for (int ii = 0; ii < cn; ++ii) {
-      float s = 0.f, dp = 0.f;
-#pragma unroll
-      for (int d = 0; d < DH; ++d) { s = fmaf(Qs[ii * DH + d], kr[d], s); dp = fmaf(dOs[ii * DH + d], vr[d], dp); }
-      float pij = __expf(s - Ls[ii]), pd = pij;
-      if (drop_p > 0.f) {
-        bool keep = dropout_keep(seed, sid, (uint32_t)((ps + i0 + ii) * 128 + j), drop_p);
-        pd = keep ? pij * keep_scale : 0.f;
-        dp = keep ? dp * keep_scale : 0.f;
-      }
-      float ds = pij * (dp - Ds[ii]);
-#pragma unroll
-      for (int d = 0; d < DH; ++d) { ak[d] = fmaf(ds, Qs[ii * DH + d], ak[d]); av[d] = fmaf(pd, dOs[ii * DH + d], av[d]); }
+      ak = fmaf(dSs[ii * LP + j], Qs[ii * DH + d], ak);      // Qs already carries `scale`
+      av = fmaf(Ps[ii * LP + j], dOs[ii * DH + d], av);
     }
-#pragma unroll
-    for (int d = 0; d < DH; ++d) {
-      atomicAdd(&dk[(int64_t)(ts + j) * lddk + h * DH + d], ak[d]);
-      atomicAdd(&dv[(int64_t)(ts + j) * lddv + h * DH + d], av[d]);
-    }
+    atomicAdd(&dk[(int64_t)(ts + j) * lddk + h * DH + d], ak);
+    atomicAdd(&dv[(int64_t)(ts + j) * lddv + h * DH + d], av);
   }
 }
 
@@ -482,7 +477,7 @@ static int cross_bwd_impl(const void* q, int64_t ldq, const void* k, const void*
                           uint32_t layer_id, void* stream_) {
   cudaStream_t st = (cudaStream_t)stream_;
   if (B <= 0 || max_points <= 0) return 0;
-  size_t smem = (size_t)max_tokens * Dh * 8 + (size_t)128 * Dh * 8 + 1024;
+  size_t smem = (size_t)max_tokens * Dh * 8 + (size_t)128 * Dh * 8 + 1024 + (size_t)128 * (max_tokens + 1) * 8;
   LOTUS_CHECK_ARG(smem <= 200 * 1024, "lotus_cross_attn_bwd: %d tokens x head_dim %d exceeds shared memory", max_tokens, Dh);
   dim3 grid(ceil_div(max_points, 128), B, H);
   DISPATCH_DH(Dh, {

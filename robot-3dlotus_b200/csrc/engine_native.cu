@@ -405,10 +405,19 @@ static Model build_model(const int64_t* cfg) {
   return m;
 }
 
+// weights to stage this step (flushed as ONE batched cast/transpose launch)
+struct StageList { std::vector<const void*> w; std::vector<void*> wb, wt; std::vector<int> A, D, B; };
+static StageList g_stage;
 static void stage_weight(Ctx& c, int idx, int A, int D, int Bdim) {
   c.WB[idx] = c.ar.alloc((size_t)A * D * Bdim * 2);
   c.WT[idx] = c.ar.alloc((size_t)A * D * Bdim * 2);
-  CALL(lotus_cast_transpose_bf16(Pf(c, idx), c.WB[idx], c.WT[idx], A, D, Bdim, c.stv));
+  g_stage.w.push_back(Pf(c, idx)); g_stage.wb.push_back(c.WB[idx]); g_stage.wt.push_back(c.WT[idx]);
+  g_stage.A.push_back(A); g_stage.D.push_back(D); g_stage.B.push_back(Bdim);
+}
+static void stage_flush(Ctx& c) {
+  CALL(lotus_cast_transpose_batch_bf16(g_stage.w.data(), g_stage.wb.data(), g_stage.wt.data(), g_stage.A.data(), g_stage.D.data(),
+                                       g_stage.B.data(), (int)g_stage.w.size(), c.stv));
+  g_stage = StageList();
 }
 static void stage_lin(Ctx& c, const Lin& l) { stage_weight(c, l.w, l.out, 1, l.in); }
 static void stage_block(Ctx& c, const BlockP& b) {
@@ -469,6 +478,7 @@ LOTUS_API int lotus_policy_step(const int64_t* cfg, const int64_t* run, const in
       if (s < S - 1) { stage_lin(c, m.unpool[s].proj); stage_lin(c, m.unpool[s].skip); stage_block(c, m.decB[s]); stage_ca(c, m.decCA[s]); }
     }
     stage_lin(c, m.txt_fc); stage_lin(c, m.hm0); stage_lin(c, m.am0);
+    stage_flush(c);
   }
   const int N0 = sg[0].n, Lt = c.Lt;
   // ---------------- context tokens

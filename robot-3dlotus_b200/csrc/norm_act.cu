@@ -778,6 +778,71 @@ LOTUS_API int lotus_cast_transpose_bf16(const float* w, void* w_bf16, void* wt_b
   return 0;
 }
 
+// batched form: every weight of the model in ONE launch (the per-weight launches were latency-bound: 114 per step)
+struct CastBatch {
+  static constexpr int MAX = 128;
+  const float* w[MAX];
+  bf16_t* wb[MAX];
+  bf16_t* wt[MAX];
+  int A[MAX], D[MAX], B[MAX];
+  int tile_start[MAX + 1];   // prefix sum of 32x32 tiles (x D) per entry
+  int n;
+};
+__global__ void k_cast_transpose_batch(const __grid_constant__ CastBatch cb) {
+  __shared__ float tile[32][33];
+  int tid = blockIdx.x;
+  int lo = 0, hi = cb.n - 1;
+  while (lo < hi) {
+    int mid = (lo + hi) >> 1;
+    if (cb.tile_start[mid + 1] > tid) hi = mid; else lo = mid + 1;
+  }
+  const int e = lo, A = cb.A[e], D = cb.D[e], B = cb.B[e];
+  const float* __restrict__ w = cb.w[e];
+  bf16_t* __restrict__ wb = cb.wb[e];
+  bf16_t* __restrict__ wt = cb.wt[e];
+  int local = tid - cb.tile_start[e];
+  int tb = (B + 31) >> 5, ta = (A + 31) >> 5;
+  int d = local / (ta * tb);
+  local -= d * ta * tb;
+  int a0 = (local / tb) * 32, b0 = (local % tb) * 32;
+  int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
+  for (int i = ty; i < 32; i += 8) {
+    int a = a0 + i, b = b0 + tx;
+    float v = 0.f;
+    if (a < A && b < B) {
+      v = w[((int64_t)a * D + d) * B + b];
+      if (wb) wb[((int64_t)a * D + d) * B + b] = __float2bfloat16(v);
+    }
+    tile[i][tx] = v;
+  }
+  __syncthreads();
+  if (wt) {
+    for (int i = ty; i < 32; i += 8) {
+      int b = b0 + i, a = a0 + tx;
+      if (a < A && b < B) wt[((int64_t)b * D + d) * A + a] = __float2bfloat16(tile[tx][i]);
+    }
+  }
+}
+// host arrays of n entries (w fp32 [A][D][B] -> w_bf16 same layout, wt_bf16 [B][D][A]; either output pointer may be null)
+LOTUS_API int lotus_cast_transpose_batch_bf16(const void* const* w, void* const* w_bf16, void* const* wt_bf16, const int* A,
+                                              const int* D, const int* B, int n, void* stream_) {
+  for (int base = 0; base < n; base += CastBatch::MAX) {
+    CastBatch cb;
+    cb.n = min(CastBatch::MAX, n - base);
+    cb.tile_start[0] = 0;
+    for (int i = 0; i < cb.n; ++i) {
+      int j = base + i;
+      LOTUS_CHECK_ARG(A[j] > 0 && B[j] > 0 && D[j] > 0, "lotus_cast_transpose_batch_bf16: empty weight %d", j);
+      cb.w[i] = (const float*)w[j]; cb.wb[i] = (bf16_t*)w_bf16[j]; cb.wt[i] = (bf16_t*)wt_bf16[j];
+      cb.A[i] = A[j]; cb.D[i] = D[j]; cb.B[i] = B[j];
+      cb.tile_start[i + 1] = cb.tile_start[i] + ceil_div(A[j], 32) * ceil_div(B[j], 32) * D[j];
+    }
+    if (cb.tile_start[cb.n] > 0) k_cast_transpose_batch<<<cb.tile_start[cb.n], 256, 0, (cudaStream_t)stream_>>>(cb);
+  }
+  LOTUS_CUDA_OK();
+  return 0;
+}
+
 // dropout: y = keep(seed, stream_id, i) ? x / (1-p) : 0 — the same call with dy gives the backward
 template <typename T>
 __global__ void k_dropout(const T* __restrict__ x, T* __restrict__ y, int64_t n, float p, uint64_t seed, uint32_t stream_id) {

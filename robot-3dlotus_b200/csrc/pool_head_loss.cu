@@ -7,6 +7,7 @@
 //   argmax decode + euler bins -> quaternion .... simple_policy_ptv3.py:250-295, action_position_utils.py:48-60,
 //                                                 rotation_transform.py:192-193
 #include "common.cuh"
+#include <cooperative_groups.h>
 
 // out[m, c] = max_{j in [ptr[m], ptr[m+1])} x[member ? member[j] : j, c]; arg[m, c] = winning source row
 template <typename T>
@@ -140,13 +141,21 @@ LOTUS_API int lotus_unpool_add_bf16(const void* skip, const void* child, const i
 // s_pos = gout[0] + gout[3]*pos_w (gout = upstream gradient of {pos, rot, open, total}; null -> {0,0,0,1}).
 // Trajectory form (motion planner, motion_planner_ptv3.py:326-337): T steps -> 3*T axes per cloud (axis a = t*3 + c,
 // logits row width 3*T*NB), row weight mask[b,t] / (3 * sum_t mask[b,t] * B); `total_idx` = index of the total in gout.
-__global__ void k_pos_ce(const float* __restrict__ logits, const float* __restrict__ prob,
+// A thread-block cluster of POS_CE_CLUSTER CTAs shares one (cloud, axis): each CTA reduces a slice of the n_b*NB logits, the
+// partial (max, sum-exp, sum p, sum p*x) are combined through distributed shared memory, and every CTA writes the gradient
+// of its own slice (one (cloud, axis) per CTA left 96 CTAs on 148 SMs for the production batch).
+constexpr int POS_CE_CLUSTER = 8;
+__global__ void __launch_bounds__(256) k_pos_ce(const float* __restrict__ logits, const float* __restrict__ prob,
                          const int32_t* __restrict__ off, int B, int NB, float* __restrict__ loss_accum,
                          float* __restrict__ dlogits, const float* __restrict__ gout, float pos_w, int T,
                          const float* __restrict__ mask, int total_idx) {
+  namespace cg = cooperative_groups;
+  cg::cluster_group cluster = cg::this_cluster();
+  const int rank = (int)cluster.block_rank(), CS = (int)cluster.num_blocks();
   float gscale = gout ? gout[0] + gout[total_idx] * pos_w : pos_w;
   __shared__ float red[32];
-  int b = blockIdx.x, c = blockIdx.y;
+  __shared__ float part[4];
+  int b = blockIdx.y, c = blockIdx.z;
   int s = off[b], n = off[b + 1] - s;
   int ld = 3 * T * NB;
   int tot = n * NB;
@@ -157,25 +166,55 @@ __global__ void k_pos_ce(const float* __restrict__ logits, const float* __restri
     wrow = mask[b * T + c / 3] / (3.f * len) / B;
   }
   const float* pb = prob + (int64_t)ld * s + (int64_t)c * tot;
+  const int chunk = (tot + CS - 1) / CS;
+  const int t0 = min(tot, rank * chunk), t1 = min(tot, t0 + chunk);
   float mx = -INFINITY;
-  for (int t = threadIdx.x; t < tot; t += blockDim.x) mx = fmaxf(mx, logits[(int64_t)(s + t / NB) * ld + c * NB + t % NB]);
+  for (int t = t0 + threadIdx.x; t < t1; t += blockDim.x) mx = fmaxf(mx, logits[(int64_t)(s + t / NB) * ld + c * NB + t % NB]);
   mx = block_max(mx, red);
   float se = 0.f, sp = 0.f, spx = 0.f;
-  for (int t = threadIdx.x; t < tot; t += blockDim.x) {
+  for (int t = t0 + threadIdx.x; t < t1; t += blockDim.x) {
     float x = logits[(int64_t)(s + t / NB) * ld + c * NB + t % NB];
     float p = pb[t];
     se += expf(x - mx); sp += p; spx += p * x;
   }
   se = block_sum(se, red); sp = block_sum(sp, red); spx = block_sum(spx, red);
-  float lse = mx + logf(se);
-  if (threadIdx.x == 0) atomicAdd(loss_accum, mask ? (lse * sp - spx) * wrow : (lse * sp - spx) / (3.f * B));
+  if (threadIdx.x == 0) { part[0] = mx; part[1] = se; part[2] = sp; part[3] = spx; }
+  cluster.sync();
+  float M = -INFINITY;
+  for (int r = 0; r < CS; ++r) M = fmaxf(M, cluster.map_shared_rank(part, r)[0]);
+  se = 0.f; sp = 0.f; spx = 0.f;
+  for (int r = 0; r < CS; ++r) {
+    const float* rp = cluster.map_shared_rank(part, r);
+    if (rp[1] > 0.f) se += rp[1] * expf(rp[0] - M);      // empty slices carry (max -inf, sum 0)
+    sp += rp[2]; spx += rp[3];
+  }
+  cluster.sync();                                          // peers may exit only after everyone has read their partials
+  float lse = M + logf(se);
+  if (threadIdx.x == 0 && rank == 0) atomicAdd(loss_accum, mask ? (lse * sp - spx) * wrow : (lse * sp - spx) / (3.f * B));
   if (dlogits) {
     float k = mask ? gscale * wrow : gscale / (3.f * B);
-    for (int t = threadIdx.x; t < tot; t += blockDim.x) {
+    for (int t = t0 + threadIdx.x; t < t1; t += blockDim.x) {
       int64_t o = (int64_t)(s + t / NB) * ld + c * NB + t % NB;
       dlogits[o] = k * (expf(logits[o] - lse) * sp - pb[t]);
     }
   }
+}
+static int launch_pos_ce(const float* logits, const float* prob, const int32_t* off, int B, int NB, float* loss_accum, float* dlogits,
+                         const float* gout, float pos_w, int T, const float* mask, int total_idx, cudaStream_t st) {
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = dim3(POS_CE_CLUSTER, B, 3 * T);
+  cfg.blockDim = dim3(256);
+  cfg.dynamicSmemBytes = 0;
+  cfg.stream = st;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeClusterDimension;
+  attr[0].val.clusterDim.x = POS_CE_CLUSTER;
+  attr[0].val.clusterDim.y = 1;
+  attr[0].val.clusterDim.z = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = 1;
+  LOTUS_CUDA_CALL(cudaLaunchKernelEx(&cfg, k_pos_ce, logits, prob, off, B, NB, loss_accum, dlogits, gout, pos_w, T, mask, total_idx));
+  return 0;
 }
 
 // rotation CE over 72 bins x 3 axes (logit index bin*3 + axis) + open BCE-with-logits on the last column.
@@ -225,7 +264,7 @@ LOTUS_API int lotus_policy_loss_f32(const float* heatmap_logits, const float* po
   cudaStream_t st = (cudaStream_t)stream_;
   LOTUS_CHECK_ARG(act_ld == rot_bins * 3 + 1, "lotus_policy_loss_f32: action width %d != %d*3+1", act_ld, rot_bins);
   LOTUS_CUDA_CALL(cudaMemsetAsync(losses, 0, 16, st));
-  k_pos_ce<<<dim3(B, 3), 256, 0, st>>>(heatmap_logits, pos_prob, cloud_off, B, NB, losses, d_heatmap, gout, pos_w, 1, nullptr, 3);
+  if (int rc = launch_pos_ce(heatmap_logits, pos_prob, cloud_off, B, NB, losses, d_heatmap, gout, pos_w, 1, nullptr, 3, st)) return rc;
   k_rot_open_loss<<<1, 256, 0, st>>>(action_logits, act_ld, gt_actions, gt_ld, B, rot_bins, losses, d_action, rot_w, gout);
   k_total_loss<<<1, 1, 0, st>>>(losses, pos_w, rot_w);
   LOTUS_CUDA_OK();
@@ -299,8 +338,7 @@ LOTUS_API int lotus_traj_loss_f32(const float* heatmap_logits, const float* pos_
   LOTUS_CHECK_ARG(act_ld == rot_bins * 3 + 2, "lotus_traj_loss_f32: action width %d != %d*3+2", act_ld, rot_bins);
   LOTUS_CHECK_ARG(B > 0 && T > 0, "lotus_traj_loss_f32: empty batch (B=%d, T=%d)", B, T);
   LOTUS_CUDA_CALL(cudaMemsetAsync(losses, 0, 20, st));
-  k_pos_ce<<<dim3(B, 3 * T), 256, 0, st>>>(heatmap_logits, pos_prob, cloud_off, B, NB, losses, d_heatmap, gout, pos_w, T,
-                                           traj_mask, 4);
+  if (int rc = launch_pos_ce(heatmap_logits, pos_prob, cloud_off, B, NB, losses, d_heatmap, gout, pos_w, T, traj_mask, 4, st)) return rc;
   k_traj_head_loss<<<1, 256, 0, st>>>(action_logits, act_ld, gt_trajs, gt_ld, stop_targets, traj_mask, B * T, rot_bins, losses,
                                       d_action, pos_w, rot_w, gout);
   LOTUS_CUDA_OK();

@@ -101,7 +101,7 @@ class FlatAdamW:
             sumsq = None
         L.lotus_adamw_step_f32(_p(self.flat_param), _p(self.flat_grad), _p(self.exp_avg), _p(self.exp_avg_sq), n,
                                _p(self.seg_end), _p(self.seg_wd), len(self.params), lr, self.betas[0], self.betas[1],
-                               self.eps, self.step_count, 1, sumsq, float(self.max_grad_norm or 0.0), scale, st)
+                               self.eps, self.step_count, 1 | 2, sumsq, float(self.max_grad_norm or 0.0), scale, st)   # 1: bias correction, 2: slots are 4-aligned
 
     def grad_norm(self):
         """global gradient norm of the last step (after the all-reduce mean) — one D2H read"""

@@ -64,6 +64,7 @@ DOC = {
     "lotus_convert": "fp32 <-> bf16 conversion between the fp32 head/loss tensors and the bf16 trunk.",
     "lotus_convert_rows_f32_to_bf16": "strided fp32 -> bf16 row copy (attention dV into the packed dqkv gradient): model.py:541 (torch.stack of q,k,v) in reverse.",
     "lotus_cast_transpose_bf16": "stages fp32 master weights for the tensor-core path: bf16 copy and [B][D][A] transpose (nn.Linear / SubMConv3d weights).",
+    "lotus_cast_transpose_batch_bf16": "All weights of the model staged for the tensor-core kernels in one launch (host arrays of per-weight pointers and extents); same per-weight semantics as lotus_cast_transpose_bf16.",
     "lotus_dropout_bf16": "bf16-activation form of lotus_dropout_f32.",
     "lotus_patch_attn_fwd_bf16": "bf16-activation form of lotus_patch_attn_fwd_f32: model.py:543-551.",
     "lotus_patch_attn_bwd_bf16": "bf16-activation form of lotus_patch_attn_bwd_f32 (fp32 gradient accumulators).",
