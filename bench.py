@@ -50,6 +50,11 @@ class ClockSampler:
         for line in self.proc.stdout:
             self.rows.append([c.strip() for c in line.split(",")])
 
+    def wait_first(self, timeout):
+        t0 = time.perf_counter()
+        while self.proc is not None and not self.rows and time.perf_counter() - t0 < timeout:
+            time.sleep(0.02)
+
     def stop(self):
         if self.proc is None:
             return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
@@ -89,25 +94,94 @@ def kernels_of(name, args):
 GEMM_ARGS = {  # name -> (index of M, N, K in the argument list, bytes per element)
     "lotus_linear_fwd_f32": (5, 6, 7, 4), "lotus_linear_dgrad_f32": (4, 5, 6, 4), "lotus_linear_wgrad_f32": (3, 4, 5, 4),
     "lotus_linear_fwd_bf16": (6, 7, 8, 2), "lotus_linear_dgrad_bf16": (4, 5, 6, 2), "lotus_linear_wgrad_bf16": (3, 4, 5, 2),
+    "lotus_linear_dgrad_act_bf16": (4, 5, 6, 2),
 }
 CONV_ARGS = {  # name -> index of n (then Cin, Cout, K3 follow)
-    "lotus_subm_conv_fwd_f32": 6, "lotus_subm_conv_dgrad_f32": 5, "lotus_subm_conv_wgrad_f32": 5,
-    "lotus_subm_conv_fwd_bf16": 6, "lotus_subm_conv_dgrad_bf16": 5, "lotus_subm_conv_wgrad_bf16": 5,
+    "lotus_subm_conv_fwd_f32": 6, "lotus_subm_conv_dgrad_f32": 6, "lotus_subm_conv_wgrad_f32": 5,
+    "lotus_subm_conv_fwd_bf16": 6, "lotus_subm_conv_dgrad_bf16": 6, "lotus_subm_conv_wgrad_bf16": 5,
+    "lotus_subm_conv_wgrad_pairs_bf16": 7,
+}
+# which device kernel a C-ABI family runs on (the roofline is reported per KERNEL: all launches of it in the step)
+KERNEL_OF = {
+    "lotus_linear_fwd_bf16": "tc::k_gemm_tc", "lotus_linear_dgrad_bf16": "tc::k_gemm_tc", "lotus_linear_wgrad_bf16": "tc::k_gemm_tc",
+    "lotus_linear_dgrad_act_bf16": "tc::k_gemm_tc",
+    "lotus_subm_conv_fwd_bf16": "tc::k_gemm_tc", "lotus_subm_conv_dgrad_bf16": "tc::k_gemm_tc",
+    "lotus_subm_conv_wgrad_pairs_bf16": "tc::k_gemm_tc", "lotus_subm_conv_wgrad_bf16": "tc::k_gemm_tc",
+    "lotus_patch_attn_fwd_bf16": "tca::k_patch_attn_fwd_tc", "lotus_patch_attn_bwd_bf16": "tca::k_patch_attn_bwd_tc",
 }
 
 
-def algorithmic_work(name, a, conv_pairs):
-    """-> (flops, bytes) of one call, from its arguments"""
+def algorithmic_work(name, a, ctx):
+    """-> (flops, bytes) of one C-ABI call, from its arguments (DESIGN.md section 4 states the formulas).
+    bytes = every operand read once + every result written once; flops = 2*M*N*K with the ACTUAL conv pair count."""
+    es = 2 if name.endswith("bf16") else 4
     if name in GEMM_ARGS:
         i, j, k, es = GEMM_ARGS[name]
         M, N, K = int(a[i]), int(a[j]), int(a[k])
-        return 2.0 * M * N * K, float(es) * (M * K + N * K + M * N)
+        out_es = 4 if "wgrad" in name else es
+        if "dgrad_act" in name:        # dx[M,K] = (dy[M,N] @ w[N,K]) * gelu'(u[M,K])
+            return 2.0 * M * N * K, float(es) * (M * N + N * K + 2 * M * K)
+        if "wgrad" in name:            # dW[N,K] = dy[M,N]^T x[M,K]
+            return 2.0 * M * N * K, float(es) * (M * N + M * K) + 4.0 * N * K
+        extra = M * N * es if (name == "lotus_linear_fwd_bf16" and a[5]) else 0      # second (pre-activation) output
+        return 2.0 * M * N * K, float(es) * (M * K + N * K) + float(out_es) * M * N + extra
     if name in CONV_ARGS:
         i = CONV_ARGS[name]
         n, cin, cout, k3 = int(a[i]), int(a[i + 1]), int(a[i + 2]), int(a[i + 3])
-        pairs = conv_pairs.get((n, k3), n * k3)            # actual (voxel, neighbour) pairs, not n * k^3
-        es = 2 if name.endswith("bf16") else 4
-        return 2.0 * pairs * cin * cout, float(es) * (pairs * cin + n * cout + k3 * cin * cout)
+        n = ctx["n_of_upper"].get(n, n)
+        pairs = ctx["conv_pairs"].get((n, k3), n * k3)            # actual (voxel, neighbour) pairs, not n * k^3
+        wbytes = (4.0 if "wgrad" in name else es) * k3 * cin * cout
+        return 2.0 * pairs * cin * cout, float(es) * (n * cin + n * cout) + 4.0 * pairs + wbytes
+    if name.startswith("lotus_patch_attn"):
+        P, K, H, D = int(a[9]), int(a[10]), int(a[11]), int(a[12])
+        npad = ctx["npad_of_patches"].get(P, P * K)
+        C = H * D
+        if "fwd" in name:              # q,k,v read + o written, the two index tables, lse
+            return 4.0 * npad * K * C, float(es) * 4 * npad * C + 8.0 * npad + 4.0 * npad * H
+        # bwd: q,k,v,o,do read; dq,dk,dv written in fp32; S, dP, dV, dQ, dK contractions + S recompute
+        return 10.0 * npad * K * C, float(es) * 5 * npad * C + 12.0 * npad * C + 8.0 * npad + 4.0 * npad * H
+    if name.startswith("lotus_cross_attn"):
+        B, H, D = int(a[8]), int(a[11]), int(a[12])
+        n = ctx["n_of_cloud_off"].get(int(a[6].value if hasattr(a[6], "value") else a[6] or 0), 0)
+        C = H * D
+        Lt = ctx["Lt"]
+        if "fwd" in name:
+            return 4.0 * n * (Lt / max(B, 1)) * C, float(es) * (2 * n * C + 2 * Lt * C) + 4.0 * n * H
+        return 8.0 * n * (Lt / max(B, 1)) * C, float(es) * (3 * n * C + 2 * Lt * C) + 4.0 * n * C + 8.0 * Lt * C + 4.0 * n * H
+    if name.startswith("lotus_layernorm_fwd"):
+        rows, C = int(a[13]), int(a[14])
+        return 0.0, float(es) * rows * C * (2 + (1 if a[8] else 0)) + 8.0 * rows
+    if name.startswith("lotus_layernorm_bwd"):
+        o = 1 if name.endswith("bf16") else 0
+        rows, C, acc = int(a[17 + o]), int(a[18 + o]), int(a[19 + o])
+        dyes = 4 if (o and int(a[1])) else es
+        return 0.0, rows * C * (float(dyes) + es + es * (2 if acc else 1)) + 8.0 * rows
+    if name.startswith("lotus_pointwise"):
+        n = int(a[3])
+        return 0.0, float(es) * n * (2 + (1 if a[1] else 0))
+    if name.startswith("lotus_dropout"):
+        return 0.0, float(es) * int(a[2]) * 2
+    if name.startswith("lotus_colsum"):
+        return 0.0, float(es) * int(a[1]) * int(a[2])
+    if name.startswith("lotus_batchnorm_fwd"):
+        o = 1 if name.endswith("bf16") else 0
+        rows, C = int(a[2 + o]), int(a[3 + o])
+        xes = 4 if (o and int(a[1])) else es
+        return 0.0, rows * C * (2.0 * xes + es)                   # statistics pass + apply pass (x read twice, y written)
+    if name.startswith("lotus_batchnorm_bwd"):
+        o = 1 if name.endswith("bf16") else 0
+        rows, C = int(a[2 + o]), int(a[3 + o])
+        return 0.0, rows * C * (5.0 * es)                         # reduce pass (dy, x) + apply pass (dy, x -> dx)
+    if name == "lotus_adamw_step_f32":
+        return 0.0, 28.0 * int(a[4])                              # p, g, m, v read; p, m, v written
+    if name == "lotus_grad_sumsq_f32":
+        return 0.0, 4.0 * int(a[1])
+    if name.startswith("lotus_cast_transpose"):
+        return 0.0, 0.0
+    if name.startswith("lotus_convert_rows"):
+        return 0.0, 6.0 * int(a[4]) * int(a[5])
+    if name == "lotus_convert":
+        return 0.0, 6.0 * int(a[2])
     return 0.0, 0.0
 
 
@@ -132,26 +206,36 @@ class CallProfiler:
     def __exit__(self, *exc):
         self.lib.call = self.orig
 
-    def summary(self, conv_pairs):
+    def summary(self, ctx, tf_peak, hbm_peak):
+        """per C-ABI family: time, calls, algorithmic flops / bytes, and the roofline floor
+        sum(max(flops / tensor peak, bytes / HBM peak)) of its calls"""
         torch.cuda.synchronize()
         fam = {}
         for name, args, e0, e1 in self.records:
             ms = e0.elapsed_time(e1)
-            fl, by = algorithmic_work(name, args, conv_pairs)
-            d = fam.setdefault(name, {"ms": 0.0, "calls": 0, "flops": 0.0, "bytes": 0.0})
+            fl, by = algorithmic_work(name, args, ctx)
+            d = fam.setdefault(name, {"ms": 0.0, "calls": 0, "flops": 0.0, "bytes": 0.0, "floor_ms": 0.0, "t_flop_ms": 0.0, "t_byte_ms": 0.0})
             d["ms"] += ms
             d["calls"] += 1
             d["flops"] += fl
             d["bytes"] += by
+            tf, tb = fl / (tf_peak * 1e12) * 1e3, by / (hbm_peak * 1e9) * 1e3
+            d["floor_ms"] += max(tf, tb)
+            d["t_flop_ms"] += tf
+            d["t_byte_ms"] += tb
         return fam
 
 
 # ------------------------------------------------------------------------------------------------ workloads
-def pack_batch(batch, pin):
-    """collate-side packing (what the reference's DataLoader workers + pin_memory do): soft labels into one buffer"""
+def pack_batch(batch, pin, labels="host"):
+    """collate-side packing (what the reference's DataLoader workers + pin_memory do): soft labels into one buffer, or
+    (labels == "device") left out of the batch: lotus_disc_pos_prob produces them on the GPU from (xyz, gt_actions)"""
     b = dict(batch)
-    b["disc_pos_probs_packed"] = torch.cat([p.reshape(-1) for p in batch["disc_pos_probs"]])
-    del b["disc_pos_probs"]
+    if labels == "device":
+        b.pop("disc_pos_probs", None)
+    if "disc_pos_probs" in b:
+        b["disc_pos_probs_packed"] = torch.cat([p.reshape(-1) for p in batch["disc_pos_probs"]])
+        del b["disc_pos_probs"]
     if pin:
         for k, v in b.items():
             if isinstance(v, torch.Tensor):
@@ -213,6 +297,11 @@ def main():
     ap.add_argument("--batch", type=int, default=32, help="keysteps per GPU per step (BASELINE configs[1]: 32)")
     ap.add_argument("--cpu-sample-batch", type=int, default=2)
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--labels", default="device", choices=["device", "host"],
+                    help="soft position labels: produced on the GPU from (xyz, gt_actions) [lotus_disc_pos_prob], or shipped from the host "
+                         "like the reference's collate does (36 MB of the 39 MB per step)")
+    ap.add_argument("--no-inference", action="store_true", help="skip the p50 inference-latency section")
+    ap.add_argument("--infer-iters", type=int, default=100)
     ap.add_argument("--engine", default="native", choices=["native", "python"],
                     help="native: one C++ call per step (lotus_policy_step); python: per-op autograd Functions over the same kernels")
     ap.add_argument("--precision", default="bf16", choices=["bf16", "fp32"],
@@ -250,7 +339,7 @@ def main():
     model.engine().use_native = args.engine == "native"
     step_fn = trainer.TrainStep(model)
     nb = 4
-    host = [pack_batch(syn.make_batch(seed=2024 + 100 * rank + i, batch_size=args.batch), pin=True) for i in range(nb)]
+    host = [pack_batch(syn.make_batch(seed=2024 + 100 * rank + i, batch_size=args.batch), pin=True, labels=args.labels) for i in range(nb)]
     resident = [to_device(b, dev) for b in host]
     torch.cuda.synchronize()
 
@@ -260,12 +349,20 @@ def main():
         torch.cuda.synchronize()
 
     # ---- device-resident throughput
-    for i in range(args.warmup):
-        step_fn(dict(resident[i % nb]))
-    barrier()
+    # (nvidia-smi attaches to the driver while the warm-up runs: its start-up stalls CUDA launches for ~100 ms, which
+    #  must not land inside the timed region)
     sampler = ClockSampler(local)
     if rank == 0:
         sampler.start()
+    for i in range(max(args.warmup, nb)):            # every rotating batch is seen once (arena sized) before timing
+        step_fn(dict(resident[i % nb]))
+    if rank == 0:
+        sampler.wait_first(5.0)
+    for i in range(3):                               # settle after the sampler attached (untimed)
+        step_fn(dict(resident[i % nb]))
+    if rank == 0:
+        sampler.rows.clear()
+    barrier()
     calls0 = L.launches
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     e0.record()
@@ -308,16 +405,6 @@ def main():
     with prof:
         step_fn(dict(resident[0]))
     model.engine().use_native = args.engine == "native"
-    conv_pairs = {}
-    for stg in model.engine().last_stages:                     # actual (voxel, neighbour) pairs -> algorithmic conv FLOPs
-        conv_pairs[(stg.n, 27)] = int((stg.nbr3[:, : stg.n] >= 0).sum())
-        if stg.nbr5 is not None:
-            conv_pairs[(stg.n, 125)] = int((stg.nbr5[:, : stg.n] >= 0).sum())
-    fam = prof.summary(conv_pairs)
-    for name, args_, _, _ in prof.records:
-        kernel_count[0] += kernels_of(name, args_)
-    tot_ms = sum(d["ms"] for d in fam.values())
-    top = sorted(fam.items(), key=lambda kv: -kv[1]["ms"])
     peaks = {}
     try:
         peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
@@ -325,20 +412,101 @@ def main():
         pass
     tf_peak = peaks.get("bf16_tflops_sustained", 1400.0)
     hbm_peak = peaks.get("hbm_gbs", 6650.0)
-    peak_src = "measured (MEASURED_PEAKS.json, sustained bf16 GEMM)" if peaks else "fallback (B200_PROFILING.md)"
-    dom_name, dom = top[0]
-    per_launch_ms = dom["ms"] / dom["calls"]
-    if dom["flops"] > 0:
-        ach = dom["flops"] / dom["calls"] / (per_launch_ms * 1e-3) / 1e12
-        roof = {"bound": "tensor", "kernel": dom_name, "achieved": ach, "peak": tf_peak, "unit": "TFLOP/s", "frac": ach / tf_peak,
-                "traffic": None, "share_of_step": dom["ms"] / tot_ms, "launches_per_step": dom["calls"], "peak_source": peak_src,
-                "note": ("tcgen05 bf16 kernel" if args.precision == "bf16" else "fp32 SIMT validation-mode GEMM") +
-                        " measured against the sustained bf16 tensor peak; achieved = algorithmic FLOPs / CUDA-event time"}
-    else:
-        roof = {"bound": "hbm", "kernel": dom_name, "achieved": None, "peak": hbm_peak, "unit": "GB/s", "frac": None, "traffic": None,
-                "share_of_step": dom["ms"] / tot_ms, "launches_per_step": dom["calls"], "peak_source": peak_src}
+    peak_src = "measured (MEASURED_PEAKS.json: hbm_gbs / bf16_tflops_sustained)" if peaks else "fallback (B200_PROFILING.md)"
+    stages = model.engine().last_stages
+    ctx = {"conv_pairs": {}, "n_of_upper": {}, "npad_of_patches": {}, "n_of_cloud_off": {}, "Lt": int(sum(int(l) for l in resident[0]["txt_lens"]))}
+    for stg in stages:                                         # actual (voxel, neighbour) pairs -> algorithmic conv FLOPs
+        ctx["conv_pairs"][(stg.n, 27)] = int((stg.nbr3[:, : stg.n] >= 0).sum())
+        if stg.nbr5 is not None:
+            ctx["conv_pairs"][(stg.n, 125)] = int((stg.nbr5[:, : stg.n] >= 0).sum())
+        pl = next(iter(stg.plans.values()))
+        ctx["npad_of_patches"][pl.n_patches] = pl.n_pad
+        ctx["n_of_cloud_off"][stg.cloud_off.data_ptr()] = stg.n
+    fam = prof.summary(ctx, tf_peak, hbm_peak)
+    for name, args_, _, _ in prof.records:
+        kernel_count[0] += kernels_of(name, args_)
+    tot_ms = sum(d["ms"] for d in fam.values())
+    top = sorted(fam.items(), key=lambda kv: -kv[1]["ms"])
+    # group the families by the device kernel they launch; the roofline object describes the dominant KERNEL
+    byk = {}
+    for name, d in fam.items():
+        k = KERNEL_OF.get(name, name)
+        g = byk.setdefault(k, {"ms": 0.0, "calls": 0, "flops": 0.0, "bytes": 0.0, "floor_ms": 0.0, "t_flop_ms": 0.0, "t_byte_ms": 0.0, "families": []})
+        for f in ("ms", "calls", "flops", "bytes", "floor_ms", "t_flop_ms", "t_byte_ms"):
+            g[f] += d[f]
+        g["families"].append(name)
+    traffic_db = {}
+    try:
+        traffic_db = json.load(open(os.path.join(ROOT, "profiles", "ncu_traffic.json")))
+    except Exception:
+        pass
+
+    def roofline_of(kname, g):
+        hbm_bound = g["t_byte_ms"] >= g["t_flop_ms"]
+        per_launch_s = g["ms"] * 1e-3 / max(g["calls"], 1)
+        if hbm_bound:
+            ach = g["bytes"] / max(g["calls"], 1) / per_launch_s / 1e9
+            peak, unit = hbm_peak, "GB/s"
+        else:
+            ach = g["flops"] / max(g["calls"], 1) / per_launch_s / 1e12
+            peak, unit = tf_peak, "TFLOP/s"
+        tr = traffic_db.get(kname, {})
+        return {"bound": "hbm" if hbm_bound else "tensor", "kernel": kname, "achieved": ach, "peak": peak, "unit": unit,
+                "frac": ach / peak, "traffic": tr.get("dram_bytes_per_launch"), "traffic_source": tr.get("source"),
+                "algorithmic_bytes_per_launch": g["bytes"] / max(g["calls"], 1),
+                "algorithmic_flops_per_launch": g["flops"] / max(g["calls"], 1),
+                "avg_launch_us": 1e3 * g["ms"] / max(g["calls"], 1), "launches_per_step": g["calls"],
+                "share_of_step": g["ms"] / tot_ms, "frac_of_mixed_roofline": g["floor_ms"] / g["ms"] if g["ms"] else None,
+                "families": sorted(g["families"]), "peak_source": peak_src,
+                "note": "achieved = algorithmic bytes (or FLOPs) of all launches of this kernel in one step / their summed CUDA-event time; "
+                        "bound = whichever of bytes/HBM-peak and FLOPs/tensor-peak is larger summed over those launches; "
+                        "frac_of_mixed_roofline = sum over launches of max(bytes/HBM peak, FLOPs/tensor peak) / measured time"}
+
+    dom_name, dom = max(byk.items(), key=lambda kv: kv[1]["ms"])
+    roof = roofline_of(dom_name, dom)
+    # the attention block (north star: "achieved fraction of the attention-block roofline"): patch self-attention fwd + bwd
+    attn = {"ms": 0.0, "calls": 0, "flops": 0.0, "bytes": 0.0, "floor_ms": 0.0, "t_flop_ms": 0.0, "t_byte_ms": 0.0, "families": []}
+    for name, d in fam.items():
+        if name.startswith("lotus_patch_attn"):
+            for f in ("ms", "calls", "flops", "bytes", "floor_ms", "t_flop_ms", "t_byte_ms"):
+                attn[f] += d[f]
+            attn["families"].append(name)
+    attn_roof = roofline_of("patch_attention(fwd+bwd)", attn) if attn["calls"] else None
     kernels = [{"call": k, "share": round(d["ms"] / tot_ms, 4), "ms_per_step": round(d["ms"], 3), "calls": d["calls"],
-                "tflops": round(d["flops"] / (d["ms"] * 1e-3) / 1e12, 2) if d["flops"] else None} for k, d in top[:40]]
+                "tflops": round(d["flops"] / (d["ms"] * 1e-3) / 1e12, 2) if d["flops"] else None,
+                "gbs": round(d["bytes"] / (d["ms"] * 1e-3) / 1e9, 1) if d["bytes"] else None,
+                "frac_of_roofline": round(d["floor_ms"] / d["ms"], 4) if d["ms"] and d["floor_ms"] else None} for k, d in top[:40]]
+
+    # ---- inference latency (BASELINE metric, second half): p50 ms per keystep, eval mode, compute_final_action=True,
+    # pinned host batch -> H2D -> forward -> D2H of the (B,8) action, one keystep of <=4096 points per call
+    infer = None
+    if not args.no_inference:
+        model.eval()
+        ib = [pack_batch(syn.make_batch(seed=4000 + i, sizes=[4096], with_targets=False), pin=True) for i in range(4)]
+        lat = []
+        with torch.no_grad():
+            for i in range(10 + args.infer_iters):
+                t0 = time.perf_counter()
+                act = model(dict(ib[i % 4]), compute_loss=False, compute_final_action=True)
+                act_h = act.cpu()
+                dt = time.perf_counter() - t0
+                if i >= 10:
+                    lat.append(dt * 1e3)
+        lat.sort()
+        bb = [pack_batch(syn.make_batch(seed=5000 + i, batch_size=args.batch, with_targets=False), pin=True) for i in range(2)]
+        with torch.no_grad():
+            for i in range(3):
+                model(dict(bb[i % 2]), compute_loss=False, compute_final_action=True)
+            torch.cuda.synchronize()
+            t0 = time.perf_counter()
+            for i in range(10):
+                act_h = model(dict(bb[i % 2]), compute_loss=False, compute_final_action=True).cpu()
+            tb = (time.perf_counter() - t0) / 10
+        infer = {"p50_ms_per_keystep": lat[len(lat) // 2], "p90_ms_per_keystep": lat[int(len(lat) * 0.9)], "batch": 1,
+                 "points": int(ib[0]["pc_fts"].shape[0]), "iters": len(lat), "timing": "host wall clock around model(batch).cpu(), pinned host inputs",
+                 "batched": {"batch": args.batch, "ms_per_call": tb * 1e3, "ms_per_keystep": tb * 1e3 / args.batch,
+                             "keysteps_per_s": args.batch / tb}}
+        model.train()
 
     cpu = None
     if not args.no_cpu_baseline and world == 1:
@@ -351,6 +519,8 @@ def main():
         "dtype": "bf16" if args.precision == "bf16" else "fp32", "data": "synthetic",
         "config": {"workload": workload, "global_batch": args.batch * world, "parallelism": f"dp{world}",
                    "l2": "4 rotating input batches; per-step working set (1.1 GB params+grads+Adam state, multi-GB activations) exceeds the 126 MB L2",
+                   "labels": ("soft position labels produced on the device from (xyz, gt_actions) inside the step" if args.labels == "device"
+                              else "soft position labels shipped from the host with the batch (reference collate layout)"),
                    "precision_note": ("bf16 activations + tcgen05 tensor-core GEMM/conv, fp32 master weights/statistics/gradients"
                                       if args.precision == "bf16" else "fp32 validation-mode kernels (1e-4 parity path)")},
         "clocks": clocks,
@@ -359,7 +529,7 @@ def main():
         "gpu_launches": int(round(kernel_count[0] * args.steps)), "c_abi_calls_per_step": calls_per_step,
         "native_launcher_calls_per_step": native_calls, "engine": args.engine,
         "host_enqueue_ms_per_step": 1e3 * t_host / args.steps, "kernel_ms_per_step_profiled": tot_ms,
-        "roofline": roof, "kernels": kernels, "cpu_baseline": cpu, "loss": loss_host,
+        "roofline": roof, "attention_block": attn_roof, "inference": infer, "kernels": kernels, "cpu_baseline": cpu, "loss": loss_host,
     }
     print(json.dumps(line))
     if world > 1:

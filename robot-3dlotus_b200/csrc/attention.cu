@@ -8,6 +8,16 @@
 #include "common.cuh"
 
 // tensor-core variants (attention_tc.cu)
+// warp-mma cross attention (cross_attn_mma.cu)
+bool lotus_cross_attn_mma_ok(const void* q, const void* k, const void* v, const void* out, int64_t ldq, int64_t ldk, int64_t ldv,
+                             int64_t ldo, int Dh, int max_tokens);
+int lotus_cross_attn_fwd_mma(const void* q, int64_t ldq, const void* k, const void* v, int64_t ldk, int64_t ldv, const int32_t* pt_off,
+                             const int32_t* tok_off, int B, int max_points, int max_tokens, int H, int Dh, float scale, void* out,
+                             int64_t ldo, float* lse, float drop_p, uint64_t seed, uint32_t layer_id, void* stream_);
+int lotus_cross_attn_bwd_mma(const void* q, int64_t ldq, const void* k, const void* v, int64_t ldk, int64_t ldv, const int32_t* pt_off,
+                             const int32_t* tok_off, int B, int max_points, int max_tokens, int H, int Dh, float scale, const void* out,
+                             const void* dout, int64_t ldo, const float* lse, float* dq, int64_t lddq, float* dk, float* dv,
+                             int64_t lddk, int64_t lddv, float drop_p, uint64_t seed, uint32_t layer_id, void* stream_);
 bool lotus_patch_attn_tc_ok(const void* q, const void* k, const void* v, int64_t ldq, int64_t ldk, int64_t ldv, const void* out,
                             int64_t ldo, int max_len, int Dh, const float* rpe_table);
 int lotus_patch_attn_fwd_tc(const void* q, const void* k, const void* v, int64_t ldq, int64_t ldk, int64_t ldv,
@@ -464,6 +474,9 @@ LOTUS_API int lotus_cross_attn_fwd_bf16(const void* q, int64_t ldq, const void* 
                                         const int32_t* pt_off, const int32_t* tok_off, int B, int max_points, int max_tokens,
                                         int H, int Dh, float scale, void* out, int64_t ldo, float* lse, float drop_p,
                                         uint64_t seed, uint32_t layer_id, void* stream_) {
+  if (lotus_cross_attn_mma_ok(q, k, v, out, ldq, ldk, ldv, ldo, Dh, max_tokens))                 // warp-mma path (cross_attn_mma.cu)
+    return lotus_cross_attn_fwd_mma(q, ldq, k, v, ldk, ldv, pt_off, tok_off, B, max_points, max_tokens, H, Dh, scale, out, ldo, lse,
+                                    drop_p, seed, layer_id, stream_);
   return cross_fwd_impl<bf16_t>(q, ldq, k, v, ldk, ldv, pt_off, tok_off, B, max_points, max_tokens, H, Dh, scale, out, ldo, lse,
                                 drop_p, seed, layer_id, stream_);
 }
@@ -503,6 +516,10 @@ LOTUS_API int lotus_cross_attn_bwd_bf16(const void* q, int64_t ldq, const void* 
                                         int H, int Dh, float scale, const void* out, const void* dout, int64_t ldo,
                                         const float* lse, float* dq, int64_t lddq, float* dk, float* dv, int64_t lddk,
                                         int64_t lddv, float drop_p, uint64_t seed, uint32_t layer_id, void* stream_) {
+  if (lotus_cross_attn_mma_ok(q, k, v, out, ldq, ldk, ldv, ldo, Dh, max_tokens) && ((uintptr_t)dout & 3) == 0 &&
+      ((uintptr_t)dq & 7) == 0 && lddq % 2 == 0)
+    return lotus_cross_attn_bwd_mma(q, ldq, k, v, ldk, ldv, pt_off, tok_off, B, max_points, max_tokens, H, Dh, scale, out, dout, ldo,
+                                    lse, dq, lddq, dk, dv, lddk, lddv, drop_p, seed, layer_id, stream_);
   return cross_bwd_impl<bf16_t>(q, ldq, k, v, ldk, ldv, pt_off, tok_off, B, max_points, max_tokens, H, Dh, scale, out, dout, ldo,
                                 lse, dq, lddq, dk, dv, lddk, lddv, drop_p, seed, layer_id, stream_);
 }

@@ -14,6 +14,7 @@
 #include "common.cuh"
 #include "../../include/lotus.h"
 #include <vector>
+#include <stdlib.h>
 
 namespace eng {
 
@@ -45,6 +46,7 @@ struct StageInfo {
 
 struct Ctx {
   cudaStream_t st; void* stv; bool bf, train, dry; int es; Arena ar; int rc;
+  cudaStream_t side; void* sidev; bool side_busy;            // weight-gradient stream (null: everything on `st`)
   uint64_t seed; uint32_t drop_next; float attn_drop, proj_drop, head_drop;
   void* const* P; void* const* G; void* const* BN;          // fp32 params, grad sinks (may be null), BN running stats
   std::vector<void*> WB, WT;                                 // bf16 staged weights (by param index)
@@ -53,6 +55,27 @@ struct Ctx {
 
 static long long g_launcher_calls = 0;   // launcher invocations of the last non-dry step (each launches >= 1 kernel)
 #define CALL(expr) do { if (!c.dry && c.rc == 0 && !c.ar.overflow) { ++g_launcher_calls; int _r = (expr); if (_r) c.rc = _r; } } while (0)
+
+// Weight / bias gradients do not sit on the backward's critical path (the activation-gradient chain): they run on a
+// second stream so the small deep-stage kernels overlap.  fork: the side stream waits for everything issued so far on the
+// main stream; join: the main stream waits for the side stream (before arena memory the side kernels read is reused, or
+// a buffer they read is modified in place, and at the end of the step).
+static cudaStream_t g_side = nullptr;
+static cudaEvent_t g_ev_fork = nullptr, g_ev_join = nullptr;
+static inline bool live(Ctx& c) { return !c.dry && c.rc == 0 && !c.ar.overflow; }
+static void fork_side(Ctx& c) {
+  if (!c.side || !live(c)) return;
+  cudaEventRecord(g_ev_fork, c.st);
+  cudaStreamWaitEvent(c.side, g_ev_fork, 0);
+  c.side_busy = true;
+}
+static void join_side(Ctx& c) {
+  if (!c.side || !c.side_busy || c.dry) return;
+  cudaEventRecord(g_ev_join, c.side);
+  cudaStreamWaitEvent(c.st, g_ev_join, 0);
+  c.side_busy = false;
+}
+static inline void* gstream(Ctx& c) { return c.side ? c.sidev : c.stv; }   // stream of the weight-gradient kernels
 
 static inline float* Pf(Ctx& c, int i) { return i < 0 ? nullptr : (float*)c.P[i]; }
 static inline float* Gf(Ctx& c, int i) { return (i < 0 || !c.G) ? nullptr : (float*)c.G[i]; }
@@ -75,14 +98,16 @@ static void linear_fwd(Ctx& c, const void* x, int M, const Lin& l, const void* r
 // dy: gradient of the layer output AFTER its dropout (if any) has been applied to dy by the caller.
 // dx = [dx_residual +] dy @ W ; dW += dy^T x ; db += colsum(dy).   tc: operands are bf16 (tensor-core path)
 static void linear_bwd(Ctx& c, const void* dy, const void* x, int M, const Lin& l, void* dx, const void* dx_residual, bool tc) {
+  fork_side(c);                                  // dy (and x) are complete on the main stream at this point
+  void* gs = gstream(c);
   if (tc) {
+    if (Gf(c, l.w)) CALL(lotus_linear_wgrad_bf16(dy, x, Gf(c, l.w), M, l.out, l.in, gs));
+    if (Gf(c, l.b)) CALL(lotus_colsum_bf16(dy, M, l.out, Gf(c, l.b), gs));
     if (dx) CALL(lotus_linear_dgrad_bf16(dy, c.WT[l.w], dx_residual, dx, M, l.out, l.in, 0, c.stv));
-    if (Gf(c, l.w)) CALL(lotus_linear_wgrad_bf16(dy, x, Gf(c, l.w), M, l.out, l.in, c.stv));
-    if (Gf(c, l.b)) CALL(lotus_colsum_bf16(dy, M, l.out, Gf(c, l.b), c.stv));
   } else {
+    if (Gf(c, l.w)) CALL(lotus_linear_wgrad_f32((const float*)dy, (const float*)x, Gf(c, l.w), M, l.out, l.in, nullptr, gs));
+    if (Gf(c, l.b)) CALL(lotus_colsum_f32((const float*)dy, M, l.out, Gf(c, l.b), gs));
     if (dx) CALL(lotus_linear_dgrad_f32((const float*)dy, Pf(c, l.w), (const float*)dx_residual, (float*)dx, M, l.out, l.in, c.stv));
-    if (Gf(c, l.w)) CALL(lotus_linear_wgrad_f32((const float*)dy, (const float*)x, Gf(c, l.w), M, l.out, l.in, nullptr, c.stv));
-    if (Gf(c, l.b)) CALL(lotus_colsum_f32((const float*)dy, M, l.out, Gf(c, l.b), c.stv));
   }
 }
 // apply a dropout mask to a gradient (out of place into the arena) -- identity when the site is inactive
@@ -145,10 +170,16 @@ static void* mlp_fwd(Ctx& c, void* x2, int n, const Norm& n2, const Lin& fc1, co
   sv.h2 = act(c, n, C);
   ln_fwd(c, x2, sv.h2, nullptr, n2, sv.mean, sv.rstd, n, 1e-5f);
   sv.u = act(c, n, fc1.out);
-  linear_fwd(c, sv.h2, n, fc1, nullptr, sv.u, 0.f, 0);
   sv.g = act(c, n, fc1.out);
   sv.d_act = drop_id(c, c.proj_drop);
-  pointwise(c, sv.u, nullptr, sv.g, (int64_t)n * fc1.out, 0, c.proj_drop, sv.d_act, c.bf);
+  if (c.bf) {
+    // GELU + dropout fused into the GEMM epilogue; the pre-activation is a second TMA store (only kept when a backward follows)
+    CALL(lotus_linear_fwd_bf16(sv.h2, c.WB[fc1.w], Pf(c, fc1.b), nullptr, sv.g, c.G ? sv.u : nullptr, n, fc1.out, fc1.in, 1, 0,
+                               drop_p(c, c.proj_drop, sv.d_act), c.seed, sv.d_act, c.stv));
+  } else {
+    linear_fwd(c, sv.h2, n, fc1, nullptr, sv.u, 0.f, 0);
+    pointwise(c, sv.u, nullptr, sv.g, (int64_t)n * fc1.out, 0, c.proj_drop, sv.d_act, c.bf);
+  }
   void* x3 = act(c, n, C);
   sv.d_out = drop_id(c, c.proj_drop);
   linear_fwd(c, sv.g, n, fc2, x2, x3, c.proj_drop, sv.d_out);
@@ -157,15 +188,22 @@ static void* mlp_fwd(Ctx& c, void* x2, int n, const Norm& n2, const Lin& fc1, co
 // D holds d(x3) on entry and d(x2) on exit
 static void mlp_bwd(Ctx& c, void* D, int n, const Norm& n2, const Lin& fc1, const Lin& fc2, const MlpSave& sv) {
   int C = n2.C;
-  size_t mark = c.ar.off;
   const void* dyd = drop_grad(c, D, (int64_t)n * C, c.proj_drop, sv.d_out, c.bf);
   void* dg = act(c, n, fc1.out);
-  linear_bwd(c, dyd, sv.g, n, fc2, dg, nullptr, c.bf);
-  pointwise(c, sv.u, dg, dg, (int64_t)n * fc1.out, 1, c.proj_drop, sv.d_act, c.bf);      // du in place
+  if (c.bf) {
+    // du = drop'(gelu'(u)) * (dyd @ W2): the activation backward rides in the data-gradient GEMM's epilogue
+    linear_bwd(c, dyd, sv.g, n, fc2, nullptr, nullptr, true);                            // weight / bias gradients only
+    CALL(lotus_linear_dgrad_act_bf16(dyd, c.WT[fc2.w], sv.u, dg, n, fc2.out, fc2.in, 1, drop_p(c, c.proj_drop, sv.d_act), c.seed,
+                                     sv.d_act, c.stv));
+  } else {
+    linear_bwd(c, dyd, sv.g, n, fc2, dg, nullptr, false);
+    pointwise(c, sv.u, dg, dg, (int64_t)n * fc1.out, 1, c.proj_drop, sv.d_act, false);   // du in place
+  }
   void* dh2 = act(c, n, C);
   linear_bwd(c, dg, sv.h2, n, fc1, dh2, nullptr, c.bf);
+  if (dyd == D) join_side(c);                                                            // fc2's weight gradient reads D
   ln_bwd(c, dh2, sv.x2, D, n2, sv.mean, sv.rstd, n, 1);                                  // D += LN'(dh2)
-  c.ar.off = mark;
+  // temporaries are released by the caller (after its join with the weight-gradient stream)
 }
 
 // ------------------------------------------------------------------------------------------------ Block
@@ -214,10 +252,10 @@ static void* block_fwd(Ctx& c, const BlockP& b, const StageInfo& sg, void* x0, c
 // branch), its gradient is returned in *d_conv_in = D_after + conv dgrad (new arena buffer, NOT released here).
 static void block_bwd(Ctx& c, const BlockP& b, const StageInfo& sg, void* D, const BlockSave& sv, void** d_conv_in) {
   int n = sv.n, C = b.C, H = b.H, Dh = C / H;
-  mlp_bwd(c, D, n, b.n2, b.fc1, b.fc2, sv.mlp);                                          // D = d(x2)
   void* dconv = nullptr;
   if (sv.own_conv_in) dconv = act(c, n, C);                                              // survives the temporaries below
   size_t mark = c.ar.off;
+  mlp_bwd(c, D, n, b.n2, b.fc1, b.fc2, sv.mlp);                                          // D = d(x2)
   // attention branch
   const void* dyd = drop_grad(c, D, (int64_t)n * C, c.proj_drop, sv.d_proj, c.bf);
   void* dout = act(c, n, C);
@@ -251,6 +289,7 @@ static void block_bwd(Ctx& c, const BlockP& b, const StageInfo& sg, void* D, con
   }
   void* dh1 = act(c, n, C);
   linear_bwd(c, dqkv, sv.h1, n, b.qkv, dh1, nullptr, c.bf);
+  if (dyd == D) join_side(c);                                                            // proj's weight gradient reads D
   ln_bwd(c, dh1, sv.x1, D, b.n1, sv.n1_mean, sv.n1_rstd, n, 1);                          // D = d(x1)
   // CPE branch: x1 = x0 + LN(c1)
   void* dc1 = act(c, n, C);
@@ -259,15 +298,18 @@ static void block_bwd(Ctx& c, const BlockP& b, const StageInfo& sg, void* D, con
   linear_bwd(c, dc1, sv.c0, n, b.cpe1, dc0, nullptr, c.bf);
   // conv: dW, db, and the input gradient (into the residual stream, or into the separate conv-input gradient)
   void* dxo = sv.own_conv_in ? dconv : D;
+  fork_side(c);
+  void* gs = gstream(c);
   if (c.bf) {
+    if (Gf(c, b.conv_w)) CALL(lotus_subm_conv_wgrad_pairs_bf16(dc0, sv.conv_in, Gf(c, b.conv_w), sg.pairs_out, sg.pairs_in, sg.pair_cnt, sg.stride, n, C, C, 27, gs));
+    if (Gf(c, b.conv_b)) CALL(lotus_colsum_bf16(dc0, n, C, Gf(c, b.conv_b), gs));
     CALL(lotus_subm_conv_dgrad_bf16(dc0, c.WT[b.conv_w], D, dxo, sg.nbr3, sg.stride, n, C, C, 27, 0, c.stv));
-    if (Gf(c, b.conv_w)) CALL(lotus_subm_conv_wgrad_pairs_bf16(dc0, sv.conv_in, Gf(c, b.conv_w), sg.pairs_out, sg.pairs_in, sg.pair_cnt, sg.stride, n, C, C, 27, c.stv));
-    if (Gf(c, b.conv_b)) CALL(lotus_colsum_bf16(dc0, n, C, Gf(c, b.conv_b), c.stv));
   } else {
+    if (Gf(c, b.conv_w)) CALL(lotus_subm_conv_wgrad_f32((const float*)dc0, (const float*)sv.conv_in, Gf(c, b.conv_w), sg.nbr3, sg.stride, n, C, C, 27, gs));
+    if (Gf(c, b.conv_b)) CALL(lotus_colsum_f32((const float*)dc0, n, C, Gf(c, b.conv_b), gs));
     CALL(lotus_subm_conv_dgrad_f32((const float*)dc0, Pf(c, b.conv_w), (const float*)D, (float*)dxo, sg.nbr3, sg.stride, n, C, C, 27, c.stv));
-    if (Gf(c, b.conv_w)) CALL(lotus_subm_conv_wgrad_f32((const float*)dc0, (const float*)sv.conv_in, Gf(c, b.conv_w), sg.nbr3, sg.stride, n, C, C, 27, c.stv));
-    if (Gf(c, b.conv_b)) CALL(lotus_colsum_f32((const float*)dc0, n, C, Gf(c, b.conv_b), c.stv));
   }
+  join_side(c);                                                                          // before the temporaries are reused
   c.ar.off = mark;
   if (d_conv_in) *d_conv_in = dconv;
 }
@@ -307,8 +349,8 @@ static void* ca_fwd(Ctx& c, const CaP& b, const StageInfo& sg, void* x0, const v
 // D: d(out) -> d(x0) in place; dctx (Lt x ctxC, activation dtype) accumulates (first use flagged by *dctx_init)
 static void ca_bwd(Ctx& c, const CaP& b, const StageInfo& sg, void* D, const void* ctx, void* dctx, bool* dctx_init, const CaSave& sv) {
   int n = sv.n, C = b.C, H = b.H, Dh = C / H, Lt = c.Lt;
-  mlp_bwd(c, D, n, b.n2, b.fc1, b.fc2, sv.mlp);
   size_t mark = c.ar.off;
+  mlp_bwd(c, D, n, b.n2, b.fc1, b.fc2, sv.mlp);
   const void* dyd = drop_grad(c, D, (int64_t)n * C, c.proj_drop, sv.d_proj, c.bf);
   void* dout = act(c, n, C);
   linear_bwd(c, dyd, sv.o, n, b.proj, dout, nullptr, c.bf);
@@ -342,7 +384,9 @@ static void ca_bwd(Ctx& c, const CaP& b, const StageInfo& sg, void* D, const voi
   *dctx_init = true;
   void* dh1 = act(c, n, C);
   linear_bwd(c, dq, sv.h1, n, b.q, dh1, nullptr, c.bf);
+  if (dyd == D) join_side(c);
   ln_bwd(c, dh1, sv.x0, D, b.n1, sv.n1_mean, sv.n1_rstd, n, 1);
+  join_side(c);
   c.ar.off = mark;
 }
 
@@ -414,8 +458,8 @@ static void stage_weight(Ctx& c, int idx, int A, int D, int Bdim) {
   g_stage.w.push_back(Pf(c, idx)); g_stage.wb.push_back(c.WB[idx]); g_stage.wt.push_back(c.WT[idx]);
   g_stage.A.push_back(A); g_stage.D.push_back(D); g_stage.B.push_back(Bdim);
 }
-static void stage_flush(Ctx& c) {
-  CALL(lotus_cast_transpose_batch_bf16(g_stage.w.data(), g_stage.wb.data(), g_stage.wt.data(), g_stage.A.data(), g_stage.D.data(),
+static void stage_flush(Ctx& c, bool skip) {
+  if (!skip) CALL(lotus_cast_transpose_batch_bf16(g_stage.w.data(), g_stage.wb.data(), g_stage.wt.data(), g_stage.A.data(), g_stage.D.data(),
                                        g_stage.B.data(), (int)g_stage.w.size(), c.stv));
   g_stage = StageList();
 }
@@ -432,7 +476,9 @@ using namespace eng;
 
 // cfg (int64): S, in_channels, txt_dim, ctx_channels, pos_bins, rot_bins, enc_channels[S], enc_heads[S], dec_channels[S-1],
 //              dec_heads[S-1]
-// run (int64): B, Lt, max_tokens, patch_size K, qk_norm, train, bf16, compute_loss, use_gt_pos, dry_run
+// run (int64): B, Lt, max_tokens, patch_size K, qk_norm, train, bf16, compute_loss, use_gt_pos, dry_run, weights_staged
+//   (weights_staged = 1: the bf16 weight copies at the head of `arena` are still valid from the previous call -- the
+//    caller guarantees same arena base and unchanged parameters; used by repeated inference calls)
 // stage_sizes (int64, 5 per stage): n, n_pad, n_patches, max_cloud, stride ; stage_ptrs (12 per stage): nbr3, pairs_out, pairs_in,
 //   pair_cnt, gather_idx, slot_of_point, cu_seqlens, cloud_off, cluster, seg_ptr, member, nbr5
 // fl (float): attn_drop, proj_drop, head_drop, pos_weight, rot_weight, euler_resolution ; dbl: pos_bin_size
@@ -450,6 +496,15 @@ LOTUS_API int lotus_policy_step(const int64_t* cfg, const int64_t* run, const in
   c.B = (int)run[0]; c.Lt = (int)run[1]; c.max_tok = (int)run[2]; c.K = (int)run[3]; c.qk_norm = (int)run[4];
   c.train = run[5] != 0; c.bf = run[6] != 0; bool compute_loss = run[7] != 0, use_gt_pos = run[8] != 0; c.dry = run[9] != 0;
   c.es = c.bf ? 2 : 4; c.rc = 0; c.seed = seed; c.drop_next = 1;
+  c.side = nullptr; c.sidev = nullptr; c.side_busy = false;
+  if (!c.dry && grads != nullptr && run[7] != 0 && getenv("LOTUS_NO_SIDE_STREAM") == nullptr) {
+    if (!g_side) {
+      LOTUS_CUDA_CALL(cudaStreamCreateWithFlags(&g_side, cudaStreamNonBlocking));
+      LOTUS_CUDA_CALL(cudaEventCreateWithFlags(&g_ev_fork, cudaEventDisableTiming));
+      LOTUS_CUDA_CALL(cudaEventCreateWithFlags(&g_ev_join, cudaEventDisableTiming));
+    }
+    c.side = g_side; c.sidev = (void*)g_side;
+  }
   c.attn_drop = fl[0]; c.proj_drop = fl[1]; c.head_drop = fl[2];
   float pos_w = fl[3], rot_w = fl[4], euler_res = fl[5];
   c.P = params; c.G = grads; c.BN = bn_stats; c.tok_off = tok_off; c.S = m.S; c.ctxC = m.ctxC;
@@ -478,7 +533,7 @@ LOTUS_API int lotus_policy_step(const int64_t* cfg, const int64_t* run, const in
       if (s < S - 1) { stage_lin(c, m.unpool[s].proj); stage_lin(c, m.unpool[s].skip); stage_block(c, m.decB[s]); stage_ca(c, m.decCA[s]); }
     }
     stage_lin(c, m.txt_fc); stage_lin(c, m.hm0); stage_lin(c, m.am0);
-    stage_flush(c);
+    stage_flush(c, run[10] != 0);      // run[10]: the arena still holds this model's staged weights (inference)
   }
   const int N0 = sg[0].n, Lt = c.Lt;
   // ---------------- context tokens
@@ -579,6 +634,7 @@ LOTUS_API int lotus_policy_step(const int64_t* cfg, const int64_t* run, const in
         linear_bwd(c, dh2, pc, B, m.am0, dpc, nullptr, c.bf);
         if (c.bf) CALL(lotus_segment_max_bwd_bf16(dpc, pc_arg, B, hid, D, 1, c.stv));
         else CALL(lotus_segment_max_bwd_f32((const float*)dpc, pc_arg, B, hid, (float*)D, 1, c.stv));
+        join_side(c);
         c.ar.off = mark;
       }
       void* dctx = act(c, Lt, m.ctxC);
@@ -638,6 +694,7 @@ LOTUS_API int lotus_policy_step(const int64_t* cfg, const int64_t* run, const in
       }
     }
   }
+  join_side(c);                                    // the caller's stream owns every result from here on
   if (arena_peak) *arena_peak = (int64_t)c.ar.peak;
   if (!c.dry && (c.ar.overflow || c.ar.peak > c.ar.cap)) {
     lotus_set_error("lotus_policy_step: arena too small (%lld needed, %lld given)", (long long)c.ar.peak, (long long)c.ar.cap);

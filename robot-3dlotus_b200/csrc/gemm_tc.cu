@@ -21,12 +21,12 @@ namespace tc {
 
 constexpr int BM = 128;
 constexpr int BK = 64;            // 64 bf16 = 128 B = one SWIZZLE_128B span
-constexpr int MAX_STAGES = 4;
+constexpr int MAX_STAGES = 6;
 constexpr int NUM_THREADS = 320;  // 10 warps: TMA, MMA, 8 epilogue (warps 2-5 double as cp.async gather producers)
 constexpr int EPI_THREADS = 128;  // gather-producer threads (warps 2-5)
 
 enum { OP_K_TMA = 0, OP_K_GATHER = 1, OP_MN_TMA = 2, OP_MN_GATHER = 3 };
-enum { ACT_NONE = 0, ACT_GELU = 1, ACT_LEAKY = 2 };
+enum { ACT_NONE = 0, ACT_GELU = 1, ACT_LEAKY = 2, ACT_GELU_GRAD = 3 };   // 3: multiply by gelu'(aux) where aux rides in `residual`
 
 struct GatherSpec {
   const __nv_bfloat16* base;   // rows of `row_elems` bf16
@@ -91,7 +91,8 @@ __device__ __forceinline__ void stage_mn_gather(uint8_t* tile, const GatherSpec&
 template <int BN>
 __global__ void __launch_bounds__(NUM_THREADS)
 k_gemm_tc(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_b,
-          const __grid_constant__ CUtensorMap map_out, const __grid_constant__ CUtensorMap map_res, const Params p) {
+          const __grid_constant__ CUtensorMap map_out, const __grid_constant__ CUtensorMap map_res,
+          const __grid_constant__ CUtensorMap map_out2, const Params p) {
   extern __shared__ __align__(1024) uint8_t smem_raw[];
   constexpr uint32_t A_BYTES = BM * BK * 2, B_BYTES = BN * BK * 2;
   const int STAGES = p.stages;
@@ -200,7 +201,7 @@ k_gemm_tc(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUt
     } else if ((a_gather || b_gather) && warp < 6) {
       // ===================== cp.async gather producers (warps 2-5) =====================
       const int t = threadIdx.x - 64;                   // 0..127
-      const int LAG = STAGES >= 3 ? 2 : 1;              // stages in flight per thread before signalling
+      const int LAG = STAGES >= 5 ? STAGES - 2 : (STAGES >= 3 ? 2 : 1);   // cp.async groups in flight per thread before signalling
       const int32_t* a_idx = p.ga.idx + (int64_t)tap * p.tap_idx_stride;
       const int32_t* b_idx = p.gb.idx + (int64_t)tap * p.tap_idx_stride;
       for (int i = 0; i < num_kb + LAG; ++i) {
@@ -225,7 +226,7 @@ k_gemm_tc(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUt
         }
         cp_async_commit();
         if (i >= LAG) {
-          if (LAG == 2) cp_async_wait<2>(); else cp_async_wait<1>();
+          if (LAG == 4) cp_async_wait<4>(); else if (LAG == 3) cp_async_wait<3>(); else if (LAG == 2) cp_async_wait<2>(); else cp_async_wait<1>();
           fence_proxy_async();
           mbar_arrive(&full[(i - LAG) % STAGES]);
         }
@@ -246,6 +247,8 @@ k_gemm_tc(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUt
     if (threadIdx.x == 64) TS(4);
     if (p.residual && !(p.debug & 2)) mbar_wait(res_full, 0);
     const bool plain = (p.act == ACT_NONE) && !(p.drop_p > 0.f);
+    const bool add_res = p.residual != nullptr && p.act != ACT_GELU_GRAD;
+    uint8_t* sOut2 = smem + (size_t)BM * BN * 2;       // pre-activation tile (bf16 outputs only), behind the output tile
     const uint32_t thr = drop_thr(p.drop_p);
     const float keep_scale = p.drop_p > 0.f ? drop_scale(thr) : 1.f;
     uint8_t* sOut = smem;                              // [BN/box_cols][128 rows][128 B], SWIZZLE_128B
@@ -268,6 +271,33 @@ k_gemm_tc(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUt
         float4 bb = b4[j];
         f[4 * j] = __uint_as_float(v[4 * j]) + bb.x; f[4 * j + 1] = __uint_as_float(v[4 * j + 1]) + bb.y;
         f[4 * j + 2] = __uint_as_float(v[4 * j + 2]) + bb.z; f[4 * j + 3] = __uint_as_float(v[4 * j + 3]) + bb.w;
+      }
+      if (p.out2) {                                    // pre-activation copy (bf16): same swizzled layout as the output tile
+        uint8_t* box2 = sOut2 + (c0 >> 6) * 16384 + r * 128;
+        const int cb2 = (c0 & 63) >> 3;
+#pragma unroll
+        for (int ch = 0; ch < 4; ++ch) {
+          const float* g = f + 8 * ch;
+          uint4 w;
+          __nv_bfloat162 h0 = __floats2bfloat162_rn(g[0], g[1]), h1 = __floats2bfloat162_rn(g[2], g[3]);
+          __nv_bfloat162 h2 = __floats2bfloat162_rn(g[4], g[5]), h3 = __floats2bfloat162_rn(g[6], g[7]);
+          w.x = *(uint32_t*)&h0; w.y = *(uint32_t*)&h1; w.z = *(uint32_t*)&h2; w.w = *(uint32_t*)&h3;
+          *(uint4*)(box2 + (((cb2 + ch) ^ sw) << 4)) = w;
+        }
+      }
+      if (p.act == ACT_GELU_GRAD) {                    // f *= gelu'(aux), aux = bf16 tile loaded through the residual map
+        const uint8_t* rbox = sRes + (c0 >> 6) * 16384 + r * 128;
+        const int cb2 = (c0 & 63) >> 3;
+#pragma unroll
+        for (int ch = 0; ch < 4; ++ch) {
+          uint4 q = *(const uint4*)(rbox + (((cb2 + ch) ^ sw) << 4));
+          const __nv_bfloat162* qh = (const __nv_bfloat162*)&q;
+#pragma unroll
+          for (int t2 = 0; t2 < 4; ++t2) {
+            float2 e = __bfloat1622float2(qh[t2]);
+            f[8 * ch + 2 * t2] *= gelu_grad_f(e.x); f[8 * ch + 2 * t2 + 1] *= gelu_grad_f(e.y);
+          }
+        }
       }
       if (!plain) {
         if (p.act == ACT_GELU) {
@@ -295,7 +325,7 @@ k_gemm_tc(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUt
 #pragma unroll
         for (int ch = 0; ch < 8; ++ch) {
           float4 w = make_float4(f[4 * ch], f[4 * ch + 1], f[4 * ch + 2], f[4 * ch + 3]);
-          if (p.residual) {
+          if (add_res) {
             float4 q = *(const float4*)(rbox + ((ch ^ sw) << 4));
             w.x += q.x; w.y += q.y; w.z += q.z; w.w += q.w;
           }
@@ -309,7 +339,7 @@ k_gemm_tc(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUt
 #pragma unroll
         for (int ch = 0; ch < 4; ++ch) {
           float* g = f + 8 * ch;
-          if (p.residual) {
+          if (add_res) {
             uint4 q = *(const uint4*)(rbox + (((cb + ch) ^ sw) << 4));
             const __nv_bfloat162* qh = (const __nv_bfloat162*)&q;
 #pragma unroll
@@ -333,6 +363,7 @@ k_gemm_tc(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUt
         if (n0 + j * box_cols >= p.N) break;
         if (p.atomic) tma_reduce_add_2d(&map_out, sOut + j * 16384, ncol0 + j * box_cols, m0);
         else tma_store_2d(&map_out, sOut + j * 16384, ncol0 + j * box_cols, m0);
+        if (p.out2) tma_store_2d(&map_out2, sOut2 + j * 16384, ncol0 + j * box_cols, m0);
       }
       if (p.debug & 4) asm volatile("cp.async.bulk.commit_group;" ::: "memory"); else tma_store_commit_wait();
       TS(6);
@@ -391,10 +422,17 @@ struct Operand {
   GatherSpec g;               // gather modes
 };
 
+static bool force_deep_gather() {
+  static int v = -1;
+  if (v < 0) { const char* e = getenv("LOTUS_TC_DEEP_GATHER"); v = e ? atoi(e) : 0; }   // measured on B200: 5-6 stages cost ~1 ms/step (one 200 KB CTA per SM, nothing co-resident), so off
+  return v != 0;
+}
+
 static int launch(const Operand& A, const Operand& B, Params p, int BN, int splits, cudaStream_t st, int taps = 1,
                   int max_kb_hint = -1) {
   if (p.M <= 0 || p.N <= 0) return 0;
-  CUtensorMap ma, mb, mo, mr;
+  CUtensorMap ma, mb, mo, mr, mo2;
+  memset(&mo2, 0, sizeof(mo2));
   memset(&ma, 0, sizeof(ma));
   memset(&mb, 0, sizeof(mb));
   memset(&mo, 0, sizeof(mo));
@@ -415,6 +453,8 @@ static int launch(const Operand& A, const Operand& B, Params p, int BN, int spli
     if (rc) return rc;
     if (p.residual) rc = make_map(&mr, p.residual, p.M, p.N, p.ldo, box_cols, BM, p.out_fp32 != 0);
     if (rc) return rc;
+    if (p.out2) rc = make_map(&mo2, p.out2, p.M, out_cols, p.ldo, box_cols, BM, false);
+    if (rc) return rc;
   }
   int num_kb = (p.K + BK - 1) / BK;
   splits = max(1, min(splits, num_kb));
@@ -433,20 +473,22 @@ static int launch(const Operand& A, const Operand& B, Params p, int BN, int spli
     p.debug = dbg;
     p.dbg_ts = g_dbg_ts;
   }
+  // dev knob (LOTUS_TC_DEEP_GATHER=1): 5-6 stage pipeline for the gathered conv operand (3-4 k-blocks of cp.async in flight)
+  if (A.mode == OP_K_GATHER && BN == 128 && kb_per_cta >= 6 && force_deep_gather()) p.stages = p.residual ? 5 : 6;
   dim3 grid((p.M + BM - 1) / BM, (p.N + BN - 1) / BN, splits * taps);
   size_t tile_bytes = (size_t)BM * BN * (p.out_fp32 ? 4 : 2);
   size_t pipe = (size_t)p.stages * (BM * BK * 2 + BN * BK * 2);
-  while (pipe < tile_bytes) { ++p.stages; pipe = (size_t)p.stages * (BM * BK * 2 + BN * BK * 2); }   // the output tile reuses the pipeline
+  while (pipe < tile_bytes * (p.out2 ? 2 : 1)) { ++p.stages; pipe = (size_t)p.stages * (BM * BK * 2 + BN * BK * 2); }   // the output tile reuses the pipeline
   size_t smem = pipe + 256 + 2048 + (size_t)BN * 4 + (p.residual ? tile_bytes : 0);
   cudaError_t e;
   if (BN == 128) {
     static bool set128 = false;
-    if (!set128) { cudaFuncSetAttribute(k_gemm_tc<128>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024); set128 = true; }
-    k_gemm_tc<128><<<grid, NUM_THREADS, smem, st>>>(ma, mb, mo, mr, p);
+    if (!set128) { cudaFuncSetAttribute(k_gemm_tc<128>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024); set128 = true; }
+    k_gemm_tc<128><<<grid, NUM_THREADS, smem, st>>>(ma, mb, mo, mr, mo2, p);
   } else {
     static bool set64 = false;
     if (!set64) { cudaFuncSetAttribute(k_gemm_tc<64>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024); set64 = true; }
-    k_gemm_tc<64><<<grid, NUM_THREADS, smem, st>>>(ma, mb, mo, mr, p);
+    k_gemm_tc<64><<<grid, NUM_THREADS, smem, st>>>(ma, mb, mo, mr, mo2, p);
   }
   e = cudaGetLastError();
   if (e != cudaSuccess) { lotus_set_error("gemm_tc launch: %s", cudaGetErrorString(e)); return 1; }
@@ -467,12 +509,14 @@ static Params base_params(int M, int N, int K, void* out, int64_t ldo, int out_f
   return p;
 }
 
-// y[M,N] = [residual +] drop(act(x[M,K] @ w[N,K]^T + bias)) ; x, w bf16 ; y (and residual) bf16 or fp32 ; y_preact: reserved (null)
+// y[M,N] = [residual +] drop(act(x[M,K] @ w[N,K]^T + bias)) ; x, w bf16 ; y (and residual) bf16 or fp32 ;
+// y_preact (bf16 [M,N], optional): receives x @ w^T + bias before the activation (saved for the backward of a fused GELU)
 LOTUS_API int lotus_linear_fwd_bf16(const void* x, const void* w, const float* bias, const void* residual, void* y,
                                     void* y_preact, int M, int N, int K, int act, int out_fp32, float drop_p, uint64_t seed,
                                     uint32_t drop_stream, void* stream_) {
   LOTUS_CHECK_ARG(K % 8 == 0, "lotus_linear_fwd_bf16: K=%d must be a multiple of 8 (16-byte TMA rows)", K);
-  LOTUS_CHECK_ARG(y_preact == nullptr, "lotus_linear_fwd_bf16: y_preact is reserved and must be null");
+  LOTUS_CHECK_ARG(y_preact == nullptr || (!out_fp32 && residual == nullptr),
+                  "lotus_linear_fwd_bf16: y_preact needs a bf16 output and no residual");
   LOTUS_CHECK_ARG(N % (out_fp32 ? 4 : 8) == 0, "lotus_linear_fwd_bf16: N=%d must keep output rows 16-byte aligned", N);
   Params p = base_params(M, N, K, y, N, out_fp32);
   p.out2 = y_preact; p.bias = bias; p.residual = residual; p.act = act; p.drop_p = drop_p; p.seed = seed; p.drop_stream = drop_stream;
@@ -486,6 +530,18 @@ LOTUS_API int lotus_linear_dgrad_bf16(const void* dy, const void* wt, const void
   LOTUS_CHECK_ARG(N % 8 == 0, "lotus_linear_dgrad_bf16: N=%d must be a multiple of 8", N);
   Params p = base_params(M, K, N, dx, K, out_fp32);
   p.residual = residual;
+  Operand A{tc::OP_K_TMA, (const __nv_bfloat16*)dy, N, {}}, B{tc::OP_K_TMA, (const __nv_bfloat16*)wt, N, {}};
+  return tc::launch(A, B, p, tc::pick_bn(K), 1, (cudaStream_t)stream_);
+}
+
+// dx[M,K] = drop(dy[M,N] @ w[N,K] * act'(preact[M,K])) : the backward of `y = drop(act(preact))` fused into the data-gradient GEMM
+// of the NEXT layer (act 1 = GELU; preact and dx bf16; the dropout mask is the forward's: same seed / stream / element index)
+LOTUS_API int lotus_linear_dgrad_act_bf16(const void* dy, const void* wt, const void* preact, void* dx, int M, int N, int K, int act,
+                                          float drop_p, uint64_t seed, uint32_t drop_stream, void* stream_) {
+  LOTUS_CHECK_ARG(N % 8 == 0 && K % 8 == 0, "lotus_linear_dgrad_act_bf16: N=%d, K=%d must be multiples of 8", N, K);
+  LOTUS_CHECK_ARG(act == 1 && preact != nullptr, "lotus_linear_dgrad_act_bf16: act must be 1 (GELU) with a pre-activation tensor");
+  Params p = base_params(M, K, N, dx, K, 0);
+  p.residual = preact; p.act = tc::ACT_GELU_GRAD; p.drop_p = drop_p; p.seed = seed; p.drop_stream = drop_stream;
   Operand A{tc::OP_K_TMA, (const __nv_bfloat16*)dy, N, {}}, B{tc::OP_K_TMA, (const __nv_bfloat16*)wt, N, {}};
   return tc::launch(A, B, p, tc::pick_bn(K), 1, (cudaStream_t)stream_);
 }

@@ -28,11 +28,66 @@ __global__ void k_segment_max(const T* __restrict__ x, int C, const int32_t* __r
     if (arg) arg[t] = bi;
   }
 }
+// Long contiguous segments (the per-cloud max of the action head: M = clouds, thousands of rows each):
+// one CTA per (segment, 8-channel chunk); 256 threads stride over the rows with 16/32-byte loads, then a
+// shared-memory tree reduction.  Ties -> lowest row, like the sequential kernel above.
+template <typename T>
+__global__ void __launch_bounds__(256) k_segment_max_long(const T* __restrict__ x, int C, const int32_t* __restrict__ ptr, T* __restrict__ out,
+                                                          int32_t* __restrict__ arg) {
+  __shared__ float sv[256][8];
+  __shared__ int si[256][8];
+  const int m = blockIdx.x, c0 = blockIdx.y * 8, tid = threadIdx.x;
+  const int s = ptr[m], e = ptr[m + 1];
+  float best[8]; int bi[8];
+#pragma unroll
+  for (int i = 0; i < 8; ++i) { best[i] = -INFINITY; bi[i] = -1; }
+  for (int r = s + tid; r < e; r += 256) {
+    float v[8];
+    if constexpr (sizeof(T) == 2) {
+      uint4 raw = *reinterpret_cast<const uint4*>(x + (int64_t)r * C + c0);
+      const __nv_bfloat162* h = reinterpret_cast<const __nv_bfloat162*>(&raw);
+#pragma unroll
+      for (int i = 0; i < 4; ++i) { float2 f = __bfloat1622float2(h[i]); v[2 * i] = f.x; v[2 * i + 1] = f.y; }
+    } else {
+      const float4* p4 = reinterpret_cast<const float4*>(x + (int64_t)r * C + c0);
+      float4 a = p4[0], b = p4[1];
+      v[0] = a.x; v[1] = a.y; v[2] = a.z; v[3] = a.w; v[4] = b.x; v[5] = b.y; v[6] = b.z; v[7] = b.w;
+    }
+#pragma unroll
+    for (int i = 0; i < 8; ++i) if (v[i] > best[i] || bi[i] < 0) { best[i] = v[i]; bi[i] = r; }
+  }
+#pragma unroll
+  for (int i = 0; i < 8; ++i) { sv[tid][i] = best[i]; si[tid][i] = bi[i]; }
+  __syncthreads();
+  for (int half = 128; half >= 1; half >>= 1) {
+    if (tid < half) {
+#pragma unroll
+      for (int i = 0; i < 8; ++i) {
+        float vo = sv[tid + half][i]; int io = si[tid + half][i];
+        float vm = sv[tid][i]; int im = si[tid][i];
+        // the other half wins on a larger value, or on an equal value from a lower row; empty slots (-1) never win
+        bool take = io >= 0 && (im < 0 || vo > vm || (vo == vm && io < im));
+        if (take) { sv[tid][i] = vo; si[tid][i] = io; }
+      }
+    }
+    __syncthreads();
+  }
+  if (tid < 8) {
+    int64_t o = (int64_t)m * C + c0 + tid;
+    stf(out, o, sv[0][tid]);
+    if (arg) arg[o] = si[0][tid];
+  }
+}
 template <typename T>
 static int segmax_fwd_impl(const void* x, int C, const int32_t* seg_ptr, const int32_t* member, int M, void* out, int32_t* argmax,
                            void* stream_) {
   if (M <= 0) return 0;
   int64_t total = (int64_t)M * C;
+  if (member == nullptr && M <= 1024 && C % 8 == 0) {
+    k_segment_max_long<T><<<dim3(M, C / 8), 256, 0, (cudaStream_t)stream_>>>((const T*)x, C, seg_ptr, (T*)out, argmax);
+    LOTUS_CUDA_OK();
+    return 0;
+  }
   k_segment_max<T><<<min(ceil_div(total, 256), kNumSM * 16), 256, 0, (cudaStream_t)stream_>>>((const T*)x, C, seg_ptr, member, M,
                                                                                              (T*)out, argmax);
   LOTUS_CUDA_OK();

@@ -24,6 +24,7 @@ class PolicyEngine:
         # "fp32": validation mode (SIMT kernels, 1e-4 parity with the reference); "bf16": tensor-core mode
         # (tcgen05 GEMMs / implicit-GEMM conv, bf16 activations, fp32 master weights, statistics and gradients)
         self.precision = "fp32"
+        self.pos_heatmap_type = "dist"  # TRAIN_DATASET.pos_heatmap_type of the job scripts ('plain' | 'dist')
         self.use_native = False        # one-call C++ executor (csrc/engine_native.cu) for the production topology
         self._native = None
         self._tc_weights = None
@@ -100,10 +101,7 @@ class PolicyEngine:
         x = ops.linear(o, a.proj.weight, a.proj.bias, residual=x, drop=drop.site(a.proj_drop_p))
         h = self._ln(blk.norm2[0], x, pd, stg)
         mlp = blk.mlp[0]
-        u = ops.linear(h, mlp.fc1.weight, mlp.fc1.bias)
-        g = ops.act(u, "gelu", drop.site(blk.proj_drop))
-        x = ops.linear(g, mlp.fc2.weight, mlp.fc2.bias, residual=x, drop=drop.site(blk.proj_drop))
-        return x
+        return ops.mlp(h, mlp.fc1, mlp.fc2, x, drop.site(blk.proj_drop), drop.site(blk.proj_drop))
 
     def _ca_block(self, blk, x, ctx, geo, drop):
         a = blk.attn
@@ -114,10 +112,7 @@ class PolicyEngine:
         x = ops.linear(o, a.proj.weight, a.proj.bias, residual=x, drop=drop.site(a.proj_drop_p))
         h = ops.layer_norm(x, blk.norm2[0].weight, blk.norm2[0].bias, blk.norm2[0].eps)
         mlp = blk.mlp[0]
-        u = ops.linear(h, mlp.fc1.weight, mlp.fc1.bias)
-        g = ops.act(u, "gelu", drop.site(blk.proj_drop))
-        x = ops.linear(g, mlp.fc2.weight, mlp.fc2.bias, residual=x, drop=drop.site(blk.proj_drop))
-        return x
+        return ops.mlp(h, mlp.fc1, mlp.fc2, x, drop.site(blk.proj_drop), drop.site(blk.proj_drop))
 
     # ------------------------------------------------------------------ backbone
     def backbone(self, feat, coord, npoints, ctx, tok_off_host, train, drop, pd=None):
@@ -335,10 +330,12 @@ class PolicyEngine:
         if not compute_loss:
             return final
         if "disc_pos_probs_packed" in batch:
-            prob = batch["disc_pos_probs_packed"]
-        else:
-            prob = torch.cat([p.reshape(-1) for p in batch["disc_pos_probs"]])
-        prob = prob.to(fts.device, non_blocking=True).float()
+            prob = batch["disc_pos_probs_packed"].to(fts.device, non_blocking=True).float()
+        elif "disc_pos_probs" in batch:
+            prob = torch.cat([p.reshape(-1) for p in batch["disc_pos_probs"]]).to(fts.device, non_blocking=True).float()
+        else:       # device-side batch producer (utils/action_position_utils.py:7-46)
+            prob = ops.disc_pos_prob(fts, s0.cloud_off, B, s0.max_cloud, gt.float().contiguous(), ac.pos_bins, ac.pos_bin_size,
+                                     self.pos_heatmap_type)
         lv = ops.policy_loss(heat, action, prob, s0.cloud_off, gt.float().contiguous(), B, NB, head.euler_bins,
                              lc.pos_weight, lc.rot_weight)
         return final, {"pos": lv[0], "rot": lv[1], "open": lv[2], "total": lv[3]}

@@ -8,7 +8,7 @@ import ctypes
 import torch
 
 from .lib import load
-from .ops import GRAD_SINK
+from .ops import GRAD_SINK, PARAM_EPOCH
 
 VP = ctypes.c_void_p
 
@@ -42,6 +42,7 @@ class NativeStep:
             bns += [up.proj[1], up.proj_skip[1]]
         self.bns = bns
         self._ptr_key = None
+        self._staged_key = None
         self.arena = None
         self.losses = None
         self.final = None
@@ -77,7 +78,7 @@ class NativeStep:
         B = len(batch["npoints_in_batch"])
         Lt = tok_off_host[-1]
         max_tok = max(b - a for a, b in zip(tok_off_host[:-1], tok_off_host[1:]))
-        run = (ctypes.c_int64 * 10)(B, Lt, max_tok, self.K, self.qk_norm, int(train), int(bf16), int(compute_loss), int(use_gt_pos), 0)
+        run = (ctypes.c_int64 * 11)(B, Lt, max_tok, self.K, self.qk_norm, int(train), int(bf16), int(compute_loss), int(use_gt_pos), 0, 0)
         sizes, ptrs = [], []
         for s, stg in enumerate(stages):
             pl = stg.plans[0]
@@ -97,7 +98,12 @@ class NativeStep:
         gt = batch.get("gt_actions")
         prob = batch.get("disc_pos_probs_packed")
         if compute_loss and prob is None:
-            prob = torch.cat([p.reshape(-1) for p in batch["disc_pos_probs"]]).to(dev, non_blocking=True)
+            if "disc_pos_probs" in batch:
+                prob = torch.cat([p.reshape(-1) for p in batch["disc_pos_probs"]]).to(dev, non_blocking=True)
+            else:   # device-side batch producer: soft labels from (xyz, gt position) instead of a host tensor
+                from . import ops
+                prob = ops.disc_pos_prob(feat, stages[0].cloud_off, B, stages[0].max_cloud, gt, ac.pos_bins, ac.pos_bin_size,
+                                         getattr(m.engine(), "pos_heatmap_type", "dist"))
         if self.losses is None or self.losses.device != dev:
             self.losses = torch.zeros(4, device=dev, dtype=torch.float32)
         final = torch.empty((B, 8), device=dev, dtype=torch.float64)
@@ -112,10 +118,17 @@ class NativeStep:
         need = int(peak.value) + 4096
         if self.arena is None or self.arena.numel() < need or self.arena.device != dev:
             self.arena = None
+            self._staged_key = None
             self.arena = torch.empty(int(need * 1.1), device=dev, dtype=torch.uint8)
         run[9] = 0
+        # inference: the staged bf16 weights at the head of the arena stay valid while the parameters are untouched
+        wkey = None
+        if not train and bf16:
+            wkey = (self.arena.data_ptr(), PARAM_EPOCH[0], sum(p._version for p in self.params))
+            run[10] = int(wkey == self._staged_key)
         L.lotus_policy_step(*common, VP(self.arena.data_ptr()), self.arena.numel(), ctypes.byref(peak), VP(self.losses.data_ptr()),
                             VP(final.data_ptr()), st)
+        self._staged_key = wkey
         if train:
             torch._foreach_add_([bn.num_batches_tracked for bn in self.bns], 1)
         return final, self.losses

@@ -93,6 +93,8 @@ NO_DROP = (0.0, 0, 0)
 # parameter has a sink, the backward kernels ACCUMULATE its gradient there directly ("flat grad
 # buffer written directly by the backward kernels") and autograd receives None for it.
 GRAD_SINK = {}
+# bumped whenever a kernel rewrites parameters through raw pointers (the fused AdamW): invalidates cached bf16 weight copies
+PARAM_EPOCH = [0]
 
 
 def _sink(param):
@@ -174,6 +176,74 @@ class LinearFn(torch.autograd.Function):
 
 def linear(x, w, b=None, residual=None, drop=NO_DROP, out_fp32=False):
     return LinearFn.apply(x, w, b, residual, drop, out_fp32)
+
+
+class MlpFn(torch.autograd.Function):
+    """y = residual + drop_out(fc2(drop_act(gelu(fc1(x)))))  (model.py:560-583 inside Block / CABlock), tensor-core mode only:
+    GELU + dropout ride in fc1's GEMM epilogue (pre-activation kept through a second TMA store) and the GELU backward rides
+    in fc2's data-gradient GEMM epilogue -- the same launches the native executor issues."""
+
+    @staticmethod
+    def forward(ctx, x, w1, b1, w2, b2, residual, drop_act, drop_out):
+        L = load()
+        x, residual = _actc(x), _actc(residual)
+        assert x.dtype == torch.bfloat16
+        M, C = x.shape
+        Hd = w1.shape[0]
+        st = _st()
+        u = torch.empty((M, Hd), device=x.device, dtype=torch.bfloat16)
+        g = torch.empty_like(u)
+        L.lotus_linear_fwd_bf16(_p(x), _p(STAGED[w1.data_ptr()][0]), _p(b1), None, _p(g), _p(u), M, Hd, C, 1, 0, drop_act[0],
+                                drop_act[1], drop_act[2], st)
+        y = torch.empty_like(x)
+        L.lotus_linear_fwd_bf16(_p(g), _p(STAGED[w2.data_ptr()][0]), _p(b2), _p(residual), _p(y), None, M, C, Hd, 0, 0, drop_out[0],
+                                drop_out[1], drop_out[2], st)
+        ctx.save_for_backward(x, u, g, w1, w2)
+        ctx.b1, ctx.b2, ctx.drop_act, ctx.drop_out = b1, b2, drop_act, drop_out
+        return y
+
+    @staticmethod
+    def backward(ctx, dy):
+        L = load()
+        x, u, g, w1, w2 = ctx.saved_tensors
+        M, C = x.shape
+        Hd = w1.shape[0]
+        st = _st()
+        dres = dy
+        dy = _actc(to_bf16(dy) if dy.dtype == torch.float32 else dy)
+        if ctx.drop_out[0] > 0:
+            dyd = torch.empty_like(dy)
+            L.lotus_dropout_bf16(_p(dy), _p(dyd), dy.numel(), ctx.drop_out[0], ctx.drop_out[1], ctx.drop_out[2], st)
+            dy = dyd
+        w2buf, dw2 = _grad_buf(w2, ctx.needs_input_grad[3])
+        if w2buf is not None:
+            L.lotus_linear_wgrad_bf16(_p(dy), _p(g), _p(w2buf), M, C, Hd, st)
+        b2buf, db2 = _grad_buf(ctx.b2, ctx.needs_input_grad[4])
+        if b2buf is not None:
+            L.lotus_colsum_bf16(_p(dy), M, C, _p(b2buf), st)
+        du = torch.empty_like(u)
+        L.lotus_linear_dgrad_act_bf16(_p(dy), _p(STAGED[w2.data_ptr()][1]), _p(u), _p(du), M, C, Hd, 1, ctx.drop_act[0],
+                                      ctx.drop_act[1], ctx.drop_act[2], st)
+        w1buf, dw1 = _grad_buf(w1, ctx.needs_input_grad[1])
+        if w1buf is not None:
+            L.lotus_linear_wgrad_bf16(_p(du), _p(x), _p(w1buf), M, Hd, C, st)
+        b1buf, db1 = _grad_buf(ctx.b1, ctx.needs_input_grad[2])
+        if b1buf is not None:
+            L.lotus_colsum_bf16(_p(du), M, Hd, _p(b1buf), st)
+        dx = None
+        if ctx.needs_input_grad[0]:
+            dx = torch.empty_like(x)
+            L.lotus_linear_dgrad_bf16(_p(du), _p(STAGED[w1.data_ptr()][1]), None, _p(dx), M, Hd, C, 0, st)
+        return dx, dw1, db1, dw2, db2, dres, None, None
+
+
+def mlp(x, fc1, fc2, residual, drop_act=NO_DROP, drop_out=NO_DROP):
+    """transformer MLP tail; bf16 activations take the fused path, fp32 the three validation-mode kernels"""
+    if x.dtype == torch.bfloat16:
+        return MlpFn.apply(x, fc1.weight, fc1.bias, fc2.weight, fc2.bias, residual, drop_act, drop_out)
+    u = linear(x, fc1.weight, fc1.bias)
+    g = act(u, "gelu", drop_act)
+    return linear(g, fc2.weight, fc2.bias, residual=residual, drop=drop_out)
 
 
 # ------------------------------------------------------------------------------------------ pointwise
@@ -800,4 +870,17 @@ def decode_trajs(heat, xyz, cloud_off, B, T, NB, bin_size, action, rot_bins, res
     out = torch.empty((B, T, 9), device=heat.device, dtype=torch.float64)
     L.lotus_decode_trajs(_p(heat), _p(xyz), xyz.stride(0), _p(cloud_off), B, T, NB, float(bin_size), _p(action), action.shape[1],
                          rot_bins, float(resolution), _p(gt_pos), gt_pos.stride(0) if gt_pos is not None else 0, _p(out), _st())
+    return out
+
+
+def disc_pos_prob(pc_fts, cloud_off, B, max_cloud, gt_actions, pos_bins, bin_size, heatmap_type="dist"):
+    """packed soft position labels (sum_b 3 * n_b * 2*pos_bins,) fp32 on the device, from the packed cloud and the ground-truth
+    positions (utils/action_position_utils.py:7-46); replaces the host-computed `disc_pos_probs` of the collate"""
+    L = load()
+    assert pc_fts.dtype == torch.float32 and pc_fts.is_cuda and gt_actions.dtype == torch.float32
+    N = pc_fts.shape[0]
+    out = torch.empty(3 * 2 * pos_bins * N, device=pc_fts.device, dtype=torch.float32)
+    scratch = torch.empty((int(L.cdll.lotus_disc_pos_prob_scratch_bytes(B)) + 7) // 8, device=pc_fts.device, dtype=torch.int64)
+    L.lotus_disc_pos_prob(_p(pc_fts), pc_fts.stride(0), _p(cloud_off), B, max_cloud, _p(gt_actions), gt_actions.stride(0), pos_bins,
+                          float(bin_size), int(heatmap_type == "plain"), _p(out), _p(scratch), _st())
     return out

@@ -84,16 +84,18 @@ class FlatAdamW:
         if self.world > 1:
             dist.all_reduce(self.flat_grad, op=dist.ReduceOp.SUM)
 
-    def step(self, lr=None):
+    def step(self, lr=None, grad_scale=1.0):
         if not self.flat_param.is_cuda:
             raise RuntimeError("FlatAdamW.step runs the fused CUDA optimizer kernels: move the model to CUDA first "
                                "(there is no CPU optimizer path)")
         L = load()
         lr = self.lr if lr is None else lr
         self.step_count += 1
+        ops.PARAM_EPOCH[0] += 1
         st = _st()
         n = self.flat_param.numel()
-        scale = 1.0 / self.world
+        scale = grad_scale / self.world
+        self.last_scale = scale
         if self.max_grad_norm and self.max_grad_norm > 0:
             L.lotus_grad_sumsq_f32(_p(self.flat_grad), n, _p(self.sumsq), st)
             sumsq = _p(self.sumsq)
@@ -105,7 +107,7 @@ class FlatAdamW:
 
     def grad_norm(self):
         """global gradient norm of the last step (after the all-reduce mean) — one D2H read"""
-        return math.sqrt(float(self.sumsq.item())) / self.world
+        return math.sqrt(float(self.sumsq.item())) * getattr(self, "last_scale", 1.0 / self.world)
 
     # ---- reference checkpoint layout (train/utils/save.py:38-45)
     def state_dict(self):
@@ -144,9 +146,17 @@ class TrainStep:
         self.opt = FlatAdamW(model, learning_rate, betas, 1e-6, weight_decay, grad_norm)
         self.learning_rate, self.warmup_steps, self.num_train_steps = learning_rate, warmup_steps, num_train_steps
         self.global_step = 0
+        self.lr_fn = None             # optional schedule override: global_step -> lr (train_loop.py)
 
     def __call__(self, batch):
-        self.opt.zero_grad()
+        losses = self.accumulate(batch, first=True)
+        self.apply()
+        return losses
+
+    def accumulate(self, batch, first=True):
+        """forward + backward of one (micro-)batch; gradients ACCUMULATE in the flat buffer (zeroed when `first`)"""
+        if first:
+            self.opt.zero_grad()
         eng = self.model.engine()
         if eng.use_native:
             batch = self.model.prepare_batch(batch)
@@ -155,8 +165,15 @@ class TrainStep:
         else:
             _, losses = self.model(batch, compute_loss=True, compute_final_action=False)
             losses["total"].backward()
+        return losses
+
+    def apply(self, accumulation=1):
+        """all-reduce, clip, AdamW with the scheduled learning rate (train_simple_policy.py:214-232); the 1/accumulation of the
+        reference's loss scaling (:206-207) is folded into the optimizer kernel's gradient scale"""
         self.opt.all_reduce()
         self.global_step += 1
-        lr = self.learning_rate * get_lr_sched_decay_rate(self.global_step, self.warmup_steps, self.num_train_steps)
-        self.opt.step(lr)
-        return losses
+        if self.lr_fn is not None:
+            lr = self.lr_fn(self.global_step)
+        else:
+            lr = self.learning_rate * get_lr_sched_decay_rate(self.global_step, self.warmup_steps, self.num_train_steps)
+        self.opt.step(lr, grad_scale=1.0 / accumulation)

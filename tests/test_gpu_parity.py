@@ -767,3 +767,74 @@ def test_planner_bf16_mode_runs_and_tracks_fp32():
         assert abs(out["bf16"][0][k] - out["fp32"][0][k]) < 3e-2 * abs(out["fp32"][0][k]) + 1e-3, (k, out)
     a, b = out["fp32"][1].flatten().double(), out["bf16"][1].flatten().double()
     assert torch.dot(a, b) / (a.norm() * b.norm()) > 0.9
+
+
+def test_disc_pos_prob_producer_matches_reference(units):
+    """device-side soft position labels (batch_producer.cu) vs the reference-minted golden vector and vs the numpy
+    restatement on a ragged batch: a degenerate axis (ground truth > 1 cm from every candidate -> one-hot at the first
+    closest candidate), a one-point cloud, both heatmap types.  Tolerance 1e-6 relative (fp64 arithmetic, fp32 storage)."""
+    ops, syn = pkg("ops"), pkg("synthetic")
+    p = units["pos_codec"]
+    xyz, gt = p["xyz"], p["gt"]
+    off = torch.tensor([0, xyz.shape[0]], dtype=torch.int32, device=DEV)
+    gta = torch.zeros(1, 7)
+    gta[0, :3] = gt
+    out = ops.disc_pos_prob(xyz.to(DEV).contiguous(), off, 1, xyz.shape[0], gta.to(DEV), 15, 0.01)
+    ref = p["prob"].float().reshape(-1)
+    assert torch.allclose(out.cpu(), ref, rtol=1e-6, atol=0), (out.cpu() - ref).abs().max()
+    # ragged batch through the packed 7-channel feature tensor
+    rng = np.random.default_rng(5)
+    sizes = [257, 1, 1000, 40]
+    clouds = [rng.uniform(-0.3, 0.3, size=(n, 3)).astype(np.float32) for n in sizes]
+    gts = np.stack([c[rng.integers(0, len(c))] + rng.normal(0, 0.003, 3).astype(np.float32) for c in clouds]).astype(np.float32)
+    gts[2, 1] = 5.0                                            # axis with no candidate within 1 cm -> fallback
+    gts[3] = clouds[3][7]                                      # exact hit: distance 0 -> weight 1 / 1e-4
+    fts = torch.from_numpy(np.concatenate([np.concatenate([c, rng.uniform(-1, 1, size=(len(c), 4)).astype(np.float32)], 1) for c in clouds]))
+    gta = torch.zeros(len(sizes), 7)
+    gta[:, :3] = torch.from_numpy(gts)
+    off = torch.tensor([0] + list(np.cumsum(sizes)), dtype=torch.int32, device=DEV)
+    for kind in ("dist", "plain"):
+        out = ops.disc_pos_prob(fts.to(DEV), off, len(sizes), max(sizes), gta.to(DEV), 15, 0.01, kind).cpu()
+        o = 0
+        for c, g in zip(clouds, gts):
+            if kind == "dist":
+                ref = syn.disc_gt_pos_prob(c, g, 0.01, 15)
+            else:                                              # action_position_utils.py:19-30
+                shift = np.arange(-15, 15) * 0.01
+                d = np.abs(g[None, :, None] - (c[:, :, None] + shift[None, None, :]))
+                d = np.transpose(d, (1, 0, 2)).reshape(3, -1)
+                ref = np.zeros_like(d, dtype=np.float32)
+                ref[d < 0.01] = 1
+                for i in range(3):
+                    if ref[i].sum() == 0:
+                        ref[i, np.argmin(d[i])] = 1
+                ref = ref / ref.sum(-1, keepdims=True)
+            n = ref.size
+            got = out[o: o + n].reshape(3, -1)
+            assert torch.allclose(got, torch.from_numpy(ref.astype(np.float32)), rtol=1e-6, atol=0), kind
+            assert torch.allclose(got.sum(-1), torch.ones(3), atol=1e-5)
+            o += n
+        assert o == out.numel()
+
+
+def test_native_step_with_device_side_labels(gold_prod):
+    """a training step fed only (pc_fts, txt, gt_actions) -- soft labels produced on the device -- gives the same losses as
+    the same step fed the host-computed `disc_pos_probs` of the collate"""
+    cfgm, syn, policy = pkg("config"), pkg("synthetic"), pkg("policy")
+    cfg = cfgm.production_model_config(attn_drop=0.0, proj_drop=0.0)
+    cfg.action_config.dropout = 0.0
+    torch.manual_seed(3)
+    model = policy.build_parameter_shell(cfg).to(DEV).train()
+    eng = model.engine()
+    eng.precision, eng.use_native = "bf16", True
+    eng.forced_perms = torch.stack([torch.arange(4)] * 5)
+    b = syn.make_batch(seed=11, sizes=[700, 300, 1200])
+    full = model.prepare_batch(dict(b))
+    _, l1 = eng.native_step(full, compute_loss=True, with_grad=False)
+    l1 = l1.clone()
+    slim = {k: v for k, v in b.items() if k != "disc_pos_probs"}
+    slim = model.prepare_batch(slim)
+    _, l2 = eng.native_step(slim, compute_loss=True, with_grad=False)
+    assert abs(l1[0].item() - l2[0].item()) <= 1e-5 * abs(l1[0].item()), (l1, l2)          # position CE: the label tensors agree
+    # (rot / open / total only see run-to-run bf16 noise: BatchNorm statistics are reduced with fp32 atomics)
+    assert torch.allclose(l1, l2, rtol=2e-3, atol=1e-4), (l1, l2)

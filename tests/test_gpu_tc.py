@@ -203,3 +203,45 @@ def test_patch_attention_tensor_core_vs_simt(H, D, drop_p):
     # (k_norm.bias has a mathematically zero gradient -- softmax shift invariance -- so it is rounding noise on both sides)
     for a, b in list(zip(res["tc"][2], res["simt"][2]))[:3]:
         assert rel(a, b) < 3e-2
+
+
+@pytest.mark.parametrize("H,D,drop_p,toks", [(2, 32, 0.0, [12, 30, 8, 1]), (4, 32, 0.1, [12, 30, 8, 32]), (8, 24, 0.1, [20, 9, 31, 5]),
+                                              (2, 16, 0.0, [33, 77, 128, 2]), (2, 64, 0.1, [40, 64, 7, 19])])
+def test_cross_attention_mma_vs_simt(H, D, drop_p, toks):
+    """warp-mma cross attention (cross_attn_mma.cu) against the SIMT kernel on the same bf16 inputs and dropout mask:
+    ragged clouds (one-point cloud, a cloud spanning several 128-point CTAs), token lists below / at / above the 32-token
+    chunk, head widths that need padding (24), forward and backward (dq, dkv, q/k-norm affine gradients)"""
+    import os
+    ops, tk = pkg("ops"), pkg("tokenizer")
+    sizes = [300, 90, 1, 417]
+    C = H * D
+    g = torch.Generator().manual_seed(H * 100 + D)
+    geo = tk.CrossGeo(torch.tensor([0] + list(np.cumsum(sizes)), dtype=torch.int32, device=DEV),
+                      torch.tensor([0] + list(np.cumsum(toks)), dtype=torch.int32, device=DEV), len(sizes), max(sizes), max(toks))
+    q0 = bf(torch.randn(sum(sizes), C, generator=g) * 1.5).to(DEV)
+    kv0 = bf(torch.randn(sum(toks), 2 * C, generator=g) * 1.5).to(DEV)
+    norm = [(1 + 0.1 * torch.randn(D, generator=g)).to(DEV), (0.1 * torch.randn(D, generator=g)).to(DEV),
+            (1 + 0.1 * torch.randn(D, generator=g)).to(DEV), (0.1 * torch.randn(D, generator=g)).to(DEV)]
+    go = bf(torch.randn(sum(sizes), C, generator=g)).to(DEV)
+    res = {}
+    for qk_norm in (True, False):
+        for mode in ("simt", "mma"):
+            if mode == "simt":
+                os.environ["LOTUS_CROSS_SIMT"] = "1"
+            else:
+                os.environ.pop("LOTUS_CROSS_SIMT", None)
+            q, kv = q0.clone().requires_grad_(True), kv0.clone().requires_grad_(True)
+            params = [t.clone().requires_grad_(True) for t in norm]
+            y = ops.CrossAttnFn.apply(q, kv, *params, geo, H, qk_norm, (drop_p, 4321, 3))
+            y.backward(go)
+            torch.cuda.synchronize()
+            res[mode] = (y.detach().float(), q.grad.float(), kv.grad.float(), [p.grad.float() if p.grad is not None else None for p in params])
+        os.environ.pop("LOTUS_CROSS_SIMT", None)
+        ys, ym = res["simt"][0], res["mma"][0]
+        assert torch.isfinite(ym).all()
+        assert rel(ym, ys) < 2e-2, rel(ym, ys)
+        assert rel(res["mma"][1], res["simt"][1]) < 3e-2, rel(res["mma"][1], res["simt"][1])
+        assert rel(res["mma"][2], res["simt"][2]) < 3e-2, rel(res["mma"][2], res["simt"][2])
+        if qk_norm:
+            for a, b in list(zip(res["mma"][3], res["simt"][3]))[:3]:
+                assert rel(a, b) < 3e-2, rel(a, b)
