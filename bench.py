@@ -211,8 +211,9 @@ class CallProfiler:
         sum(max(flops / tensor peak, bytes / HBM peak)) of its calls"""
         torch.cuda.synchronize()
         fam = {}
-        for name, args, e0, e1 in self.records:
-            ms = e0.elapsed_time(e1)
+        timed = [(name, args, e0.elapsed_time(e1)) for name, args, e0, e1 in self.records] + list(getattr(self, "native_records", []))
+        self.timed = timed
+        for name, args, ms in timed:
             fl, by = algorithmic_work(name, args, ctx)
             d = fam.setdefault(name, {"ms": 0.0, "calls": 0, "flops": 0.0, "bytes": 0.0, "floor_ms": 0.0, "t_flop_ms": 0.0, "t_byte_ms": 0.0})
             d["ms"] += ms
@@ -396,15 +397,26 @@ def main():
             torch.distributed.destroy_process_group()
         return
 
-    # ---- one profiled step: per-C-call CUDA events -> shares, dominant kernel, roofline
+    # ---- one profiled step: per-call CUDA events -> shares, dominant kernel, roofline.
+    # native engine: lotus_policy_step's own profile mode (events around every launcher call inside the C++ executor, so no
+    # Python sits between launches); the optimizer / tokeniser calls are timed around their ctypes calls.
     kernel_count = [0]
     native_calls = int(L.cdll.lotus_policy_step_calls()) if args.engine == "native" else 0
-    model.engine().use_native = False          # the per-kernel table comes from the per-op path (same kernels, same order)
-    step_fn(dict(resident[0]))
     prof = CallProfiler(L)
-    with prof:
+    if args.engine == "native":
+        native = pkg("native")
         step_fn(dict(resident[0]))
-    model.engine().use_native = args.engine == "native"
+        holder = {}
+        with prof:
+            holder["rec"] = native.profile_step(lambda: step_fn(dict(resident[0])))
+        torch.cuda.synchronize()
+        prof.native_records = [(n_, a_, ms_) for n_, a_, ms_ in holder["rec"]]
+        prof.records = [r for r in prof.records if r[0] != "lotus_policy_step"]
+    else:
+        model.engine().use_native = False
+        step_fn(dict(resident[0]))
+        with prof:
+            step_fn(dict(resident[0]))
     peaks = {}
     try:
         peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
@@ -423,7 +435,7 @@ def main():
         ctx["npad_of_patches"][pl.n_patches] = pl.n_pad
         ctx["n_of_cloud_off"][stg.cloud_off.data_ptr()] = stg.n
     fam = prof.summary(ctx, tf_peak, hbm_peak)
-    for name, args_, _, _ in prof.records:
+    for name, args_, _ in prof.timed:
         kernel_count[0] += kernels_of(name, args_)
     tot_ms = sum(d["ms"] for d in fam.values())
     top = sorted(fam.items(), key=lambda kv: -kv[1]["ms"])

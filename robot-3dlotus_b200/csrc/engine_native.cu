@@ -14,6 +14,7 @@
 #include "common.cuh"
 #include "../../include/lotus.h"
 #include <vector>
+#include <type_traits>
 #include <stdlib.h>
 
 namespace eng {
@@ -54,7 +55,36 @@ struct Ctx {
 };
 
 static long long g_launcher_calls = 0;   // launcher invocations of the last non-dry step (each launches >= 1 kernel)
-#define CALL(expr) do { if (!c.dry && c.rc == 0 && !c.ar.overflow) { ++g_launcher_calls; int _r = (expr); if (_r) c.rc = _r; } } while (0)
+// every kernel-launching C-ABI call of the step goes through CALL: in profile mode (lotus_policy_step_profile) each call is
+// bracketed by CUDA events on the launching stream and its scalar / pointer arguments are recorded, so bench.py gets per-call
+// device times of the NATIVE path (no Python between launches) together with the shapes the byte / FLOP model needs
+struct ProfRec { const char* name; cudaEvent_t e0, e1; int nargs; int64_t a[40]; };
+static bool g_prof_on = false;
+static std::vector<ProfRec> g_prof;
+static std::vector<cudaEvent_t> g_prof_events;
+static size_t g_prof_ev_next = 0;
+static cudaEvent_t prof_event() {
+  if (g_prof_ev_next == g_prof_events.size()) { cudaEvent_t e; cudaEventCreate(&e); g_prof_events.push_back(e); }
+  return g_prof_events[g_prof_ev_next++];
+}
+template <typename T> static inline int64_t prof_arg(T v) {
+  if constexpr (std::is_null_pointer_v<T>) return 0;
+  else if constexpr (std::is_pointer_v<T>) return (int64_t)(uintptr_t)v;
+  else if constexpr (std::is_floating_point_v<T>) return (int64_t)(v != 0);
+  else return (int64_t)v;
+}
+template <typename F, typename... A> static int prof_call(cudaStream_t st, const char* name, F fn, A... args) {
+  if (!g_prof_on) return fn(args...);
+  ProfRec r; r.name = name; r.nargs = (int)sizeof...(A);
+  int i = 0; ((r.a[i < 40 ? i : 39] = prof_arg(args), ++i), ...);
+  r.e0 = prof_event(); r.e1 = prof_event();
+  cudaEventRecord(r.e0, st);
+  int rc = fn(args...);
+  cudaEventRecord(r.e1, st);
+  g_prof.push_back(r);
+  return rc;
+}
+#define CALL(fn, ...) do { if (!c.dry && c.rc == 0 && !c.ar.overflow) { ++g_launcher_calls; int _r = prof_call(c.st, #fn, fn, __VA_ARGS__); if (_r) c.rc = _r; } } while (0)
 
 // Weight / bias gradients do not sit on the backward's critical path (the activation-gradient chain): they run on a
 // second stream so the small deep-stage kernels overlap.  fork: the side stream waits for everything issued so far on the
@@ -89,11 +119,11 @@ static inline float drop_p(Ctx& c, float p, uint32_t id) { return id ? p : 0.f; 
 static void linear_fwd(Ctx& c, const void* x, int M, const Lin& l, const void* residual, void* y, float dp, uint32_t did,
                        bool out_fp32 = false, bool x_bf = true) {
   if (c.bf && x_bf)
-    CALL(lotus_linear_fwd_bf16(x, c.WB[l.w], Pf(c, l.b), residual, y, nullptr, M, l.out, l.in, 0, out_fp32 ? 1 : 0, drop_p(c, dp, did),
-                               c.seed, did, c.stv));
+    CALL(lotus_linear_fwd_bf16, x, c.WB[l.w], Pf(c, l.b), residual, y, nullptr, M, l.out, l.in, 0, out_fp32 ? 1 : 0, drop_p(c, dp, did),
+                               c.seed, did, c.stv);
   else
-    CALL(lotus_linear_fwd_f32((const float*)x, Pf(c, l.w), Pf(c, l.b), (const float*)residual, (float*)y, M, l.out, l.in, 0, nullptr,
-                              drop_p(c, dp, did), c.seed, did, c.stv));
+    CALL(lotus_linear_fwd_f32, (const float*)x, Pf(c, l.w), Pf(c, l.b), (const float*)residual, (float*)y, M, l.out, l.in, 0, nullptr,
+                              drop_p(c, dp, did), c.seed, did, c.stv);
 }
 // dy: gradient of the layer output AFTER its dropout (if any) has been applied to dy by the caller.
 // dx = [dx_residual +] dy @ W ; dW += dy^T x ; db += colsum(dy).   tc: operands are bf16 (tensor-core path)
@@ -101,47 +131,47 @@ static void linear_bwd(Ctx& c, const void* dy, const void* x, int M, const Lin& 
   fork_side(c);                                  // dy (and x) are complete on the main stream at this point
   void* gs = gstream(c);
   if (tc) {
-    if (Gf(c, l.w)) CALL(lotus_linear_wgrad_bf16(dy, x, Gf(c, l.w), M, l.out, l.in, gs));
-    if (Gf(c, l.b)) CALL(lotus_colsum_bf16(dy, M, l.out, Gf(c, l.b), gs));
-    if (dx) CALL(lotus_linear_dgrad_bf16(dy, c.WT[l.w], dx_residual, dx, M, l.out, l.in, 0, c.stv));
+    if (Gf(c, l.w)) CALL(lotus_linear_wgrad_bf16, dy, x, Gf(c, l.w), M, l.out, l.in, gs);
+    if (Gf(c, l.b)) CALL(lotus_colsum_bf16, dy, M, l.out, Gf(c, l.b), gs);
+    if (dx) CALL(lotus_linear_dgrad_bf16, dy, c.WT[l.w], dx_residual, dx, M, l.out, l.in, 0, c.stv);
   } else {
-    if (Gf(c, l.w)) CALL(lotus_linear_wgrad_f32((const float*)dy, (const float*)x, Gf(c, l.w), M, l.out, l.in, nullptr, gs));
-    if (Gf(c, l.b)) CALL(lotus_colsum_f32((const float*)dy, M, l.out, Gf(c, l.b), gs));
-    if (dx) CALL(lotus_linear_dgrad_f32((const float*)dy, Pf(c, l.w), (const float*)dx_residual, (float*)dx, M, l.out, l.in, c.stv));
+    if (Gf(c, l.w)) CALL(lotus_linear_wgrad_f32, (const float*)dy, (const float*)x, Gf(c, l.w), M, l.out, l.in, nullptr, gs);
+    if (Gf(c, l.b)) CALL(lotus_colsum_f32, (const float*)dy, M, l.out, Gf(c, l.b), gs);
+    if (dx) CALL(lotus_linear_dgrad_f32, (const float*)dy, Pf(c, l.w), (const float*)dx_residual, (float*)dx, M, l.out, l.in, c.stv);
   }
 }
 // apply a dropout mask to a gradient (out of place into the arena) -- identity when the site is inactive
 static const void* drop_grad(Ctx& c, const void* dy, int64_t n, float p, uint32_t did, bool bf) {
   if (!did) return dy;
   void* o = c.ar.alloc((size_t)n * (bf ? 2 : 4));
-  if (bf) CALL(lotus_dropout_bf16(dy, o, n, p, c.seed, did, c.stv));
-  else CALL(lotus_dropout_f32((const float*)dy, (float*)o, n, p, c.seed, did, c.stv));
+  if (bf) CALL(lotus_dropout_bf16, dy, o, n, p, c.seed, did, c.stv);
+  else CALL(lotus_dropout_f32, (const float*)dy, (float*)o, n, p, c.seed, did, c.stv);
   return o;
 }
 static void ln_fwd(Ctx& c, const void* x, void* y, const void* residual, const Norm& nm, float* mean, float* rstd, int64_t rows, float eps) {
-  if (c.bf) CALL(lotus_layernorm_fwd_bf16(x, 1, nm.C, 0, y, 1, nm.C, 0, residual, Pf(c, nm.w), Pf(c, nm.b), mean, rstd, rows, nm.C, eps, c.stv));
-  else CALL(lotus_layernorm_fwd_f32((const float*)x, 1, nm.C, 0, (float*)y, 1, nm.C, 0, (const float*)residual, Pf(c, nm.w), Pf(c, nm.b), mean, rstd, rows, nm.C, eps, c.stv));
+  if (c.bf) CALL(lotus_layernorm_fwd_bf16, x, 1, nm.C, 0, y, 1, nm.C, 0, residual, Pf(c, nm.w), Pf(c, nm.b), mean, rstd, rows, nm.C, eps, c.stv);
+  else CALL(lotus_layernorm_fwd_f32, (const float*)x, 1, nm.C, 0, (float*)y, 1, nm.C, 0, (const float*)residual, Pf(c, nm.w), Pf(c, nm.b), mean, rstd, rows, nm.C, eps, c.stv);
 }
 static void ln_bwd(Ctx& c, const void* dy, const void* x, void* dx, const Norm& nm, const float* mean, const float* rstd, int64_t rows, int accumulate) {
-  if (c.bf) CALL(lotus_layernorm_bwd_bf16(dy, 0, 1, nm.C, 0, x, 1, nm.C, 0, dx, 1, nm.C, 0, Pf(c, nm.w), mean, rstd, Gf(c, nm.w), Gf(c, nm.b), rows, nm.C, accumulate, c.stv));
-  else CALL(lotus_layernorm_bwd_f32((const float*)dy, 1, nm.C, 0, (const float*)x, 1, nm.C, 0, (float*)dx, 1, nm.C, 0, Pf(c, nm.w), mean, rstd, Gf(c, nm.w), Gf(c, nm.b), rows, nm.C, accumulate, c.stv));
+  if (c.bf) CALL(lotus_layernorm_bwd_bf16, dy, 0, 1, nm.C, 0, x, 1, nm.C, 0, dx, 1, nm.C, 0, Pf(c, nm.w), mean, rstd, Gf(c, nm.w), Gf(c, nm.b), rows, nm.C, accumulate, c.stv);
+  else CALL(lotus_layernorm_bwd_f32, (const float*)dy, 1, nm.C, 0, (const float*)x, 1, nm.C, 0, (float*)dx, 1, nm.C, 0, Pf(c, nm.w), mean, rstd, Gf(c, nm.w), Gf(c, nm.b), rows, nm.C, accumulate, c.stv);
 }
 // per-head LayerNorm over Dh of a strided view (rows = N*H): x row (n,h) at n*x_outer + h*Dh -> y contiguous (N*H, Dh)
 static void head_ln_fwd(Ctx& c, const void* x, int64_t x_outer, void* y, const Norm& nm, float* mean, float* rstd, int64_t N, int H) {
   int D = nm.C;
-  if (c.bf) CALL(lotus_layernorm_fwd_bf16(x, H, x_outer, D, y, 1, D, 0, nullptr, Pf(c, nm.w), Pf(c, nm.b), mean, rstd, N * H, D, 1e-6f, c.stv));
-  else CALL(lotus_layernorm_fwd_f32((const float*)x, H, x_outer, D, (float*)y, 1, D, 0, nullptr, Pf(c, nm.w), Pf(c, nm.b), mean, rstd, N * H, D, 1e-6f, c.stv));
+  if (c.bf) CALL(lotus_layernorm_fwd_bf16, x, H, x_outer, D, y, 1, D, 0, nullptr, Pf(c, nm.w), Pf(c, nm.b), mean, rstd, N * H, D, 1e-6f, c.stv);
+  else CALL(lotus_layernorm_fwd_f32, (const float*)x, H, x_outer, D, (float*)y, 1, D, 0, nullptr, Pf(c, nm.w), Pf(c, nm.b), mean, rstd, N * H, D, 1e-6f, c.stv);
 }
 // dy fp32 contiguous (N*H, Dh) -> dx strided like x
 static void head_ln_bwd(Ctx& c, const float* dy, const void* x, int64_t x_outer, void* dx, const Norm& nm, const float* mean,
                         const float* rstd, int64_t N, int H) {
   int D = nm.C;
-  if (c.bf) CALL(lotus_layernorm_bwd_bf16(dy, 1, 1, D, 0, x, H, x_outer, D, dx, H, x_outer, D, Pf(c, nm.w), mean, rstd, Gf(c, nm.w), Gf(c, nm.b), N * H, D, 0, c.stv));
-  else CALL(lotus_layernorm_bwd_f32(dy, 1, D, 0, (const float*)x, H, x_outer, D, (float*)dx, H, x_outer, D, Pf(c, nm.w), mean, rstd, Gf(c, nm.w), Gf(c, nm.b), N * H, D, 0, c.stv));
+  if (c.bf) CALL(lotus_layernorm_bwd_bf16, dy, 1, 1, D, 0, x, H, x_outer, D, dx, H, x_outer, D, Pf(c, nm.w), mean, rstd, Gf(c, nm.w), Gf(c, nm.b), N * H, D, 0, c.stv);
+  else CALL(lotus_layernorm_bwd_f32, dy, 1, D, 0, (const float*)x, H, x_outer, D, (float*)dx, H, x_outer, D, Pf(c, nm.w), mean, rstd, Gf(c, nm.w), Gf(c, nm.b), N * H, D, 0, c.stv);
 }
 static void pointwise(Ctx& c, const void* x, const void* a, void* y, int64_t n, int op, float dp, uint32_t did, bool bf) {
-  if (bf) CALL(lotus_pointwise_bf16(x, a, y, n, op, 0.02f, drop_p(c, dp, did), c.seed, did, c.stv));
-  else CALL(lotus_pointwise_f32((const float*)x, (const float*)a, (float*)y, n, op, 0.02f, drop_p(c, dp, did), c.seed, did, c.stv));
+  if (bf) CALL(lotus_pointwise_bf16, x, a, y, n, op, 0.02f, drop_p(c, dp, did), c.seed, did, c.stv);
+  else CALL(lotus_pointwise_f32, (const float*)x, (const float*)a, (float*)y, n, op, 0.02f, drop_p(c, dp, did), c.seed, did, c.stv);
 }
 
 struct BnSave { const void* x; float *mean, *rstd; int64_t rows; bool x_fp32; };
@@ -150,16 +180,16 @@ static void bn_fwd(Ctx& c, const void* x, bool x_fp32, void* y, int64_t rows, co
   sv.mean = f32(c, b.C); sv.rstd = f32(c, b.C);
   float* scratch = f32(c, b.C);
   float* rm = (float*)c.BN[2 * b.buf]; float* rv = (float*)c.BN[2 * b.buf + 1];
-  if (c.bf) CALL(lotus_batchnorm_fwd_bf16(x, x_fp32 ? 1 : 0, y, rows, b.C, Pf(c, b.w), Pf(c, b.b), rm, rv, sv.mean, sv.rstd, scratch, c.train ? 1 : 0, 1e-3f, 0.01f, 1, c.stv));
-  else CALL(lotus_batchnorm_fwd_f32((const float*)x, (float*)y, rows, b.C, Pf(c, b.w), Pf(c, b.b), rm, rv, sv.mean, sv.rstd, scratch, c.train ? 1 : 0, 1e-3f, 0.01f, 1, c.stv));
+  if (c.bf) CALL(lotus_batchnorm_fwd_bf16, x, x_fp32 ? 1 : 0, y, rows, b.C, Pf(c, b.w), Pf(c, b.b), rm, rv, sv.mean, sv.rstd, scratch, c.train ? 1 : 0, 1e-3f, 0.01f, 1, c.stv);
+  else CALL(lotus_batchnorm_fwd_f32, (const float*)x, (float*)y, rows, b.C, Pf(c, b.w), Pf(c, b.b), rm, rv, sv.mean, sv.rstd, scratch, c.train ? 1 : 0, 1e-3f, 0.01f, 1, c.stv);
 }
 static void bn_bwd(Ctx& c, const void* dy, void* dx, const BNorm& b, const BnSave& sv) {
   float* dg = f32(c, 2 * b.C); float* db = dg + b.C;
   zero(c, dg, (size_t)2 * b.C * 4);
-  if (c.bf) CALL(lotus_batchnorm_bwd_bf16(dy, sv.x, sv.x_fp32 ? 1 : 0, sv.rows, b.C, Pf(c, b.w), Pf(c, b.b), sv.mean, sv.rstd, dx, dg, db, c.train ? 1 : 0, 1, c.stv));
-  else CALL(lotus_batchnorm_bwd_f32((const float*)dy, (const float*)sv.x, sv.rows, b.C, Pf(c, b.w), Pf(c, b.b), sv.mean, sv.rstd, (float*)dx, dg, db, c.train ? 1 : 0, 1, c.stv));
-  if (Gf(c, b.w)) CALL(lotus_pointwise_f32(dg, Gf(c, b.w), Gf(c, b.w), b.C, 4, 0.f, 0.f, 0, 0, c.stv));
-  if (Gf(c, b.b)) CALL(lotus_pointwise_f32(db, Gf(c, b.b), Gf(c, b.b), b.C, 4, 0.f, 0.f, 0, 0, c.stv));
+  if (c.bf) CALL(lotus_batchnorm_bwd_bf16, dy, sv.x, sv.x_fp32 ? 1 : 0, sv.rows, b.C, Pf(c, b.w), Pf(c, b.b), sv.mean, sv.rstd, dx, dg, db, c.train ? 1 : 0, 1, c.stv);
+  else CALL(lotus_batchnorm_bwd_f32, (const float*)dy, (const float*)sv.x, sv.rows, b.C, Pf(c, b.w), Pf(c, b.b), sv.mean, sv.rstd, (float*)dx, dg, db, c.train ? 1 : 0, 1, c.stv);
+  if (Gf(c, b.w)) CALL(lotus_pointwise_f32, dg, Gf(c, b.w), Gf(c, b.w), b.C, 4, 0.f, 0.f, 0, 0, c.stv);
+  if (Gf(c, b.b)) CALL(lotus_pointwise_f32, db, Gf(c, b.b), Gf(c, b.b), b.C, 4, 0.f, 0.f, 0, 0, c.stv);
 }
 
 // ------------------------------------------------------------------------------------------------ MLP tail shared by Block / CABlock
@@ -174,8 +204,8 @@ static void* mlp_fwd(Ctx& c, void* x2, int n, const Norm& n2, const Lin& fc1, co
   sv.d_act = drop_id(c, c.proj_drop);
   if (c.bf) {
     // GELU + dropout fused into the GEMM epilogue; the pre-activation is a second TMA store (only kept when a backward follows)
-    CALL(lotus_linear_fwd_bf16(sv.h2, c.WB[fc1.w], Pf(c, fc1.b), nullptr, sv.g, c.G ? sv.u : nullptr, n, fc1.out, fc1.in, 1, 0,
-                               drop_p(c, c.proj_drop, sv.d_act), c.seed, sv.d_act, c.stv));
+    CALL(lotus_linear_fwd_bf16, sv.h2, c.WB[fc1.w], Pf(c, fc1.b), nullptr, sv.g, c.G ? sv.u : nullptr, n, fc1.out, fc1.in, 1, 0,
+                               drop_p(c, c.proj_drop, sv.d_act), c.seed, sv.d_act, c.stv);
   } else {
     linear_fwd(c, sv.h2, n, fc1, nullptr, sv.u, 0.f, 0);
     pointwise(c, sv.u, nullptr, sv.g, (int64_t)n * fc1.out, 0, c.proj_drop, sv.d_act, c.bf);
@@ -193,8 +223,8 @@ static void mlp_bwd(Ctx& c, void* D, int n, const Norm& n2, const Lin& fc1, cons
   if (c.bf) {
     // du = drop'(gelu'(u)) * (dyd @ W2): the activation backward rides in the data-gradient GEMM's epilogue
     linear_bwd(c, dyd, sv.g, n, fc2, nullptr, nullptr, true);                            // weight / bias gradients only
-    CALL(lotus_linear_dgrad_act_bf16(dyd, c.WT[fc2.w], sv.u, dg, n, fc2.out, fc2.in, 1, drop_p(c, c.proj_drop, sv.d_act), c.seed,
-                                     sv.d_act, c.stv));
+    CALL(lotus_linear_dgrad_act_bf16, dyd, c.WT[fc2.w], sv.u, dg, n, fc2.out, fc2.in, 1, drop_p(c, c.proj_drop, sv.d_act), c.seed,
+                                     sv.d_act, c.stv);
   } else {
     linear_bwd(c, dyd, sv.g, n, fc2, dg, nullptr, false);
     pointwise(c, sv.u, dg, dg, (int64_t)n * fc1.out, 1, c.proj_drop, sv.d_act, false);   // du in place
@@ -215,8 +245,8 @@ static void* block_fwd(Ctx& c, const BlockP& b, const StageInfo& sg, void* x0, c
   int n = sg.n, C = b.C, H = b.H, D = C / H;
   sv.n = n; sv.x0 = x0; sv.conv_in = conv_in ? conv_in : x0; sv.own_conv_in = conv_in != nullptr;
   sv.c0 = act(c, n, C);
-  if (c.bf) CALL(lotus_subm_conv_fwd_bf16(sv.conv_in, c.WB[b.conv_w], Pf(c, b.conv_b), sv.c0, sg.nbr3, sg.stride, n, C, C, 27, 0, c.stv));
-  else CALL(lotus_subm_conv_fwd_f32((const float*)sv.conv_in, Pf(c, b.conv_w), Pf(c, b.conv_b), (float*)sv.c0, sg.nbr3, sg.stride, n, C, C, 27, c.stv));
+  if (c.bf) CALL(lotus_subm_conv_fwd_bf16, sv.conv_in, c.WB[b.conv_w], Pf(c, b.conv_b), sv.c0, sg.nbr3, sg.stride, n, C, C, 27, 0, c.stv);
+  else CALL(lotus_subm_conv_fwd_f32, (const float*)sv.conv_in, Pf(c, b.conv_w), Pf(c, b.conv_b), (float*)sv.c0, sg.nbr3, sg.stride, n, C, C, 27, c.stv);
   sv.c1 = act(c, n, C);
   linear_fwd(c, sv.c0, n, b.cpe1, nullptr, sv.c1, 0.f, 0);
   sv.cpe_mean = f32(c, n); sv.cpe_rstd = f32(c, n);
@@ -241,8 +271,8 @@ static void* block_fwd(Ctx& c, const BlockP& b, const StageInfo& sg, void* x0, c
   sv.d_attn = drop_id(c, c.attn_drop);
   const void* vp = (char*)sv.qkv + (size_t)2 * C * c.es;
   float scale = 1.0f / sqrtf((float)D);
-  if (c.bf) CALL(lotus_patch_attn_fwd_bf16(qp, kp, vp, ldq, ldq, 3 * C, sg.gather_idx, sg.slot_of_point, sg.cu_seqlens, sg.n_patches, c.K, H, D, scale, nullptr, nullptr, 0, sv.o, C, sv.lse, drop_p(c, c.attn_drop, sv.d_attn), c.seed, sv.d_attn, c.stv));
-  else CALL(lotus_patch_attn_fwd_f32((const float*)qp, (const float*)kp, (const float*)vp, ldq, ldq, 3 * C, sg.gather_idx, sg.slot_of_point, sg.cu_seqlens, sg.n_patches, c.K, H, D, scale, nullptr, nullptr, 0, (float*)sv.o, C, sv.lse, drop_p(c, c.attn_drop, sv.d_attn), c.seed, sv.d_attn, c.stv));
+  if (c.bf) CALL(lotus_patch_attn_fwd_bf16, qp, kp, vp, ldq, ldq, 3 * C, sg.gather_idx, sg.slot_of_point, sg.cu_seqlens, sg.n_patches, c.K, H, D, scale, nullptr, nullptr, 0, sv.o, C, sv.lse, drop_p(c, c.attn_drop, sv.d_attn), c.seed, sv.d_attn, c.stv);
+  else CALL(lotus_patch_attn_fwd_f32, (const float*)qp, (const float*)kp, (const float*)vp, ldq, ldq, 3 * C, sg.gather_idx, sg.slot_of_point, sg.cu_seqlens, sg.n_patches, c.K, H, D, scale, nullptr, nullptr, 0, (float*)sv.o, C, sv.lse, drop_p(c, c.attn_drop, sv.d_attn), c.seed, sv.d_attn, c.stv);
   void* x2 = act(c, n, C);
   sv.d_proj = drop_id(c, c.proj_drop);
   linear_fwd(c, sv.o, n, b.proj, sv.x1, x2, c.proj_drop, sv.d_proj);
@@ -271,21 +301,21 @@ static void block_bwd(Ctx& c, const BlockP& b, const StageInfo& sg, void* D, con
     if (c.bf) zero(c, dvh, (size_t)n * C * 4); else zero(c, dqkv, (size_t)n * 3 * C * 4);
     const void *qp = c.qk_norm ? sv.qh : sv.qkv, *kp = c.qk_norm ? sv.kh : (void*)((char*)sv.qkv + (size_t)C * c.es);
     int64_t ldq = c.qk_norm ? C : 3 * C;
-    if (c.bf) CALL(lotus_patch_attn_bwd_bf16(qp, kp, vp, ldq, ldq, 3 * C, sg.gather_idx, sg.slot_of_point, sg.cu_seqlens, sg.n_patches, c.K, H, Dh, scale, nullptr, nullptr, 0, nullptr, sv.o, dout, C, sv.lse, dqh, dkh, dvh, C, C, lddv, drop_p(c, c.attn_drop, sv.d_attn), c.seed, sv.d_attn, c.stv));
-    else CALL(lotus_patch_attn_bwd_f32((const float*)qp, (const float*)kp, (const float*)vp, ldq, ldq, 3 * C, sg.gather_idx, sg.slot_of_point, sg.cu_seqlens, sg.n_patches, c.K, H, Dh, scale, nullptr, nullptr, 0, nullptr, (const float*)sv.o, (const float*)dout, C, sv.lse, dqh, dkh, dvh, C, C, lddv, drop_p(c, c.attn_drop, sv.d_attn), c.seed, sv.d_attn, c.stv));
+    if (c.bf) CALL(lotus_patch_attn_bwd_bf16, qp, kp, vp, ldq, ldq, 3 * C, sg.gather_idx, sg.slot_of_point, sg.cu_seqlens, sg.n_patches, c.K, H, Dh, scale, nullptr, nullptr, 0, nullptr, sv.o, dout, C, sv.lse, dqh, dkh, dvh, C, C, lddv, drop_p(c, c.attn_drop, sv.d_attn), c.seed, sv.d_attn, c.stv);
+    else CALL(lotus_patch_attn_bwd_f32, (const float*)qp, (const float*)kp, (const float*)vp, ldq, ldq, 3 * C, sg.gather_idx, sg.slot_of_point, sg.cu_seqlens, sg.n_patches, c.K, H, Dh, scale, nullptr, nullptr, 0, nullptr, (const float*)sv.o, (const float*)dout, C, sv.lse, dqh, dkh, dvh, C, C, lddv, drop_p(c, c.attn_drop, sv.d_attn), c.seed, sv.d_attn, c.stv);
     if (c.qk_norm) {
       int64_t nh = (int64_t)n * H;
       head_ln_bwd(c, dqh, sv.qkv, 3 * C, dqkv, b.qn, sv.qk_stats, sv.qk_stats + nh, n, H);
       head_ln_bwd(c, dkh, (char*)sv.qkv + (size_t)C * c.es, 3 * C, (char*)dqkv + (size_t)C * c.es, b.kn, sv.qk_stats + 2 * nh, sv.qk_stats + 3 * nh, n, H);
     } else {
-      CALL(lotus_convert_rows_f32_to_bf16(dqh, C, dqkv, 3 * C, n, C, c.stv));
-      CALL(lotus_convert_rows_f32_to_bf16(dkh, C, (char*)dqkv + (size_t)C * 2, 3 * C, n, C, c.stv));
+      CALL(lotus_convert_rows_f32_to_bf16, dqh, C, dqkv, 3 * C, n, C, c.stv);
+      CALL(lotus_convert_rows_f32_to_bf16, dkh, C, (char*)dqkv + (size_t)C * 2, 3 * C, n, C, c.stv);
     }
-    if (c.bf) CALL(lotus_convert_rows_f32_to_bf16(dvh, C, (char*)dqkv + (size_t)2 * C * 2, 3 * C, n, C, c.stv));
+    if (c.bf) CALL(lotus_convert_rows_f32_to_bf16, dvh, C, (char*)dqkv + (size_t)2 * C * 2, 3 * C, n, C, c.stv);
   } else {
     zero(c, dqkv, (size_t)n * 3 * C * 4);
     float* dq = (float*)dqkv;
-    CALL(lotus_patch_attn_bwd_f32((const float*)sv.qkv, (const float*)sv.qkv + C, (const float*)vp, 3 * C, 3 * C, 3 * C, sg.gather_idx, sg.slot_of_point, sg.cu_seqlens, sg.n_patches, c.K, H, Dh, scale, nullptr, nullptr, 0, nullptr, (const float*)sv.o, (const float*)dout, C, sv.lse, dq, dq + C, dq + 2 * C, 3 * C, 3 * C, 3 * C, drop_p(c, c.attn_drop, sv.d_attn), c.seed, sv.d_attn, c.stv));
+    CALL(lotus_patch_attn_bwd_f32, (const float*)sv.qkv, (const float*)sv.qkv + C, (const float*)vp, 3 * C, 3 * C, 3 * C, sg.gather_idx, sg.slot_of_point, sg.cu_seqlens, sg.n_patches, c.K, H, Dh, scale, nullptr, nullptr, 0, nullptr, (const float*)sv.o, (const float*)dout, C, sv.lse, dq, dq + C, dq + 2 * C, 3 * C, 3 * C, 3 * C, drop_p(c, c.attn_drop, sv.d_attn), c.seed, sv.d_attn, c.stv);
   }
   void* dh1 = act(c, n, C);
   linear_bwd(c, dqkv, sv.h1, n, b.qkv, dh1, nullptr, c.bf);
@@ -301,13 +331,13 @@ static void block_bwd(Ctx& c, const BlockP& b, const StageInfo& sg, void* D, con
   fork_side(c);
   void* gs = gstream(c);
   if (c.bf) {
-    if (Gf(c, b.conv_w)) CALL(lotus_subm_conv_wgrad_pairs_bf16(dc0, sv.conv_in, Gf(c, b.conv_w), sg.pairs_out, sg.pairs_in, sg.pair_cnt, sg.stride, n, C, C, 27, gs));
-    if (Gf(c, b.conv_b)) CALL(lotus_colsum_bf16(dc0, n, C, Gf(c, b.conv_b), gs));
-    CALL(lotus_subm_conv_dgrad_bf16(dc0, c.WT[b.conv_w], D, dxo, sg.nbr3, sg.stride, n, C, C, 27, 0, c.stv));
+    if (Gf(c, b.conv_w)) CALL(lotus_subm_conv_wgrad_pairs_bf16, dc0, sv.conv_in, Gf(c, b.conv_w), sg.pairs_out, sg.pairs_in, sg.pair_cnt, sg.stride, n, C, C, 27, gs);
+    if (Gf(c, b.conv_b)) CALL(lotus_colsum_bf16, dc0, n, C, Gf(c, b.conv_b), gs);
+    CALL(lotus_subm_conv_dgrad_bf16, dc0, c.WT[b.conv_w], D, dxo, sg.nbr3, sg.stride, n, C, C, 27, 0, c.stv);
   } else {
-    if (Gf(c, b.conv_w)) CALL(lotus_subm_conv_wgrad_f32((const float*)dc0, (const float*)sv.conv_in, Gf(c, b.conv_w), sg.nbr3, sg.stride, n, C, C, 27, gs));
-    if (Gf(c, b.conv_b)) CALL(lotus_colsum_f32((const float*)dc0, n, C, Gf(c, b.conv_b), gs));
-    CALL(lotus_subm_conv_dgrad_f32((const float*)dc0, Pf(c, b.conv_w), (const float*)D, (float*)dxo, sg.nbr3, sg.stride, n, C, C, 27, c.stv));
+    if (Gf(c, b.conv_w)) CALL(lotus_subm_conv_wgrad_f32, (const float*)dc0, (const float*)sv.conv_in, Gf(c, b.conv_w), sg.nbr3, sg.stride, n, C, C, 27, gs);
+    if (Gf(c, b.conv_b)) CALL(lotus_colsum_f32, (const float*)dc0, n, C, Gf(c, b.conv_b), gs);
+    CALL(lotus_subm_conv_dgrad_f32, (const float*)dc0, Pf(c, b.conv_w), (const float*)D, (float*)dxo, sg.nbr3, sg.stride, n, C, C, 27, c.stv);
   }
   join_side(c);                                                                          // before the temporaries are reused
   c.ar.off = mark;
@@ -339,8 +369,8 @@ static void* ca_fwd(Ctx& c, const CaP& b, const StageInfo& sg, void* x0, const v
   sv.d_attn = drop_id(c, c.attn_drop);
   const void* vp = (char*)sv.kv + (size_t)C * c.es;
   float scale = 1.0f / sqrtf((float)D);
-  if (c.bf) CALL(lotus_cross_attn_fwd_bf16(qp, C, kp, vp, ldk, 2 * C, sg.cloud_off, c.tok_off, c.B, sg.max_cloud, c.max_tok, H, D, scale, sv.o, C, sv.lse, drop_p(c, c.attn_drop, sv.d_attn), c.seed, sv.d_attn, c.stv));
-  else CALL(lotus_cross_attn_fwd_f32((const float*)qp, C, (const float*)kp, (const float*)vp, ldk, 2 * C, sg.cloud_off, c.tok_off, c.B, sg.max_cloud, c.max_tok, H, D, scale, (float*)sv.o, C, sv.lse, drop_p(c, c.attn_drop, sv.d_attn), c.seed, sv.d_attn, c.stv));
+  if (c.bf) CALL(lotus_cross_attn_fwd_bf16, qp, C, kp, vp, ldk, 2 * C, sg.cloud_off, c.tok_off, c.B, sg.max_cloud, c.max_tok, H, D, scale, sv.o, C, sv.lse, drop_p(c, c.attn_drop, sv.d_attn), c.seed, sv.d_attn, c.stv);
+  else CALL(lotus_cross_attn_fwd_f32, (const float*)qp, C, (const float*)kp, (const float*)vp, ldk, 2 * C, sg.cloud_off, c.tok_off, c.B, sg.max_cloud, c.max_tok, H, D, scale, (float*)sv.o, C, sv.lse, drop_p(c, c.attn_drop, sv.d_attn), c.seed, sv.d_attn, c.stv);
   void* x2 = act(c, n, C);
   sv.d_proj = drop_id(c, c.proj_drop);
   linear_fwd(c, sv.o, n, b.proj, x0, x2, c.proj_drop, sv.d_proj);
@@ -366,19 +396,19 @@ static void ca_bwd(Ctx& c, const CaP& b, const StageInfo& sg, void* D, const voi
     if (c.bf) zero(c, dvh, (size_t)Lt * C * 4); else zero(c, dkv, (size_t)Lt * 2 * C * 4);
     const void *qp = c.qk_norm ? sv.qh : sv.q, *kp = c.qk_norm ? sv.kh : sv.kv;
     int64_t ldk = c.qk_norm ? C : 2 * C;
-    if (c.bf) CALL(lotus_cross_attn_bwd_bf16(qp, C, kp, vp, ldk, 2 * C, sg.cloud_off, c.tok_off, c.B, sg.max_cloud, c.max_tok, H, Dh, scale, sv.o, dout, C, sv.lse, dqh, C, dkh, dvh, C, lddv, drop_p(c, c.attn_drop, sv.d_attn), c.seed, sv.d_attn, c.stv));
-    else CALL(lotus_cross_attn_bwd_f32((const float*)qp, C, (const float*)kp, (const float*)vp, ldk, 2 * C, sg.cloud_off, c.tok_off, c.B, sg.max_cloud, c.max_tok, H, Dh, scale, (const float*)sv.o, (const float*)dout, C, sv.lse, dqh, C, dkh, dvh, C, lddv, drop_p(c, c.attn_drop, sv.d_attn), c.seed, sv.d_attn, c.stv));
+    if (c.bf) CALL(lotus_cross_attn_bwd_bf16, qp, C, kp, vp, ldk, 2 * C, sg.cloud_off, c.tok_off, c.B, sg.max_cloud, c.max_tok, H, Dh, scale, sv.o, dout, C, sv.lse, dqh, C, dkh, dvh, C, lddv, drop_p(c, c.attn_drop, sv.d_attn), c.seed, sv.d_attn, c.stv);
+    else CALL(lotus_cross_attn_bwd_f32, (const float*)qp, C, (const float*)kp, (const float*)vp, ldk, 2 * C, sg.cloud_off, c.tok_off, c.B, sg.max_cloud, c.max_tok, H, Dh, scale, (const float*)sv.o, (const float*)dout, C, sv.lse, dqh, C, dkh, dvh, C, lddv, drop_p(c, c.attn_drop, sv.d_attn), c.seed, sv.d_attn, c.stv);
     if (c.qk_norm) {
       head_ln_bwd(c, dqh, sv.q, C, dq, b.qn, sv.q_stats, sv.q_stats + (int64_t)n * H, n, H);
       head_ln_bwd(c, dkh, sv.kv, 2 * C, dkv, b.kn, sv.k_stats, sv.k_stats + (int64_t)Lt * H, Lt, H);
     } else {
-      CALL(lotus_convert_rows_f32_to_bf16(dqh, C, dq, C, n, C, c.stv));
-      CALL(lotus_convert_rows_f32_to_bf16(dkh, C, dkv, 2 * C, Lt, C, c.stv));
+      CALL(lotus_convert_rows_f32_to_bf16, dqh, C, dq, C, n, C, c.stv);
+      CALL(lotus_convert_rows_f32_to_bf16, dkh, C, dkv, 2 * C, Lt, C, c.stv);
     }
-    if (c.bf) CALL(lotus_convert_rows_f32_to_bf16(dvh, C, (char*)dkv + (size_t)C * 2, 2 * C, Lt, C, c.stv));
+    if (c.bf) CALL(lotus_convert_rows_f32_to_bf16, dvh, C, (char*)dkv + (size_t)C * 2, 2 * C, Lt, C, c.stv);
   } else {
     zero(c, dkv, (size_t)Lt * 2 * C * 4);
-    CALL(lotus_cross_attn_bwd_f32((const float*)sv.q, C, (const float*)sv.kv, (const float*)vp, 2 * C, 2 * C, sg.cloud_off, c.tok_off, c.B, sg.max_cloud, c.max_tok, H, Dh, scale, (const float*)sv.o, (const float*)dout, C, sv.lse, (float*)dq, C, (float*)dkv, (float*)dkv + C, 2 * C, 2 * C, drop_p(c, c.attn_drop, sv.d_attn), c.seed, sv.d_attn, c.stv));
+    CALL(lotus_cross_attn_bwd_f32, (const float*)sv.q, C, (const float*)sv.kv, (const float*)vp, 2 * C, 2 * C, sg.cloud_off, c.tok_off, c.B, sg.max_cloud, c.max_tok, H, Dh, scale, (const float*)sv.o, (const float*)dout, C, sv.lse, (float*)dq, C, (float*)dkv, (float*)dkv + C, 2 * C, 2 * C, drop_p(c, c.attn_drop, sv.d_attn), c.seed, sv.d_attn, c.stv);
   }
   linear_bwd(c, dkv, ctx, Lt, b.kv, dctx, *dctx_init ? dctx : nullptr, c.bf);           // dctx (+)= dkv @ Wkv
   *dctx_init = true;
@@ -459,8 +489,8 @@ static void stage_weight(Ctx& c, int idx, int A, int D, int Bdim) {
   g_stage.A.push_back(A); g_stage.D.push_back(D); g_stage.B.push_back(Bdim);
 }
 static void stage_flush(Ctx& c, bool skip) {
-  if (!skip) CALL(lotus_cast_transpose_batch_bf16(g_stage.w.data(), g_stage.wb.data(), g_stage.wt.data(), g_stage.A.data(), g_stage.D.data(),
-                                       g_stage.B.data(), (int)g_stage.w.size(), c.stv));
+  if (!skip) CALL(lotus_cast_transpose_batch_bf16, g_stage.w.data(), g_stage.wb.data(), g_stage.wt.data(), g_stage.A.data(), g_stage.D.data(),
+                                       g_stage.B.data(), (int)g_stage.w.size(), c.stv);
   g_stage = StageList();
 }
 static void stage_lin(Ctx& c, const Lin& l) { stage_weight(c, l.w, l.out, 1, l.in); }
@@ -497,7 +527,8 @@ LOTUS_API int lotus_policy_step(const int64_t* cfg, const int64_t* run, const in
   c.train = run[5] != 0; c.bf = run[6] != 0; bool compute_loss = run[7] != 0, use_gt_pos = run[8] != 0; c.dry = run[9] != 0;
   c.es = c.bf ? 2 : 4; c.rc = 0; c.seed = seed; c.drop_next = 1;
   c.side = nullptr; c.sidev = nullptr; c.side_busy = false;
-  if (!c.dry && grads != nullptr && run[7] != 0 && getenv("LOTUS_NO_SIDE_STREAM") == nullptr) {
+  if (!c.dry) { g_prof.clear(); g_prof_ev_next = 0; }
+  if (!c.dry && grads != nullptr && run[7] != 0 && !g_prof_on && getenv("LOTUS_NO_SIDE_STREAM") == nullptr) {
     if (!g_side) {
       LOTUS_CUDA_CALL(cudaStreamCreateWithFlags(&g_side, cudaStreamNonBlocking));
       LOTUS_CUDA_CALL(cudaEventCreateWithFlags(&g_ev_fork, cudaEventDisableTiming));
@@ -538,12 +569,12 @@ LOTUS_API int lotus_policy_step(const int64_t* cfg, const int64_t* run, const in
   const int N0 = sg[0].n, Lt = c.Lt;
   // ---------------- context tokens
   const void* txt_in = txt;
-  if (c.bf) { void* t = c.ar.alloc((size_t)Lt * m.txtC * 2); CALL(lotus_convert(txt, t, (int64_t)Lt * m.txtC, 0, c.stv)); txt_in = t; }
+  if (c.bf) { void* t = c.ar.alloc((size_t)Lt * m.txtC * 2); CALL(lotus_convert, txt, t, (int64_t)Lt * m.txtC, 0, c.stv); txt_in = t; }
   void* ctx = act(c, Lt, m.ctxC);
   linear_fwd(c, txt_in, Lt, m.txt_fc, nullptr, ctx, 0.f, 0);
   // ---------------- stem (fp32 SIMT conv, narrow input) + BN + GELU
   float* stem_out = f32(c, (int64_t)N0 * m.encC[0]);
-  CALL(lotus_subm_conv_fwd_f32(feat, Pf(c, m.stem_w), nullptr, stem_out, sg[0].nbr5, sg[0].stride, N0, m.inC, m.encC[0], 125, c.stv));
+  CALL(lotus_subm_conv_fwd_f32, feat, Pf(c, m.stem_w), nullptr, stem_out, sg[0].nbr5, sg[0].stride, N0, m.inC, m.encC[0], 125, c.stv);
   BnSave stem_sv;
   void* x = act(c, N0, m.encC[0]);
   bn_fwd(c, stem_out, true, x, N0, m.stem_bn, stem_sv);
@@ -561,8 +592,8 @@ LOTUS_API int lotus_policy_step(const int64_t* cfg, const int64_t* run, const in
       linear_fwd(c, x, np, m.pool[s].proj, nullptr, pool_proj[s], 0.f, 0);
       pooled[s] = act(c, n, C);
       pool_arg[s] = (int32_t*)c.ar.alloc((size_t)n * C * 4);
-      if (c.bf) CALL(lotus_segment_max_fwd_bf16(pool_proj[s], C, sg[s].seg_ptr, sg[s].member, n, pooled[s], pool_arg[s], c.stv));
-      else CALL(lotus_segment_max_fwd_f32((const float*)pool_proj[s], C, sg[s].seg_ptr, sg[s].member, n, (float*)pooled[s], pool_arg[s], c.stv));
+      if (c.bf) CALL(lotus_segment_max_fwd_bf16, pool_proj[s], C, sg[s].seg_ptr, sg[s].member, n, pooled[s], pool_arg[s], c.stv);
+      else CALL(lotus_segment_max_fwd_f32, (const float*)pool_proj[s], C, sg[s].seg_ptr, sg[s].member, n, (float*)pooled[s], pool_arg[s], c.stv);
       x = act(c, n, C);
       bn_fwd(c, pooled[s], false, x, n, m.pool[s].bn, poolBn[s]);
     }
@@ -582,8 +613,8 @@ LOTUS_API int lotus_policy_step(const int64_t* cfg, const int64_t* run, const in
     up_b[s] = act(c, n, C);
     bn_fwd(c, up_skip_lin[s], false, up_b[s], n, m.unpool[s].bn_skip, upBnSkip[s]);
     void* xu = act(c, n, C);
-    if (c.bf) CALL(lotus_unpool_add_bf16(up_b[s], up_a[s], sg[s + 1].cluster, n, C, xu, c.stv));
-    else CALL(lotus_unpool_add_f32((const float*)up_b[s], (const float*)up_a[s], sg[s + 1].cluster, n, C, (float*)xu, c.stv));
+    if (c.bf) CALL(lotus_unpool_add_bf16, up_b[s], up_a[s], sg[s + 1].cluster, n, C, xu, c.stv);
+    else CALL(lotus_unpool_add_f32, (const float*)up_b[s], (const float*)up_a[s], sg[s + 1].cluster, n, C, (float*)xu, c.stv);
     x = block_fwd(c, m.decB[s], sg[s], xu, up_b[s], dB[s]);          // the CPE conv reads the skip branch only (model.py:824 vs 235-238)
     x = ca_fwd(c, m.decCA[s], sg[s], x, ctx, dC[s]);
   }
@@ -598,8 +629,8 @@ LOTUS_API int lotus_policy_step(const int64_t* cfg, const int64_t* run, const in
   linear_fwd(c, hl, N0, m.hm3, nullptr, heat, 0.f, 0, true, false);
   void* pc = act(c, B, hid);
   int32_t* pc_arg = (int32_t*)c.ar.alloc((size_t)B * hid * 4);
-  if (c.bf) CALL(lotus_segment_max_fwd_bf16(x, hid, sg[0].cloud_off, nullptr, B, pc, pc_arg, c.stv));
-  else CALL(lotus_segment_max_fwd_f32((const float*)x, hid, sg[0].cloud_off, nullptr, B, (float*)pc, pc_arg, c.stv));
+  if (c.bf) CALL(lotus_segment_max_fwd_bf16, x, hid, sg[0].cloud_off, nullptr, B, pc, pc_arg, c.stv);
+  else CALL(lotus_segment_max_fwd_f32, (const float*)x, hid, sg[0].cloud_off, nullptr, B, (float*)pc, pc_arg, c.stv);
   float* h2 = f32(c, (int64_t)B * hid);
   linear_fwd(c, pc, B, m.am0, nullptr, h2, 0.f, 0, true);
   float* hl2 = f32(c, (int64_t)B * hid);
@@ -607,12 +638,12 @@ LOTUS_API int lotus_policy_step(const int64_t* cfg, const int64_t* run, const in
   pointwise(c, h2, nullptr, hl2, (int64_t)B * hid, 2, c.head_drop, d_h2, false);
   float* action = f32(c, (int64_t)B * aw);
   linear_fwd(c, hl2, B, m.am3, nullptr, action, 0.f, 0, true, false);
-  CALL(lotus_decode_actions(heat, feat, m.inC, sg[0].cloud_off, B, NB, pos_bin_size, action, aw, m.rot_bins, euler_res,
-                            use_gt_pos ? gt_actions : nullptr, 7, final_actions, c.stv));
+  CALL(lotus_decode_actions, heat, feat, m.inC, sg[0].cloud_off, B, NB, pos_bin_size, action, aw, m.rot_bins, euler_res,
+                            use_gt_pos ? gt_actions : nullptr, 7, final_actions, c.stv);
   if (compute_loss) {
     float* dheat = need_grad ? f32(c, (int64_t)N0 * hw) : nullptr;
     float* daction = need_grad ? f32(c, (int64_t)B * aw) : nullptr;
-    CALL(lotus_policy_loss_f32(heat, pos_prob, sg[0].cloud_off, B, NB, action, aw, m.rot_bins, gt_actions, 7, pos_w, rot_w, losses, dheat, daction, nullptr, c.stv));
+    CALL(lotus_policy_loss_f32, heat, pos_prob, sg[0].cloud_off, B, NB, action, aw, m.rot_bins, gt_actions, 7, pos_w, rot_w, losses, dheat, daction, nullptr, c.stv);
     if (need_grad) {
       // ================= backward =================
       // head
@@ -623,17 +654,17 @@ LOTUS_API int lotus_policy_step(const int64_t* cfg, const int64_t* run, const in
         linear_bwd(c, dheat, hl, N0, m.hm3, dhl, nullptr, false);
         pointwise(c, h, dhl, dhl, (int64_t)N0 * hid, 3, c.head_drop, d_h, false);       // dh (fp32) in place
         const void* dh = dhl;
-        if (c.bf) { void* t = c.ar.alloc((size_t)N0 * hid * 2); CALL(lotus_convert(dhl, t, (int64_t)N0 * hid, 0, c.stv)); dh = t; }
+        if (c.bf) { void* t = c.ar.alloc((size_t)N0 * hid * 2); CALL(lotus_convert, dhl, t, (int64_t)N0 * hid, 0, c.stv); dh = t; }
         linear_bwd(c, dh, x, N0, m.hm0, D, nullptr, c.bf);
         float* dhl2 = f32(c, (int64_t)B * hid);
         linear_bwd(c, daction, hl2, B, m.am3, dhl2, nullptr, false);
         pointwise(c, h2, dhl2, dhl2, (int64_t)B * hid, 3, c.head_drop, d_h2, false);
         const void* dh2 = dhl2;
-        if (c.bf) { void* t = c.ar.alloc((size_t)B * hid * 2); CALL(lotus_convert(dhl2, t, (int64_t)B * hid, 0, c.stv)); dh2 = t; }
+        if (c.bf) { void* t = c.ar.alloc((size_t)B * hid * 2); CALL(lotus_convert, dhl2, t, (int64_t)B * hid, 0, c.stv); dh2 = t; }
         void* dpc = act(c, B, hid);
         linear_bwd(c, dh2, pc, B, m.am0, dpc, nullptr, c.bf);
-        if (c.bf) CALL(lotus_segment_max_bwd_bf16(dpc, pc_arg, B, hid, D, 1, c.stv));
-        else CALL(lotus_segment_max_bwd_f32((const float*)dpc, pc_arg, B, hid, (float*)D, 1, c.stv));
+        if (c.bf) CALL(lotus_segment_max_bwd_bf16, dpc, pc_arg, B, hid, D, 1, c.stv);
+        else CALL(lotus_segment_max_bwd_f32, (const float*)dpc, pc_arg, B, hid, (float*)D, 1, c.stv);
         join_side(c);
         c.ar.off = mark;
       }
@@ -648,8 +679,8 @@ LOTUS_API int lotus_policy_step(const int64_t* cfg, const int64_t* run, const in
         block_bwd(c, m.decB[s], sg[s], D, dB[s], &dconv);            // D = d(xu); dconv = D + conv-input grad = d(b)
         // unpool: xu = b + a[cluster]
         void* da = act(c, nc, C);
-        if (c.bf) CALL(lotus_segment_sum_bf16(D, C, sg[s + 1].seg_ptr, sg[s + 1].member, nc, 0, da, c.stv));
-        else CALL(lotus_segment_sum_f32((const float*)D, C, sg[s + 1].seg_ptr, sg[s + 1].member, nc, 0, (float*)da, c.stv));
+        if (c.bf) CALL(lotus_segment_sum_bf16, D, C, sg[s + 1].seg_ptr, sg[s + 1].member, nc, 0, da, c.stv);
+        else CALL(lotus_segment_sum_f32, (const float*)D, C, sg[s + 1].seg_ptr, sg[s + 1].member, nc, 0, (float*)da, c.stv);
         // skip branch: b = gelu(bn(lin(skip)))
         void* dlin_b = act(c, n, C);
         bn_bwd(c, dconv, dlin_b, m.unpool[s].bn_skip, upBnSkip[s]);
@@ -674,8 +705,8 @@ LOTUS_API int lotus_policy_step(const int64_t* cfg, const int64_t* run, const in
           bn_bwd(c, D, dpooled, m.pool[s].bn, poolBn[s]);
           void* dproj = act(c, np, C);
           zero(c, dproj, (size_t)np * C * c.es);
-          if (c.bf) CALL(lotus_segment_max_bwd_bf16(dpooled, pool_arg[s], n, C, dproj, 0, c.stv));
-          else CALL(lotus_segment_max_bwd_f32((const float*)dpooled, pool_arg[s], n, C, (float*)dproj, 0, c.stv));
+          if (c.bf) CALL(lotus_segment_max_bwd_bf16, dpooled, pool_arg[s], n, C, dproj, 0, c.stv);
+          else CALL(lotus_segment_max_bwd_f32, (const float*)dpooled, pool_arg[s], n, C, (float*)dproj, 0, c.stv);
           // d(skip[s-1]) = Gskip[s-1] (decoder) + dproj @ Wpool
           linear_bwd(c, dproj, skip[s - 1], np, m.pool[s].proj, Gskip[s - 1], Gskip[s - 1], c.bf);
           D = Gskip[s - 1];
@@ -685,7 +716,7 @@ LOTUS_API int lotus_policy_step(const int64_t* cfg, const int64_t* run, const in
       {
         float* dstem = f32(c, (int64_t)N0 * m.encC[0]);
         bn_bwd(c, D, dstem, m.stem_bn, stem_sv);
-        if (Gf(c, m.stem_w)) CALL(lotus_subm_conv_wgrad_f32(dstem, feat, Gf(c, m.stem_w), sg[0].nbr5, sg[0].stride, N0, m.inC, m.encC[0], 125, c.stv));
+        if (Gf(c, m.stem_w)) CALL(lotus_subm_conv_wgrad_f32, dstem, feat, Gf(c, m.stem_w), sg[0].nbr5, sg[0].stride, N0, m.inC, m.encC[0], 125, c.stv);
       }
       // context tokens
       {
@@ -705,3 +736,20 @@ LOTUS_API int lotus_policy_step(const int64_t* cfg, const int64_t* run, const in
 
 // number of kernel-launching calls issued by the last (non-dry) lotus_policy_step on this process
 LOTUS_API int64_t lotus_policy_step_calls(void) { return (int64_t)eng::g_launcher_calls; }
+
+// Profile mode of lotus_policy_step: when enabled, the next step brackets every launcher call with CUDA events on the caller's
+// stream (the weight-gradient side stream is folded back so the times are per call) and keeps (name, arguments).
+LOTUS_API int lotus_policy_step_profile(int enable) { eng::g_prof_on = enable != 0; return 0; }
+LOTUS_API int64_t lotus_policy_step_profile_count(void) { return (int64_t)eng::g_prof.size(); }
+// record `index` of the last profiled step (synchronise the stream first): name (<= 63 chars + NUL), device milliseconds,
+// the call's arguments in C-ABI order (pointers as addresses, floats as 0/1 = zero / non-zero), their count.  Host pointers.
+LOTUS_API int lotus_policy_step_profile_read(int64_t index, char* name_out, float* ms_out, int64_t* args_out, int* nargs_out) {
+  if (index < 0 || index >= (int64_t)eng::g_prof.size()) { lotus_set_error("lotus_policy_step_profile_read: index out of range"); return 2; }
+  const eng::ProfRec& r = eng::g_prof[(size_t)index];
+  strncpy(name_out, r.name, 63); name_out[63] = 0;
+  float ms = 0.f;
+  LOTUS_CUDA_CALL(cudaEventElapsedTime(&ms, r.e0, r.e1));
+  *ms_out = ms; *nargs_out = r.nargs;
+  for (int i = 0; i < r.nargs && i < 40; ++i) args_out[i] = r.a[i];
+  return 0;
+}

@@ -19,6 +19,26 @@
 
 namespace tc {
 
+// GELU (exact erf form, model.py:566 nn.GELU) for the GEMM epilogues: erf by Abramowitz-Stegun 7.1.26 (|err| <= 1.5e-7,
+// far below bf16 resolution).  z = |x| / sqrt(2) makes exp(-z^2) = exp(-x^2 / 2), which the derivative needs as well, so
+// gelu and gelu' cost one ex2 + one rcp + ~10 FMAs instead of erff + expf (the epilogue warps are ALU-bound otherwise).
+__device__ __forceinline__ float rcp_approx(float x) { float y; asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x)); return y; }
+__device__ __forceinline__ float ex2_approx(float x) { float y; asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x)); return y; }
+// half_s = 0.5 * s: cdf comes back pre-multiplied by s (the dropout keep-scale folds in for free)
+__device__ __forceinline__ void gelu_parts(float x, float half_s, float& cdf_s, float& e) {
+  const float z = fabsf(x) * 0.70710678118654752f;
+  const float t = rcp_approx(fmaf(0.3275911f, z, 1.f));
+  e = ex2_approx(x * x * -0.72134752044448170f);             // exp(-x^2 / 2)
+  float poly = fmaf(fmaf(fmaf(fmaf(1.061405429f, t, -1.453152027f), t, 1.421413741f), t, -0.284496736f), t, 0.254829592f) * t;
+  const float erf_abs = fmaf(-poly, e, 1.f);
+  cdf_s = fmaf(copysignf(erf_abs, x), half_s, half_s);
+}
+__device__ __forceinline__ float gelu_fast(float x, float half_s) { float c, e; gelu_parts(x, half_s, c, e); return x * c; }
+__device__ __forceinline__ float gelu_grad_fast(float x, float half_s) {
+  float c, e; gelu_parts(x, half_s, c, e);
+  return fmaf(x * e, 0.79788456080286535588f * half_s, c);   // s * (cdf + x * pdf), pdf = e / sqrt(2 pi)
+}
+
 constexpr int BM = 128;
 constexpr int BK = 64;            // 64 bf16 = 128 B = one SWIZZLE_128B span
 constexpr int MAX_STAGES = 6;
@@ -89,7 +109,7 @@ __device__ __forceinline__ void stage_mn_gather(uint8_t* tile, const GatherSpec&
 }
 
 template <int BN>
-__global__ void __launch_bounds__(NUM_THREADS)
+__global__ void __launch_bounds__(NUM_THREADS, 3)
 k_gemm_tc(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_b,
           const __grid_constant__ CUtensorMap map_out, const __grid_constant__ CUtensorMap map_res,
           const __grid_constant__ CUtensorMap map_out2, const Params p) {
@@ -110,6 +130,13 @@ k_gemm_tc(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUt
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int m0 = blockIdx.x * BM, n0 = blockIdx.y * BN;
   if (threadIdx.x == 0) TS(0);
+  if (threadIdx.x == 32) {   // descriptor fetches overlap the barrier / TMEM set-up (short tiles are prologue-latency bound)
+    if (p.a_mode == OP_K_TMA || p.a_mode == OP_MN_TMA) asm volatile("prefetch.tensormap [%0];" ::"l"(&map_a) : "memory");
+    if (p.b_mode == OP_K_TMA || p.b_mode == OP_MN_TMA) asm volatile("prefetch.tensormap [%0];" ::"l"(&map_b) : "memory");
+    asm volatile("prefetch.tensormap [%0];" ::"l"(&map_out) : "memory");
+    if (p.residual) asm volatile("prefetch.tensormap [%0];" ::"l"(&map_res) : "memory");
+    if (p.out2) asm volatile("prefetch.tensormap [%0];" ::"l"(&map_out2) : "memory");
+  }
   // reduction range of this CTA
   int tap = 0, Kext = p.K, kb0, kb1;
   if (p.k_dev) {
@@ -246,11 +273,14 @@ k_gemm_tc(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUt
     if (!(p.debug & 2)) { mbar_wait(tmem_full, 0); tc_fence_after(); }
     if (threadIdx.x == 64) TS(4);
     if (p.residual && !(p.debug & 2)) mbar_wait(res_full, 0);
-    const bool plain = (p.act == ACT_NONE) && !(p.drop_p > 0.f);
     const bool add_res = p.residual != nullptr && p.act != ACT_GELU_GRAD;
     uint8_t* sOut2 = smem + (size_t)BM * BN * 2;       // pre-activation tile (bf16 outputs only), behind the output tile
     const uint32_t thr = drop_thr(p.drop_p);
-    const float keep_scale = p.drop_p > 0.f ? drop_scale(thr) : 1.f;
+    const bool has_drop = p.drop_p > 0.f;
+    const float keep_scale = has_drop ? drop_scale(thr) : 1.f;
+    const float half_ks = 0.5f * keep_scale;
+    const uint32_t thr4 = thr * 0x01010101u;
+    const bool mask_in_float = has_drop && (add_res || p.out_fp32);   // otherwise the mask is ANDed into the packed bf16 pairs
     uint8_t* sOut = smem;                              // [BN/box_cols][128 rows][128 B], SWIZZLE_128B
     const uint32_t sw = (uint32_t)(r & 7);
 #pragma unroll 1
@@ -285,6 +315,17 @@ k_gemm_tc(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUt
           *(uint4*)(box2 + (((cb2 + ch) ^ sw) << 4)) = w;
         }
       }
+      // dropout keep-masks of the 32 columns: one hash per four columns, bytes compared against the threshold in one SIMD op
+      uint32_t dm[8];
+      if (has_drop) {
+        const uint64_t o0 = (uint64_t)((int64_t)row * p.ldo + nbase);   // multiple of 4: four columns share one hash
+#pragma unroll
+        for (int j = 0; j < 8; ++j) dm[j] = __vcmpgeu4(drop_hash4(p.seed, p.drop_stream, o0 + 4 * j), thr4);   // 0xFF keep / 0x00 drop
+      } else {
+#pragma unroll
+        for (int j = 0; j < 8; ++j) dm[j] = 0xFFFFFFFFu;
+      }
+      // activation (the keep-scale of the dropout is folded into it)
       if (p.act == ACT_GELU_GRAD) {                    // f *= gelu'(aux), aux = bf16 tile loaded through the residual map
         const uint8_t* rbox = sRes + (c0 >> 6) * 16384 + r * 128;
         const int cb2 = (c0 & 63) >> 3;
@@ -295,27 +336,24 @@ k_gemm_tc(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUt
 #pragma unroll
           for (int t2 = 0; t2 < 4; ++t2) {
             float2 e = __bfloat1622float2(qh[t2]);
-            f[8 * ch + 2 * t2] *= gelu_grad_f(e.x); f[8 * ch + 2 * t2 + 1] *= gelu_grad_f(e.y);
+            f[8 * ch + 2 * t2] *= gelu_grad_fast(e.x, half_ks); f[8 * ch + 2 * t2 + 1] *= gelu_grad_fast(e.y, half_ks);
           }
         }
+      } else if (p.act == ACT_GELU) {
+#pragma unroll
+        for (int j = 0; j < 32; ++j) f[j] = gelu_fast(f[j], half_ks);
+      } else if (p.act == ACT_LEAKY) {
+#pragma unroll
+        for (int j = 0; j < 32; ++j) f[j] = (f[j] > 0.f ? f[j] : 0.02f * f[j]) * keep_scale;
+      } else if (has_drop) {
+#pragma unroll
+        for (int j = 0; j < 32; ++j) f[j] *= keep_scale;
       }
-      if (!plain) {
-        if (p.act == ACT_GELU) {
+      if (mask_in_float) {                             // a residual (or an fp32 store) follows: zero the dropped values now
 #pragma unroll
-          for (int j = 0; j < 32; ++j) f[j] = gelu_f(f[j]);
-        } else if (p.act == ACT_LEAKY) {
+        for (int j = 0; j < 8; ++j)
 #pragma unroll
-          for (int j = 0; j < 32; ++j) f[j] = f[j] > 0.f ? f[j] : 0.02f * f[j];
-        }
-        if (p.drop_p > 0.f) {
-          const uint64_t o0 = (uint64_t)((int64_t)row * p.ldo + nbase);   // multiple of 4: four columns share one hash
-#pragma unroll
-          for (int j = 0; j < 8; ++j) {
-            uint32_t h = drop_hash4(p.seed, p.drop_stream, o0 + 4 * j);
-#pragma unroll
-            for (int q = 0; q < 4; ++q) f[4 * j + q] = (((h >> (8 * q)) & 0xFFu) >= thr) ? f[4 * j + q] * keep_scale : 0.f;
-          }
-        }
+          for (int q = 0; q < 4; ++q) f[4 * j + q] = ((dm[j] >> (8 * q)) & 1u) ? f[4 * j + q] : 0.f;
       }
       if (p.debug & 16) { if (f[3] == 12345.678f) sBias[0] = f[5]; continue; }
       if (p.out_fp32) {
@@ -349,6 +387,10 @@ k_gemm_tc(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUt
           __nv_bfloat162 h0 = __floats2bfloat162_rn(g[0], g[1]), h1 = __floats2bfloat162_rn(g[2], g[3]);
           __nv_bfloat162 h2 = __floats2bfloat162_rn(g[4], g[5]), h3 = __floats2bfloat162_rn(g[6], g[7]);
           w.x = *(uint32_t*)&h0; w.y = *(uint32_t*)&h1; w.z = *(uint32_t*)&h2; w.w = *(uint32_t*)&h3;
+          if (has_drop && !mask_in_float) {            // bytes (keep ? 0xFF : 0) of four columns -> 16-bit lanes of the bf16 pairs
+            w.x &= __byte_perm(dm[2 * ch], 0, 0x1100); w.y &= __byte_perm(dm[2 * ch], 0, 0x3322);
+            w.z &= __byte_perm(dm[2 * ch + 1], 0, 0x1100); w.w &= __byte_perm(dm[2 * ch + 1], 0, 0x3322);
+          }
           *(uint4*)(box + (((cb + ch) ^ sw) << 4)) = w;
         }
       }

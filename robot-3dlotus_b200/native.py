@@ -132,3 +132,29 @@ class NativeStep:
         if train:
             torch._foreach_add_([bn.num_batches_tracked for bn in self.bns], 1)
         return final, self.losses
+
+
+def profile_step(run_step):
+    """Run `run_step()` (one native step) in profile mode and return [(c_abi_name, args tuple, device_ms)], one entry per
+    launcher call of `lotus_policy_step` in issue order.  Arguments are in C-ABI order: pointers as integer addresses
+    (0 = null), integers as given, floats as 0 / 1 (zero / non-zero)."""
+    L = load()
+    L.cdll.lotus_policy_step_profile(1)
+    try:
+        run_step()
+        torch.cuda.synchronize()
+        L.cdll.lotus_policy_step_profile_count.restype = ctypes.c_int64
+        n = int(L.cdll.lotus_policy_step_profile_count())
+        name = ctypes.create_string_buffer(64)
+        ms = ctypes.c_float(0)
+        args = (ctypes.c_int64 * 40)()
+        na = ctypes.c_int(0)
+        out = []
+        for i in range(n):
+            rc = L.cdll.lotus_policy_step_profile_read(ctypes.c_int64(i), name, ctypes.byref(ms), args, ctypes.byref(na))
+            if rc:
+                raise RuntimeError(L.cdll.lotus_last_error().decode())
+            out.append((name.value.decode(), tuple(int(args[j]) for j in range(na.value)), float(ms.value)))
+        return out
+    finally:
+        L.cdll.lotus_policy_step_profile(0)

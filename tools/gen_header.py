@@ -33,6 +33,9 @@ DOC = {
     "lotus_policy_step": "One whole policy step in a single call: replaces SimplePolicyPTV3CA.forward + compute_loss + loss.backward() "
                          "(models/simple_policy_ptv3.py:225-373; models/PointTransformerV3/model_ca.py:383-412) for the production topology; "
                          "parameter gradients accumulate into the caller's sinks (train/train_simple_policy.py:211-216).",
+    "lotus_policy_step_profile": "Measurement aid: switch lotus_policy_step's profile mode (CUDA events around every launcher call, side stream folded back).",
+    "lotus_policy_step_profile_count": "Number of launcher calls recorded by the last profiled lotus_policy_step.",
+    "lotus_policy_step_profile_read": "One record of the last profiled step: C-ABI name, device milliseconds, the call's arguments (bench.py per-kernel table).",
     "lotus_policy_step_calls": "Kernel-launching calls issued by the last lotus_policy_step (bench accounting).",
     "lotus_tc_debug_buffer": "Development aid: per-CTA %globaltimer stamps of the tensor-core GEMM phases.",
     "lotus_fps": "Replaces farthest_point_sample (explicit start index): train/datasets/common.py:108-129. Bit-exact indices.",
