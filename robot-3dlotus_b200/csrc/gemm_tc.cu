@@ -45,7 +45,7 @@ constexpr int MAX_STAGES = 6;
 constexpr int NUM_THREADS = 320;  // 10 warps: TMA, MMA, 8 epilogue (warps 2-5 double as cp.async gather producers)
 constexpr int EPI_THREADS = 128;  // gather-producer threads (warps 2-5)
 
-enum { OP_K_TMA = 0, OP_K_GATHER = 1, OP_MN_TMA = 2, OP_MN_GATHER = 3 };
+enum { OP_K_TMA = 0, OP_K_GATHER = 1, OP_MN_TMA = 2, OP_MN_GATHER = 3, OP_K_TMAGATHER = 4 };   // 4: rows gathered by the TMA unit (tile::gather4)
 enum { ACT_NONE = 0, ACT_GELU = 1, ACT_LEAKY = 2, ACT_GELU_GRAD = 3 };   // 3: multiply by gelu'(aux) where aux rides in `residual`
 
 struct GatherSpec {
@@ -56,6 +56,8 @@ struct GatherSpec {
   int kb_per_tap;              // k-blocks per kernel tap (Cin / 64)
   int mirror_taps;             // K-major gather: use tap (ntaps-1-d) (conv dgrad)
   int ntaps;
+  int idx_in_smem;             // K-major gather: the tile's index rows are staged in shared memory (set by launch())
+  int src_rows;                // rows of the gathered tensor (TMA gather: indices >= src_rows read as zeros)
 };
 
 struct Params {
@@ -64,6 +66,8 @@ struct Params {
   int kb_begin_stride;         // k-blocks per split (split-K over blockIdx.z)
   unsigned long long* dbg_ts;  // dev knob: per-CTA timestamps (8 slots), set via lotus_tc_debug_buffer
   int debug;                   // dev knob (LOTUS_TC_DEBUG): 1 skip epilogue math+store, 2 skip mainloop, 4 no store wait
+  int pair_commit;             // one `empty` barrier (and one tcgen05.commit) per PAIR of stages
+  int async_arrive;            // gather producers signal `full` with cp.async.mbarrier.arrive.noinc (no wait_group lag)
   int stages;                  // smem pipeline depth (2..4): shallow pipelines leave room for several CTAs per SM
   // pair-list mode (sparse-conv weight gradient): blockIdx.z = tap * splits + split, K read from the device
   const int32_t* k_dev;        // [taps] reduction extent per tap, or null
@@ -92,11 +96,8 @@ struct Params {
 //                (LBO = 8192 between 64-wide MN blocks, SBO = 1024 between 8-k-row groups)
 // stage one BK x WIDTH MN-major tile whose k-rows are gathered through idx[] (rows >= kext are zero)
 template <int WIDTH>
-__device__ __forceinline__ void stage_mn_gather(uint8_t* tile, const GatherSpec& g, const int32_t* idx, int kb, int kext, int mn0,
-                                                int mn_extent, int t) {
+__device__ __forceinline__ void stage_mn_gather(uint8_t* tile, const GatherSpec& g, int src_row, int mn0, int mn_extent, int t) {
   int r = t >> 1, half = t & 1;
-  int kpt = kb * BK + r;
-  int src_row = (kpt < kext) ? idx[kpt] : -1;
   const __nv_bfloat16* src = g.base + (int64_t)max(src_row, 0) * g.row_elems + mn0;
   constexpr int CH = WIDTH / 8;                 // 16-B chunks per row
 #pragma unroll
@@ -126,12 +127,15 @@ k_gemm_tc(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUt
   uint32_t* tmem_slot = (uint32_t*)(res_full + 1);
   float* sBias = (float*)(tmem_slot + 4);                                                 // [BN] bias slice of this tile
   uint8_t* sRes = (uint8_t*)(((uintptr_t)(sBias + BN) + 1023) & ~(uintptr_t)1023);        // residual tile (only when p.residual)
+  // K-major gather (sparse conv): this tile's rows of the neighbour table, [ntaps][128] int32, staged once by the producer
+  // threads -- the per-k-block index lookup was a dependent global load in front of every cp.async group
+  int32_t* sIdx = (int32_t*)(sRes + (p.residual ? (size_t)BM * BN * (p.out_fp32 ? 4 : 2) : 0));
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int m0 = blockIdx.x * BM, n0 = blockIdx.y * BN;
   if (threadIdx.x == 0) TS(0);
   if (threadIdx.x == 32) {   // descriptor fetches overlap the barrier / TMEM set-up (short tiles are prologue-latency bound)
-    if (p.a_mode == OP_K_TMA || p.a_mode == OP_MN_TMA) asm volatile("prefetch.tensormap [%0];" ::"l"(&map_a) : "memory");
+    if (p.a_mode == OP_K_TMA || p.a_mode == OP_MN_TMA || p.a_mode == OP_K_TMAGATHER) asm volatile("prefetch.tensormap [%0];" ::"l"(&map_a) : "memory");
     if (p.b_mode == OP_K_TMA || p.b_mode == OP_MN_TMA) asm volatile("prefetch.tensormap [%0];" ::"l"(&map_b) : "memory");
     asm volatile("prefetch.tensormap [%0];" ::"l"(&map_out) : "memory");
     if (p.residual) asm volatile("prefetch.tensormap [%0];" ::"l"(&map_res) : "memory");
@@ -155,10 +159,13 @@ k_gemm_tc(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUt
   const int num_kb = max(0, kb1 - kb0);
   const bool a_gather = (p.a_mode == OP_K_GATHER || p.a_mode == OP_MN_GATHER);
   const bool b_gather = (p.b_mode == OP_MN_GATHER);
-  const bool a_mn = (p.a_mode >= OP_MN_TMA), b_mn = (p.b_mode >= OP_MN_TMA);
+  const bool a_mn = (p.a_mode == OP_MN_TMA || p.a_mode == OP_MN_GATHER), b_mn = (p.b_mode >= OP_MN_TMA);
+  const bool a_tmag = p.a_mode == OP_K_TMAGATHER;
+  const int PAIR = p.pair_commit;
 
   if (threadIdx.x == 0) {
-    uint32_t full_count = 1 + ((a_gather || b_gather) ? EPI_THREADS : 0);
+    // TMA producer + the gather producers: every thread's cp.async completion (async mode) or one elected lane per warp
+    uint32_t full_count = 1 + ((a_gather || b_gather) ? (p.async_arrive ? EPI_THREADS : EPI_THREADS / 32) : 0);
     for (int s = 0; s < STAGES; ++s) { mbar_init(&full[s], full_count); mbar_init(&empty[s], 1); }
     mbar_init(tmem_full, 1);
     mbar_init(res_full, 1);
@@ -169,6 +176,20 @@ k_gemm_tc(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUt
     int n = n0 + threadIdx.x - 64;
     sBias[threadIdx.x - 64] = (p.bias && n < p.N) ? p.bias[n] : 0.f;
   }
+  if ((p.a_mode == OP_K_GATHER || a_tmag) && p.ga.idx_in_smem && threadIdx.x >= 64 && threadIdx.x < 64 + EPI_THREADS) {
+    const int t = threadIdx.x - 64, m = m0 + t;
+    for (int tp0 = 0; tp0 < p.ga.ntaps; tp0 += 9) {          // nine independent loads in flight, then the stores
+      int v[9];
+#pragma unroll
+      for (int j = 0; j < 9; ++j) {
+        int tp = tp0 + j, src_tp = p.ga.mirror_taps ? p.ga.ntaps - 1 - tp : tp;
+        v[j] = (tp < p.ga.ntaps && m < p.M) ? p.ga.idx[(int64_t)src_tp * p.ga.idx_stride + m] : -1;
+        if (a_tmag && v[j] < 0) v[j] = p.ga.src_rows;           // absent neighbour -> an out-of-range row: the TMA zero-fills it
+      }
+#pragma unroll
+      for (int j = 0; j < 9; ++j) if (tp0 + j < p.ga.ntaps) sIdx[(tp0 + j) * EPI_THREADS + t] = v[j];
+    }
+  }
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
@@ -178,23 +199,46 @@ k_gemm_tc(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUt
   if (num_kb > 0 && !(p.debug & 2)) {
     if (warp == 0) {
       // ===================== TMA producer =====================
-      if (lane == 0) {
+      if (a_tmag) {
+        // ---- A rows gathered by the TMA unit: lane j issues ONE tile::gather4 for rows 4j..4j+3 of the tile per k-block
+        // (the cp.async form of this gather is bound by the LSU: one 16-byte request per cycle per SM, zero-fills included)
+        if (lane == 0 && p.residual) {
+          const int box_cols = p.out_fp32 ? 32 : 64;
+          mbar_arrive_expect_tx(res_full, (uint32_t)(BM * BN * (p.out_fp32 ? 4 : 2)));
+          for (int j = 0; j < BN / box_cols; ++j) tma_load_2d(sRes + j * 16384, &map_res, res_full, n0 + j * box_cols, m0);
+        }
+        for (int i = 0; i < num_kb; ++i) {
+          int s = i % STAGES, ph = (i / STAGES) & 1;
+          int kb = kb0 + i;
+          int tp = kb / p.ga.kb_per_tap, c0 = (kb - tp * p.ga.kb_per_tap) * BK;
+          int4 rows = *reinterpret_cast<const int4*>(sIdx + tp * EPI_THREADS + lane * 4);
+          if (lane == 0) {
+            mbar_wait_hot(&empty[PAIR ? (s >> 1) : s], ph ^ 1);
+            mbar_arrive_expect_tx(&full[s], A_BYTES + B_BYTES);
+            tma_load_2d(sB + s * B_BYTES, &map_b, &full[s], kb * BK, n0);
+          }
+          __syncwarp();
+          tma_gather4_2d(sA + s * A_BYTES + lane * 512, &map_a, &full[s], c0, rows.x, rows.y, rows.z, rows.w);
+        }
+      } else if (lane == 0) {
         if (p.residual) {   // residual tile [128 x BN] (same dtype as the output), boxes of 128-byte rows
           const int box_cols = p.out_fp32 ? 32 : 64;
           mbar_arrive_expect_tx(res_full, (uint32_t)(BM * BN * (p.out_fp32 ? 4 : 2)));
           for (int j = 0; j < BN / box_cols; ++j) tma_load_2d(sRes + j * 16384, &map_res, res_full, n0 + j * box_cols, m0);
         }
         uint32_t tx = (a_gather ? 0 : A_BYTES) + (b_gather ? 0 : B_BYTES);
+        if (p.debug & 128) tx -= B_BYTES;                  // dev knobs: no B / no A loads (timing experiments only)
+        if ((p.debug & 512) && !a_gather) tx -= A_BYTES;
         for (int i = 0; i < num_kb; ++i) {
           int s = i % STAGES, ph = (i / STAGES) & 1;
-          mbar_wait(&empty[s], ph ^ 1);
+          mbar_wait_hot(&empty[PAIR ? (s >> 1) : s], ph ^ 1);
           mbar_arrive_expect_tx(&full[s], tx);
           int k0 = (kb0 + i) * BK;
-          if (!a_gather) {
+          if (!a_gather && !(p.debug & 512)) {
             if (!a_mn) tma_load_2d(sA + s * A_BYTES, &map_a, &full[s], k0, m0);
             else { tma_load_2d(sA + s * A_BYTES, &map_a, &full[s], m0, k0); tma_load_2d(sA + s * A_BYTES + 8192, &map_a, &full[s], m0 + 64, k0); }
           }
-          if (!b_gather) {
+          if (!b_gather && !(p.debug & 128)) {
             if (!b_mn) tma_load_2d(sB + s * B_BYTES, &map_b, &full[s], k0, n0);
             else {
 #pragma unroll
@@ -206,12 +250,15 @@ k_gemm_tc(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUt
     } else if (warp == 1) {
       // ===================== MMA issuer =====================
       if (lane == 0) {
+        // (measured and rejected on B200, all within +-8 % of ~380 ns per k-block for a TMA-fed 4-stage pipeline, even with the
+        // loads and the MMAs knocked out: 6 stages, warp-uniform role loops, one commit per two stages, short try_wait hints)
         uint32_t idesc = (1u << 4) | (1u << 7) | (1u << 10) | ((a_mn ? 1u : 0u) << 15) | ((b_mn ? 1u : 0u) << 16) |
                          ((uint32_t)(BN >> 3) << 17) | ((uint32_t)(BM >> 4) << 24);
         for (int i = 0; i < num_kb; ++i) {
           int s = i % STAGES, ph = (i / STAGES) & 1;
-          mbar_wait(&full[s], ph);
-          tc_fence_after();
+          mbar_wait_hot(&full[s], ph);
+          if ((a_gather || b_gather) && p.async_arrive) fence_proxy_async();   // cp.async (generic proxy) data -> the MMA's async proxy
+          if (!(p.debug & 1024)) tc_fence_after();
           if (i == 0) TS(2);
           uint32_t a_addr = smem_u32(sA + s * A_BYTES), b_addr = smem_u32(sB + s * B_BYTES);
 #pragma unroll
@@ -219,43 +266,85 @@ k_gemm_tc(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUt
             // K-major: +32 B per 16-element K step inside the 128-B swizzle span; MN-major: +2 k-groups of 1024 B
             uint64_t da = a_mn ? make_desc(a_addr + k * 2048, 8192, 1024) : make_desc(a_addr + k * 32, 16, 1024);
             uint64_t db = b_mn ? make_desc(b_addr + k * 2048, 8192, 1024) : make_desc(b_addr + k * 32, 16, 1024);
-            umma_bf16(tmem_base, da, db, idesc, (i > 0 || k > 0) ? 1u : 0u);
+            if (!(p.debug & 256)) umma_bf16(tmem_base, da, db, idesc, (i > 0 || k > 0) ? 1u : 0u);
           }
-          umma_commit(&empty[s]);                       // frees the smem stage when these MMAs retire
+          // frees the smem stage(s) when these MMAs retire; pair mode: ONE commit per two stages (tcgen05.commit arrivals
+          // retire at a fixed ~380 ns each -- the whole pipeline advanced one k-block per commit whatever it loaded or multiplied)
+          if (!PAIR || (s & 1) || i == num_kb - 1) umma_commit(&empty[PAIR ? (s >> 1) : s]);
           if (i == num_kb - 1) { umma_commit(tmem_full); TS(3); }  // accumulator complete
         }
       }
-    } else if ((a_gather || b_gather) && warp < 6) {
-      // ===================== cp.async gather producers (warps 2-5) =====================
-      const int t = threadIdx.x - 64;                   // 0..127
+    } else if ((a_gather || b_gather) && (warp < 6 || p.async_arrive)) {
+      // ===================== cp.async gather producers =====================
+      // async-arrive mode: TWO producer groups (warps 2-5 take the even k-blocks, warps 6-9 the odd ones).  A producer
+      // thread's own loop iteration (poll `empty`, index, eight copies, arrive) takes ~600 ns whatever the pipeline depth --
+      // with copies and B loads knocked out the loop ran at the same rate -- so the k-blocks are dealt to two sets of threads.
+      const int t = (threadIdx.x - 64) & (EPI_THREADS - 1);   // 0..127: row of the tile this thread stages
+      const int grp = p.async_arrive ? (threadIdx.x - 64) >> 7 : 0, ngrp = p.async_arrive ? 2 : 1;
       const int LAG = STAGES >= 5 ? STAGES - 2 : (STAGES >= 3 ? 2 : 1);   // cp.async groups in flight per thread before signalling
       const int32_t* a_idx = p.ga.idx + (int64_t)tap * p.tap_idx_stride;
       const int32_t* b_idx = p.gb.idx + (int64_t)tap * p.tap_idx_stride;
-      for (int i = 0; i < num_kb + LAG; ++i) {
+      // MN-major gathers (pair-list weight gradient): the source row of each k-row comes from an index table; its load is
+      // issued two k-blocks ahead so the cp.async never waits on a dependent global load (-25 % on that kernel).
+      auto a_row_of = [&](int i) -> int {
+        if (i >= num_kb) return -1;
+        int kb = kb0 + i;
+        if (p.a_mode == OP_MN_GATHER) { int kpt = kb * BK + (t >> 1); return (kpt < Kext) ? a_idx[kpt] : -1; }
+        return -1;
+      };
+      auto b_row_of = [&](int i) -> int {
+        if (!b_gather || i >= num_kb) return -1;
+        int kpt = (kb0 + i) * BK + (t >> 1);
+        return (kpt < Kext) ? b_idx[kpt] : -1;
+      };
+      int a_r0 = a_row_of(grp), a_r1 = a_row_of(grp + ngrp), b_r0 = b_row_of(grp), b_r1 = b_row_of(grp + ngrp);
+      for (int i = grp; i < num_kb + (p.async_arrive ? 0 : LAG); i += ngrp) {
         if (i < num_kb) {
           int s = i % STAGES, ph = (i / STAGES) & 1;
-          mbar_wait(&empty[s], ph ^ 1);
+          const int a_row = a_r0, b_row = b_r0;
+          a_r0 = a_r1; b_r0 = b_r1;
+          a_r1 = a_row_of(i + 2 * ngrp); b_r1 = b_row_of(i + 2 * ngrp);
+          mbar_wait_hot(&empty[PAIR ? (s >> 1) : s], ph ^ 1);
           int kb = kb0 + i;
           if (p.a_mode == OP_K_GATHER) {
             // thread t stages row (m0 + t): 8 chunks of 16 B
+            // thread t stages row (m0 + t): 8 chunks of 16 B.  (Measured alternatives, all slower or equal: four whole rows per
+            // warp instruction, zero stores for absent rows, TMA tile::gather4 -- the loop is bound by barrier traffic, not by
+            // the copies: with the copies AND the B loads knocked out it ran at the same ns per k-block.)
             int tp = kb / p.ga.kb_per_tap, c0 = (kb - tp * p.ga.kb_per_tap) * BK;
-            if (p.ga.mirror_taps) tp = p.ga.ntaps - 1 - tp;
-            int m = m0 + t;
-            int src_row = (m < p.M) ? p.ga.idx[(int64_t)tp * p.ga.idx_stride + m] : -1;
+            int src_row;
+            if (p.ga.idx_in_smem) {
+              src_row = sIdx[tp * EPI_THREADS + t];
+            } else {
+              if (p.ga.mirror_taps) tp = p.ga.ntaps - 1 - tp;
+              int m = m0 + t;
+              src_row = (m < p.M) ? p.ga.idx[(int64_t)tp * p.ga.idx_stride + m] : -1;
+            }
             const __nv_bfloat16* src = p.ga.base + (int64_t)max(src_row, 0) * p.ga.row_elems + c0;
             uint8_t* dst = sA + s * A_BYTES + t * 128;
+            if (!(p.debug & 64)) {
 #pragma unroll
-            for (int c = 0; c < 8; ++c) cp_async_16(dst + ((c ^ (t & 7)) << 4), src + c * 8, src_row >= 0);
+              for (int c = 0; c < 8; ++c) cp_async_16(dst + ((c ^ (t & 7)) << 4), src + c * 8, src_row >= 0);
+            }
           } else if (p.a_mode == OP_MN_GATHER) {
-            stage_mn_gather<BM>(sA + s * A_BYTES, p.ga, a_idx, kb, Kext, m0, p.M, t);
+            stage_mn_gather<BM>(sA + s * A_BYTES, p.ga, a_row, m0, p.M, t);
           }
-          if (b_gather) stage_mn_gather<BN>(sB + s * B_BYTES, p.gb, b_idx, kb, Kext, n0, p.N, t);
+          if (b_gather) stage_mn_gather<BN>(sB + s * B_BYTES, p.gb, b_row, n0, p.N, t);
+        }
+        if (p.async_arrive) {
+          // the barrier tracks this thread's copies: it arrives when they land, the thread moves on to the next free stage
+          // (with commit/wait_group the slack left for the MMA round trip was STAGES - LAG = 2 stages: ~650 ns per k-block)
+          if (i < num_kb) {
+            cp_async_mbar_arrive_noinc(&full[i % STAGES]);
+          }
+          continue;
         }
         cp_async_commit();
         if (i >= LAG) {
           if (LAG == 4) cp_async_wait<4>(); else if (LAG == 3) cp_async_wait<3>(); else if (LAG == 2) cp_async_wait<2>(); else cp_async_wait<1>();
           fence_proxy_async();
-          mbar_arrive(&full[(i - LAG) % STAGES]);
+          __syncwarp();                                  // every lane's copies have landed and are fenced: ONE arrival per warp
+          if (lane == 0) mbar_arrive(&full[(i - LAG) % STAGES]);   // (128 per-thread arrivals serialised on the barrier word)
         }
       }
     }
@@ -270,9 +359,14 @@ k_gemm_tc(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUt
     const int half = (warp - 2) >> 2;                  // warps w and w+4 share a lane group and split the columns
     const int r = lane_grp * 32 + lane;                // row inside the tile
     const int row = m0 + r;
-    if (!(p.debug & 2)) { mbar_wait(tmem_full, 0); tc_fence_after(); }
+    if (!(p.debug & 2)) {
+      // one poller per warp (256 threads spinning on try_wait for the whole mainloop slowed every barrier hand-off of the pipeline)
+      if (lane == 0) mbar_wait(tmem_full, 0);
+      __syncwarp();
+      tc_fence_after();
+    }
     if (threadIdx.x == 64) TS(4);
-    if (p.residual && !(p.debug & 2)) mbar_wait(res_full, 0);
+    if (p.residual && !(p.debug & 2)) { if (lane == 0) mbar_wait(res_full, 0); __syncwarp(); }
     const bool add_res = p.residual != nullptr && p.act != ACT_GELU_GRAD;
     uint8_t* sOut2 = smem + (size_t)BM * BN * 2;       // pre-activation tile (bf16 outputs only), behind the output tile
     const uint32_t thr = drop_thr(p.drop_p);
@@ -482,6 +576,7 @@ static int launch(const Operand& A, const Operand& B, Params p, int BN, int spli
   p.a_mode = A.mode; p.b_mode = B.mode; p.ga = A.g; p.gb = B.g;
   int rc = 0;
   if (A.mode == OP_K_TMA) rc = make_map(&ma, A.ptr, p.M, p.K, A.ld, BK, BM);
+  else if (A.mode == OP_K_TMAGATHER) rc = make_map(&ma, A.g.base, A.g.src_rows, A.g.row_elems, A.g.row_elems, BK, 1);   // box {64 columns, 1 row}
   else if (A.mode == OP_MN_TMA) rc = make_map(&ma, A.ptr, p.K, p.M, A.ld, 64, BK);
   if (rc) return rc;
   if (B.mode == OP_K_TMA) rc = make_map(&mb, B.ptr, p.N, p.K, B.ld, BK, BN);
@@ -517,11 +612,37 @@ static int launch(const Operand& A, const Operand& B, Params p, int BN, int spli
   }
   // dev knob (LOTUS_TC_DEEP_GATHER=1): 5-6 stage pipeline for the gathered conv operand (3-4 k-blocks of cp.async in flight)
   if (A.mode == OP_K_GATHER && BN == 128 && kb_per_cta >= 6 && force_deep_gather()) p.stages = p.residual ? 5 : 6;
+  {
+    // long reductions: the per-CTA rate is STAGES per (load latency + hand-offs) ~ 1.5 us, i.e. ~380 ns per k-block at 4 stages
+    // whatever the tile does; with >= 12 k-blocks per CTA take 6 stages (5 with a residual tile) -- LOTUS_TC_DEEP=0 disables
+    static int deep = -1;
+    if (deep < 0) { const char* e = getenv("LOTUS_TC_DEEP"); deep = e ? atoi(e) : 0; }
+    if (deep && kb_per_cta >= 12 && !p.k_dev) p.stages = (BN == 128) ? (p.residual ? 5 : 6) : 6;
+  }
+  {
+    static int aa = -1;                                 // dev knob: LOTUS_TC_ASYNC_ARRIVE=0 restores commit/wait_group signalling
+    if (aa < 0) { const char* e = getenv("LOTUS_TC_ASYNC_ARRIVE"); aa = e ? atoi(e) : 1; }
+    p.async_arrive = aa;
+  }
   dim3 grid((p.M + BM - 1) / BM, (p.N + BN - 1) / BN, splits * taps);
   size_t tile_bytes = (size_t)BM * BN * (p.out_fp32 ? 4 : 2);
+  int want_pair;
+  { static int pc = -1; if (pc < 0) { const char* e = getenv("LOTUS_TC_PAIR"); pc = e ? atoi(e) : 0; } want_pair = pc; }
   size_t pipe = (size_t)p.stages * (BM * BK * 2 + BN * BK * 2);
   while (pipe < tile_bytes * (p.out2 ? 2 : 1)) { ++p.stages; pipe = (size_t)p.stages * (BM * BK * 2 + BN * BK * 2); }   // the output tile reuses the pipeline
   size_t smem = pipe + 256 + 2048 + (size_t)BN * 4 + (p.residual ? tile_bytes : 0);
+  if ((A.mode == OP_K_GATHER || A.mode == OP_K_TMAGATHER) && A.g.ntaps <= 32) {
+    // neighbour-table tile in shared memory; keep two 64-wide CTAs per SM (<= ~113 KB each) by giving up one pipeline stage
+    size_t idx_bytes = (size_t)A.g.ntaps * EPI_THREADS * 4;
+    if (BN == 64 && smem + idx_bytes > 113 * 1024 && p.stages > 2 && (size_t)(p.stages - 1) * (BM * BK * 2 + BN * BK * 2) >= tile_bytes) {
+      --p.stages;
+      pipe = (size_t)p.stages * (BM * BK * 2 + BN * BK * 2);
+      smem = pipe + 256 + 2048 + (size_t)BN * 4 + (p.residual ? tile_bytes : 0);
+    }
+    smem += idx_bytes;
+    p.ga.idx_in_smem = 1;
+  }
+  p.pair_commit = (want_pair && (p.stages % 2 == 0)) ? 1 : 0;
   cudaError_t e;
   if (BN == 128) {
     static bool set128 = false;
@@ -529,7 +650,7 @@ static int launch(const Operand& A, const Operand& B, Params p, int BN, int spli
     k_gemm_tc<128><<<grid, NUM_THREADS, smem, st>>>(ma, mb, mo, mr, mo2, p);
   } else {
     static bool set64 = false;
-    if (!set64) { cudaFuncSetAttribute(k_gemm_tc<64>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024); set64 = true; }
+    if (!set64) { cudaFuncSetAttribute(k_gemm_tc<64>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024); set64 = true; }
     k_gemm_tc<64><<<grid, NUM_THREADS, smem, st>>>(ma, mb, mo, mr, mo2, p);
   }
   e = cudaGetLastError();
@@ -538,6 +659,13 @@ static int launch(const Operand& A, const Operand& B, Params p, int BN, int spli
 }
 
 static int pick_bn(int N) { return N <= 64 ? 64 : 128; }
+// sparse-conv A operand: cp.async gather by default; LOTUS_TC_TMA_GATHER=1 gathers with the TMA unit instead (tile::gather4:
+// correct, and frees the LSU, but the TMA unit retires one 128-byte row per ~10 ns, half the cp.async rate)
+static int conv_gather_mode(const void* src, int K3) {
+  static int v = -1;
+  if (v < 0) { const char* e = getenv("LOTUS_TC_TMA_GATHER"); v = e ? atoi(e) : 0; }   // measured: gather4 sustains ~1290 ns per 128-row k-block, cp.async ~610
+  return (v && K3 <= 32 && ((uintptr_t)src & 15) == 0) ? OP_K_TMAGATHER : OP_K_GATHER;
+}
 
 }  // namespace tc
 
@@ -606,7 +734,7 @@ LOTUS_API int lotus_subm_conv_fwd_bf16(const void* x, const void* w, const float
   LOTUS_CHECK_ARG(Cin % 64 == 0, "lotus_subm_conv_fwd_bf16: Cin=%d must be a multiple of 64", Cin);
   Params p = base_params(n, Cout, K3 * Cin, y, Cout, out_fp32);
   p.bias = bias;
-  Operand A{tc::OP_K_GATHER, nullptr, 0, {(const __nv_bfloat16*)x, nbr, nbr_stride, Cin, Cin / 64, 0, K3}};
+  Operand A{tc::conv_gather_mode(x, K3), nullptr, 0, {(const __nv_bfloat16*)x, nbr, nbr_stride, Cin, Cin / 64, 0, K3, 0, n}};
   Operand B{tc::OP_K_TMA, (const __nv_bfloat16*)w, (int64_t)K3 * Cin, {}};
   return tc::launch(A, B, p, tc::pick_bn(Cout), 1, (cudaStream_t)stream_);
 }
@@ -617,7 +745,7 @@ LOTUS_API int lotus_subm_conv_dgrad_bf16(const void* dy, const void* wt, const v
   LOTUS_CHECK_ARG(Cout % 64 == 0, "lotus_subm_conv_dgrad_bf16: Cout=%d must be a multiple of 64", Cout);
   Params p = base_params(n, Cin, K3 * Cout, dx, Cin, out_fp32);
   p.residual = residual;
-  Operand A{tc::OP_K_GATHER, nullptr, 0, {(const __nv_bfloat16*)dy, nbr, nbr_stride, Cout, Cout / 64, 1, K3}};
+  Operand A{tc::conv_gather_mode(dy, K3), nullptr, 0, {(const __nv_bfloat16*)dy, nbr, nbr_stride, Cout, Cout / 64, 1, K3, 0, n}};
   Operand B{tc::OP_K_TMA, (const __nv_bfloat16*)wt, (int64_t)K3 * Cout, {}};
   return tc::launch(A, B, p, tc::pick_bn(Cin), 1, (cudaStream_t)stream_);
 }

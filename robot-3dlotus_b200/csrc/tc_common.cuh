@@ -32,10 +32,34 @@ __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
       "r"(parity)
       : "memory");
 }
+// Hot pipeline hand-offs (TMA producer <-> MMA issuer <-> gather producers): try_wait with a SHORT suspend-time hint.  With the
+// default (system-chosen) time limit a waiter that misses the phase sleeps a fixed quantum: the 4-stage pipelines then advanced
+// one k-block per ~380 ns whatever they loaded or multiplied (measured with loads and MMAs knocked out).
+__device__ __forceinline__ void mbar_wait_hot(uint64_t* bar, uint32_t parity) {
+  asm volatile(
+      "{\n"
+      ".reg .pred p;\n"
+      "LAB_WAIT_HOT:\n"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1, %2;\n"
+      "@p bra DONE_HOT;\n"
+      "bra LAB_WAIT_HOT;\n"
+      "DONE_HOT:\n"
+      "}\n" ::"r"(smem_u32(bar)),
+      "r"(parity), "r"(20u)
+      : "memory");
+}
 __device__ __forceinline__ void tma_load_2d(void* dst, const CUtensorMap* map, uint64_t* bar, int c0, int c1) {
   asm volatile(
       "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];" ::"r"(smem_u32(dst)),
       "l"(map), "r"(smem_u32(bar)), "r"(c0), "r"(c1)
+      : "memory");
+}
+// TMA gather: four rows (r0..r3, any order, out-of-range -> zeros) x one box of columns starting at `col` land in four
+// consecutive 128-byte rows of shared memory (tensor map: 2-D, box {columns, 1}); completes 4 * box bytes on `bar`
+__device__ __forceinline__ void tma_gather4_2d(void* dst, const CUtensorMap* map, uint64_t* bar, int col, int r0, int r1, int r2, int r3) {
+  asm volatile(
+      "cp.async.bulk.tensor.2d.shared::cluster.global.tile::gather4.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5, %6, %7}], [%2];" ::
+          "r"(smem_u32(dst)), "l"(map), "r"(smem_u32(bar)), "r"(col), "r"(r0), "r"(r1), "r"(r2), "r"(r3)
       : "memory");
 }
 __device__ __forceinline__ void tma_store_2d(const CUtensorMap* map, const void* src, int c0, int c1) {
@@ -55,6 +79,10 @@ __device__ __forceinline__ void tma_store_commit_wait() {
 __device__ __forceinline__ void cp_async_16(void* dst, const void* src, bool valid) {
   int sz = valid ? 16 : 0;  // src-size 0 -> zero fill
   asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(smem_u32(dst)), "l"(src), "r"(sz) : "memory");
+}
+// arrive on `bar` once all cp.async issued so far by this thread have completed (the arrival is pre-counted in the barrier's init)
+__device__ __forceinline__ void cp_async_mbar_arrive_noinc(uint64_t* bar) {
+  asm volatile("cp.async.mbarrier.arrive.noinc.shared::cta.b64 [%0];" ::"r"(smem_u32(bar)) : "memory");
 }
 __device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
 template <int N>

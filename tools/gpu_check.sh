@@ -7,10 +7,9 @@ grep -E "^(FAILED|ERROR)|passed|failed" gpurun_out/pytest_gpu.log | tail -15
 timeout 900 python bench.py --steps 20 --warmup 5 > gpurun_out/bench.json 2> gpurun_out/bench.err
 tail -3 gpurun_out/bench.err
 LOTUS_NO_SIDE_STREAM=1 timeout 600 python bench.py --steps 20 --warmup 5 --no-cpu-baseline --no-inference > gpurun_out/bench_noside.json 2> gpurun_out/bench_noside.err
-LOTUS_TC_DEEP_GATHER=0 timeout 600 python bench.py --steps 20 --warmup 5 --no-cpu-baseline --no-inference > gpurun_out/bench_nodeep.json 2> gpurun_out/bench_nodeep.err
 python - <<'PY'
 import json
-for f in ("bench", "bench_noside", "bench_nodeep"):
+for f in ("bench", "bench_noside"):
     try:
         d = json.load(open(f"gpurun_out/{f}.json"))
         print(f, round(d["value"], 1), round(d["ms_per_step"], 3), "e2e", round(d["e2e"]["value"], 1), d.get("inference"))
