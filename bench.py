@@ -330,7 +330,10 @@ def main():
     dev = torch.device("cuda", local)
     if world > 1:
         import torch.distributed as dist
-        dist.init_process_group("nccl", device_id=dev)
+        import datetime
+        if os.environ.get("NCCL_DEBUG", "").upper() in ("VERSION", ""):
+            os.environ["NCCL_DEBUG"] = "WARN"        # NCCL prints its version banner to STDOUT otherwise; rank 0 must print ONE JSON line
+        dist.init_process_group("nccl", device_id=dev, timeout=datetime.timedelta(seconds=120))
     cfgm, syn, policy, trainer, lib = pkg("config"), pkg("synthetic"), pkg("policy"), pkg("trainer"), pkg("lib")
     L = lib.load()
     cfg = cfgm.production_model_config()
@@ -355,13 +358,12 @@ def main():
     sampler = ClockSampler(local)
     if rank == 0:
         sampler.start()
-    # warm-up: at least W steps, every rotating batch seen once (arena sized), and at least ~3 s of load: the first process on a
+    # warm-up: at least W steps, every rotating batch seen once (arena sized), and at least ~2.5 s of load (120 steps): the first process on a
     # fresh box ran its first ~0.5 s of steps 20-40 % slower than everything after (observed twice; clocks already at max)
-    t_warm, i = time.perf_counter(), 0
-    while i < max(args.warmup, nb) or time.perf_counter() - t_warm < 3.0:
+    # (a FIXED count: every rank must issue the same number of all-reduces)
+    for i in range(max(args.warmup, nb, 120)):
         step_fn(dict(resident[i % nb]))
-        i += 1
-        if i % 8 == 0:
+        if i % 8 == 7:
             torch.cuda.synchronize()
     if rank == 0:
         sampler.wait_first(10.0)
@@ -407,6 +409,7 @@ def main():
     # native engine: lotus_policy_step's own profile mode (events around every launcher call inside the C++ executor, so no
     # Python sits between launches); the optimizer / tokeniser calls are timed around their ctypes calls.
     kernel_count = [0]
+    step_fn.opt.world = 1                       # rank 0 profiles alone: no collective from here on (the other ranks have left)
     native_calls = int(L.cdll.lotus_policy_step_calls()) if args.engine == "native" else 0
     prof = CallProfiler(L)
     if args.engine == "native":
