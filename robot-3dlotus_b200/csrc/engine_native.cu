@@ -345,25 +345,37 @@ static void block_bwd(Ctx& c, const BlockP& b, const StageInfo& sg, void* D, con
 }
 
 // ------------------------------------------------------------------------------------------------ CABlock
-struct CaSave { void *x0, *h1, *q, *kv, *qh, *kh, *o; float *n1_mean, *n1_rstd, *q_stats, *k_stats, *lse; uint32_t d_attn, d_proj; MlpSave mlp; int n; };
+struct CaSave { void *x0, *h1, *q, *kv, *qh, *kh, *o; float *n1_mean, *n1_rstd, *q_stats, *k_stats, *lse; uint32_t d_attn, d_proj; MlpSave mlp; int n; bool kv_ready = false; };
+// keys / values of a CABlock depend on the text tokens only: all blocks' kv projections (+ per-head k LayerNorm) are issued up
+// front on the side stream, off the point-feature chain (18 small launches per forward)
+static void ca_kv(Ctx& c, const CaP& b, const void* ctx, CaSave& sv) {
+  int C = b.C, H = b.H, Lt = c.Lt;
+  sv.kv = act(c, Lt, 2 * C);
+  linear_fwd(c, ctx, Lt, b.kv, nullptr, sv.kv, 0.f, 0);
+  if (c.qk_norm) {
+    sv.kh = act(c, Lt, C);
+    sv.k_stats = f32(c, (int64_t)2 * Lt * H);
+    head_ln_fwd(c, sv.kv, 2 * C, sv.kh, b.kn, sv.k_stats, sv.k_stats + (int64_t)Lt * H, Lt, H);
+  }
+  sv.kv_ready = true;
+}
 static void* ca_fwd(Ctx& c, const CaP& b, const StageInfo& sg, void* x0, const void* ctx, CaSave& sv) {
-  int n = sg.n, C = b.C, H = b.H, D = C / H, Lt = c.Lt;
+  int n = sg.n, C = b.C, H = b.H, D = C / H;
   sv.n = n; sv.x0 = x0;
   sv.n1_mean = f32(c, n); sv.n1_rstd = f32(c, n);
   sv.h1 = act(c, n, C);
   ln_fwd(c, x0, sv.h1, nullptr, b.n1, sv.n1_mean, sv.n1_rstd, n, 1e-5f);
   sv.q = act(c, n, C);
   linear_fwd(c, sv.h1, n, b.q, nullptr, sv.q, 0.f, 0);
-  sv.kv = act(c, Lt, 2 * C);
-  linear_fwd(c, ctx, Lt, b.kv, nullptr, sv.kv, 0.f, 0);
+  if (!sv.kv_ready) ca_kv(c, b, ctx, sv);
   const void *qp = sv.q, *kp = sv.kv; int64_t ldk = 2 * C;
   if (c.qk_norm) {
-    sv.qh = act(c, n, C); sv.kh = act(c, Lt, C);
-    sv.q_stats = f32(c, (int64_t)2 * n * H); sv.k_stats = f32(c, (int64_t)2 * Lt * H);
+    sv.qh = act(c, n, C);
+    sv.q_stats = f32(c, (int64_t)2 * n * H);
     head_ln_fwd(c, sv.q, C, sv.qh, b.qn, sv.q_stats, sv.q_stats + (int64_t)n * H, n, H);
-    head_ln_fwd(c, sv.kv, 2 * C, sv.kh, b.kn, sv.k_stats, sv.k_stats + (int64_t)Lt * H, Lt, H);
     qp = sv.qh; kp = sv.kh; ldk = C;
   }
+  join_side(c);                                       // the up-front kv projections (no-op after the first CABlock)
   sv.o = act(c, n, C);
   sv.lse = f32(c, (int64_t)n * H);
   sv.d_attn = drop_id(c, c.attn_drop);
@@ -528,7 +540,7 @@ LOTUS_API int lotus_policy_step(const int64_t* cfg, const int64_t* run, const in
   c.es = c.bf ? 2 : 4; c.rc = 0; c.seed = seed; c.drop_next = 1;
   c.side = nullptr; c.sidev = nullptr; c.side_busy = false;
   if (!c.dry) { g_prof.clear(); g_prof_ev_next = 0; }
-  if (!c.dry && grads != nullptr && run[7] != 0 && !g_prof_on && getenv("LOTUS_NO_SIDE_STREAM") == nullptr) {
+  if (!c.dry && !g_prof_on && getenv("LOTUS_NO_SIDE_STREAM") == nullptr) {
     if (!g_side) {
       LOTUS_CUDA_CALL(cudaStreamCreateWithFlags(&g_side, cudaStreamNonBlocking));
       LOTUS_CUDA_CALL(cudaEventCreateWithFlags(&g_ev_fork, cudaEventDisableTiming));
@@ -572,6 +584,15 @@ LOTUS_API int lotus_policy_step(const int64_t* cfg, const int64_t* run, const in
   if (c.bf) { void* t = c.ar.alloc((size_t)Lt * m.txtC * 2); CALL(lotus_convert, txt, t, (int64_t)Lt * m.txtC, 0, c.stv); txt_in = t; }
   void* ctx = act(c, Lt, m.ctxC);
   linear_fwd(c, txt_in, Lt, m.txt_fc, nullptr, ctx, 0.f, 0);
+  std::vector<BlockSave> eB(S), dB(S - 1); std::vector<CaSave> eC(S), dC(S - 1);
+  if (c.side) {
+    fork_side(c);                                     // ctx is complete on the main stream
+    cudaStream_t st_main = c.st; void* stv_main = c.stv;
+    c.st = c.side; c.stv = c.sidev;
+    for (int s = 0; s < S; ++s) ca_kv(c, m.encCA[s], ctx, eC[s]);
+    for (int s = S - 2; s >= 0; --s) ca_kv(c, m.decCA[s], ctx, dC[s]);
+    c.st = st_main; c.stv = stv_main;
+  }
   // ---------------- stem (fp32 SIMT conv, narrow input) + BN + GELU
   float* stem_out = f32(c, (int64_t)N0 * m.encC[0]);
   CALL(lotus_subm_conv_fwd_f32, feat, Pf(c, m.stem_w), nullptr, stem_out, sg[0].nbr5, sg[0].stride, N0, m.inC, m.encC[0], 125, c.stv);
@@ -579,7 +600,6 @@ LOTUS_API int lotus_policy_step(const int64_t* cfg, const int64_t* run, const in
   void* x = act(c, N0, m.encC[0]);
   bn_fwd(c, stem_out, true, x, N0, m.stem_bn, stem_sv);
   // ---------------- encoder
-  std::vector<BlockSave> eB(S), dB(S - 1); std::vector<CaSave> eC(S), dC(S - 1);
   std::vector<BnSave> poolBn(S), upBn(S - 1), upBnSkip(S - 1);
   std::vector<void*> skip(S, nullptr), pool_proj(S, nullptr), pooled(S, nullptr), up_lin(S - 1, nullptr), up_skip_lin(S - 1, nullptr),
       up_a(S - 1, nullptr), up_b(S - 1, nullptr), up_in(S - 1, nullptr);

@@ -130,7 +130,7 @@ class PolicyEngine:
         for s in range(S - 1):
             assert pt.dec_patch_size[s] == psz[s], "enc/dec patch sizes of a stage must match (shared patch plan)"
         stages = tokenize(coord, npoints, pt.order, pt.stride, psz, rows, self._perms(S, R, pt.shuffle_orders),
-                          self.m.config.action_config.voxel_size, self.div_mode)
+                          self.m.config.action_config.voxel_size, self.div_mode, need_pairs=torch.is_grad_enabled())
         self.last_stages = stages
         dev = feat.device
         B = len(npoints)
@@ -196,7 +196,7 @@ class PolicyEngine:
         S, R = pt.num_stages, len(pt.order)
         rows = [[0]] * S
         stages = tokenize(fts[:, :3], npoints, pt.order, pt.stride, list(pt.enc_patch_size), rows, self._perms(S, R, pt.shuffle_orders),
-                          m.config.action_config.voxel_size, self.div_mode)
+                          m.config.action_config.voxel_size, self.div_mode, need_pairs=bool(with_grad and compute_loss))
         self.last_stages = stages
         tok_off = [0]
         for l in batch["txt_lens"]:

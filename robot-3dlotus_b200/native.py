@@ -83,7 +83,7 @@ class NativeStep:
         for s, stg in enumerate(stages):
             pl = stg.plans[0]
             sizes += [stg.n, pl.n_pad, pl.n_patches, stg.max_cloud, stg.stride_alloc]
-            ptrs += [stg.nbr3.data_ptr(), stg.pairs_out.data_ptr(), stg.pairs_in.data_ptr(), stg.pair_cnt.data_ptr(),
+            ptrs += [stg.nbr3.data_ptr(), *(t.data_ptr() if t is not None else 0 for t in (stg.pairs_out, stg.pairs_in, stg.pair_cnt)),
                      pl.gather_idx.data_ptr(), pl.slot_of_point.data_ptr(), pl.cu_seqlens.data_ptr(), stg.cloud_off.data_ptr(),
                      stg.cluster.data_ptr() if stg.cluster is not None else 0, stg.seg_ptr.data_ptr() if stg.seg_ptr is not None else 0,
                      stg.member.data_ptr() if stg.member is not None else 0, stg.nbr5.data_ptr() if stg.nbr5 is not None else 0]

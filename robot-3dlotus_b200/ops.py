@@ -418,7 +418,7 @@ class SubmConvFn(torch.autograd.Function):
                 L.lotus_subm_conv_dgrad_f32(_p(dy), _p(w), None, _p(dx), _p(nbr), nbr_stride, n, cin, cout, k3, st)
         wbuf, dw = _grad_buf(w, ctx.needs_input_grad[1])
         if wbuf is not None:
-            if tc and ctx.rule is not None:
+            if tc and ctx.rule is not None and ctx.rule.pairs_out is not None:
                 r = ctx.rule      # compact per-tap pair lists: contract only over existing (voxel, neighbour) pairs
                 L.lotus_subm_conv_wgrad_pairs_bf16(_p(dy), _p(x), _p(wbuf), _p(r.pairs_out), _p(r.pairs_in), _p(r.pair_cnt),
                                                    r.stride_alloc, n, cin, cout, k3, st)

@@ -80,9 +80,11 @@ def _next_pow2(x):
 
 
 def tokenize(coord, npoints: List[int], orders, strides, patch_sizes, rows_needed, perms=None, grid_size=0.01,
-             div_mode=0, need_stem=True):
+             div_mode=0, need_stem=True, need_pairs=True):
     """coord (N,3) fp32 cuda (may be a strided view of pc_fts); npoints: host list of per-cloud counts.
-    perms: list of S row permutations (host lists) or None.  Returns [Stage_0 .. Stage_{S-1}]."""
+    perms: list of S row permutations (host lists) or None.  Returns [Stage_0 .. Stage_{S-1}].
+    Only the serialization rows a stage uses are computed (rows 0..max(rows_needed[s]); row 0 also drives the pooling), and the
+    compact pair lists (weight-gradient rulebook) only when `need_pairs` (training)."""
     L = load()
     dev = coord.device
     st = _st()
@@ -121,16 +123,18 @@ def tokenize(coord, npoints: List[int], orders, strides, patch_sizes, rows_neede
         stg.order = torch.empty((R, N0), **i32)
         stg.inverse = torch.empty((R, N0), **i32)
         cv = (ctypes.c_int32 * 4)(*(curves + [0] * (4 - R)))
-        L.lotus_serialize(_p(grid), _p(batch), _p(stg.cloud_off), B, N0, max_cloud, _p(meta[s]), cv, R, N0, _p(stg.code),
+        nrows = min(R, max([0] + list(rows_needed[s])) + 1)
+        L.lotus_serialize(_p(grid), _p(batch), _p(stg.cloud_off), B, N0, max_cloud, _p(meta[s]), cv, nrows, N0, _p(stg.code),
                           _p(stg.order), _p(stg.inverse), _p(err), st)
         # sparse-conv neighbourhoods (hash built once per stage, probed for k=3 and, at stage 0, k=5)
         stg.nbr3 = torch.empty((27, N0), **i32)
         L.lotus_neighbor_table(_p(grid), _p(batch), _p(meta[s]), N0, 3, _p(hkeys), _p(hvals), hash_cap, 1, _p(stg.nbr3), N0, st)
-        stg.pairs_out = torch.empty((27, N0), **i32)
-        stg.pairs_in = torch.empty((27, N0), **i32)
-        stg.pair_cnt = torch.empty(27, **i32)
-        L.lotus_pair_lists(_p(stg.nbr3), N0, _p(meta[s]), N0, 27, _p(stg.pairs_out), _p(stg.pairs_in), _p(stg.pair_cnt),
-                           _p(pair_scratch), st)
+        if need_pairs:
+            stg.pairs_out = torch.empty((27, N0), **i32)
+            stg.pairs_in = torch.empty((27, N0), **i32)
+            stg.pair_cnt = torch.empty(27, **i32)
+            L.lotus_pair_lists(_p(stg.nbr3), N0, _p(meta[s]), N0, 27, _p(stg.pairs_out), _p(stg.pairs_in), _p(stg.pair_cnt),
+                               _p(pair_scratch), st)
         if s == 0 and need_stem:
             stg.nbr5 = torch.empty((125, N0), **i32)
             L.lotus_neighbor_table(_p(grid), _p(batch), _p(meta[s]), N0, 5, _p(hkeys), _p(hvals), hash_cap, 0, _p(stg.nbr5), N0, st)

@@ -153,7 +153,7 @@ def test_empty_and_tiny_clouds():
     sizes = [1, 300, 2, 129]
     coord, _ = lattice_clouds(sizes, 40, 0)
     stages = tk.tokenize(coord.to(DEV), sizes, ["z", "z-trans", "hilbert", "hilbert-trans"], [2, 2, 2, 2], [128] * 5,
-                         [[0]] * 5, None)
+                         [[0, 1, 2, 3]] * 5, None)          # all four serialization rows are checked below
     off = torch.tensor(np.cumsum(sizes))
     pad, unpad, cu = O.patch_plan(off, 128)
     pl = stages[0].plans[0]
