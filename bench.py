@@ -301,6 +301,7 @@ def main():
     ap.add_argument("--labels", default="device", choices=["device", "host"],
                     help="soft position labels: produced on the GPU from (xyz, gt_actions) [lotus_disc_pos_prob], or shipped from the host "
                          "like the reference's collate does (36 MB of the 39 MB per step)")
+    ap.add_argument("--no-prefetch", action="store_true", help="do not pipeline the next batch's H2D copy + tokeniser behind the current step")
     ap.add_argument("--no-inference", action="store_true", help="skip the p50 inference-latency section")
     ap.add_argument("--infer-iters", type=int, default=100)
     ap.add_argument("--engine", default="native", choices=["native", "python"],
@@ -361,14 +362,23 @@ def main():
     # warm-up: at least W steps, every rotating batch seen once (arena sized), and at least ~2.5 s of load (120 steps): the first process on a
     # fresh box ran its first ~0.5 s of steps 20-40 % slower than everything after (observed twice; clocks already at max)
     # (a FIXED count: every rank must issue the same number of all-reduces)
+    pipelined = args.engine == "native" and not args.no_prefetch
+
+    def run_step(pool, i):
+        """one optimizer step on pool[i % nb]; the next batch's H2D copy + tokeniser are launched on a side stream (input
+        pipelining, as a DataLoader with pin_memory does for the reference)"""
+        if pipelined:
+            return step_fn(dict(pool[i % nb]), next_batch=pool[(i + 1) % nb])
+        return step_fn(dict(pool[i % nb]))
+
     for i in range(max(args.warmup, nb, 120)):
-        step_fn(dict(resident[i % nb]))
+        run_step(resident, i)
         if i % 8 == 7:
             torch.cuda.synchronize()
     if rank == 0:
         sampler.wait_first(10.0)
     for i in range(3):                               # settle after the sampler attached (untimed)
-        step_fn(dict(resident[i % nb]))
+        run_step(resident, i)
     if rank == 0:
         sampler.rows.clear()
     barrier()
@@ -377,7 +387,7 @@ def main():
     e0.record()
     t_host0 = time.perf_counter()
     for i in range(args.steps):
-        losses = step_fn(dict(resident[i % nb]))
+        losses = run_step(resident, i + 3)
     t_host = time.perf_counter() - t_host0          # host time to ENQUEUE the K steps (includes the tokeniser's size sync)
     e1.record()
     barrier()
@@ -390,7 +400,7 @@ def main():
     f0, f1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     f0.record()
     for i in range(args.steps):
-        losses = step_fn(dict(host[i % nb]))
+        losses = run_step(host, i)
         loss_host = float(losses["total"].item())
     f1.record()
     barrier()
@@ -540,6 +550,8 @@ def main():
         "dtype": "bf16" if args.precision == "bf16" else "fp32", "data": "synthetic",
         "config": {"workload": workload, "global_batch": args.batch * world, "parallelism": f"dp{world}",
                    "l2": "4 rotating input batches; per-step working set (1.1 GB params+grads+Adam state, multi-GB activations) exceeds the 126 MB L2",
+                   "input_pipeline": ("next batch's H2D copy + integer tokeniser run on a side stream during the current step" if pipelined
+                                      else "synchronous: copy + tokenise at the start of each step"),
                    "labels": ("soft position labels produced on the device from (xyz, gt_actions) inside the step" if args.labels == "device"
                               else "soft position labels shipped from the host with the batch (reference collate layout)"),
                    "precision_note": ("bf16 activations + tcgen05 tensor-core GEMM/conv, fp32 master weights/statistics/gradients"

@@ -10,7 +10,7 @@ import torch
 from . import ops
 from .lib import load
 from .modules import PDNorm
-from .tokenizer import tokenize, CrossGeo
+from .tokenizer import tokenize, tokenize_launch, tokenize_finish, CrossGeo
 
 
 class PolicyEngine:
@@ -27,6 +27,8 @@ class PolicyEngine:
         self.pos_heatmap_type = "dist"  # TRAIN_DATASET.pos_heatmap_type of the job scripts ('plain' | 'dist')
         self.use_native = False        # one-call C++ executor (csrc/engine_native.cu) for the production topology
         self._native = None
+        self._pf_stream = None
+        self._prefetched = None
         self._tc_weights = None
         load()                         # fail loudly if the CUDA library is absent
 
@@ -180,8 +182,40 @@ class PolicyEngine:
         return x, stages
 
     # ------------------------------------------------------------------ native one-call step
-    def native_step(self, batch, compute_loss=True, with_grad=True, compute_final_action=False, dropout_seed=None):
-        """forward (+ loss + backward into the gradient sinks) through `lotus_policy_step`.  Returns (final, losses(4,))."""
+    def _launch_tokens(self, fts, npoints, need_pairs):
+        pt = self.m.ptv3_model
+        S, R = pt.num_stages, len(pt.order)
+        return tokenize_launch(fts[:, :3], npoints, pt.order, pt.stride, list(pt.enc_patch_size), [[0]] * S,
+                               self._perms(S, R, pt.shuffle_orders), self.m.config.action_config.voxel_size, self.div_mode,
+                               need_pairs=need_pairs)
+
+    def prefetch(self, batch, need_pairs=True):
+        """Input pipelining for the native step: copy the NEXT batch to the device and run its integer tokeniser on a side stream
+        while the current step executes (the reference overlaps its DataLoader / pin_memory copies the same way).  The next
+        `native_step(batch)` with this very batch object picks the result up instead of tokenising synchronously."""
+        if self._pf_stream is None:
+            self._pf_stream = torch.cuda.Stream()
+        main = torch.cuda.current_stream()
+        key = id(batch["pc_fts"])
+        with torch.cuda.stream(self._pf_stream):
+            dev_batch = self.m.prepare_batch(dict(batch))
+            fts = dev_batch["pc_fts"]
+            npoints = [int(v) for v in dev_batch["npoints_in_batch"]]
+            pend = self._launch_tokens(fts, npoints, need_pairs)
+        for t in pend.tensors + [v for v in dev_batch.values() if isinstance(v, torch.Tensor)]:
+            t.record_stream(main)                    # allocated on the side stream, consumed on the main one
+        self._prefetched = (key, dev_batch, pend, need_pairs)
+
+    def take_prefetched(self, batch):
+        """-> (device batch, pending tokens) if `prefetch` was called with this batch object, else None"""
+        pf, self._prefetched = self._prefetched, None
+        if pf is not None and pf[0] == id(batch["pc_fts"]):
+            return pf[1], pf[2], pf[3]
+        return None
+
+    def native_step(self, batch, compute_loss=True, with_grad=True, compute_final_action=False, dropout_seed=None, pending=None):
+        """forward (+ loss + backward into the gradient sinks) through `lotus_policy_step`.  Returns (final, losses(4,)).
+        `pending`: tokens of this batch already in flight (`prefetch`)."""
         from . import native
         m = self.m
         if self._native is None:
@@ -194,9 +228,11 @@ class PolicyEngine:
             raise RuntimeError("lotus engine needs the model on a CUDA device (there is no CPU fallback)")
         npoints = [int(v) for v in batch["npoints_in_batch"]]
         S, R = pt.num_stages, len(pt.order)
-        rows = [[0]] * S
-        stages = tokenize(fts[:, :3], npoints, pt.order, pt.stride, list(pt.enc_patch_size), rows, self._perms(S, R, pt.shuffle_orders),
-                          m.config.action_config.voxel_size, self.div_mode, need_pairs=bool(with_grad and compute_loss))
+        if pending is None:
+            pending = self._launch_tokens(fts, npoints, bool(with_grad and compute_loss))
+        else:
+            torch.cuda.current_stream().wait_event(pending.event)     # side-stream copies + tokeniser -> visible to this stream
+        stages = tokenize_finish(pending)
         self.last_stages = stages
         tok_off = [0]
         for l in batch["txt_lens"]:

@@ -79,8 +79,26 @@ def _next_pow2(x):
     return p
 
 
+class PendingTokens:
+    """kernels of one tokenisation in flight on `stream`; `finish()` waits for the size copy and slices the stage tables"""
+
+    def __init__(self):
+        self.tensors = []          # every device allocation of this tokenisation (for record_stream when it ran on a side stream)
+        self.stages = None
+        self.event = None
+        self.host = None
+        self.S = self.B = 0
+
+
 def tokenize(coord, npoints: List[int], orders, strides, patch_sizes, rows_needed, perms=None, grid_size=0.01,
              div_mode=0, need_stem=True, need_pairs=True):
+    """launch + finish in one go (the single host sync of a forward)"""
+    return tokenize_finish(tokenize_launch(coord, npoints, orders, strides, patch_sizes, rows_needed, perms, grid_size, div_mode,
+                                           need_stem, need_pairs))
+
+
+def tokenize_launch(coord, npoints: List[int], orders, strides, patch_sizes, rows_needed, perms=None, grid_size=0.01,
+                    div_mode=0, need_stem=True, need_pairs=True):
     """coord (N,3) fp32 cuda (may be a strided view of pc_fts); npoints: host list of per-cloud counts.
     perms: list of S row permutations (host lists) or None.  Returns [Stage_0 .. Stage_{S-1}].
     Only the serialization rows a stage uses are computed (rows 0..max(rows_needed[s]); row 0 also drives the pooling), and the
@@ -162,8 +180,28 @@ def tokenize(coord, npoints: List[int], orders, strides, patch_sizes, rows_neede
             stg._next = (cluster, head, seg_ptr)
             grid, batch = nxt_grid, nxt_batch
 
-    # ---- the single host sync of the forward: data-dependent sizes
-    host = torch.cat([meta.reshape(-1), cloud_off_all.reshape(-1), err]).cpu()
+    # ---- data-dependent sizes: one asynchronous copy into pinned memory + an event (the only host sync of the forward)
+    dev_sizes = torch.cat([meta.reshape(-1), cloud_off_all.reshape(-1), err])
+    pend = PendingTokens()
+    pend.host = torch.empty(dev_sizes.shape, dtype=dev_sizes.dtype, pin_memory=True)
+    pend.host.copy_(dev_sizes, non_blocking=True)
+    pend.event = torch.cuda.Event()
+    pend.event.record(torch.cuda.current_stream())
+    pend.stages, pend.S, pend.B = stages, S, B
+    pend.tensors = [coordc, cloud_off_all, meta, scratch, err, pair_scratch, hkeys, hvals, dev_sizes]
+    for stg in stages:
+        pend.tensors += [t for t in (stg.grid, stg.batch, stg.code, stg.order, stg.inverse, stg.nbr3, stg.pairs_out, stg.pairs_in,
+                                     stg.pair_cnt, stg.nbr5) if t is not None]
+        pend.tensors += [t for t in getattr(stg, "_next", ()) if t is not None]
+        for pl in stg.plans.values():
+            pend.tensors += [pl.gather_idx, pl.slot_of_point, pl.cu_seqlens, pl.pad, pl.unpad]
+    return pend
+
+
+def tokenize_finish(pend):
+    """wait for the size copy of `tokenize_launch`, slice the tables to their true extents -> [Stage_0 .. Stage_{S-1}]"""
+    pend.event.synchronize()
+    stages, S, B, host = pend.stages, pend.S, pend.B, pend.host
     meta_h = host[: S * META_STRIDE].view(S, META_STRIDE).tolist()
     off_h = host[S * META_STRIDE: S * META_STRIDE + S * (B + 1)].view(S, B + 1).tolist()
     if int(host[-1]) != 0:

@@ -209,8 +209,9 @@ def train(config, make_epoch, steps_per_epoch, val_batches=None, device=None, ra
     for epoch_id in range(restart_epoch, num_epochs):
         if global_step >= num_train_steps:
             break
-        for step, batch in enumerate(make_epoch(epoch_id)):
-            losses = step_fn.accumulate(batch, first=(step % acc == 0))
+        for step, (batch, upcoming) in enumerate(_lookahead(make_epoch(epoch_id))):
+            # `upcoming` is copied to the device and tokenised on a side stream while this step runs (native engine)
+            losses = step_fn.accumulate(batch, first=(step % acc == 0), next_batch=upcoming if eng.use_native else None)
             if (step + 1) % acc == 0:
                 step_fn.apply(accumulation=acc)
                 global_step = step_fn.global_step
@@ -241,6 +242,19 @@ def train(config, make_epoch, steps_per_epoch, val_batches=None, device=None, ra
             best_val, best_val_step = vm["pos_loss"], global_step
         LOGGER.info(f"Validation: Best loss: {best_val:.4f} at step {best_val_step}")
     return model, step_fn
+
+
+def _lookahead(it):
+    """(item, next item or None) pairs of an iterable"""
+    it = iter(it)
+    try:
+        cur = next(it)
+    except StopIteration:
+        return
+    for nxt in it:
+        yield cur, nxt
+        cur = nxt
+    yield cur, None
 
 
 def _plain(node):

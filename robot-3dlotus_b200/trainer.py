@@ -148,19 +148,28 @@ class TrainStep:
         self.global_step = 0
         self.lr_fn = None             # optional schedule override: global_step -> lr (train_loop.py)
 
-    def __call__(self, batch):
-        losses = self.accumulate(batch, first=True)
+    def __call__(self, batch, next_batch=None):
+        losses = self.accumulate(batch, first=True, next_batch=next_batch)
         self.apply()
         return losses
 
-    def accumulate(self, batch, first=True):
-        """forward + backward of one (micro-)batch; gradients ACCUMULATE in the flat buffer (zeroed when `first`)"""
+    def accumulate(self, batch, first=True, next_batch=None):
+        """forward + backward of one (micro-)batch; gradients ACCUMULATE in the flat buffer (zeroed when `first`).
+        `next_batch` (native engine): the batch of the NEXT call -- its host->device copy and integer tokeniser are launched on a
+        side stream now, so they overlap this step instead of opening the next one with an idle GPU."""
         if first:
             self.opt.zero_grad()
         eng = self.model.engine()
         if eng.use_native:
-            batch = self.model.prepare_batch(batch)
-            _, lv = eng.native_step(batch, compute_loss=True, with_grad=True, compute_final_action=False)
+            pre = eng.take_prefetched(batch)
+            pending = None
+            if pre is not None and pre[2]:
+                batch, pending = pre[0], pre[1]
+            else:
+                batch = self.model.prepare_batch(batch)
+            _, lv = eng.native_step(batch, compute_loss=True, with_grad=True, compute_final_action=False, pending=pending)
+            if next_batch is not None:                   # after this step is enqueued: the GPU is busy while the host prepares the next
+                eng.prefetch(next_batch, need_pairs=True)
             losses = {"pos": lv[0], "rot": lv[1], "open": lv[2], "total": lv[3]}
         else:
             _, losses = self.model(batch, compute_loss=True, compute_final_action=False)

@@ -838,3 +838,33 @@ def test_native_step_with_device_side_labels(gold_prod):
     assert abs(l1[0].item() - l2[0].item()) <= 1e-5 * abs(l1[0].item()), (l1, l2)          # position CE: the label tensors agree
     # (rot / open / total only see run-to-run bf16 noise: BatchNorm statistics are reduced with fp32 atomics)
     assert torch.allclose(l1, l2, rtol=2e-3, atol=1e-4), (l1, l2)
+
+
+def test_pipelined_input_prefetch_matches_synchronous_steps():
+    """TrainStep with `next_batch` (H2D copy + tokeniser of the next batch on a side stream during the current step) walks the same
+    trajectory as the synchronous steps: same losses over 4 optimizer steps from pinned host batches of different sizes"""
+    cfgm, syn, policy, trainer = pkg("config"), pkg("synthetic"), pkg("policy"), pkg("trainer")
+    batches = [syn.make_batch(seed=70 + i, sizes=sz) for i, sz in enumerate([[600, 300], [900], [200, 250, 400], [1000, 128]])]
+    host = []
+    for b in batches:
+        b = {k: v for k, v in b.items() if k != "disc_pos_probs"}
+        host.append({k: (v.pin_memory() if isinstance(v, torch.Tensor) else v) for k, v in b.items()})
+    traj = {}
+    for mode in ("sync", "pipelined"):
+        cfg = cfgm.production_model_config(attn_drop=0.0, proj_drop=0.0)
+        cfg.action_config.dropout = 0.0
+        torch.manual_seed(5)
+        model = policy.build_parameter_shell(cfg).to(DEV).train()
+        eng = model.engine()
+        eng.precision, eng.use_native = "bf16", True
+        eng.forced_perms = torch.stack([torch.arange(4)] * 5)
+        step = trainer.TrainStep(model, learning_rate=1e-4, warmup_steps=1)
+        out = []
+        for i in range(4):
+            nb = host[i + 1] if (mode == "pipelined" and i + 1 < 4) else None
+            losses = step(dict(host[i]), next_batch=nb)
+            out.append(torch.stack([losses[k] for k in ("pos", "rot", "open", "total")]).clone())
+        torch.cuda.synchronize()
+        traj[mode] = torch.stack(out).cpu()
+    assert torch.isfinite(traj["pipelined"]).all()
+    assert torch.allclose(traj["sync"], traj["pipelined"], rtol=5e-3, atol=1e-3), (traj["sync"], traj["pipelined"])
