@@ -329,11 +329,15 @@ def main():
     assert torch.cuda.is_available(), "bench.py needs a CUDA device (no CPU fallback exists for the product path)"
     torch.cuda.set_device(local)
     dev = torch.device("cuda", local)
+    saved_stdout = None
     if world > 1:
         import torch.distributed as dist
         import datetime
-        if os.environ.get("NCCL_DEBUG", "").upper() in ("VERSION", ""):
-            os.environ["NCCL_DEBUG"] = "WARN"        # NCCL prints its version banner to STDOUT otherwise; rank 0 must print ONE JSON line
+        # the NCCL communicator set-up prints a "NCCL version ..." banner on STDOUT; rank 0 must print ONE JSON line, so stdout is
+        # pointed at stderr until the warm-up (first collectives) is over
+        sys.stdout.flush()
+        saved_stdout = os.dup(1)
+        os.dup2(2, 1)
         dist.init_process_group("nccl", device_id=dev, timeout=datetime.timedelta(seconds=120))
     cfgm, syn, policy, trainer, lib = pkg("config"), pkg("synthetic"), pkg("policy"), pkg("trainer"), pkg("lib")
     L = lib.load()
@@ -375,6 +379,11 @@ def main():
         run_step(resident, i)
         if i % 8 == 7:
             torch.cuda.synchronize()
+    if saved_stdout is not None:
+        torch.cuda.synchronize()
+        sys.stdout.flush()
+        os.dup2(saved_stdout, 1)
+        os.close(saved_stdout)
     if rank == 0:
         sampler.wait_first(10.0)
     for i in range(3):                               # settle after the sampler attached (untimed)

@@ -12,5 +12,5 @@ try:
 except Exception as e:
     print("bench failed", e)
 PY
-timeout 300 python tools/infer_sweep.py --iters 15 --warmup 3 --batches 1,4,16,64,256 > gpurun_out/infer_sweep.json 2> gpurun_out/infer_sweep.err
-tail -2 gpurun_out/infer_sweep.err | cut -c1-200
+timeout 400 ncu --metrics gpu__time_duration.sum --clock-control none --csv --log-file gpurun_out/launches.csv python tools/one_step.py 3 > gpurun_out/ncu_launch.log 2>&1
+tail -1 gpurun_out/ncu_launch.log
