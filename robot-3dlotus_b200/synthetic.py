@@ -16,15 +16,19 @@ import torch
 VOXEL = 0.01
 
 
-def disc_gt_pos_prob(xyz, gt_pos, pos_bin_size=0.01, pos_bins=15):
-    """'dist' soft labels, restating genrobo3d/utils/action_position_utils.py:7-46 (heatmap_type='dist',
-    no robot mask).  xyz (n,3) f32/f64, gt_pos (3,) -> (3, n*2*pos_bins) float (dtype follows numpy promotion)."""
+def disc_gt_pos_prob(xyz, gt_pos, pos_bin_size=0.01, pos_bins=15, heatmap_type="dist"):
+    """soft position labels, restating genrobo3d/utils/action_position_utils.py:7-46 (no robot mask).
+    xyz (n,3) f32/f64, gt_pos (3,) -> (3, n*2*pos_bins) float (dtype follows numpy promotion; 'plain' is float32)."""
     shift = np.arange(-pos_bins, pos_bins) * pos_bin_size
     cands = xyz[:, :, None] + shift[None, None, :]                # (n,3,2b)
     dists = np.abs(gt_pos[None, :, None] - cands)
     dists = np.transpose(dists, (1, 0, 2)).reshape(3, -1)          # 'n c b -> c (n b)'
-    prob = 1.0 / np.maximum(dists, 1e-4)
-    prob[dists > 0.01] = 0
+    if heatmap_type == "plain":
+        prob = np.zeros(dists.shape, dtype=np.float32)
+        prob[dists < 0.01] = 1
+    else:
+        prob = 1.0 / np.maximum(dists, 1e-4)
+        prob[dists > 0.01] = 0
     for i in range(3):
         if prob[i].sum() == 0:
             prob[i, np.argmin(dists[i])] = 1

@@ -222,3 +222,24 @@ def test_variant_models_match_reference(kind, gold_variants):
                  compute_loss=False, compute_final_action=True, variant=_variant_of(kind))
     assert ev["final"].dtype == g["final_actions_eval"].dtype == torch.float64
     assert torch.allclose(ev["final"], g["final_actions_eval"], rtol=1e-5, atol=1e-6)
+
+
+def test_soft_label_restatement_matches_reference_all_branches():
+    """`synthetic.disc_gt_pos_prob` (the restatement the GPU producer test compares `lotus_disc_pos_prob` with) against vectors
+    minted from the reference's own `get_disc_gt_pos_prob` (oracle/make_golden_labels.py): both heatmap types, the argmin one-hot
+    fallback of an axis with no candidate within 1 cm, an exact hit (distance 0), a one-point cloud."""
+    from conftest import load_golden
+    syn = pkg("synthetic")
+    cases = load_golden("labels.pt")
+    assert len(cases) == 4
+    for c in cases:
+        xyz, gt = c["xyz"].numpy(), c["gt"].numpy()
+        for kind in ("dist", "plain"):
+            ref = c[kind].numpy()
+            got = syn.disc_gt_pos_prob(xyz, gt, 0.01, 15, kind)
+            assert got.shape == ref.shape == (3, xyz.shape[0] * 30)
+            assert np.allclose(got, ref, rtol=1e-12, atol=0), kind
+            assert np.allclose(ref.sum(-1), 1.0, atol=1e-6)
+    # the degenerate case really exercises the fallback: axis 1 is a one-hot
+    deg = cases[3]["dist"].numpy()
+    assert (deg[1] > 0).sum() == 1 and deg[1].max() == 1.0
