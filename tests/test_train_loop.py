@@ -79,3 +79,33 @@ def test_train_save_resume_roundtrip(tmp_path):
     for (n1, p1), (n2, p2) in zip(model.state_dict().items(), model2.state_dict().items()):
         assert n1 == n2 and torch.equal(p1.cpu(), p2.cpu()), n1
     assert torch.equal(step_fn.opt.exp_avg.cpu(), step2.opt.exp_avg.cpu())
+
+
+def test_lookahead_pairs():
+    tl = pkg("train_loop")
+    assert list(tl._lookahead([])) == []
+    assert list(tl._lookahead([1])) == [(1, None)]
+    assert list(tl._lookahead(iter([1, 2, 3]))) == [(1, 2), (2, 3), (3, None)]
+
+
+def test_model_saver_layout(tmp_path):
+    """ModelSaver writes `model_step_N.pt` (CPU tensors, 'module.' stripped) and `train_state_latest.pt` = {'step', 'optimizer'}
+    exactly where the reference's resume logic looks for them (train/utils/save.py:20-45, train_simple_policy.py:130-146)"""
+    tl = pkg("train_loop")
+
+    class Opt:
+        def state_dict(self):
+            return {"state": {}, "param_groups": []}
+
+    class Wrapped(torch.nn.Module):
+        def __init__(self):
+            super().__init__()
+            self.module = torch.nn.Linear(3, 2)
+
+    saver = tl.ModelSaver(str(tmp_path))
+    saver.save(Wrapped(), 40, optimizer=Opt(), rewrite_optimizer=True)
+    saver.save(Wrapped(), 50, optimizer=Opt(), rewrite_optimizer=False)
+    assert sorted(os.listdir(tmp_path)) == ["model_step_40.pt", "model_step_50.pt", "train_state_50.pt", "train_state_latest.pt"]
+    sd = torch.load(tmp_path / "model_step_40.pt")
+    assert sorted(sd) == ["bias", "weight"]
+    assert torch.load(tmp_path / "train_state_latest.pt", weights_only=False)["step"] == 40
