@@ -15,29 +15,10 @@
 //   OP_MN_TMA ...... operand stored [K][rows] (rows contiguous)      -> MN-major smem tile via TMA
 //   OP_MN_GATHER ... K-rows gathered through an index table          -> MN-major smem tile via cp.async
 #include "tc_common.cuh"
+#include "tc_host.cuh"
 #include <stdlib.h>
 
 namespace tc {
-
-// GELU (exact erf form, model.py:566 nn.GELU) for the GEMM epilogues: erf by Abramowitz-Stegun 7.1.26 (|err| <= 1.5e-7,
-// far below bf16 resolution).  z = |x| / sqrt(2) makes exp(-z^2) = exp(-x^2 / 2), which the derivative needs as well, so
-// gelu and gelu' cost one ex2 + one rcp + ~10 FMAs instead of erff + expf (the epilogue warps are ALU-bound otherwise).
-__device__ __forceinline__ float rcp_approx(float x) { float y; asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x)); return y; }
-__device__ __forceinline__ float ex2_approx(float x) { float y; asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x)); return y; }
-// half_s = 0.5 * s: cdf comes back pre-multiplied by s (the dropout keep-scale folds in for free)
-__device__ __forceinline__ void gelu_parts(float x, float half_s, float& cdf_s, float& e) {
-  const float z = fabsf(x) * 0.70710678118654752f;
-  const float t = rcp_approx(fmaf(0.3275911f, z, 1.f));
-  e = ex2_approx(x * x * -0.72134752044448170f);             // exp(-x^2 / 2)
-  float poly = fmaf(fmaf(fmaf(fmaf(1.061405429f, t, -1.453152027f), t, 1.421413741f), t, -0.284496736f), t, 0.254829592f) * t;
-  const float erf_abs = fmaf(-poly, e, 1.f);
-  cdf_s = fmaf(copysignf(erf_abs, x), half_s, half_s);
-}
-__device__ __forceinline__ float gelu_fast(float x, float half_s) { float c, e; gelu_parts(x, half_s, c, e); return x * c; }
-__device__ __forceinline__ float gelu_grad_fast(float x, float half_s) {
-  float c, e; gelu_parts(x, half_s, c, e);
-  return fmaf(x * e, 0.79788456080286535588f * half_s, c);   // s * (cdf + x * pdf), pdf = e / sqrt(2 pi)
-}
 
 constexpr int BM = 128;
 constexpr int BK = 64;            // 64 bf16 = 128 B = one SWIZZLE_128B span
@@ -512,43 +493,6 @@ k_gemm_tc(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUt
 }
 
 // ------------------------------------------------------------------------------------------------ host side
-typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
-                                  const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
-                                  CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
-static EncodeTiledFn get_encode() {
-  static EncodeTiledFn fn = nullptr;
-  if (!fn) {
-    void* ptr = nullptr;
-    cudaDriverEntryPointQueryResult qres;
-    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &ptr, cudaEnableDefault, &qres) == cudaSuccess &&
-        qres == cudaDriverEntryPointSuccess)
-      fn = (EncodeTiledFn)ptr;
-  }
-  return fn;
-}
-
-// 2-D tensor [rows][cols] (cols contiguous, row stride ld elements); box = {box_cols, box_rows}; 128-byte swizzle
-static int make_map(CUtensorMap* m, const void* base, int64_t rows, int64_t cols, int64_t ld, int box_cols, int box_rows,
-                    bool fp32 = false) {
-  EncodeTiledFn enc = get_encode();
-  if (!enc) { lotus_set_error("cuTensorMapEncodeTiled unavailable"); return 1; }
-  int es = fp32 ? 4 : 2;
-  cuuint64_t dims[2] = {(cuuint64_t)cols, (cuuint64_t)rows};
-  cuuint64_t strides[1] = {(cuuint64_t)ld * es};
-  cuuint32_t box[2] = {(cuuint32_t)box_cols, (cuuint32_t)box_rows};
-  cuuint32_t estr[2] = {1, 1};
-  CUresult r = enc(m, fp32 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT32 : CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, (void*)base, dims, strides, box,
-                   estr, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
-                   CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
-  if (r != CUDA_SUCCESS) {
-    lotus_set_error("cuTensorMapEncodeTiled failed (%d): base=%p rows=%lld cols=%lld ld=%lld box=%dx%d fp32=%d (base must be 16-byte "
-                    "aligned, row stride a multiple of 16 bytes)", (int)r, base, (long long)rows, (long long)cols, (long long)ld,
-                    box_cols, box_rows, (int)fp32);
-    return 1;
-  }
-  return 0;
-}
-
 static unsigned long long* g_dbg_ts = nullptr;
 
 struct Operand {
@@ -677,43 +621,6 @@ static Params base_params(int M, int N, int K, void* out, int64_t ldo, int out_f
   memset(&p, 0, sizeof(p));
   p.M = M; p.N = N; p.K = K; p.out = out; p.ldo = ldo; p.out_fp32 = out_fp32;
   return p;
-}
-
-// y[M,N] = [residual +] drop(act(x[M,K] @ w[N,K]^T + bias)) ; x, w bf16 ; y (and residual) bf16 or fp32 ;
-// y_preact (bf16 [M,N], optional): receives x @ w^T + bias before the activation (saved for the backward of a fused GELU)
-LOTUS_API int lotus_linear_fwd_bf16(const void* x, const void* w, const float* bias, const void* residual, void* y,
-                                    void* y_preact, int M, int N, int K, int act, int out_fp32, float drop_p, uint64_t seed,
-                                    uint32_t drop_stream, void* stream_) {
-  LOTUS_CHECK_ARG(K % 8 == 0, "lotus_linear_fwd_bf16: K=%d must be a multiple of 8 (16-byte TMA rows)", K);
-  LOTUS_CHECK_ARG(y_preact == nullptr || (!out_fp32 && residual == nullptr),
-                  "lotus_linear_fwd_bf16: y_preact needs a bf16 output and no residual");
-  LOTUS_CHECK_ARG(N % (out_fp32 ? 4 : 8) == 0, "lotus_linear_fwd_bf16: N=%d must keep output rows 16-byte aligned", N);
-  Params p = base_params(M, N, K, y, N, out_fp32);
-  p.out2 = y_preact; p.bias = bias; p.residual = residual; p.act = act; p.drop_p = drop_p; p.seed = seed; p.drop_stream = drop_stream;
-  Operand A{tc::OP_K_TMA, (const __nv_bfloat16*)x, K, {}}, B{tc::OP_K_TMA, (const __nv_bfloat16*)w, K, {}};
-  return tc::launch(A, B, p, tc::pick_bn(N), 1, (cudaStream_t)stream_);
-}
-
-// dx[M,K] = [residual +] dy[M,N] @ w[N,K]   using the pre-transposed weight wt[K,N] (bf16)
-LOTUS_API int lotus_linear_dgrad_bf16(const void* dy, const void* wt, const void* residual, void* dx, int M, int N, int K,
-                                      int out_fp32, void* stream_) {
-  LOTUS_CHECK_ARG(N % 8 == 0, "lotus_linear_dgrad_bf16: N=%d must be a multiple of 8", N);
-  Params p = base_params(M, K, N, dx, K, out_fp32);
-  p.residual = residual;
-  Operand A{tc::OP_K_TMA, (const __nv_bfloat16*)dy, N, {}}, B{tc::OP_K_TMA, (const __nv_bfloat16*)wt, N, {}};
-  return tc::launch(A, B, p, tc::pick_bn(K), 1, (cudaStream_t)stream_);
-}
-
-// dx[M,K] = drop(dy[M,N] @ w[N,K] * act'(preact[M,K])) : the backward of `y = drop(act(preact))` fused into the data-gradient GEMM
-// of the NEXT layer (act 1 = GELU; preact and dx bf16; the dropout mask is the forward's: same seed / stream / element index)
-LOTUS_API int lotus_linear_dgrad_act_bf16(const void* dy, const void* wt, const void* preact, void* dx, int M, int N, int K, int act,
-                                          float drop_p, uint64_t seed, uint32_t drop_stream, void* stream_) {
-  LOTUS_CHECK_ARG(N % 8 == 0 && K % 8 == 0, "lotus_linear_dgrad_act_bf16: N=%d, K=%d must be multiples of 8", N, K);
-  LOTUS_CHECK_ARG(act == 1 && preact != nullptr, "lotus_linear_dgrad_act_bf16: act must be 1 (GELU) with a pre-activation tensor");
-  Params p = base_params(M, K, N, dx, K, 0);
-  p.residual = preact; p.act = tc::ACT_GELU_GRAD; p.drop_p = drop_p; p.seed = seed; p.drop_stream = drop_stream;
-  Operand A{tc::OP_K_TMA, (const __nv_bfloat16*)dy, N, {}}, B{tc::OP_K_TMA, (const __nv_bfloat16*)wt, N, {}};
-  return tc::launch(A, B, p, tc::pick_bn(K), 1, (cudaStream_t)stream_);
 }
 
 // dw[N,K] (fp32) += dy[M,N]^T @ x[M,K]   (both operands consumed MN-major straight from their row-major storage)

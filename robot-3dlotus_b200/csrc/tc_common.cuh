@@ -136,5 +136,25 @@ __device__ __forceinline__ uint64_t make_desc(uint32_t saddr, uint32_t lbo_bytes
   return d;
 }
 
+// GELU (exact erf form, model.py:566 nn.GELU) for the GEMM epilogues: erf by Abramowitz-Stegun 7.1.26 (|err| <= 1.5e-7,
+// far below bf16 resolution).  z = |x| / sqrt(2) makes exp(-z^2) = exp(-x^2 / 2), which the derivative needs as well, so
+// gelu and gelu' cost one ex2 + one rcp + ~10 FMAs instead of erff + expf (the epilogue warps are ALU-bound otherwise).
+__device__ __forceinline__ float rcp_approx(float x) { float y; asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x)); return y; }
+__device__ __forceinline__ float ex2_approx(float x) { float y; asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x)); return y; }
+// half_s = 0.5 * s: cdf comes back pre-multiplied by s (the dropout keep-scale folds in for free)
+__device__ __forceinline__ void gelu_parts(float x, float half_s, float& cdf_s, float& e) {
+  const float z = fabsf(x) * 0.70710678118654752f;
+  const float t = rcp_approx(fmaf(0.3275911f, z, 1.f));
+  e = ex2_approx(x * x * -0.72134752044448170f);             // exp(-x^2 / 2)
+  float poly = fmaf(fmaf(fmaf(fmaf(1.061405429f, t, -1.453152027f), t, 1.421413741f), t, -0.284496736f), t, 0.254829592f) * t;
+  const float erf_abs = fmaf(-poly, e, 1.f);
+  cdf_s = fmaf(copysignf(erf_abs, x), half_s, half_s);
+}
+__device__ __forceinline__ float gelu_fast(float x, float half_s) { float c, e; gelu_parts(x, half_s, c, e); return x * c; }
+__device__ __forceinline__ float gelu_grad_fast(float x, float half_s) {
+  float c, e; gelu_parts(x, half_s, c, e);
+  return fmaf(x * e, 0.79788456080286535588f * half_s, c);   // s * (cdf + x * pdf), pdf = e / sqrt(2 pi)
+}
+
 
 }  // namespace tc

@@ -196,7 +196,7 @@ class PolicyEngine:
         if self._pf_stream is None:
             self._pf_stream = torch.cuda.Stream()
         main = torch.cuda.current_stream()
-        key = id(batch["pc_fts"])
+        key = batch["pc_fts"]                        # the tensor object itself (kept alive: an id() could be reused after a free)
         with torch.cuda.stream(self._pf_stream):
             dev_batch = self.m.prepare_batch(dict(batch))
             fts = dev_batch["pc_fts"]
@@ -209,7 +209,7 @@ class PolicyEngine:
     def take_prefetched(self, batch):
         """-> (device batch, pending tokens) if `prefetch` was called with this batch object, else None"""
         pf, self._prefetched = self._prefetched, None
-        if pf is not None and pf[0] == id(batch["pc_fts"]):
+        if pf is not None and pf[0] is batch["pc_fts"]:
             return pf[1], pf[2], pf[3]
         return None
 

@@ -20,7 +20,25 @@ def supported(model):
             and all(d == 1 for d in pt.enc_depths) and all(d == 1 for d in pt.dec_depths)
             and not ac.use_ee_pose and not ac.use_step_id and ac.pos_pred_type == "heatmap_disc"
             and ac.rot_pred_type == "euler_disc" and ac.reduce == "max"
-            and len(set(pt.enc_patch_size + pt.dec_patch_size)) == 1)
+            and len(set(pt.enc_patch_size + pt.dec_patch_size)) == 1
+            and _no_drop_path(pt))
+
+
+def _no_drop_path(pt):
+    """the C++ executor has no stochastic depth (model.py:659-680 DropPath; 0 in every shipped job script, 0.1 in the bare yaml)"""
+    from .modules import Block
+    return all(getattr(b, "drop_path_p", 0.0) == 0 for b in pt.modules() if isinstance(b, Block) or hasattr(b, "drop_path_p"))
+
+
+def _f32_dev(t, dev, name):
+    """-> contiguous float32 tensor on `dev` (no copy when it already is one)"""
+    if not isinstance(t, torch.Tensor):
+        raise TypeError(f"native step: batch['{name}'] must be a tensor, got {type(t).__name__}")
+    if t.device != dev:
+        t = t.to(dev, non_blocking=True)
+    if t.dtype != torch.float32:
+        t = t.float()
+    return t if t.is_contiguous() else t.contiguous()
 
 
 class NativeStep:
@@ -93,13 +111,19 @@ class NativeStep:
         fl = (ctypes.c_float * 6)(float(pt.enc.enc0.block0.attn.attn_drop), float(pt.enc.enc0.block0.proj_drop),
                                   float(m.act_proj_head.dropout), float(lc.pos_weight), float(lc.rot_weight),
                                   float(m.act_proj_head.euler_resolution))
-        feat = batch["pc_fts"]
-        txt = batch["txt_embeds"]
+        # the C ABI takes raw `const float*`: coerce what a reference collate may hand over (float64 soft labels from
+        # numpy arithmetic, `action_position_utils.py:7-46`; non-contiguous slices) BEFORE any pointer is taken
+        feat = _f32_dev(batch["pc_fts"], dev, "pc_fts")
+        txt = _f32_dev(batch["txt_embeds"], dev, "txt_embeds")
         gt = batch.get("gt_actions")
+        if gt is not None:
+            gt = _f32_dev(gt, dev, "gt_actions")
         prob = batch.get("disc_pos_probs_packed")
+        if prob is not None:
+            prob = _f32_dev(prob, dev, "disc_pos_probs_packed")
         if compute_loss and prob is None:
             if "disc_pos_probs" in batch:
-                prob = torch.cat([p.reshape(-1) for p in batch["disc_pos_probs"]]).to(dev, non_blocking=True)
+                prob = _f32_dev(torch.cat([p.reshape(-1) for p in batch["disc_pos_probs"]]), dev, "disc_pos_probs")
             else:   # device-side batch producer: soft labels from (xyz, gt position) instead of a host tensor
                 from . import ops
                 prob = ops.disc_pos_prob(feat, stages[0].cloud_off, B, stages[0].max_cloud, gt, ac.pos_bins, ac.pos_bin_size,

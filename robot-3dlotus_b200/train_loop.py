@@ -210,22 +210,25 @@ def train(config, make_epoch, steps_per_epoch, val_batches=None, device=None, ra
         if global_step >= num_train_steps:
             break
         for step, (batch, upcoming) in enumerate(_lookahead(make_epoch(epoch_id))):
-            # `upcoming` is copied to the device and tokenised on a side stream while this step runs (native engine)
-            losses = step_fn.accumulate(batch, first=(step % acc == 0), next_batch=upcoming if eng.use_native else None)
-            if (step + 1) % acc == 0:
+            # `upcoming` is copied to the device and tokenised on a side stream while this step runs (native engine).
+            # Accumulation windows run on a micro-step counter that survives epoch boundaries (the reference only zeroes
+            # gradients after optimizer.step(), train_simple_policy.py:214-243)
+            losses = step_fn.accumulate(batch, first=None, next_batch=upcoming if eng.use_native else None)
+            stepped = step_fn.micro_step >= acc
+            if stepped:
                 step_fn.apply(accumulation=acc)
                 global_step = step_fn.global_step
                 n_log += 1
-            if global_step % T.log_steps == 0 and (step + 1) % acc == 0:
+            if global_step % T.log_steps == 0 and stepped:
                 vals = {k: float(v) for k, v in zip(("pos", "rot", "open", "total"), torch.stack([losses[k] for k in ("pos", "rot", "open", "total")]).tolist())}
                 running.update({f"loss_{k}": v for k, v in vals.items()})
                 dt = time.time() - t_log
                 LOGGER.info(f"==============Epoch {epoch_id} Step {global_step}===============")
                 LOGGER.info(", ".join("%s:%.4f" % kv for kv in running.items()) + ", grad_norm:%.4f, steps/s:%.2f" % (step_fn.opt.grad_norm(), n_log / max(dt, 1e-9)))
                 t_log, n_log = time.time(), 0
-            if default_gpu and global_step % T.save_steps == 0 and (step + 1) % acc == 0:
+            if default_gpu and global_step % T.save_steps == 0 and stepped:
                 saver.save(model, global_step, optimizer=step_fn.opt, rewrite_optimizer=True)
-            if val_batches is not None and T.val_steps and global_step % T.val_steps == 0 and (step + 1) % acc == 0:
+            if val_batches is not None and T.val_steps and global_step % T.val_steps == 0 and stepped:
                 vm = validate(model, val_batches)
                 LOGGER.info("=================Validation=================")
                 LOGGER.info(", ".join("%s: %.4f" % kv for kv in vm.items()))

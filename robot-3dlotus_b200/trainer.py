@@ -11,6 +11,7 @@ BatchNorm statistics stay per-rank: identical to the reference a
 gradient all-reduce the only collective.
 """
 import math
+import weakref
 
 import torch
 import torch.distributed as dist
@@ -31,6 +32,13 @@ def warmup_cosine(step, warmup_step, tot_step, num_cycles=0.5):
 def get_lr_sched_decay_rate(global_step, warmup_steps, num_train_steps):
     """train/optim/sched.py:95-113 (cosine)"""
     return max(warmup_cosine(global_step, warmup_steps, num_train_steps), 1e-5)
+
+
+def _drop_sinks(keys, grad_base):
+    for k in keys:
+        g = ops.GRAD_SINK.get(k)
+        if g is not None and g.untyped_storage().data_ptr() == grad_base:
+            del ops.GRAD_SINK[k]
 
 
 class FlatAdamW:
@@ -58,7 +66,11 @@ class FlatAdamW:
         self.exp_avg = torch.zeros(total, device=dev, dtype=torch.float32)
         self.exp_avg_sq = torch.zeros(total, device=dev, dtype=torch.float32)
         ends, off = [], 0
-        ops.GRAD_SINK.clear()
+        # gradient sinks are process-global (keyed by parameter address): drop only what THIS model registered before
+        # (re-building an optimizer for the same model), never another live model's entries
+        for p in self.params:
+            ops.GRAD_SINK.pop(p.data_ptr(), None)
+        self._sink_keys = []
         for p, n, slot in zip(self.params, sizes, slots):
             view = self.flat_param[off: off + n].view_as(p)
             view.copy_(p.data)
@@ -66,8 +78,11 @@ class FlatAdamW:
             g = self.flat_grad[off: off + n].view_as(p)
             p.grad = g                                      # reference-style access (`p.grad`) keeps working
             ops.GRAD_SINK[p.data_ptr()] = g
+            self._sink_keys.append(p.data_ptr())
             off += slot
             ends.append(off)
+        # the entries die with this optimizer (its flat buffer is freed then; a later allocation may reuse the addresses)
+        weakref.finalize(self, _drop_sinks, list(self._sink_keys), self.flat_grad.data_ptr())
         self.seg_end = torch.tensor(ends, dtype=torch.int64, device=dev)
         wd = [weight_decay] * len(decay) + [0.0] * len(no_decay)
         self.seg_wd = torch.tensor(wd, dtype=torch.float32, device=dev)
@@ -78,6 +93,18 @@ class FlatAdamW:
 
     def zero_grad(self):
         self.flat_grad.zero_()
+
+    def broadcast_parameters(self, model, src=0):
+        """What DDP's wrap does once (reference train/utils/distributed.py:196-212 `wrap_model` -> DistributedDataParallel broadcasts
+        rank 0's parameters and buffers at construction): the per-rank seeds (train_simple_policy.py:64-67) make every rank
+        initialise different weights; after this call all replicas start from rank `src`'s.  One broadcast of the flat parameter
+        buffer plus the BatchNorm buffers; set-up only, never inside a step."""
+        if self.world <= 1:
+            return
+        dist.broadcast(self.flat_param, src=src)
+        for b in model.buffers():
+            dist.broadcast(b, src=src)
+        ops.PARAM_EPOCH[0] += 1
 
     def all_reduce(self):
         """the one collective of the path: sum of the flat gradient over ranks (mean applied inside the AdamW kernel)"""
@@ -147,6 +174,8 @@ class TrainStep:
         self.learning_rate, self.warmup_steps, self.num_train_steps = learning_rate, warmup_steps, num_train_steps
         self.global_step = 0
         self.lr_fn = None             # optional schedule override: global_step -> lr (train_loop.py)
+        self.micro_step = 0           # micro-batches accumulated since the last optimizer step (carried across epochs)
+        self.opt.broadcast_parameters(model)      # world > 1: replicas start from rank 0's weights, as under DDP
 
     def __call__(self, batch, next_batch=None):
         losses = self.accumulate(batch, first=True, next_batch=next_batch)
@@ -157,8 +186,12 @@ class TrainStep:
         """forward + backward of one (micro-)batch; gradients ACCUMULATE in the flat buffer (zeroed when `first`).
         `next_batch` (native engine): the batch of the NEXT call -- its host->device copy and integer tokeniser are launched on a
         side stream now, so they overlap this step instead of opening the next one with an idle GPU."""
+        if first is None:                                # running counter: zero only after an optimizer step (reference: zero_grad
+            first = self.micro_step == 0                 # follows optimizer.step(), so a partial window carries over an epoch boundary)
         if first:
             self.opt.zero_grad()
+            self.micro_step = 0
+        self.micro_step += 1
         eng = self.model.engine()
         if eng.use_native:
             pre = eng.take_prefetched(batch)
@@ -180,6 +213,7 @@ class TrainStep:
         """all-reduce, clip, AdamW with the scheduled learning rate (train_simple_policy.py:214-232); the 1/accumulation of the
         reference's loss scaling (:206-207) is folded into the optimizer kernel's gradient scale"""
         self.opt.all_reduce()
+        self.micro_step = 0
         self.global_step += 1
         if self.lr_fn is not None:
             lr = self.lr_fn(self.global_step)

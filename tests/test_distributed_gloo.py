@@ -158,3 +158,75 @@ def test_keystep_sharding_world2():
     ret = mgr.dict()
     mp.spawn(_shard_worker, args=(world, _free_port(), ret), nprocs=world, join=True)
     assert dict(ret) == {0: "ok", 1: "ok"}
+
+
+def _bcast_worker(rank, world, port, ret):
+    sys.path.insert(0, ROOT)
+    import importlib
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port), RANK=str(rank), WORLD_SIZE=str(world))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        cfgm = importlib.import_module("robot-3dlotus_b200.config")
+        policy = importlib.import_module("robot-3dlotus_b200.policy")
+        trainer = importlib.import_module("robot-3dlotus_b200.trainer")
+        # per-rank seeds BEFORE the model is built, exactly like train_loop.train / train_simple_policy.py:64-67: the replicas
+        # initialise differently and only the set-up broadcast (DDP's wrap in the reference) makes them equal
+        torch.manual_seed(2024 + rank)
+        model = policy.build_parameter_shell(cfgm.small_model_config())
+        # make the BatchNorm buffers rank-dependent too (they are broadcast as well)
+        for b in model.buffers():
+            if b.dtype.is_floating_point:
+                b.add_(float(rank))
+        d0 = torch.tensor([float(sum(p.double().abs().sum() for p in model.parameters()))], dtype=torch.float64)
+        both = [torch.zeros_like(d0) for _ in range(world)]
+        dist.all_gather(both, d0)
+        assert not torch.equal(both[0], both[1]), "test is vacuous: replicas already equal before the broadcast"
+        step = trainer.TrainStep(model)                          # no deterministic_reinit, no manual broadcast
+        digest = torch.tensor([float(step.opt.flat_param.double().sum()), float(step.opt.flat_param.double().abs().sum()),
+                               float(sum(b.double().sum() for b in model.buffers()))], dtype=torch.float64)
+        both = [torch.zeros_like(digest) for _ in range(world)]
+        dist.all_gather(both, digest)
+        assert torch.equal(both[0], both[1]), (both[0], both[1])
+        # parameters still alias the flat buffer after the broadcast
+        for p in model.parameters():
+            o = (p.data_ptr() - step.opt.flat_param.data_ptr()) // 4
+            assert torch.equal(p.detach().reshape(-1), step.opt.flat_param[o: o + p.numel()])
+        ret[rank] = "ok"
+    except BaseException as e:
+        ret[rank] = f"{type(e).__name__}: {e}"
+        raise
+    finally:
+        dist.destroy_process_group()
+
+
+def test_replicas_start_equal_world2():
+    """without DDP nothing broadcast rank 0's initial weights; TrainStep now does it at construction."""
+    world = 2
+    mgr = mp.Manager()
+    ret = mgr.dict()
+    mp.spawn(_bcast_worker, args=(world, _free_port(), ret), nprocs=world, join=True)
+    assert dict(ret) == {0: "ok", 1: "ok"}
+
+
+def test_grad_sinks_are_scoped_per_optimizer():
+    """a second optimizer in the process must not drop the first model's gradient sinks."""
+    sys.path.insert(0, ROOT)
+    import importlib
+    cfgm = importlib.import_module("robot-3dlotus_b200.config")
+    policy = importlib.import_module("robot-3dlotus_b200.policy")
+    trainer = importlib.import_module("robot-3dlotus_b200.trainer")
+    ops = importlib.import_module("robot-3dlotus_b200.ops")
+    m1 = policy.build_parameter_shell(cfgm.small_model_config())
+    o1 = trainer.FlatAdamW(m1)
+    keys1 = [p.data_ptr() for p in m1.parameters()]
+    m2 = policy.build_parameter_shell(cfgm.small_model_config())
+    o2 = trainer.FlatAdamW(m2)
+    assert all(k in ops.GRAD_SINK for k in keys1)
+    for p in m1.parameters():
+        assert ops.GRAD_SINK[p.data_ptr()].data_ptr() == p.grad.data_ptr()
+    keys2 = [p.data_ptr() for p in m2.parameters()]
+    del o2, m2
+    import gc
+    gc.collect()
+    assert not any(k in ops.GRAD_SINK for k in keys2) and all(k in ops.GRAD_SINK for k in keys1)
+    assert o1 is not None

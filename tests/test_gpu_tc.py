@@ -75,6 +75,56 @@ def test_linear_dgrad_wgrad_bf16(M, N, K):
     assert rel(dw, dy.float().t() @ x.float()) < 2e-3, rel(dw, dy.float().t() @ x.float())
 
 
+@pytest.mark.parametrize("M,N,K", [(5000, 192, 64), (130, 64, 64), (4096, 256, 128), (131, 768, 3072), (70000, 64, 256), (40000, 512, 128),
+                                   (647, 1536, 256), (20011, 128, 512)])
+@pytest.mark.parametrize("fused_act", [False, True])
+def test_linear_dgrad_bias_bf16(M, N, K, fused_act):
+    """the data-gradient GEMM also emits the bias gradient (column sums of dy taken from the operand tiles in shared memory);
+    checked against fp32 torch on the same bf16-rounded operands: dx 1e-2 (bf16 store), db 2e-3 (fp32 accumulate), accumulation kept"""
+    L = pkg("lib").load()
+    g = torch.Generator().manual_seed(M * 3 + N + K)
+    w = bf(torch.randn(N, K, generator=g) * K ** -0.5).to(DEV)
+    dy = bf(torch.randn(M, N, generator=g)).to(DEV)
+    wt = w.t().contiguous()
+    dx = torch.full((M, K), float("nan"), device=DEV, dtype=torch.bfloat16)
+    db0 = torch.randn(N, generator=g).to(DEV)
+    db = db0.clone()
+    ref = dy.float() @ w.float()
+    if fused_act:
+        u = bf(torch.randn(M, K, generator=g)).to(DEV)
+        uf = u.float().requires_grad_(True)
+        torch.nn.functional.gelu(uf).backward(ref)
+        ref = uf.grad
+        L.lotus_linear_dgrad_act_bias_bf16(P(dy), P(wt), P(u), P(dx), P(db), M, N, K, 1, 0.0, 0, 0, None)
+    else:
+        L.lotus_linear_dgrad_bias_bf16(P(dy), P(wt), None, P(dx), P(db), M, N, K, 0, None)
+    torch.cuda.synchronize()
+    assert rel(dx.float(), ref) < 1e-2, rel(dx.float(), ref)
+    ref_db = db0.double() + dy.double().sum(0)
+    assert ((db.double() - ref_db).abs().max() / ref_db.abs().max()).item() < 2e-3
+
+
+def test_linear_dropout_mask_matches_elementwise_kernel():
+    """the GEMM epilogue's dropout mask is the mask lotus_dropout_bf16 draws for the same (seed, stream, element index):
+    the backward re-creates the forward's mask with the elementwise kernel"""
+    L = pkg("lib").load()
+    M, N, K = 3000, 256, 64
+    g = torch.Generator().manual_seed(5)
+    x = bf(torch.randn(M, K, generator=g)).to(DEV)
+    w = bf(torch.randn(N, K, generator=g) * K ** -0.5).to(DEV)
+    y0 = torch.empty(M, N, device=DEV, dtype=torch.bfloat16)
+    y1 = torch.empty_like(y0)
+    yd = torch.empty_like(y0)
+    L.lotus_linear_fwd_bf16(P(x), P(w), None, None, P(y0), None, M, N, K, 0, 0, 0.0, 0, 0, None)
+    L.lotus_linear_fwd_bf16(P(x), P(w), None, None, P(y1), None, M, N, K, 0, 0, 0.25, 1234, 7, None)
+    L.lotus_dropout_bf16(P(y0), P(yd), M * N, 0.25, 1234, 7, None)
+    torch.cuda.synchronize()
+    assert torch.equal((y1 == 0), (yd == 0)) or ((y1 == 0) ^ (yd == 0)).float().mean().item() < 1e-4   # exact zeros of y0 aside
+    keep = (yd != 0).float().mean().item()
+    assert 0.70 < keep < 0.80, keep
+    assert rel(y1.float(), yd.float()) < 1e-2
+
+
 @pytest.mark.parametrize("cin,cout", [(64, 64), (128, 128), (64, 192)])
 def test_subm_conv_bf16(cin, cout):
     import test_gpu_parity as tp

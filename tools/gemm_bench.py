@@ -12,9 +12,14 @@ for (M, N, K) in shapes:
     y = torch.empty(M, N, device=dev, dtype=torch.bfloat16); b = torch.randn(N, device=dev)
     dy = torch.randn(M, N, device=dev).bfloat16(); wt = w.t().contiguous(); dx = torch.empty_like(x)
     dw = torch.zeros(N, K, device=dev)
+    db = torch.zeros(N, device=dev); pre = torch.empty_like(y); u = torch.randn(M, K, device=dev).bfloat16(); resd = torch.randn(M, N, device=dev).bfloat16()
     res = {}
     for name, fn in (("fwd", lambda: L.lotus_linear_fwd_bf16(P(x), P(w), P(b), None, P(y), None, M, N, K, 0, 0, 0.0, 0, 0, None)),
                      ("dgrad", lambda: L.lotus_linear_dgrad_bf16(P(dy), P(wt), None, P(dx), M, N, K, 0, None)),
+                     ("fwd_gelu2", lambda: L.lotus_linear_fwd_bf16(P(x), P(w), P(b), None, P(y), P(pre), M, N, K, 1, 0, 0.1, 1, 1, None)),
+                     ("fwd_res", lambda: L.lotus_linear_fwd_bf16(P(x), P(w), P(b), P(resd), P(y), None, M, N, K, 0, 0, 0.1, 1, 1, None)),
+                     ("dgrad_b", lambda: L.lotus_linear_dgrad_bias_bf16(P(dy), P(wt), None, P(dx), P(db), M, N, K, 0, None)),
+                     ("dgrad_act_b", lambda: L.lotus_linear_dgrad_act_bias_bf16(P(dy), P(wt), P(u), P(dx), P(db), M, N, K, 1, 0.1, 1, 1, None)),
                      ("wgrad", lambda: L.lotus_linear_wgrad_bf16(P(dy), P(x), P(dw), M, N, K, None)),
                      ("cublas", lambda: torch.matmul(x, w.t()))):
         for _ in range(3): fn()

@@ -52,6 +52,9 @@ DOC = {
     "lotus_linear_fwd_bf16": "bf16 tensor-core (tcgen05/TMEM/TMA) form of nn.Linear forward, same call sites as lotus_linear_fwd_f32; "
                              "fused bias/GELU/LeakyReLU/dropout/residual epilogue, optional pre-activation copy.",
     "lotus_linear_dgrad_bf16": "bf16 tensor-core backward of nn.Linear w.r.t. its input (uses the pre-transposed bf16 weight).",
+    "lotus_linear_dgrad_bias_bf16": "lotus_linear_dgrad_bf16 that also accumulates the layer's bias gradient (column sums of dy, read from the operand tiles already in shared memory): "
+                                    "autograd of nn.Linear at the call sites of lotus_linear_fwd_f32.",
+    "lotus_linear_dgrad_act_bias_bf16": "lotus_linear_dgrad_act_bf16 that also accumulates fc2's bias gradient (column sums of dy): model.py:560-583.",
     "lotus_linear_dgrad_act_bf16": "bf16 tensor-core backward of `fc2(drop(GELU(u)))` w.r.t. u (MLP, model.py:560-583): data-gradient GEMM with gelu'(u) and the forward's dropout mask applied in the epilogue.",
     "lotus_disc_pos_prob": "Replaces get_disc_gt_pos_prob (soft position labels, computed per keystep by the DataLoader workers): utils/action_position_utils.py:7-46, "
                            "call site train/datasets/simple_policy_dataset.py:346-354. float64 arithmetic like numpy, packed fp32 output.",
