@@ -250,11 +250,16 @@ def patch_attention(x, P, pre, H, order, inverse, plan, K=128, qk_norm=True, rpe
     """SerializedAttention.forward, flash branch semantics in fp32 (model.py:468-557).
     x is the *normed* input; returns proj(attn) (dropout 0)."""
     pad, unpad, cu = plan
-    C = x.shape[1]
-    D = C // H
     o = order[pad]
     inv = unpad[inverse]
-    qkv = F.linear(x, P[pre + "qkv.weight"], P.get(pre + "qkv.bias"))[o].reshape(-1, 3, H, D)
+    if P.get(pre + "qkv.weight") is None:      # kernel-level tests: `x` already holds the (N, 3C) projections
+        C = x.shape[1] // 3
+        D = C // H
+        qkv = x[o].reshape(-1, 3, H, D)
+    else:
+        C = x.shape[1]
+        D = C // H
+        qkv = F.linear(x, P[pre + "qkv.weight"], P.get(pre + "qkv.bias"))[o].reshape(-1, 3, H, D)
     q, k, v = qkv.unbind(1)
     if qk_norm:
         q = layer_norm(q, P[pre + "q_norm.weight"], P[pre + "q_norm.bias"], 1e-6)
@@ -275,8 +280,11 @@ def cross_attention(x, ctx, P, pre, H, offset, ctx_offset, qk_norm=True):
     """CrossAttention.forward (model_ca.py:46-101), flash branch semantics in fp32."""
     C = x.shape[1]
     D = C // H
-    q = F.linear(x, P[pre + "q.weight"], P[pre + "q.bias"]).view(-1, H, D)
-    kv = F.linear(ctx, P[pre + "kv.weight"], P[pre + "kv.bias"]).view(-1, 2, H, D)
+    if P.get(pre + "q.weight") is None:        # kernel-level tests: `x` / `ctx` already hold the q / kv projections
+        q, kv = x.view(-1, H, D), ctx.view(-1, 2, H, D)
+    else:
+        q = F.linear(x, P[pre + "q.weight"], P[pre + "q.bias"]).view(-1, H, D)
+        kv = F.linear(ctx, P[pre + "kv.weight"], P[pre + "kv.bias"]).view(-1, 2, H, D)
     k, v = kv[:, 0], kv[:, 1]
     if qk_norm:
         q = layer_norm(q, P[pre + "q_norm.weight"], P[pre + "q_norm.bias"], 1e-6)

@@ -295,3 +295,90 @@ def test_cross_attention_mma_vs_simt(H, D, drop_p, toks):
         if qk_norm:
             for a, b in list(zip(res["mma"][3], res["simt"][3]))[:3]:
                 assert rel(a, b) < 3e-2, rel(a, b)
+
+
+def _grad_of(fn, inputs, go):
+    xs = [t.clone().requires_grad_(True) for t in inputs]
+    y = fn(*xs)
+    y.backward(go)
+    return y.detach(), [x.grad for x in xs]
+
+
+@pytest.mark.parametrize("H,D", [(2, 32), (4, 32), (32, 24), (2, 16), (2, 64)])
+@pytest.mark.parametrize("qk_norm", [True, False])
+def test_patch_attention_bf16_vs_fp32_oracle(H, D, qk_norm):
+    """the tensor-core patch attention against the fp32 ORACLE (oracle/lotus_oracle.py::patch_attention, itself pinned
+    to the reference by tests/test_oracle_golden.py) evaluated on the same bf16-rounded q/k/v -- not against the repo's own SIMT kernel.
+    Ragged clouds: short sequences, a one-point cloud, a padded tail with alias slots.  Tolerances: output 1e-2 (bf16 store + bf16 P),
+    gradients 2e-2 of the tensor's max (bf16 dS / dP operands), q/k-norm affine gradients 3e-2."""
+    ops, tk = pkg("ops"), pkg("tokenizer")
+    from test_gpu_parity import lattice_clouds
+    sizes = [300, 90, 129, 1, 128, 400]
+    coord, grid = lattice_clouds(sizes, 24, 6)
+    stg = tk.tokenize(coord.to(DEV), sizes, ["hilbert"], [2], [128, 128], [[0], [0]], None)[0]
+    off = torch.tensor(np.cumsum(sizes))
+    ser = O.serialize(O.grid_coords(coord), O.offset2batch(off), ["hilbert"])
+    plan = O.patch_plan(off, 128)
+    C, n = H * D, sum(sizes)
+    g = torch.Generator().manual_seed(H * 131 + D)
+    qkv = bf(torch.randn(n, 3 * C, generator=g) * 1.5)
+    norm = [1 + 0.1 * torch.randn(D, generator=g), 0.1 * torch.randn(D, generator=g),
+            1 + 0.1 * torch.randn(D, generator=g), 0.1 * torch.randn(D, generator=g)]
+    go = bf(torch.randn(n, C, generator=g))
+
+    def ref_fn(x, qg, qb, kg, kb):
+        P = {"qkv.weight": None, "q_norm.weight": qg, "q_norm.bias": qb, "k_norm.weight": kg, "k_norm.bias": kb,
+             "proj.weight": torch.eye(C), "proj.bias": torch.zeros(C)}
+        return O.patch_attention(x, P, "", H, ser["order"][0], ser["inverse"][0], plan, 128, qk_norm, None, None)
+
+    def cuda_fn(x, qg, qb, kg, kb):
+        return ops.PatchAttnFn.apply(x, qg if qk_norm else None, qb if qk_norm else None, kg if qk_norm else None, kb if qk_norm else None,
+                                     None, stg.plans[0], H, qk_norm, ops.NO_DROP, stg.grid, 15)
+
+    yr, gr = _grad_of(ref_fn, [qkv.float()] + norm, go.float())
+    yc, gc = _grad_of(cuda_fn, [qkv.to(DEV)] + [t.to(DEV) for t in norm], go.to(DEV))
+    torch.cuda.synchronize()
+    assert yc.dtype == torch.bfloat16 and torch.isfinite(yc.float()).all()
+    assert rel(yc.float(), yr) < 1e-2, rel(yc.float(), yr)
+    assert rel(gc[0].float(), gr[0]) < 2e-2, rel(gc[0].float(), gr[0])
+    if qk_norm:
+        for i in (0, 1, 2):       # k_norm.bias has a mathematically zero gradient (softmax shift invariance): rounding noise on both sides
+            assert rel(gc[1 + i].float(), gr[1 + i]) < 3e-2, (i, rel(gc[1 + i].float(), gr[1 + i]))
+
+
+@pytest.mark.parametrize("H,D,toks", [(2, 32, [12, 30, 8, 1]), (4, 32, [12, 30, 8, 32]), (8, 24, [20, 9, 31, 5]), (2, 16, [33, 77, 128, 2]),
+                                      (2, 64, [40, 64, 7, 19])])
+@pytest.mark.parametrize("qk_norm", [True, False])
+def test_cross_attention_bf16_vs_fp32_oracle(H, D, toks, qk_norm):
+    """the tensor-core cross attention against the fp32 ORACLE (lotus_oracle.py::cross_attention) on the same
+    bf16-rounded q / kv.  Tolerances as for the patch attention."""
+    ops, tk = pkg("ops"), pkg("tokenizer")
+    sizes = [300, 90, 1, 417]
+    C = H * D
+    g = torch.Generator().manual_seed(H * 977 + D)
+    geo = tk.CrossGeo(torch.tensor([0] + list(np.cumsum(sizes)), dtype=torch.int32, device=DEV),
+                      torch.tensor([0] + list(np.cumsum(toks)), dtype=torch.int32, device=DEV), len(sizes), max(sizes), max(toks))
+    q0 = bf(torch.randn(sum(sizes), C, generator=g) * 1.5)
+    kv0 = bf(torch.randn(sum(toks), 2 * C, generator=g) * 1.5)
+    norm = [1 + 0.1 * torch.randn(D, generator=g), 0.1 * torch.randn(D, generator=g),
+            1 + 0.1 * torch.randn(D, generator=g), 0.1 * torch.randn(D, generator=g)]
+    go = bf(torch.randn(sum(sizes), C, generator=g))
+
+    def ref_fn(q, kv, qg, qb, kg, kb):
+        P = {"q.weight": None, "kv.weight": None,
+             "q_norm.weight": qg, "q_norm.bias": qb, "k_norm.weight": kg, "k_norm.bias": kb, "proj.weight": torch.eye(C), "proj.bias": torch.zeros(C)}
+        return O.cross_attention(q, kv, P, "", H, torch.tensor(np.cumsum(sizes)), torch.tensor(np.cumsum(toks)), qk_norm)
+
+    def cuda_fn(q, kv, qg, qb, kg, kb):
+        return ops.CrossAttnFn.apply(q, kv, qg, qb, kg, kb, geo, H, qk_norm, ops.NO_DROP)
+
+    yr, gr = _grad_of(ref_fn, [q0.float(), kv0.float()] + norm, go.float())
+    yc, gc = _grad_of(cuda_fn, [q0.to(DEV), kv0.to(DEV)] + [t.to(DEV) for t in norm], go.to(DEV))
+    torch.cuda.synchronize()
+    assert yc.dtype == torch.bfloat16 and torch.isfinite(yc.float()).all()
+    assert rel(yc.float(), yr) < 1e-2, rel(yc.float(), yr)
+    assert rel(gc[0].float(), gr[0]) < 2e-2, rel(gc[0].float(), gr[0])
+    assert rel(gc[1].float(), gr[1]) < 2e-2, rel(gc[1].float(), gr[1])
+    if qk_norm:
+        for i in (0, 1, 2):
+            assert rel(gc[2 + i].float(), gr[2 + i]) < 3e-2, (i, rel(gc[2 + i].float(), gr[2 + i]))

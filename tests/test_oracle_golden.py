@@ -67,9 +67,10 @@ def _integer_checks(inter, res_inter):
     pass
 
 
-@pytest.mark.parametrize("which", ["small", "prod"])
-def test_policy_forward_backward_matches_reference(which, gold_small, gold_prod):
-    g = gold_small if which == "small" else gold_prod
+@pytest.mark.parametrize("which", ["small", "prod", "big"])
+def test_policy_forward_backward_matches_reference(which, gold_small, gold_prod, request):
+    # "big": two keysteps of 4096 / 3000 points at production width (BASELINE config-2 per-keystep sizes)
+    g = gold_small if which == "small" else (gold_prod if which == "prod" else request.getfixturevalue("gold_big"))
     cfgm, testing = pkg("config"), pkg("testing")
     cfg = cfgm.ConfigNode(g["config"])
     # weights: re-derived exactly as the generator did (same seeded procedure over the same names/shapes)
@@ -243,3 +244,28 @@ def test_soft_label_restatement_matches_reference_all_branches():
     # the degenerate case really exercises the fallback: axis 1 is a one-hot
     deg = cases[3]["dist"].numpy()
     assert (deg[1] > 0).sum() == 1 and deg[1].max() == 1.0
+
+
+def test_adamw_restatement_matches_reference_optimizer():
+    """`O.adamw_step` (the checker of the fused CUDA optimizer and of the gloo data-parallel test) against the reference's own
+    AdamW + build_optimizer + clip_grad_norm_ (fixture: oracle/make_golden_optim.py, minted from train/optim/adamw.py:53-112,
+    train/optim/misc.py:13-55, train_simple_policy.py:237-243).  Four steps, changing lr, gradients below / above the clip norm."""
+    from conftest import load_golden
+    g = load_golden("adamw.pt")
+    names = [n for n, _ in g["shapes"]]
+    # the reference's grouping: names containing 'bias' escape weight decay
+    nodecay = set(g["groups"][1])
+    assert nodecay == {i for i, n in enumerate(names) if "bias" in n} and g["group_wd"] == [0.05, 0.0]
+    wds = [0.0 if i in nodecay else g["weight_decay"] for i in range(len(names))]
+    params = [p.clone() for p in g["init"]]
+    m = [torch.zeros_like(p) for p in params]
+    v = [torch.zeros_like(p) for p in params]
+    for step in range(1, 5):
+        norm = O.adamw_step(params, [x.clone() for x in g["grads"][step - 1]], m, v, step, g["lr"][step - 1], wds, betas=g["betas"], eps=1e-6,
+                            max_grad_norm=g["max_grad_norm"])
+        assert abs(norm - g["norm"][step - 1]) <= 1e-6 * g["norm"][step - 1]
+        for i, n in enumerate(names):
+            # fp32 arithmetic on both sides; the clip coefficient is formed in a different order -> a few ulp
+            assert rel_err(params[i], g["params"][step - 1][i]) < 2e-6, (step, n)
+            assert rel_err(m[i], g["exp_avg"][step - 1][i]) < 2e-6, (step, n)
+            assert rel_err(v[i], g["exp_avg_sq"][step - 1][i]) < 2e-6, (step, n)

@@ -68,3 +68,11 @@ def test_synthetic_batch_schema():
     g = torch.div(c - c.min(0)[0], 0.01, rounding_mode="trunc").int()
     key = torch.cat([torch.repeat_interleave(torch.arange(3), torch.tensor(n))[:, None], g], 1)
     assert torch.unique(key, dim=0).shape[0] == key.shape[0]
+
+
+def test_native_executor_refuses_stochastic_depth():
+    """the C++ executor has no DropPath; the bare yaml default (drop_path 0.1 -> per-block rates linspace(0, .1, 5))
+    must not be routed to it silently.  The shipped job scripts set drop_path 0.0 and stay supported."""
+    cfgm, policy, native = pkg("config"), pkg("policy"), pkg("native")
+    assert native.supported(policy.build_parameter_shell(cfgm.production_model_config()))
+    assert not native.supported(policy.build_parameter_shell(cfgm.production_model_config(drop_path=0.1)))
