@@ -108,6 +108,7 @@ KERNEL_OF = {
     "lotus_subm_conv_fwd_bf16": "tc::k_gemm_tc", "lotus_subm_conv_dgrad_bf16": "tc::k_gemm_tc",
     "lotus_subm_conv_wgrad_pairs_bf16": "tc::k_gemm_tc", "lotus_subm_conv_wgrad_bf16": "tc::k_gemm_tc",
     "lotus_patch_attn_fwd_bf16": "tca::k_patch_attn_fwd_tc", "lotus_patch_attn_bwd_bf16": "tca::k_patch_attn_bwd_tc",
+    "lotus_patch_attn_fused_fwd_bf16": "paf::k_pattn_fwd", "lotus_patch_attn_fused_bwd_bf16": "paf::k_pattn_bwd",
 }
 
 
@@ -134,6 +135,16 @@ def algorithmic_work(name, a, ctx):
         pairs = ctx["conv_pairs"].get((n, k3), n * k3)            # actual (voxel, neighbour) pairs, not n * k^3
         wbytes = (4.0 if "wgrad" in name else es) * k3 * cin * cout
         return 2.0 * pairs * cin * cout, float(es) * (n * cin + n * cout) + 4.0 * pairs + wbytes
+    if name.startswith("lotus_patch_attn_fused"):
+        # the fused kernels read the RAW q / k / v rows once (per-head LayerNorm in registers) and write o (fwd) or bf16 dq / dk / dv
+        # (bwd: + o and do read); index tables and lse as before
+        o = 1 if "bwd" in name else 0
+        P, K, H, D = int(a[13]), int(a[14 + o]), int(a[15 + o]), int(a[16 + o])
+        npad = ctx["npad_of_patches"].get(P, P * K)
+        C = H * D
+        if "fwd" in name:
+            return 4.0 * npad * K * C, 2.0 * 4 * npad * C + 8.0 * npad + 4.0 * npad * H
+        return 10.0 * npad * K * C, 2.0 * 8 * npad * C + 8.0 * npad + 4.0 * npad * H
     if name.startswith("lotus_patch_attn"):
         P, K, H, D = int(a[9]), int(a[10]), int(a[11]), int(a[12])
         npad = ctx["npad_of_patches"].get(P, P * K)

@@ -18,20 +18,7 @@ int lotus_cross_attn_bwd_mma(const void* q, int64_t ldq, const void* k, const vo
                              const int32_t* tok_off, int B, int max_points, int max_tokens, int H, int Dh, float scale, const void* out,
                              const void* dout, int64_t ldo, const float* lse, float* dq, int64_t lddq, float* dk, float* dv,
                              int64_t lddk, int64_t lddv, float drop_p, uint64_t seed, uint32_t layer_id, void* stream_);
-bool lotus_patch_attn_tc_ok(const void* q, const void* k, const void* v, int64_t ldq, int64_t ldk, int64_t ldv, const void* out,
-                            int64_t ldo, int max_len, int Dh, const float* rpe_table);
-int lotus_patch_attn_fwd_tc(const void* q, const void* k, const void* v, int64_t ldq, int64_t ldk, int64_t ldv,
-                            const int32_t* gather_idx, const int32_t* slot_of_point, const int32_t* cu_seqlens, int n_patches, int H,
-                            int Dh, float scale, void* out, int64_t ldo, float* lse, float drop_p, uint64_t seed, uint32_t layer_id,
-                            void* stream_);
 
-bool lotus_patch_attn_bwd_tc_ok(const float* dq, const float* dk, const float* dv, int64_t lddq, int64_t lddk, int64_t lddv, int Dh,
-                                const float* drpe_table);
-int lotus_patch_attn_bwd_tc(const void* q, const void* k, const void* v, int64_t ldq, int64_t ldk, int64_t ldv,
-                            const int32_t* gather_idx, const int32_t* slot_of_point, const int32_t* cu_seqlens, int n_patches, int H,
-                            int Dh, float scale, const void* out, const void* dout, int64_t ldo, const float* lse, float* dq, float* dk,
-                            float* dv, int64_t lddq, int64_t lddk, int64_t lddv, float drop_p, uint64_t seed, uint32_t layer_id,
-                            void* stream_);
 
 struct RpeArgs {
   const float* table;   // [3*(2*bnd+1), H] or null
@@ -91,7 +78,7 @@ __global__ void __launch_bounds__(128) k_patch_attn_fwd(
       l = l * corr + pj;
       float pv = pj;
       if (drop_p > 0.f)
-        pv = dropout_keep(seed, layer_id * 0x9E37u + (uint32_t)(p * H + h), (uint32_t)(i * len + j), drop_p) ? pj * keep_scale : 0.f;
+        pv = attn_drop_keep(attn_drop_rowhash(seed, layer_id * 0x9E37u + (uint32_t)(p * H + h), (uint32_t)i), (uint32_t)j, attn_drop_thr(drop_p)) ? pj * keep_scale : 0.f;
 #pragma unroll
       for (int d = 0; d < DH; ++d) o[d] = o[d] * corr + pv * Vs[j * DH + d];
       m = mn;
@@ -163,7 +150,7 @@ __global__ void __launch_bounds__(128) k_patch_attn_bwd(
       float pij = __expf(s - Ls[i]);
       float pd = pij;
       if (drop_p > 0.f) {
-        bool keep = dropout_keep(seed, sid, (uint32_t)(i * len + j), drop_p);
+        bool keep = attn_drop_keep(attn_drop_rowhash(seed, sid, (uint32_t)i), (uint32_t)j, attn_drop_thr(drop_p));
         pd = keep ? pij * keep_scale : 0.f;
         dp = keep ? dp * keep_scale : 0.f;
       }
@@ -190,7 +177,7 @@ __global__ void __launch_bounds__(128) k_patch_attn_bwd(
       for (int d = 0; d < DH; ++d) { s = fmaf(qr[d], Ks[j * DH + d], s); dp = fmaf(dor[d], Vs[j * DH + d], dp); }
       if (rpe.table) s += rpe_bias_ij(rpe, H, h, Gs[i], Gs[j]);
       float pij = __expf(s - li);
-      if (drop_p > 0.f) dp = dropout_keep(seed, sid, (uint32_t)(i * len + j), drop_p) ? dp * keep_scale : 0.f;
+      if (drop_p > 0.f) dp = attn_drop_keep(attn_drop_rowhash(seed, sid, (uint32_t)i), (uint32_t)j, attn_drop_thr(drop_p)) ? dp * keep_scale : 0.f;
       float ds = pij * (dp - di);
 #pragma unroll
       for (int d = 0; d < DH; ++d) aq[d] = fmaf(ds, Ks[j * DH + d], aq[d]);
@@ -257,9 +244,7 @@ LOTUS_API int lotus_patch_attn_fwd_bf16(const void* q, const void* k, const void
                                         int n_patches, int max_len, int H, int Dh, float scale, const float* rpe_table,
                                         const int32_t* grid, int pos_bnd, void* out, int64_t ldo, float* lse, float drop_p,
                                         uint64_t seed, uint32_t layer_id, void* stream_) {
-  if (lotus_patch_attn_tc_ok(q, k, v, ldq, ldk, ldv, out, ldo, max_len, Dh, rpe_table))      // tcgen05 path (attention_tc.cu)
-    return lotus_patch_attn_fwd_tc(q, k, v, ldq, ldk, ldv, gather_idx, slot_of_point, cu_seqlens, n_patches, H, Dh, scale, out, ldo,
-                                   lse, drop_p, seed, layer_id, stream_);
+  // (bf16 activations through the SIMT kernel: A/B reference of the fused tcgen05 kernels in attention_fused.cu, and shapes those refuse)
   return patch_fwd_impl<bf16_t>(q, k, v, ldq, ldk, ldv, gather_idx, slot_of_point, cu_seqlens, n_patches, max_len, H, Dh, scale,
                                 rpe_table, grid, pos_bnd, out, ldo, lse, drop_p, seed, layer_id, stream_);
 }
@@ -306,10 +291,6 @@ LOTUS_API int lotus_patch_attn_bwd_bf16(const void* q, const void* k, const void
                                         int64_t ldo, const float* lse, float* dq, float* dk, float* dv, int64_t lddq,
                                         int64_t lddk, int64_t lddv, float drop_p, uint64_t seed, uint32_t layer_id,
                                         void* stream_) {
-  if (lotus_patch_attn_tc_ok(q, k, v, ldq, ldk, ldv, out, ldo, max_len, Dh, rpe_table) &&
-      lotus_patch_attn_bwd_tc_ok(dq, dk, dv, lddq, lddk, lddv, Dh, drpe_table) && ((uintptr_t)dout & 15) == 0)
-    return lotus_patch_attn_bwd_tc(q, k, v, ldq, ldk, ldv, gather_idx, slot_of_point, cu_seqlens, n_patches, H, Dh, scale, out, dout,
-                                   ldo, lse, dq, dk, dv, lddq, lddk, lddv, drop_p, seed, layer_id, stream_);
   return patch_bwd_impl<bf16_t>(q, k, v, ldq, ldk, ldv, gather_idx, slot_of_point, cu_seqlens, n_patches, max_len, H, Dh, scale,
                                 rpe_table, grid, pos_bnd, drpe_table, out, dout, ldo, lse, dq, dk, dv, lddq, lddk, lddv, drop_p,
                                 seed, layer_id, stream_);

@@ -117,7 +117,20 @@ __device__ __forceinline__ uint32_t drop_hash4(uint64_t seed, uint32_t sid, uint
 __device__ __forceinline__ bool drop_keep_e(uint64_t seed, uint32_t sid, uint64_t idx, uint32_t thr) {
   return ((drop_hash4(seed, sid, idx) >> (8 * (uint32_t)(idx & 3))) & 0xFFu) >= thr;
 }
-// attention-probability dropout keeps the per-element hash
+// patch-attention probability dropout: ONE full hash per (patch, head, query) and a cheap multiplicative mix per key, so the
+// element loops of the attention kernels (128 x 128 probabilities per patch and head, forward and backward) spend ~6 integer
+// instructions per mask bit instead of ~14.  keep(q, key) is the same function in the SIMT and the tensor-core kernels.
+__device__ __forceinline__ uint32_t attn_drop_rowhash(uint64_t seed, uint32_t sid, uint32_t q) {
+  return lotus_hash3((uint32_t)seed ^ sid * 0x27D4EB2Fu, (uint32_t)(seed >> 32), q);
+}
+__device__ __forceinline__ uint32_t attn_drop_thr(float p) { return (uint32_t)(p * 16777216.f); }
+__device__ __forceinline__ bool attn_drop_keep(uint32_t hq, uint32_t key, uint32_t thr24) {
+  uint32_t y = (hq + key * 0x9E3779B1u) * 0x85EBCA77u;
+  y ^= y >> 15;
+  y *= 0xC2B2AE3Du;
+  return (y >> 8) >= thr24;
+}
+// cross-attention probability dropout keeps the per-element hash
 __device__ __forceinline__ bool dropout_keep(uint64_t seed, uint32_t idx_hi, uint32_t idx_lo, float p) {
   uint32_t h = lotus_hash3((uint32_t)seed ^ idx_hi * 0x27D4EB2Fu, (uint32_t)(seed >> 32), idx_lo);
   return (h >> 8) * (1.0f / 16777216.0f) >= p;

@@ -58,7 +58,7 @@ static long long g_launcher_calls = 0;   // launcher invocations of the last non
 // every kernel-launching C-ABI call of the step goes through CALL: in profile mode (lotus_policy_step_profile) each call is
 // bracketed by CUDA events on the launching stream and its scalar / pointer arguments are recorded, so bench.py gets per-call
 // device times of the NATIVE path (no Python between launches) together with the shapes the byte / FLOP model needs
-struct ProfRec { const char* name; cudaEvent_t e0, e1; int nargs; int64_t a[40]; };
+struct ProfRec { const char* name; cudaEvent_t e0, e1; int nargs; int64_t a[48]; };
 static bool g_prof_on = false;
 static std::vector<ProfRec> g_prof;
 static std::vector<cudaEvent_t> g_prof_events;
@@ -75,8 +75,8 @@ template <typename T> static inline int64_t prof_arg(T v) {
 }
 template <typename F, typename... A> static int prof_call(cudaStream_t st, const char* name, F fn, A... args) {
   if (!g_prof_on) return fn(args...);
-  ProfRec r; r.name = name; r.nargs = (int)sizeof...(A);
-  int i = 0; ((r.a[i < 40 ? i : 39] = prof_arg(args), ++i), ...);
+  ProfRec r; r.name = name; r.nargs = (int)sizeof...(A) < 48 ? (int)sizeof...(A) : 48;
+  int i = 0; ((r.a[i < 48 ? i : 47] = prof_arg(args), ++i), ...);
   r.e0 = prof_event(); r.e1 = prof_event();
   cudaEventRecord(r.e0, st);
   int rc = fn(args...);
@@ -242,7 +242,7 @@ static void mlp_bwd(Ctx& c, void* D, int n, const Norm& n2, const Lin& fc1, cons
 // ------------------------------------------------------------------------------------------------ Block
 struct BlockSave {
   const void* conv_in; void *x0, *c0, *c1, *x1, *h1, *qkv, *qh, *kh, *o; float *cpe_mean, *cpe_rstd, *n1_mean, *n1_rstd, *qk_stats, *lse;
-  uint32_t d_attn, d_proj; MlpSave mlp; int n; bool own_conv_in;
+  uint32_t d_attn, d_proj; MlpSave mlp; int n; bool own_conv_in, fused;
 };
 static void* block_fwd(Ctx& c, const BlockP& b, const StageInfo& sg, void* x0, const void* conv_in, BlockSave& sv) {
   int n = sg.n, C = b.C, H = b.H, D = C / H;
@@ -261,21 +261,29 @@ static void* block_fwd(Ctx& c, const BlockP& b, const StageInfo& sg, void* x0, c
   sv.qkv = act(c, n, 3 * C);
   linear_fwd(c, sv.h1, n, b.qkv, nullptr, sv.qkv, 0.f, 0);
   const void *qp = sv.qkv, *kp = (char*)sv.qkv + (size_t)C * c.es;
+  const void* vp = (char*)sv.qkv + (size_t)2 * C * c.es;
   int64_t ldq = 3 * C;
-  if (c.qk_norm) {
-    sv.qh = act(c, n, C); sv.kh = act(c, n, C);
-    sv.qk_stats = f32(c, (int64_t)4 * n * H);
-    head_ln_fwd(c, sv.qkv, 3 * C, sv.qh, b.qn, sv.qk_stats, sv.qk_stats + (int64_t)n * H, n, H);
-    head_ln_fwd(c, (char*)sv.qkv + (size_t)C * c.es, 3 * C, sv.kh, b.kn, sv.qk_stats + (int64_t)2 * n * H, sv.qk_stats + (int64_t)3 * n * H, n, H);
-    qp = sv.qh; kp = sv.kh; ldq = C;
-  }
+  float scale = 1.0f / sqrtf((float)D);
   sv.o = act(c, n, C);
   sv.lse = f32(c, (int64_t)sg.n_pad * H);
   sv.d_attn = drop_id(c, c.attn_drop);
-  const void* vp = (char*)sv.qkv + (size_t)2 * C * c.es;
-  float scale = 1.0f / sqrtf((float)D);
-  if (c.bf) CALL(lotus_patch_attn_fwd_bf16, qp, kp, vp, ldq, ldq, 3 * C, sg.gather_idx, sg.slot_of_point, sg.cu_seqlens, sg.n_patches, c.K, H, D, scale, nullptr, nullptr, 0, sv.o, C, sv.lse, drop_p(c, c.attn_drop, sv.d_attn), c.seed, sv.d_attn, c.stv);
-  else CALL(lotus_patch_attn_fwd_f32, (const float*)qp, (const float*)kp, (const float*)vp, ldq, ldq, 3 * C, sg.gather_idx, sg.slot_of_point, sg.cu_seqlens, sg.n_patches, c.K, H, D, scale, nullptr, nullptr, 0, (float*)sv.o, C, sv.lse, drop_p(c, c.attn_drop, sv.d_attn), c.seed, sv.d_attn, c.stv);
+  sv.fused = c.bf && c.K <= 128 && D % 8 == 0 && D <= 64;
+  if (sv.fused) {
+    // gather + per-head q/k LayerNorm + attention + scatter in one tcgen05 kernel (attention_fused.cu)
+    CALL(lotus_patch_attn_fused_fwd_bf16, qp, kp, vp, ldq, ldq, ldq, c.qk_norm ? Pf(c, b.qn.w) : nullptr, c.qk_norm ? Pf(c, b.qn.b) : nullptr,
+         c.qk_norm ? Pf(c, b.kn.w) : nullptr, c.qk_norm ? Pf(c, b.kn.b) : nullptr, sg.gather_idx, sg.slot_of_point, sg.cu_seqlens, sg.n_patches,
+         c.K, H, D, scale, nullptr, nullptr, 0, sv.o, C, sv.lse, drop_p(c, c.attn_drop, sv.d_attn), c.seed, sv.d_attn, c.stv);
+  } else {
+    if (c.qk_norm) {
+      sv.qh = act(c, n, C); sv.kh = act(c, n, C);
+      sv.qk_stats = f32(c, (int64_t)4 * n * H);
+      head_ln_fwd(c, sv.qkv, 3 * C, sv.qh, b.qn, sv.qk_stats, sv.qk_stats + (int64_t)n * H, n, H);
+      head_ln_fwd(c, (char*)sv.qkv + (size_t)C * c.es, 3 * C, sv.kh, b.kn, sv.qk_stats + (int64_t)2 * n * H, sv.qk_stats + (int64_t)3 * n * H, n, H);
+      qp = sv.qh; kp = sv.kh; ldq = C;
+    }
+    if (c.bf) CALL(lotus_patch_attn_fwd_bf16, qp, kp, vp, ldq, ldq, 3 * C, sg.gather_idx, sg.slot_of_point, sg.cu_seqlens, sg.n_patches, c.K, H, D, scale, nullptr, nullptr, 0, sv.o, C, sv.lse, drop_p(c, c.attn_drop, sv.d_attn), c.seed, sv.d_attn, c.stv);
+    else CALL(lotus_patch_attn_fwd_f32, (const float*)qp, (const float*)kp, (const float*)vp, ldq, ldq, 3 * C, sg.gather_idx, sg.slot_of_point, sg.cu_seqlens, sg.n_patches, c.K, H, D, scale, nullptr, nullptr, 0, (float*)sv.o, C, sv.lse, drop_p(c, c.attn_drop, sv.d_attn), c.seed, sv.d_attn, c.stv);
+  }
   void* x2 = act(c, n, C);
   sv.d_proj = drop_id(c, c.proj_drop);
   linear_fwd(c, sv.o, n, b.proj, sv.x1, x2, c.proj_drop, sv.d_proj);
@@ -296,7 +304,15 @@ static void block_bwd(Ctx& c, const BlockP& b, const StageInfo& sg, void* D, con
   void* dqkv = act(c, n, 3 * C);
   float scale = 1.0f / sqrtf((float)Dh);
   const void* vp = (char*)sv.qkv + (size_t)2 * C * c.es;
-  if (c.bf || c.qk_norm) {
+  if (sv.fused) {
+    // every row of dqkv is written by the kernel (bf16, raw-space gradients: the per-head LayerNorm backward runs in its epilogue)
+    void* alias = c.ar.alloc((size_t)sg.n_pad * 2 * C * 2);
+    CALL(lotus_patch_attn_fused_bwd_bf16, sv.qkv, (char*)sv.qkv + (size_t)C * 2, vp, 3 * C, 3 * C, 3 * C, c.qk_norm ? Pf(c, b.qn.w) : nullptr,
+         c.qk_norm ? Pf(c, b.qn.b) : nullptr, c.qk_norm ? Pf(c, b.kn.w) : nullptr, c.qk_norm ? Pf(c, b.kn.b) : nullptr, sg.gather_idx, sg.slot_of_point,
+         sg.cu_seqlens, sg.n_patches, sg.n_pad, c.K, H, Dh, scale, nullptr, nullptr, 0, nullptr, sv.o, dout, C, sv.lse, dqkv, (char*)dqkv + (size_t)C * 2,
+         (char*)dqkv + (size_t)2 * C * 2, 3 * C, 3 * C, 3 * C, Gf(c, b.qn.w), Gf(c, b.qn.b), Gf(c, b.kn.w), Gf(c, b.kn.b), alias,
+         drop_p(c, c.attn_drop, sv.d_attn), c.seed, sv.d_attn, c.stv);
+  } else if (c.bf || c.qk_norm) {
     float* dqh = f32(c, (int64_t)n * C); float* dkh = f32(c, (int64_t)n * C);
     float* dvh = c.bf ? f32(c, (int64_t)n * C) : (float*)dqkv + 2 * C;
     int64_t lddv = c.bf ? C : 3 * C;
@@ -773,6 +789,6 @@ LOTUS_API int lotus_policy_step_profile_read(int64_t index, char* name_out, floa
   float ms = 0.f;
   LOTUS_CUDA_CALL(cudaEventElapsedTime(&ms, r.e0, r.e1));
   *ms_out = ms; *nargs_out = r.nargs;
-  for (int i = 0; i < r.nargs && i < 40; ++i) args_out[i] = r.a[i];
+  for (int i = 0; i < r.nargs && i < 48; ++i) args_out[i] = r.a[i];
   return 0;
 }

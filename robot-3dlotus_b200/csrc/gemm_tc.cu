@@ -98,7 +98,7 @@ k_gemm_tc(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUt
   extern __shared__ __align__(1024) uint8_t smem_raw[];
   constexpr uint32_t A_BYTES = BM * BK * 2, B_BYTES = BN * BK * 2;
   const int STAGES = p.stages;
-  uint8_t* smem = (uint8_t*)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
+  uint8_t* smem = smem_raw + ((1024u - (tc::smem_u32(smem_raw) & 1023u)) & 1023u);   // 1024-byte aligned, still a SHARED-space pointer (LDS / STS, not generic LD / ST)
   uint8_t* sA = smem;
   uint8_t* sB = smem + STAGES * A_BYTES;
   uint64_t* full = (uint64_t*)(sB + STAGES * B_BYTES);

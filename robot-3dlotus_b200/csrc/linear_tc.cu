@@ -57,7 +57,7 @@ k_lin(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtenso
   constexpr int B_BYTES = BN * BK * 2;
   const int STAGES = p.stages;
   const int tile_bytes = BM * BN * (p.out_fp32 ? 4 : 2);
-  uint8_t* smem = (uint8_t*)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
+  uint8_t* smem = smem_raw + ((1024u - (tc::smem_u32(smem_raw) & 1023u)) & 1023u);   // 1024-byte aligned, still a SHARED-space pointer (LDS / STS, not generic LD / ST)
   uint8_t* sA = smem;
   uint8_t* sB = sA + STAGES * A_BYTES;
   const int out_bufs = p.out_bufs;                             // epilogue staging tiles (TMA store sources)

@@ -171,7 +171,7 @@ def profile_step(run_step):
         n = int(L.cdll.lotus_policy_step_profile_count())
         name = ctypes.create_string_buffer(64)
         ms = ctypes.c_float(0)
-        args = (ctypes.c_int64 * 40)()
+        args = (ctypes.c_int64 * 48)()
         na = ctypes.c_int(0)
         out = []
         for i in range(n):

@@ -439,6 +439,14 @@ def subm_conv(x, w, b, nbr, nbr_stride, rule=None):
 # ------------------------------------------------------------------------------------------ attention
 
 
+def _fused_attn_ok(qkv, plan, D):
+    """bf16 activations, patches of at most 128 tokens, head dim a multiple of 8 up to 64 -> the fused tcgen05 kernels
+    (LOTUS_ATTN_SIMT=1 keeps the SIMT kernels: A/B tests)"""
+    import os
+    return (qkv.dtype == torch.bfloat16 and plan.max_len <= 128 and D % 8 == 0 and 8 <= D <= 64 and qkv.shape[1] % 8 == 0
+            and os.environ.get("LOTUS_ATTN_SIMT") is None)
+
+
 class PatchAttnFn(torch.autograd.Function):
     """qkv (N,3C) raw projections -> per-head LN on q,k -> attention inside each serialized patch -> (N,C) in
     point order (gather by order[pad] and scatter by unpad[inverse] fused).  fp32 or bf16 activations."""
@@ -453,6 +461,22 @@ class PatchAttnFn(torch.autograd.Function):
         D = C // H
         dev = qkv.device
         st = _st()
+        fused = _fused_attn_ok(qkv, plan, D)
+        if fused:
+            # bf16: gather + per-head q/k LayerNorm + QK^T + (RPE) softmax + PV + scatter in ONE tcgen05 kernel (attention_fused.cu)
+            out = torch.empty((N, C), device=dev, dtype=qkv.dtype)
+            lse = torch.empty((plan.n_pad * H,), device=dev, dtype=torch.float32)
+            L.lotus_patch_attn_fused_fwd_bf16(
+                _p(qkv), _po(qkv, C * es), _po(qkv, 2 * C * es), C3, C3, C3, _p(qg) if qk_norm else None, _p(qb) if qk_norm else None,
+                _p(kg) if qk_norm else None, _p(kb) if qk_norm else None, _p(plan.gather_idx), _p(plan.slot_of_point), _p(plan.cu_seqlens),
+                plan.n_patches, plan.max_len, H, D, float(D) ** -0.5, _p(rpe_table), _p(grid) if rpe_table is not None else None, pos_bnd,
+                _p(out), C, _p(lse), attn_drop[0], attn_drop[1], attn_drop[2], st)
+            ctx.save_for_backward(qkv, qg, kg, None, None, None, out, lse, rpe_table, grid if rpe_table is not None else None)
+            ctx.plan, ctx.H, ctx.qk_norm, ctx.attn_drop, ctx.pos_bnd = plan, H, qk_norm, attn_drop, pos_bnd
+            ctx.nb = (qb, kb)
+            ctx.fused = True
+            return out
+        ctx.fused = False
         ln_fwd = getattr(L, "lotus_layernorm_fwd_" + sfx)
         if qk_norm:
             qh = torch.empty((N, C), device=dev, dtype=qkv.dtype)
@@ -490,6 +514,22 @@ class PatchAttnFn(torch.autograd.Function):
         st = _st()
         f32 = dict(device=dev, dtype=torch.float32)
         drpe = torch.zeros_like(rpe_table) if rpe_table is not None else None
+        if ctx.fused:
+            dqkv = torch.empty_like(qkv)
+            alias = torch.empty((plan.n_pad, 2, C), device=dev, dtype=torch.bfloat16)
+            dqg = dqb = dkg = dkb = None
+            qgb = qbb = kgb = kbb = None
+            if ctx.qk_norm:
+                (qgb, dqg), (qbb, dqb) = _grad_buf(qg, True), _grad_buf(ctx.nb[0], True)
+                (kgb, dkg), (kbb, dkb) = _grad_buf(kg, True), _grad_buf(ctx.nb[1], True)
+            L.lotus_patch_attn_fused_bwd_bf16(
+                _p(qkv), _po(qkv, C * es), _po(qkv, 2 * C * es), C3, C3, C3, _p(qg) if ctx.qk_norm else None,
+                _p(ctx.nb[0]) if ctx.qk_norm else None, _p(kg) if ctx.qk_norm else None, _p(ctx.nb[1]) if ctx.qk_norm else None,
+                _p(plan.gather_idx), _p(plan.slot_of_point), _p(plan.cu_seqlens), plan.n_patches, plan.n_pad, plan.max_len, H, D,
+                float(D) ** -0.5, _p(rpe_table), _p(grid), ctx.pos_bnd, _p(drpe), _p(out), _p(dout), C, _p(lse), _p(dqkv),
+                _po(dqkv, C * es), _po(dqkv, 2 * C * es), C3, C3, C3, _p(qgb), _p(qbb), _p(kgb), _p(kbb), _p(alias),
+                ctx.attn_drop[0], ctx.attn_drop[1], ctx.attn_drop[2], st)
+            return dqkv, dqg, dqb, dkg, dkb, drpe, None, None, None, None, None, None
         # fp32 gradient accumulators of the attention core (alias slots add a second contribution -> atomics)
         if bf or ctx.qk_norm:
             dqh, dkh = torch.zeros((N, C), **f32), torch.zeros((N, C), **f32)

@@ -382,3 +382,72 @@ def test_cross_attention_bf16_vs_fp32_oracle(H, D, toks, qk_norm):
     if qk_norm:
         for i in (0, 1, 2):
             assert rel(gc[2 + i].float(), gr[2 + i]) < 3e-2, (i, rel(gc[2 + i].float(), gr[2 + i]))
+
+
+@pytest.mark.parametrize("H,D", [(2, 32), (1, 32), (4, 16), (3, 24)])
+def test_patch_attention_bf16_rpe_fused_vs_fp32_oracle(H, D):
+    """SURVEY §8a row 8 / north star ("per-point position bias ... fused in the epilogue" of the MMA kernel): the tensor-core kernel adds
+    the RPE bias (model.py:307-326, 400-408, 520-521) to the scaled logits before the softmax, and its backward accumulates the table
+    gradient.  Against the fp32 oracle on bf16-rounded q/k/v; full patches only (the reference's RPE branch reshapes to (-1, K, 3))."""
+    ops, tk = pkg("ops"), pkg("tokenizer")
+    from test_gpu_parity import lattice_clouds
+    sizes = [256, 128, 384]
+    coord, grid = lattice_clouds(sizes, 24, 8)
+    stg = tk.tokenize(coord.to(DEV), sizes, ["z"], [2], [128, 128], [[0], [0]], None)[0]
+    off = torch.tensor(np.cumsum(sizes))
+    ser = O.serialize(O.grid_coords(coord), O.offset2batch(off), ["z"])
+    plan = O.patch_plan(off, 128)
+    C, n = H * D, sum(sizes)
+    g = torch.Generator().manual_seed(H * 17 + D)
+    qkv = bf(torch.randn(n, 3 * C, generator=g) * 1.2)
+    norm = [1 + 0.1 * torch.randn(D, generator=g), 0.1 * torch.randn(D, generator=g),
+            1 + 0.1 * torch.randn(D, generator=g), 0.1 * torch.randn(D, generator=g)]
+    table = torch.randn(93, H, generator=g) * 0.5
+    go = bf(torch.randn(n, C, generator=g))
+
+    def ref_fn(x, qg, qb, kg, kb, tab):
+        P = {"qkv.weight": None, "q_norm.weight": qg, "q_norm.bias": qb, "k_norm.weight": kg, "k_norm.bias": kb,
+             "proj.weight": torch.eye(C), "proj.bias": torch.zeros(C)}
+        return O.patch_attention(x, P, "", H, ser["order"][0], ser["inverse"][0], plan, 128, True, tab, O.grid_coords(coord))
+
+    def cuda_fn(x, qg, qb, kg, kb, tab):
+        return ops.PatchAttnFn.apply(x, qg, qb, kg, kb, tab, stg.plans[0], H, True, ops.NO_DROP, stg.grid, 15)
+
+    yr, gr = _grad_of(ref_fn, [qkv.float()] + norm + [table], go.float())
+    yc, gc = _grad_of(cuda_fn, [qkv.to(DEV)] + [t.to(DEV) for t in norm] + [table.to(DEV)], go.to(DEV))
+    torch.cuda.synchronize()
+    assert rel(yc.float(), yr) < 1e-2, rel(yc.float(), yr)
+    assert rel(gc[0].float(), gr[0]) < 2e-2, rel(gc[0].float(), gr[0])
+    for i in (0, 1, 2):
+        assert rel(gc[1 + i].float(), gr[1 + i]) < 3e-2, (i, rel(gc[1 + i].float(), gr[1 + i]))
+    assert rel(gc[5].float(), gr[5]) < 3e-2, rel(gc[5].float(), gr[5])      # RPE table gradient
+
+
+@pytest.mark.parametrize("H,D,drop_p", [(2, 32, 0.1), (4, 32, 0.1)])
+def test_patch_attention_fused_dropout_mask_matches_simt(H, D, drop_p):
+    """attention dropout: the fused tensor-core kernels draw the same counter-based mask as the SIMT kernels (same seed / stream / element
+    index), forward and backward -- so fp32 validation mode and bf16 mode drop the same probabilities"""
+    import os
+    ops, tk = pkg("ops"), pkg("tokenizer")
+    from test_gpu_parity import lattice_clouds
+    sizes = [300, 90, 129, 1]
+    coord, grid = lattice_clouds(sizes, 24, 6)
+    stg = tk.tokenize(coord.to(DEV), sizes, ["hilbert"], [2], [128, 128], [[0], [0]], None)[0]
+    C = H * D
+    g = torch.Generator().manual_seed(H + D)
+    qkv = bf(torch.randn(sum(sizes), 3 * C, generator=g) * 1.5).to(DEV)
+    norm = [(1 + 0.1 * torch.randn(D, generator=g)).to(DEV), (0.1 * torch.randn(D, generator=g)).to(DEV),
+            (1 + 0.1 * torch.randn(D, generator=g)).to(DEV), (0.1 * torch.randn(D, generator=g)).to(DEV)]
+    go = bf(torch.randn(sum(sizes), C, generator=g)).to(DEV)
+    res = {}
+    for mode in ("simt", "fused"):
+        if mode == "simt":
+            os.environ["LOTUS_ATTN_SIMT"] = "1"
+        else:
+            os.environ.pop("LOTUS_ATTN_SIMT", None)
+        y, gr = _grad_of(lambda x, a, b, c, d: ops.PatchAttnFn.apply(x, a, b, c, d, None, stg.plans[0], H, True, (drop_p, 1234, 7), stg.grid, 15),
+                         [qkv] + norm, go)
+        torch.cuda.synchronize()
+        res[mode] = (y.float(), gr[0].float())
+    os.environ.pop("LOTUS_ATTN_SIMT", None)
+    assert rel(res["fused"][0], res["simt"][0]) < 2e-2 and rel(res["fused"][1], res["simt"][1]) < 3e-2

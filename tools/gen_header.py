@@ -37,6 +37,7 @@ DOC = {
     "lotus_policy_step_profile_count": "Number of launcher calls recorded by the last profiled lotus_policy_step.",
     "lotus_policy_step_profile_read": "One record of the last profiled step: C-ABI name, device milliseconds, the call's arguments (bench.py per-kernel table).",
     "lotus_policy_step_calls": "Kernel-launching calls issued by the last lotus_policy_step (bench accounting).",
+    "lotus_attn_debug_buffer": "Development aid: per-CTA clock64 stamps of the fused patch-attention phases.",
     "lotus_tc_debug_buffer": "Development aid: per-CTA %globaltimer stamps of the tensor-core GEMM phases.",
     "lotus_fps": "Replaces farthest_point_sample (explicit start index): train/datasets/common.py:108-129. Bit-exact indices.",
     "lotus_knn": "North-star kNN grouping (no reference function; SURVEY §8a row 13): brute force inside each cloud, ties -> lowest index.",
@@ -76,6 +77,10 @@ DOC = {
     "lotus_cast_transpose_bf16": "stages fp32 master weights for the tensor-core path: bf16 copy and [B][D][A] transpose (nn.Linear / SubMConv3d weights).",
     "lotus_cast_transpose_batch_bf16": "All weights of the model staged for the tensor-core kernels in one launch (host arrays of per-weight pointers and extents); same per-weight semantics as lotus_cast_transpose_bf16.",
     "lotus_dropout_bf16": "bf16-activation form of lotus_dropout_f32.",
+    "lotus_patch_attn_fused_fwd_bf16": "Replaces SerializedAttention.forward between the qkv and proj linears in ONE tcgen05 kernel: qkv[order] gather, per-head q/k LayerNorm "
+                                       "(model.py:393-394,532-535), QK^T, scale + RPE bias (model.py:307-326,400-408,520-521), softmax, attention dropout, PV, feat[inverse] scatter: model.py:497-551.",
+    "lotus_patch_attn_fused_bwd_bf16": "Backward of lotus_patch_attn_fused_fwd_bf16: bf16 gradients w.r.t. the raw q/k/v rows written straight into the packed dqkv tensor "
+                                       "(per-head LayerNorm backward in the epilogue), q/k-norm affine and RPE table gradients accumulated.",
     "lotus_patch_attn_fwd_bf16": "bf16-activation form of lotus_patch_attn_fwd_f32: model.py:543-551.",
     "lotus_patch_attn_bwd_bf16": "bf16-activation form of lotus_patch_attn_bwd_f32 (fp32 gradient accumulators).",
     "lotus_cross_attn_fwd_bf16": "bf16-activation form of lotus_cross_attn_fwd_f32: model_ca.py:56-67.",
