@@ -543,13 +543,17 @@ using namespace eng;
 // stage_sizes (int64, 5 per stage): n, n_pad, n_patches, max_cloud, stride ; stage_ptrs (12 per stage): nbr3, pairs_out, pairs_in,
 //   pair_cnt, gather_idx, slot_of_point, cu_seqlens, cloud_off, cluster, seg_ptr, member, nbr5
 // fl (float): attn_drop, proj_drop, head_drop, pos_weight, rot_weight, euler_resolution ; dbl: pos_bin_size
+// slice_events (host array of 3 cudaEvent_t, or null): recorded on `stream` during the backward when the parameter gradients of
+//   (0) head + decoder, (1) the deepest encoder stage, (2) the stage above it are complete (weight-gradient side stream joined), so the
+//   caller can start the gradient all-reduce of those slices while the rest of the backward runs (train/utils/distributed.py:196-212:
+//   DDP overlaps its bucketed all-reduces with the backward the same way)
 // Returns 0 and writes losses[4] (device), final actions (B,8 double, device); *arena_peak receives the bytes used
 // (with dry_run = 1 nothing is launched: call once to size the arena).
 LOTUS_API int lotus_policy_step(const int64_t* cfg, const int64_t* run, const int64_t* stage_sizes, void* const* stage_ptrs,
                                 void* const* params, void* const* grads, void* const* bn_stats, const float* feat,
                                 const float* txt, const int32_t* tok_off, const float* gt_actions, const float* pos_prob,
                                 const float* fl, double pos_bin_size, uint64_t seed, void* arena, int64_t arena_bytes,
-                                int64_t* arena_peak, float* losses, double* final_actions, void* stream_) {
+                                int64_t* arena_peak, float* losses, double* final_actions, void* const* slice_events, void* stream_) {
   Model m = build_model(cfg);
   Ctx c;
   if (run[9] == 0) g_launcher_calls = 0;
@@ -733,6 +737,12 @@ LOTUS_API int lotus_policy_step(const int64_t* cfg, const int64_t* run, const in
         linear_bwd(c, dlin_a, up_in[s], nc, m.unpool[s].proj, Dn, nullptr, c.bf);
         D = Dn;                                                       // gradient of the deeper stage's residual stream
       }
+      auto slice_done = [&](int k) {                                 // gradients of slice k are final on the main stream
+        if (slice_events == nullptr || slice_events[k] == nullptr || !live(c)) return;
+        join_side(c);
+        cudaEventRecord((cudaEvent_t)slice_events[k], c.st);
+      };
+      slice_done(0);                                                 // head + decoder
       // encoder, deep to shallow
       for (int s = S - 1; s >= 0; --s) {
         int n = sg[s].n, C = m.encC[s];
@@ -750,6 +760,8 @@ LOTUS_API int lotus_policy_step(const int64_t* cfg, const int64_t* run, const in
           linear_bwd(c, dproj, skip[s - 1], np, m.pool[s].proj, Gskip[s - 1], Gskip[s - 1], c.bf);
           D = Gskip[s - 1];
         }
+        if (s == S - 1) slice_done(1);
+        else if (s == S - 2) slice_done(2);
       }
       // stem: BN+GELU backward then the narrow conv weight gradient (the input features carry no gradient)
       {

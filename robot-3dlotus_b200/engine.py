@@ -213,7 +213,8 @@ class PolicyEngine:
             return pf[1], pf[2], pf[3]
         return None
 
-    def native_step(self, batch, compute_loss=True, with_grad=True, compute_final_action=False, dropout_seed=None, pending=None):
+    def native_step(self, batch, compute_loss=True, with_grad=True, compute_final_action=False, dropout_seed=None, pending=None,
+                    slice_events=None):
         """forward (+ loss + backward into the gradient sinks) through `lotus_policy_step`.  Returns (final, losses(4,)).
         `pending`: tokens of this batch already in flight (`prefetch`)."""
         from . import native
@@ -241,7 +242,7 @@ class PolicyEngine:
         self.seed_counter += 1
         seed = dropout_seed if dropout_seed is not None else int(torch.initial_seed()) * 1000003 + self.seed_counter
         return self._native.run(batch, stages, tok_dev, tok_off, m.training, self.precision == "bf16", compute_loss,
-                                not compute_final_action, with_grad and compute_loss, seed)
+                                not compute_final_action, with_grad and compute_loss, seed, slice_events=slice_events)
 
     # ------------------------------------------------------------------ context (prepare_ptv3_batch)
     def _pose_embedding(self, poses):

@@ -86,7 +86,7 @@ class NativeStep:
             self._ptr_key = key
         return self.c_params, (self.c_grads if with_grad else None), self.c_bn
 
-    def run(self, batch, stages, tok_off_dev, tok_off_host, train, bf16, compute_loss, use_gt_pos, with_grad, seed):
+    def run(self, batch, stages, tok_off_dev, tok_off_host, train, bf16, compute_loss, use_gt_pos, with_grad, seed, slice_events=None):
         L = load()
         m = self.m
         ac = m.config.action_config
@@ -138,7 +138,15 @@ class NativeStep:
                   VP(prob.data_ptr()) if prob is not None else None, fl, float(ac.pos_bin_size), int(seed) & (2 ** 63 - 1))
         # dry run sizes the arena (host-only, nothing is launched)
         run[9] = 1
-        L.lotus_policy_step(*common, None, 0, ctypes.byref(peak), VP(self.losses.data_ptr()), VP(final.data_ptr()), st)
+        ev = None
+        if slice_events is not None:
+            # torch.cuda.Event creates its CUDA event lazily: record once so the handle exists, then hand the raw cudaEvent_t over
+            for e in slice_events:
+                if not getattr(e, "_lotus_ready", False):
+                    e.record()
+                    e._lotus_ready = True
+            ev = (VP * len(slice_events))(*[e.cuda_event for e in slice_events])
+        L.lotus_policy_step(*common, None, 0, ctypes.byref(peak), VP(self.losses.data_ptr()), VP(final.data_ptr()), None, st)
         need = int(peak.value) + 4096
         if self.arena is None or self.arena.numel() < need or self.arena.device != dev:
             self.arena = None
@@ -151,7 +159,7 @@ class NativeStep:
             wkey = (self.arena.data_ptr(), PARAM_EPOCH[0], sum(p._version for p in self.params))
             run[10] = int(wkey == self._staged_key)
         L.lotus_policy_step(*common, VP(self.arena.data_ptr()), self.arena.numel(), ctypes.byref(peak), VP(self.losses.data_ptr()),
-                            VP(final.data_ptr()), st)
+                            VP(final.data_ptr()), ev, st)
         self._staged_key = wkey
         if train:
             torch._foreach_add_([bn.num_batches_tracked for bn in self.bns], 1)

@@ -41,6 +41,22 @@ def _drop_sinks(keys, grad_base):
             del ops.GRAD_SINK[k]
 
 
+def _completion_group(name, deepest):
+    """which slice of the backward completes this parameter's gradient (csrc/engine_native.cu records one event per slice):
+    0 head + decoder, 1 the deepest encoder stage (44 % of the bytes in production), 2 the stage above it, 3 everything that
+    finishes with the step (shallow encoder stages, stem, text projection)"""
+    if name.startswith("act_proj_head") or ".dec." in name:
+        return 0
+    if f".enc.enc{deepest}." in name:
+        return 1
+    if deepest >= 1 and f".enc.enc{deepest - 1}." in name:
+        return 2
+    return 3
+
+
+N_GRAD_SLICES = 4
+
+
 class FlatAdamW:
     """The reference optimizer (optim/misc.py:13-55 grouping: names containing 'bias' are not decayed; optim/adamw.py)
     over flat buffers.  `state_dict()` / `load_state_dict()` use the reference's per-parameter layout
@@ -65,13 +81,28 @@ class FlatAdamW:
         self.flat_grad = torch.zeros(total, device=dev, dtype=torch.float32)
         self.exp_avg = torch.zeros(total, device=dev, dtype=torch.float32)
         self.exp_avg_sq = torch.zeros(total, device=dev, dtype=torch.float32)
+        # The FLAT layout follows the order in which the backward completes gradients (head + decoder first, then encoder stage 4, 3,
+        # and the shallow stages / stem / text projection last), so the one logical gradient all-reduce of the path can be issued as a
+        # few contiguous slices behind events recorded inside the backward and overlap it (`all_reduce_slices`).  `self.params` keeps
+        # the reference's group order (decayed tensors, then biases) for the optimizer state dict; `self.offsets[i]` locates params[i].
+        import re
+        stage_ids = [int(m.group(1)) for n in self.names for m in [re.search(r"\.enc\.enc(\d+)\.", n)] if m]
+        deepest = max(stage_ids) if stage_ids else 0
+        grp = [_completion_group(n, deepest) for n in self.names]
+        layout = sorted(range(len(self.params)), key=lambda i: (grp[i], i))
+        self.offsets = [0] * len(self.params)
         ends, off = [], 0
+        starts = [None] * N_GRAD_SLICES
         # gradient sinks are process-global (keyed by parameter address): drop only what THIS model registered before
         # (re-building an optimizer for the same model), never another live model's entries
         for p in self.params:
             ops.GRAD_SINK.pop(p.data_ptr(), None)
         self._sink_keys = []
-        for p, n, slot in zip(self.params, sizes, slots):
+        for pos, i in enumerate(layout):
+            p, n, slot = self.params[i], sizes[i], slots[i]
+            if starts[grp[i]] is None:
+                starts[grp[i]] = off
+            self.offsets[i] = off
             view = self.flat_param[off: off + n].view_as(p)
             view.copy_(p.data)
             p.data = view                                   # parameters now alias the flat buffer
@@ -81,11 +112,18 @@ class FlatAdamW:
             self._sink_keys.append(p.data_ptr())
             off += slot
             ends.append(off)
+        self.layout = layout
+        nxt = total
+        for g in reversed(range(N_GRAD_SLICES)):            # an empty group starts where the next one does
+            if starts[g] is None:
+                starts[g] = nxt
+            nxt = starts[g]
+        self.slice_bounds = starts + [total]                # slice k = flat[slice_bounds[k] : slice_bounds[k + 1]], k in completion order
         # the entries die with this optimizer (its flat buffer is freed then; a later allocation may reuse the addresses)
         weakref.finalize(self, _drop_sinks, list(self._sink_keys), self.flat_grad.data_ptr())
         self.seg_end = torch.tensor(ends, dtype=torch.int64, device=dev)
-        wd = [weight_decay] * len(decay) + [0.0] * len(no_decay)
-        self.seg_wd = torch.tensor(wd, dtype=torch.float32, device=dev)
+        wd_of = [weight_decay] * len(decay) + [0.0] * len(no_decay)
+        self.seg_wd = torch.tensor([wd_of[i] for i in layout], dtype=torch.float32, device=dev)     # segments are in LAYOUT order
         self.lr, self.betas, self.eps, self.weight_decay, self.max_grad_norm = lr, betas, eps, weight_decay, max_grad_norm
         self.step_count = 0
         self.sumsq = torch.zeros(1, device=dev, dtype=torch.float32)
@@ -110,6 +148,37 @@ class FlatAdamW:
         """the one collective of the path: sum of the flat gradient over ranks (mean applied inside the AdamW kernel)"""
         if self.world > 1:
             dist.all_reduce(self.flat_grad, op=dist.ReduceOp.SUM)
+
+    def slices(self):
+        return [self.flat_grad[a:b] for a, b in zip(self.slice_bounds[:-1], self.slice_bounds[1:])]
+
+    def all_reduce_slices(self, events=None):
+        """The same collective, issued as contiguous slices in backward-completion order.  `events[k]` (torch.cuda.Event recorded by the
+        native backward when slice k's gradients are complete; the last slice needs none) lets slice k start on a communication stream
+        while the backward is still producing slices k+1..: only the last, small slice stays exposed.  Without events (CPU / gloo
+        tests, per-op engine) the slices are reduced back to back -- same result as `all_reduce`."""
+        if self.world <= 1:
+            return
+        if events is None or not self.flat_grad.is_cuda:
+            for sl in self.slices():
+                if sl.numel():
+                    dist.all_reduce(sl, op=dist.ReduceOp.SUM)
+            return
+        if getattr(self, "_comm_stream", None) is None:
+            self._comm_stream = torch.cuda.Stream()
+        main = torch.cuda.current_stream()
+        works = []
+        with torch.cuda.stream(self._comm_stream):
+            for k, sl in enumerate(self.slices()):
+                if k < len(events) and events[k] is not None:
+                    self._comm_stream.wait_event(events[k])
+                else:
+                    self._comm_stream.wait_stream(main)        # the tail slice: everything enqueued so far
+                if sl.numel():
+                    works.append(dist.all_reduce(sl, op=dist.ReduceOp.SUM, async_op=True))
+        for w in works:
+            w.wait()                                           # the main stream waits for the collectives
+        main.wait_stream(self._comm_stream)
 
     def step(self, lr=None, grad_scale=1.0):
         if not self.flat_param.is_cuda:
@@ -138,12 +207,11 @@ class FlatAdamW:
 
     # ---- reference checkpoint layout (train/utils/save.py:38-45)
     def state_dict(self):
-        state, off = {}, 0
+        state = {}
         for i, p in enumerate(self.params):
-            n = p.numel()
+            n, off = p.numel(), self.offsets[i]
             state[i] = {"step": self.step_count, "exp_avg": self.exp_avg[off: off + n].view_as(p).clone(),
                         "exp_avg_sq": self.exp_avg_sq[off: off + n].view_as(p).clone()}
-            off += (n + 31) // 32 * 32
         nd = self.group_sizes[0]
         groups = [
             {"lr": self.lr, "betas": self.betas, "eps": self.eps, "weight_decay": self.weight_decay, "correct_bias": True,
@@ -154,14 +222,12 @@ class FlatAdamW:
         return {"state": state, "param_groups": groups}
 
     def load_state_dict(self, sd):
-        off = 0
         for i, p in enumerate(self.params):
-            n = p.numel()
+            n, off = p.numel(), self.offsets[i]
             if i in sd["state"]:
                 self.exp_avg[off: off + n].copy_(sd["state"][i]["exp_avg"].reshape(-1))
                 self.exp_avg_sq[off: off + n].copy_(sd["state"][i]["exp_avg_sq"].reshape(-1))
                 self.step_count = int(sd["state"][i]["step"])
-            off += (n + 31) // 32 * 32
 
 
 class TrainStep:
@@ -175,6 +241,10 @@ class TrainStep:
         self.global_step = 0
         self.lr_fn = None             # optional schedule override: global_step -> lr (train_loop.py)
         self.micro_step = 0           # micro-batches accumulated since the last optimizer step (carried across epochs)
+        import os
+        # world > 1, native engine: reduce gradient slices behind the backward (LOTUS_NO_AR_OVERLAP=1: one slice after the other at the end)
+        self.overlap_allreduce = os.environ.get("LOTUS_NO_AR_OVERLAP") is None
+        self._events, self._slice_events = None, None
         self.opt.broadcast_parameters(model)      # world > 1: replicas start from rank 0's weights, as under DDP
 
     def __call__(self, batch, next_batch=None):
@@ -200,7 +270,13 @@ class TrainStep:
                 batch, pending = pre[0], pre[1]
             else:
                 batch = self.model.prepare_batch(batch)
-            _, lv = eng.native_step(batch, compute_loss=True, with_grad=True, compute_final_action=False, pending=pending)
+            self._slice_events = None
+            if self.opt.world > 1 and self.overlap_allreduce:
+                if self._events is None:
+                    self._events = [torch.cuda.Event() for _ in range(N_GRAD_SLICES - 1)]
+                self._slice_events = self._events
+            _, lv = eng.native_step(batch, compute_loss=True, with_grad=True, compute_final_action=False, pending=pending,
+                                    slice_events=self._slice_events)
             if next_batch is not None:                   # after this step is enqueued: the GPU is busy while the host prepares the next
                 eng.prefetch(next_batch, need_pairs=True)
             losses = {"pos": lv[0], "rot": lv[1], "open": lv[2], "total": lv[3]}
@@ -212,7 +288,9 @@ class TrainStep:
     def apply(self, accumulation=1):
         """all-reduce, clip, AdamW with the scheduled learning rate (train_simple_policy.py:214-232); the 1/accumulation of the
         reference's loss scaling (:206-207) is folded into the optimizer kernel's gradient scale"""
-        self.opt.all_reduce()
+        # (with gradient accumulation the early slices are only final after the LAST micro-batch: events of that one are used)
+        self.opt.all_reduce_slices(self._slice_events)
+        self._slice_events = None
         self.micro_step = 0
         self.global_step += 1
         if self.lr_fn is not None:
