@@ -30,7 +30,7 @@ def main():
     ap.add_argument("--batches", default="1,2,4,8,16,32,64,128,256")
     ap.add_argument("--iters", type=int, default=30)
     ap.add_argument("--warmup", type=int, default=5)
-    ap.add_argument("--max-total-points", type=int, default=1 << 20, help="skip cells whose packed batch exceeds this many points per rank")
+    ap.add_argument("--max-total-points", type=int, default=(1 << 22) + 1, help="skip cells whose packed batch exceeds this many points per rank")
     args = ap.parse_args()
     rank, world, local = int(os.environ.get("RANK", 0)), int(os.environ.get("WORLD_SIZE", 1)), int(os.environ.get("LOCAL_RANK", 0))
     torch.cuda.set_device(local)
@@ -43,6 +43,13 @@ def main():
     model = policy.build_parameter_shell(cfgm.production_model_config()).to(dev).eval()
     model.engine().precision = "bf16"
     model.engine().use_native = True
+    native = pkg("native")
+    peaks = {}
+    try:
+        peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
+    except Exception:
+        pass
+    hbm_peak, tf_peak = peaks.get("hbm_gbs", 6650.0), peaks.get("bf16_tflops_sustained", 1400.0)
     cells = []
     clouds = {}
     for n in [int(x) for x in args.points.split(",")]:
@@ -68,6 +75,13 @@ def main():
                      "txt_lens": [base["txt_lens"][i] for i in ids],
                      "offset": torch.tensor([npts[i] for i in ids]).cumsum(0)}
             lat = []
+            try:
+                with torch.no_grad():
+                    model(dict(batch), compute_loss=False, compute_final_action=True)
+            except torch.OutOfMemoryError:
+                torch.cuda.empty_cache()
+                cells.append({"points": n, "batch": Bl * world, "batch_per_gpu": Bl, "skipped": "out of device memory"})
+                continue
             with torch.no_grad():
                 for it in range(args.warmup + args.iters):
                     torch.cuda.synchronize()
@@ -82,13 +96,35 @@ def main():
             if world > 1:
                 torch.distributed.all_reduce(t, op=torch.distributed.ReduceOp.MAX)
             p50 = float(t.item())
+            # roofline column: algorithmic bytes / FLOPs of every kernel call of ONE forward of this cell (native profile mode: the
+            # arguments of each launcher call; same read-once / write-once accounting as bench.py), floor = sum over calls of
+            # max(bytes / HBM peak, FLOPs / tensor peak); device_ms = the same calls' summed CUDA-event time
+            floor_ms = dev_ms = None
+            if rank == 0:
+                with torch.no_grad():
+                    rec = native.profile_step(lambda: model(dict(batch), compute_loss=False, compute_final_action=True))
+                stages = model.engine().last_stages
+                ctx = {"conv_pairs": {}, "n_of_upper": {}, "npad_of_patches": {}, "n_of_cloud_off": {}, "Lt": int(sum(batch["txt_lens"]))}
+                for stg in stages:
+                    pl = next(iter(stg.plans.values()))
+                    ctx["npad_of_patches"][pl.n_patches] = pl.n_pad
+                    ctx["n_of_cloud_off"][stg.cloud_off.data_ptr()] = stg.n
+                floor_ms = dev_ms = 0.0
+                for name, a_, ms_ in rec:
+                    fl, by = bench.algorithmic_work(name, a_, ctx)
+                    floor_ms += max(fl / (tf_peak * 1e12), by / (hbm_peak * 1e9)) * 1e3
+                    dev_ms += ms_
             cells.append({"points": n, "batch": Bl * world, "batch_per_gpu": Bl, "p50_ms": p50, "p50_ms_per_keystep": p50 / (Bl * world) * world,
-                          "keysteps_per_s": Bl * world / (p50 * 1e-3), "h2d_bytes": bench.h2d_bytes(batch), "finite": bool(torch.isfinite(act).all())})
+                          "keysteps_per_s": Bl * world / (p50 * 1e-3), "h2d_bytes": bench.h2d_bytes(batch), "finite": bool(torch.isfinite(act).all()),
+                          "roofline_floor_ms": floor_ms, "device_ms_profiled": dev_ms,
+                          "frac_of_roofline": (floor_ms / p50) if floor_ms else None})
             if rank == 0:
                 print(json.dumps(cells[-1]), file=sys.stderr)
     if rank == 0:
         print(json.dumps({"workload": "3D-LOTUS inference sweep, SimplePolicyPTV3CA (68.2M params), bf16 tensor-core mode, eval, "
                                       "compute_final_action=True, synthetic voxel1cm clouds", "n_gpus": world,
+                          "roofline": "roofline_floor_ms = sum over the kernel calls of one forward of max(algorithmic bytes / %.0f GB/s, FLOPs / %.0f TFLOP/s) "
+                                      "(MEASURED_PEAKS.json; conv FLOPs counted dense over 27 taps); frac_of_roofline = floor / p50 (host in -> host out); rank 0's replica" % (hbm_peak, tf_peak),
                           "timing": "host wall clock around model(batch).cpu() with pinned host inputs, p50 over %d iterations after %d warm-ups; "
                                     "multi-GPU = independent replicas, max latency over ranks" % (args.iters, args.warmup),
                           "cells": cells}))
