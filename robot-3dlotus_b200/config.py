@@ -102,6 +102,15 @@ def production_model_config(**ptv3_overrides):
                       loss_config=dict(pos_weight=1, rot_weight=1))
 
 
+def production_planner_config(**ptv3_overrides):
+    """`config.MODEL` of the 3D-LOTUS++ motion planner: job_scripts/train_3dlotusplus_motion_planner.sh:76-110 applied over
+    configs/rlbench/motion_planner_ptv3.yaml (pc_label_channels 64, traj_embed_size 64, max_traj_len 5; xyz + height inputs)."""
+    cfg = production_model_config(in_channels=4, **ptv3_overrides)
+    cfg.model_class = "MotionPlannerPTV3CA"
+    cfg.action_config.update(max_traj_len=5, pc_label_channels=64, traj_embed_size=64, txt_reduce="attn", use_ee_pose=False)
+    return cfg
+
+
 def small_model_config(**ptv3_overrides):
     """Production topology at reduced width — used for committed golden fixtures (weights fit in git)."""
     return production_model_config(
