@@ -750,3 +750,27 @@ def adamw_step(params, grads, exp_avg, exp_avg_sq, step, lr, weight_decays, beta
         if wd > 0.0:
             p.add_(p, alpha=-lr * wd)
     return norm
+
+
+# ---------------------------------------------------------------------------------------------------------------------
+# batch producer: geometric augmentation + feature assembly of one keystep
+# (train/datasets/simple_policy_dataset.py:158-181 `_augment_pc`, :281-296 subsample + height, :321-346 centring / features;
+#  train/datasets/common.py:81-87 `random_rotate_z`).  The random draws (point indices, angle, noise) are INPUTS.
+def augment_keystep(xyz, rgb, point_idxs, angle, noise, gt_pos, table_height, xyz_shift="center", use_height=True):
+    """xyz (m,3) float32 raw, rgb (m,3) uint8 or None -> pc_ft (n, 7|6|4|3) float32, centroid (3,) float64, gt position float32"""
+    xyz = np.asarray(xyz)[point_idxs]
+    height = xyz[:, -1] - table_height
+    cosval, sinval = np.cos(angle), np.sin(angle)
+    Rm = np.array([[cosval, -sinval, 0], [sinval, cosval, 0], [0, 0, 1]])
+    xyz = np.dot(xyz, np.transpose(Rm))
+    gt = np.dot(np.asarray(gt_pos, dtype=np.float64), np.transpose(Rm))
+    xyz = noise + xyz
+    centroid = np.mean(xyz, 0) if xyz_shift == "center" else np.zeros(3)
+    xyz = xyz - centroid
+    gt = gt - centroid
+    cols = [xyz]
+    if rgb is not None:
+        cols.append((np.asarray(rgb)[point_idxs] / 255.) * 2 - 1)
+    if use_height:
+        cols.append(height[:, None])
+    return torch.from_numpy(np.concatenate(cols, 1)).float(), centroid, torch.from_numpy(gt).float()

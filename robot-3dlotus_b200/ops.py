@@ -924,3 +924,49 @@ def disc_pos_prob(pc_fts, cloud_off, B, max_cloud, gt_actions, pos_bins, bin_siz
     L.lotus_disc_pos_prob(_p(pc_fts), pc_fts.stride(0), _p(cloud_off), B, max_cloud, _p(gt_actions), gt_actions.stride(0), pos_bins,
                           float(bin_size), int(heatmap_type == "plain"), _p(out), _p(scratch), _st())
     return out
+
+
+# ---------------------------------------------------------------------------------------------------- batch producer (device side)
+def subsample_keysteps(raw_off, counts, seed):
+    """uniform random `counts[b]`-subset (random order) of every raw cloud: train/datasets/simple_policy_dataset.py:281-294.
+    raw_off (B+1,) int32 device offsets of the raw clouds; counts: python list.  -> (sel_idx (sum counts,) int32, out_off (B+1,) int32)"""
+    L = load()
+    dev = raw_off.device
+    B = raw_off.numel() - 1
+    out_off = torch.tensor([0] + list(torch.tensor(counts).cumsum(0).tolist()), dtype=torch.int32, device=dev)
+    sel = torch.empty(int(sum(counts)), dtype=torch.int32, device=dev)
+    err = torch.zeros(1, dtype=torch.int32, device=dev)
+    raw = raw_off.cpu()
+    max_raw = int((raw[1:] - raw[:-1]).max()) if B else 0
+    L.lotus_subsample_keysteps(_p(raw_off), _p(out_off), B, max_raw, int(seed) & (2 ** 63 - 1), _p(sel), _p(err), _st())
+    if int(err.item()):
+        raise RuntimeError("lotus_subsample_keysteps: a raw cloud exceeds 16384 points or a count exceeds its cloud")
+    return sel, out_off
+
+
+def augment_keysteps(raw_xyz, raw_rgb, sel_idx, out_off, angle, noise=None, noise_amp=0.002, seed=0, table_height=0.7505, center=True,
+                     gt_pos=None, use_height=True):
+    """the per-keystep augmentation + feature assembly of the reference's DataLoader workers on the device
+    (train/datasets/simple_policy_dataset.py:158-181, 296, 321-346): -> (pc_fts (N, 7|6|4|3) f32, centroid (B,3) f64, gt_pos (B,3) f32 or None)"""
+    L = load()
+    dev = raw_xyz.device
+    B = out_off.numel() - 1
+    oc = out_off.cpu()
+    N = int(oc[-1])
+    max_cloud = int((oc[1:] - oc[:-1]).max()) if B else 0
+    width = 3 + (3 if raw_rgb is not None else 0) + (1 if use_height else 0)
+    fts = torch.empty((N, width), dtype=torch.float32, device=dev)
+    centroid = torch.empty((B, 3), dtype=torch.float64, device=dev)
+    gt_out = torch.empty((B, 3), dtype=torch.float32, device=dev) if gt_pos is not None else None
+    scratch = torch.empty(3 * B, dtype=torch.float64, device=dev)
+    # (every converted input is held in a local until the call is enqueued: a temporary would hand its memory back to the allocator)
+    angle = angle.to(dev, torch.float64).contiguous()
+    raw_xyz = raw_xyz.contiguous()
+    raw_rgb = raw_rgb.contiguous() if raw_rgb is not None else None
+    noise = noise.to(dev, torch.float64).contiguous() if noise is not None else None
+    gt_pos = gt_pos.to(dev, torch.float64).contiguous() if gt_pos is not None else None
+    assert raw_xyz.dtype == torch.float32 and (raw_rgb is None or raw_rgb.dtype == torch.uint8) and sel_idx is None or sel_idx.dtype == torch.int32
+    L.lotus_augment_keysteps(_p(raw_xyz), _p(raw_rgb), _p(sel_idx), _p(out_off), B, max_cloud, _p(angle), _p(noise), float(noise_amp),
+                             int(seed) & (2 ** 63 - 1), float(table_height), int(center), _p(gt_pos), _p(fts), width, _p(centroid),
+                             _p(gt_out), 3, _p(scratch), _st())
+    return fts, centroid, gt_out

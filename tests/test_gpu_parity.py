@@ -961,3 +961,73 @@ def test_pipelined_input_prefetch_matches_synchronous_steps():
         traj[mode] = torch.stack(out).cpu()
     assert torch.isfinite(traj["pipelined"]).all()
     assert torch.allclose(traj["sync"], traj["pipelined"], rtol=5e-3, atol=1e-3), (traj["sync"], traj["pipelined"])
+
+
+def test_augmentation_producer_matches_reference_stream():
+    """SURVEY §8f row 2 / VERDICT r1 #9: z-rotation, U(0, 2 mm) jitter, subsample gather, centring and feature assembly on the device,
+    fed the reference stream's own random draws (indices, angle, noise): features equal the numpy result to one float32 ulp (the
+    float64 sums behind the centroid are formed in a different order), all four fixture keysteps in ONE packed call"""
+    from conftest import load_golden
+    ops = pkg("ops")
+    cases = load_golden("producer.pt")
+    for use_color in (True, False):
+        cs = [c for c in cases if c["use_color"] == use_color]
+        raw_xyz = torch.cat([c["raw_xyz"] for c in cs]).to(DEV)
+        raw_rgb = torch.cat([c["raw_rgb"] for c in cs]).to(DEV) if use_color else None
+        roff = np.cumsum([0] + [c["raw_xyz"].shape[0] for c in cs])
+        sel = torch.cat([c["point_idxs"] + int(roff[i]) for i, c in enumerate(cs)]).int().to(DEV)
+        out_off = torch.tensor(np.cumsum([0] + [c["point_idxs"].numel() for c in cs]), dtype=torch.int32, device=DEV)
+        angle = torch.tensor([c["angle"] for c in cs], dtype=torch.float64)
+        noise = torch.cat([c["noise"] for c in cs])
+        gt_in = torch.stack([c["gt_pos_in"] for c in cs])
+        fts, cen, gt = ops.augment_keysteps(raw_xyz, raw_rgb, sel, out_off, angle, noise=noise, table_height=cs[0]["table_height"], gt_pos=gt_in)
+        ref = torch.cat([c["pc_ft"] for c in cs])
+        assert fts.shape == ref.shape
+        assert torch.allclose(cen.cpu(), torch.stack([c["centroid"] for c in cs]), rtol=0, atol=1e-12), (cen.cpu(), [c["centroid"] for c in cs])
+        assert torch.allclose(fts.cpu(), ref, rtol=0, atol=2e-7), (fts.cpu() - ref).abs().max()
+        assert (fts.cpu() == ref).float().mean().item() > 0.999
+        assert torch.allclose(cen.cpu(), torch.stack([c["centroid"] for c in cs]), rtol=0, atol=1e-12)
+        assert torch.allclose(gt.cpu(), torch.stack([c["gt_pos_out"] for c in cs]), rtol=0, atol=2e-7)
+
+
+def test_subsample_producer_draws_uniform_subsets():
+    """device-side subsampling (simple_policy_dataset.py:281-294): exactly count[b] distinct indices inside cloud b, different per
+    seed, every point roughly equally likely; then the device-generated jitter stays inside [0, 2 mm) and the clouds come out centred"""
+    ops = pkg("ops")
+    sizes, counts = [5000, 3000, 130, 9000], [4096, 2900, 125, 4096]
+    raw_off = torch.tensor(np.cumsum([0] + sizes), dtype=torch.int32, device=DEV)
+    hits = torch.zeros(sum(sizes))
+    first = None
+    for seed in range(40):
+        sel, out_off = ops.subsample_keysteps(raw_off, counts, seed)
+        s = sel.cpu().long()
+        o = 0
+        for b, (n, k) in enumerate(zip(sizes, counts)):
+            part = s[o: o + k]
+            o += k
+            assert part.numel() == k and part.unique().numel() == k
+            assert int(part.min()) >= int(raw_off[b]) and int(part.max()) < int(raw_off[b + 1])
+        hits[s] += 1
+        if first is None:
+            first = s.clone()
+        elif seed == 1:
+            assert not torch.equal(first, s)
+    # inclusion frequency ~ k / n per cloud
+    o = 0
+    for n, k in zip(sizes, counts):
+        f = hits[o: o + n] / 40
+        assert abs(f.mean().item() - k / n) < 1e-6 and f.std().item() < 0.12
+        o += n
+    g = torch.Generator().manual_seed(0)
+    raw_xyz = (torch.rand(sum(sizes), 3, generator=g) + torch.tensor([0.0, 0.0, 0.76])).to(DEV)
+    sel, out_off = ops.subsample_keysteps(raw_off, counts, 7)
+    angle = torch.zeros(4, dtype=torch.float64)
+    f0, c0, _ = ops.augment_keysteps(raw_xyz, None, sel, out_off, angle, noise=None, noise_amp=0.0, center=False)
+    f1, c1, _ = ops.augment_keysteps(raw_xyz, None, sel, out_off, angle, noise=None, noise_amp=0.002, seed=11, center=False)
+    d = (f1[:, :3] - f0[:, :3]).cpu()
+    assert float(d.min()) >= -1e-7 and float(d.max()) < 0.002 + 1e-6 and 0.0008 < float(d.mean()) < 0.0012
+    assert torch.equal(f0[:, 3], f1[:, 3])                                 # height is taken before the augmentation
+    f2, c2, _ = ops.augment_keysteps(raw_xyz, None, sel, out_off, angle, noise_amp=0.002, seed=11, center=True)
+    oc = out_off.cpu().tolist()
+    for b in range(4):
+        assert f2[oc[b]: oc[b + 1], :3].double().mean(0).abs().max().item() < 1e-6

@@ -269,3 +269,14 @@ def test_adamw_restatement_matches_reference_optimizer():
             assert rel_err(params[i], g["params"][step - 1][i]) < 2e-6, (step, n)
             assert rel_err(m[i], g["exp_avg"][step - 1][i]) < 2e-6, (step, n)
             assert rel_err(v[i], g["exp_avg_sq"][step - 1][i]) < 2e-6, (step, n)
+
+
+def test_producer_restatement_matches_reference_stream():
+    """batch-producer restatement (`O.augment_keystep`) against the fixture replayed around the reference's own `random_rotate_z`
+    with numpy's global generator (oracle/make_golden_producer.py; simple_policy_dataset.py:158-181, 281-346): identical float32 features"""
+    from conftest import load_golden
+    for c in load_golden("producer.pt"):
+        ft, cen, gt = O.augment_keystep(c["raw_xyz"].numpy(), c["raw_rgb"].numpy() if c["use_color"] else None, c["point_idxs"].numpy(), c["angle"],
+                                        c["noise"].numpy(), c["gt_pos_in"].numpy(), c["table_height"])
+        assert torch.equal(ft, c["pc_ft"]) and torch.equal(gt, c["gt_pos_out"])
+        assert np.array_equal(cen, c["centroid"].numpy())

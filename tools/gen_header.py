@@ -59,6 +59,10 @@ DOC = {
     "lotus_linear_dgrad_act_bf16": "bf16 tensor-core backward of `fc2(drop(GELU(u)))` w.r.t. u (MLP, model.py:560-583): data-gradient GEMM with gelu'(u) and the forward's dropout mask applied in the epilogue.",
     "lotus_disc_pos_prob": "Replaces get_disc_gt_pos_prob (soft position labels, computed per keystep by the DataLoader workers): utils/action_position_utils.py:7-46, "
                            "call site train/datasets/simple_policy_dataset.py:346-354. float64 arithmetic like numpy, packed fp32 output.",
+    "lotus_subsample_keysteps": "Replaces the per-keystep point subsampling of the DataLoader workers (np.random.permutation(len)[:k] / np.random.choice(len, k, replace=False)): "
+                                "train/datasets/simple_policy_dataset.py:281-294. Uniform random k-subset in random order from counter-based keys sorted per cloud.",
+    "lotus_augment_keysteps": "Replaces the per-keystep geometric augmentation + feature assembly of the DataLoader workers: height, z-rotation, U(0, 2 mm) jitter, centring, "
+                              "colour scaling: train/datasets/simple_policy_dataset.py:158-181,296,321-346; train/datasets/common.py:81-87. float64 arithmetic like numpy.",
     "lotus_disc_pos_prob_scratch_bytes": "Scratch size (bytes) lotus_disc_pos_prob needs for B clouds.",
     "lotus_linear_wgrad_bf16": "bf16 tensor-core backward of nn.Linear w.r.t. its weight: split-K, MN-major operands read in place, fp32 accumulate.",
     "lotus_subm_conv_fwd_bf16": "bf16 tensor-core implicit-GEMM form of spconv.SubMConv3d forward (CPE k=3): model.py:616-622; gathered operand staged by cp.async.",
