@@ -774,3 +774,33 @@ def augment_keystep(xyz, rgb, point_idxs, angle, noise, gt_pos, table_height, xy
     if use_height:
         cols.append(height[:, None])
     return torch.from_numpy(np.concatenate(cols, 1)).float(), centroid, torch.from_numpy(gt).float()
+
+
+# ---------------------------------------------------------------------------------------------------------------------
+# inference front end: workspace crop + voxel down-sample (evaluation/eval_simple_policy.py:151-175).
+# PARITY UNPINNED for this function: open3d 0.18.0 (`voxel_down_sample_and_trace`) is a third-party dependency that is neither under
+# /root/reference nor installed offline, so no reference output could be minted; this restates its published algorithm
+# (open3d/geometry/PointCloud.cpp VoxelDownSampleAndTrace: voxel_min_bound = min_bound - voxel_size / 2, index = floor((p - voxel_min_bound)
+# / voxel_size), output = mean of the voxel's points, trace = its point indices in input order) anchored on the call site, which keeps
+# the colour of trace[v][0].  Voxel ORDER: open3d's is unordered_map iteration order; fixed here to first appearance.
+def voxel_downsample(xyz, rgb, crop_lo, crop_hi, voxel_size):
+    """xyz (n,3) float32, rgb (n,3) uint8 -> (mean xyz float64 (m,3), rgb uint8 (m,3), first index (m,))"""
+    xyz = np.asarray(xyz).reshape(-1, 3)
+    lo, hi = np.asarray(crop_lo, dtype=np.float64), np.asarray(crop_hi, dtype=np.float64)
+    in_mask = np.all((xyz > lo) & (xyz < hi), 1)
+    idx = np.nonzero(in_mask)[0]
+    pts = xyz[idx].astype(np.float64)
+    if len(pts) == 0:
+        return np.zeros((0, 3)), np.zeros((0, 3), dtype=np.uint8), np.zeros((0,), dtype=np.int64)
+    vmin = np.min(pts, 0) - voxel_size * 0.5
+    vox = np.floor((pts - vmin) / voxel_size).astype(np.int64)
+    _, inv = np.unique(vox, axis=0, return_inverse=True)
+    inv = inv.reshape(-1)
+    m = int(inv.max()) + 1
+    first = np.full(m, np.iinfo(np.int64).max)
+    np.minimum.at(first, inv, idx)
+    cnt = np.bincount(inv, minlength=m).astype(np.float64)
+    mean = np.stack([np.bincount(inv, weights=pts[:, a], minlength=m) / cnt for a in range(3)], 1)
+    order = np.argsort(first)
+    first = first[order]
+    return mean[order], (np.asarray(rgb).reshape(-1, 3)[first] if rgb is not None else None), first

@@ -260,3 +260,149 @@ LOTUS_API int lotus_augment_keysteps(const float* raw_xyz, const uint8_t* raw_rg
   LOTUS_CUDA_OK();
   return 0;
 }
+
+// ---------------------------------------------------------------------------------------------- inference front end: crop + voxel down-sample
+// reference: evaluation/eval_simple_policy.py:151-175 (Actioner.process_point_clouds): keep the points inside the robot workspace
+// (and above the table), then open3d 0.18.0 `PointCloud.voxel_down_sample_and_trace(voxel_size, min(xyz), max(xyz))` (third party, not
+// under /root/reference; requirements.txt).  Its published algorithm (open3d/geometry/PointCloud.cpp, VoxelDownSampleAndTrace):
+//   voxel_min_bound = min_bound - voxel_size / 2 ;  voxel index = floor((p - voxel_min_bound) / voxel_size)   (float64)
+//   output point of a voxel = mean of its points ;  trace[v] = indices of its points in input order
+// and the call site keeps `rgb[trace[v][0]]`: the colour of the FIRST input point of the voxel.  open3d emits voxels in the
+// iteration order of an unordered_map; here the order is fixed: voxels appear in the order of their first input point.
+//
+// Three stream-ordered passes over the H x W x cameras points (no sort): (1) crop + 64-bit voxel key + open-addressing hash insert with
+// float64 sums, counts and atomicMin of the point index; (2) flag the first point of every voxel and scan the flags; (3) write
+// mean / colour / first index at the scanned position.  meta[0] = number of voxels, meta[1] = points inside the crop.
+struct VoxSlot { unsigned long long key; double sx, sy, sz; int cnt, first; };
+__global__ void k_vox_init(VoxSlot* __restrict__ tab, int64_t cap, int32_t* __restrict__ meta) {
+  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < cap; i += (int64_t)gridDim.x * blockDim.x) {
+    tab[i].key = ~0ull; tab[i].sx = 0; tab[i].sy = 0; tab[i].sz = 0; tab[i].cnt = 0; tab[i].first = 0x7fffffff;
+  }
+  if (blockIdx.x == 0 && threadIdx.x < 4) meta[threadIdx.x] = 0;
+}
+__global__ void k_vox_insert(const float* __restrict__ xyz, int n, const double* __restrict__ bounds /* crop lo[3], hi[3], voxel_min_bound[3] */,
+                             double voxel_size, VoxSlot* __restrict__ tab, uint64_t cap_mask, int32_t* __restrict__ slot_of_point,
+                             int32_t* __restrict__ meta) {
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
+    const double x = xyz[(int64_t)i * 3], y = xyz[(int64_t)i * 3 + 1], z = xyz[(int64_t)i * 3 + 2];
+    const bool in = x > bounds[0] && x < bounds[3] && y > bounds[1] && y < bounds[4] && z > bounds[2] && z < bounds[5];
+    int slot = -1;
+    if (in) {
+      const long long vx = (long long)floor((x - bounds[6]) / voxel_size), vy = (long long)floor((y - bounds[7]) / voxel_size),
+                      vz = (long long)floor((z - bounds[8]) / voxel_size);
+      const unsigned long long key = ((unsigned long long)(vx & 0x1FFFFF) << 42) | ((unsigned long long)(vy & 0x1FFFFF) << 21) | (unsigned long long)(vz & 0x1FFFFF);
+      uint64_t k2 = key;
+      k2 ^= k2 >> 33; k2 *= 0xff51afd7ed558ccdull; k2 ^= k2 >> 33; k2 *= 0xc4ceb9fe1a85ec53ull; k2 ^= k2 >> 33;
+      uint64_t h = k2 & cap_mask;
+      while (true) {
+        unsigned long long prev = atomicCAS(&tab[h].key, ~0ull, key);
+        if (prev == ~0ull || prev == key) break;
+        h = (h + 1) & cap_mask;
+      }
+      slot = (int)h;
+      atomicAdd(&tab[h].sx, x); atomicAdd(&tab[h].sy, y); atomicAdd(&tab[h].sz, z);
+      atomicAdd(&tab[h].cnt, 1);
+      atomicMin(&tab[h].first, i);
+      atomicAdd(&meta[1], 1);
+    }
+    slot_of_point[i] = slot;
+  }
+}
+// single block: flags (first point of its voxel) -> exclusive scan -> position ; meta[0] = voxel count
+__global__ void __launch_bounds__(1024) k_vox_scan(const VoxSlot* __restrict__ tab, const int32_t* __restrict__ slot_of_point, int n,
+                                                   int32_t* __restrict__ pos, int32_t* __restrict__ meta) {
+  __shared__ int wsum[32];
+  __shared__ int carry;
+  if (threadIdx.x == 0) carry = 0;
+  __syncthreads();
+  const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+  for (int base = 0; base < n; base += 1024) {
+    const int i = base + threadIdx.x;
+    int f = 0;
+    if (i < n) { int s = slot_of_point[i]; f = (s >= 0 && tab[s].first == i) ? 1 : 0; }
+    int v = f;
+    for (int o = 1; o < 32; o <<= 1) { int t = __shfl_up_sync(0xffffffffu, v, o); if (lane >= o) v += t; }
+    if (lane == 31) wsum[w] = v;
+    __syncthreads();
+    if (w == 0) {
+      int t = wsum[lane];
+      for (int o = 1; o < 32; o <<= 1) { int u = __shfl_up_sync(0xffffffffu, t, o); if (lane >= o) t += u; }
+      wsum[lane] = t;
+    }
+    __syncthreads();
+    const int before = carry + (w > 0 ? wsum[w - 1] : 0) + v - f;
+    if (i < n) pos[i] = f ? before : -1;
+    __syncthreads();
+    if (threadIdx.x == 1023) carry = carry + wsum[31];
+    __syncthreads();
+  }
+  if (threadIdx.x == 0) meta[0] = carry;
+}
+__global__ void k_vox_write(const VoxSlot* __restrict__ tab, const int32_t* __restrict__ slot_of_point, const int32_t* __restrict__ pos,
+                            const uint8_t* __restrict__ rgb, int n, double* __restrict__ out_xyz, uint8_t* __restrict__ out_rgb,
+                            int32_t* __restrict__ out_first) {
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
+    const int p = pos[i];
+    if (p < 0) continue;
+    const VoxSlot& s = tab[slot_of_point[i]];
+    const double c = (double)s.cnt;
+    out_xyz[(int64_t)p * 3] = s.sx / c; out_xyz[(int64_t)p * 3 + 1] = s.sy / c; out_xyz[(int64_t)p * 3 + 2] = s.sz / c;
+    if (rgb) { out_rgb[(int64_t)p * 3] = rgb[(int64_t)i * 3]; out_rgb[(int64_t)p * 3 + 1] = rgb[(int64_t)i * 3 + 1]; out_rgb[(int64_t)p * 3 + 2] = rgb[(int64_t)i * 3 + 2]; }
+    out_first[p] = i;
+  }
+}
+
+LOTUS_API int64_t lotus_voxel_downsample_scratch_bytes(int n) {
+  int64_t cap = 1024;
+  while (cap < 2 * (int64_t)n) cap <<= 1;
+  return cap * (int64_t)sizeof(VoxSlot) + 2 * (int64_t)n * 4 + 64;
+}
+// xyz [n,3] f32 (all cameras, row-major), rgb [n,3] u8 or null, bounds (device, 9 doubles): workspace crop lo / hi (strict inequalities;
+// fold the table height into lo[2]) and open3d's voxel_min_bound = min(cropped xyz) - voxel_size / 2.  Outputs sized for n voxels:
+// out_xyz f64 [.,3], out_rgb u8 [.,3], out_first int32 [.]; meta int32[4]: [0] voxels, [1] points inside the crop.
+LOTUS_API int lotus_voxel_downsample(const float* xyz, const uint8_t* rgb, int n, const double* bounds, double voxel_size, double* out_xyz,
+                                     uint8_t* out_rgb, int32_t* out_first, int32_t* meta, void* scratch, void* stream_) {
+  if (n <= 0) return 0;
+  cudaStream_t st = (cudaStream_t)stream_;
+  int64_t cap = 1024;
+  while (cap < 2 * (int64_t)n) cap <<= 1;
+  VoxSlot* tab = (VoxSlot*)scratch;
+  int32_t* slot_of_point = (int32_t*)(tab + cap);
+  int32_t* pos = slot_of_point + n;
+  k_vox_init<<<min((int)((cap + 255) / 256), kNumSM * 8), 256, 0, st>>>(tab, cap, meta);
+  k_vox_insert<<<min(ceil_div(n, 256), kNumSM * 8), 256, 0, st>>>(xyz, n, bounds, voxel_size, tab, (uint64_t)(cap - 1), slot_of_point, meta);
+  k_vox_scan<<<1, 1024, 0, st>>>(tab, slot_of_point, n, pos, meta);
+  k_vox_write<<<min(ceil_div(n, 256), kNumSM * 8), 256, 0, st>>>(tab, slot_of_point, pos, rgb, n, out_xyz, out_rgb, out_first);
+  LOTUS_CUDA_OK();
+  return 0;
+}
+// min / max over the points inside the crop (float64 [6]: min xyz, max xyz), initialised to +-inf by the caller's memset pattern
+__global__ void k_crop_minmax(const float* __restrict__ xyz, int n, const double* __restrict__ crop, unsigned long long* __restrict__ mm) {
+  // order-preserving map of a double onto uint64 so that atomicMin / atomicMax work on the bit patterns
+  auto enc = [](double v) { unsigned long long b = (unsigned long long)__double_as_longlong(v); return (b & 0x8000000000000000ull) ? ~b : (b | 0x8000000000000000ull); };
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
+    const double x = xyz[(int64_t)i * 3], y = xyz[(int64_t)i * 3 + 1], z = xyz[(int64_t)i * 3 + 2];
+    if (x > crop[0] && x < crop[3] && y > crop[1] && y < crop[4] && z > crop[2] && z < crop[5]) {
+      atomicMin(&mm[0], enc(x)); atomicMin(&mm[1], enc(y)); atomicMin(&mm[2], enc(z));
+      atomicMax(&mm[3], enc(x)); atomicMax(&mm[4], enc(y)); atomicMax(&mm[5], enc(z));
+    }
+  }
+}
+__global__ void k_crop_bounds_finish(const unsigned long long* __restrict__ mm, const double* __restrict__ crop, double voxel_size, double* __restrict__ bounds) {
+  const int t = threadIdx.x;
+  auto dec = [](unsigned long long e) { unsigned long long b = (e & 0x8000000000000000ull) ? (e & 0x7FFFFFFFFFFFFFFFull) : ~e; return __longlong_as_double((long long)b); };
+  if (t < 6) bounds[t] = crop[t];
+  if (t < 3) bounds[6 + t] = dec(mm[t]) - voxel_size * 0.5;
+}
+// bounds[9] (device) from the crop box: the crop itself and voxel_min_bound = min over the cropped points - voxel_size / 2
+// (eval_simple_policy.py:171-173 passes np.min(xyz, 0) of the cropped cloud).  scratch: 6 x uint64.
+LOTUS_API int lotus_voxel_bounds(const float* xyz, int n, const double* crop_lo_hi, double voxel_size, double* bounds, void* scratch, void* stream_) {
+  cudaStream_t st = (cudaStream_t)stream_;
+  unsigned long long* mm = (unsigned long long*)scratch;
+  LOTUS_CUDA_CALL(cudaMemsetAsync(mm, 0xFF, 3 * 8, st));
+  LOTUS_CUDA_CALL(cudaMemsetAsync(mm + 3, 0x00, 3 * 8, st));
+  if (n > 0) k_crop_minmax<<<min(ceil_div(n, 256), kNumSM * 8), 256, 0, st>>>(xyz, n, crop_lo_hi, mm);
+  k_crop_bounds_finish<<<1, 32, 0, st>>>(mm, crop_lo_hi, voxel_size, bounds);
+  LOTUS_CUDA_OK();
+  return 0;
+}

@@ -970,3 +970,28 @@ def augment_keysteps(raw_xyz, raw_rgb, sel_idx, out_off, angle, noise=None, nois
                              int(seed) & (2 ** 63 - 1), float(table_height), int(center), _p(gt_pos), _p(fts), width, _p(centroid),
                              _p(gt_out), 3, _p(scratch), _st())
     return fts, centroid, gt_out
+
+
+def voxel_downsample(xyz, rgb, crop_lo, crop_hi, voxel_size=0.01):
+    """workspace crop + 1 cm voxel down-sample of the merged camera clouds on the device (Actioner.process_point_clouds,
+    evaluation/eval_simple_policy.py:151-175; open3d voxel_down_sample_and_trace restated): xyz (n,3) f32, rgb (n,3) u8 or None ->
+    (voxel means (m,3) f64, colours (m,3) u8 of each voxel's first input point, first input index (m,) int32); voxels in order of first appearance"""
+    L = load()
+    dev = xyz.device
+    xyz = xyz.reshape(-1, 3).contiguous()
+    rgb = rgb.reshape(-1, 3).contiguous() if rgb is not None else None
+    assert xyz.dtype == torch.float32 and (rgb is None or rgb.dtype == torch.uint8)
+    n = xyz.shape[0]
+    crop = torch.tensor(list(crop_lo) + list(crop_hi), dtype=torch.float64, device=dev)
+    bounds = torch.empty(9, dtype=torch.float64, device=dev)
+    mm = torch.empty(6, dtype=torch.int64, device=dev)
+    st = _st()
+    L.lotus_voxel_bounds(_p(xyz), n, _p(crop), float(voxel_size), _p(bounds), _p(mm), st)
+    out_xyz = torch.empty((n, 3), dtype=torch.float64, device=dev)
+    out_rgb = torch.empty((n, 3), dtype=torch.uint8, device=dev) if rgb is not None else None
+    out_first = torch.empty(n, dtype=torch.int32, device=dev)
+    meta = torch.zeros(4, dtype=torch.int32, device=dev)
+    scratch = torch.empty((int(L.cdll.lotus_voxel_downsample_scratch_bytes(n)) + 7) // 8, dtype=torch.int64, device=dev)
+    L.lotus_voxel_downsample(_p(xyz), _p(rgb), n, _p(bounds), float(voxel_size), _p(out_xyz), _p(out_rgb), _p(out_first), _p(meta), _p(scratch), st)
+    m = int(meta[0].item())            # one size read-back (the reference holds the whole front end on the host)
+    return out_xyz[:m], (out_rgb[:m] if rgb is not None else None), out_first[:m]

@@ -1031,3 +1031,32 @@ def test_subsample_producer_draws_uniform_subsets():
     oc = out_off.cpu().tolist()
     for b in range(4):
         assert f2[oc[b]: oc[b + 1], :3].double().mean(0).abs().max().item() < 1e-6
+
+
+def test_voxel_downsample_front_end():
+    """SURVEY §8f row 4 (second half): workspace crop + 1 cm voxel down-sample of the merged camera clouds on the device against the
+    numpy restatement of open3d's algorithm (oracle; parity unpinned: open3d is absent offline): same voxels in the same (first
+    appearance) order, first-point colours and indices bit-equal, voxel means equal to float64 rounding (the sums are atomics).
+    Edge cases: points outside the crop, many points per voxel, an empty crop."""
+    ops = pkg("ops")
+    g = np.random.default_rng(5)
+    n = 4 * 128 * 128
+    xyz = np.concatenate([g.uniform([-0.6, -0.8, 0.6], [0.9, 0.8, 1.8], size=(n // 2, 3)),
+                          g.normal([0.2, 0.0, 0.9], 0.03, size=(n // 2, 3))]).astype(np.float32)       # half of it piles into a few hundred voxels
+    xyz = xyz[g.permutation(n)]
+    rgb = g.integers(0, 256, size=(n, 3)).astype(np.uint8)
+    lo, hi = [-0.5, -0.6, 0.7505], [0.75, 0.6, 1.6]                    # workspace box with the table height folded into z_lo
+    m_ref, c_ref, f_ref = O.voxel_downsample(xyz, rgb, lo, hi, 0.01)
+    m, c, f = ops.voxel_downsample(torch.from_numpy(xyz).to(DEV), torch.from_numpy(rgb).to(DEV), lo, hi, 0.01)
+    assert m.shape[0] == m_ref.shape[0] and 1000 < m.shape[0] < n // 2
+    assert torch.equal(f.cpu().long(), torch.from_numpy(f_ref)) and torch.equal(c.cpu(), torch.from_numpy(c_ref))
+    assert np.allclose(m.cpu().numpy(), m_ref, rtol=0, atol=1e-12)
+    # every output point lies inside the crop and inside its own voxel
+    assert bool(((m > torch.tensor(lo, device=DEV)) & (m < torch.tensor(hi, device=DEV))).all())
+    # empty crop
+    m0, c0, f0 = ops.voxel_downsample(torch.from_numpy(xyz).to(DEV), torch.from_numpy(rgb).to(DEV), [5, 5, 5], [6, 6, 6], 0.01)
+    assert m0.shape[0] == 0 and f0.numel() == 0
+    # then the rest of process_point_clouds (:224-251: height, centring, colour scaling) through the producer kernel on the voxel means
+    out_off = torch.tensor([0, m.shape[0]], dtype=torch.int32, device=DEV)
+    fts, cen, _ = ops.augment_keysteps(m.float(), c, None, out_off, torch.zeros(1, dtype=torch.float64), noise_amp=0.0, table_height=0.7505)
+    assert fts.shape == (m.shape[0], 7) and abs(float(fts[:, :3].double().mean())) < 1e-6 and float(fts[:, 6].min()) > 0

@@ -63,6 +63,10 @@ DOC = {
                                 "train/datasets/simple_policy_dataset.py:281-294. Uniform random k-subset in random order from counter-based keys sorted per cloud.",
     "lotus_augment_keysteps": "Replaces the per-keystep geometric augmentation + feature assembly of the DataLoader workers: height, z-rotation, U(0, 2 mm) jitter, centring, "
                               "colour scaling: train/datasets/simple_policy_dataset.py:158-181,296,321-346; train/datasets/common.py:81-87. float64 arithmetic like numpy.",
+    "lotus_voxel_downsample": "Replaces the workspace crop + open3d voxel_down_sample_and_trace of Actioner.process_point_clouds: evaluation/eval_simple_policy.py:151-175 "
+                              "(voxel mean, colour of the voxel's first input point; voxels ordered by first appearance).",
+    "lotus_voxel_downsample_scratch_bytes": "Scratch size (bytes) lotus_voxel_downsample needs for n input points.",
+    "lotus_voxel_bounds": "The crop box and open3d's voxel_min_bound (min of the cropped cloud - voxel_size / 2) on the device: evaluation/eval_simple_policy.py:154-173.",
     "lotus_disc_pos_prob_scratch_bytes": "Scratch size (bytes) lotus_disc_pos_prob needs for B clouds.",
     "lotus_linear_wgrad_bf16": "bf16 tensor-core backward of nn.Linear w.r.t. its weight: split-K, MN-major operands read in place, fp32 accumulate.",
     "lotus_subm_conv_fwd_bf16": "bf16 tensor-core implicit-GEMM form of spconv.SubMConv3d forward (CPE k=3): model.py:616-622; gathered operand staged by cp.async.",
