@@ -507,10 +507,21 @@ __global__ void k_fps(const float* __restrict__ xyz, int64_t row_stride, const i
   __shared__ int s_far;
   int b = blockIdx.x, s = cloud_off[b], n = cloud_off[b + 1] - s;
   float* sx = sm; float* sy = sx + n; float* sz = sy + n; float* sd = sz + n;
-  for (int i = threadIdx.x; i < n; i += blockDim.x) {
-    const float* p = xyz + (int64_t)(s + i) * row_stride;
-    sx[i] = p[0]; sy[i] = p[1]; sz[i] = p[2];
-    sd[i] = 1e10f;
+  if (row_stride == 3) {
+    // packed xyz: the cloud is one contiguous run of 3 n floats -> coalesced loads, de-interleaved into the SoA staging
+    const float* src = xyz + (int64_t)s * 3;
+    for (int f = threadIdx.x; f < 3 * n; f += blockDim.x) {
+      const float v = src[f];
+      const int pi = f / 3, c = f - 3 * pi;
+      (c == 0 ? sx : c == 1 ? sy : sz)[pi] = v;
+    }
+    for (int i = threadIdx.x; i < n; i += blockDim.x) sd[i] = 1e10f;
+  } else {
+    for (int i = threadIdx.x; i < n; i += blockDim.x) {
+      const float* p = xyz + (int64_t)(s + i) * row_stride;       // xyz columns of a wider feature row (pc_fts): 12 of every row_stride*4 bytes
+      sx[i] = p[0]; sy[i] = p[1]; sz[i] = p[2];
+      sd[i] = 1e10f;
+    }
   }
   if (threadIdx.x == 0) s_far = start_idx[b];
   __syncthreads();
@@ -566,11 +577,20 @@ LOTUS_API int lotus_fps(const float* xyz, int64_t row_stride, const int32_t* clo
 // brute-force kNN / ball query inside each cloud: reference points tiled through shared memory
 // ------------------------------------------------------------------------------------------------
 #define KNN_TILE 1024
+// coalesced staging of one reference tile: the tile is a contiguous run of 3 tn floats; stored as float4 (x, y, z, -) so the scan
+// loop reads one candidate with ONE broadcast 16-byte shared load
+__device__ __forceinline__ void knn_stage_tile(const float* __restrict__ src, int tn, float4* tile) {
+  float* flat = (float*)tile;
+  for (int f = threadIdx.x; f < 3 * tn; f += blockDim.x) {
+    const int pi = f / 3, c = f - 3 * pi;
+    flat[pi * 4 + c] = src[f];
+  }
+}
 template <int KMAX>
-__global__ void k_knn(const float* __restrict__ q, const int32_t* __restrict__ q_off, const float* __restrict__ r,
+__global__ void __launch_bounds__(128) k_knn(const float* __restrict__ q, const int32_t* __restrict__ q_off, const float* __restrict__ r,
                       const int32_t* __restrict__ r_off, int k, int32_t* __restrict__ idx_out,
                       float* __restrict__ dist_out) {
-  __shared__ float tx[KNN_TILE], ty[KNN_TILE], tz[KNN_TILE];
+  __shared__ float4 tile[KNN_TILE];
   int b = blockIdx.y;
   int qs = q_off[b], qn = q_off[b + 1] - qs, rs = r_off[b], rn = r_off[b + 1] - rs;
   int qi = blockIdx.x * blockDim.x + threadIdx.x;
@@ -581,30 +601,43 @@ __global__ void k_knn(const float* __restrict__ q, const int32_t* __restrict__ q
   float bd[KMAX]; int bi[KMAX];
 #pragma unroll
   for (int j = 0; j < KMAX; ++j) { bd[j] = INFINITY; bi[j] = -1; }
+  float thr = INFINITY;                        // current k-th best distance, kept in a register: the scan loop is compare-only
   for (int t0 = 0; t0 < rn; t0 += KNN_TILE) {
     int tn = min(KNN_TILE, rn - t0);
     __syncthreads();
-    for (int i = threadIdx.x; i < tn; i += blockDim.x) {
-      const float* p = r + (int64_t)(rs + t0 + i) * 3;
-      tx[i] = p[0]; ty[i] = p[1]; tz[i] = p[2];
-    }
+    knn_stage_tile(r + (int64_t)(rs + t0) * 3, tn, tile);
     __syncthreads();
     if (!active) continue;
+#pragma unroll 4
     for (int i = 0; i < tn; ++i) {
-      float dx = __fsub_rn(qx, tx[i]), dy = __fsub_rn(qy, ty[i]), dz = __fsub_rn(qz, tz[i]);
+      const float4 p = tile[i];
+      float dx = __fsub_rn(qx, p.x), dy = __fsub_rn(qy, p.y), dz = __fsub_rn(qz, p.z);
       float d = __fadd_rn(__fadd_rn(__fmul_rn(dx, dx), __fmul_rn(dy, dy)), __fmul_rn(dz, dz));
-      if (d < bd[k - 1]) {  // strict: equal distances keep the earlier (lower) index
-        int j = k - 1;
-        while (j > 0 && bd[j - 1] > d) { bd[j] = bd[j - 1]; bi[j] = bi[j - 1]; --j; }
-        bd[j] = d; bi[j] = rs + t0 + i;
+      if (d < thr) {
+        // bubble the candidate through the sorted list with STATIC register indexing (a data-dependent shift loop put the list in
+        // local memory, and every insertion of any lane stalled its whole warp on it): the candidate takes the first slot whose entry
+        // is strictly larger (equal distances keep the earlier, lower index in front), everything behind shifts, the largest falls out
+        float cd = d; int ci = rs + t0 + i;
+        bool sw = false;                                       // sticky: past the insertion slot every entry just shifts right
+#pragma unroll
+        for (int j = 0; j < KMAX; ++j) {
+          sw = sw || cd < bd[j];
+          const float td = bd[j]; const int ti = bi[j];
+          bd[j] = sw ? cd : td; bi[j] = sw ? ci : ti;
+          cd = sw ? td : cd; ci = sw ? ti : ci;
+        }
+        thr = bd[KMAX - 1];
       }
     }
   }
-  if (active)
-    for (int j = 0; j < k; ++j) {
-      idx_out[(int64_t)(qs + qi) * k + j] = bi[j];
-      if (dist_out) dist_out[(int64_t)(qs + qi) * k + j] = bd[j];
-    }
+  if (active) {
+#pragma unroll
+    for (int j = 0; j < KMAX; ++j)
+      if (j < k) {
+        idx_out[(int64_t)(qs + qi) * k + j] = bi[j];
+        if (dist_out) dist_out[(int64_t)(qs + qi) * k + j] = bd[j];
+      }
+  }
 }
 
 LOTUS_API int lotus_knn(const float* query, const int32_t* q_off, const float* ref, const int32_t* r_off, int B,
@@ -621,7 +654,7 @@ LOTUS_API int lotus_knn(const float* query, const int32_t* q_off, const float* r
 
 __global__ void k_ball(const float* __restrict__ q, const int32_t* __restrict__ q_off, const float* __restrict__ r,
                        const int32_t* __restrict__ r_off, float radius2, int nsample, int32_t* __restrict__ idx_out) {
-  __shared__ float tx[KNN_TILE], ty[KNN_TILE], tz[KNN_TILE];
+  __shared__ float4 tile[KNN_TILE];
   int b = blockIdx.y;
   int qs = q_off[b], qn = q_off[b + 1] - qs, rs = r_off[b], rn = r_off[b + 1] - rs;
   int qi = blockIdx.x * blockDim.x + threadIdx.x;
@@ -634,14 +667,12 @@ __global__ void k_ball(const float* __restrict__ q, const int32_t* __restrict__ 
   for (int t0 = 0; t0 < rn; t0 += KNN_TILE) {
     int tn = min(KNN_TILE, rn - t0);
     __syncthreads();
-    for (int i = threadIdx.x; i < tn; i += blockDim.x) {
-      const float* p = r + (int64_t)(rs + t0 + i) * 3;
-      tx[i] = p[0]; ty[i] = p[1]; tz[i] = p[2];
-    }
+    knn_stage_tile(r + (int64_t)(rs + t0) * 3, tn, tile);
     __syncthreads();
     if (!active || cnt >= nsample) continue;
     for (int i = 0; i < tn && cnt < nsample; ++i) {
-      float dx = __fsub_rn(qx, tx[i]), dy = __fsub_rn(qy, ty[i]), dz = __fsub_rn(qz, tz[i]);
+      const float4 p = tile[i];
+      float dx = __fsub_rn(qx, p.x), dy = __fsub_rn(qy, p.y), dz = __fsub_rn(qz, p.z);
       float d = __fadd_rn(__fadd_rn(__fmul_rn(dx, dx), __fmul_rn(dy, dy)), __fmul_rn(dz, dz));
       if (d < radius2) {
         if (cnt == 0) first = rs + t0 + i;

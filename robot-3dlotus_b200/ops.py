@@ -70,7 +70,8 @@ def to_bf16(x):
 def to_f32(x):
     L = load()
     y = torch.empty(x.shape, device=x.device, dtype=torch.float32)
-    L.lotus_convert(_p(x.contiguous()), _p(y), x.numel(), 1, _st())
+    x = x.contiguous()                 # (held in a local: a temporary would return its memory before the kernel is enqueued)
+    L.lotus_convert(_p(x), _p(y), x.numel(), 1, _st())
     return y
 
 
