@@ -12,7 +12,7 @@ for line in out.splitlines():
         continue
     if cur is None:
         continue
-    mm = re.search(r"/\*[0-9a-f]{4}\*/\s+(?:@!?U?P\d+\s+)?([A-Z0-9_.]+)", line)
+    mm = re.search(r"/\*[0-9a-f]{4,}\*/\s+(?:@!?U?P\d+\s+)?([A-Z0-9_.]+)", line)
     if mm:
         op = mm.group(1)
         for k in keys:
