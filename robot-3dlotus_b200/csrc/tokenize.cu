@@ -88,6 +88,83 @@ LOTUS_API int lotus_grid_coord(const float* coord, int64_t n, float grid_size, i
   return 0;
 }
 
+// Shape-static form for CUDA-graph replay: the launch covers `n_upper` points, the ACTUAL count is read on the device (n_dev, e.g.
+// &cloud_off[B]) so that one captured graph serves every cloud of a size bucket ("CUDA-graph capture with
+// shape bucketing").  Points beyond *n_dev are never read.
+__global__ void k_coord_min_n(const float* __restrict__ coord, const int32_t* __restrict__ n_dev, uint32_t* __restrict__ mn) {
+  const int64_t n = *n_dev;
+  float m0 = INFINITY, m1 = INFINITY, m2 = INFINITY;
+  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
+    m0 = fminf(m0, coord[i * 3 + 0]); m1 = fminf(m1, coord[i * 3 + 1]); m2 = fminf(m2, coord[i * 3 + 2]);
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) {
+    m0 = fminf(m0, __shfl_xor_sync(0xffffffffu, m0, o)); m1 = fminf(m1, __shfl_xor_sync(0xffffffffu, m1, o)); m2 = fminf(m2, __shfl_xor_sync(0xffffffffu, m2, o));
+  }
+  if ((threadIdx.x & 31) == 0) { atomicMin(&mn[0], f2ord(m0)); atomicMin(&mn[1], f2ord(m1)); atomicMin(&mn[2], f2ord(m2)); }
+}
+__global__ void k_grid_n(const float* __restrict__ coord, const int32_t* __restrict__ n_dev, const uint32_t* __restrict__ mn, float gs, int mode,
+                         int32_t* __restrict__ grid, int32_t* __restrict__ gmax) {
+  const int64_t n = *n_dev;
+  float m[3] = {ord2f(mn[0]), ord2f(mn[1]), ord2f(mn[2])};
+  float inv = __fdiv_rn(1.0f, gs);
+  int mx = 0;
+  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n * 3; i += (int64_t)gridDim.x * blockDim.x) {
+    float d = __fsub_rn(coord[i], m[i % 3]);
+    float q = mode ? __fmul_rn(d, inv) : __fdiv_rn(d, gs);
+    int g = (int)truncf(q);
+    grid[i] = g;
+    mx = max(mx, g);
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) mx = max(mx, __shfl_xor_sync(0xffffffffu, mx, o));
+  if ((threadIdx.x & 31) == 0) atomicMax(gmax, mx);
+}
+__global__ void k_finish_meta0_n(const int32_t* gmax, const int32_t* n_dev, int32_t* meta) {
+  int m = *gmax;
+  meta[META_N] = *n_dev;
+  meta[META_DEPTH] = (m <= 0) ? 0 : (32 - __clz(m));
+}
+LOTUS_API int lotus_grid_coord_n(const float* coord, int64_t n_upper, const int32_t* n_dev, float grid_size, int mode, int32_t* grid,
+                                 int32_t* meta, void* scratch16, void* stream_) {
+  cudaStream_t st = (cudaStream_t)stream_;
+  LOTUS_CHECK_ARG(n_upper > 0 && n_upper < (1ll << 31) / 3, "lotus_grid_coord_n: n_upper=%lld out of range", (long long)n_upper);
+  uint32_t* mn = (uint32_t*)scratch16;
+  int32_t* gmax = (int32_t*)scratch16 + 3;
+  LOTUS_CUDA_CALL(cudaMemsetAsync(mn, 0xFF, 12, st));
+  LOTUS_CUDA_CALL(cudaMemsetAsync(gmax, 0, 4, st));
+  k_coord_min_n<<<min(ceil_div(n_upper, 256), kNumSM * 8), 256, 0, st>>>(coord, n_dev, mn);
+  k_grid_n<<<min(ceil_div(n_upper * 3, 256), kNumSM * 8), 256, 0, st>>>(coord, n_dev, mn, grid_size, mode, grid, gmax);
+  k_finish_meta0_n<<<1, 1, 0, st>>>(gmax, n_dev, meta);
+  LOTUS_CUDA_OK();
+  return 0;
+}
+
+// Makes the rows between a stage's ACTUAL point count (device meta) and the static upper bound the kernels are launched over inert:
+// neighbour-table rows -> -1 (no neighbour), the pooling cluster of such a row -> 0, and the child stage's CSR pointers beyond its
+// actual size -> empty segments.  With that, every kernel of a forward may run over the bucket's row bound: rows past the real count
+// compute garbage that no real row ever reads (graph replay with shape bucketing; inference).
+__global__ void k_stage_sanitize(const int32_t* __restrict__ meta, int n_upper, int32_t* __restrict__ nbr3, int64_t stride, int32_t* __restrict__ nbr5,
+                                 int32_t* __restrict__ cluster, const int32_t* __restrict__ meta_child, int n_child_upper, int32_t* __restrict__ seg_ptr_child) {
+  const int n = meta[META_N];
+  const int tid = blockIdx.x * blockDim.x + threadIdx.x, nt = gridDim.x * blockDim.x;
+  const int tail = max(0, n_upper - n);
+  for (int64_t t = tid; t < (int64_t)tail * 27; t += nt) { int d = (int)(t / tail), m = n + (int)(t % tail); nbr3[(int64_t)d * stride + m] = -1; }
+  if (nbr5) for (int64_t t = tid; t < (int64_t)tail * 125; t += nt) { int d = (int)(t / tail), m = n + (int)(t % tail); nbr5[(int64_t)d * stride + m] = -1; }
+  if (cluster) for (int t = tid; t < tail; t += nt) cluster[n + t] = 0;
+  if (seg_ptr_child) {
+    const int nc = meta_child[META_N];
+    const int last = seg_ptr_child[nc];
+    for (int t = nc + 1 + tid; t <= n_child_upper; t += nt) seg_ptr_child[t] = last;
+  }
+}
+LOTUS_API int lotus_stage_sanitize(const int32_t* meta, int n_upper, int32_t* nbr3, int64_t nbr_stride, int32_t* nbr5, int32_t* cluster,
+                                   const int32_t* meta_child, int n_child_upper, int32_t* seg_ptr_child, void* stream_) {
+  k_stage_sanitize<<<kNumSM, 256, 0, (cudaStream_t)stream_>>>(meta, n_upper, nbr3, nbr_stride, nbr5, cluster, meta_child, n_child_upper, seg_ptr_child);
+  LOTUS_CUDA_OK();
+  return 0;
+}
+
 // batch id per point from device offsets (model.py:37-42)
 __global__ void k_batch_ids(const int32_t* __restrict__ off, int B, int32_t* __restrict__ batch) {
   int b = blockIdx.x;
@@ -138,9 +215,11 @@ __device__ __forceinline__ uint64_t hilbert3(uint32_t x0, uint32_t x1, uint32_t 
 struct Curves { int c[4]; };  // 0 z, 1 z-trans, 2 hilbert, 3 hilbert-trans
 
 __global__ void k_codes(const int32_t* __restrict__ grid, const int32_t* __restrict__ batch,
-                        const int32_t* __restrict__ meta, Curves cv, int nrows, int64_t row_stride,
+                        const int32_t* __restrict__ meta, Curves cv, const int32_t* __restrict__ cv_dev, int nrows, int64_t row_stride,
                         int64_t* __restrict__ code) {
   int n = meta[META_N], depth = meta[META_DEPTH];
+  if (cv_dev)                                  // graph replay: the shuffled curve of every row comes from device memory
+    for (int r = 0; r < nrows; ++r) cv.c[r] = cv_dev[r] & 3;
   for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
     uint32_t x = grid[i * 3], y = grid[i * 3 + 1], z = grid[i * 3 + 2];
     uint64_t hi = (uint64_t)batch[i] << (3 * depth);
@@ -208,19 +287,19 @@ __global__ void k_cloud_sort(const int64_t* __restrict__ code, const int32_t* __
   }
 }
 
-LOTUS_API int lotus_serialize(const int32_t* grid, const int32_t* batch, const int32_t* cloud_off, int B,
+static int serialize_impl(const int32_t* grid, const int32_t* batch, const int32_t* cloud_off, int B,
                               int n_upper, int max_cloud_upper, const int32_t* meta, const int32_t* curve_of_row,
                               int nrows, int64_t row_stride, int64_t* code, int32_t* order, int32_t* inverse,
-                              int32_t* err_flag, void* stream_) {
+                              int32_t* err_flag, const int32_t* curves_dev, void* stream_) {
   cudaStream_t st = (cudaStream_t)stream_;
   LOTUS_CHECK_ARG(nrows >= 1 && nrows <= 4, "lotus_serialize: nrows=%d", nrows);
   LOTUS_CHECK_ARG(max_cloud_upper <= 16384, "lotus_serialize: clouds above 16384 points (%d) exceed the shared-memory sort", max_cloud_upper);
   Curves cv;
   for (int r = 0; r < 4; ++r) {
-    cv.c[r] = r < nrows ? curve_of_row[r] : 0;
+    cv.c[r] = (r < nrows && curve_of_row) ? curve_of_row[r] : 0;
     LOTUS_CHECK_ARG(cv.c[r] >= 0 && cv.c[r] < 4, "lotus_serialize: bad curve id");
   }
-  k_codes<<<min(ceil_div(n_upper, 256), kNumSM * 8), 256, 0, st>>>(grid, batch, meta, cv, nrows, row_stride, code);
+  k_codes<<<min(ceil_div(n_upper, 256), kNumSM * 8), 256, 0, st>>>(grid, batch, meta, cv, curves_dev, nrows, row_stride, code);
   int np2 = 1, bits = 0;
   while (np2 < max_cloud_upper) { np2 <<= 1; ++bits; }
   if (bits < 1) bits = 1;
@@ -234,6 +313,23 @@ LOTUS_API int lotus_serialize(const int32_t* grid, const int32_t* batch, const i
   k_cloud_sort<<<dim3(B, nrows), threads, smem, st>>>(code, cloud_off, meta, row_stride, bits, np2, order, inverse, err_flag);
   LOTUS_CUDA_OK();
   return 0;
+}
+
+LOTUS_API int lotus_serialize(const int32_t* grid, const int32_t* batch, const int32_t* cloud_off, int B,
+                              int n_upper, int max_cloud_upper, const int32_t* meta, const int32_t* curve_of_row,
+                              int nrows, int64_t row_stride, int64_t* code, int32_t* order, int32_t* inverse,
+                              int32_t* err_flag, void* stream_) {
+  return serialize_impl(grid, batch, cloud_off, B, n_upper, max_cloud_upper, meta, curve_of_row, nrows, row_stride, code, order, inverse, err_flag,
+                        nullptr, stream_);
+}
+// curve ids of the rows read from DEVICE memory (curve_of_row_dev[nrows]): the per-forward `shuffle_orders` draw (model.py:130-134,
+// 750-754) stays a run-time input of a captured CUDA graph
+LOTUS_API int lotus_serialize_dev(const int32_t* grid, const int32_t* batch, const int32_t* cloud_off, int B,
+                                  int n_upper, int max_cloud_upper, const int32_t* meta, const int32_t* curve_of_row_dev,
+                                  int nrows, int64_t row_stride, int64_t* code, int32_t* order, int32_t* inverse,
+                                  int32_t* err_flag, void* stream_) {
+  return serialize_impl(grid, batch, cloud_off, B, n_upper, max_cloud_upper, meta, nullptr, nrows, row_stride, code, order, inverse, err_flag,
+                        curve_of_row_dev, stream_);
 }
 
 // ------------------------------------------------------------------------------------------------

@@ -30,6 +30,9 @@ class PolicyEngine:
         self._pf_stream = None
         self._prefetched = None
         self._tc_weights = None
+        self.use_graph = False         # inference: replay the whole forward as one CUDA graph per size bucket (native.GraphedForward)
+        self._graphs = {}
+        self.graph_stats = {"replays": 0, "captures": 0, "fallbacks": 0}
         load()                         # fail loudly if the CUDA library is absent
 
     def _stage_weights(self):
@@ -244,6 +247,31 @@ class PolicyEngine:
         return self._native.run(batch, stages, tok_dev, tok_off, m.training, self.precision == "bf16", compute_loss,
                                 not compute_final_action, with_grad and compute_loss, seed, slice_events=slice_events)
 
+    def _graphed_forward(self, batch):
+        """inference through a captured CUDA graph of the bucket this batch falls in (points rounded up to 512, tokens to 16); returns
+        the (B, 8) float64 actions on the host, or None (the caller runs the eager path) when a stage outgrew the bucket's bounds"""
+        from . import native
+        pt = self.m.ptv3_model
+        npts = [int(v) for v in batch["npoints_in_batch"]]
+        lens = [int(v) for v in batch["txt_lens"]]
+        B = len(npts)
+        key = (B, native._round_up(sum(npts), 512), native._round_up(sum(lens), 16), native._round_up(max(npts), 512), native._round_up(max(lens), 16))
+        if key[3] > 16384 or key[4] > 128:
+            return None                      # beyond the shared-memory sort / token-list limits of the static path
+        perms = self._perms(pt.num_stages, len(pt.order), pt.shuffle_orders)
+        g = self._graphs.get(key)
+        if g is None or g.stale():
+            g = native.GraphedForward(self.m, *key)
+            g.capture(batch, perms)
+            self._graphs[key] = g
+            self.graph_stats["captures"] += 1
+        out = g(batch, perms)
+        if out is None:
+            self.graph_stats["fallbacks"] += 1
+        else:
+            self.graph_stats["replays"] += 1
+        return out
+
     # ------------------------------------------------------------------ context (prepare_ptv3_batch)
     def _pose_embedding(self, poses):
         """RobotPoseEmbedding.forward (models/base.py:61-78); the quaternion -> euler step runs in scipy on the host
@@ -303,6 +331,11 @@ class PolicyEngine:
         fts = batch["pc_fts"]
         if not fts.is_cuda:
             raise RuntimeError("lotus engine needs the model on a CUDA device (there is no CPU fallback)")
+        if (self.use_native and self.use_graph and not torch.is_grad_enabled() and not compute_loss and not m.training
+                and self.precision == "bf16" and kwargs.get("compute_final_action", True)):
+            out = self._graphed_forward(batch)
+            if out is not None:
+                return out
         if self.use_native and not torch.is_grad_enabled():
             final, lv = self.native_step(batch, compute_loss=compute_loss, with_grad=False,
                                          compute_final_action=kwargs.get("compute_final_action", True))

@@ -190,3 +190,128 @@ def profile_step(run_step):
         return out
     finally:
         L.cdll.lotus_policy_step_profile(0)
+
+
+# ---------------------------------------------------------------------------------------------------- CUDA-graph replay (inference)
+def _round_up(x, m):
+    return (int(x) + m - 1) // m * m
+
+
+class GraphedForward:
+    """CUDA-graph capture of the WHOLE inference forward for one size bucket: integer tokeniser (all five stages) + lotus_policy_step
+    (forward + final-action decode), ~370 kernel nodes replayed with one launch.  SURVEY §7.10 / §8f row 1 ("CUDA-graph capture with
+    shape bucketing"); reference hot loop: evaluation/eval_simple_policy.py:316-321 (one model call per keystep).
+
+    Shape bucketing: the graph is captured over STATIC buffers sized by the bucket (points rounded up to 512, text tokens to 16);
+    the actual cloud / token offsets are device data.  Every kernel runs over the bucket's row bounds; rows between a stage's actual
+    size and its bound are inert (lotus_stage_sanitize) and compute garbage no real row reads (BatchNorm uses running statistics in
+    eval mode, so no kernel reduces over rows).  The deeper stages' bounds are fractions of the point bucket (RATIOS, ~1.5-7x the
+    sizes measured on voxel1cm-like clouds); after every replay the actual sizes come back with the actions and an overflow falls
+    back to the eager path.  The per-forward `shuffle_orders` draw stays a run-time input (curve ids in device memory)."""
+    RATIOS = (1.0, 0.65, 0.32, 0.16, 0.09)
+
+    def __init__(self, model, B, n_bucket, lt_bucket, cloud_bucket, tok_bucket):
+        from . import tokenizer as tk
+        self.tk, self.model, self.eng = tk, model, model.engine()
+        self.ns = NativeStep(model)          # a private executor: its arena (and the bf16 weights staged in it) is baked into the graph
+        self.tokb = tok_bucket
+        pt = model.ptv3_model
+        self.B, self.N0b, self.Ltb, self.S = B, n_bucket, lt_bucket, pt.num_stages
+        dev = next(model.parameters()).device
+        self.dev = dev
+        inC = pt.embedding.stem.conv.in_channels
+        ratios = list(self.RATIOS) + [self.RATIOS[-1]] * max(0, self.S - len(self.RATIOS))
+        self.bounds = [max(B, min(n_bucket, int(n_bucket * ratios[s]) + B)) for s in range(self.S)]
+        self.cloud_bounds = [max(1, min(self.bounds[s], int(cloud_bucket * ratios[s]) + 1)) for s in range(self.S)]
+        self.fts = torch.zeros((n_bucket, inC), device=dev, dtype=torch.float32)
+        self.txt = torch.zeros((lt_bucket, model.config.action_config.txt_ft_size), device=dev, dtype=torch.float32)
+        self.off0 = torch.zeros(B + 1, device=dev, dtype=torch.int32)
+        self.tok_off = torch.zeros(B + 1, device=dev, dtype=torch.int32)
+        self.curves = torch.zeros((self.S, 4), device=dev, dtype=torch.int32)
+        self.h_small = torch.zeros(2 * (B + 1) + 4 * self.S, dtype=torch.int32).pin_memory()
+        self.graph, self.final, self.sizes, self.h_out = None, None, None, None
+        self.param_epoch = None
+
+    def _stage_inputs(self, batch, perms):
+        """copy this call's inputs into the static buffers (stream-ordered H2D copies from the caller's tensors)"""
+        B, S = self.B, self.S
+        npts = [int(v) for v in batch["npoints_in_batch"]]
+        lens = [int(v) for v in batch["txt_lens"]]
+        N, Lt = sum(npts), sum(lens)
+        h = self.h_small
+        off = 0
+        for i, c in enumerate(npts):
+            h[i] = off
+            off += c
+        h[B] = off
+        off = 0
+        for i, l in enumerate(lens):
+            h[B + 1 + i] = off
+            off += l
+        h[2 * B + 1] = off
+        pt = self.model.ptv3_model
+        curves = [self.tk.CURVE_ID[o] for o in pt.order]
+        for s in range(S):
+            if perms is not None:
+                curves = [curves[int(i)] for i in perms[s]]
+            for r in range(4):
+                h[2 * (B + 1) + 4 * s + r] = curves[r] if r < len(curves) else 0
+        self.off0.copy_(h[: B + 1], non_blocking=True)
+        self.tok_off.copy_(h[B + 1: 2 * (B + 1)], non_blocking=True)
+        self.curves.copy_(h[2 * (B + 1):].view(S, 4), non_blocking=True)
+        self.fts[:N].copy_(batch["pc_fts"], non_blocking=True)
+        self.txt[:Lt].copy_(batch["txt_embeds"], non_blocking=True)
+        return npts, lens
+
+    def _forward_static(self):
+        """tokeniser + native step over the static buffers (this is what gets captured)"""
+        m, pt, eng = self.model, self.model.ptv3_model, self.eng
+        S, B = self.S, self.B
+        static = {"off0": self.off0, "bounds": self.bounds, "cloud_bounds": self.cloud_bounds, "curves_dev": self.curves}
+        pend = self.tk.tokenize_launch(self.fts[:, :3], [1] * B, pt.order, pt.stride, list(pt.enc_patch_size), [[0]] * S, None,
+                                       m.config.action_config.voxel_size, eng.div_mode, need_pairs=False, static=static)
+        stages = self.tk.tokenize_finish(pend)
+        batch = {"pc_fts": self.fts, "txt_embeds": self.txt, "npoints_in_batch": [1] * B, "txt_lens": [1] * B}
+        # host-side token geometry of the bucket: total = Ltb rows, longest list = tokb (the kernels read the real offsets on the device)
+        tok_host = [min(i * self.tokb, self.Ltb) for i in range(B)] + [self.Ltb]
+        final, _ = self.ns.run(batch, stages, self.tok_off, tok_host, False, True, False, False, False, 0)
+        return final, pend.dev_sizes
+
+    def capture(self, batch, perms):
+        from .ops import PARAM_EPOCH
+        self._stage_inputs(batch, perms)
+        # eager warm-up over the static buffers: first-use initialisation inside the library (function attributes, side stream),
+        # arena sizing and bf16 weight staging happen OUTSIDE the capture
+        self._forward_static()
+        self._forward_static()
+        torch.cuda.synchronize()
+        self.graph = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(self.graph):
+            self.final, self.sizes = self._forward_static()
+        self.h_out = torch.empty(self.final.numel() * 2 + self.sizes.numel(), dtype=torch.int32).pin_memory()
+        self.param_epoch = (PARAM_EPOCH[0], sum(p._version for p in self.ns.params))
+
+    def stale(self):
+        from .ops import PARAM_EPOCH
+        return self.param_epoch != (PARAM_EPOCH[0], sum(p._version for p in self.ns.params))
+
+    def __call__(self, batch, perms):
+        """-> final actions (B, 8) float64 on the HOST (pinned), or None when a stage outgrew its bound (caller falls back to eager)"""
+        self._stage_inputs(batch, perms)
+        self.graph.replay()
+        nf = self.final.numel()
+        out_f = self.h_out[: 2 * nf].view(torch.float64)
+        out_f.copy_(self.final.reshape(-1), non_blocking=True)
+        self.h_out[2 * nf:].copy_(self.sizes, non_blocking=True)
+        torch.cuda.current_stream().synchronize()
+        S, B = self.S, self.B
+        sizes = self.h_out[2 * nf:]
+        meta = sizes[: S * 8].view(S, 8)
+        if int(sizes[-1]) != 0:
+            return None
+        offs = sizes[S * 8: S * 8 + S * (B + 1)].view(S, B + 1)
+        for s in range(S):
+            cl = offs[s][1:] - offs[s][:-1]
+            if int(meta[s][0]) > self.bounds[s] or int(cl.max()) > self.cloud_bounds[s]:
+                return None
+        return out_f.view(B, 8).clone()

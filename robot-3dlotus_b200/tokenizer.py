@@ -98,7 +98,7 @@ def tokenize(coord, npoints: List[int], orders, strides, patch_sizes, rows_neede
 
 
 def tokenize_launch(coord, npoints: List[int], orders, strides, patch_sizes, rows_needed, perms=None, grid_size=0.01,
-                    div_mode=0, need_stem=True, need_pairs=True):
+                    div_mode=0, need_stem=True, need_pairs=True, static=None):
     """coord (N,3) fp32 cuda (may be a strided view of pc_fts); npoints: host list of per-cloud counts.
     perms: list of S row permutations (host lists) or None.  Returns [Stage_0 .. Stage_{S-1}].
     Only the serialization rows a stage uses are computed (rows 0..max(rows_needed[s]); row 0 also drives the pooling), and the
@@ -109,6 +109,11 @@ def tokenize_launch(coord, npoints: List[int], orders, strides, patch_sizes, row
     S = len(strides) + 1
     B = len(npoints)
     N0 = int(sum(npoints))
+    if static is not None:
+        # shape-static form (CUDA-graph capture with size buckets): `coord` is a static buffer of `n_upper` rows, the ACTUAL cloud
+        # offsets live in the device tensor static["off0"] (B+1 int32; the point count is read on the device), and the stage tables
+        # are used over static["bounds"][s] rows; no host copy, no size read-back
+        N0 = int(coord.shape[0])
     i32 = dict(device=dev, dtype=torch.int32)
     coordc = coord if coord.is_contiguous() else coord.contiguous()
 
@@ -116,11 +121,14 @@ def tokenize_launch(coord, npoints: List[int], orders, strides, patch_sizes, row
     for c in npoints:
         off0.append(off0[-1] + int(c))
     cloud_off_all = torch.empty((S, B + 1), **i32)
-    cloud_off_all[0].copy_(torch.tensor(off0, dtype=torch.int32), non_blocking=True)
+    if static is not None:
+        cloud_off_all[0].copy_(static["off0"])
+    else:
+        cloud_off_all[0].copy_(torch.tensor(off0, dtype=torch.int32), non_blocking=True)
     meta = torch.zeros((S, META_STRIDE), **i32)
     scratch = torch.empty(4 * (B + 2) + 8, **i32)
     err = torch.zeros(1, **i32)
-    max_cloud = max(npoints)
+    max_cloud = max(npoints) if static is None else int(static["cloud_bounds"][0])
     hash_cap = _next_pow2(2 * N0)
     pair_scratch = torch.empty(27 * ((N0 + 1023) // 1024 + 1), **i32)
     hkeys = torch.empty(hash_cap, device=dev, dtype=torch.int64)
@@ -129,7 +137,10 @@ def tokenize_launch(coord, npoints: List[int], orders, strides, patch_sizes, row
     stages: List[Stage] = []
     grid = torch.empty((N0, 3), **i32)
     batch = torch.empty(N0, **i32)
-    L.lotus_grid_coord(_p(coordc), N0, grid_size, div_mode, _p(grid), _p(meta[0]), _p(scratch), st)
+    if static is not None:
+        L.lotus_grid_coord_n(_p(coordc), N0, _p(cloud_off_all[0][B:]), grid_size, div_mode, _p(grid), _p(meta[0]), _p(scratch), st)
+    else:
+        L.lotus_grid_coord(_p(coordc), N0, grid_size, div_mode, _p(grid), _p(meta[0]), _p(scratch), st)
     L.lotus_batch_ids(_p(cloud_off_all[0]), B, _p(batch), st)
     curves = [CURVE_ID[o] for o in orders]
     R = len(curves)
@@ -142,8 +153,13 @@ def tokenize_launch(coord, npoints: List[int], orders, strides, patch_sizes, row
         stg.inverse = torch.empty((R, N0), **i32)
         cv = (ctypes.c_int32 * 4)(*(curves + [0] * (4 - R)))
         nrows = min(R, max([0] + list(rows_needed[s])) + 1)
-        L.lotus_serialize(_p(grid), _p(batch), _p(stg.cloud_off), B, N0, max_cloud, _p(meta[s]), cv, nrows, N0, _p(stg.code),
-                          _p(stg.order), _p(stg.inverse), _p(err), st)
+        if static is not None and static.get("curves_dev") is not None:
+            # graph replay: this forward's shuffled curve ids are read from the static device array (S, 4)
+            L.lotus_serialize_dev(_p(grid), _p(batch), _p(stg.cloud_off), B, N0, max_cloud, _p(meta[s]), _p(static["curves_dev"][s]), nrows, N0,
+                                  _p(stg.code), _p(stg.order), _p(stg.inverse), _p(err), st)
+        else:
+            L.lotus_serialize(_p(grid), _p(batch), _p(stg.cloud_off), B, N0, max_cloud, _p(meta[s]), cv, nrows, N0, _p(stg.code),
+                              _p(stg.order), _p(stg.inverse), _p(err), st)
         # sparse-conv neighbourhoods (hash built once per stage, probed for k=3 and, at stage 0, k=5)
         stg.nbr3 = torch.empty((27, N0), **i32)
         L.lotus_neighbor_table(_p(grid), _p(batch), _p(meta[s]), N0, 3, _p(hkeys), _p(hvals), hash_cap, 1, _p(stg.nbr3), N0, st)
@@ -180,8 +196,17 @@ def tokenize_launch(coord, npoints: List[int], orders, strides, patch_sizes, row
             stg._next = (cluster, head, seg_ptr)
             grid, batch = nxt_grid, nxt_batch
 
-    # ---- data-dependent sizes: one asynchronous copy into pinned memory + an event (the only host sync of the forward)
     dev_sizes = torch.cat([meta.reshape(-1), cloud_off_all.reshape(-1), err])
+    if static is not None:
+        for s_, stg in enumerate(stages):
+            nxt = getattr(stg, "_next", None)
+            L.lotus_stage_sanitize(_p(meta[s_]), int(static["bounds"][s_]), _p(stg.nbr3), N0, _p(stg.nbr5) if stg.nbr5 is not None else None,
+                                   _p(nxt[0]) if nxt is not None else None, _p(meta[s_ + 1]) if nxt is not None else None,
+                                   int(static["bounds"][s_ + 1]) if nxt is not None else 0, _p(nxt[2]) if nxt is not None else None, st)
+        pend = PendingTokens()
+        pend.stages, pend.S, pend.B, pend.static, pend.dev_sizes = stages, S, B, static, dev_sizes
+        return pend
+    # ---- data-dependent sizes: one asynchronous copy into pinned memory + an event (the only host sync of the forward)
     pend = PendingTokens()
     pend.host = torch.empty(dev_sizes.shape, dtype=dev_sizes.dtype, pin_memory=True)
     pend.host.copy_(dev_sizes, non_blocking=True)
@@ -198,8 +223,33 @@ def tokenize_launch(coord, npoints: List[int], orders, strides, patch_sizes, row
     return pend
 
 
+def tokenize_finish_static(pend):
+    """shape-static tokenisation: every stage is used over its bucket bound (rows past the actual count are inert, see
+    lotus_stage_sanitize); the actual sizes stay on the device in `pend.dev_sizes` (meta, cloud offsets, error flag)"""
+    stages, S, B, st = pend.stages, pend.S, pend.B, pend.static
+    for s, stg in enumerate(stages):
+        nb = int(st["bounds"][s])
+        stg.n, stg.depth = nb, -1
+        cb = int(st["cloud_bounds"][s])
+        stg.cloud_off_host = [0, cb] + [cb] * (B - 1)           # only max_cloud is derived from it
+        stg.grid, stg.batch = stg.grid[:nb], stg.batch[:nb]
+        for pl in stg.plans.values():
+            K = pl.max_len
+            pl.n_pad, pl.n_patches = min(nb + B * K, pl.gather_idx.numel()), min(nb // K + B + 1, pl.cu_seqlens.numel() - 1)
+            pl.slot_of_point, pl.unpad = pl.slot_of_point[:nb], pl.unpad[:nb]
+        if s > 0:
+            cluster, head, seg_ptr = stages[s - 1]._next
+            stg.cluster = cluster[: stages[s - 1].n]
+            stg.head = head[:nb]
+            stg.seg_ptr = seg_ptr[: nb + 1]
+            stg.member = stages[s - 1].order[0]
+    return stages
+
+
 def tokenize_finish(pend):
     """wait for the size copy of `tokenize_launch`, slice the tables to their true extents -> [Stage_0 .. Stage_{S-1}]"""
+    if getattr(pend, "static", None) is not None:
+        return tokenize_finish_static(pend)
     pend.event.synchronize()
     stages, S, B, host = pend.stages, pend.S, pend.B, pend.host
     meta_h = host[: S * META_STRIDE].view(S, META_STRIDE).tolist()

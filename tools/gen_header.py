@@ -18,10 +18,13 @@ DOC = {
     "lotus_grid_coord": "Replaces Point.serialization grid step: models/PointTransformerV3/model.py:96-103 "
                         "(grid = trunc((coord-min_over_batch)/grid_size), depth = bit_length(max)). mode 0 = true "
                         "division (torch CPU kernel), 1 = multiply by reciprocal (torch CUDA kernel). meta[0]=n, meta[1]=depth.",
+    "lotus_grid_coord_n": "lotus_grid_coord with the point count read on the device (shape-static launch for CUDA-graph replay with size buckets): model.py:96-103.",
+    "lotus_stage_sanitize": "Graph-replay support (train/train_simple_policy.py:202-243 / evaluation/eval_simple_policy.py:316-321 hot loops; SURVEY §8f row 1): makes the table rows between a stage's actual size and its bucket bound inert.",
     "lotus_batch_ids": "Replaces offset2batch: model.py:37-42.",
     "lotus_serialize": "Replaces serialization.encode x4 + argsort + inverse scatter (+ shuffle_orders row permutation): "
                        "serialization/default.py:10-27, z_order.py:66-101, hilbert.py:91-198, model.py:117-138. "
                        "curve_of_row: 0 z, 1 z-trans, 2 hilbert, 3 hilbert-trans (row r of the outputs uses that curve).",
+    "lotus_serialize_dev": "lotus_serialize with the rows' curve ids read from device memory (the shuffle_orders draw stays a run-time input of a captured CUDA graph): model.py:117-138.",
     "lotus_pool_structure": "Replaces the integer half of SerializedPooling.forward: model.py:713-755,766-771 "
                             "(code>>3, unique -> cluster, CSR over the code-sorted order, head attributes, pooled depth/offsets).",
     "lotus_patch_plan": "Replaces SerializedAttention.get_padding_and_inverse and the order[pad] / unpad[inverse] "
