@@ -134,6 +134,74 @@ __device__ __forceinline__ void stage_row_copy(const __nv_bfloat16* __restrict__
 }
 
 
+// ------------------------------------------------------------------------------------------------ coalesced gather / scatter
+// The gathered tiles are 128 rows x 128 bytes.  With one row per lane every warp-level load touches 32 different lines = 32 L1TEX
+// wavefronts, and the phase stamps (lotus_attn_debug_buffer) showed the kernels bound by exactly that.  Here LPR = HG*DHP/8 lanes
+// cover ONE row (lane = 16-byte chunk), so a warp instruction touches 32/LPR lines; the per-head LayerNorm statistics are formed by
+// shuffles inside the DHP/8 lanes that hold a head.
+template <int DHP, int HG, int NT>
+struct Coal {
+  static constexpr int LPR = HG * DHP / 8;        // lanes per row
+  static constexpr int RPP = NT / LPR;            // rows per pass of the CTA
+  static constexpr int RPT = 128 / RPP;           // passes = rows per thread
+  static constexpr int GL = DHP / 8;              // lanes per head
+};
+// source rows (points) of this thread's RPT tile rows; -1 for rows beyond the patch
+template <int DHP, int HG, int NT>
+__device__ __forceinline__ void coal_rows(const int32_t* __restrict__ gidx, int len, int t, int* pts) {
+  using C = Coal<DHP, HG, NT>;
+#pragma unroll
+  for (int i = 0; i < C::RPT; ++i) { const int row = t / C::LPR + i * C::RPP; pts[i] = row < len ? gidx[row] : -1; }
+}
+// issue the loads of this thread's chunks of a gathered tensor (rows `pts`, columns col0 + head * Dh + chunk * 8) into registers
+template <int DHP, int HG, int NT>
+__device__ __forceinline__ void coal_load(const __nv_bfloat16* __restrict__ base, int64_t ld, int col0, const int* pts, int nh, int Dh, int t, uint4* regs) {
+  using C = Coal<DHP, HG, NT>;
+  const int ch = t % C::LPR, j = ch / C::GL, c = ch % C::GL;
+#pragma unroll
+  for (int i = 0; i < C::RPT; ++i) {
+    regs[i] = make_uint4(0, 0, 0, 0);
+    if (pts[i] >= 0 && j < nh && c * 8 < Dh) regs[i] = *(const uint4*)(base + (int64_t)pts[i] * ld + col0 + j * Dh + c * 8);
+  }
+}
+// registers -> (optional per-head LayerNorm) -> K-major SWIZZLE_128B tile
+template <int DHP, int HG, int NT>
+__device__ __forceinline__ void coal_store(const uint4* regs, const int* pts, int nh, int Dh, const float* __restrict__ sg, const float* __restrict__ sb, int t,
+                                           uint8_t* tile) {
+  using C = Coal<DHP, HG, NT>;
+  const int ch = t % C::LPR, j = ch / C::GL, c = ch % C::GL;
+  const bool col_ok = j < nh && c * 8 < Dh;
+#pragma unroll
+  for (int i = 0; i < C::RPT; ++i) {
+    const int row = t / C::LPR + i * C::RPP;
+    uint4 w = regs[i];
+    if (sg != nullptr) {
+      const bool on = pts[i] >= 0 && col_ok;
+      float x[8];
+      const __nv_bfloat162* h2 = (const __nv_bfloat162*)&regs[i];
+#pragma unroll
+      for (int e = 0; e < 4; ++e) { float2 f = __bfloat1622float2(h2[e]); x[2 * e] = f.x; x[2 * e + 1] = f.y; }
+      float sum = 0.f;
+#pragma unroll
+      for (int e = 0; e < 8; ++e) sum += x[e];
+#pragma unroll
+      for (int o = C::GL >> 1; o > 0; o >>= 1) sum += __shfl_xor_sync(0xffffffffu, sum, o);
+      const float mu = sum / (float)Dh;
+      float q = 0.f;
+#pragma unroll
+      for (int e = 0; e < 8; ++e) { const float d = on ? x[e] - mu : 0.f; q += d * d; }
+#pragma unroll
+      for (int o = C::GL >> 1; o > 0; o >>= 1) q += __shfl_xor_sync(0xffffffffu, q, o);
+      const float rs = rsqrtf(q / (float)Dh + 1e-6f);
+      float y[8];
+#pragma unroll
+      for (int e = 0; e < 8; ++e) y[e] = on ? (x[e] - mu) * rs * sg[c * 8 + e] + sb[c * 8 + e] : 0.f;
+      w.x = pack2(y[0], y[1]); w.y = pack2(y[2], y[3]); w.z = pack2(y[4], y[5]); w.w = pack2(y[6], y[7]);
+    }
+    *(uint4*)(tile + row * 128 + ((ch ^ (row & 7)) << 4)) = w;
+  }
+}
+
 // ------------------------------------------------------------------------------------------------ forward softmax passes
 struct RowCtx {
   uint32_t lane_addr; int len, r, j; float sl2;
@@ -208,7 +276,8 @@ struct FwdSmem {
   static constexpr int AFF_OFF = MISC_OFF + 64;                  // float[4][DHP]: q gamma, q beta, k gamma, k beta
   static constexpr int GRID_OFF = AFF_OFF + 4 * DHP * 4;         // int[128][3]
   static constexpr int TAB_OFF = GRID_OFF + 1536;                // float[MAX_TAB][HG]
-  static constexpr int TOTAL = TAB_OFF + MAX_TAB * HG * 4 + 1024;
+  static constexpr int PT_OFF = TAB_OFF + MAX_TAB * HG * 4;      // int[128]: destination point of every REAL query row (-1: dead / alias slot)
+  static constexpr int TOTAL = PT_OFF + 512 + 1024;
 };
 
 template <int DHP, int HG>
@@ -222,6 +291,9 @@ __global__ void __launch_bounds__(128 * HG, 2) k_pattn_fwd(const Args a) {
   float* sAff = (float*)(smem + L::AFF_OFF);
   int* sGrid = (int*)(smem + L::GRID_OFF);
   float* sTab = (float*)(smem + L::TAB_OFF);
+  int* sPt = (int*)(smem + L::PT_OFF);
+  constexpr int NT = 128 * HG;
+  using C = Coal<DHP, HG, NT>;
 
   const int p = blockIdx.x, h0 = blockIdx.y * HG;
   const int s0 = a.cu[p], len = a.cu[p + 1] - s0;
@@ -240,37 +312,32 @@ __global__ void __launch_bounds__(128 * HG, 2) k_pattn_fwd(const Args a) {
   const int ntab = has_rpe ? 3 * (2 * a.pos_bnd + 1) : 0;
   for (int i = t; i < ntab * HG; i += 128 * HG) { int row = i / HG, j = i - row * HG; sTab[i] = (j < nh) ? a.rpe_table[row * a.H + h0 + j] : 0.f; }
   const bool live = r < len;
-  const int pt = live ? a.gather_idx[s0 + r] : 0;
-  // ---- gather: Q rows by threads 0-127, K rows by threads 128-255 (HG == 2), V split by head.  The loads are issued first, the
-  // barrier that publishes the LayerNorm parameters comes after, then normalise + store.
-  uint4 rq[HG * (DHP / 8)], rk[HG == 1 ? DHP / 8 : 1];
-  const bool real_q = live && a.slot_of_point[pt] == s0 + r;     // alias slots of a padded tail are keys only (consumed in the epilogue)
-  if (HG == 2) {
-    if (hf == 0) load_row<DHP, HG>(a.q + (int64_t)pt * a.ldq + h0 * Dh, live, nh, Dh, rq);
-    else load_row<DHP, HG>(a.k + (int64_t)pt * a.ldk + h0 * Dh, live, nh, Dh, rq);
-    stage_row_copy<DHP>(a.v + (int64_t)pt * a.ldv + (h0 + hf) * Dh, live && hf < nh, Dh, r, sV, hf * (DHP / 8));
-  } else {
-    load_row<DHP, HG>(a.q + (int64_t)pt * a.ldq + h0 * Dh, live, nh, Dh, rq);
-    load_row<DHP, HG>(a.k + (int64_t)pt * a.ldk + h0 * Dh, live, nh, Dh, rk);
-    stage_row_copy<DHP>(a.v + (int64_t)pt * a.ldv + h0 * Dh, live, Dh, r, sV, 0);
+  // ---- gather, coalesced (8 lanes per 128-byte row): all three tensors' loads are issued first, the barrier that publishes the
+  // LayerNorm parameters comes after, then normalise + store.  In parallel, thread r < 128 resolves where query row r goes.
+  int pts[C::RPT];
+  coal_rows<DHP, HG, NT>(a.gather_idx + s0, len, t, pts);
+  uint4 rq[C::RPT], rk[C::RPT], rv[C::RPT];
+  coal_load<DHP, HG, NT>(a.q, a.ldq, h0 * Dh, pts, nh, Dh, t, rq);
+  coal_load<DHP, HG, NT>(a.k, a.ldk, h0 * Dh, pts, nh, Dh, t, rk);
+  coal_load<DHP, HG, NT>(a.v, a.ldv, h0 * Dh, pts, nh, Dh, t, rv);
+  if (hf == 0) {
+    const int pt = live ? a.gather_idx[s0 + r] : 0;
+    const bool real_q = live && a.slot_of_point[pt] == s0 + r;   // alias slots of a padded tail are keys only
+    sPt[r] = real_q ? pt : -1;
+    if (has_rpe && live) { sGrid[r * 3] = a.grid[pt * 3]; sGrid[r * 3 + 1] = a.grid[pt * 3 + 1]; sGrid[r * 3 + 2] = a.grid[pt * 3 + 2]; }
   }
-  if (has_rpe && live && hf == 0) { sGrid[r * 3] = a.grid[pt * 3]; sGrid[r * 3 + 1] = a.grid[pt * 3 + 1]; sGrid[r * 3 + 2] = a.grid[pt * 3 + 2]; }
-  if (has_ln && t >= 128 * HG - DHP) {                            // LayerNorm parameters -> shared memory, AFTER this warp's row loads are in flight
-    const int d = t - (128 * HG - DHP);
+  if (has_ln && t >= NT - DHP) {                                   // LayerNorm parameters -> shared memory, AFTER this warp's row loads are in flight
+    const int d = t - (NT - DHP);
     const bool ok = d < Dh;
     sAff[d] = ok ? a.qg[d] : 0.f; sAff[DHP + d] = ok ? a.qb[d] : 0.f;
     sAff[2 * DHP + d] = ok ? a.kg[d] : 0.f; sAff[3 * DHP + d] = ok ? a.kb[d] : 0.f;
   }
-  if (a.dbg != nullptr && t == 0 && pt >= 0) a.dbg[(blockIdx.x + gridDim.x * blockIdx.y) * 8 + 6] = clock64();
+  if (a.dbg != nullptr && t == 0 && pts[0] >= -1) a.dbg[(blockIdx.x + gridDim.x * blockIdx.y) * 8 + 6] = clock64();
   if (has_ln) __syncthreads();                                   // the affine parameters are in shared memory
   PTS(7);
-  if (HG == 2) {
-    if (hf == 0) ln_store_row<DHP, HG>(rq, live, nh, Dh, has_ln ? sAff : nullptr, sAff + DHP, r, sQ);
-    else ln_store_row<DHP, HG>(rq, live, nh, Dh, has_ln ? sAff + 2 * DHP : nullptr, sAff + 3 * DHP, r, sK);
-  } else {
-    ln_store_row<DHP, HG>(rq, live, nh, Dh, has_ln ? sAff : nullptr, sAff + DHP, r, sQ);
-    ln_store_row<DHP, HG>(rk, live, nh, Dh, has_ln ? sAff + 2 * DHP : nullptr, sAff + 3 * DHP, r, sK);
-  }
+  coal_store<DHP, HG, NT>(rq, pts, nh, Dh, has_ln ? sAff : nullptr, sAff + DHP, t, sQ);
+  coal_store<DHP, HG, NT>(rk, pts, nh, Dh, has_ln ? sAff + 2 * DHP : nullptr, sAff + 3 * DHP, t, sK);
+  coal_store<DHP, HG, NT>(rv, pts, nh, Dh, nullptr, nullptr, t, sV);
   fence_proxy_async();
   tc_fence_before();
   __syncthreads();
@@ -340,28 +407,36 @@ __global__ void __launch_bounds__(128 * HG, 2) k_pattn_fwd(const Args a) {
   mbar_wait_hot(&bars[1], 0);
   tc_fence_after();
   PTS(4);
+  // ---- epilogue: row r of head j -> normalised bf16 -> staging tile (over the dead V tile) -> coalesced scatter to the real rows
+  uint8_t* sO = sV;
   if (act) {
     constexpr int NLD = (DHP + 31) / 32;
     uint32_t o[NLD * 32];
 #pragma unroll
     for (int c = 0; c < NLD; ++c) tmem_ld_32x32b_x32(lane_addr + (uint32_t)(j * DHP + c * 32), o + c * 32);
     tmem_ld_wait();
-    if (live) {
-      a.lse[(int64_t)(s0 + r) * a.H + h0 + j] = (m + lg2_approx(l)) * 0.6931471805599453f;
-      if (real_q) {                                              // alias slots of a padded tail are keys only
-        const float inv = 1.f / l;
-        uint4* go = (uint4*)(a.out + (int64_t)pt * a.ldo + (h0 + j) * Dh);
+    if (live) a.lse[(int64_t)(s0 + r) * a.H + h0 + j] = (m + lg2_approx(l)) * 0.6931471805599453f;
+    const float inv = 1.f / l;
 #pragma unroll
-        for (int c = 0; c < DHP / 8; ++c) {
-          if (c * 8 < Dh) {
-            uint4 w;
-            w.x = pack2(__uint_as_float(o[c * 8 + 0]) * inv, __uint_as_float(o[c * 8 + 1]) * inv);
-            w.y = pack2(__uint_as_float(o[c * 8 + 2]) * inv, __uint_as_float(o[c * 8 + 3]) * inv);
-            w.z = pack2(__uint_as_float(o[c * 8 + 4]) * inv, __uint_as_float(o[c * 8 + 5]) * inv);
-            w.w = pack2(__uint_as_float(o[c * 8 + 6]) * inv, __uint_as_float(o[c * 8 + 7]) * inv);
-            go[c] = w;
-          }
-        }
+    for (int c = 0; c < DHP / 8; ++c) {
+      uint4 w;
+      w.x = pack2(__uint_as_float(o[c * 8 + 0]) * inv, __uint_as_float(o[c * 8 + 1]) * inv);
+      w.y = pack2(__uint_as_float(o[c * 8 + 2]) * inv, __uint_as_float(o[c * 8 + 3]) * inv);
+      w.z = pack2(__uint_as_float(o[c * 8 + 4]) * inv, __uint_as_float(o[c * 8 + 5]) * inv);
+      w.w = pack2(__uint_as_float(o[c * 8 + 6]) * inv, __uint_as_float(o[c * 8 + 7]) * inv);
+      *(uint4*)(sO + r * 128 + (((j * (DHP / 8) + c) ^ (r & 7)) << 4)) = w;
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  {
+    const int ch = t % C::LPR, jj = ch / C::GL, c = ch % C::GL;
+    if (jj < nh && c * 8 < Dh) {
+#pragma unroll
+      for (int i = 0; i < C::RPT; ++i) {
+        const int row = t / C::LPR + i * C::RPP;
+        const int dst = sPt[row];
+        if (dst >= 0) *(uint4*)(a.out + (int64_t)dst * a.ldo + (h0 + jj) * Dh + c * 8) = *(const uint4*)(sO + row * 128 + ((ch ^ (row & 7)) << 4));
       }
     }
   }
@@ -402,10 +477,15 @@ struct BwdSmem {
   static constexpr int AFF_OFF = LSE_OFF + 2 * HG * 128 * 4;     // float[4][DHP]
   static constexpr int GRID_OFF = AFF_OFF + 4 * DHP * 4;         // int[128][3]
   static constexpr int TAB_OFF = GRID_OFF + 1536;                // float[MAX_TAB][HG] table, then float[MAX_TAB][HG] table gradient
-  static constexpr int RED_OFF = TAB_OFF + 2 * MAX_TAB * HG * 4; // float[8 HG warps][2][NV] affine-gradient partials
-  static constexpr int NV = DHP < 32 ? 32 : DHP;
-  static constexpr int HQ_OFF = RED_OFF + 8 * HG * 2 * NV * 4;   // uint32[HG][128] dropout row hashes (one per head and query)
-  static constexpr int TOTAL = HQ_OFF + HG * 128 * 4 + 1024;
+  static constexpr int HQ_OFF = TAB_OFF + 2 * MAX_TAB * HG * 4;  // uint32[HG][128] dropout row hashes (one per head and query)
+  static constexpr int ROW_OFF = HQ_OFF + HG * 128 * 4;          // int[128] point of every live row (-1: dead), int[128] 1 = real slot / 0 = alias slot
+  static constexpr int TOTAL = ROW_OFF + 1024 + 1024;
+  // epilogue overlays (every operand tile is dead once the phase-B MMAs have completed):
+  //   V tile   -> dV rows, bf16, K-major swizzled like the operand tiles
+  //   P^T tile -> dK-hat rows (gradient w.r.t. the NORMALISED k), fp32 [128][HG * DHP], 16-byte chunks swizzled by (row & 7)
+  //   dS^T tile-> dQ-hat rows, same layout
+  //   Q tile   -> float[warps][4][HG * DHP] LayerNorm affine-gradient partials
+  static_assert((8 * HG) * 4 * HG * DHP * 4 <= 16384, "affine partials must fit the Q tile");
 };
 
 // sum over the 32 lanes of a warp of v[0..31]: lane L ends up with the total of element L (31 shuffles instead of 160)
@@ -423,51 +503,73 @@ __device__ __forceinline__ float warp_transpose_sum32(float* v, int lane) {
   return v[0];
 }
 
-// LayerNorm backward of one head of one row: dy (gradient w.r.t. the normalised + affine output, fp32, DHP values) -> dx (gradient
-// w.r.t. the raw row); accumulates this row's dgamma / dbeta contributions into ag / ab.
-template <int DHP>
-__device__ __forceinline__ void ln_bwd_row(const uint4* xraw, int Dh, const float* __restrict__ sg, float* dy, float* ag, float* ab) {
-  float x[DHP];
+// LayerNorm backward of one 8-channel chunk of one (row, head); the GL lanes that hold the head cooperate through shuffles.
+// xraw: the raw chunk, dy: gradient w.r.t. the normalised + affine output (in) -> gradient w.r.t. the raw values (out);
+// this lane's dgamma / dbeta contributions are accumulated into ag / ab.  All 32 lanes must call it (`on` masks rows / chunks).
+template <int GL>
+__device__ __forceinline__ void ln_bwd_chunk(const uint4& xraw, bool on, int Dh, const float* __restrict__ sg8, float* dy, float* ag, float* ab) {
+  float x[8];
+  const __nv_bfloat162* h2 = (const __nv_bfloat162*)&xraw;
 #pragma unroll
-  for (int c = 0; c < DHP / 8; ++c) {
-    const __nv_bfloat162* h2 = (const __nv_bfloat162*)&xraw[c];
-#pragma unroll
-    for (int e = 0; e < 4; ++e) { float2 f = __bfloat1622float2(h2[e]); x[c * 8 + 2 * e] = f.x; x[c * 8 + 2 * e + 1] = f.y; }
-  }
+  for (int e = 0; e < 4; ++e) { float2 f = __bfloat1622float2(h2[e]); x[2 * e] = f.x; x[2 * e + 1] = f.y; }
   float s = 0.f;
 #pragma unroll
-  for (int d = 0; d < DHP; ++d) s += (d < Dh) ? x[d] : 0.f;
+  for (int e = 0; e < 8; ++e) s += on ? x[e] : 0.f;
+#pragma unroll
+  for (int o = GL >> 1; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
   const float mu = s / (float)Dh;
   float qv = 0.f;
 #pragma unroll
-  for (int d = 0; d < DHP; ++d) { float t = (d < Dh) ? x[d] - mu : 0.f; qv += t * t; }
+  for (int e = 0; e < 8; ++e) { const float d = on ? x[e] - mu : 0.f; qv += d * d; }
+#pragma unroll
+  for (int o = GL >> 1; o > 0; o >>= 1) qv += __shfl_xor_sync(0xffffffffu, qv, o);
   const float rs = rsqrtf(qv / (float)Dh + 1e-6f);
   float s1 = 0.f, s2 = 0.f;
 #pragma unroll
-  for (int d = 0; d < DHP; ++d) {
-    const float xh = (d < Dh) ? (x[d] - mu) * rs : 0.f;
-    const float g = (d < Dh) ? dy[d] * sg[d] : 0.f;
-    ag[d] += (d < Dh) ? dy[d] * xh : 0.f;
-    ab[d] += (d < Dh) ? dy[d] : 0.f;
+  for (int e = 0; e < 8; ++e) {
+    const float xh = on ? (x[e] - mu) * rs : 0.f;
+    const float d = on ? dy[e] : 0.f;
+    const float g = d * sg8[e];
+    ag[e] += d * xh;
+    ab[e] += d;
     s1 += g; s2 += g * xh;
-    x[d] = xh;
+    x[e] = xh; dy[e] = g;
   }
+#pragma unroll
+  for (int o = GL >> 1; o > 0; o >>= 1) { s1 += __shfl_xor_sync(0xffffffffu, s1, o); s2 += __shfl_xor_sync(0xffffffffu, s2, o); }
   s1 /= (float)Dh; s2 /= (float)Dh;
 #pragma unroll
-  for (int d = 0; d < DHP; ++d) dy[d] = (d < Dh) ? rs * (dy[d] * sg[d] - s1 - x[d] * s2) : 0.f;
+  for (int e = 0; e < 8; ++e) dy[e] = on ? rs * (dy[e] - s1 - x[e] * s2) : 0.f;
 }
 
-template <int DHP>
-__device__ __forceinline__ void store_row_bf16(__nv_bfloat16* dst, const float* v, int Dh) {
+// TMEM columns [col, col + ncols) of this thread's lane -> fp32 staging row (16-byte chunks c0 .., swizzled by the row)
+template <int NCOLS>
+__device__ __forceinline__ void tmem_to_stage_f32(uint32_t taddr, uint8_t* stage_row, int c0, int r) {
 #pragma unroll
-  for (int c = 0; c < DHP / 8; ++c) {
-    if (c * 8 < Dh) {
-      uint4 w;
-      w.x = pack2(v[c * 8 + 0], v[c * 8 + 1]); w.y = pack2(v[c * 8 + 2], v[c * 8 + 3]);
-      w.z = pack2(v[c * 8 + 4], v[c * 8 + 5]); w.w = pack2(v[c * 8 + 6], v[c * 8 + 7]);
-      *(uint4*)(dst + c * 8) = w;
+  for (int b = 0; b < NCOLS / 16; ++b) {
+    uint32_t o[16];
+    tmem_ld_32x32b_x16(taddr + b * 16, o);
+    tmem_ld_wait();
+#pragma unroll
+    for (int c = 0; c < 4; ++c) {
+      const int ch = c0 + b * 4 + c;
+      *(uint4*)(stage_row + (((ch & ~7) | ((ch ^ r) & 7)) << 4)) = make_uint4(o[c * 4], o[c * 4 + 1], o[c * 4 + 2], o[c * 4 + 3]);
     }
   }
+}
+// one 8-float chunk `ch` of staging row `row` (row pitch W floats)
+template <int W>
+__device__ __forceinline__ void stage_read8(const uint8_t* stage, int row, int ch, float* v) {
+  const uint8_t* rp = stage + row * (W * 4);
+  const int c0 = 2 * ch, c1 = 2 * ch + 1;
+  const float4 a = *(const float4*)(rp + (((c0 & ~7) | ((c0 ^ row) & 7)) << 4));
+  const float4 b = *(const float4*)(rp + (((c1 & ~7) | ((c1 ^ row) & 7)) << 4));
+  v[0] = a.x; v[1] = a.y; v[2] = a.z; v[3] = a.w; v[4] = b.x; v[5] = b.y; v[6] = b.z; v[7] = b.w;
+}
+__device__ __forceinline__ uint4 pack8(const float* v) {
+  uint4 w;
+  w.x = pack2(v[0], v[1]); w.y = pack2(v[2], v[3]); w.z = pack2(v[4], v[5]); w.w = pack2(v[6], v[7]);
+  return w;
 }
 
 // score-gradient pass of one thread: key row r of head j against queries q0 .. q0 + 63 (rolled 16-column steps)
@@ -525,7 +627,8 @@ __device__ __forceinline__ void score_grad_pass(const ColCtx& c, uint8_t* sPTrow
 template <int DHP, int HG>
 __global__ void __launch_bounds__(256 * HG, 1) k_pattn_bwd(const Args a) {
   using L = BwdSmem<DHP, HG>;
-  constexpr int NV = L::NV, NT = 256 * HG;
+  constexpr int NT = 256 * HG, W = HG * DHP;
+  using C = Coal<DHP, HG, NT>;
   extern __shared__ __align__(1024) uint8_t smem_raw[];
   uint8_t* smem = smem_raw + ((1024u - (tc::smem_u32(smem_raw) & 1023u)) & 1023u);   // 1024-byte aligned, still a SHARED-space pointer (LDS / STS, not generic LD / ST)
   uint8_t *sQ = smem + L::Q_OFF, *sK = smem + L::K_OFF, *sV = smem + L::V_OFF, *sdO = smem + L::DO_OFF;
@@ -538,15 +641,16 @@ __global__ void __launch_bounds__(256 * HG, 1) k_pattn_bwd(const Args a) {
   int* sGrid = (int*)(smem + L::GRID_OFF);
   float* sTab = (float*)(smem + L::TAB_OFF);
   float* sDTab = sTab + MAX_TAB * HG;
-  float* sRed = (float*)(smem + L::RED_OFF);
+  float* sRed = (float*)sQ;                                       // epilogue overlay
   uint32_t* sHq = (uint32_t*)(smem + L::HQ_OFF);
+  int* sPt = (int*)(smem + L::ROW_OFF);
+  int* sReal = sPt + 128;
 
   const int p = blockIdx.x, h0 = blockIdx.y * HG;
   const int s0 = a.cu[p], len = a.cu[p + 1] - s0;
   if (len <= 0) return;
   const int nh = min(HG, a.H - h0);
   const int t = threadIdx.x, r = t & 127, hf = (t >> 7) & 1, j = t >> 8, warp = t >> 5, lane = t & 31;
-  const int role = t >> 7;                                       // load-phase role
   const int Dh = a.Dh;
   PTS(0);
   const bool has_ln = a.qg != nullptr, has_rpe = a.rpe_table != nullptr;
@@ -562,61 +666,57 @@ __global__ void __launch_bounds__(256 * HG, 1) k_pattn_bwd(const Args a) {
     sTab[i] = (jj < nh) ? a.rpe_table[row * a.H + h0 + jj] : 0.f;
     sDTab[i] = 0.f;
   }
-  for (int i = t; i < 8 * HG * 2 * NV; i += NT) sRed[i] = 0.f;
   const bool live = r < len;
-  const int pt = live ? a.gather_idx[s0 + r] : 0;
-  const bool real = live && a.slot_of_point[pt] == s0 + r;       // alias slots are keys only: their dO (and so dQ) is zero
-  // ---- gather roles: Q (+LN) | K (+LN) | dO, delta, lse, dropout row hashes | V   (HG == 1: two roles take two jobs each).
-  // Row loads are issued first; the barrier that publishes the LayerNorm parameters follows; then normalise + store.
-  uint4 rrow[HG * (DHP / 8)];
-  const bool ln_role = (HG == 2) ? role < 2 : true;
-  if (ln_role) {
-    if (role == 0) load_row<DHP, HG>(a.q + (int64_t)pt * a.ldq + h0 * Dh, live, nh, Dh, rrow);
-    else load_row<DHP, HG>(a.k + (int64_t)pt * a.ldk + h0 * Dh, live, nh, Dh, rrow);
-  }
-  auto stage_do = [&]() {
-#pragma unroll
-    for (int jj = 0; jj < HG; ++jj) {
-      const bool on = live && jj < nh;                           // (loaded whether or not the slot is real: no dependent load in front)
-      const __nv_bfloat16* go = a.dout + (int64_t)pt * a.ldo + (h0 + jj) * Dh;
-      const __nv_bfloat16* oo = a.out + (int64_t)pt * a.ldo + (h0 + jj) * Dh;
-      float dsum = 0.f;
-#pragma unroll
-      for (int c = 0; c < DHP / 8; ++c) {
-        uint4 g = make_uint4(0, 0, 0, 0), o = make_uint4(0, 0, 0, 0);
-        if (on && c * 8 < Dh) { g = *(const uint4*)(go + c * 8); o = *(const uint4*)(oo + c * 8); }
-        if (!real) g = make_uint4(0, 0, 0, 0);
-        const __nv_bfloat162 *g2 = (const __nv_bfloat162*)&g, *o2 = (const __nv_bfloat162*)&o;
-#pragma unroll
-        for (int e = 0; e < 4; ++e) { float2 x = __bfloat1622float2(g2[e]), y = __bfloat1622float2(o2[e]); dsum = fmaf(x.x, y.x, fmaf(x.y, y.y, dsum)); }
-        *(uint4*)(sdO + r * 128 + (((jj * (DHP / 8) + c) ^ (r & 7)) << 4)) = g;
-      }
-      sDelta[jj * 128 + r] = dsum;
-      // dead query columns: exp2(x - inf) = 0
-      sLse[jj * 128 + r] = (live && jj < nh) ? a.lse[(int64_t)(s0 + r) * a.H + h0 + jj] * 1.4426950408889634f : INFINITY;
-      sHq[jj * 128 + r] = attn_drop_rowhash(a.seed, a.layer_id * 0x9E37u + (uint32_t)(p * a.H + h0 + jj), (uint32_t)r);
+  // ---- gather, coalesced (LPR lanes per 128-byte row): the loads of all five tensors are issued first, the barrier that publishes
+  // the LayerNorm parameters follows, then normalise + store.  Alias slots are keys only: their query column is switched off through
+  // lse = +inf (P^T column 0, dS^T column 0), which is what a zero dO row did before, without a dependent load in front of dO.
+  int pts[C::RPT];
+  coal_rows<DHP, HG, NT>(a.gather_idx + s0, len, t, pts);
+  uint4 rq[C::RPT], rk[C::RPT], rv[C::RPT], rg[C::RPT], ro[C::RPT];
+  coal_load<DHP, HG, NT>(a.q, a.ldq, h0 * Dh, pts, nh, Dh, t, rq);
+  coal_load<DHP, HG, NT>(a.k, a.ldk, h0 * Dh, pts, nh, Dh, t, rk);
+  coal_load<DHP, HG, NT>(a.v, a.ldv, h0 * Dh, pts, nh, Dh, t, rv);
+  coal_load<DHP, HG, NT>(a.dout, a.ldo, h0 * Dh, pts, nh, Dh, t, rg);
+  coal_load<DHP, HG, NT>(a.out, a.ldo, h0 * Dh, pts, nh, Dh, t, ro);
+  if (t < 128 * HG) {                                            // per-row scalars: thread (head jj, row r)
+    const int jj = t >> 7;
+    const int pt = live ? a.gather_idx[s0 + r] : 0;
+    const bool real = live && a.slot_of_point[pt] == s0 + r;
+    if (jj == 0) {
+      sPt[r] = live ? pt : -1;
+      sReal[r] = real ? 1 : 0;
+      if (has_rpe && live) { sGrid[r * 3] = a.grid[pt * 3]; sGrid[r * 3 + 1] = a.grid[pt * 3 + 1]; sGrid[r * 3 + 2] = a.grid[pt * 3 + 2]; }
     }
-  };
-  auto stage_v = [&]() {
-#pragma unroll
-    for (int jj = 0; jj < HG; ++jj)
-      stage_row_copy<DHP>(a.v + (int64_t)pt * a.ldv + (h0 + jj) * Dh, live && jj < nh, Dh, r, sV, jj * (DHP / 8));
-  };
-  if (HG == 2) { if (role == 2) stage_do(); else if (role == 3) stage_v(); }
-  else { if (role == 0) stage_do(); else stage_v(); }
-  if (has_rpe && live && role == 0) { sGrid[r * 3] = a.grid[pt * 3]; sGrid[r * 3 + 1] = a.grid[pt * 3 + 1]; sGrid[r * 3 + 2] = a.grid[pt * 3 + 2]; }
+    // dead and alias query columns: exp2(x - inf) = 0
+    sLse[jj * 128 + r] = (real && jj < nh) ? a.lse[(int64_t)(s0 + r) * a.H + h0 + jj] * 1.4426950408889634f : INFINITY;
+    sHq[jj * 128 + r] = attn_drop_rowhash(a.seed, a.layer_id * 0x9E37u + (uint32_t)(p * a.H + h0 + jj), (uint32_t)r);
+  }
   if (has_ln && t >= NT - DHP) {                            // LayerNorm parameters -> shared memory, AFTER this warp's row loads are in flight
     const int d = t - (NT - DHP);
     const bool ok = d < Dh;
     sAff[d] = ok ? a.qg[d] : 0.f; sAff[DHP + d] = ok ? a.qb[d] : 0.f;
     sAff[2 * DHP + d] = ok ? a.kg[d] : 0.f; sAff[3 * DHP + d] = ok ? a.kb[d] : 0.f;
   }
-  if (a.dbg != nullptr && t == 0 && pt >= 0) a.dbg[(blockIdx.x + gridDim.x * blockIdx.y) * 8 + 6] = clock64();
+  if (a.dbg != nullptr && t == 0 && pts[0] >= -1) a.dbg[(blockIdx.x + gridDim.x * blockIdx.y) * 8 + 6] = clock64();
   if (has_ln) __syncthreads();                                   // the affine parameters are in shared memory
   PTS(7);
-  if (ln_role) {
-    if (role == 0) ln_store_row<DHP, HG>(rrow, live, nh, Dh, has_ln ? sAff : nullptr, sAff + DHP, r, sQ);
-    else ln_store_row<DHP, HG>(rrow, live, nh, Dh, has_ln ? sAff + 2 * DHP : nullptr, sAff + 3 * DHP, r, sK);
+  coal_store<DHP, HG, NT>(rq, pts, nh, Dh, has_ln ? sAff : nullptr, sAff + DHP, t, sQ);
+  coal_store<DHP, HG, NT>(rk, pts, nh, Dh, has_ln ? sAff + 2 * DHP : nullptr, sAff + 3 * DHP, t, sK);
+  coal_store<DHP, HG, NT>(rv, pts, nh, Dh, nullptr, nullptr, t, sV);
+  coal_store<DHP, HG, NT>(rg, pts, nh, Dh, nullptr, nullptr, t, sdO);
+  {                                                              // delta = rowsum(dO * O) per (row, head)
+    const int ch = t % C::LPR, jj = ch / C::GL, c = ch % C::GL;
+#pragma unroll
+    for (int i = 0; i < C::RPT; ++i) {
+      const int row = t / C::LPR + i * C::RPP;
+      const __nv_bfloat162 *g2 = (const __nv_bfloat162*)&rg[i], *o2 = (const __nv_bfloat162*)&ro[i];
+      float dsum = 0.f;
+#pragma unroll
+      for (int e = 0; e < 4; ++e) { float2 x = __bfloat1622float2(g2[e]), y = __bfloat1622float2(o2[e]); dsum = fmaf(x.x, y.x, fmaf(x.y, y.y, dsum)); }
+#pragma unroll
+      for (int o = C::GL >> 1; o > 0; o >>= 1) dsum += __shfl_xor_sync(0xffffffffu, dsum, o);
+      if (c == 0) sDelta[jj * 128 + row] = dsum;
+    }
   }
   fence_proxy_async();
   tc_fence_before();
@@ -691,74 +791,94 @@ __global__ void __launch_bounds__(256 * HG, 1) k_pattn_bwd(const Args a) {
     }
     umma_commit(&bars[1]);
   }
-  // the raw k (key rows) / q (query rows) of the LayerNorm backward: loaded while the MMAs run
-  uint4 xraw[DHP / 8];
-  {
-    const __nv_bfloat16* src = (hf == 0 ? a.k + (int64_t)pt * a.ldk : a.q + (int64_t)pt * a.ldq) + (h0 + j) * Dh;
+  // the raw k / q chunks of the LayerNorm backward (coalesced mapping): loaded while the MMAs run
+  uint4 xk[C::RPT], xq[C::RPT];
+  if (has_ln) {
+    coal_load<DHP, HG, NT>(a.k, a.ldk, h0 * Dh, pts, nh, Dh, t, xk);
+    coal_load<DHP, HG, NT>(a.q, a.ldq, h0 * Dh, pts, nh, Dh, t, xq);
+  } else {
 #pragma unroll
-    for (int c = 0; c < DHP / 8; ++c) {
-      xraw[c] = make_uint4(0, 0, 0, 0);
-      if (j < nh && has_ln && live && c * 8 < Dh) xraw[c] = *(const uint4*)(src + c * 8);
-    }
+    for (int i = 0; i < C::RPT; ++i) { xk[i] = make_uint4(0, 0, 0, 0); xq[i] = make_uint4(0, 0, 0, 0); }
   }
   mbar_wait_hot(&bars[1], 0);
   tc_fence_after();
   PTS(4);
-  // ---- epilogue: (head j, hf 0) = key rows: dV, dK ; (head j, hf 1) = query rows: dQ ; per-head LayerNorm backward in registers
+  // ---- epilogue 1: TMEM -> staging tiles (thread = (head j, row r); the two halves share the dK columns)
+  uint8_t *stV = sV, *stK = sPT, *stQ = sDST;
   if (act) {
-    constexpr int NLD = (DHP + 31) / 32;
-    const int hcol = (h0 + j) * Dh;
-    float ag[NV], ab[NV];                                        // this row's dgamma / dbeta contributions
-#pragma unroll
-    for (int d = 0; d < NV; ++d) { ag[d] = 0.f; ab[d] = 0.f; }
-    uint32_t o[NLD * 32];
+    constexpr int HALF = DHP >= 32 ? DHP / 2 : DHP;
     if (hf == 0) {
+      constexpr int NLD = (DHP + 31) / 32;
+      uint32_t o[NLD * 32];
 #pragma unroll
       for (int c = 0; c < NLD; ++c) tmem_ld_32x32b_x32(lane_addr + (uint32_t)(j * DHP + c * 32), o + c * 32);
       tmem_ld_wait();
-      __nv_bfloat16 *dvp, *dkp;
-      if (real) { dvp = a.dv + (int64_t)pt * a.lddv + hcol; dkp = a.dk + (int64_t)pt * a.lddk + hcol; }
-      else { dkp = a.alias_dkv + (int64_t)(s0 + r) * 2 * (a.H * Dh) + hcol; dvp = dkp + a.H * Dh; }
-      if (live) store_row_bf16<DHP>(dvp, (const float*)o, Dh);
 #pragma unroll
-      for (int c = 0; c < NLD; ++c) tmem_ld_32x32b_x32(lane_addr + (uint32_t)(64 + j * DHP + c * 32), o + c * 32);
-      tmem_ld_wait();
-      if (live) {
-        if (has_ln) ln_bwd_row<DHP>(xraw, Dh, sAff + 2 * DHP, (float*)o, ag, ab);
-        store_row_bf16<DHP>(dkp, (const float*)o, Dh);
-      }
+      for (int c = 0; c < DHP / 8; ++c) *(uint4*)(stV + r * 128 + (((j * (DHP / 8) + c) ^ (r & 7)) << 4)) = pack8((const float*)o + c * 8);
+      tmem_to_stage_f32<HALF>(lane_addr + (uint32_t)(64 + j * DHP), stK + r * (W * 4), j * (DHP / 4), r);
     } else {
-#pragma unroll
-      for (int c = 0; c < NLD; ++c) tmem_ld_32x32b_x32(lane_addr + (uint32_t)(128 + j * DHP + c * 32), o + c * 32);
-      tmem_ld_wait();
-      if (real) {
-        if (has_ln) ln_bwd_row<DHP>(xraw, Dh, sAff, (float*)o, ag, ab);
-        store_row_bf16<DHP>(a.dq + (int64_t)pt * a.lddq + hcol, (const float*)o, Dh);
-      }
-    }
-    if (has_ln && a.dqg != nullptr) {                            // warp transpose-sum: lane d ends up with the warp's total of channel d
-#pragma unroll
-      for (int b0 = 0; b0 < NV; b0 += 32) {
-        const float g = warp_transpose_sum32(ag + b0, lane), bb = warp_transpose_sum32(ab + b0, lane);
-        sRed[(warp * 2 + 0) * NV + b0 + lane] = g;
-        sRed[(warp * 2 + 1) * NV + b0 + lane] = bb;
-      }
+      tmem_to_stage_f32<DHP>(lane_addr + (uint32_t)(128 + j * DHP), stQ + r * (W * 4), j * (DHP / 4), r);
+      if constexpr (HALF < DHP) tmem_to_stage_f32<DHP - HALF>(lane_addr + (uint32_t)(64 + j * DHP + HALF), stK + r * (W * 4), j * (DHP / 4) + HALF / 4, r);
     }
   }
   tc_fence_before();
   __syncthreads();
+  // ---- epilogue 2: coalesced pass (LPR lanes per row): dV copy, LayerNorm backward of dK-hat / dQ-hat, stores to the packed
+  // gradients (real slots) or the alias side buffer (alias slots: dk / dv only)
+  {
+    const int ch = t % C::LPR, jj = ch / C::GL, c = ch % C::GL;
+    const bool col_ok = jj < nh && c * 8 < Dh;
+    const int hcol = (h0 + jj) * Dh + c * 8, Call = a.H * Dh;
+    float agk[8], abk[8], agq[8], abq[8];
+#pragma unroll
+    for (int e = 0; e < 8; ++e) { agk[e] = 0.f; abk[e] = 0.f; agq[e] = 0.f; abq[e] = 0.f; }
+#pragma unroll
+    for (int i = 0; i < C::RPT; ++i) {
+      const int row = t / C::LPR + i * C::RPP;
+      const int pt = pts[i];
+      const bool real = sReal[row] != 0;
+      const bool on_k = pt >= 0 && col_ok, on_q = real && col_ok;
+      __nv_bfloat16 *dvp = nullptr, *dkp = nullptr;
+      if (on_k) {
+        if (real) { dvp = a.dv + (int64_t)pt * a.lddv + hcol; dkp = a.dk + (int64_t)pt * a.lddk + hcol; }
+        else { dkp = a.alias_dkv + (int64_t)(s0 + row) * 2 * Call + hcol; dvp = dkp + Call; }
+        *(uint4*)dvp = *(const uint4*)(stV + row * 128 + ((ch ^ (row & 7)) << 4));
+      }
+      float dy[8];
+      stage_read8<W>(stK, row, ch, dy);
+      if (has_ln) ln_bwd_chunk<C::GL>(xk[i], on_k, Dh, sAff + 2 * DHP + c * 8, dy, agk, abk);
+      if (on_k) *(uint4*)dkp = pack8(dy);
+      stage_read8<W>(stQ, row, ch, dy);
+      if (has_ln) ln_bwd_chunk<C::GL>(xq[i], on_q, Dh, sAff + c * 8, dy, agq, abq);
+      if (on_q) *(uint4*)(a.dq + (int64_t)pt * a.lddq + hcol) = pack8(dy);
+    }
+    if (has_ln && a.dqg != nullptr) {                            // lanes that hold the same chunk: xor-reduce, then one partial row per warp
+#pragma unroll
+      for (int e = 0; e < 8; ++e) {
+#pragma unroll
+        for (int o = C::LPR; o < 32; o <<= 1) {
+          agk[e] += __shfl_xor_sync(0xffffffffu, agk[e], o); abk[e] += __shfl_xor_sync(0xffffffffu, abk[e], o);
+          agq[e] += __shfl_xor_sync(0xffffffffu, agq[e], o); abq[e] += __shfl_xor_sync(0xffffffffu, abq[e], o);
+        }
+      }
+      if (lane < C::LPR) {
+        float* dst = sRed + warp * 4 * W + lane * 8;
+#pragma unroll
+        for (int e = 0; e < 8; ++e) { dst[e] = agk[e]; dst[W + e] = abk[e]; dst[2 * W + e] = agq[e]; dst[3 * W + e] = abq[e]; }
+      }
+    }
+  }
+  __syncthreads();
   PTS(5);
-  // ---- LayerNorm affine gradients: per-warp partials -> one atomic per (parameter, channel) per CTA
-  if (has_ln && a.dqg != nullptr && t < 4 * NV) {
-    const int which = t / NV, d = t - which * NV;                // 0: k gamma, 1: k beta (hf 0 warps), 2: q gamma, 3: q beta (hf 1 warps)
-    const int side = which >> 1, gb = which & 1;
+  // ---- LayerNorm affine gradients: per-warp partials -> one atomic per (parameter, head, channel) per CTA
+  if (has_ln && a.dqg != nullptr && t < 4 * W) {
+    const int which = t / W, col = t - which * W;                // 0: k gamma, 1: k beta, 2: q gamma, 3: q beta
+    const int jj = col / DHP, d = col - jj * DHP;
     float v = 0.f;
 #pragma unroll
-    for (int jj = 0; jj < HG; ++jj)
-#pragma unroll
-      for (int w = 0; w < 4; ++w) v += sRed[(((jj * 2 + side) * 4 + w) * 2 + gb) * NV + d];
+    for (int w = 0; w < NT / 32; ++w) v += sRed[(w * 4 + which) * W + col];
     float* dst = which == 0 ? a.dkg : which == 1 ? a.dkb : which == 2 ? a.dqg : a.dqb;
-    if (d < Dh && v != 0.f) atomicAdd(&dst[d], v);
+    if (jj < nh && d < Dh && v != 0.f) atomicAdd(&dst[d], v);
   }
   if (a.drpe != nullptr && has_rpe) {
     for (int i = t; i < ntab * HG; i += NT) {

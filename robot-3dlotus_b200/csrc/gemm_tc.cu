@@ -49,6 +49,7 @@ struct Params {
   int debug;                   // dev knob (LOTUS_TC_DEBUG): 1 skip epilogue math+store, 2 skip mainloop, 4 no store wait
   int pair_commit;             // one `empty` barrier (and one tcgen05.commit) per PAIR of stages
   int async_arrive;            // gather producers signal `full` with cp.async.mbarrier.arrive.noinc (no wait_group lag)
+  int ldg_gather;              // K-major gather through registers: 8 lanes load one whole 128-byte row (coalesced), then STS
   int stages;                  // smem pipeline depth (2..4): shallow pipelines leave room for several CTAs per SM
   // pair-list mode (sparse-conv weight gradient): blockIdx.z = tap * splits + split, K read from the device
   const int32_t* k_dev;        // [taps] reduction extent per tap, or null
@@ -287,6 +288,30 @@ k_gemm_tc(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUt
           a_r1 = a_row_of(i + 2 * ngrp); b_r1 = b_row_of(i + 2 * ngrp);
           mbar_wait_hot(&empty[PAIR ? (s >> 1) : s], ph ^ 1);
           int kb = kb0 + i;
+          if (p.a_mode == OP_K_GATHER && p.ldg_gather && p.ga.idx_in_smem && p.async_arrive) {
+            // Coalesced gather: EIGHT LANES read one whole 128-byte source row (lane = 16-byte chunk), four rows per warp
+            // instruction, through registers.  With one row per lane (the cp.async form below) every warp instruction touches 32
+            // different lines = 32 L1TEX wavefronts, and the gather -- not the tensor pipe -- sets the k-block rate.
+            const int tp = kb / p.ga.kb_per_tap, c0 = (kb - tp * p.ga.kb_per_tap) * BK;
+            const int ch = t & 7, r0 = (t >> 5) * 32 + ((t & 31) >> 3);
+            uint4 v[8];
+#pragma unroll
+            for (int q = 0; q < 8; ++q) {
+              const int row = r0 + q * 4;
+              const int src_row = sIdx[tp * EPI_THREADS + row];
+              v[q] = make_uint4(0, 0, 0, 0);
+              if (src_row >= 0) v[q] = *(const uint4*)(p.ga.base + (int64_t)src_row * p.ga.row_elems + c0 + ch * 8);
+            }
+            uint8_t* dstt = sA + s * A_BYTES;
+#pragma unroll
+            for (int q = 0; q < 8; ++q) {
+              const int row = r0 + q * 4;
+              *(uint4*)(dstt + row * 128 + ((ch ^ (row & 7)) << 4)) = v[q];
+            }
+            fence_proxy_async();                               // generic-proxy stores -> visible to the MMA's async proxy
+            mbar_arrive(&full[s]);                             // one arrival per producer thread, like the cp.async form
+            continue;
+          }
           if (p.a_mode == OP_K_GATHER) {
             // thread t stages row (m0 + t): 8 chunks of 16 B
             // thread t stages row (m0 + t): 8 chunks of 16 B.  (Measured alternatives, all slower or equal: four whole rows per
@@ -567,6 +592,9 @@ static int launch(const Operand& A, const Operand& B, Params p, int BN, int spli
     static int aa = -1;                                 // dev knob: LOTUS_TC_ASYNC_ARRIVE=0 restores commit/wait_group signalling
     if (aa < 0) { const char* e = getenv("LOTUS_TC_ASYNC_ARRIVE"); aa = e ? atoi(e) : 1; }
     p.async_arrive = aa;
+    static int lg = -1;                                 // dev knob: LOTUS_TC_LDG_GATHER=1 gathers through registers (8 lanes per row)
+    if (lg < 0) { const char* e = getenv("LOTUS_TC_LDG_GATHER"); lg = e ? atoi(e) : 0; }   // measured equal on B200: the conv is bound by L2->SM weight-tile traffic, not by the gather instruction form
+    p.ldg_gather = lg;
   }
   dim3 grid((p.M + BM - 1) / BM, (p.N + BN - 1) / BN, splits * taps);
   size_t tile_bytes = (size_t)BM * BN * (p.out_fp32 ? 4 : 2);
