@@ -180,13 +180,17 @@ struct BnSave { const void* x; float *mean, *rstd; int64_t rows; bool x_fp32; };
 static void bn_fwd(Ctx& c, const void* x, bool x_fp32, void* y, int64_t rows, const BNorm& b, BnSave& sv) {
   sv.x = x; sv.rows = rows; sv.x_fp32 = x_fp32;
   sv.mean = f32(c, b.C); sv.rstd = f32(c, b.C);
-  float* scratch = f32(c, b.C);
+  float* scratch = f32(c, 2 * b.C);
   float* rm = (float*)c.BN[2 * b.buf]; float* rv = (float*)c.BN[2 * b.buf + 1];
   if (c.bf) CALL(lotus_batchnorm_fwd_bf16, x, x_fp32 ? 1 : 0, y, rows, b.C, Pf(c, b.w), Pf(c, b.b), rm, rv, sv.mean, sv.rstd, scratch, c.train ? 1 : 0, 1e-3f, 0.01f, 1, c.stv);
   else CALL(lotus_batchnorm_fwd_f32, (const float*)x, (float*)y, rows, b.C, Pf(c, b.w), Pf(c, b.b), rm, rv, sv.mean, sv.rstd, scratch, c.train ? 1 : 0, 1e-3f, 0.01f, 1, c.stv);
 }
 static void bn_bwd(Ctx& c, const void* dy, void* dx, const BNorm& b, const BnSave& sv) {
   float* dg = f32(c, 2 * b.C); float* db = dg + b.C;
+  if (c.bf && c.train && b.C % 8 == 0 && b.C <= 1024) {          // one launch: sums, dx, and the adds into the gradient accumulators
+    CALL(lotus_batchnorm_bwd_acc_bf16, dy, sv.x, sv.x_fp32 ? 1 : 0, sv.rows, b.C, Pf(c, b.w), Pf(c, b.b), sv.mean, sv.rstd, dx, dg, db, Gf(c, b.w), Gf(c, b.b), 1, c.stv);
+    return;
+  }
   zero(c, dg, (size_t)2 * b.C * 4);
   if (c.bf) CALL(lotus_batchnorm_bwd_bf16, dy, sv.x, sv.x_fp32 ? 1 : 0, sv.rows, b.C, Pf(c, b.w), Pf(c, b.b), sv.mean, sv.rstd, dx, dg, db, c.train ? 1 : 0, 1, c.stv);
   else CALL(lotus_batchnorm_bwd_f32, (const float*)dy, (const float*)sv.x, sv.rows, b.C, Pf(c, b.w), Pf(c, b.b), sv.mean, sv.rstd, (float*)dx, dg, db, c.train ? 1 : 0, 1, c.stv);

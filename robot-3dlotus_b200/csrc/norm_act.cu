@@ -13,6 +13,21 @@ struct RowMap {  // row r -> element offset (r / inner) * outer_stride + (r % in
   }
 };
 
+// Blocks of `kern` that are resident at once on the whole GPU (148 SMs x occupancy).  The persistent kernels below are launched with
+// at most this many blocks: a grid of 4 blocks per SM whose occupancy is 3 runs as two waves, and for these 10-20 us kernels the second
+// wave doubled the time.  Cached per kernel (the dynamic shared memory they use is a few KB and never the limiter).
+#include <unordered_map>
+template <typename K>
+static int resident_blocks(K kern, int threads, size_t smem) {
+  thread_local std::unordered_map<const void*, int> cache;
+  auto it = cache.find((const void*)kern);
+  if (it != cache.end()) return it->second;
+  int occ = 0;
+  if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kern, threads, smem) != cudaSuccess || occ < 1) occ = 1;
+  cache[(const void*)kern] = occ * kNumSM;
+  return occ * kNumSM;
+}
+
 // ---------------------------------------------------------------- LayerNorm
 // y = [residual +] (x - mean) * rstd * gamma + beta ; one warp per row
 template <typename T>
@@ -179,8 +194,9 @@ __global__ void __launch_bounds__(256) k_ln_fwd_vec(const bf16_t* __restrict__ x
   }
 }
 
-template <int VPL, typename TDY>
-__global__ void __launch_bounds__(256) k_ln_bwd_vec(const TDY* __restrict__ dy, RowMap dym, const bf16_t* __restrict__ x, RowMap xm,
+// U row groups per warp iteration: their loads are issued together (one group in flight per warp leaves the memory system half idle)
+template <int VPL, int U, typename TDY>
+__global__ void __launch_bounds__(256, U == 2 ? 3 : 1) k_ln_bwd_vec(const TDY* __restrict__ dy, RowMap dym, const bf16_t* __restrict__ x, RowMap xm,
                                                     bf16_t* __restrict__ dx, RowMap dxm, const float* __restrict__ gamma,
                                                     const float* __restrict__ mean, const float* __restrict__ rstd,
                                                     float* __restrict__ dgamma, float* __restrict__ dbeta, int64_t rows, int C,
@@ -200,48 +216,65 @@ __global__ void __launch_bounds__(256) k_ln_bwd_vec(const TDY* __restrict__ dy, 
   }
   const int64_t warps = (int64_t)gridDim.x * (blockDim.x >> 5);
   const float invC = 1.f / (float)C;
-  for (int64_t r0 = ((int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5)) * rpw; r0 < rows; r0 += warps * rpw) {
-    int64_t r = r0 + lane / lpr;
-    bool rok = r < rows;
-    float xh[VPL][8], d[VPL][8];
-    float mu = rok ? mean[r] : 0.f, rs = rok ? rstd[r] : 0.f;
-    float s1 = 0.f, s2 = 0.f;
-    const bf16_t* xr = x + (rok ? xm(r) : 0);
-    const TDY* dyr = dy + (rok ? dym(r) : 0);
+  for (int64_t r0 = ((int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5)) * rpw; r0 < rows; r0 += warps * rpw * U) {
+    int64_t r[U];
+    bool rok[U];
+    float mu[U], rs[U];
+    uint4 xv[U][VPL];
+    float d[U][VPL][8];
 #pragma unroll
-    for (int j = 0; j < VPL; ++j) {
-      int vi = lig + j * lpr;
-      if (rok && vi < nvec) {
-        load8(xr + vi * 8, xh[j]); load8(dyr + vi * 8, d[j]);
+    for (int u = 0; u < U; ++u) {
+      r[u] = r0 + (int64_t)u * warps * rpw + lane / lpr;
+      rok[u] = r[u] < rows;
+      mu[u] = rok[u] ? mean[r[u]] : 0.f; rs[u] = rok[u] ? rstd[r[u]] : 0.f;
+      const bf16_t* xr = x + (rok[u] ? xm(r[u]) : 0);
+      const TDY* dyr = dy + (rok[u] ? dym(r[u]) : 0);
 #pragma unroll
-        for (int e = 0; e < 8; ++e) {
-          xh[j][e] = (xh[j][e] - mu) * rs;
-          float gg = d[j][e] * g[j][e];
-          s1 += gg; s2 += gg * xh[j][e];
-          ag[j][e] += d[j][e] * xh[j][e]; ab[j][e] += d[j][e];
+      for (int j = 0; j < VPL; ++j) {
+        int vi = lig + j * lpr;
+        if (rok[u] && vi < nvec) { xv[u][j] = *(const uint4*)(xr + vi * 8); load8(dyr + vi * 8, d[u][j]); }
+        else {
+          xv[u][j] = make_uint4(0, 0, 0, 0);
+#pragma unroll
+          for (int e = 0; e < 8; ++e) d[u][j][e] = 0.f;
         }
-      } else {
-#pragma unroll
-        for (int e = 0; e < 8; ++e) { xh[j][e] = 0.f; d[j][e] = 0.f; }
       }
     }
-    s1 = group_sum(s1, lpr) * invC; s2 = group_sum(s2, lpr) * invC;
-    if (!rok) continue;
-    int64_t xo = dxm(r);
 #pragma unroll
-    for (int j = 0; j < VPL; ++j) {
-      int vi = lig + j * lpr;
-      if (vi < nvec) {
-        float o[8];
+    for (int u = 0; u < U; ++u) {
+      float xh[VPL][8];
+      float s1 = 0.f, s2 = 0.f;
 #pragma unroll
-        for (int e = 0; e < 8; ++e) o[e] = rs * (d[j][e] * g[j][e] - s1 - xh[j][e] * s2);
-        if (accumulate_dx) {
-          float old[8];
-          load8(dx + xo + vi * 8, old);
+      for (int j = 0; j < VPL; ++j) {
+        int vi = lig + j * lpr;
+        unpack8(xv[u][j], xh[j]);
+        const bool on = rok[u] && vi < nvec;
 #pragma unroll
-          for (int e = 0; e < 8; ++e) o[e] += old[e];
+        for (int e = 0; e < 8; ++e) {
+          xh[j][e] = on ? (xh[j][e] - mu[u]) * rs[u] : 0.f;
+          float gg = d[u][j][e] * g[j][e];
+          s1 += gg; s2 += gg * xh[j][e];
+          ag[j][e] += d[u][j][e] * xh[j][e]; ab[j][e] += d[u][j][e];
         }
-        *(uint4*)(dx + xo + vi * 8) = pack8(o);
+      }
+      s1 = group_sum(s1, lpr) * invC; s2 = group_sum(s2, lpr) * invC;
+      if (!rok[u]) continue;
+      int64_t xo = dxm(r[u]);
+#pragma unroll
+      for (int j = 0; j < VPL; ++j) {
+        int vi = lig + j * lpr;
+        if (vi < nvec) {
+          float o[8];
+#pragma unroll
+          for (int e = 0; e < 8; ++e) o[e] = rs[u] * (d[u][j][e] * g[j][e] - s1 - xh[j][e] * s2);
+          if (accumulate_dx) {
+            float old[8];
+            load8(dx + xo + vi * 8, old);
+#pragma unroll
+            for (int e = 0; e < 8; ++e) o[e] += old[e];
+          }
+          *(uint4*)(dx + xo + vi * 8) = pack8(o);
+        }
       }
     }
   }
@@ -276,9 +309,8 @@ static int ln_fwd_impl(const void* x, int x_inner, int64_t x_outer_stride, int64
   if (sizeof(T) == 2 && C % 8 == 0 && C <= 1024 && vec_ok(xm) && vec_ok(ym) && aligned16(x) && aligned16(y) &&
       (!residual || aligned16(residual)) && aligned16(gamma) && aligned16(beta)) {
     int lpr = pick_lpr(C), vpl = ceil_div(C >> 3, lpr), rpw = 32 / lpr;
-    int blocks = min(ceil_div(ceil_div(rows, rpw), 8), kNumSM * 8);
     cudaStream_t st = (cudaStream_t)stream_;
-#define LNF(V) k_ln_fwd_vec<V><<<blocks, 256, 0, st>>>((const bf16_t*)x, xm, (bf16_t*)y, ym, (const bf16_t*)residual, gamma, beta, mean, rstd, rows, C, lpr, eps)
+#define LNF(V) k_ln_fwd_vec<V><<<min(ceil_div(ceil_div(rows, rpw), 8), resident_blocks(k_ln_fwd_vec<V>, 256, 0)), 256, 0, st>>>((const bf16_t*)x, xm, (bf16_t*)y, ym, (const bf16_t*)residual, gamma, beta, mean, rstd, rows, C, lpr, eps)
     if (vpl == 1) LNF(1); else if (vpl == 2) LNF(2); else if (vpl == 3) LNF(3); else LNF(4);
 #undef LNF
     LOTUS_CUDA_OK();
@@ -322,9 +354,8 @@ static int ln_bwd_impl(const void* dy, int dy_inner, int64_t dy_outer_stride, in
   if (sizeof(T) == 2 && C % 8 == 0 && vec_ok(dym) && vec_ok(xm) && vec_ok(dxm) && aligned16(dy) && aligned16(x) && aligned16(dx) &&
       aligned16(gamma)) {
     int lpr = pick_lpr(C), vpl = ceil_div(C >> 3, lpr), rpw = 32 / lpr;
-    int vblocks = min(ceil_div(ceil_div(rows, rpw), 8), kNumSM * 4);
-#define LNB(V) k_ln_bwd_vec<V, TDY><<<vblocks, 256, smem, st>>>((const TDY*)dy, dym, (const bf16_t*)x, xm, (bf16_t*)dx, dxm, gamma, mean, rstd, dgamma, dbeta, rows, C, lpr, accumulate_dx)
-    if (vpl == 1) LNB(1); else if (vpl == 2) LNB(2); else if (vpl == 3) LNB(3); else LNB(4);
+#define LNB(V, U) k_ln_bwd_vec<V, U, TDY><<<min(ceil_div(ceil_div(rows, rpw * U), 8), resident_blocks(k_ln_bwd_vec<V, U, TDY>, 256, smem)), 256, smem, st>>>((const TDY*)dy, dym, (const bf16_t*)x, xm, (bf16_t*)dx, dxm, gamma, mean, rstd, dgamma, dbeta, rows, C, lpr, accumulate_dx)
+    if (vpl == 1) LNB(1, 2); else if (vpl == 2) LNB(2, 1); else if (vpl == 3) LNB(3, 1); else LNB(4, 1);
 #undef LNB
     LOTUS_CUDA_OK();
     return 0;
@@ -537,6 +568,268 @@ __global__ void k_bn_apply(const TX* __restrict__ x, TY* __restrict__ y, const f
   }
 }
 
+
+// ---------------------------------------------------------------- fused BatchNorm [+GELU], bf16 path: ONE cooperative launch
+// The multi-kernel form above (memset x2, column sums x2, finalize x2, apply) costs 45 us on [96652, 64] where the three passes over
+// the tensor are worth 5 us.  Here a grid of resident blocks (cooperative launch: co-scheduled, so the grid barrier cannot deadlock)
+// does   zero the accumulators | barrier | pivot-shifted column sums of x and x^2 | barrier | per-channel scale / shift | apply,
+// with 16-byte accesses (8 channels per thread) and the second read of x served by L2.  The variance comes from sums shifted by the
+// first row (pivot p[c] = x[0][c]):  var = E[(x - p)^2] - E[x - p]^2, which keeps the cancellation harmless when |mean| >> std.
+#include <cooperative_groups.h>
+namespace cg = cooperative_groups;
+__device__ __forceinline__ void store8(bf16_t* p, const float* v) { *(uint4*)p = pack8(v); }
+__device__ __forceinline__ void store8(float* p, const float* v) {
+  *(float4*)p = make_float4(v[0], v[1], v[2], v[3]);
+  *(float4*)(p + 4) = make_float4(v[4], v[5], v[6], v[7]);
+}
+// exact-erf GELU by Abramowitz-Stegun 7.1.26 (|err| <= 1.5e-7): same approximation as the GEMM epilogues (tc_common.cuh)
+__device__ __forceinline__ void gelu_parts_na(float x, float& cdf, float& e) {
+  const float z = fabsf(x) * 0.70710678118654752f;
+  const float t = __fdividef(1.f, fmaf(0.3275911f, z, 1.f));
+  e = exp2f(x * x * -0.72134752044448170f);
+  const float poly = fmaf(fmaf(fmaf(fmaf(1.061405429f, t, -1.453152027f), t, 1.421413741f), t, -0.284496736f), t, 0.254829592f) * t;
+  cdf = fmaf(copysignf(fmaf(-poly, e, 1.f), x), 0.5f, 0.5f);
+}
+__device__ __forceinline__ float gelu_na(float x) { float c, e; gelu_parts_na(x, c, e); return x * c; }
+__device__ __forceinline__ float gelu_grad_na(float x) { float c, e; gelu_parts_na(x, c, e); return fmaf(x * e, 0.39894228040143267794f, c); }
+
+template <typename TX>
+__global__ void __launch_bounds__(256) k_bn_fwd_fused(const TX* __restrict__ x, bf16_t* __restrict__ y, int64_t rows, int C,
+                                                      const float* __restrict__ gamma, const float* __restrict__ beta,
+                                                      float* __restrict__ run_mean, float* __restrict__ run_var,
+                                                      float* __restrict__ save_mean, float* __restrict__ save_rstd,
+                                                      float* __restrict__ acc /*[2][C]*/, int train, float eps, float momentum, int act) {
+  __shared__ float sA[1024], sB[1024];
+  cg::grid_group grid = cg::this_grid();
+  const int nvec = C >> 3, tpr = nvec, rg = 256 / tpr;
+  const int tv = threadIdx.x % tpr, tr = threadIdx.x / tpr;
+  const bool active = tr < rg;
+  const int64_t stride = (int64_t)gridDim.x * rg;
+  const int64_t rfirst = (int64_t)blockIdx.x * rg + tr;
+  if (train) {
+    for (int c = blockIdx.x * 256 + threadIdx.x; c < 2 * C; c += gridDim.x * 256) acc[c] = 0.f;
+    for (int c = threadIdx.x; c < 2 * C; c += 256) { if (c < C) sA[c] = 0.f; else sB[c - C] = 0.f; }
+    float sq[2][8], pv[8];
+#pragma unroll
+    for (int e = 0; e < 8; ++e) { sq[0][e] = 0.f; sq[1][e] = 0.f; pv[e] = 0.f; }
+    if (active) load8(x + tv * 8, pv);                           // pivot: row 0
+    if (active) {
+      int64_t r = rfirst;
+      for (; r + 3 * stride < rows; r += 4 * stride) {           // four rows in flight
+        float v[4][8];
+#pragma unroll
+        for (int u = 0; u < 4; ++u) load8(x + (r + u * stride) * C + tv * 8, v[u]);
+#pragma unroll
+        for (int u = 0; u < 4; ++u)
+#pragma unroll
+          for (int e = 0; e < 8; ++e) { const float d = v[u][e] - pv[e]; sq[0][e] += d; sq[1][e] = fmaf(d, d, sq[1][e]); }
+      }
+      for (; r < rows; r += stride) {
+        float v[8];
+        load8(x + r * C + tv * 8, v);
+#pragma unroll
+        for (int e = 0; e < 8; ++e) { const float d = v[e] - pv[e]; sq[0][e] += d; sq[1][e] = fmaf(d, d, sq[1][e]); }
+      }
+    }
+    __syncthreads();
+    // both partial sets go through one [2][C] view: sA = sums, sB = squares
+    {
+      const int lane = threadIdx.x & 31;
+      const bool pow2 = (tpr & (tpr - 1)) == 0 && tpr < 32;
+#pragma unroll
+      for (int e = 0; e < 8; ++e) {
+        float a = active ? sq[0][e] : 0.f, b = active ? sq[1][e] : 0.f;
+        if (pow2) for (int o = 16; o >= tpr; o >>= 1) { a += __shfl_xor_sync(0xffffffffu, a, o); b += __shfl_xor_sync(0xffffffffu, b, o); }
+        if (active && (!pow2 || lane < tpr)) { atomicAdd(&sA[tv * 8 + e], a); atomicAdd(&sB[tv * 8 + e], b); }
+      }
+    }
+    grid.sync();                                                 // accumulators zeroed everywhere (and this block's partials complete)
+    for (int c = threadIdx.x; c < C; c += 256) { atomicAdd(&acc[c], sA[c]); atomicAdd(&acc[C + c], sB[c]); }
+    grid.sync();
+  }
+  // per-channel scale / shift
+  const float invn = 1.f / (float)rows;
+  for (int c = threadIdx.x; c < C; c += 256) {
+    float mean, rs;
+    if (train) {
+      const float m = __ldcg(&acc[c]) * invn;
+      const float var = fmaxf(__ldcg(&acc[C + c]) * invn - m * m, 0.f);
+      mean = ldf(x, c) + m;
+      rs = rsqrtf(var + eps);
+      if (blockIdx.x == 0 && run_mean) {
+        run_mean[c] = (1.f - momentum) * run_mean[c] + momentum * mean;
+        const float unb = rows > 1 ? var * ((float)rows / (float)(rows - 1)) : var;
+        run_var[c] = (1.f - momentum) * run_var[c] + momentum * unb;
+      }
+    } else {
+      mean = run_mean[c];
+      rs = rsqrtf(run_var[c] + eps);
+    }
+    if (blockIdx.x == 0) { save_mean[c] = mean; save_rstd[c] = rs; }
+    const float sc = rs * gamma[c];
+    sA[c] = sc;
+    sB[c] = beta[c] - mean * sc;
+  }
+  __syncthreads();
+  if (!active) return;
+  float sc[8], sh[8];
+#pragma unroll
+  for (int e = 0; e < 8; ++e) { sc[e] = sA[tv * 8 + e]; sh[e] = sB[tv * 8 + e]; }
+  int64_t r = rfirst;
+  for (; r + 3 * stride < rows; r += 4 * stride) {
+    float v[4][8];
+#pragma unroll
+    for (int u = 0; u < 4; ++u) load8(x + (r + u * stride) * C + tv * 8, v[u]);
+#pragma unroll
+    for (int u = 0; u < 4; ++u) {
+#pragma unroll
+      for (int e = 0; e < 8; ++e) { const float z = fmaf(v[u][e], sc[e], sh[e]); v[u][e] = act ? gelu_na(z) : z; }
+      store8(y + (r + u * stride) * C + tv * 8, v[u]);
+    }
+  }
+  for (; r < rows; r += stride) {
+    float v[8];
+    load8(x + r * C + tv * 8, v);
+#pragma unroll
+    for (int e = 0; e < 8; ++e) { const float z = fmaf(v[e], sc[e], sh[e]); v[e] = act ? gelu_na(z) : z; }
+    store8(y + r * C + tv * 8, v);
+  }
+}
+
+// backward of y = act(bn(x)), training statistics: zero | barrier | sum dz, sum dz * xhat | barrier | dx; the batch sums are left in
+// dgamma_batch / dbeta_batch and (optionally) added to the parameter-gradient accumulators by block 0
+template <typename TX>
+__global__ void __launch_bounds__(256) k_bn_bwd_fused(const bf16_t* __restrict__ dy, const TX* __restrict__ x, int64_t rows, int C,
+                                                      const float* __restrict__ gamma, const float* __restrict__ beta,
+                                                      const float* __restrict__ mean, const float* __restrict__ rstd, TX* __restrict__ dx,
+                                                      float* __restrict__ dgamma_batch, float* __restrict__ dbeta_batch,
+                                                      float* __restrict__ dgamma_acc, float* __restrict__ dbeta_acc, int act) {
+  __shared__ float sA[1024], sB[1024];
+  cg::grid_group grid = cg::this_grid();
+  const int nvec = C >> 3, tpr = nvec, rg = 256 / tpr;
+  const int tv = threadIdx.x % tpr, tr = threadIdx.x / tpr;
+  const bool active = tr < rg;
+  const int64_t stride = (int64_t)gridDim.x * rg;
+  const int64_t rfirst = (int64_t)blockIdx.x * rg + tr;
+  for (int c = blockIdx.x * 256 + threadIdx.x; c < C; c += gridDim.x * 256) { dgamma_batch[c] = 0.f; dbeta_batch[c] = 0.f; }
+  for (int c = threadIdx.x; c < C; c += 256) { sA[c] = 0.f; sB[c] = 0.f; }
+  float mu[8], rs[8], g[8], b[8];
+#pragma unroll
+  for (int e = 0; e < 8; ++e) { mu[e] = 0.f; rs[e] = 0.f; g[e] = 0.f; b[e] = 0.f; }
+  if (active) { load8(mean + tv * 8, mu); load8(rstd + tv * 8, rs); load8(gamma + tv * 8, g); load8(beta + tv * 8, b); }
+  {
+    float sg[8], sb[8];
+#pragma unroll
+    for (int e = 0; e < 8; ++e) { sg[e] = 0.f; sb[e] = 0.f; }
+    if (active) {
+      int64_t r = rfirst;
+      for (; r + stride < rows; r += 2 * stride) {               // two rows (four vectors) in flight
+        float xv[2][8], dv[2][8];
+#pragma unroll
+        for (int u = 0; u < 2; ++u) { load8(x + (r + u * stride) * C + tv * 8, xv[u]); load8(dy + (r + u * stride) * C + tv * 8, dv[u]); }
+#pragma unroll
+        for (int u = 0; u < 2; ++u)
+#pragma unroll
+          for (int e = 0; e < 8; ++e) {
+            const float xh = (xv[u][e] - mu[e]) * rs[e];
+            float dz = dv[u][e];
+            if (act) dz *= gelu_grad_na(fmaf(xh, g[e], b[e]));
+            sg[e] = fmaf(dz, xh, sg[e]); sb[e] += dz;
+          }
+      }
+      for (; r < rows; r += stride) {
+        float xv[8], dv[8];
+        load8(x + r * C + tv * 8, xv); load8(dy + r * C + tv * 8, dv);
+#pragma unroll
+        for (int e = 0; e < 8; ++e) {
+          const float xh = (xv[e] - mu[e]) * rs[e];
+          float dz = dv[e];
+          if (act) dz *= gelu_grad_na(fmaf(xh, g[e], b[e]));
+          sg[e] = fmaf(dz, xh, sg[e]); sb[e] += dz;
+        }
+      }
+    }
+    __syncthreads();
+    const int lane = threadIdx.x & 31;
+    const bool pow2 = (tpr & (tpr - 1)) == 0 && tpr < 32;
+#pragma unroll
+    for (int e = 0; e < 8; ++e) {
+      float a = active ? sg[e] : 0.f, bb = active ? sb[e] : 0.f;
+      if (pow2) for (int o = 16; o >= tpr; o >>= 1) { a += __shfl_xor_sync(0xffffffffu, a, o); bb += __shfl_xor_sync(0xffffffffu, bb, o); }
+      if (active && (!pow2 || lane < tpr)) { atomicAdd(&sA[tv * 8 + e], a); atomicAdd(&sB[tv * 8 + e], bb); }
+    }
+  }
+  grid.sync();
+  for (int c = threadIdx.x; c < C; c += 256) { atomicAdd(&dgamma_batch[c], sA[c]); atomicAdd(&dbeta_batch[c], sB[c]); }
+  grid.sync();
+  if (blockIdx.x == 0) {
+    for (int c = threadIdx.x; c < C; c += 256) {
+      if (dgamma_acc) dgamma_acc[c] += __ldcg(&dgamma_batch[c]);
+      if (dbeta_acc) dbeta_acc[c] += __ldcg(&dbeta_batch[c]);
+    }
+  }
+  if (!active) return;
+  const float invn = 1.f / (float)rows;
+  float k1[8], k2[8];
+#pragma unroll
+  for (int e = 0; e < 8; ++e) { k2[e] = __ldcg(&dgamma_batch[tv * 8 + e]) * invn; k1[e] = __ldcg(&dbeta_batch[tv * 8 + e]) * invn; }
+  int64_t r = rfirst;
+  for (; r + stride < rows; r += 2 * stride) {
+    float xv[2][8], dv[2][8];
+#pragma unroll
+    for (int u = 0; u < 2; ++u) { load8(x + (r + u * stride) * C + tv * 8, xv[u]); load8(dy + (r + u * stride) * C + tv * 8, dv[u]); }
+#pragma unroll
+    for (int u = 0; u < 2; ++u) {
+#pragma unroll
+      for (int e = 0; e < 8; ++e) {
+        const float xh = (xv[u][e] - mu[e]) * rs[e];
+        float dz = dv[u][e];
+        if (act) dz *= gelu_grad_na(fmaf(xh, g[e], b[e]));
+        xv[u][e] = g[e] * rs[e] * (dz - k1[e] - xh * k2[e]);
+      }
+      store8(dx + (r + u * stride) * C + tv * 8, xv[u]);
+    }
+  }
+  for (; r < rows; r += stride) {
+    float xv[8], dv[8];
+    load8(x + r * C + tv * 8, xv); load8(dy + r * C + tv * 8, dv);
+#pragma unroll
+    for (int e = 0; e < 8; ++e) {
+      const float xh = (xv[e] - mu[e]) * rs[e];
+      float dz = dv[e];
+      if (act) dz *= gelu_grad_na(fmaf(xh, g[e], b[e]));
+      xv[e] = g[e] * rs[e] * (dz - k1[e] - xh * k2[e]);
+    }
+    store8(dx + r * C + tv * 8, xv);
+  }
+}
+
+static inline bool bn_fused_ok(int64_t rows, int C, const void* a, const void* b, const void* c) {
+  return C % 8 == 0 && C <= 1024 && C >= 8 && (C >> 3) <= 256 && rows >= 1 && aligned16(a) && aligned16(b) && (!c || aligned16(c));
+}
+template <typename TX>
+static int bn_fwd_fused_launch(const void* x, void* y, int64_t rows, int C, const float* gamma, const float* beta, float* run_mean,
+                               float* run_var, float* save_mean, float* save_rstd, float* acc, int train, float eps, float momentum,
+                               int act, cudaStream_t st) {
+  const int rg = 256 / (C >> 3);
+  int blocks = (int)min((int64_t)resident_blocks(k_bn_fwd_fused<TX>, 256, 0), (rows + rg - 1) / rg);
+  const TX* xp = (const TX*)x; bf16_t* yp = (bf16_t*)y;
+  void* args[] = {&xp, &yp, &rows, &C, &gamma, &beta, &run_mean, &run_var, &save_mean, &save_rstd, &acc, &train, &eps, &momentum, &act};
+  LOTUS_CUDA_CALL(cudaLaunchCooperativeKernel((const void*)k_bn_fwd_fused<TX>, dim3(blocks), dim3(256), args, 0, st));
+  return 0;
+}
+template <typename TX>
+static int bn_bwd_fused_launch(const void* dy, const void* x, int64_t rows, int C, const float* gamma, const float* beta,
+                               const float* mean, const float* rstd, void* dx, float* dgb, float* dbb, float* dga, float* dba, int act,
+                               cudaStream_t st) {
+  const int rg = 256 / (C >> 3);
+  int blocks = (int)min((int64_t)resident_blocks(k_bn_bwd_fused<TX>, 256, 0), (rows + rg - 1) / rg);
+  const bf16_t* dyp = (const bf16_t*)dy; const TX* xp = (const TX*)x; TX* dxp = (TX*)dx;
+  void* args[] = {&dyp, &xp, &rows, &C, &gamma, &beta, &mean, &rstd, &dxp, &dgb, &dbb, &dga, &dba, &act};
+  LOTUS_CUDA_CALL(cudaLaunchCooperativeKernel((const void*)k_bn_bwd_fused<TX>, dim3(blocks), dim3(256), args, 0, st));
+  return 0;
+}
+
 // training: batch statistics (two-pass: mean, then centred second moment), running stats updated in place.
 // eval (train=0): mean/rstd derived from the running stats.  save_mean/save_rstd (C each) feed the backward.
 template <typename TX, typename TY>
@@ -578,6 +871,11 @@ LOTUS_API int lotus_batchnorm_fwd_bf16(const void* x, int x_fp32, void* y, int64
                                        const float* beta, float* run_mean, float* run_var, float* save_mean,
                                        float* save_rstd, float* scratch_C, int train, float eps, float momentum,
                                        int act_gelu, void* stream_) {
+  // scratch_C: 2 * C floats on this path (column sums and sums of squares)
+  if (bn_fused_ok(rows, C, x, y, nullptr) && aligned16(gamma) && aligned16(beta)) {
+    if (x_fp32) return bn_fwd_fused_launch<float>(x, y, rows, C, gamma, beta, run_mean, run_var, save_mean, save_rstd, scratch_C, train, eps, momentum, act_gelu, (cudaStream_t)stream_);
+    return bn_fwd_fused_launch<bf16_t>(x, y, rows, C, gamma, beta, run_mean, run_var, save_mean, save_rstd, scratch_C, train, eps, momentum, act_gelu, (cudaStream_t)stream_);
+  }
   if (x_fp32)
     return bn_fwd_impl<float, bf16_t>(x, y, rows, C, gamma, beta, run_mean, run_var, save_mean, save_rstd, scratch_C, train, eps,
                                       momentum, act_gelu, stream_);
@@ -660,11 +958,28 @@ LOTUS_API int lotus_batchnorm_bwd_f32(const float* dy, const float* x, int64_t r
 LOTUS_API int lotus_batchnorm_bwd_bf16(const void* dy, const void* x, int x_fp32, int64_t rows, int C, const float* gamma,
                                        const float* beta, const float* save_mean, const float* save_rstd, void* dx,
                                        float* dgamma_batch, float* dbeta_batch, int train, int act_gelu, void* stream_) {
+  if (train && bn_fused_ok(rows, C, x, dy, dx) && aligned16(gamma) && aligned16(beta) && aligned16(save_mean) && aligned16(save_rstd)) {
+    if (x_fp32) return bn_bwd_fused_launch<float>(dy, x, rows, C, gamma, beta, save_mean, save_rstd, dx, dgamma_batch, dbeta_batch, nullptr, nullptr, act_gelu, (cudaStream_t)stream_);
+    return bn_bwd_fused_launch<bf16_t>(dy, x, rows, C, gamma, beta, save_mean, save_rstd, dx, dgamma_batch, dbeta_batch, nullptr, nullptr, act_gelu, (cudaStream_t)stream_);
+  }
   if (x_fp32)
     return bn_bwd_impl<float, bf16_t>(dy, x, rows, C, gamma, beta, save_mean, save_rstd, dx, dgamma_batch, dbeta_batch, train,
                                       act_gelu, stream_);
   return bn_bwd_impl<bf16_t, bf16_t>(dy, x, rows, C, gamma, beta, save_mean, save_rstd, dx, dgamma_batch, dbeta_batch, train,
                                      act_gelu, stream_);
+}
+
+// training-mode backward in one launch that also adds the batch sums into the parameter-gradient accumulators (either may be null);
+// dgamma_batch / dbeta_batch: C-float scratch each (zeroed by the kernel).  Fails on shapes the fused kernel does not take.
+LOTUS_API int lotus_batchnorm_bwd_acc_bf16(const void* dy, const void* x, int x_fp32, int64_t rows, int C, const float* gamma,
+                                           const float* beta, const float* save_mean, const float* save_rstd, void* dx,
+                                           float* dgamma_batch, float* dbeta_batch, float* dgamma_acc, float* dbeta_acc, int act_gelu,
+                                           void* stream_) {
+  if (rows <= 0) return 0;
+  LOTUS_CHECK_ARG(bn_fused_ok(rows, C, x, dy, dx) && aligned16(gamma) && aligned16(beta) && aligned16(save_mean) && aligned16(save_rstd),
+                  "lotus_batchnorm_bwd_acc_bf16: C=%d must be a multiple of 8, <= 1024, 16-byte aligned operands", C);
+  if (x_fp32) return bn_bwd_fused_launch<float>(dy, x, rows, C, gamma, beta, save_mean, save_rstd, dx, dgamma_batch, dbeta_batch, dgamma_acc, dbeta_acc, act_gelu, (cudaStream_t)stream_);
+  return bn_bwd_fused_launch<bf16_t>(dy, x, rows, C, gamma, beta, save_mean, save_rstd, dx, dgamma_batch, dbeta_batch, dgamma_acc, dbeta_acc, act_gelu, (cudaStream_t)stream_);
 }
 
 // ---------------------------------------------------------------- pointwise

@@ -337,7 +337,7 @@ class BatchNormActFn(torch.autograd.Function):
         y = torch.empty((rows, C), device=x.device, dtype=torch.bfloat16 if bf else torch.float32)
         mean = torch.empty(C, device=x.device, dtype=torch.float32)
         rstd = torch.empty_like(mean)
-        scratch = torch.empty_like(mean)
+        scratch = torch.empty(2 * C, device=x.device, dtype=torch.float32)
         if bf:
             L.lotus_batchnorm_fwd_bf16(_p(x), int(x.dtype == torch.float32), _p(y), rows, C, _p(g), _p(b), _p(run_mean), _p(run_var),
                                        _p(mean), _p(rstd), _p(scratch), int(train), eps, momentum, int(gelu), _st())
