@@ -580,6 +580,9 @@ def main():
             holder["rec"] = native.profile_step(lambda: step_fn(dict(resident[0])))
         torch.cuda.synchronize()
         prof.native_records = [(n_, a_, ms_) for n_, a_, ms_ in holder["rec"]]
+        if os.environ.get("LOTUS_BENCH_DUMP"):                   # dev: per-call records of the profiled step (name, C-ABI args, device ms)
+            with open(os.environ["LOTUS_BENCH_DUMP"], "w") as f:
+                json.dump([[n_, list(a_), ms_] for n_, a_, ms_ in holder["rec"]], f)
         prof.records = [r for r in prof.records if r[0] != "lotus_policy_step"]
     else:
         model.engine().use_native = False

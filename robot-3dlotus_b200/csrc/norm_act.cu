@@ -576,22 +576,16 @@ __global__ void k_bn_apply(const TX* __restrict__ x, TY* __restrict__ y, const f
 // with 16-byte accesses (8 channels per thread) and the second read of x served by L2.  The variance comes from sums shifted by the
 // first row (pivot p[c] = x[0][c]):  var = E[(x - p)^2] - E[x - p]^2, which keeps the cancellation harmless when |mean| >> std.
 #include <cooperative_groups.h>
+#include "tc_common.cuh"
 namespace cg = cooperative_groups;
 __device__ __forceinline__ void store8(bf16_t* p, const float* v) { *(uint4*)p = pack8(v); }
 __device__ __forceinline__ void store8(float* p, const float* v) {
   *(float4*)p = make_float4(v[0], v[1], v[2], v[3]);
   *(float4*)(p + 4) = make_float4(v[4], v[5], v[6], v[7]);
 }
-// exact-erf GELU by Abramowitz-Stegun 7.1.26 (|err| <= 1.5e-7): same approximation as the GEMM epilogues (tc_common.cuh)
-__device__ __forceinline__ void gelu_parts_na(float x, float& cdf, float& e) {
-  const float z = fabsf(x) * 0.70710678118654752f;
-  const float t = __fdividef(1.f, fmaf(0.3275911f, z, 1.f));
-  e = exp2f(x * x * -0.72134752044448170f);
-  const float poly = fmaf(fmaf(fmaf(fmaf(1.061405429f, t, -1.453152027f), t, 1.421413741f), t, -0.284496736f), t, 0.254829592f) * t;
-  cdf = fmaf(copysignf(fmaf(-poly, e, 1.f), x), 0.5f, 0.5f);
-}
-__device__ __forceinline__ float gelu_na(float x) { float c, e; gelu_parts_na(x, c, e); return x * c; }
-__device__ __forceinline__ float gelu_grad_na(float x) { float c, e; gelu_parts_na(x, c, e); return fmaf(x * e, 0.39894228040143267794f, c); }
+// GELU of the bf16 path: the same function as the GEMM epilogues (tc_common.cuh gelu_fast / gelu_grad_fast)
+__device__ __forceinline__ float gelu_na(float x) { return tc::gelu_fast(x, 0.5f); }
+__device__ __forceinline__ float gelu_grad_na(float x) { return tc::gelu_grad_fast(x, 0.5f); }
 
 template <typename TX>
 __global__ void __launch_bounds__(256) k_bn_fwd_fused(const TX* __restrict__ x, bf16_t* __restrict__ y, int64_t rows, int C,

@@ -158,11 +158,33 @@ __device__ __forceinline__ void gelu_parts(float x, float half_s, float& cdf_s, 
   const float erf_abs = fmaf(-poly, e, 1.f);
   cdf_s = fmaf(copysignf(erf_abs, x), half_s, half_s);
 }
+#ifdef LOTUS_GELU_ERF_EPILOGUE
 __device__ __forceinline__ float gelu_fast(float x, float half_s) { float c, e; gelu_parts(x, half_s, c, e); return x * c; }
 __device__ __forceinline__ float gelu_grad_fast(float x, float half_s) {
   float c, e; gelu_parts(x, half_s, c, e);
   return fmaf(x * e, 0.79788456080286535588f * half_s, c);   // s * (cdf + x * pdf), pdf = e / sqrt(2 pi)
 }
+#else
+// Default for the bf16 epilogues: the tanh form, Phi(x) ~ 0.5 (1 + tanh(sqrt(2/pi) (x + 0.044715 x^3))), on MUFU.TANH.  The GELU
+// epilogues of k_lin are ISSUE-bound (8 epilogue warps, ~25 instructions per element with the erf form above of which 16 are the
+// activation); this form is 6 instructions (10 for the derivative) and one MUFU instead of two.  |tanh form - erf form| <= 5e-4
+// absolute (below the bf16 rounding of the stored activation except in the negative tail |gelu| < 0.05, where it is ~2 ulp);
+// forward and backward use the same function, so the gradient is the exact derivative of what the forward computed.  The fp32
+// validation path (norm_act.cu gelu_f, erff) is untouched.  -DLOTUS_GELU_ERF_EPILOGUE restores the erf form.
+__device__ __forceinline__ float tanh_approx(float x) { float y; asm("tanh.approx.f32 %0, %1;" : "=f"(y) : "f"(x)); return y; }
+__device__ __forceinline__ float gelu_fast(float x, float half_s) {
+  const float x2 = x * x;
+  const float t = tanh_approx(x * fmaf(x2, 0.0356774081363001f, 0.7978845608028654f));
+  return x * fmaf(t, half_s, half_s);
+}
+__device__ __forceinline__ float gelu_grad_fast(float x, float half_s) {
+  const float x2 = x * x;
+  const float t = tanh_approx(x * fmaf(x2, 0.0356774081363001f, 0.7978845608028654f));
+  const float c = fmaf(t, half_s, half_s);                     // s * Phi
+  const float g = x * fmaf(x2, 0.1070322244089003f, 0.7978845608028654f) * fmaf(-t, t, 1.f);   // x * u'(x) * (1 - t^2)
+  return fmaf(g, half_s, c);
+}
+#endif
 
 
 }  // namespace tc
