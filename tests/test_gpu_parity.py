@@ -370,7 +370,9 @@ def test_subm_conv_kernel():
     stages = tk.tokenize(coord.to(DEV), sizes, ["z"], [2], [128, 128], [[0], [0]], None)
     batch_ids = O.offset2batch(torch.tensor(np.cumsum(sizes)))
     g = torch.Generator().manual_seed(2)
-    for k, cin, cout, nbr_dev in [(3, 32, 48, stages[0].nbr3), (5, 7, 16, stages[0].nbr5)]:
+    # (5, 7, 64) / (5, 6, 128) / (5, 8, 64): the stem shapes -> the sparse SIMT kernels (k_conv_fwd_narrow / k_conv_wgrad_narrow2)
+    for k, cin, cout, nbr_dev in [(3, 32, 48, stages[0].nbr3), (5, 7, 16, stages[0].nbr5), (5, 7, 64, stages[0].nbr5),
+                                  (5, 6, 128, stages[0].nbr5), (5, 8, 64, stages[0].nbr5)]:
         nbr = O.neighbor_table(batch_ids, O.grid_coords(coord), k)
         _check_grads(lambda x, w, b: ops.subm_conv(x, w, b, nbr_dev, stages[0].stride_alloc),
                      lambda x, w, b: O.subm_conv(x, nbr, w, b),
