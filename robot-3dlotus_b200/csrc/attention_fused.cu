@@ -296,6 +296,8 @@ __global__ void __launch_bounds__(128 * HG, 2) k_pattn_fwd(const Args a) {
   using C = Coal<DHP, HG, NT>;
 
   const int p = blockIdx.x, h0 = blockIdx.y * HG;
+  pdl_wait();                                                    // programmatic dependent launch (common.cuh): q / k / v come from the previous kernel
+  pdl_launch_dependents();
   const int s0 = a.cu[p], len = a.cu[p + 1] - s0;
   if (len <= 0) return;                                          // uniform per CTA
   const int nh = min(HG, a.H - h0);
@@ -454,7 +456,7 @@ static int launch_fwd(const Args& a, int n_patches, cudaStream_t st) {
     LOTUS_CUDA_CALL(cudaFuncSetAttribute(k_pattn_fwd<DHP, HG>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM));
     attr_set = true;
   }
-  k_pattn_fwd<DHP, HG><<<dim3(n_patches, (a.H + HG - 1) / HG), 128 * HG, SMEM, st>>>(a);
+  launch_pdl(k_pattn_fwd<DHP, HG>, dim3(n_patches, (a.H + HG - 1) / HG), dim3(128 * HG), SMEM, st, a);
   LOTUS_CUDA_OK();
   return 0;
 }
@@ -647,6 +649,8 @@ __global__ void __launch_bounds__(256 * HG, 1) k_pattn_bwd(const Args a) {
   int* sReal = sPt + 128;
 
   const int p = blockIdx.x, h0 = blockIdx.y * HG;
+  pdl_wait();
+  pdl_launch_dependents();
   const int s0 = a.cu[p], len = a.cu[p + 1] - s0;
   if (len <= 0) return;
   const int nh = min(HG, a.H - h0);
@@ -893,6 +897,8 @@ __global__ void __launch_bounds__(256 * HG, 1) k_pattn_bwd(const Args a) {
 __global__ void k_alias_fold(const int32_t* __restrict__ gather_idx, const int32_t* __restrict__ slot_of_point, int n_pad, int C,
                              const __nv_bfloat16* __restrict__ alias, __nv_bfloat16* __restrict__ dk, __nv_bfloat16* __restrict__ dv,
                              int64_t lddk, int64_t lddv) {
+  pdl_wait();
+  pdl_launch_dependents();
   const int lanes = C / 8;                                       // 16-byte chunks per row
   const int per_block = blockDim.x / lanes;
   const int slot = blockIdx.x * per_block + threadIdx.x / lanes, c = threadIdx.x % lanes;
@@ -921,12 +927,12 @@ static int launch_bwd(const Args& a, int n_patches, int n_pad, cudaStream_t st) 
     LOTUS_CUDA_CALL(cudaFuncSetAttribute(k_pattn_bwd<DHP, HG>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM));
     attr_set = true;
   }
-  k_pattn_bwd<DHP, HG><<<dim3(n_patches, (a.H + HG - 1) / HG), 256 * HG, SMEM, st>>>(a);
+  launch_pdl(k_pattn_bwd<DHP, HG>, dim3(n_patches, (a.H + HG - 1) / HG), dim3(256 * HG), SMEM, st, a);
   LOTUS_CUDA_OK();
   const int C = a.H * a.Dh, lanes = C / 8;
   const int threads = lanes >= 256 ? lanes : 256, per_block = threads / lanes;
   if (lanes <= 1024) {
-    k_alias_fold<<<(n_pad + per_block - 1) / per_block, threads, 0, st>>>(a.gather_idx, a.slot_of_point, n_pad, C, a.alias_dkv, a.dk, a.dv, a.lddk, a.lddv);
+    launch_pdl(k_alias_fold, dim3((n_pad + per_block - 1) / per_block), dim3(threads), 0, st, a.gather_idx, a.slot_of_point, n_pad, C, (const __nv_bfloat16*)a.alias_dkv, a.dk, a.dv, a.lddk, a.lddv);
     LOTUS_CUDA_OK();
   }
   return 0;

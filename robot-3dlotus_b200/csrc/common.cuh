@@ -40,6 +40,33 @@ void lotus_set_error(const char* fmt, ...);
 static inline int ceil_div(int64_t a, int64_t b) { return (int)((a + b - 1) / b); }
 static const int kNumSM = 148;  // B200
 
+// ---- programmatic dependent launch (PDL) ----
+// The step is ~700 dependent launches of 5-40 us kernels on one stream; with plain launches every boundary pays the previous grid's
+// drain + the next grid's launch and prologue in series.  Kernels launched through launch_pdl() may be scheduled while the previous
+// kernel of the stream is still draining; they call pdl_wait() BEFORE their first access to global memory (it returns once the
+// previous grid has completed and its writes are visible) and pdl_launch_dependents() right after, which lets the next kernel's CTAs
+// take SM slots as this grid's CTAs retire.  Both instructions are no-ops in a kernel launched without the attribute.
+// LOTUS_NO_PDL=1 turns the attribute off (A/B knob, read once).
+#include <stdlib.h>
+static inline bool pdl_enabled() {
+  static int v = -1;
+  if (v < 0) { const char* e = getenv("LOTUS_NO_PDL"); v = (e && atoi(e) != 0) ? 0 : 1; }
+  return v != 0;
+}
+template <typename... KArgs, typename... Args>
+static inline cudaError_t launch_pdl(void (*kern)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t st, Args... args) {
+  cudaLaunchConfig_t cfg;
+  memset(&cfg, 0, sizeof(cfg));
+  cfg.gridDim = grid; cfg.blockDim = block; cfg.dynamicSmemBytes = smem; cfg.stream = st;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[0].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = attr; cfg.numAttrs = pdl_enabled() ? 1 : 0;
+  return cudaLaunchKernelEx(&cfg, kern, KArgs(args)...);
+}
+__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+__device__ __forceinline__ void pdl_launch_dependents() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+
 // ---- device helpers ----
 __device__ __forceinline__ float warp_sum(float v) {
 #pragma unroll

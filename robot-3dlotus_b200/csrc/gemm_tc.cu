@@ -123,6 +123,24 @@ k_gemm_tc(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUt
     if (p.residual) asm volatile("prefetch.tensormap [%0];" ::"l"(&map_res) : "memory");
     if (p.out2) asm volatile("prefetch.tensormap [%0];" ::"l"(&map_out2) : "memory");
   }
+  const bool a_gather = (p.a_mode == OP_K_GATHER || p.a_mode == OP_MN_GATHER);
+  const bool b_gather = (p.b_mode == OP_MN_GATHER);
+  const bool a_mn = (p.a_mode == OP_MN_TMA || p.a_mode == OP_MN_GATHER), b_mn = (p.b_mode >= OP_MN_TMA);
+  const bool a_tmag = p.a_mode == OP_K_TMAGATHER;
+  const int PAIR = p.pair_commit;
+
+  if (threadIdx.x == 0) {
+    // TMA producer + the gather producers: every thread's cp.async completion (async mode) or one elected lane per warp
+    uint32_t full_count = 1 + ((a_gather || b_gather) ? (p.async_arrive ? EPI_THREADS : EPI_THREADS / 32) : 0);
+    for (int s = 0; s < STAGES; ++s) { mbar_init(&full[s], full_count); mbar_init(&empty[s], 1); }
+    mbar_init(tmem_full, 1);
+    mbar_init(res_full, 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  if (warp == 1) tmem_alloc(tmem_slot, BN);   // BN in {64,128}: power of two >= 32
+  // programmatic dependent launch: nothing above read global data; from here on the previous kernel's results are needed
+  pdl_wait();
+  pdl_launch_dependents();
   // reduction range of this CTA
   int tap = 0, Kext = p.K, kb0, kb1;
   if (p.k_dev) {
@@ -139,21 +157,6 @@ k_gemm_tc(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUt
     kb1 = min(nkb, kb0 + p.kb_begin_stride);
   }
   const int num_kb = max(0, kb1 - kb0);
-  const bool a_gather = (p.a_mode == OP_K_GATHER || p.a_mode == OP_MN_GATHER);
-  const bool b_gather = (p.b_mode == OP_MN_GATHER);
-  const bool a_mn = (p.a_mode == OP_MN_TMA || p.a_mode == OP_MN_GATHER), b_mn = (p.b_mode >= OP_MN_TMA);
-  const bool a_tmag = p.a_mode == OP_K_TMAGATHER;
-  const int PAIR = p.pair_commit;
-
-  if (threadIdx.x == 0) {
-    // TMA producer + the gather producers: every thread's cp.async completion (async mode) or one elected lane per warp
-    uint32_t full_count = 1 + ((a_gather || b_gather) ? (p.async_arrive ? EPI_THREADS : EPI_THREADS / 32) : 0);
-    for (int s = 0; s < STAGES; ++s) { mbar_init(&full[s], full_count); mbar_init(&empty[s], 1); }
-    mbar_init(tmem_full, 1);
-    mbar_init(res_full, 1);
-    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
-  }
-  if (warp == 1) tmem_alloc(tmem_slot, BN);   // BN in {64,128}: power of two >= 32
   if (threadIdx.x >= 64 && threadIdx.x - 64 < BN) {   // stage the bias slice once (one coalesced load instead of per-element loads)
     int n = n0 + threadIdx.x - 64;
     sBias[threadIdx.x - 64] = (p.bias && n < p.N) ? p.bias[n] : 0.f;
@@ -619,11 +622,11 @@ static int launch(const Operand& A, const Operand& B, Params p, int BN, int spli
   if (BN == 128) {
     static bool set128 = false;
     if (!set128) { cudaFuncSetAttribute(k_gemm_tc<128>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024); set128 = true; }
-    k_gemm_tc<128><<<grid, NUM_THREADS, smem, st>>>(ma, mb, mo, mr, mo2, p);
+    launch_pdl(k_gemm_tc<128>, grid, dim3(NUM_THREADS), smem, st, ma, mb, mo, mr, mo2, p);
   } else {
     static bool set64 = false;
     if (!set64) { cudaFuncSetAttribute(k_gemm_tc<64>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024); set64 = true; }
-    k_gemm_tc<64><<<grid, NUM_THREADS, smem, st>>>(ma, mb, mo, mr, mo2, p);
+    launch_pdl(k_gemm_tc<64>, grid, dim3(NUM_THREADS), smem, st, ma, mb, mo, mr, mo2, p);
   }
   e = cudaGetLastError();
   if (e != cudaSuccess) { lotus_set_error("gemm_tc launch: %s", cudaGetErrorString(e)); return 1; }

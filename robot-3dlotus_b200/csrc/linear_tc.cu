@@ -100,6 +100,11 @@ k_lin(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtenso
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
+  // Programmatic dependent launch: everything above (barriers, TMEM, descriptor prefetch) touched no global data and may run while
+  // the previous kernel of the stream drains; global reads / writes start below.  The dependents of THIS kernel may be scheduled as
+  // soon as every CTA is past this point (they wait at their own griddepcontrol.wait until this grid has completed and flushed).
+  pdl_wait();
+  pdl_launch_dependents();
 
   if (warp == 0) {
     // ===================== TMA producer =====================
@@ -411,18 +416,25 @@ static int launch(const void* A, int64_t lda, const void* B, int64_t ldb, Params
   if (!rc && out2) rc = make_map(&mo2, out2, p.M, p.N, p.ldo, box_cols, BM, false);
   if (rc) return rc;
   const int threads = p.colsum ? (COL_WARP0 + COL_WARPS) * 32 : COL_WARP0 * 32;
+  cudaLaunchConfig_t cfg;
+  memset(&cfg, 0, sizeof(cfg));
+  cfg.gridDim = dim3(grid); cfg.blockDim = dim3(threads); cfg.dynamicSmemBytes = smem; cfg.stream = st;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[0].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = attr; cfg.numAttrs = pdl_enabled() ? 1 : 0;
   if (BN == 128) {
     static bool set = false;
     if (!set) { cudaFuncSetAttribute(k_lin<128>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024); set = true; }
-    k_lin<128><<<grid, threads, smem, st>>>(ma, mb, mo, mr, mo2, p);
+    cudaLaunchKernelEx(&cfg, k_lin<128>, ma, mb, mo, mr, mo2, p);
   } else if (BN == 192) {
     static bool set = false;
     if (!set) { cudaFuncSetAttribute(k_lin<192>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024); set = true; }
-    k_lin<192><<<grid, threads, smem, st>>>(ma, mb, mo, mr, mo2, p);
+    cudaLaunchKernelEx(&cfg, k_lin<192>, ma, mb, mo, mr, mo2, p);
   } else {
     static bool set = false;
     if (!set) { cudaFuncSetAttribute(k_lin<64>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024); set = true; }
-    k_lin<64><<<grid, threads, smem, st>>>(ma, mb, mo, mr, mo2, p);
+    cudaLaunchKernelEx(&cfg, k_lin<64>, ma, mb, mo, mr, mo2, p);
   }
   cudaError_t e = cudaGetLastError();
   if (e != cudaSuccess) { lotus_set_error("linear_tc launch: %s", cudaGetErrorString(e)); return 1; }

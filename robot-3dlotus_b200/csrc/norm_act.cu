@@ -140,6 +140,8 @@ __global__ void __launch_bounds__(256) k_ln_fwd_vec(const bf16_t* __restrict__ x
                                                     const bf16_t* __restrict__ residual, const float* __restrict__ gamma,
                                                     const float* __restrict__ beta, float* __restrict__ mean,
                                                     float* __restrict__ rstd, int64_t rows, int C, int lpr, float eps) {
+  pdl_wait();                                                    // programmatic dependent launch (common.cuh)
+  pdl_launch_dependents();
   const int lane = threadIdx.x & 31, lig = lane & (lpr - 1), rpw = 32 / lpr;
   const int nvec = C >> 3;
   const int64_t warps = (int64_t)gridDim.x * (blockDim.x >> 5);
@@ -206,6 +208,8 @@ __global__ void __launch_bounds__(256, U == 2 ? 3 : 1) k_ln_bwd_vec(const TDY* _
   const int nvec = C >> 3;
   for (int c = threadIdx.x; c < 2 * C; c += blockDim.x) sacc[c] = 0.f;
   __syncthreads();
+  pdl_wait();                                                    // programmatic dependent launch (common.cuh)
+  pdl_launch_dependents();
   float ag[VPL][8], ab[VPL][8], g[VPL][8];
 #pragma unroll
   for (int j = 0; j < VPL; ++j) {
@@ -310,7 +314,7 @@ static int ln_fwd_impl(const void* x, int x_inner, int64_t x_outer_stride, int64
       (!residual || aligned16(residual)) && aligned16(gamma) && aligned16(beta)) {
     int lpr = pick_lpr(C), vpl = ceil_div(C >> 3, lpr), rpw = 32 / lpr;
     cudaStream_t st = (cudaStream_t)stream_;
-#define LNF(V) k_ln_fwd_vec<V><<<min(ceil_div(ceil_div(rows, rpw), 8), resident_blocks(k_ln_fwd_vec<V>, 256, 0)), 256, 0, st>>>((const bf16_t*)x, xm, (bf16_t*)y, ym, (const bf16_t*)residual, gamma, beta, mean, rstd, rows, C, lpr, eps)
+#define LNF(V) launch_pdl(k_ln_fwd_vec<V>, dim3(min(ceil_div(ceil_div(rows, rpw), 8), resident_blocks(k_ln_fwd_vec<V>, 256, 0))), dim3(256), 0, st, (const bf16_t*)x, xm, (bf16_t*)y, ym, (const bf16_t*)residual, gamma, beta, mean, rstd, rows, C, lpr, eps)
     if (vpl == 1) LNF(1); else if (vpl == 2) LNF(2); else if (vpl == 3) LNF(3); else LNF(4);
 #undef LNF
     LOTUS_CUDA_OK();
@@ -354,7 +358,7 @@ static int ln_bwd_impl(const void* dy, int dy_inner, int64_t dy_outer_stride, in
   if (sizeof(T) == 2 && C % 8 == 0 && vec_ok(dym) && vec_ok(xm) && vec_ok(dxm) && aligned16(dy) && aligned16(x) && aligned16(dx) &&
       aligned16(gamma)) {
     int lpr = pick_lpr(C), vpl = ceil_div(C >> 3, lpr), rpw = 32 / lpr;
-#define LNB(V, U) k_ln_bwd_vec<V, U, TDY><<<min(ceil_div(ceil_div(rows, rpw * U), 8), resident_blocks(k_ln_bwd_vec<V, U, TDY>, 256, smem)), 256, smem, st>>>((const TDY*)dy, dym, (const bf16_t*)x, xm, (bf16_t*)dx, dxm, gamma, mean, rstd, dgamma, dbeta, rows, C, lpr, accumulate_dx)
+#define LNB(V, U) launch_pdl(k_ln_bwd_vec<V, U, TDY>, dim3(min(ceil_div(ceil_div(rows, rpw * U), 8), resident_blocks(k_ln_bwd_vec<V, U, TDY>, 256, smem))), dim3(256), smem, st, (const TDY*)dy, dym, (const bf16_t*)x, xm, (bf16_t*)dx, dxm, gamma, mean, rstd, dgamma, dbeta, rows, C, lpr, accumulate_dx)
     if (vpl == 1) LNB(1, 2); else if (vpl == 2) LNB(2, 1); else if (vpl == 3) LNB(3, 1); else LNB(4, 1);
 #undef LNB
     LOTUS_CUDA_OK();
@@ -436,6 +440,8 @@ static void col_launch_cfg(int64_t rows, int C, dim3* grid, int* rpb) {
 // 8 bf16 per thread (16-byte accesses); same op codes and dropout mask as k_pointwise
 __global__ void __launch_bounds__(256) k_pointwise_vec(const bf16_t* __restrict__ x, const bf16_t* __restrict__ a, bf16_t* __restrict__ y,
                                                        int64_t nvec, int op, float alpha, float drop_p, uint64_t seed, uint32_t sid) {
+  pdl_wait();                                                    // programmatic dependent launch (common.cuh)
+  pdl_launch_dependents();
   const uint32_t thr = drop_thr(drop_p);
   const float ks = drop_p > 0.f ? drop_scale(thr) : 1.f;
   for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < nvec; i += (int64_t)gridDim.x * blockDim.x) {
@@ -471,6 +477,8 @@ __global__ void __launch_bounds__(256) k_pointwise_vec(const bf16_t* __restrict_
 }
 __global__ void __launch_bounds__(256) k_dropout_vec(const bf16_t* __restrict__ x, bf16_t* __restrict__ y, int64_t nvec, float p,
                                                      uint64_t seed, uint32_t sid) {
+  pdl_wait();                                                    // programmatic dependent launch (common.cuh)
+  pdl_launch_dependents();
   const uint32_t thr = drop_thr(p);
   const float ks = drop_scale(thr);
   for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < nvec; i += (int64_t)gridDim.x * blockDim.x) {
@@ -1017,7 +1025,7 @@ LOTUS_API int lotus_pointwise_bf16(const void* x, const void* a, void* y, int64_
                                    uint64_t seed, uint32_t drop_stream, void* stream_) {
   if (n <= 0) return 0;
   if (n % 8 == 0 && aligned16(x) && aligned16(y) && (!a || aligned16(a))) {
-    k_pointwise_vec<<<min(ceil_div(n / 8, 256), kNumSM * 16), 256, 0, (cudaStream_t)stream_>>>(
+    launch_pdl(k_pointwise_vec, dim3(min(ceil_div(n / 8, 256), kNumSM * 16)), dim3(256), 0, (cudaStream_t)stream_, 
         (const bf16_t*)x, (const bf16_t*)a, (bf16_t*)y, n / 8, op, alpha, drop_p, seed, drop_stream);
     LOTUS_CUDA_OK();
     return 0;
@@ -1172,7 +1180,7 @@ LOTUS_API int lotus_dropout_bf16(const void* x, void* y, int64_t n, float p, uin
   if (n <= 0) return 0;
   LOTUS_CHECK_ARG(p >= 0.f && p < 1.f, "lotus_dropout_bf16: p=%f", p);
   if (n % 8 == 0 && aligned16(x) && aligned16(y)) {
-    k_dropout_vec<<<min(ceil_div(n / 8, 256), kNumSM * 16), 256, 0, (cudaStream_t)stream_>>>((const bf16_t*)x, (bf16_t*)y, n / 8, p, seed,
+    launch_pdl(k_dropout_vec, dim3(min(ceil_div(n / 8, 256), kNumSM * 16)), dim3(256), 0, (cudaStream_t)stream_, (const bf16_t*)x, (bf16_t*)y, n / 8, p, seed,
                                                                                           stream_id);
     LOTUS_CUDA_OK();
     return 0;
