@@ -252,7 +252,10 @@ static void* block_fwd(Ctx& c, const BlockP& b, const StageInfo& sg, void* x0, c
   int n = sg.n, C = b.C, H = b.H, D = C / H;
   sv.n = n; sv.x0 = x0; sv.conv_in = conv_in ? conv_in : x0; sv.own_conv_in = conv_in != nullptr;
   sv.c0 = act(c, n, C);
-  if (c.bf) CALL(lotus_subm_conv_fwd_bf16, sv.conv_in, c.WB[b.conv_w], Pf(c, b.conv_b), sv.c0, sg.nbr3, sg.stride, n, C, C, 27, 0, c.stv);
+  if (c.bf && lotus_subm_conv_splits(n, C, 27 * C) > 1) {          // deep stages: split reduction through an fp32 scratch
+    float* scr = f32(c, (int64_t)n * C);                           // (a few MB at these stages; not handed back: the side stream is live)
+    CALL(lotus_subm_conv_fwd_splitk_bf16, sv.conv_in, c.WB[b.conv_w], Pf(c, b.conv_b), sv.c0, sg.nbr3, sg.stride, n, C, C, 27, scr, c.stv);
+  } else if (c.bf) CALL(lotus_subm_conv_fwd_bf16, sv.conv_in, c.WB[b.conv_w], Pf(c, b.conv_b), sv.c0, sg.nbr3, sg.stride, n, C, C, 27, 0, c.stv);
   else CALL(lotus_subm_conv_fwd_f32, (const float*)sv.conv_in, Pf(c, b.conv_w), Pf(c, b.conv_b), (float*)sv.c0, sg.nbr3, sg.stride, n, C, C, 27, c.stv);
   sv.c1 = act(c, n, C);
   linear_fwd(c, sv.c0, n, b.cpe1, nullptr, sv.c1, 0.f, 0);
@@ -356,7 +359,10 @@ static void block_bwd(Ctx& c, const BlockP& b, const StageInfo& sg, void* D, con
   if (c.bf) {
     if (Gf(c, b.conv_w)) CALL(lotus_subm_conv_wgrad_pairs_bf16, dc0, sv.conv_in, Gf(c, b.conv_w), sg.pairs_out, sg.pairs_in, sg.pair_cnt, sg.stride, n, C, C, 27, gs);
     if (Gf(c, b.conv_b)) CALL(lotus_colsum_bf16, dc0, n, C, Gf(c, b.conv_b), gs);
-    CALL(lotus_subm_conv_dgrad_bf16, dc0, c.WT[b.conv_w], D, dxo, sg.nbr3, sg.stride, n, C, C, 27, 0, c.stv);
+    if (lotus_subm_conv_splits(n, C, 27 * C) > 1) {
+      float* scr = f32(c, (int64_t)n * C);
+      CALL(lotus_subm_conv_dgrad_splitk_bf16, dc0, c.WT[b.conv_w], D, dxo, sg.nbr3, sg.stride, n, C, C, 27, scr, c.stv);
+    } else CALL(lotus_subm_conv_dgrad_bf16, dc0, c.WT[b.conv_w], D, dxo, sg.nbr3, sg.stride, n, C, C, 27, 0, c.stv);
   } else {
     if (Gf(c, b.conv_w)) CALL(lotus_subm_conv_wgrad_f32, (const float*)dc0, (const float*)sv.conv_in, Gf(c, b.conv_w), sg.nbr3, sg.stride, n, C, C, 27, gs);
     if (Gf(c, b.conv_b)) CALL(lotus_colsum_f32, (const float*)dc0, n, C, Gf(c, b.conv_b), gs);

@@ -688,6 +688,79 @@ LOTUS_API int lotus_subm_conv_dgrad_bf16(const void* dy, const void* wt, const v
   return tc::launch(A, B, p, tc::pick_bn(Cin), 1, (cudaStream_t)stream_);
 }
 
+// ---- split-K forms for the deep stages ----
+// With n = 976 / 3210 / 12140 rows the grid of the plain form is 48 / 104 / 190 CTAs, each walking 324 / 216 / 108 k-blocks in series at
+// ~0.5 us per k-block: 120-170 us for tensors a few MB in size, and uneven across SMs.  Here the reduction is cut into `splits` ranges
+// (grid z), the partial tiles are added into an fp32 scratch [n, N] with TMA reduce-add, and a small pass adds the bias / residual and
+// rounds to bf16.  lotus_subm_conv_splits() says how many ranges a shape gets (1 = use the plain entry point, no scratch needed).
+static int conv_splits(int n, int N, int K) {
+  const int bn = tc::pick_bn(N);
+  const int tiles = ((n + 127) / 128) * ((N + bn - 1) / bn);
+  const int num_kb = (K + 63) / 64;
+  int s = (kNumSM * 3) / max(1, tiles);                          // three CTAs of this kernel fit an SM
+  s = min(s, min(8, num_kb / 12));
+  return max(1, s);
+}
+LOTUS_API int lotus_subm_conv_splits(int n, int N, int K) { return conv_splits(n, N, K); }
+
+__global__ void __launch_bounds__(256) k_splitk_finalize(const float* __restrict__ acc, const float* __restrict__ bias,
+                                                         const __nv_bfloat16* __restrict__ residual, __nv_bfloat16* __restrict__ out,
+                                                         int64_t nvec, int C) {
+  pdl_wait();
+  pdl_launch_dependents();
+  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < nvec; i += (int64_t)gridDim.x * blockDim.x) {
+    const float4 a = *(const float4*)(acc + i * 8), b = *(const float4*)(acc + i * 8 + 4);
+    float v[8] = {a.x, a.y, a.z, a.w, b.x, b.y, b.z, b.w};
+    const int c = (int)((i * 8) % C);
+    if (bias) {
+      const float4 p0 = *(const float4*)(bias + c), p1 = *(const float4*)(bias + c + 4);
+      v[0] += p0.x; v[1] += p0.y; v[2] += p0.z; v[3] += p0.w; v[4] += p1.x; v[5] += p1.y; v[6] += p1.z; v[7] += p1.w;
+    }
+    if (residual) {
+      const uint4 q = *(const uint4*)(residual + i * 8);
+      const __nv_bfloat162* qh = (const __nv_bfloat162*)&q;
+#pragma unroll
+      for (int e = 0; e < 4; ++e) { const float2 f = __bfloat1622float2(qh[e]); v[2 * e] += f.x; v[2 * e + 1] += f.y; }
+    }
+    uint4 w;
+    __nv_bfloat162 h0 = __floats2bfloat162_rn(v[0], v[1]), h1 = __floats2bfloat162_rn(v[2], v[3]);
+    __nv_bfloat162 h2 = __floats2bfloat162_rn(v[4], v[5]), h3 = __floats2bfloat162_rn(v[6], v[7]);
+    w.x = *(uint32_t*)&h0; w.y = *(uint32_t*)&h1; w.z = *(uint32_t*)&h2; w.w = *(uint32_t*)&h3;
+    *(uint4*)(out + i * 8) = w;
+  }
+}
+static int splitk_conv(const void* src, const void* wmat, const float* bias, const void* residual, void* out, const int32_t* nbr,
+                       int64_t nbr_stride, int n, int Cred, int N, int K3, int mirror, float* scratch, cudaStream_t st) {
+  const int K = K3 * Cred, splits = conv_splits(n, N, K);
+  LOTUS_CHECK_ARG(scratch != nullptr && N % 8 == 0, "split-K conv: needs an fp32 scratch of n * N floats and N %% 8 == 0 (N=%d)", N);
+  LOTUS_CUDA_CALL(cudaMemsetAsync(scratch, 0, (size_t)n * N * 4, st));
+  Params p = base_params(n, N, K, scratch, N, 1);
+  p.atomic = 1;
+  Operand A{tc::conv_gather_mode(src, K3), nullptr, 0, {(const __nv_bfloat16*)src, nbr, nbr_stride, Cred, Cred / 64, mirror, K3, 0, n}};
+  Operand B{tc::OP_K_TMA, (const __nv_bfloat16*)wmat, (int64_t)K, {}};
+  int rc = tc::launch(A, B, p, tc::pick_bn(N), splits, st);
+  if (rc) return rc;
+  const int64_t nvec = (int64_t)n * N / 8;
+  launch_pdl(k_splitk_finalize, dim3((unsigned)min((int64_t)kNumSM * 8, (nvec + 255) / 256)), dim3(256), 0, st, (const float*)scratch, bias,
+             (const __nv_bfloat16*)residual, (__nv_bfloat16*)out, nvec, N);
+  LOTUS_CUDA_OK();
+  return 0;
+}
+// forward with the reduction split (bf16 output); scratch: n * Cout floats
+LOTUS_API int lotus_subm_conv_fwd_splitk_bf16(const void* x, const void* w, const float* bias, void* y, const int32_t* nbr,
+                                              int64_t nbr_stride, int n, int Cin, int Cout, int K3, float* scratch, void* stream_) {
+  LOTUS_CHECK_ARG(Cin % 64 == 0, "lotus_subm_conv_fwd_splitk_bf16: Cin=%d must be a multiple of 64", Cin);
+  if (n <= 0) return 0;
+  return splitk_conv(x, w, bias, nullptr, y, nbr, nbr_stride, n, Cin, Cout, K3, 0, scratch, (cudaStream_t)stream_);
+}
+// data gradient with the reduction split (bf16 output, optional bf16 residual); scratch: n * Cin floats
+LOTUS_API int lotus_subm_conv_dgrad_splitk_bf16(const void* dy, const void* wt, const void* residual, void* dx, const int32_t* nbr,
+                                                int64_t nbr_stride, int n, int Cin, int Cout, int K3, float* scratch, void* stream_) {
+  LOTUS_CHECK_ARG(Cout % 64 == 0, "lotus_subm_conv_dgrad_splitk_bf16: Cout=%d must be a multiple of 64", Cout);
+  if (n <= 0) return 0;
+  return splitk_conv(dy, wt, nullptr, residual, dx, nbr, nbr_stride, n, Cout, Cin, K3, 1, scratch, (cudaStream_t)stream_);
+}
+
 // wgrad: dw[co, d, ci] (fp32) += sum_p dy[p,co] * x[nbr[d][p], ci]
 LOTUS_API int lotus_subm_conv_wgrad_bf16(const void* dy, const void* x, float* dw, const int32_t* nbr, int64_t nbr_stride,
                                          int n, int Cin, int Cout, int K3, void* stream_) {

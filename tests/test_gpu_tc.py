@@ -150,6 +150,16 @@ def test_subm_conv_bf16(cin, cout):
     dx = torch.empty(n, cin, device=DEV, dtype=torch.bfloat16)
     L.lotus_subm_conv_dgrad_bf16(P(dyd), P(wt), None, P(dx), P(stg.nbr3), stg.stride_alloc, n, cin, cout, 27, 0, None)
     assert rel(dx.float(), xr.grad) < 1e-2
+    # split-K forms (deep stages): same contraction, reduction cut over the grid, partials met in an fp32 scratch
+    assert L.cdll.lotus_subm_conv_splits(n, cout, 27 * cin) > 1 and L.cdll.lotus_subm_conv_splits(96652, 64, 27 * 64) == 1   # returns a count, not a status
+    res = bf(torch.randn(n, cin, generator=g)).to(DEV)
+    y2 = torch.empty_like(y)
+    scr = torch.empty(n * max(cin, cout), device=DEV, dtype=torch.float32)
+    L.lotus_subm_conv_fwd_splitk_bf16(P(xd), P(wd), P(bd), P(y2), P(stg.nbr3), stg.stride_alloc, n, cin, cout, 27, P(scr), None)
+    assert rel(y2.float(), yr) < 1e-2 and rel(y2.float(), y.float()) < 6e-3
+    dx2 = torch.empty_like(dx)
+    L.lotus_subm_conv_dgrad_splitk_bf16(P(dyd), P(wt), P(res), P(dx2), P(stg.nbr3), stg.stride_alloc, n, cin, cout, 27, P(scr), None)
+    assert rel(dx2.float(), xr.grad + res.float().cpu()) < 1e-2
     dw = torch.zeros(cout, 27, cin, device=DEV, dtype=torch.float32)
     L.lotus_subm_conv_wgrad_bf16(P(dyd), P(xd), P(dw), P(stg.nbr3), stg.stride_alloc, n, cin, cout, 27, None)
     torch.cuda.synchronize()
