@@ -131,7 +131,8 @@ k_gemm_tc(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUt
 
   if (threadIdx.x == 0) {
     // TMA producer + the gather producers: every thread's cp.async completion (async mode) or one elected lane per warp
-    uint32_t full_count = 1 + ((a_gather || b_gather) ? (p.async_arrive ? EPI_THREADS : EPI_THREADS / 32) : 0);
+    const bool warp_arrive = !p.async_arrive || (p.a_mode == OP_K_GATHER && p.ldg_gather && p.ga.idx_in_smem);
+    uint32_t full_count = 1 + ((a_gather || b_gather) ? (warp_arrive ? EPI_THREADS / 32 : EPI_THREADS) : 0);
     for (int s = 0; s < STAGES; ++s) { mbar_init(&full[s], full_count); mbar_init(&empty[s], 1); }
     mbar_init(tmem_full, 1);
     mbar_init(res_full, 1);
@@ -214,11 +215,12 @@ k_gemm_tc(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUt
         uint32_t tx = (a_gather ? 0 : A_BYTES) + (b_gather ? 0 : B_BYTES);
         if (p.debug & 128) tx -= B_BYTES;                  // dev knobs: no B / no A loads (timing experiments only)
         if ((p.debug & 512) && !a_gather) tx -= A_BYTES;
-        for (int i = 0; i < num_kb; ++i) {
-          int s = i % STAGES, ph = (i / STAGES) & 1;
+        // (ring position and phase are carried, not recomputed: STAGES is a run-time value, and an integer division in a
+        // single-thread loop is ~40 dependent instructions -- the k-block rate of these role loops is set by instruction latency)
+        int s = 0, ph = 0, k0 = kb0 * BK;
+        for (int i = 0; i < num_kb; ++i, k0 += BK, ph ^= (s + 1 == STAGES), s = (s + 1 == STAGES) ? 0 : s + 1) {
           mbar_wait_hot(&empty[PAIR ? (s >> 1) : s], ph ^ 1);
           mbar_arrive_expect_tx(&full[s], tx);
-          int k0 = (kb0 + i) * BK;
           if (!a_gather && !(p.debug & 512)) {
             if (!a_mn) tma_load_2d(sA + s * A_BYTES, &map_a, &full[s], k0, m0);
             else { tma_load_2d(sA + s * A_BYTES, &map_a, &full[s], m0, k0); tma_load_2d(sA + s * A_BYTES + 8192, &map_a, &full[s], m0 + 64, k0); }
@@ -239,24 +241,31 @@ k_gemm_tc(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUt
         // loads and the MMAs knocked out: 6 stages, warp-uniform role loops, one commit per two stages, short try_wait hints)
         uint32_t idesc = (1u << 4) | (1u << 7) | (1u << 10) | ((a_mn ? 1u : 0u) << 15) | ((b_mn ? 1u : 0u) << 16) |
                          ((uint32_t)(BN >> 3) << 17) | ((uint32_t)(BM >> 4) << 24);
+        // Descriptors: built once; the start-address field (bits 0-13, units of 16 bytes) is advanced by plain additions
+        // (shared-memory addresses stay below 2^18, so no carry leaves the field).  K-major: +32 B per 16-element K step inside
+        // the 128-B swizzle span; MN-major: +2 k-groups of 1024 B.  The loop carries ring position and phase: as a chain of
+        // dependent instructions in ONE thread, the old form (i % STAGES, i / STAGES, eight make_desc per k-block) was ~700 cycles per
+        // k-block, which -- not tcgen05.commit -- was the "fixed ~380 ns per k-block" every variant of this pipeline ran at.
+        const uint64_t da0 = a_mn ? make_desc(smem_u32(sA), 8192, 1024) : make_desc(smem_u32(sA), 16, 1024);
+        const uint64_t db0 = b_mn ? make_desc(smem_u32(sB), 8192, 1024) : make_desc(smem_u32(sB), 16, 1024);
+        const uint32_t a_kstep = a_mn ? (2048u >> 4) : (32u >> 4), b_kstep = b_mn ? (2048u >> 4) : (32u >> 4);
+        const bool gen_fence = (a_gather || b_gather) && p.async_arrive;
+        int s = 0, ph = 0;
         for (int i = 0; i < num_kb; ++i) {
-          int s = i % STAGES, ph = (i / STAGES) & 1;
           mbar_wait_hot(&full[s], ph);
-          if ((a_gather || b_gather) && p.async_arrive) fence_proxy_async();   // cp.async (generic proxy) data -> the MMA's async proxy
+          if (gen_fence) fence_proxy_async();   // cp.async (generic proxy) data -> the MMA's async proxy
           if (!(p.debug & 1024)) tc_fence_after();
           if (i == 0) TS(2);
-          uint32_t a_addr = smem_u32(sA + s * A_BYTES), b_addr = smem_u32(sB + s * B_BYTES);
+          const uint64_t da = da0 + (uint64_t)((uint32_t)s * (A_BYTES >> 4)), db = db0 + (uint64_t)((uint32_t)s * (B_BYTES >> 4));
 #pragma unroll
           for (int k = 0; k < BK / 16; ++k) {
-            // K-major: +32 B per 16-element K step inside the 128-B swizzle span; MN-major: +2 k-groups of 1024 B
-            uint64_t da = a_mn ? make_desc(a_addr + k * 2048, 8192, 1024) : make_desc(a_addr + k * 32, 16, 1024);
-            uint64_t db = b_mn ? make_desc(b_addr + k * 2048, 8192, 1024) : make_desc(b_addr + k * 32, 16, 1024);
-            if (!(p.debug & 256)) umma_bf16(tmem_base, da, db, idesc, (i > 0 || k > 0) ? 1u : 0u);
+            if (!(p.debug & 256)) umma_bf16(tmem_base, da + (uint64_t)(k * a_kstep), db + (uint64_t)(k * b_kstep), idesc, (i > 0 || k > 0) ? 1u : 0u);
           }
           // frees the smem stage(s) when these MMAs retire; pair mode: ONE commit per two stages (tcgen05.commit arrivals
           // retire at a fixed ~380 ns each -- the whole pipeline advanced one k-block per commit whatever it loaded or multiplied)
           if (!PAIR || (s & 1) || i == num_kb - 1) umma_commit(&empty[PAIR ? (s >> 1) : s]);
           if (i == num_kb - 1) { umma_commit(tmem_full); TS(3); }  // accumulator complete
+          if (++s == STAGES) { s = 0; ph ^= 1; }
         }
       }
     } else if ((a_gather || b_gather) && (warp < 6 || p.async_arrive)) {
@@ -282,20 +291,32 @@ k_gemm_tc(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUt
         int kpt = (kb0 + i) * BK + (t >> 1);
         return (kpt < Kext) ? b_idx[kpt] : -1;
       };
-      int a_r0 = a_row_of(grp), a_r1 = a_row_of(grp + ngrp), b_r0 = b_row_of(grp), b_r1 = b_row_of(grp + ngrp);
+      const bool mn_rows = p.a_mode == OP_MN_GATHER || b_gather;    // only the MN-major gathers look rows up per k-block
+      int a_r0 = -1, a_r1 = -1, b_r0 = -1, b_r1 = -1;
+      if (mn_rows) { a_r0 = a_row_of(grp); a_r1 = a_row_of(grp + ngrp); b_r0 = b_row_of(grp); b_r1 = b_row_of(grp + ngrp); }
+      // ring position / phase / (tap, channel block) of k-block i are carried along (no run-time divisions in the loop: eight
+      // producer warps x ~330 instructions per k-block made these kernels ISSUE-bound at ~0.5 us per k-block per SM)
+      int s = grp % STAGES, ph = (grp / STAGES) & 1;
+      int tp_c = 0, cb_c = 0;                                       // K-major gather: tap and 64-channel block of k-block kb0 + i
+      if (p.a_mode == OP_K_GATHER) { tp_c = (kb0 + grp) / p.ga.kb_per_tap; cb_c = (kb0 + grp) - tp_c * p.ga.kb_per_tap; }
+      int s_lag = 0;                                                // commit/wait_group mode: stage of k-block i - LAG
       for (int i = grp; i < num_kb + (p.async_arrive ? 0 : LAG); i += ngrp) {
         if (i < num_kb) {
-          int s = i % STAGES, ph = (i / STAGES) & 1;
-          const int a_row = a_r0, b_row = b_r0;
-          a_r0 = a_r1; b_r0 = b_r1;
-          a_r1 = a_row_of(i + 2 * ngrp); b_r1 = b_row_of(i + 2 * ngrp);
-          mbar_wait_hot(&empty[PAIR ? (s >> 1) : s], ph ^ 1);
+          int a_row = -1, b_row = -1;
+          if (mn_rows) {
+            a_row = a_r0; b_row = b_r0;
+            a_r0 = a_r1; b_r0 = b_r1;
+            a_r1 = a_row_of(i + 2 * ngrp); b_r1 = b_row_of(i + 2 * ngrp);
+          }
+          // one lane per warp polls the barrier word (fewer spinning threads competing for issue slots)
+          if (lane == 0) mbar_wait_hot(&empty[PAIR ? (s >> 1) : s], ph ^ 1);
+          __syncwarp();
           int kb = kb0 + i;
           if (p.a_mode == OP_K_GATHER && p.ldg_gather && p.ga.idx_in_smem && p.async_arrive) {
             // Coalesced gather: EIGHT LANES read one whole 128-byte source row (lane = 16-byte chunk), four rows per warp
             // instruction, through registers.  With one row per lane (the cp.async form below) every warp instruction touches 32
             // different lines = 32 L1TEX wavefronts, and the gather -- not the tensor pipe -- sets the k-block rate.
-            const int tp = kb / p.ga.kb_per_tap, c0 = (kb - tp * p.ga.kb_per_tap) * BK;
+            const int tp = tp_c, c0 = cb_c * BK;
             const int ch = t & 7, r0 = (t >> 5) * 32 + ((t & 31) >> 3);
             uint4 v[8];
 #pragma unroll
@@ -312,7 +333,10 @@ k_gemm_tc(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUt
               *(uint4*)(dstt + row * 128 + ((ch ^ (row & 7)) << 4)) = v[q];
             }
             fence_proxy_async();                               // generic-proxy stores -> visible to the MMA's async proxy
-            mbar_arrive(&full[s]);                             // one arrival per producer thread, like the cp.async form
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&full[s]);              // one arrival per producer WARP (full_count is set to match)
+            s += ngrp; if (s >= STAGES) { s -= STAGES; ph ^= 1; }
+            cb_c += ngrp; while (cb_c >= p.ga.kb_per_tap) { cb_c -= p.ga.kb_per_tap; ++tp_c; }
             continue;
           }
           if (p.a_mode == OP_K_GATHER) {
@@ -320,7 +344,7 @@ k_gemm_tc(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUt
             // thread t stages row (m0 + t): 8 chunks of 16 B.  (Measured alternatives, all slower or equal: four whole rows per
             // warp instruction, zero stores for absent rows, TMA tile::gather4 -- the loop is bound by barrier traffic, not by
             // the copies: with the copies AND the B loads knocked out it ran at the same ns per k-block.)
-            int tp = kb / p.ga.kb_per_tap, c0 = (kb - tp * p.ga.kb_per_tap) * BK;
+            int tp = tp_c, c0 = cb_c * BK;
             int src_row;
             if (p.ga.idx_in_smem) {
               src_row = sIdx[tp * EPI_THREADS + t];
@@ -344,16 +368,23 @@ k_gemm_tc(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUt
           // the barrier tracks this thread's copies: it arrives when they land, the thread moves on to the next free stage
           // (with commit/wait_group the slack left for the MMA round trip was STAGES - LAG = 2 stages: ~650 ns per k-block)
           if (i < num_kb) {
-            cp_async_mbar_arrive_noinc(&full[i % STAGES]);
+            cp_async_mbar_arrive_noinc(&full[s]);
+            s += ngrp; if (s >= STAGES) { s -= STAGES; ph ^= 1; }
+            cb_c += ngrp; while (cb_c >= p.ga.kb_per_tap && p.a_mode == OP_K_GATHER) { cb_c -= p.ga.kb_per_tap; ++tp_c; }
           }
           continue;
+        }
+        if (i < num_kb) {
+          s += 1; if (s >= STAGES) { s -= STAGES; ph ^= 1; }       // (ngrp == 1 in this mode)
+          cb_c += 1; while (cb_c >= p.ga.kb_per_tap && p.a_mode == OP_K_GATHER) { cb_c -= p.ga.kb_per_tap; ++tp_c; }
         }
         cp_async_commit();
         if (i >= LAG) {
           if (LAG == 4) cp_async_wait<4>(); else if (LAG == 3) cp_async_wait<3>(); else if (LAG == 2) cp_async_wait<2>(); else cp_async_wait<1>();
           fence_proxy_async();
           __syncwarp();                                  // every lane's copies have landed and are fenced: ONE arrival per warp
-          if (lane == 0) mbar_arrive(&full[(i - LAG) % STAGES]);   // (128 per-thread arrivals serialised on the barrier word)
+          if (lane == 0) mbar_arrive(&full[s_lag]);      // (128 per-thread arrivals serialised on the barrier word)
+          if (++s_lag == STAGES) s_lag = 0;
         }
       }
     }

@@ -110,7 +110,10 @@ k_lin(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtenso
     // ===================== TMA producer =====================
     if (lane == 0) {
       const int box_cols = p.out_fp32 ? 32 : 64;
-      uint32_t g = 0;                                           // running k-block counter over all my tiles (ring position)
+      // The ring position and phase are CARRIED (STAGES is a run-time value): these role loops are chains of dependent instructions in
+      // one thread, and `g % STAGES`, `g / STAGES` plus eight descriptor constructions per k-block cost ~700 cycles -- that, not
+      // tcgen05.commit, was the "fixed ~380 ns per k-block" of this pipeline.
+      int s = 0, ph = 0;
       int it = 0;
       for (int t = blockIdx.x; t < p.num_tiles; t += gridDim.x, ++it) {
         const int m0 = (t / p.n_tiles) * BM, n0 = (t % p.n_tiles) * BN;
@@ -120,12 +123,12 @@ k_lin(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtenso
           mbar_arrive_expect_tx(&res_full[rb], (uint32_t)tile_bytes);
           for (int j = 0; j < BN / box_cols; ++j) tma_load_2d(sAux + rb * tile_bytes + j * 16384, &map_res, &res_full[rb], n0 + j * box_cols, m0);
         }
-        for (int kb = 0; kb < num_kb; ++kb, ++g) {
-          const int s = g % STAGES, ph = (g / STAGES) & 1;
+        for (int kb = 0; kb < num_kb; ++kb) {
           mbar_wait(&empty[s], ph ^ 1);
           mbar_arrive_expect_tx(&full[s], A_BYTES + B_BYTES);
           tma_load_2d(sA + s * A_BYTES, &map_a, &full[s], kb * BK, m0);
           tma_load_2d(sB + s * B_BYTES, &map_b, &full[s], kb * BK, n0);
+          if (++s == STAGES) { s = 0; ph ^= 1; }
         }
       }
     }
@@ -133,22 +136,25 @@ k_lin(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtenso
     // ===================== MMA issuer =====================
     if (lane == 0) {
       const uint32_t idesc = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(BN >> 3) << 17) | ((uint32_t)(BM >> 4) << 24);
-      uint32_t g = 0;
+      // descriptors are built once; the start-address field (bits 0-13, units of 16 bytes) advances by plain additions: +2 per
+      // 16-element K step inside the 128-byte swizzle span, + stage size per ring slot (shared addresses < 2^18: no carry out)
+      const uint64_t da0 = make_desc(smem_u32(sA), 16, 1024), db0 = make_desc(smem_u32(sB), 16, 1024);
+      int s = 0, ph = 0;
       int it = 0;
       for (int t = blockIdx.x; t < p.num_tiles; t += gridDim.x, ++it) {
         const int ab = it & 1;
         mbar_wait(&tmem_empty[ab], ((it >> 1) & 1) ^ 1);       // the epilogue has drained this accumulator (two tiles ago)
         tc_fence_after();
         const uint32_t d_tmem = tmem_base + (uint32_t)(ab * BN);
-        for (int kb = 0; kb < num_kb; ++kb, ++g) {
-          const int s = g % STAGES, ph = (g / STAGES) & 1;
+        for (int kb = 0; kb < num_kb; ++kb) {
           mbar_wait(&full[s], ph);
           tc_fence_after();
-          const uint32_t a_addr = smem_u32(sA + s * A_BYTES), b_addr = smem_u32(sB + s * B_BYTES);
+          const uint64_t da = da0 + (uint64_t)((uint32_t)s * (A_BYTES >> 4)), db = db0 + (uint64_t)((uint32_t)s * ((uint32_t)B_BYTES >> 4));
 #pragma unroll
           for (int k = 0; k < BK / 16; ++k)
-            umma_bf16(d_tmem, make_desc(a_addr + k * 32, 16, 1024), make_desc(b_addr + k * 32, 16, 1024), idesc, (kb > 0 || k > 0) ? 1u : 0u);
+            umma_bf16(d_tmem, da + (uint64_t)(2 * k), db + (uint64_t)(2 * k), idesc, (kb > 0 || k > 0) ? 1u : 0u);
           umma_commit(&empty[s]);                               // stage free once these MMAs have read it
+          if (++s == STAGES) { s = 0; ph ^= 1; }
         }
         umma_commit(&tmem_full[ab]);                            // accumulator complete
       }
@@ -316,13 +322,14 @@ k_lin(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtenso
     const int cw = warp - COL_WARP0;
     const int c = lane & 7, rg = lane >> 3;                     // 16-byte chunk (8 k-columns) x interleaved row group
     float* myCol = sCol + cw * num_kb * BK;
-    uint32_t g = 0;
+    int s = -1, ph = 0, turn = -1;                               // ring position / phase / (k-block counter mod CW), carried
     for (int t = blockIdx.x; t < p.num_tiles; t += gridDim.x) {
       const int mt = t / p.n_tiles, nt = t % p.n_tiles;
       const bool mine = nt == (mt % p.n_tiles);
-      for (int kb = 0; kb < num_kb; ++kb, ++g) {
-        if ((int)(g % CW) != cw) continue;
-        const int s = g % STAGES, ph = (g / STAGES) & 1;
+      for (int kb = 0; kb < num_kb; ++kb) {
+        if (++s == STAGES) { s = 0; ph ^= 1; }
+        if (++turn == CW) turn = 0;
+        if (turn != cw) continue;
         if (lane == 0) mbar_wait(&full[s], ph);
         __syncwarp();
         if (mine) {

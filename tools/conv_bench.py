@@ -21,6 +21,8 @@ for s, C in chans:
            "dgrad": lambda: L.lotus_subm_conv_dgrad_bf16(P(x), P(wt), None, P(dx), P(stg.nbr3), stg.stride_alloc, n, C, C, 27, 0, None),
            "wgrad": lambda: L.lotus_subm_conv_wgrad_pairs_bf16(P(x), P(x), P(dw), P(stg.pairs_out), P(stg.pairs_in), P(stg.pair_cnt), stg.stride_alloc, n, C, C, 27, None)}
     res = {}
+    only = os.environ.get("FNS")
+    if only: fns = {k: v for k, v in fns.items() if k in only.split(",")}
     for name, fn in fns.items():
         for _ in range(3): fn()
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
@@ -29,4 +31,4 @@ for s, C in chans:
         e1.record(); torch.cuda.synchronize()
         res[name] = e0.elapsed_time(e1) / 10 * 1e3
     pairs = int((stg.nbr3[:, :n] >= 0).sum())
-    print(f"stage {s} n={n} C={C} pairs/pt={pairs / n:.1f}: " + "  ".join(f"{k} {v:7.1f}us" for k, v in res.items()) + f"   useful {2.0 * pairs * C * C / res['fwd'] / 1e6:6.1f} TF/s")
+    print(f"stage {s} n={n} C={C} pairs/pt={pairs / n:.1f}: " + "  ".join(f"{k} {v:7.1f}us" for k, v in res.items()) + (f"   useful {2.0 * pairs * C * C / res['fwd'] / 1e6:6.1f} TF/s" if "fwd" in res else ""))
