@@ -252,7 +252,9 @@ static void* block_fwd(Ctx& c, const BlockP& b, const StageInfo& sg, void* x0, c
   int n = sg.n, C = b.C, H = b.H, D = C / H;
   sv.n = n; sv.x0 = x0; sv.conv_in = conv_in ? conv_in : x0; sv.own_conv_in = conv_in != nullptr;
   sv.c0 = act(c, n, C);
-  if (c.bf && lotus_subm_conv_splits(n, C, 27 * C) > 1) {          // deep stages: split reduction through an fp32 scratch
+  // deep stages, training only: split reduction through an fp32 scratch (the partial tiles are summed in arrival order, so inference
+  // keeps the single-pass form: its output stays bit-reproducible and independent of the size bucket a CUDA-graph replay runs at)
+  if (c.bf && c.train && lotus_subm_conv_splits(n, C, 27 * C) > 1) {
     float* scr = f32(c, (int64_t)n * C);                           // (a few MB at these stages; not handed back: the side stream is live)
     CALL(lotus_subm_conv_fwd_splitk_bf16, sv.conv_in, c.WB[b.conv_w], Pf(c, b.conv_b), sv.c0, sg.nbr3, sg.stride, n, C, C, 27, scr, c.stv);
   } else if (c.bf) CALL(lotus_subm_conv_fwd_bf16, sv.conv_in, c.WB[b.conv_w], Pf(c, b.conv_b), sv.c0, sg.nbr3, sg.stride, n, C, C, 27, 0, c.stv);

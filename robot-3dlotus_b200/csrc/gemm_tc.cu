@@ -131,7 +131,7 @@ k_gemm_tc(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUt
 
   if (threadIdx.x == 0) {
     // TMA producer + the gather producers: every thread's cp.async completion (async mode) or one elected lane per warp
-    const bool warp_arrive = !p.async_arrive || (p.a_mode == OP_K_GATHER && p.ldg_gather && p.ga.idx_in_smem);
+    const bool warp_arrive = !p.async_arrive;
     uint32_t full_count = 1 + ((a_gather || b_gather) ? (warp_arrive ? EPI_THREADS / 32 : EPI_THREADS) : 0);
     for (int s = 0; s < STAGES; ++s) { mbar_init(&full[s], full_count); mbar_init(&empty[s], 1); }
     mbar_init(tmem_full, 1);
@@ -292,6 +292,12 @@ k_gemm_tc(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUt
         return (kpt < Kext) ? b_idx[kpt] : -1;
       };
       const bool mn_rows = p.a_mode == OP_MN_GATHER || b_gather;    // only the MN-major gathers look rows up per k-block
+      // K-major gather, two forms.  cp.async (LDGSTS): asynchronous, but the LSU takes ONE 16-byte request per cycle, absent rows
+      // (zero fills) included -- 1024 cycles per k-block per SM, shared by the resident CTAs.  LDG.128 with eight lanes per row +
+      // STS.128: a quarter of the requests and none for absent rows, but the loads are waited for.  Measured (tools/conv_bench.py):
+      // the sparse 96k-row stage (23 % of the (row, tap) pairs present, 5 waves of CTAs) is 5-8 % faster on the first, every deeper
+      // stage (36-46 % present, one wave) 8-15 % faster on the second; launch() picks by the row count (p.ldg_gather).
+      const bool ldg_path = p.a_mode == OP_K_GATHER && p.ga.idx_in_smem && p.async_arrive && p.ldg_gather;
       int a_r0 = -1, a_r1 = -1, b_r0 = -1, b_r1 = -1;
       if (mn_rows) { a_r0 = a_row_of(grp); a_r1 = a_row_of(grp + ngrp); b_r0 = b_row_of(grp); b_r1 = b_row_of(grp + ngrp); }
       // ring position / phase / (tap, channel block) of k-block i are carried along (no run-time divisions in the loop: eight
@@ -312,7 +318,7 @@ k_gemm_tc(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUt
           if (lane == 0) mbar_wait_hot(&empty[PAIR ? (s >> 1) : s], ph ^ 1);
           __syncwarp();
           int kb = kb0 + i;
-          if (p.a_mode == OP_K_GATHER && p.ldg_gather && p.ga.idx_in_smem && p.async_arrive) {
+          if (ldg_path) {
             // Coalesced gather: EIGHT LANES read one whole 128-byte source row (lane = 16-byte chunk), four rows per warp
             // instruction, through registers.  With one row per lane (the cp.async form below) every warp instruction touches 32
             // different lines = 32 L1TEX wavefronts, and the gather -- not the tensor pipe -- sets the k-block rate.
@@ -334,7 +340,7 @@ k_gemm_tc(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUt
             }
             fence_proxy_async();                               // generic-proxy stores -> visible to the MMA's async proxy
             __syncwarp();
-            if (lane == 0) mbar_arrive(&full[s]);              // one arrival per producer WARP (full_count is set to match)
+            if (lane == 0) mbar_arrive_count(&full[s], 32);    // the warp's 32 arrivals in one instruction (same count as the cp.async form)
             s += ngrp; if (s >= STAGES) { s -= STAGES; ph ^= 1; }
             cb_c += ngrp; while (cb_c >= p.ga.kb_per_tap) { cb_c -= p.ga.kb_per_tap; ++tp_c; }
             continue;
@@ -353,6 +359,8 @@ k_gemm_tc(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUt
               int m = m0 + t;
               src_row = (m < p.M) ? p.ga.idx[(int64_t)tp * p.ga.idx_stride + m] : -1;
             }
+            // (eight lanes per row with cp.async -- four rows per warp instruction -- measured SLOWER than this form: LDGSTS is
+            // handled per thread, 16 bytes per request, whatever the addresses)
             const __nv_bfloat16* src = p.ga.base + (int64_t)max(src_row, 0) * p.ga.row_elems + c0;
             uint8_t* dst = sA + s * A_BYTES + t * 128;
             if (!(p.debug & 64)) {
@@ -627,8 +635,8 @@ static int launch(const Operand& A, const Operand& B, Params p, int BN, int spli
     if (aa < 0) { const char* e = getenv("LOTUS_TC_ASYNC_ARRIVE"); aa = e ? atoi(e) : 1; }
     p.async_arrive = aa;
     static int lg = -1;                                 // dev knob: LOTUS_TC_LDG_GATHER=1 gathers through registers (8 lanes per row)
-    if (lg < 0) { const char* e = getenv("LOTUS_TC_LDG_GATHER"); lg = e ? atoi(e) : 0; }   // measured equal on B200: the conv is bound by L2->SM weight-tile traffic, not by the gather instruction form
-    p.ldg_gather = lg;
+    if (lg < 0) { const char* e = getenv("LOTUS_TC_LDG_GATHER"); lg = e ? atoi(e) : 2; }   // 0 cp.async, 1 LDG + STS, 2 by row count (see the kernel)
+    p.ldg_gather = lg == 2 ? (p.M <= 65536 ? 1 : 0) : lg;
   }
   dim3 grid((p.M + BM - 1) / BM, (p.N + BN - 1) / BN, splits * taps);
   size_t tile_bytes = (size_t)BM * BN * (p.out_fp32 ? 4 : 2);

@@ -35,6 +35,9 @@ __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
 // Hot pipeline hand-offs (TMA producer <-> MMA issuer <-> gather producers): try_wait with a SHORT suspend-time hint.  With the
 // default (system-chosen) time limit a waiter that misses the phase sleeps a fixed quantum: the 4-stage pipelines then advanced
 // one k-block per ~380 ns whatever they loaded or multiplied (measured with loads and MMAs knocked out).
+__device__ __forceinline__ void mbar_arrive_count(uint64_t* bar, uint32_t count) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");
+}
 __device__ __forceinline__ void mbar_wait_hot(uint64_t* bar, uint32_t parity) {
   asm volatile(
       "{\n"
