@@ -701,7 +701,9 @@ LOTUS_API int lotus_linear_wgrad_bf16(const void* dy, const void* x, float* dw, 
   Operand A{tc::OP_MN_TMA, (const __nv_bfloat16*)dy, N, {}}, B{tc::OP_MN_TMA, (const __nv_bfloat16*)x, K, {}};
   int bn = tc::pick_bn(K);
   int tiles = ((N + 127) / 128) * ((K + bn - 1) / bn);
-  int splits = max(1, (kNumSM * 2) / tiles);
+  static int ctas = -1;                                          // CTAs the reduction is cut over: one per SM (measured best at every shape of the step: two per SM doubles the reduce-add traffic onto the same tile); LOTUS_WGRAD_CTAS overrides
+  if (ctas < 0) { const char* e = getenv("LOTUS_WGRAD_CTAS"); ctas = e ? atoi(e) : kNumSM; }
+  int splits = max(1, ctas / tiles);
   return tc::launch(A, B, p, bn, splits, (cudaStream_t)stream_);
 }
 
