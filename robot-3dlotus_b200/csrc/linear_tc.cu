@@ -63,7 +63,7 @@ k_lin(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtenso
   const int out_bufs = p.out_bufs;                             // epilogue staging tiles (TMA store sources)
   uint8_t* sOut = sB + STAGES * B_BYTES;
   uint8_t* sAux = sOut + out_bufs * tile_bytes;                // residual ring [2] (or the pre-activation tile of out2)
-  uint8_t* tail = sAux + (p.has_res ? 2 * tile_bytes : (p.has_out2 ? tile_bytes : 0));
+  uint8_t* tail = sAux + (p.has_res ? 2 * tile_bytes : (p.has_out2 ? out_bufs * tile_bytes : 0));
   uint64_t* full = (uint64_t*)tail;
   uint64_t* empty = full + MAX_STAGES;
   uint64_t* tmem_full = empty + MAX_STAGES;                    // [2]
@@ -174,7 +174,6 @@ k_lin(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtenso
     const bool add_res = p.has_res && p.act != ACT_GELU_GRAD;
     const bool mask_in_float = has_drop && (add_res || p.out_fp32);
     const int box_cols = p.out_fp32 ? 32 : 64;
-    uint8_t* sOut2 = sAux;
     int it = 0;
     for (int t = blockIdx.x; t < p.num_tiles; t += gridDim.x, ++it) {
       const int m0 = (t / p.n_tiles) * BM, n0 = (t % p.n_tiles) * BN;
@@ -184,6 +183,7 @@ k_lin(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtenso
       // finished READING it before it is overwritten -- the most recent store may still be in flight
       if (et == 0) { if (out_bufs == 2) asm volatile("cp.async.bulk.wait_group.read 1;" ::: "memory"); else asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory"); }
       uint8_t* sO = sOut + (out_bufs == 2 ? (it & 1) * tile_bytes : 0);
+      uint8_t* sOut2 = sAux + (out_bufs == 2 ? (it & 1) * tile_bytes : 0);   // pre-activation copy (only without a residual ring)
       if (et < BN) { int n = n0 + et; sBias[et] = (p.bias && n < p.N) ? p.bias[n] : 0.f; }
       named_bar_sync(1, EPI_WARPS * 32);
       if (lane == 0) { mbar_wait(&tmem_full[ab], aph); if (p.has_res) mbar_wait(&res_full[ab], aph); }
@@ -393,12 +393,18 @@ static int launch(const void* A, int64_t lda, const void* B, int64_t ldb, Params
   const int tile_bytes = BM * BN * (p.out_fp32 ? 4 : 2);
   // one staging tile where the epilogue is ALU-bound anyway (GELU + pre-activation copy, gelu' of the fused data gradient):
   // the shared memory goes to ring stages instead
-  p.out_bufs = (p.has_out2 || p.act == ACT_GELU_GRAD) ? 1 : 2;
-  const size_t fixed = 1024 /*alignment slack*/ + (size_t)tile_bytes * p.out_bufs +
-                       (p.has_res ? 2 * (size_t)tile_bytes : (p.has_out2 ? (size_t)tile_bytes : 0)) + 256 /*barriers*/ + (size_t)BN * 4 +
-                       (p.colsum ? (size_t)COL_WARPS * p.num_kb * BK * 4 : 0) + 64;
+  // Two staging tiles (per output) wherever they leave enough ring stages: with one, the epilogue of tile i + 1 waits until the TMA
+  // store of tile i has finished READING the tile -- ~1 us of serialisation per tile on the wide outputs of the MLP GEMMs.
   const size_t stage_bytes = (size_t)A_BYTES + (size_t)BN * BK * 2;
   const size_t budget = 227 * 1024;
+  auto fixed_bytes = [&](int bufs) {
+    return (size_t)1024 /*alignment slack*/ + (size_t)tile_bytes * bufs +
+           (p.has_res ? 2 * (size_t)tile_bytes : (p.has_out2 ? (size_t)bufs * tile_bytes : 0)) + 256 /*barriers*/ + (size_t)BN * 4 +
+           (p.colsum ? (size_t)COL_WARPS * p.num_kb * BK * 4 : 0) + 64;
+  };
+  const int want_stages = p.num_kb >= 4 ? 4 : 2;                 // (bias-gradient mode rounds the ring down to 2 / 4 / 8)
+  p.out_bufs = (fixed_bytes(2) + (size_t)want_stages * stage_bytes <= budget) ? 2 : 1;
+  const size_t fixed = fixed_bytes(p.out_bufs);
   if (fixed + 2 * stage_bytes > budget) { lotus_set_error("linear_tc: shared-memory budget exceeded"); return 2; }
   int stages = (int)((budget - fixed) / stage_bytes);
   if (p.colsum) stages = stages >= 8 ? 8 : (stages >= 4 ? 4 : 2);
