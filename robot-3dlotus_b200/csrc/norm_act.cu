@@ -1105,8 +1105,10 @@ struct CastBatch {
   int tile_start[MAX + 1];   // prefix sum of 32x32 tiles (x D) per entry
   int n;
 };
-__global__ void k_cast_transpose_batch(const __grid_constant__ CastBatch cb) {
-  __shared__ float tile[32][33];
+// 64 x 64 tiles: fp32 rows read as float4 (256-byte segments), both bf16 outputs written as 8-byte vectors (128-byte segments);
+// weights whose A or B is not a multiple of 4 (or whose pointers are not vector aligned) take the scalar path of the same kernel
+__global__ void __launch_bounds__(256) k_cast_transpose_batch(const __grid_constant__ CastBatch cb) {
+  __shared__ float tile[64][65];
   int tid = blockIdx.x;
   int lo = 0, hi = cb.n - 1;
   while (lo < hi) {
@@ -1118,25 +1120,56 @@ __global__ void k_cast_transpose_batch(const __grid_constant__ CastBatch cb) {
   bf16_t* __restrict__ wb = cb.wb[e];
   bf16_t* __restrict__ wt = cb.wt[e];
   int local = tid - cb.tile_start[e];
-  int tb = (B + 31) >> 5, ta = (A + 31) >> 5;
-  int d = local / (ta * tb);
+  const int tb = (B + 63) >> 6, ta = (A + 63) >> 6;
+  const int d = local / (ta * tb);
   local -= d * ta * tb;
-  int a0 = (local / tb) * 32, b0 = (local % tb) * 32;
-  int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
-  for (int i = ty; i < 32; i += 8) {
-    int a = a0 + i, b = b0 + tx;
+  const int a0 = (local / tb) * 64, b0 = (local % tb) * 64;
+  const bool vec = (A % 4 == 0) && (B % 4 == 0) && (((uintptr_t)w & 15) == 0) && (!wb || ((uintptr_t)wb & 7) == 0) && (!wt || ((uintptr_t)wt & 7) == 0);
+  const int tx = threadIdx.x & 15, ty = threadIdx.x >> 4;      // 16 x 16
+  if (vec) {
+#pragma unroll
+    for (int i = ty; i < 64; i += 16) {
+      const int a = a0 + i, b = b0 + 4 * tx;
+      float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+      if (a < A && b < B) {
+        const int64_t o = ((int64_t)a * D + d) * B + b;
+        v = *(const float4*)(w + o);
+        if (wb) {
+          __nv_bfloat162 h0 = __floats2bfloat162_rn(v.x, v.y), h1 = __floats2bfloat162_rn(v.z, v.w);
+          *(uint2*)(wb + o) = make_uint2(*(uint32_t*)&h0, *(uint32_t*)&h1);
+        }
+      }
+      tile[i][4 * tx] = v.x; tile[i][4 * tx + 1] = v.y; tile[i][4 * tx + 2] = v.z; tile[i][4 * tx + 3] = v.w;
+    }
+    __syncthreads();
+    if (wt) {
+#pragma unroll
+      for (int i = ty; i < 64; i += 16) {
+        const int b = b0 + i, a = a0 + 4 * tx;
+        if (a < A && b < B) {
+          __nv_bfloat162 h0 = __floats2bfloat162_rn(tile[4 * tx][i], tile[4 * tx + 1][i]);
+          __nv_bfloat162 h1 = __floats2bfloat162_rn(tile[4 * tx + 2][i], tile[4 * tx + 3][i]);
+          *(uint2*)(wt + ((int64_t)b * D + d) * A + a) = make_uint2(*(uint32_t*)&h0, *(uint32_t*)&h1);
+        }
+      }
+    }
+    return;
+  }
+  const int sx = threadIdx.x & 63, sy = threadIdx.x >> 6;       // 64 x 4
+  for (int i = sy; i < 64; i += 4) {
+    int a = a0 + i, b = b0 + sx;
     float v = 0.f;
     if (a < A && b < B) {
       v = w[((int64_t)a * D + d) * B + b];
       if (wb) wb[((int64_t)a * D + d) * B + b] = __float2bfloat16(v);
     }
-    tile[i][tx] = v;
+    tile[i][sx] = v;
   }
   __syncthreads();
   if (wt) {
-    for (int i = ty; i < 32; i += 8) {
-      int b = b0 + i, a = a0 + tx;
-      if (a < A && b < B) wt[((int64_t)b * D + d) * A + a] = __float2bfloat16(tile[tx][i]);
+    for (int i = sy; i < 64; i += 4) {
+      int b = b0 + i, a = a0 + sx;
+      if (a < A && b < B) wt[((int64_t)b * D + d) * A + a] = __float2bfloat16(tile[sx][i]);
     }
   }
 }
@@ -1152,7 +1185,7 @@ LOTUS_API int lotus_cast_transpose_batch_bf16(const void* const* w, void* const*
       LOTUS_CHECK_ARG(A[j] > 0 && B[j] > 0 && D[j] > 0, "lotus_cast_transpose_batch_bf16: empty weight %d", j);
       cb.w[i] = (const float*)w[j]; cb.wb[i] = (bf16_t*)w_bf16[j]; cb.wt[i] = (bf16_t*)wt_bf16[j];
       cb.A[i] = A[j]; cb.D[i] = D[j]; cb.B[i] = B[j];
-      cb.tile_start[i + 1] = cb.tile_start[i] + ceil_div(A[j], 32) * ceil_div(B[j], 32) * D[j];
+      cb.tile_start[i + 1] = cb.tile_start[i] + ceil_div(A[j], 64) * ceil_div(B[j], 64) * D[j];
     }
     if (cb.tile_start[cb.n] > 0) k_cast_transpose_batch<<<cb.tile_start[cb.n], 256, 0, (cudaStream_t)stream_>>>(cb);
   }

@@ -461,3 +461,23 @@ def test_patch_attention_fused_dropout_mask_matches_simt(H, D, drop_p):
         res[mode] = (y.float(), gr[0].float())
     os.environ.pop("LOTUS_ATTN_SIMT", None)
     assert rel(res["fused"][0], res["simt"][0]) < 2e-2 and rel(res["fused"][1], res["simt"][1]) < 3e-2
+
+
+def test_cast_transpose_batch():
+    """weight staging of the bf16 step: fp32 [A][D][B] -> bf16 same layout + bf16 [B][D][A], all weights in one launch; vector path
+    (A, B multiples of 4) and scalar path (odd extents) against torch"""
+    import ctypes
+    L = pkg("lib").load()
+    g = torch.Generator().manual_seed(11)
+    shapes = [(64, 27, 64), (192, 1, 64), (7, 125, 64), (90, 1, 128), (130, 3, 70), (768, 1, 3072)]
+    ws = [torch.randn(a, d, b, generator=g).to(DEV) for a, d, b in shapes]
+    wb = [torch.empty(a, d, b, device=DEV, dtype=torch.bfloat16) for a, d, b in shapes]
+    wt = [torch.empty(b, d, a, device=DEV, dtype=torch.bfloat16) for a, d, b in shapes]
+    n = len(shapes)
+    VP = ctypes.c_void_p * n
+    IA = ctypes.c_int * n
+    L.lotus_cast_transpose_batch_bf16(VP(*[t.data_ptr() for t in ws]), VP(*[t.data_ptr() for t in wb]), VP(*[t.data_ptr() for t in wt]),
+                                      IA(*[s[0] for s in shapes]), IA(*[s[1] for s in shapes]), IA(*[s[2] for s in shapes]), n, None)
+    torch.cuda.synchronize()
+    for w, b, t in zip(ws, wb, wt):
+        assert torch.equal(b, w.bfloat16()) and torch.equal(t, w.bfloat16().permute(2, 1, 0).contiguous())
