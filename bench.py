@@ -348,6 +348,7 @@ def planner_main(args, rank, world, local):
     dev = torch.device("cuda", local)
     if world > 1:
         import datetime
+        pkg("trainer").nccl_env_defaults()
         torch.distributed.init_process_group("nccl", device_id=dev, timeout=datetime.timedelta(seconds=120))
     L = lib.load()
     cfg = cfgm.production_planner_config()
@@ -473,6 +474,7 @@ def main():
         sys.stdout.flush()
         saved_stdout = os.dup(1)
         os.dup2(2, 1)
+        pkg("trainer").nccl_env_defaults()
         dist.init_process_group("nccl", device_id=dev, timeout=datetime.timedelta(seconds=120))
     cfgm, syn, policy, trainer, lib = pkg("config"), pkg("synthetic"), pkg("policy"), pkg("trainer"), pkg("lib")
     L = lib.load()

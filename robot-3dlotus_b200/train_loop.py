@@ -293,6 +293,8 @@ def main(argv=None):
     torch.cuda.set_device(local)
     dev = torch.device("cuda", local)
     if world > 1:
+        from .trainer import nccl_env_defaults
+        nccl_env_defaults()
         torch.distributed.init_process_group("nccl", device_id=dev)
     if not args.synthetic:
         raise SystemExit("the LMDB keystep dataset reader is outside this path (SURVEY §8f row 2): pass --synthetic N, or call "

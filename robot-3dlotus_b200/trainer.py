@@ -57,6 +57,15 @@ def _completion_group(name, deepest):
 N_GRAD_SLICES = 4
 
 
+
+def nccl_env_defaults():
+    """Call BEFORE torch.distributed.init_process_group("nccl").  The gradient all-reduce runs on a communication stream underneath the
+    backward; the compute kernels are persistent (one CTA per SM holding ~200 KB of shared memory) and chained by programmatic dependent
+    launch, so every SM an NCCL channel occupies is an SM a GEMM tile waits for.  With NCCL's default channel count the 2-GPU step measured
+    18.6 ms; capped at 12 channels 15.2 ms (2: 19.1, 4: 16.2, 8: 15.2, 12: 15.2; one GPU: 14.3).  A value already in the environment wins."""
+    import os
+    os.environ.setdefault("NCCL_MAX_NCHANNELS", "12")
+
 class FlatAdamW:
     """The reference optimizer (optim/misc.py:13-55 grouping: names containing 'bias' are not decayed; optim/adamw.py)
     over flat buffers.  `state_dict()` / `load_state_dict()` use the reference's per-parameter layout

@@ -285,3 +285,16 @@ def test_gradient_allreduce_in_completion_order_slices_world2():
     ret = mgr.dict()
     mp.spawn(_slice_worker, args=(world, _free_port(), ret), nprocs=world, join=True)
     assert dict(ret) == {0: "ok", 1: "ok"}
+
+
+def test_nccl_channel_cap_default(monkeypatch):
+    """the launchers cap NCCL's channel count before creating the communicator (the all-reduce shares the SMs with persistent compute
+    kernels); a value already in the environment wins"""
+    import importlib
+    trainer = importlib.import_module("robot-3dlotus_b200.trainer")
+    monkeypatch.delenv("NCCL_MAX_NCHANNELS", raising=False)
+    trainer.nccl_env_defaults()
+    assert os.environ["NCCL_MAX_NCHANNELS"] == "12"
+    monkeypatch.setenv("NCCL_MAX_NCHANNELS", "4")
+    trainer.nccl_env_defaults()
+    assert os.environ["NCCL_MAX_NCHANNELS"] == "4"
