@@ -131,11 +131,9 @@ static void linear_bwd(Ctx& c, const void* dy, const void* x, int M, const Lin& 
   fork_side(c);                                  // dy (and x) are complete on the main stream at this point
   void* gs = gstream(c);
   if (tc) {
-    if (Gf(c, l.w)) CALL(lotus_linear_wgrad_bf16, dy, x, Gf(c, l.w), M, l.out, l.in, gs);
-    // the bias gradient (column sums of dy) rides in the data-gradient GEMM, which reads dy through shared memory anyway;
-    // a separate column-sum launch remains only where no data gradient is needed
-    if (dx) CALL(lotus_linear_dgrad_bias_bf16, dy, c.WT[l.w], dx_residual, dx, Gf(c, l.b), M, l.out, l.in, 0, c.stv);
-    else if (Gf(c, l.b)) CALL(lotus_colsum_bf16, dy, M, l.out, Gf(c, l.b), gs);
+    // the bias gradient rides in the weight-gradient GEMM (db = dy^T 1: one extra MMA per K step against a tile of ones), on the side stream
+    if (Gf(c, l.w) || Gf(c, l.b)) CALL(lotus_linear_wgrad_bias_bf16, dy, x, Gf(c, l.w), Gf(c, l.b), M, l.out, l.in, gs);
+    if (dx) CALL(lotus_linear_dgrad_bias_bf16, dy, c.WT[l.w], dx_residual, dx, nullptr, M, l.out, l.in, 0, c.stv);
   } else {
     if (Gf(c, l.w)) CALL(lotus_linear_wgrad_f32, (const float*)dy, (const float*)x, Gf(c, l.w), M, l.out, l.in, nullptr, gs);
     if (Gf(c, l.b)) CALL(lotus_colsum_f32, (const float*)dy, M, l.out, Gf(c, l.b), gs);
@@ -229,8 +227,8 @@ static void mlp_bwd(Ctx& c, void* D, int n, const Norm& n2, const Lin& fc1, cons
   if (c.bf) {
     // du = drop'(gelu'(u)) * (dyd @ W2): the activation backward rides in the data-gradient GEMM's epilogue
     fork_side(c);
-    if (Gf(c, fc2.w)) CALL(lotus_linear_wgrad_bf16, dyd, sv.g, Gf(c, fc2.w), n, fc2.out, fc2.in, gstream(c));   // weight gradient (side stream)
-    CALL(lotus_linear_dgrad_act_bias_bf16, dyd, c.WT[fc2.w], sv.u, dg, Gf(c, fc2.b), n, fc2.out, fc2.in, 1, drop_p(c, c.proj_drop, sv.d_act),
+    if (Gf(c, fc2.w) || Gf(c, fc2.b)) CALL(lotus_linear_wgrad_bias_bf16, dyd, sv.g, Gf(c, fc2.w), Gf(c, fc2.b), n, fc2.out, fc2.in, gstream(c));   // weight + bias gradient (side stream)
+    CALL(lotus_linear_dgrad_act_bias_bf16, dyd, c.WT[fc2.w], sv.u, dg, nullptr, n, fc2.out, fc2.in, 1, drop_p(c, c.proj_drop, sv.d_act),
                                           c.seed, sv.d_act, c.stv);
   } else {
     linear_bwd(c, dyd, sv.g, n, fc2, dg, nullptr, false);

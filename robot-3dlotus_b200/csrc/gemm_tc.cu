@@ -64,6 +64,7 @@ struct Params {
   int out_fp32;
   int atomic;                  // fp32 atomicAdd accumulate (split-K)
   const float* bias;           // [N] or null
+  float* rowsum_a;             // [M] fp32, accumulated: sum over the reduction of A (weight-gradient GEMM: the BIAS gradient, db = dy^T 1), or null
   const void* residual;        // [M, ldo] same dtype as out, or null
   int act;
   float drop_p;
@@ -112,6 +113,11 @@ k_gemm_tc(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUt
   // K-major gather (sparse conv): this tile's rows of the neighbour table, [ntaps][128] int32, staged once by the producer
   // threads -- the per-k-block index lookup was a dependent global load in front of every cp.async group
   int32_t* sIdx = (int32_t*)(sRes + (p.residual ? (size_t)BM * BN * (p.out_fp32 ? 4 : 2) : 0));
+  // Bias gradient inside the weight-gradient GEMM: db[n] = sum_m dy[m, n] is the same contraction with x replaced by ones, so one extra
+  // MMA per K step multiplies the A tile with a 16-column tile of ones (2 KB, here) into 16 spare TMEM columns; every column holds db.
+  // (The column sums used to ride in the data-gradient GEMM on CUDA cores, where they cost as much as the GEMM itself.)
+  uint8_t* sOnes = sRes;                                       // only with p.rowsum_a (then there is no residual and no index tile)
+  const uint32_t tmem_cols = p.rowsum_a ? 2 * BN : BN;
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int m0 = blockIdx.x * BM, n0 = blockIdx.y * BN;
@@ -138,7 +144,11 @@ k_gemm_tc(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUt
     mbar_init(res_full, 1);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
-  if (warp == 1) tmem_alloc(tmem_slot, BN);   // BN in {64,128}: power of two >= 32
+  if (warp == 1) tmem_alloc(tmem_slot, tmem_cols);   // BN in {64,128}: power of two >= 32
+  if (p.rowsum_a && threadIdx.x >= 64 && threadIdx.x < 64 + 128) {
+    ((uint4*)sOnes)[threadIdx.x - 64] = make_uint4(0x3F803F80u, 0x3F803F80u, 0x3F803F80u, 0x3F803F80u);   // bf16 1.0
+    fence_proxy_async();                               // generic-proxy stores -> visible to the MMA's async proxy
+  }
   // programmatic dependent launch: nothing above read global data; from here on the previous kernel's results are needed
   pdl_wait();
   pdl_launch_dependents();
@@ -250,6 +260,9 @@ k_gemm_tc(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUt
         const uint64_t db0 = b_mn ? make_desc(smem_u32(sB), 8192, 1024) : make_desc(smem_u32(sB), 16, 1024);
         const uint32_t a_kstep = a_mn ? (2048u >> 4) : (32u >> 4), b_kstep = b_mn ? (2048u >> 4) : (32u >> 4);
         const bool gen_fence = (a_gather || b_gather) && p.async_arrive;
+        // A x ones: N = 16, B read K-major from the all-ones tile (any K step reads ones, so the descriptor does not advance)
+        const uint32_t idesc_ones = (1u << 4) | (1u << 7) | (1u << 10) | ((a_mn ? 1u : 0u) << 15) | ((uint32_t)(16 >> 3) << 17) | ((uint32_t)(BM >> 4) << 24);
+        const uint64_t d_ones = make_desc(smem_u32(sOnes), 16, 1024);
         int s = 0, ph = 0;
         for (int i = 0; i < num_kb; ++i) {
           mbar_wait_hot(&full[s], ph);
@@ -260,6 +273,11 @@ k_gemm_tc(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUt
 #pragma unroll
           for (int k = 0; k < BK / 16; ++k) {
             if (!(p.debug & 256)) umma_bf16(tmem_base, da + (uint64_t)(k * a_kstep), db + (uint64_t)(k * b_kstep), idesc, (i > 0 || k > 0) ? 1u : 0u);
+          }
+          if (p.rowsum_a) {
+#pragma unroll
+            for (int k = 0; k < BK / 16; ++k)
+              umma_bf16(tmem_base + BN, da + (uint64_t)(k * a_kstep), d_ones, idesc_ones, (i > 0 || k > 0) ? 1u : 0u);
           }
           // frees the smem stage(s) when these MMAs retire; pair mode: ONE commit per two stages (tcgen05.commit arrivals
           // retire at a fixed ~380 ns each -- the whole pipeline advanced one k-block per commit whatever it loaded or multiplied)
@@ -414,6 +432,13 @@ k_gemm_tc(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUt
       tc_fence_after();
     }
     if (threadIdx.x == 64) TS(4);
+    if (p.rowsum_a && half == 0 && blockIdx.y == 0) {        // one n-tile column of CTAs reports the sums (every split adds its part)
+      uint32_t v[16];
+      tmem_ld_32x32b_x16(tmem_base + ((uint32_t)(lane_grp * 32) << 16) + (uint32_t)BN, v);
+      tmem_ld_wait();
+      const float sum = __uint_as_float(v[0]);
+      if (row < p.M && sum != 0.f) atomicAdd(&p.rowsum_a[row], sum);
+    }
     if (p.residual && !(p.debug & 2)) { if (lane == 0) mbar_wait(res_full, 0); __syncwarp(); }
     const bool add_res = p.residual != nullptr && p.act != ACT_GELU_GRAD;
     uint8_t* sOut2 = smem + (size_t)BM * BN * 2;       // pre-activation tile (bf16 outputs only), behind the output tile
@@ -555,7 +580,7 @@ k_gemm_tc(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUt
   }
   tc_fence_before();
   __syncthreads();
-  if (warp == 1) tmem_dealloc(tmem_base, BN);
+  if (warp == 1) tmem_dealloc(tmem_base, tmem_cols);
   if (threadIdx.x == 0) TS(7);
 }
 
@@ -644,7 +669,7 @@ static int launch(const Operand& A, const Operand& B, Params p, int BN, int spli
   { static int pc = -1; if (pc < 0) { const char* e = getenv("LOTUS_TC_PAIR"); pc = e ? atoi(e) : 0; } want_pair = pc; }
   size_t pipe = (size_t)p.stages * (BM * BK * 2 + BN * BK * 2);
   while (pipe < tile_bytes * (p.out2 ? 2 : 1)) { ++p.stages; pipe = (size_t)p.stages * (BM * BK * 2 + BN * BK * 2); }   // the output tile reuses the pipeline
-  size_t smem = pipe + 256 + 2048 + (size_t)BN * 4 + (p.residual ? tile_bytes : 0);
+  size_t smem = pipe + 256 + 2048 + (size_t)BN * 4 + (p.residual ? tile_bytes : 0) + (p.rowsum_a ? 2048 : 0);
   if ((A.mode == OP_K_GATHER || A.mode == OP_K_TMAGATHER) && A.g.ntaps <= 32) {
     // neighbour-table tile in shared memory; keep two 64-wide CTAs per SM (<= ~113 KB each) by giving up one pipeline stage
     size_t idx_bytes = (size_t)A.g.ntaps * EPI_THREADS * 4;
@@ -702,6 +727,23 @@ LOTUS_API int lotus_linear_wgrad_bf16(const void* dy, const void* x, float* dw, 
   int bn = tc::pick_bn(K);
   int tiles = ((N + 127) / 128) * ((K + bn - 1) / bn);
   static int ctas = -1;                                          // CTAs the reduction is cut over: one per SM (measured best at every shape of the step: two per SM doubles the reduce-add traffic onto the same tile); LOTUS_WGRAD_CTAS overrides
+  if (ctas < 0) { const char* e = getenv("LOTUS_WGRAD_CTAS"); ctas = e ? atoi(e) : kNumSM; }
+  int splits = max(1, ctas / tiles);
+  return tc::launch(A, B, p, bn, splits, (cudaStream_t)stream_);
+}
+
+// weight and bias gradient in one GEMM: dw[N,K] (fp32) += dy^T x, db[N] (fp32) += dy^T 1 (either may be null)
+extern "C" int lotus_colsum_bf16(const void* x, int64_t rows, int C, float* out_accum, void* stream_);
+LOTUS_API int lotus_linear_wgrad_bias_bf16(const void* dy, const void* x, float* dw, float* db, int M, int N, int K, void* stream_) {
+  if (dw == nullptr) return db ? lotus_colsum_bf16(dy, M, N, db, stream_) : 0;
+  LOTUS_CHECK_ARG(N % 8 == 0 && K % 8 == 0, "lotus_linear_wgrad_bias_bf16: N=%d, K=%d must be multiples of 8", N, K);
+  Params p = base_params(N, K, M, dw, K, 1);
+  p.atomic = 1;
+  p.rowsum_a = db;
+  Operand A{tc::OP_MN_TMA, (const __nv_bfloat16*)dy, N, {}}, B{tc::OP_MN_TMA, (const __nv_bfloat16*)x, K, {}};
+  int bn = tc::pick_bn(K);
+  int tiles = ((N + 127) / 128) * ((K + bn - 1) / bn);
+  static int ctas = -1;
   if (ctas < 0) { const char* e = getenv("LOTUS_WGRAD_CTAS"); ctas = e ? atoi(e) : kNumSM; }
   int splits = max(1, ctas / tiles);
   return tc::launch(A, B, p, bn, splits, (cudaStream_t)stream_);

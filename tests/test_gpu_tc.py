@@ -481,3 +481,23 @@ def test_cast_transpose_batch():
     torch.cuda.synchronize()
     for w, b, t in zip(ws, wb, wt):
         assert torch.equal(b, w.bfloat16()) and torch.equal(t, w.bfloat16().permute(2, 1, 0).contiguous())
+
+
+@pytest.mark.parametrize("M,N,K", [(5000, 128, 128), (3000, 192, 64), (1500, 512, 256), (777, 64, 64), (40000, 128, 512)])
+def test_linear_wgrad_bias_bf16(M, N, K):
+    """weight and bias gradient in one tcgen05 GEMM (the bias gradient is the same contraction against a tile of ones) vs torch fp32 on
+    the same bf16-rounded operands; accumulates into non-zero buffers; split-K over the grid"""
+    L = pkg("lib").load()
+    g = torch.Generator().manual_seed(M + N + K)
+    dy, x = bf(torch.randn(M, N, generator=g)), bf(torch.randn(M, K, generator=g))
+    dw0, db0 = torch.randn(N, K, generator=g), torch.randn(N, generator=g)
+    dw, db = dw0.clone().to(DEV), db0.clone().to(DEV)
+    dyd, xd = dy.to(DEV), x.to(DEV)                       # (held in locals: the pointers must outlive the call)
+    L.lotus_linear_wgrad_bias_bf16(P(dyd), P(xd), P(dw), P(db), M, N, K, None)
+    torch.cuda.synchronize()
+    assert rel(dw.cpu() - dw0, dy.float().t() @ x.float()) < 2e-3
+    assert rel(db.cpu() - db0, dy.float().sum(0)) < 2e-3
+    db2 = torch.zeros(N, device=DEV)                      # bias gradient alone (no weight gradient): the column-sum kernel
+    L.lotus_linear_wgrad_bias_bf16(P(dyd), P(xd), None, P(db2), M, N, K, None)
+    torch.cuda.synchronize()
+    assert rel(db2.cpu(), dy.float().sum(0)) < 2e-3
