@@ -165,6 +165,9 @@ def algorithmic_work(name, a, ctx):
     if name.startswith("lotus_layernorm_fwd"):
         rows, C = int(a[13]), int(a[14])
         return 0.0, float(es) * rows * C * (2 + (1 if a[8] else 0)) + 8.0 * rows
+    if name.startswith("lotus_layernorm_bwd_mask"):             # (dy, x, dx, dx_masked, gamma, mean, rstd, dgamma, dbeta, rows, C, accumulate, ...)
+        rows, C, acc = int(a[9]), int(a[10]), int(a[11])
+        return 0.0, rows * C * (float(es) + es + es * (2 if acc else 1) + es) + 8.0 * rows
     if name.startswith("lotus_layernorm_bwd"):
         o = 1 if name.endswith("bf16") else 0
         rows, C, acc = int(a[17 + o]), int(a[18 + o]), int(a[19 + o])

@@ -152,7 +152,15 @@ static void ln_fwd(Ctx& c, const void* x, void* y, const void* residual, const N
   if (c.bf) CALL(lotus_layernorm_fwd_bf16, x, 1, nm.C, 0, y, 1, nm.C, 0, residual, Pf(c, nm.w), Pf(c, nm.b), mean, rstd, rows, nm.C, eps, c.stv);
   else CALL(lotus_layernorm_fwd_f32, (const float*)x, 1, nm.C, 0, (float*)y, 1, nm.C, 0, (const float*)residual, Pf(c, nm.w), Pf(c, nm.b), mean, rstd, rows, nm.C, eps, c.stv);
 }
-static void ln_bwd(Ctx& c, const void* dy, const void* x, void* dx, const Norm& nm, const float* mean, const float* rstd, int64_t rows, int accumulate) {
+// masked / mask_did (optional, bf16 mode): also write dropout_mask(dx) for the NEXT layer's output dropout site (saves the separate
+// masking pass over the residual-stream gradient; bit-identical to lotus_dropout_bf16 applied to the stored dx)
+static void ln_bwd(Ctx& c, const void* dy, const void* x, void* dx, const Norm& nm, const float* mean, const float* rstd, int64_t rows, int accumulate,
+                   void* masked = nullptr, uint32_t mask_did = 0) {
+  if (c.bf && masked && mask_did) {
+    CALL(lotus_layernorm_bwd_mask_bf16, dy, x, dx, masked, Pf(c, nm.w), mean, rstd, Gf(c, nm.w), Gf(c, nm.b), rows, nm.C, accumulate,
+                                       c.proj_drop, c.seed, mask_did, c.stv);
+    return;
+  }
   if (c.bf) CALL(lotus_layernorm_bwd_bf16, dy, 0, 1, nm.C, 0, x, 1, nm.C, 0, dx, 1, nm.C, 0, Pf(c, nm.w), mean, rstd, Gf(c, nm.w), Gf(c, nm.b), rows, nm.C, accumulate, c.stv);
   else CALL(lotus_layernorm_bwd_f32, (const float*)dy, 1, nm.C, 0, (const float*)x, 1, nm.C, 0, (float*)dx, 1, nm.C, 0, Pf(c, nm.w), mean, rstd, Gf(c, nm.w), Gf(c, nm.b), rows, nm.C, accumulate, c.stv);
 }
@@ -220,9 +228,12 @@ static void* mlp_fwd(Ctx& c, void* x2, int n, const Norm& n2, const Lin& fc1, co
   return x3;
 }
 // D holds d(x3) on entry and d(x2) on exit
-static void mlp_bwd(Ctx& c, void* D, int n, const Norm& n2, const Lin& fc1, const Lin& fc2, const MlpSave& sv) {
+// dyd_in: mask_{d_out}(D) already produced by the LayerNorm backward that wrote D (or null); next_masked / next_did: where to leave
+// mask_{next_did}(D) for the projection that follows this MLP in the backward order
+static void mlp_bwd(Ctx& c, void* D, int n, const Norm& n2, const Lin& fc1, const Lin& fc2, const MlpSave& sv, const void* dyd_in = nullptr,
+                    void* next_masked = nullptr, uint32_t next_did = 0) {
   int C = n2.C;
-  const void* dyd = drop_grad(c, D, (int64_t)n * C, c.proj_drop, sv.d_out, c.bf);
+  const void* dyd = dyd_in ? dyd_in : drop_grad(c, D, (int64_t)n * C, c.proj_drop, sv.d_out, c.bf);
   void* dg = act(c, n, fc1.out);
   if (c.bf) {
     // du = drop'(gelu'(u)) * (dyd @ W2): the activation backward rides in the data-gradient GEMM's epilogue
@@ -237,7 +248,7 @@ static void mlp_bwd(Ctx& c, void* D, int n, const Norm& n2, const Lin& fc1, cons
   void* dh2 = act(c, n, C);
   linear_bwd(c, dg, sv.h2, n, fc1, dh2, nullptr, c.bf);
   if (dyd == D) join_side(c);                                                            // fc2's weight gradient reads D
-  ln_bwd(c, dh2, sv.x2, D, n2, sv.mean, sv.rstd, n, 1);                                  // D += LN'(dh2)
+  ln_bwd(c, dh2, sv.x2, D, n2, sv.mean, sv.rstd, n, 1, next_masked, next_did);           // D += LN'(dh2)
   // temporaries are released by the caller (after its join with the weight-gradient stream)
 }
 
@@ -298,14 +309,15 @@ static void* block_fwd(Ctx& c, const BlockP& b, const StageInfo& sg, void* x0, c
 }
 // D: d(x3) on entry -> d(x0) on exit (residual stream, in place).  If the conv read a different tensor (decoder: the skip
 // branch), its gradient is returned in *d_conv_in = D_after + conv dgrad (new arena buffer, NOT released here).
-static void block_bwd(Ctx& c, const BlockP& b, const StageInfo& sg, void* D, const BlockSave& sv, void** d_conv_in) {
+static void block_bwd(Ctx& c, const BlockP& b, const StageInfo& sg, void* D, const BlockSave& sv, void** d_conv_in, const void* mlp_dyd_in = nullptr) {
   int n = sv.n, C = b.C, H = b.H, Dh = C / H;
   void* dconv = nullptr;
   if (sv.own_conv_in) dconv = act(c, n, C);                                              // survives the temporaries below
   size_t mark = c.ar.off;
-  mlp_bwd(c, D, n, b.n2, b.fc1, b.fc2, sv.mlp);                                          // D = d(x2)
+  void* pm = (c.bf && sv.d_proj) ? act(c, n, C) : nullptr;                               // mask_{d_proj}(D), written by the MLP's LayerNorm backward
+  mlp_bwd(c, D, n, b.n2, b.fc1, b.fc2, sv.mlp, mlp_dyd_in, pm, sv.d_proj);               // D = d(x2)
   // attention branch
-  const void* dyd = drop_grad(c, D, (int64_t)n * C, c.proj_drop, sv.d_proj, c.bf);
+  const void* dyd = pm ? pm : drop_grad(c, D, (int64_t)n * C, c.proj_drop, sv.d_proj, c.bf);
   void* dout = act(c, n, C);
   linear_bwd(c, dyd, sv.o, n, b.proj, dout, nullptr, c.bf);
   void* dqkv = act(c, n, 3 * C);
@@ -418,11 +430,13 @@ static void* ca_fwd(Ctx& c, const CaP& b, const StageInfo& sg, void* x0, const v
   return mlp_fwd(c, x2, n, b.n2, b.fc1, b.fc2, sv.mlp);
 }
 // D: d(out) -> d(x0) in place; dctx (Lt x ctxC, activation dtype) accumulates (first use flagged by *dctx_init)
-static void ca_bwd(Ctx& c, const CaP& b, const StageInfo& sg, void* D, const void* ctx, void* dctx, bool* dctx_init, const CaSave& sv) {
+static void ca_bwd(Ctx& c, const CaP& b, const StageInfo& sg, void* D, const void* ctx, void* dctx, bool* dctx_init, const CaSave& sv,
+                   void* next_masked = nullptr, uint32_t next_did = 0) {
   int n = sv.n, C = b.C, H = b.H, Dh = C / H, Lt = c.Lt;
   size_t mark = c.ar.off;
-  mlp_bwd(c, D, n, b.n2, b.fc1, b.fc2, sv.mlp);
-  const void* dyd = drop_grad(c, D, (int64_t)n * C, c.proj_drop, sv.d_proj, c.bf);
+  void* pm = (c.bf && sv.d_proj) ? act(c, n, C) : nullptr;
+  mlp_bwd(c, D, n, b.n2, b.fc1, b.fc2, sv.mlp, nullptr, pm, sv.d_proj);
+  const void* dyd = pm ? pm : drop_grad(c, D, (int64_t)n * C, c.proj_drop, sv.d_proj, c.bf);
   void* dout = act(c, n, C);
   linear_bwd(c, dyd, sv.o, n, b.proj, dout, nullptr, c.bf);
   void* dq = act(c, n, C);
@@ -456,7 +470,7 @@ static void ca_bwd(Ctx& c, const CaP& b, const StageInfo& sg, void* D, const voi
   void* dh1 = act(c, n, C);
   linear_bwd(c, dq, sv.h1, n, b.q, dh1, nullptr, c.bf);
   if (dyd == D) join_side(c);
-  ln_bwd(c, dh1, sv.x0, D, b.n1, sv.n1_mean, sv.n1_rstd, n, 1);
+  ln_bwd(c, dh1, sv.x0, D, b.n1, sv.n1_mean, sv.n1_rstd, n, 1, next_masked, next_did);   // (+ the mask for the block MLP that follows)
   join_side(c);
   c.ar.off = mark;
 }
@@ -727,9 +741,10 @@ LOTUS_API int lotus_policy_step(const int64_t* cfg, const int64_t* run, const in
       // decoder, shallow to deep
       for (int s = 0; s <= S - 2; ++s) {
         int nc = sg[s + 1].n, n = sg[s].n, C = m.decC[s];
-        ca_bwd(c, m.decCA[s], sg[s], D, ctx, dctx, &dctx_init, dC[s]);
+        void* dm = (c.bf && dB[s].mlp.d_out) ? act(c, n, C) : nullptr;   // mask(D) for the block's MLP, written by the CA block's last LayerNorm backward
+        ca_bwd(c, m.decCA[s], sg[s], D, ctx, dctx, &dctx_init, dC[s], dm, dB[s].mlp.d_out);
         void* dconv = nullptr;
-        block_bwd(c, m.decB[s], sg[s], D, dB[s], &dconv);            // D = d(xu); dconv = D + conv-input grad = d(b)
+        block_bwd(c, m.decB[s], sg[s], D, dB[s], &dconv, dm);        // D = d(xu); dconv = D + conv-input grad = d(b)
         // unpool: xu = b + a[cluster]
         void* da = act(c, nc, C);
         if (c.bf) CALL(lotus_segment_sum_bf16, D, C, sg[s + 1].seg_ptr, sg[s + 1].member, nc, 0, da, c.stv);
@@ -756,8 +771,9 @@ LOTUS_API int lotus_policy_step(const int64_t* cfg, const int64_t* run, const in
       // encoder, deep to shallow
       for (int s = S - 1; s >= 0; --s) {
         int n = sg[s].n, C = m.encC[s];
-        ca_bwd(c, m.encCA[s], sg[s], D, ctx, dctx, &dctx_init, eC[s]);
-        block_bwd(c, m.encB[s], sg[s], D, eB[s], nullptr);            // D = d(stage input)
+        void* dm = (c.bf && eB[s].mlp.d_out) ? act(c, n, C) : nullptr;
+        ca_bwd(c, m.encCA[s], sg[s], D, ctx, dctx, &dctx_init, eC[s], dm, eB[s].mlp.d_out);
+        block_bwd(c, m.encB[s], sg[s], D, eB[s], nullptr, dm);        // D = d(stage input)
         if (s > 0) {
           int np = sg[s - 1].n;
           void* dpooled = act(c, n, C);

@@ -202,7 +202,8 @@ __global__ void __launch_bounds__(256, U == 2 ? 3 : 1) k_ln_bwd_vec(const TDY* _
                                                     bf16_t* __restrict__ dx, RowMap dxm, const float* __restrict__ gamma,
                                                     const float* __restrict__ mean, const float* __restrict__ rstd,
                                                     float* __restrict__ dgamma, float* __restrict__ dbeta, int64_t rows, int C,
-                                                    int lpr, int accumulate_dx) {
+                                                    int lpr, int accumulate_dx, bf16_t* __restrict__ dx_masked, float drop_p, uint64_t seed,
+                                                    uint32_t drop_sid) {
   extern __shared__ float sacc[];  // [2][C]
   const int lane = threadIdx.x & 31, lig = lane & (lpr - 1), rpw = 32 / lpr;
   const int nvec = C >> 3;
@@ -210,6 +211,8 @@ __global__ void __launch_bounds__(256, U == 2 ? 3 : 1) k_ln_bwd_vec(const TDY* _
   __syncthreads();
   pdl_wait();                                                    // programmatic dependent launch (common.cuh)
   pdl_launch_dependents();
+  const uint32_t dthr = drop_thr(drop_p);
+  const float dks = dx_masked ? drop_scale(dthr) : 1.f;
   float ag[VPL][8], ab[VPL][8], g[VPL][8];
 #pragma unroll
   for (int j = 0; j < VPL; ++j) {
@@ -277,7 +280,22 @@ __global__ void __launch_bounds__(256, U == 2 ? 3 : 1) k_ln_bwd_vec(const TDY* _
 #pragma unroll
             for (int e = 0; e < 8; ++e) o[e] += old[e];
           }
-          *(uint4*)(dx + xo + vi * 8) = pack8(o);
+          const uint4 packed = pack8(o);
+          *(uint4*)(dx + xo + vi * 8) = packed;
+          if (dx_masked) {
+            // the gradient that continues into the NEXT layer's output dropout: mask(dx), contiguous [rows, C], same element index,
+            // hash and rounding as lotus_dropout_bf16 on the stored bf16 values (bit-identical to the separate launch it replaces)
+            float m[8];
+            unpack8(packed, m);
+            const int64_t fo = r[u] * C + vi * 8;
+            const uint32_t h0 = drop_hash4(seed, drop_sid, (uint64_t)fo), h1 = drop_hash4(seed, drop_sid, (uint64_t)fo + 4);
+#pragma unroll
+            for (int e = 0; e < 4; ++e) {
+              m[e] = (((h0 >> (8 * e)) & 0xFFu) >= dthr) ? m[e] * dks : 0.f;
+              m[4 + e] = (((h1 >> (8 * e)) & 0xFFu) >= dthr) ? m[4 + e] * dks : 0.f;
+            }
+            *(uint4*)(dx_masked + fo) = pack8(m);
+          }
         }
       }
     }
@@ -345,7 +363,8 @@ template <typename TDY, typename T>
 static int ln_bwd_impl(const void* dy, int dy_inner, int64_t dy_outer_stride, int64_t dy_inner_stride, const void* x,
                        int x_inner, int64_t x_outer_stride, int64_t x_inner_stride, void* dx, int dx_inner,
                        int64_t dx_outer_stride, int64_t dx_inner_stride, const float* gamma, const float* mean,
-                       const float* rstd, float* dgamma, float* dbeta, int64_t rows, int C, int accumulate_dx, void* stream_) {
+                       const float* rstd, float* dgamma, float* dbeta, int64_t rows, int C, int accumulate_dx, void* stream_,
+                       void* dx_masked = nullptr, float drop_p = 0.f, uint64_t seed = 0, uint32_t drop_sid = 0) {
   if (rows <= 0) return 0;
   cudaStream_t st = (cudaStream_t)stream_;
   RowMap dym{dy_inner, dy_outer_stride, dy_inner_stride}, xm{x_inner, x_outer_stride, x_inner_stride},
@@ -358,12 +377,13 @@ static int ln_bwd_impl(const void* dy, int dy_inner, int64_t dy_outer_stride, in
   if (sizeof(T) == 2 && C % 8 == 0 && vec_ok(dym) && vec_ok(xm) && vec_ok(dxm) && aligned16(dy) && aligned16(x) && aligned16(dx) &&
       aligned16(gamma)) {
     int lpr = pick_lpr(C), vpl = ceil_div(C >> 3, lpr), rpw = 32 / lpr;
-#define LNB(V, U) launch_pdl(k_ln_bwd_vec<V, U, TDY>, dim3(min(ceil_div(ceil_div(rows, rpw * U), 8), resident_blocks(k_ln_bwd_vec<V, U, TDY>, 256, smem))), dim3(256), smem, st, (const TDY*)dy, dym, (const bf16_t*)x, xm, (bf16_t*)dx, dxm, gamma, mean, rstd, dgamma, dbeta, rows, C, lpr, accumulate_dx)
+#define LNB(V, U) launch_pdl(k_ln_bwd_vec<V, U, TDY>, dim3(min(ceil_div(ceil_div(rows, rpw * U), 8), resident_blocks(k_ln_bwd_vec<V, U, TDY>, 256, smem))), dim3(256), smem, st, (const TDY*)dy, dym, (const bf16_t*)x, xm, (bf16_t*)dx, dxm, gamma, mean, rstd, dgamma, dbeta, rows, C, lpr, accumulate_dx, (bf16_t*)dx_masked, drop_p, seed, drop_sid)
     if (vpl == 1) LNB(1, 2); else if (vpl == 2) LNB(2, 1); else if (vpl == 3) LNB(3, 1); else LNB(4, 1);
 #undef LNB
     LOTUS_CUDA_OK();
     return 0;
   }
+  LOTUS_CHECK_ARG(dx_masked == nullptr, "layernorm_bwd: the masked second output needs the vectorised path (C %% 8 == 0, 16-byte aligned rows)");
 #define LN_BWD(CPL)                                                                                                   \
   k_ln_bwd<CPL, TDY, T><<<blocks, 256, smem, st>>>((const TDY*)dy, dym, (const T*)x, xm, (T*)dx, dxm, gamma, mean, rstd, \
                                                    dgamma, dbeta, rows, C, rpb, accumulate_dx)
@@ -399,6 +419,16 @@ LOTUS_API int lotus_layernorm_bwd_bf16(const void* dy, int dy_fp32, int dy_inner
   return ln_bwd_impl<bf16_t, bf16_t>(dy, dy_inner, dy_outer_stride, dy_inner_stride, x, x_inner, x_outer_stride, x_inner_stride,
                                      dx, dx_inner, dx_outer_stride, dx_inner_stride, gamma, mean, rstd, dgamma, dbeta, rows, C,
                                      accumulate_dx, stream_);
+}
+
+// contiguous [rows, C] form that also emits dropout_mask(dx) for the next layer's output dropout (drop_p, seed, drop_stream as in
+// lotus_dropout_bf16): saves the separate masking pass over the residual-stream gradient.  x, dy, dx, dx_masked bf16.
+LOTUS_API int lotus_layernorm_bwd_mask_bf16(const void* dy, const void* x, void* dx, void* dx_masked, const float* gamma, const float* mean,
+                                            const float* rstd, float* dgamma, float* dbeta, int64_t rows, int C, int accumulate_dx,
+                                            float drop_p, uint64_t seed, uint32_t drop_stream, void* stream_) {
+  LOTUS_CHECK_ARG(dx_masked != nullptr && drop_p > 0.f && drop_p < 1.f && aligned16(dx_masked), "lotus_layernorm_bwd_mask_bf16: needs a masked output and 0 < p < 1");
+  return ln_bwd_impl<bf16_t, bf16_t>(dy, 1, C, 0, x, 1, C, 0, dx, 1, C, 0, gamma, mean, rstd, dgamma, dbeta, rows, C, accumulate_dx, stream_,
+                                     dx_masked, drop_p, seed, drop_stream);
 }
 
 // ---------------------------------------------------------------- BatchNorm (+GELU)

@@ -164,14 +164,19 @@ class LinearFn(torch.autograd.Function):
             else:
                 L.lotus_linear_dgrad_f32(_p(dy), _p(w), None, _p(dx), M, N, K, st)
         wbuf, dw = _grad_buf(w, ctx.needs_input_grad[1])
-        if wbuf is not None:
-            if ctx.tc:
-                L.lotus_linear_wgrad_bf16(_p(dy), _p(x), _p(wbuf), M, N, K, st)
-            else:
-                L.lotus_linear_wgrad_f32(_p(dy), _p(x), _p(wbuf), M, N, K, None, st)
         bbuf, db = _grad_buf(ctx.bias, ctx.has_b and ctx.needs_input_grad[2])
-        if bbuf is not None:
-            getattr(L, "lotus_colsum_" + sfx)(_p(dy), M, N, _p(bbuf), st)
+        if ctx.tc and N % 8 == 0 and K % 8 == 0:
+            if wbuf is not None or bbuf is not None:      # weight and bias gradient in one GEMM (db = dy^T 1)
+                L.lotus_linear_wgrad_bias_bf16(_p(dy), _p(x), None if wbuf is None else _p(wbuf), None if bbuf is None else _p(bbuf),
+                                               M, N, K, st)
+        else:
+            if wbuf is not None:
+                if ctx.tc:
+                    L.lotus_linear_wgrad_bf16(_p(dy), _p(x), _p(wbuf), M, N, K, st)
+                else:
+                    L.lotus_linear_wgrad_f32(_p(dy), _p(x), _p(wbuf), M, N, K, None, st)
+            if bbuf is not None:
+                getattr(L, "lotus_colsum_" + sfx)(_p(dy), M, N, _p(bbuf), st)
         return dx, dw, db, dres, None, None
 
 
@@ -217,20 +222,18 @@ class MlpFn(torch.autograd.Function):
             L.lotus_dropout_bf16(_p(dy), _p(dyd), dy.numel(), ctx.drop_out[0], ctx.drop_out[1], ctx.drop_out[2], st)
             dy = dyd
         w2buf, dw2 = _grad_buf(w2, ctx.needs_input_grad[3])
-        if w2buf is not None:
-            L.lotus_linear_wgrad_bf16(_p(dy), _p(g), _p(w2buf), M, C, Hd, st)
         b2buf, db2 = _grad_buf(ctx.b2, ctx.needs_input_grad[4])
-        if b2buf is not None:
-            L.lotus_colsum_bf16(_p(dy), M, C, _p(b2buf), st)
+        if w2buf is not None or b2buf is not None:
+            L.lotus_linear_wgrad_bias_bf16(_p(dy), _p(g), None if w2buf is None else _p(w2buf), None if b2buf is None else _p(b2buf),
+                                           M, C, Hd, st)
         du = torch.empty_like(u)
         L.lotus_linear_dgrad_act_bf16(_p(dy), _p(STAGED[w2.data_ptr()][1]), _p(u), _p(du), M, C, Hd, 1, ctx.drop_act[0],
                                       ctx.drop_act[1], ctx.drop_act[2], st)
         w1buf, dw1 = _grad_buf(w1, ctx.needs_input_grad[1])
-        if w1buf is not None:
-            L.lotus_linear_wgrad_bf16(_p(du), _p(x), _p(w1buf), M, Hd, C, st)
         b1buf, db1 = _grad_buf(ctx.b1, ctx.needs_input_grad[2])
-        if b1buf is not None:
-            L.lotus_colsum_bf16(_p(du), M, Hd, _p(b1buf), st)
+        if w1buf is not None or b1buf is not None:
+            L.lotus_linear_wgrad_bias_bf16(_p(du), _p(x), None if w1buf is None else _p(w1buf), None if b1buf is None else _p(b1buf),
+                                           M, Hd, C, st)
         dx = None
         if ctx.needs_input_grad[0]:
             dx = torch.empty_like(x)

@@ -501,3 +501,28 @@ def test_linear_wgrad_bias_bf16(M, N, K):
     L.lotus_linear_wgrad_bias_bf16(P(dyd), P(xd), None, P(db2), M, N, K, None)
     torch.cuda.synchronize()
     assert rel(db2.cpu(), dy.float().sum(0)) < 2e-3
+
+
+@pytest.mark.parametrize("rows,C", [(5000, 64), (3001, 128), (700, 512)])
+def test_layernorm_bwd_masked_output(rows, C):
+    """LayerNorm backward that also writes dropout_mask(dx) for the next layer's output dropout == the plain backward followed by
+    lotus_dropout_bf16 on the stored dx, bit for bit (accumulating form, as the native step uses it)"""
+    L = pkg("lib").load()
+    g = torch.Generator().manual_seed(rows + C)
+    x = bf(torch.randn(rows, C, generator=g)).to(DEV)
+    dy = bf(torch.randn(rows, C, generator=g)).to(DEV)
+    d0 = bf(torch.randn(rows, C, generator=g)).to(DEV)
+    gam = torch.randn(C, generator=g).to(DEV)
+    mean, rstd = x.float().mean(1).contiguous(), (x.float().var(1, unbiased=False) + 1e-5).rsqrt().contiguous()
+    dxa, dxb = d0.clone(), d0.clone()
+    dga, dba, dgb, dbb = (torch.zeros(C, device=DEV) for _ in range(4))
+    L.lotus_layernorm_bwd_bf16(P(dy), 0, 1, C, 0, P(x), 1, C, 0, P(dxa), 1, C, 0, P(gam), P(mean), P(rstd), P(dga), P(dba), rows, C, 1, None)
+    ma = torch.empty_like(dxa)
+    L.lotus_dropout_bf16(P(dxa), P(ma), rows * C, 0.3, 99, 17, None)
+    mb = torch.empty_like(dxb)
+    L.lotus_layernorm_bwd_mask_bf16(P(dy), P(x), P(dxb), P(mb), P(gam), P(mean), P(rstd), P(dgb), P(dbb), rows, C, 1, 0.3, 99, 17, None)
+    torch.cuda.synchronize()
+    assert torch.equal(dxa, dxb) and torch.equal(ma, mb)
+    assert rel(dga, dgb) < 1e-5 and rel(dba, dbb) < 1e-5
+    keep = (mb != 0).float().mean().item()
+    assert 0.65 < keep < 0.75

@@ -86,6 +86,7 @@ DOC = {
     "lotus_subm_conv_fwd_splitk_bf16": "lotus_subm_conv_fwd_bf16 with the 27 * Cin reduction split over the grid (deep stages: few rows, long K); partial tiles meet in an fp32 scratch.",
     "lotus_subm_conv_dgrad_splitk_bf16": "Split-K form of lotus_subm_conv_dgrad_bf16.",
     "lotus_linear_wgrad_bias_bf16": "nn.Linear weight AND bias gradient in one tcgen05 GEMM (db = dy^T 1 through one extra MMA per K step against a tile of ones): model.py:386-387,572-574.",
+    "lotus_layernorm_bwd_mask_bf16": "lotus_layernorm_bwd_bf16 (contiguous rows) that also writes dropout_mask(dx) for the next layer's output dropout (nn.Dropout backward of proj / fc2: model.py:555-557,577-583).",
     "lotus_batchnorm_bwd_acc_bf16": "Training-mode backward of BatchNorm1d + GELU in ONE cooperative launch (sums, grid barrier, dx) that also adds the batch sums into the parameter-gradient accumulators: model.py:932,785-788,854-857.",
     "lotus_pointwise_bf16": "bf16-activation form of lotus_pointwise_f32 (GELU / LeakyReLU and derivatives with fused dropout).",
     "lotus_convert": "fp32 <-> bf16 conversion between the fp32 head/loss tensors and the bf16 trunk.",
