@@ -223,14 +223,32 @@ __global__ void __launch_bounds__(256) k_pos_ce(const float* __restrict__ logits
   const float* pb = prob + (int64_t)ld * s + (int64_t)c * tot;
   const int chunk = (tot + CS - 1) / CS;
   const int t0 = min(tot, rank * chunk), t1 = min(tot, t0 + chunk);
+  // element t of the (cloud, axis) slice is logits[(s + t / NB) * ld + c * NB + t % NB]: (row, column) are carried along the
+  // thread's stride instead of divided out per element (three passes x two run-time divisions per element were most of this kernel)
+  const int first = t0 + threadIdx.x;
+  const int row_first = first / NB, col_first = first - row_first * NB;
+  const int drow = blockDim.x / NB, dcol = blockDim.x - drow * NB;
+  const float* lbase = logits + (int64_t)s * ld + c * NB;
   float mx = -INFINITY;
-  for (int t = t0 + threadIdx.x; t < t1; t += blockDim.x) mx = fmaxf(mx, logits[(int64_t)(s + t / NB) * ld + c * NB + t % NB]);
+  {
+    int row = row_first, col = col_first;
+    for (int t = first; t < t1; t += blockDim.x) {
+      mx = fmaxf(mx, lbase[(int64_t)row * ld + col]);
+      row += drow; col += dcol;
+      if (col >= NB) { col -= NB; ++row; }
+    }
+  }
   mx = block_max(mx, red);
   float se = 0.f, sp = 0.f, spx = 0.f;
-  for (int t = t0 + threadIdx.x; t < t1; t += blockDim.x) {
-    float x = logits[(int64_t)(s + t / NB) * ld + c * NB + t % NB];
-    float p = pb[t];
-    se += expf(x - mx); sp += p; spx += p * x;
+  {
+    int row = row_first, col = col_first;
+    for (int t = first; t < t1; t += blockDim.x) {
+      float x = lbase[(int64_t)row * ld + col];
+      float p = pb[t];
+      se += expf(x - mx); sp += p; spx += p * x;
+      row += drow; col += dcol;
+      if (col >= NB) { col -= NB; ++row; }
+    }
   }
   se = block_sum(se, red); sp = block_sum(sp, red); spx = block_sum(spx, red);
   if (threadIdx.x == 0) { part[0] = mx; part[1] = se; part[2] = sp; part[3] = spx; }
@@ -248,9 +266,13 @@ __global__ void __launch_bounds__(256) k_pos_ce(const float* __restrict__ logits
   if (threadIdx.x == 0 && rank == 0) atomicAdd(loss_accum, mask ? (lse * sp - spx) * wrow : (lse * sp - spx) / (3.f * B));
   if (dlogits) {
     float k = mask ? gscale * wrow : gscale / (3.f * B);
-    for (int t = t0 + threadIdx.x; t < t1; t += blockDim.x) {
-      int64_t o = (int64_t)(s + t / NB) * ld + c * NB + t % NB;
-      dlogits[o] = k * (expf(logits[o] - lse) * sp - pb[t]);
+    int row = row_first, col = col_first;
+    float* dbase = dlogits + (int64_t)s * ld + c * NB;
+    for (int t = first; t < t1; t += blockDim.x) {
+      const int64_t o = (int64_t)row * ld + col;
+      dbase[o] = k * (expf(lbase[o] - lse) * sp - pb[t]);
+      row += drow; col += dcol;
+      if (col >= NB) { col -= NB; ++row; }
     }
   }
 }
