@@ -871,7 +871,13 @@ LOTUS_API int lotus_subm_conv_wgrad_pairs_bf16(const void* dy, const void* x, fl
   int bn = tc::pick_bn(Cin);
   int tiles = ((Cout + 127) / 128) * ((Cin + bn - 1) / bn);
   int max_kb = (n_upper + tc::BK - 1) / tc::BK;
-  int splits = max(1, min(max_kb, (kNumSM * 3) / max(1, tiles * K3) + 1));
+  // CTAs the (tap, tile) reductions are cut over.  Unlike the dense weight gradient this kernel is bound by the request rate of its
+  // gathers, so the sparse 96k-row stage wants MORE CTAs in flight (measured, tools/conv_bench.py: 5 per SM 56 / 114 us, 3 per SM
+  // 79 / 135 us at C = 64 / 128), the deep stages fewer (less reduce-add traffic).  LOTUS_CONV_WGRAD_CTAS overrides.
+  static int ctas_env = -1;
+  if (ctas_env < 0) { const char* e = getenv("LOTUS_CONV_WGRAD_CTAS"); ctas_env = e ? atoi(e) : 0; }
+  const int ctas = ctas_env > 0 ? ctas_env : (n_upper > 65536 ? kNumSM * 5 : (n_upper > 8192 ? kNumSM * 3 : kNumSM * 2));
+  int splits = max(1, min(max_kb, ctas / max(1, tiles * K3) + 1));
   Params p = base_params(Cout, Cin, n_upper, dw, (int64_t)K3 * Cin, 1);
   p.atomic = 1;
   p.k_dev = pair_cnt;
