@@ -100,6 +100,7 @@ GEMM_ARGS = {  # name -> (index of M, N, K in the argument list, bytes per eleme
 CONV_ARGS = {  # name -> index of n (then Cin, Cout, K3 follow)
     "lotus_subm_conv_fwd_f32": 6, "lotus_subm_conv_dgrad_f32": 6, "lotus_subm_conv_wgrad_f32": 5,
     "lotus_subm_conv_fwd_bf16": 6, "lotus_subm_conv_dgrad_bf16": 6, "lotus_subm_conv_wgrad_bf16": 5,
+    "lotus_subm_conv_fwd_splitk_bf16": 6, "lotus_subm_conv_dgrad_splitk_bf16": 6,
     "lotus_subm_conv_wgrad_pairs_bf16": 7,
 }
 # which device kernel a C-ABI family runs on (the roofline is reported per KERNEL: all launches of it in the step)
@@ -107,6 +108,7 @@ KERNEL_OF = {
     "lotus_linear_fwd_bf16": "lin::k_lin", "lotus_linear_dgrad_bf16": "lin::k_lin", "lotus_linear_dgrad_bias_bf16": "lin::k_lin",
     "lotus_linear_dgrad_act_bf16": "lin::k_lin", "lotus_linear_dgrad_act_bias_bf16": "lin::k_lin", "lotus_linear_wgrad_bf16": "tc::k_gemm_tc", "lotus_linear_wgrad_bias_bf16": "tc::k_gemm_tc",
     "lotus_subm_conv_fwd_bf16": "tc::k_gemm_tc", "lotus_subm_conv_dgrad_bf16": "tc::k_gemm_tc",
+    "lotus_subm_conv_fwd_splitk_bf16": "tc::k_gemm_tc", "lotus_subm_conv_dgrad_splitk_bf16": "tc::k_gemm_tc",
     "lotus_subm_conv_wgrad_pairs_bf16": "tc::k_gemm_tc", "lotus_subm_conv_wgrad_bf16": "tc::k_gemm_tc",
     "lotus_patch_attn_fwd_bf16": "tca::k_patch_attn_fwd_tc", "lotus_patch_attn_bwd_bf16": "tca::k_patch_attn_bwd_tc",
     "lotus_patch_attn_fused_fwd_bf16": "paf::k_pattn_fwd", "lotus_patch_attn_fused_bwd_bf16": "paf::k_pattn_bwd",

@@ -772,14 +772,15 @@ LOTUS_API int lotus_subm_conv_dgrad_bf16(const void* dy, const void* wt, const v
 }
 
 // ---- split-K forms for the deep stages ----
-// With n = 976 / 3210 / 12140 rows the grid of the plain form is 48 / 104 / 190 CTAs, each walking 324 / 216 / 108 k-blocks in series at
-// ~0.5 us per k-block: 120-170 us for tensors a few MB in size, and uneven across SMs.  Here the reduction is cut into `splits` ranges
+// With n = 976 rows the grid of the plain form is 48 CTAs, each walking 324 k-blocks in series: 140-160 us for a tensor of 1.5 MB on a
+// third of the SMs (the 3210- and 12140-row stages launch 104 / 190 CTAs and, with the coalesced gather, no longer gain from a split).  Here the reduction is cut into `splits` ranges
 // (grid z), the partial tiles are added into an fp32 scratch [n, N] with TMA reduce-add, and a small pass adds the bias / residual and
 // rounds to bf16.  lotus_subm_conv_splits() says how many ranges a shape gets (1 = use the plain entry point, no scratch needed).
 static int conv_splits(int n, int N, int K) {
   const int bn = tc::pick_bn(N);
   const int tiles = ((n + 127) / 128) * ((N + bn - 1) / bn);
   const int num_kb = (K + 63) / 64;
+  if (tiles * 2 >= kNumSM) return 1;                             // with the coalesced gather only grids under half a wave gain from the split (measured)
   int s = (kNumSM * 3) / max(1, tiles);                          // three CTAs of this kernel fit an SM
   s = min(s, min(8, num_kb / 12));
   return max(1, s);
