@@ -335,7 +335,6 @@ k_gemm_tc(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUt
           // one lane per warp polls the barrier word (fewer spinning threads competing for issue slots)
           if (lane == 0) mbar_wait_hot(&empty[PAIR ? (s >> 1) : s], ph ^ 1);
           __syncwarp();
-          int kb = kb0 + i;
           if (ldg_path) {
             // Coalesced gather: EIGHT LANES read one whole 128-byte source row (lane = 16-byte chunk), four rows per warp
             // instruction, through registers.  With one row per lane (the cp.async form below) every warp instruction touches 32
