@@ -57,3 +57,16 @@ def test_product_never_imports_oracle():
             src = open(os.path.join(pdir, fn)).read()
             assert "oracle" not in src.replace("oracle/", "").replace("the oracle", "").replace("CPU oracle", "") or fn == "testing.py", fn
             assert "import oracle" not in src and "from oracle" not in src, fn
+
+
+def test_conv_split_rule_is_host_logic():
+    """lotus_subm_conv_splits is pure host arithmetic (no launch): only grids under half a wave of 128-row tiles get a split reduction
+    (the 976-row stage of the production step), never the wide stages"""
+    lib = pkg("lib")
+    cdll = ctypes.CDLL(lib.LIB_PATH)
+    f = cdll.lotus_subm_conv_splits
+    f.restype = ctypes.c_int
+    assert f(976, 768, 27 * 768) > 1 and f(976, 768, 27 * 768) <= 8
+    assert f(3210, 512, 27 * 512) == 1 and f(12140, 256, 27 * 256) == 1
+    assert f(45262, 128, 27 * 128) == 1 and f(96652, 64, 27 * 64) == 1
+    assert f(500, 64, 64) == 1                                     # a short reduction is never split
