@@ -63,3 +63,16 @@ def test_algorithmic_work_formulas():
     fl, by = b.algorithmic_work("lotus_layernorm_bwd_bf16", (1, 0, 1, 64, 0, 1, 1, 64, 0, 1, 1, 64, 0, 1, 1, 1, 1, 1, 1000, 64, 1, 0), ctx)
     assert fl == 0 and by == 1000 * 64 * (2 + 2 + 4) + 8.0 * 1000
     assert b.algorithmic_work("lotus_adamw_step_f32", (1, 1, 1, 1, 1000) + (0,) * 13, ctx) == (0.0, 28000.0)
+
+
+def test_traffic_db_covers_every_roofline_kernel():
+    """`roofline.traffic` / `attention_block.traffic` come from profiles/ncu_traffic.json: every device kernel bench.py can name as dominant
+    (KERNEL_OF values that the round-2 step actually launches) and the attention pair must have a measured DRAM-bytes entry with its source"""
+    import json
+    b = _bench()
+    db = json.load(open(os.path.join(ROOT, "profiles", "ncu_traffic.json")))
+    need = {"lin::k_lin", "tc::k_gemm_tc", "paf::k_pattn_fwd", "paf::k_pattn_bwd", "patch_attention(fwd+bwd)"}
+    assert need <= set(db), sorted(need - set(db))
+    assert need - {"patch_attention(fwd+bwd)"} <= set(b.KERNEL_OF.values())
+    for k in need:
+        assert db[k]["dram_bytes_per_launch"] > 0 and db[k]["launches"] > 0 and "ncu" in db[k]["source"]
